@@ -1,0 +1,111 @@
+/* xkv_b200 — C ABI of the B200-native xKV hot path (cross-layer SVD KV-cache compression).
+ *
+ * The reference (LiuTaowen-Tony/xKV) has no native code and no FFI: its hot path is the
+ * Python function chain
+ *     FakeLayerMergingCache.update            xKV/customized_cache/fake_layer_merge_dynamic_cache.py:127-153
+ *       -> grouped_layer_merging              ...:155-208   (torch.cat over the group's layers)
+ *       -> fake_svd                           ...:11-29     (transpose/reshape, torch.linalg.svd, matmul back)
+ *       -> apply_rotary_pos_emb               ...:142-152   (RoPE on the reconstructed keys)
+ *     decode attention over the dense result  xKV/attn_patch/llama.py:51-69 (SDPA)
+ * Every entry point below replaces one of those library-call sites with a hand-written
+ * sm_100a kernel (or a stream-ordered sequence of them).  The Python host mirror
+ * (xkv_b200/customized_cache, xkv_b200/attn_patch) binds them with ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - bf16 buffers are `void*` holding __nv_bfloat16, fp32 buffers are `float*`;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it,
+ *     nothing allocates, nothing synchronises (workspace comes from the caller);
+ *   - functions return 0 on success, non-zero on error; xkv_last_error() gives the message
+ *     of the calling thread's last failure.
+ */
+#ifndef XKV_B200_H_
+#define XKV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define XKV_API __attribute__((visibility("default")))
+#else
+#define XKV_API
+#endif
+
+#define XKV_MAX_GROUP_LAYERS 16
+#define XKV_MAX_GEMM_PROBLEMS 16
+#define XKV_MAX_BATCH 16
+
+/* ---- library ------------------------------------------------------------------------ */
+XKV_API const char* xkv_last_error(void);
+XKV_API int xkv_version(void);
+/* number of kernels this library has launched since load (bench.py's `gpu_launches`) */
+XKV_API int64_t xkv_launch_count(void);
+
+/* ---- (1) prefill gather: replaces torch.cat(dim=1) + transpose(1,2).reshape ----------
+ * cache:170-171 and cache:13-14.  Gathers the G layers' (bs, H, S, D) bf16 tensors (arbitrary
+ * batch/head/token strides, unit stride over D) into the token-major matrix
+ * X[bs*S][G*H*D] whose column order is (layer, head, dim), exactly the reference's. */
+XKV_API int xkv_pack_group(const void* const* layer_ptrs_host, int num_layers, int bs, int heads, int seq,
+                   int head_dim, int64_t stride_b, int64_t stride_h, int64_t stride_s, void* X,
+                   void* stream);
+/* inverse scatter (used by tests / the dense-materialise debug path): X -> per-layer tensors */
+XKV_API int xkv_unpack_group(const void* X, int num_layers, int bs, int heads, int seq, int head_dim,
+                     int64_t stride_b, int64_t stride_h, int64_t stride_s, void* const* layer_ptrs_host,
+                     void* stream);
+
+/* ---- (2) tcgen05 GEMM engine: replaces torch.linalg.svd / torch.matmul call sites -------
+ * cache:20,26.  D (+split slabs) = sum_t A[term_a[t]] * B[term_b[t]]^T, bf16 operands, fp32
+ * accumulation in TMEM.  Operands are given as up to three bf16 "limbs" (hi, mid, lo) of an
+ * fp32 matrix so that products of fp32 matrices reach ~fp32 accuracy on the bf16 tensor path. */
+typedef struct xkv_gemm_problem {
+  int32_t M, N, K;
+  int32_t num_terms;     /* 1..6 */
+  int32_t a_mn_major;    /* 0: A stored [M][lda] (K contiguous); 1: A stored [K][lda] (M contiguous) */
+  int32_t b_mn_major;    /* 0: B stored [N][ldb] (K contiguous); 1: B stored [K][ldb] (N contiguous) */
+  const void* A[3];      /* bf16 limbs */
+  const void* B[3];
+  int64_t lda, ldb;      /* leading dimensions in elements (multiples of 8) */
+  uint8_t term_a[6], term_b[6];
+  void* D;               /* fp32 or bf16 output */
+  int64_t ldd;
+  int32_t out_bf16;        /* 0: fp32 output, 1: bf16 output */
+  int32_t out_transposed;  /* 0: D[M][ldd], 1: D[N][ldd] */
+  int32_t sym_upper;       /* 1: compute only tiles that intersect the upper triangle (Gram) */
+  int32_t split_k;         /* >= 1: split s accumulates k-blocks of its slice into D + s*split_stride */
+  int64_t split_stride;    /* elements */
+} xkv_gemm_problem;
+XKV_API int xkv_gemm_grouped(const xkv_gemm_problem* problems_host, int num_problems, void* stream);
+
+/* ---- small fp32 helpers of the factorisation ------------------------------------------ */
+/* out[i][j] = sum_s slabs[s][i][j]; with symmetrize=1 the strictly-lower triangle is mirrored
+ * from the upper one (Gram). rows x cols, ld in elements. */
+XKV_API int xkv_reduce_slabs(const float* slabs, int num_slabs, int64_t slab_stride, int rows, int cols, int64_t ld,
+                     int symmetrize, float* out, int64_t ld_out, void* stream);
+/* split an fp32 matrix into bf16 limbs: hi = bf16(x), mid = bf16(x-hi), lo = bf16(x-hi-mid).
+ * mid / lo may be NULL. */
+XKV_API int xkv_split_bf16(const float* x, int rows, int cols, int64_t ld, void* hi, void* mid, void* lo,
+                   int64_t ld_out, void* stream);
+/* deterministic N(0,1) test matrix rounded to bf16 (counter-based generator) */
+XKV_API int xkv_fill_gaussian_bf16(void* out, int rows, int cols, int64_t ld, uint64_t seed, void* stream);
+/* rows of Yt (each a column of Y) are scaled to unit 2-norm in place (zero rows are left zero) */
+XKV_API int xkv_normalize_rows(float* Yt, int rows, int cols, int64_t ld, void* stream);
+/* batched (blockIdx.y) lower Cholesky S = L L^T of `batch` l x l matrices, and Linv = L^{-1}.
+ * Pivots below pivot_floor * max_diag are clamped (never fails). S is overwritten by L. */
+XKV_API int xkv_cholesky_inverse(float* const* S_host, float* const* Linv_host, int batch, int l, int64_t ld,
+                         float pivot_floor, void* workspace, size_t workspace_bytes, void* stream);
+/* batched symmetric eigen-decomposition of l x l matrices by block two-sided Jacobi.
+ * On return T holds the (nearly) diagonal matrix, V its eigenvectors as columns,
+ * evals/order the eigenvalues sorted descending and the permutation. */
+XKV_API int xkv_jacobi_eigh(float* const* T_host, float* const* V_host, float* const* evals_host,
+                    int32_t* const* order_host, int batch, int l, int64_t ld, int sweeps,
+                    void* workspace, size_t workspace_bytes, void* stream);
+XKV_API size_t xkv_small_workspace_bytes(int batch, int l);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XKV_B200_H_ */

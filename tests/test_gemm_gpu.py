@@ -1,0 +1,130 @@
+"""GPU parity of the tcgen05 GEMM engine against torch fp32 matmul of the same bf16 operands.
+
+bf16 x bf16 products are exact in fp32, so with small-integer data the result is exact; with
+Gaussian data the only difference from torch is fp32 summation order (tolerance 1e-4 relative to
+the row/column norm product)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(rows, cols, ints, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    if ints:
+        return torch.randint(-3, 4, (rows, cols), device="cuda", generator=g).to(torch.bfloat16)
+    return torch.randn(rows, cols, device="cuda", generator=g).bfloat16()
+
+
+def _run(M, N, K, a_mn, b_mn, ints=False, terms=None, transposed=False, out_bf16=False, split_k=1, sym=False):
+    from xkv_b200 import ops
+
+    terms = terms or ops.TERMS_1
+    nl = max(max(t) for t in terms) + 1
+    A = [_mk(K, M, ints, 10 + i) if a_mn else _mk(M, K, ints, 10 + i) for i in range(nl)]
+    if sym:
+        B = A
+    else:
+        B = [_mk(K, N, ints, 20 + i) if b_mn else _mk(N, K, ints, 20 + i) for i in range(nl)]
+    ref = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+    for ta, tb in terms:
+        a = A[ta].float().t() if a_mn else A[ta].float()
+        b = B[tb].float().t() if b_mn else B[tb].float()
+        ref += a @ b.t()
+    shape = (N, M) if transposed else (M, N)
+    dt = torch.bfloat16 if out_bf16 else torch.float32
+    out = torch.full((split_k,) + shape, float("nan"), device="cuda", dtype=dt)
+    p = ops.make_problem(A, B, out[0], M=M, N=N, K=K, a_mn_major=a_mn, b_mn_major=b_mn, terms=terms,
+                         out_transposed=transposed, sym_upper=sym, split_k=split_k,
+                         split_stride=out.stride(0))
+    ops.gemm_grouped([p])
+    torch.cuda.synchronize()
+    got = out.float().sum(0)
+    if transposed:
+        got = got.t()
+    return got, ref
+
+
+def _check(got, ref, exact, sym=False, out_bf16=False):
+    if sym:
+        # only tiles touching the upper triangle are defined
+        mask = torch.triu(torch.ones_like(ref, dtype=torch.bool))
+        assert not torch.isnan(got[mask]).any()
+        got = torch.where(mask, got, ref)
+    assert not torch.isnan(got).any(), "unwritten output elements"
+    if exact and not out_bf16:
+        assert torch.equal(got, ref), f"max abs diff {(got - ref).abs().max().item()}"
+    else:
+        tol = 1e-2 if out_bf16 else 1e-4
+        scale = ref.abs().max().item() + 1e-6
+        assert (got - ref).abs().max().item() <= tol * scale
+
+
+MAJORS = [(False, False), (False, True), (True, False), (True, True)]
+
+
+@pytest.mark.parametrize("a_mn,b_mn", MAJORS)
+def test_single_tile_exact(a_mn, b_mn):
+    got, ref = _run(128, 256, 64, a_mn, b_mn, ints=True)
+    _check(got, ref, exact=True)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", MAJORS)
+def test_multi_kblock_exact(a_mn, b_mn):
+    got, ref = _run(256, 512, 512, a_mn, b_mn, ints=True)
+    _check(got, ref, exact=True)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", MAJORS)
+def test_ragged_shapes(a_mn, b_mn):
+    # M, N not multiples of the tile, K not a multiple of 64 (TMA zero-fills the tails)
+    got, ref = _run(200, 328, 168, a_mn, b_mn, ints=True)
+    _check(got, ref, exact=True)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", MAJORS)
+def test_gaussian(a_mn, b_mn):
+    got, ref = _run(384, 768, 1024, a_mn, b_mn)
+    _check(got, ref, exact=False)
+
+
+def test_terms_and_split_k():
+    from xkv_b200 import ops
+
+    got, ref = _run(256, 256, 1024, False, False, ints=True, terms=ops.TERMS_6, split_k=4)
+    _check(got, ref, exact=True)
+    got, ref = _run(130, 250, 640, False, True, ints=True, terms=ops.TERMS_3, split_k=3)
+    _check(got, ref, exact=True)
+
+
+def test_transposed_and_bf16_outputs():
+    got, ref = _run(256, 320, 256, False, False, ints=True, transposed=True)
+    _check(got, ref, exact=True)
+    got, ref = _run(256, 512, 256, False, False, out_bf16=True)
+    _check(got, ref, exact=False, out_bf16=True)
+    got, ref = _run(200, 300, 128, False, True, out_bf16=True, transposed=True)
+    _check(got, ref, exact=False, out_bf16=True)
+
+
+def test_symmetric_gram_tiles():
+    # G = X^T X with X (K x n) row-major: both operands MN-major views of the same matrix
+    got, ref = _run(768, 768, 1024, True, True, ints=True, sym=True, split_k=2)
+    _check(got, ref, exact=True, sym=True)
+
+
+def test_grouped_launch():
+    from xkv_b200 import ops
+
+    torch.manual_seed(1)
+    probs, refs, outs = [], [], []
+    for (M, N, K) in [(128, 256, 128), (300, 100, 256), (640, 640, 512)]:
+        A = torch.randint(-3, 4, (M, K), device="cuda").to(torch.bfloat16)
+        B = torch.randint(-3, 4, (N, K), device="cuda").to(torch.bfloat16)
+        out = torch.full((M, N), float("nan"), device="cuda")
+        probs.append(ops.make_problem([A], [B], out, M=M, N=N, K=K))
+        refs.append(A.float() @ B.float().t())
+        outs.append(out)
+    ops.gemm_grouped(probs)
+    torch.cuda.synchronize()
+    for o, r in zip(outs, refs):
+        assert torch.equal(o, r)

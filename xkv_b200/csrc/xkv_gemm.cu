@@ -1,0 +1,361 @@
+// xkv_b200 — grouped tcgen05 GEMM engine (sm_100a).
+//
+// One kernel serves every matrix product of the factorisation (reference call sites:
+// torch.linalg.svd / torch.matmul, fake_layer_merge_dynamic_cache.py:20,26):
+//   Gram          G  = X^T X          both operands MN-major tiles of X, symmetric tile set, split-K
+//   power step    Yt = Qt G           K-major x K-major (G symmetric), multi-limb terms
+//   small Grams   S  = Yt Yt^T        K-major x K-major
+//   tri-solve     Qt = Linv Yt        K-major x MN-major
+//   Ritz vectors  Vt = Wt Qt          K-major x MN-major
+//   projection    A  = X V            K-major x K-major, bf16 output
+//
+// Structure (one 128 x 256 output tile per CTA, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes, 128B swizzle, 4-stage mbarrier ring
+//   warp 1      allocates 256 TMEM columns, one lane issues tcgen05.mma (M128 N256 K16, bf16 -> fp32),
+//               tcgen05.commit releases smem stages / publishes the accumulator
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns) -> registers -> global (fp32 / bf16,
+//               optionally transposed)
+// Problems are passed by value in __grid_constant__ parameter space (tensor maps included), so a
+// launch needs no device-side descriptor memory.
+#include "xkv_common.cuh"
+#include "xkv_host.h"
+
+namespace xkv {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int B_TILE_BYTES = BN * BK * 2;  // 32 KiB
+constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+constexpr int CHUNK_BYTES = 64 * BK * 2;   // one 64-wide MN-major chunk: BK rows x 128 B
+constexpr int GEMM_THREADS = 192;
+constexpr int TMEM_COLS = 256;
+constexpr size_t GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct alignas(64) GemmProb {
+  CUtensorMap a_map[3];
+  CUtensorMap b_map[3];
+  void* D;
+  long long ldd;
+  long long split_stride;
+  int M, N, K;
+  int nterms;
+  int tiles_m, tiles_n, ntiles;
+  int split_k, kblocks_per_split, nkb;
+  int cta_begin;
+  int out_bf16, out_transposed, sym_upper;
+  unsigned char ta[6], tb[6];
+};
+struct GemmParams {
+  int nprob;
+  GemmProb p[XKV_MAX_GEMM_PROBLEMS];
+};
+
+template <int A_MN, int B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- locate this CTA's problem / split / tile ----
+  int pi = 0;
+  while (pi + 1 < P.nprob && static_cast<int>(blockIdx.x) >= P.p[pi + 1].cta_begin) ++pi;
+  const GemmProb& pr = P.p[pi];
+  const int local = static_cast<int>(blockIdx.x) - pr.cta_begin;
+  const int split = local / pr.ntiles;
+  int t = local - split * pr.ntiles;
+  int tm, tn;
+  if (pr.sym_upper) {
+    tm = 0;
+    tn = 0;
+    for (int i = 0; i < pr.tiles_m; ++i) {
+      const int first = (i * BM) / BN;
+      const int cnt = pr.tiles_n - first;
+      if (t < cnt) {
+        tm = i;
+        tn = first + t;
+        break;
+      }
+      t -= cnt;
+    }
+  } else {
+    tm = t / pr.tiles_n;
+    tn = t - tm * pr.tiles_n;
+  }
+  const int m0 = tm * BM;
+  const int n0 = tn * BN;
+  const int kb0 = split * pr.kblocks_per_split;
+  const int kb1 = min(kb0 + pr.kblocks_per_split, pr.nkb);
+  const int nk = max(kb1 - kb0, 0);
+  const int niter = nk * pr.nterms;
+
+  // ---- one-time setup ----
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+    for (int i = 0; i < 3; ++i) {
+      tma_prefetch_desc(&pr.a_map[i]);
+      tma_prefetch_desc(&pr.b_map[i]);
+    }
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < niter; ++it) {
+        const int kb = kb0 + it / pr.nterms;
+        const int term = it - (it / pr.nterms) * pr.nterms;
+        const CUtensorMap* amap = &pr.a_map[pr.ta[term]];
+        const CUtensorMap* bmap = &pr.b_map[pr.tb[term]];
+        uint8_t* sA = smem + s * STAGE_BYTES;
+        uint8_t* sB = sA + A_TILE_BYTES;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        if (A_MN == 0) {
+          tma_load_2d(sA, amap, &full_bar[s], kb * BK, m0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BM / 64; ++c) tma_load_2d(sA + c * CHUNK_BYTES, amap, &full_bar[s], m0 + 64 * c, kb * BK);
+        }
+        if (B_MN == 0) {
+          tma_load_2d(sB, bmap, &full_bar[s], kb * BK, n0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c) tma_load_2d(sB + c * CHUNK_BYTES, bmap, &full_bar[s], n0 + 64 * c, kb * BK);
+        }
+        if (++s == STAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < niter; ++it) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_base = a_base + A_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t da = A_MN ? umma_desc_sw128(a_base + k * 2048, CHUNK_BYTES, 1024)
+                                   : umma_desc_sw128(a_base + k * 32, 16, 1024);
+          const uint64_t db = B_MN ? umma_desc_sw128(b_base + k * 2048, CHUNK_BYTES, 1024)
+                                   : umma_desc_sw128(b_base + k * 32, 16, 1024);
+          umma_bf16_ss(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+        if (++s == STAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const bool row_ok = row < pr.M;
+    float* outf = reinterpret_cast<float*>(pr.D) + static_cast<long long>(split) * pr.split_stride;
+    __nv_bfloat16* outh = reinterpret_cast<__nv_bfloat16*>(pr.D) + static_cast<long long>(split) * pr.split_stride;
+    const bool vec_ok = (pr.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(pr.D) & 15) == 0) &&
+                        ((pr.split_stride % 8) == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int col0 = n0 + c * 32;
+      if (col0 >= pr.N) break;  // warp-uniform
+      uint32_t v[32];
+      __syncwarp();
+      if (niter > 0) {
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      const bool full = (col0 + 32 <= pr.N);
+      if (!pr.out_transposed) {
+        if (!row_ok) {
+          // rows past M (zero-filled by TMA): nothing to store
+        } else if (!pr.out_bf16) {
+          float* dst = outf + static_cast<long long>(row) * pr.ldd + col0;
+          if (full && vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<uint4*>(dst)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < pr.N) dst[j] = __uint_as_float(v[j]);
+          }
+        } else {
+          __nv_bfloat16* dst = outh + static_cast<long long>(row) * pr.ldd + col0;
+          if (full && vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 w;
+              w.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+              w.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+              w.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+              w.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+              reinterpret_cast<uint4*>(dst)[j] = w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < pr.N) dst[j] = __float2bfloat16_rn(__uint_as_float(v[j]));
+          }
+        }
+      } else {
+        // transposed store: for a fixed column the warp's 32 rows are contiguous in memory
+        if (!pr.out_bf16) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (row_ok && col0 + j < pr.N)
+              outf[static_cast<long long>(col0 + j) * pr.ldd + row] = __uint_as_float(v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (row_ok && col0 + j < pr.N)
+              outh[static_cast<long long>(col0 + j) * pr.ldd + row] = __float2bfloat16_rn(__uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int build_problem(const xkv_gemm_problem& in, GemmProb& out, int& cta_cursor) {
+  XKV_REQUIRE(in.M > 0 && in.N > 0 && in.K > 0, "gemm: empty problem M=%d N=%d K=%d", in.M, in.N, in.K);
+  XKV_REQUIRE(in.num_terms >= 1 && in.num_terms <= 6, "gemm: num_terms=%d out of range", in.num_terms);
+  XKV_REQUIRE(in.lda % 8 == 0 && in.ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements");
+  XKV_REQUIRE(in.split_k >= 1, "gemm: split_k must be >= 1");
+  XKV_REQUIRE(in.D != nullptr, "gemm: null output");
+  std::memset(&out, 0, sizeof(out));
+  bool used_a[3] = {false, false, false}, used_b[3] = {false, false, false};
+  for (int t = 0; t < in.num_terms; ++t) {
+    XKV_REQUIRE(in.term_a[t] < 3 && in.term_b[t] < 3, "gemm: limb index out of range");
+    used_a[in.term_a[t]] = true;
+    used_b[in.term_b[t]] = true;
+    out.ta[t] = in.term_a[t];
+    out.tb[t] = in.term_b[t];
+  }
+  for (int i = 0; i < 3; ++i) {
+    // unused limbs alias limb 0 so every tensor map in parameter space is valid to prefetch
+    const void* a = used_a[i] ? in.A[i] : in.A[in.term_a[0]];
+    const void* b = used_b[i] ? in.B[i] : in.B[in.term_b[0]];
+    XKV_REQUIRE(a != nullptr && b != nullptr, "gemm: null operand limb %d", i);
+    XKV_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0,
+                "gemm: operands must be 16-byte aligned");
+    int rc;
+    if (!in.a_mn_major)
+      rc = encode_tmap_2d_bf16(&out.a_map[i], a, in.K, in.M, in.lda, BK, BM);
+    else
+      rc = encode_tmap_2d_bf16(&out.a_map[i], a, in.M, in.K, in.lda, 64, BK);
+    if (rc) return rc;
+    if (!in.b_mn_major)
+      rc = encode_tmap_2d_bf16(&out.b_map[i], b, in.K, in.N, in.ldb, BK, BN);
+    else
+      rc = encode_tmap_2d_bf16(&out.b_map[i], b, in.N, in.K, in.ldb, 64, BK);
+    if (rc) return rc;
+  }
+  out.D = in.D;
+  out.ldd = in.ldd;
+  out.split_stride = in.split_stride;
+  out.M = in.M;
+  out.N = in.N;
+  out.K = in.K;
+  out.nterms = in.num_terms;
+  out.tiles_m = (in.M + BM - 1) / BM;
+  out.tiles_n = (in.N + BN - 1) / BN;
+  out.sym_upper = in.sym_upper ? 1 : 0;
+  if (out.sym_upper) {
+    int cnt = 0;
+    for (int i = 0; i < out.tiles_m; ++i) cnt += out.tiles_n - (i * BM) / BN;
+    out.ntiles = cnt;
+  } else {
+    out.ntiles = out.tiles_m * out.tiles_n;
+  }
+  out.nkb = (in.K + BK - 1) / BK;
+  out.split_k = in.split_k;
+  out.kblocks_per_split = (out.nkb + in.split_k - 1) / in.split_k;
+  out.out_bf16 = in.out_bf16 ? 1 : 0;
+  out.out_transposed = in.out_transposed ? 1 : 0;
+  out.cta_begin = cta_cursor;
+  cta_cursor += out.ntiles * out.split_k;
+  return 0;
+}
+
+template <int A_MN, int B_MN>
+static int launch_variant(const GemmParams& params, int grid, cudaStream_t stream) {
+  auto kern = gemm_kernel<A_MN, B_MN>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    XKV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(GEMM_SMEM_BYTES)));
+    configured = true;
+  }
+  kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(params);
+  XKV_LAUNCHED();
+  return 0;
+}
+
+}  // namespace xkv
+
+extern "C" int xkv_gemm_grouped(const xkv_gemm_problem* problems, int num_problems, void* stream) {
+  using namespace xkv;
+  XKV_REQUIRE(problems != nullptr && num_problems >= 1, "gemm: no problems");
+  XKV_REQUIRE(num_problems <= XKV_MAX_GEMM_PROBLEMS, "gemm: at most %d problems per launch", XKV_MAX_GEMM_PROBLEMS);
+  const int a_mn = problems[0].a_mn_major ? 1 : 0;
+  const int b_mn = problems[0].b_mn_major ? 1 : 0;
+  static thread_local GemmParams params;  // ~14 KiB, keep it off the stack
+  params.nprob = num_problems;
+  int cursor = 0;
+  for (int i = 0; i < num_problems; ++i) {
+    XKV_REQUIRE((problems[i].a_mn_major ? 1 : 0) == a_mn && (problems[i].b_mn_major ? 1 : 0) == b_mn,
+                "gemm: all problems of one launch must share operand majors");
+    int rc = build_problem(problems[i], params.p[i], cursor);
+    if (rc) return rc;
+  }
+  cudaStream_t st = as_stream(stream);
+  if (!a_mn && !b_mn) return launch_variant<0, 0>(params, cursor, st);
+  if (!a_mn && b_mn) return launch_variant<0, 1>(params, cursor, st);
+  if (a_mn && !b_mn) return launch_variant<1, 0>(params, cursor, st);
+  return launch_variant<1, 1>(params, cursor, st);
+}

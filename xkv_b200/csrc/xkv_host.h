@@ -1,0 +1,47 @@
+// xkv_b200 — host-side plumbing shared by the C-ABI translation units.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/xkv_b200.h"
+
+namespace xkv {
+
+// thread-local error text returned by xkv_last_error()
+char* error_buffer();
+int set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launch_count;
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define XKV_CHECK_CUDA(expr)                                                                        \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return ::xkv::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define XKV_REQUIRE(cond, ...)                    \
+  do {                                            \
+    if (!(cond)) return ::xkv::set_error(__VA_ARGS__); \
+  } while (0)
+
+// after a kernel launch: count it and surface launch-configuration errors immediately
+#define XKV_LAUNCHED()                 \
+  do {                                 \
+    ::xkv::g_launch_count.fetch_add(1); \
+    XKV_CHECK_CUDA(cudaGetLastError()); \
+  } while (0)
+
+// Encode a 2-D bf16 tensor map (row-major [outer][ld], `inner` valid elements per row) with
+// 128-byte swizzle. Returns 0 on success.
+int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                        uint32_t box_inner, uint32_t box_outer);
+
+}  // namespace xkv

@@ -1,0 +1,127 @@
+"""Tensor-level wrappers over the C-ABI (``include/xkv_b200.h``).
+
+PyTorch is used only for device memory and streams: every function takes CUDA tensors, passes raw
+``data_ptr()``s and the current stream to the library, and returns without synchronising.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import GemmProblem, check
+
+# term lists (indices into the limb arrays: 0 = hi, 1 = mid, 2 = lo)
+TERMS_1 = ((0, 0),)
+TERMS_3 = ((0, 0), (0, 1), (1, 0))
+TERMS_6 = ((0, 0), (0, 1), (1, 0), (1, 1), (0, 2), (2, 0))
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.XkvError("xkv_b200 ops need CUDA tensors: there is no CPU path")
+
+
+def launch_count() -> int:
+    return int(_lib.load().xkv_launch_count())
+
+
+# ---------------------------------------------------------------------------------------------
+# (1) gather
+# ---------------------------------------------------------------------------------------------
+def pack_group(layers: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Gather G tensors (bs, H, S, D) bf16 into X (bs, S, G*H*D) bf16, columns ordered (layer, head, dim).
+
+    Same result as ``torch.cat(layers, dim=1).transpose(1, 2).reshape(bs, S, G*H*D)``
+    (reference: fake_layer_merge_dynamic_cache.py:170-171 and :13-14)."""
+    lib = _lib.load()
+    _require_cuda(*layers)
+    g = len(layers)
+    bs, h, s, d = layers[0].shape
+    sb, sh, ss, sd = layers[0].stride()
+    for t in layers:
+        if t.dtype != torch.bfloat16:
+            raise _lib.XkvError("pack_group: bf16 tensors required")
+        if tuple(t.shape) != (bs, h, s, d) or t.stride() != (sb, sh, ss, sd):
+            raise _lib.XkvError("pack_group: all layers of a group must share shape and strides")
+    if s > 0 and sd != 1:
+        raise _lib.XkvError("pack_group: head_dim must be contiguous")
+    if out is None:
+        out = torch.empty((bs, s, g * h * d), dtype=torch.bfloat16, device=layers[0].device)
+    ptrs = (C.c_void_p * g)(*[t.data_ptr() for t in layers])
+    check(lib.xkv_pack_group(ptrs, g, bs, h, s, d, sb, sh, ss, C.c_void_p(out.data_ptr()), _stream()))
+    return out
+
+
+def unpack_group(x: torch.Tensor, layers: Sequence[torch.Tensor]) -> None:
+    """Inverse of :func:`pack_group`: scatter X (bs, S, G*H*D) back into the per-layer tensors."""
+    lib = _lib.load()
+    _require_cuda(x, *layers)
+    g = len(layers)
+    bs, h, s, d = layers[0].shape
+    sb, sh, ss, sd = layers[0].stride()
+    ptrs = (C.c_void_p * g)(*[t.data_ptr() for t in layers])
+    check(lib.xkv_unpack_group(C.c_void_p(x.data_ptr()), g, bs, h, s, d, sb, sh, ss, ptrs, _stream()))
+
+
+# ---------------------------------------------------------------------------------------------
+# (2) GEMM engine
+# ---------------------------------------------------------------------------------------------
+def make_problem(
+    a_limbs: Sequence[torch.Tensor],
+    b_limbs: Sequence[torch.Tensor],
+    out: torch.Tensor,
+    *,
+    M: int,
+    N: int,
+    K: int,
+    a_mn_major: bool = False,
+    b_mn_major: bool = False,
+    terms: Sequence[Tuple[int, int]] = TERMS_1,
+    out_transposed: bool = False,
+    sym_upper: bool = False,
+    split_k: int = 1,
+    split_stride: int = 0,
+) -> GemmProblem:
+    """Describe D = sum_t A[ta] @ B[tb]^T.  A limbs: (M, K) row-major, or (K, M) if a_mn_major;
+    B limbs: (N, K) row-major, or (K, N) if b_mn_major. `out`: fp32/bf16, (M, N) or (N, M) if transposed;
+    with split_k > 1 `out` is the first of split_k slabs `split_stride` elements apart."""
+    p = GemmProblem()
+    p.M, p.N, p.K = M, N, K
+    p.num_terms = len(terms)
+    p.a_mn_major, p.b_mn_major = int(a_mn_major), int(b_mn_major)
+    for i in range(3):
+        a = a_limbs[i] if i < len(a_limbs) else None
+        b = b_limbs[i] if i < len(b_limbs) else None
+        p.A[i] = a.data_ptr() if a is not None else None
+        p.B[i] = b.data_ptr() if b is not None else None
+    for t in list(a_limbs) + list(b_limbs):
+        if t is not None and (t.dtype != torch.bfloat16 or t.stride(-1) != 1):
+            raise _lib.XkvError("gemm operands must be bf16 with unit inner stride")
+    p.lda = a_limbs[0].stride(0)
+    p.ldb = b_limbs[0].stride(0)
+    for t, (ta, tb) in enumerate(terms):
+        p.term_a[t], p.term_b[t] = ta, tb
+    if out.dtype not in (torch.float32, torch.bfloat16) or out.stride(-1) != 1:
+        raise _lib.XkvError("gemm output must be fp32 or bf16 with unit inner stride")
+    p.D = out.data_ptr()
+    p.ldd = out.stride(-2)
+    p.out_bf16 = int(out.dtype == torch.bfloat16)
+    p.out_transposed = int(out_transposed)
+    p.sym_upper = int(sym_upper)
+    p.split_k = split_k
+    p.split_stride = split_stride
+    return p
+
+
+def gemm_grouped(problems: Sequence[GemmProblem]) -> None:
+    lib = _lib.load()
+    arr = (GemmProblem * len(problems))(*problems)
+    check(lib.xkv_gemm_grouped(arr, len(problems), _stream()))
