@@ -91,19 +91,26 @@ XKV_API int xkv_split_bf16(const float* x, int rows, int cols, int64_t ld, void*
                    int64_t ld_out, void* stream);
 /* deterministic N(0,1) test matrix rounded to bf16 (counter-based generator) */
 XKV_API int xkv_fill_gaussian_bf16(void* out, int rows, int cols, int64_t ld, uint64_t seed, void* stream);
-/* rows of Yt (each a column of Y) are scaled to unit 2-norm in place (zero rows are left zero) */
-XKV_API int xkv_normalize_rows(float* Yt, int rows, int cols, int64_t ld, void* stream);
-/* batched (blockIdx.y) lower Cholesky S = L L^T of `batch` l x l matrices, and Linv = L^{-1}.
- * Pivots below pivot_floor * max_diag are clamped (never fails). S is overwritten by L. */
+/* Batched row normalisation: every row of Y[b] (rows x cols fp32, each row is a column of the sketch)
+ * is scaled to unit 2-norm in place; if hi_host is non-NULL the bf16 limbs of the scaled rows are
+ * written too (mid_host / lo_host may be NULL). */
+XKV_API int xkv_normalize_rows(float* const* Y_host, void* const* hi_host, void* const* mid_host,
+                               void* const* lo_host, int batch, int rows, int cols, int64_t ld, int64_t ld_out,
+                               void* stream);
+/* Batched blocked Cholesky S = L L^T of l x l fp32 matrices (l % 64 == 0, unit diagonal expected) with
+ * explicit inverse Linv = L^{-1} (dense l x l, zero above the diagonal). S is overwritten: its strictly
+ * lower 64-blocks hold L, its diagonal blocks are left untouched. Pivots below pivot_floor are clamped,
+ * so the factorisation never fails (CholeskyQR is repeated instead). */
 XKV_API int xkv_cholesky_inverse(float* const* S_host, float* const* Linv_host, int batch, int l, int64_t ld,
-                         float pivot_floor, void* workspace, size_t workspace_bytes, void* stream);
-/* batched symmetric eigen-decomposition of l x l matrices by block two-sided Jacobi.
- * On return T holds the (nearly) diagonal matrix, V its eigenvectors as columns,
- * evals/order the eigenvalues sorted descending and the permutation. */
-XKV_API int xkv_jacobi_eigh(float* const* T_host, float* const* V_host, float* const* evals_host,
-                    int32_t* const* order_host, int batch, int l, int64_t ld, int sweeps,
-                    void* workspace, size_t workspace_bytes, void* stream);
-XKV_API size_t xkv_small_workspace_bytes(int batch, int l);
+                                 float pivot_floor, void* stream);
+/* Shared-memory two-sided Jacobi eigen-solver for the Rayleigh-Ritz windows: `count` symmetric W x W
+ * fp32 matrices (W even, <= 160), one CTA each. evals: eigenvalues sorted descending; Wt (optional):
+ * eigenvectors as rows, same order. */
+XKV_API int xkv_jacobi_eigh(const float* const* T_host, float* const* evals_host, float* const* Wt_host, int count,
+                            int W, int64_t ld, int64_t ld_w, int sweeps, void* stream);
+/* fp32 (rows x cols) -> bf16 copy `dst` and/or transposed bf16 copy `dstT` (cols x rows) */
+XKV_API int xkv_convert_bf16(const float* src, int rows, int cols, int64_t ld, void* dst, int64_t ld_dst, void* dstT,
+                             int64_t ld_dstT, void* stream);
 
 #ifdef __cplusplus
 }

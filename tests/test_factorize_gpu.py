@@ -1,0 +1,83 @@
+"""GPU parity of the stored factorisation against the reference's own torch SVD path.
+
+Reference: fake_svd (fake_layer_merge_dynamic_cache.py:11-29) = torch.linalg.svd in fp32, truncate,
+multiply back, cast to the cache dtype (:176).  Factors are compared through the reconstruction
+(singular vectors are sign/rotation ambiguous).  Tolerances are BASELINE.json's:
+  * relative Frobenius reconstruction error <= 1.01 x the reference's at equal rank,
+  * leading singular values within 1e-3 relative.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_fake_svd(x_bf16: torch.Tensor, rank: int):
+    """The reference's arithmetic on the same device: fp32 SVD, truncate, multiply back, cast to bf16."""
+    x = x_bf16.float()[None]  # (bs=1, S, n), as fake_svd sees it after its reshape
+    u, s, vh = torch.linalg.svd(x, full_matrices=False)
+    approx = torch.matmul(u[:, :, :rank], torch.matmul(torch.diag_embed(s[:, :rank]), vh[:, :rank, :]))
+    return approx[0].to(torch.bfloat16), s[0]
+
+
+def _rel_err(x, xh):
+    x = x.double()
+    return (torch.linalg.norm(x - xh.double()) / torch.linalg.norm(x)).item()
+
+
+@pytest.mark.parametrize(
+    "tokens,cols,rank,alpha",
+    [
+        (1024, 1024, 128, 1.0),    # single-layer shape (config 3 columns), skinny rank
+        (1024, 1024, 192, 0.5),
+        (2048, 2048, 256, 1.0),
+        (4096, 4096, 512, 1.0),    # config 1, K rank
+        (4096, 4096, 768, 0.5),    # config 1, V rank
+        (4096, 4096, 512, None),   # i.i.d. Gaussian: worst case for any low-rank method
+        (1536, 2048, 512, 1.0),    # fewer tokens than columns
+    ],
+)
+def test_reconstruction_matches_reference_svd(tokens, cols, rank, alpha):
+    from xkv_b200 import factorize, synthetic
+
+    x = synthetic.group_matrix(tokens, cols, alpha, seed=1234, device="cuda")
+    ref_hat, s_ref = _ref_fake_svd(x, rank)
+    (f,) = factorize.factorize_batch([x], rank)
+    torch.cuda.synchronize()
+    assert f.A.shape == (tokens, rank) and f.Vt.shape == (rank, cols) and f.V.shape == (cols, rank)
+    assert torch.equal(f.V, f.Vt.t())
+    e_ref = _rel_err(x, ref_hat)
+    e_ours = _rel_err(x, f.reconstruct())
+    print(f"tokens={tokens} cols={cols} r={rank} alpha={alpha}: err ref={e_ref:.6f} ours={e_ours:.6f} "
+          f"ratio={e_ours / e_ref:.5f}")
+    assert e_ours <= 1.01 * e_ref
+    # right factor is orthonormal (to bf16 rounding)
+    vt = f.Vt.float()
+    assert (vt @ vt.t() - torch.eye(rank, device="cuda")).abs().max().item() < 2e-2
+    if alpha is not None:
+        k = 16
+        rel = ((f.sigma_lead[:k] - s_ref[:k]).abs() / s_ref[:k]).max().item()
+        print(f"   leading singular values: max rel dev {rel:.2e}")
+        assert rel < 1e-3
+
+
+def test_batch_of_two_ranks_shapes_and_determinism():
+    from xkv_b200 import factorize, synthetic
+
+    xs = [synthetic.group_matrix(1024, 1024, 1.0, seed=s, device="cuda") for s in (1, 2, 3)]
+    f1 = factorize.factorize_batch(xs, 128)
+    f2 = factorize.factorize_batch(xs, 128)
+    torch.cuda.synchronize()
+    for a, b in zip(f1, f2):
+        assert torch.equal(a.A, b.A) and torch.equal(a.Vt, b.Vt)   # same seed -> bit-identical factors
+    assert not torch.equal(f1[0].Vt, f1[1].Vt)
+
+
+def test_rejects_rank_that_does_not_fit():
+    from xkv_b200 import _lib, factorize
+
+    x = torch.zeros(64, 256, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(_lib.XkvError):
+        factorize.factorize_batch([x], 128)      # rank > tokens
+    with pytest.raises(_lib.XkvError):
+        factorize.factorize_batch([torch.zeros(512, 256, device="cuda", dtype=torch.bfloat16)], 256)  # sketch > cols

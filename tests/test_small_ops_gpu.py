@@ -1,0 +1,127 @@
+"""GPU checks of the small fp32 kernels against torch (each is a restatement of one torch call)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reduce_slabs_and_symmetrize():
+    from xkv_b200 import ops
+
+    torch.manual_seed(0)
+    slabs = torch.randn(3, 200, 200, device="cuda")
+    out = torch.empty(200, 200, device="cuda")
+    ops.reduce_slabs(slabs, out, symmetrize=False)
+    torch.cuda.synchronize()
+    assert torch.allclose(out, slabs.sum(0), atol=1e-5)
+    ops.reduce_slabs(slabs, out, symmetrize=True)
+    torch.cuda.synchronize()
+    up = torch.triu(slabs.sum(0))
+    ref = up + torch.triu(up, 1).t()
+    assert torch.allclose(out, ref, atol=1e-5)
+
+
+def test_split_bf16_limbs_reconstruct_fp32():
+    from xkv_b200 import ops
+
+    x = torch.randn(64, 256, device="cuda") * 37.0
+    h, m, l = (torch.empty(64, 256, device="cuda", dtype=torch.bfloat16) for _ in range(3))
+    ops.split_bf16(x, h, m, l)
+    torch.cuda.synchronize()
+    assert torch.equal(h, x.bfloat16())
+    rec = h.float() + m.float() + l.float()
+    assert (rec - x).abs().max().item() <= 2e-7 * x.abs().max().item()
+
+
+def test_fill_gaussian_is_deterministic_and_normal():
+    from xkv_b200 import ops
+
+    a = torch.empty(512, 1024, device="cuda", dtype=torch.bfloat16)
+    b = torch.empty_like(a)
+    ops.fill_gaussian_bf16(a, 7)
+    ops.fill_gaussian_bf16(b, 7)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    af = a.float()
+    assert abs(af.mean().item()) < 0.01 and abs(af.std().item() - 1.0) < 0.01
+    ops.fill_gaussian_bf16(b, 8)
+    torch.cuda.synchronize()
+    assert not torch.equal(a, b)
+
+
+def test_normalize_rows_with_limbs():
+    from xkv_b200 import ops
+
+    ys = [torch.randn(64, 512, device="cuda") * (i + 1) for i in range(3)]
+    ref = [y / y.norm(dim=1, keepdim=True) for y in ys]
+    hi = [torch.empty(64, 512, device="cuda", dtype=torch.bfloat16) for _ in ys]
+    mid = [torch.empty_like(h) for h in hi]
+    lo = [torch.empty_like(h) for h in hi]
+    ops.normalize_rows(ys, hi, mid, lo)
+    torch.cuda.synchronize()
+    for y, r, h, m, l in zip(ys, ref, hi, mid, lo):
+        assert torch.allclose(y, r, atol=1e-6)
+        assert (h.float() + m.float() + l.float() - y).abs().max().item() < 1e-7
+
+
+@pytest.mark.parametrize("l,cond", [(64, 10.0), (192, 1e3), (576, 1e4), (832, 1e2)])
+def test_cholesky_inverse(l, cond):
+    from xkv_b200 import ops
+
+    torch.manual_seed(l)
+    batch = 3
+    ss, refs, linvs = [], [], []
+    for b in range(batch):
+        q = torch.linalg.qr(torch.randn(l, l, device="cuda", dtype=torch.float64))[0]
+        ev = torch.logspace(0, -torch.log10(torch.tensor(cond)).item(), l, device="cuda", dtype=torch.float64)
+        s = (q * ev) @ q.t()
+        d = s.diagonal().rsqrt()
+        s = s * d[:, None] * d[None, :]      # unit diagonal, as after row normalisation
+        refs.append(s)
+        ss.append(s.float().contiguous())
+        linvs.append(torch.full((l, l), float("nan"), device="cuda"))
+    ops.cholesky_inverse(ss, linvs, pivot_floor=1e-9)
+    torch.cuda.synchronize()
+    for s64, li in zip(refs, linvs):
+        assert not torch.isnan(li).any()
+        assert torch.equal(torch.triu(li, 1), torch.zeros_like(li))
+        eye = li.double() @ s64 @ li.double().t()
+        err = (eye - torch.eye(l, device="cuda", dtype=torch.float64)).abs().max().item()
+        assert err < 5e-3 * max(1.0, cond / 1e3), f"Linv S Linv^T deviates from I by {err}"
+
+
+@pytest.mark.parametrize("w", [32, 128, 160])
+def test_jacobi_window_eigh(w):
+    from xkv_b200 import ops
+
+    torch.manual_seed(w)
+    count = 5
+    ts, refs = [], []
+    for b in range(count):
+        a = torch.randn(w, w, device="cuda", dtype=torch.float64)
+        s = a @ a.t() / w + torch.diag(torch.linspace(3, 0, w, device="cuda", dtype=torch.float64))
+        refs.append(s)
+        ts.append(s.float().contiguous())
+    evals = [torch.empty(w, device="cuda") for _ in range(count)]
+    wts = [torch.empty(w, w, device="cuda") if b != 1 else None for b in range(count)]
+    ops.jacobi_eigh(ts, evals, wts, sweeps=10)
+    torch.cuda.synchronize()
+    for s64, ev, wt in zip(refs, evals, wts):
+        ref = torch.linalg.eigvalsh(s64).flip(0)
+        assert torch.allclose(ev.double(), ref, rtol=1e-4, atol=1e-5)
+        if wt is not None:
+            wd = wt.double()
+            assert (wd @ wd.t() - torch.eye(w, device="cuda", dtype=torch.float64)).abs().max().item() < 1e-4
+            assert (wd @ s64 @ wd.t() - torch.diag(ev.double())).abs().max().item() < 1e-3
+
+
+def test_convert_bf16_and_transpose():
+    from xkv_b200 import ops
+
+    x = torch.randn(100, 264, device="cuda")
+    d = torch.empty(100, 264, device="cuda", dtype=torch.bfloat16)
+    dt = torch.empty(264, 104, device="cuda", dtype=torch.bfloat16)[:, :100]
+    ops.convert_bf16(x, d, dt)
+    torch.cuda.synchronize()
+    assert torch.equal(d, x.bfloat16())
+    assert torch.equal(dt, x.bfloat16().t())

@@ -1,0 +1,636 @@
+// xkv_b200 — the small fp32 kernels around the tensor-core GEMMs of the factorisation:
+// split-K reduction / Gram symmetrisation, fp32 -> bf16 limb splitting, the Gaussian test matrix,
+// row normalisation, blocked Cholesky with explicit triangular inverse (CholeskyQR), the
+// shared-memory Jacobi eigen-solver for the Rayleigh-Ritz window, and bf16 conversion/transposition
+// of the right factor.  Together with xkv_gemm.cu they replace torch.linalg.svd
+// (fake_layer_merge_dynamic_cache.py:20).
+#include "xkv_common.cuh"
+#include "xkv_host.h"
+
+namespace xkv {
+
+// =============================================================================================
+// split-K slab reduction (+ symmetrisation of the Gram matrix)
+// =============================================================================================
+template <int SYM>
+__global__ void __launch_bounds__(256) reduce_slabs_kernel(const float* __restrict__ slabs, int num_slabs,
+                                                           long long slab_stride, int rows, int cols, long long ld,
+                                                           float* __restrict__ out, long long ldo, int tiles_per_row) {
+  __shared__ float tile[32][33];
+  int bi, bj;
+  if (SYM) {
+    // linear index over tile pairs bi <= bj
+    int t = blockIdx.x;
+    bi = 0;
+    int cnt = tiles_per_row;
+    while (t >= cnt) {
+      t -= cnt;
+      ++bi;
+      --cnt;
+    }
+    bj = bi + t;
+  } else {
+    bi = blockIdx.x / tiles_per_row;
+    bj = blockIdx.x - bi * tiles_per_row;
+  }
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi * 32 + r, j = bj * 32 + tx;
+    float acc = 0.f;
+    if (i < rows && j < cols) {
+      const float* p = slabs + static_cast<long long>(i) * ld + j;
+      for (int s = 0; s < num_slabs; ++s) acc += p[static_cast<long long>(s) * slab_stride];
+      if (!SYM || j >= i) out[static_cast<long long>(i) * ldo + j] = acc;
+    }
+    if (SYM) tile[r][tx] = acc;
+  }
+  if (SYM) {
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+      // mirrored element: out[bj*32 + r][bi*32 + tx] = sum(bi*32 + tx, bj*32 + r)
+      const int i = bj * 32 + r, j = bi * 32 + tx;
+      if (i < rows && j < cols && i > j) out[static_cast<long long>(i) * ldo + j] = tile[tx][r];
+    }
+  }
+}
+
+// =============================================================================================
+// fp32 -> bf16 limbs
+// =============================================================================================
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
+  h = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(h);
+  m = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(m);
+  l = __float2bfloat16_rn(r2);
+}
+
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, int rows, int cols, long long ld,
+                                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
+                                                         __nv_bfloat16* __restrict__ lo, long long ldo) {
+  const int cols4 = cols >> 2;  // host guarantees cols % 4 == 0
+  const long long total = static_cast<long long>(rows) * cols4;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(idx / cols4);
+    const int c = static_cast<int>(idx - static_cast<long long>(r) * cols4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + static_cast<long long>(r) * ld + c);
+    __nv_bfloat16 h[4], m[4], l[4];
+    split3(v.x, h[0], m[0], l[0]);
+    split3(v.y, h[1], m[1], l[1]);
+    split3(v.z, h[2], m[2], l[2]);
+    split3(v.w, h[3], m[3], l[3]);
+    const long long o = static_cast<long long>(r) * ldo + c;
+    *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<uint2*>(h);
+    if (mid) *reinterpret_cast<uint2*>(mid + o) = *reinterpret_cast<uint2*>(m);
+    if (lo) *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<uint2*>(l);
+  }
+}
+
+// =============================================================================================
+// deterministic Gaussian test matrix (counter-based: value depends only on seed and position)
+// =============================================================================================
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256) fill_gaussian_kernel(__nv_bfloat16* __restrict__ out, int rows, int cols,
+                                                            long long ld, uint64_t seed) {
+  const int cols2 = cols >> 1;  // host guarantees cols % 2 == 0
+  const long long total = static_cast<long long>(rows) * cols2;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(idx / cols2);
+    const int c = static_cast<int>(idx - static_cast<long long>(r) * cols2) * 2;
+    const uint64_t z = mix64(seed * 0xD1342543DE82EF95ull + static_cast<uint64_t>(idx));
+    const float u1 = (static_cast<float>(static_cast<uint32_t>(z >> 40)) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = (static_cast<float>(static_cast<uint32_t>(z) >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float rad = sqrtf(-2.0f * __logf(u1));
+    float sn, cs;
+    __sincosf(6.283185307179586f * u2, &sn, &cs);
+    *reinterpret_cast<uint32_t*>(out + static_cast<long long>(r) * ld + c) = pack_bf16x2(rad * cs, rad * sn);
+  }
+}
+
+// =============================================================================================
+// row normalisation (each row of Yt is a column of Y), optionally emitting bf16 limbs
+// =============================================================================================
+struct NormParams {
+  float* Y[XKV_MAX_BATCH];
+  __nv_bfloat16* hi[XKV_MAX_BATCH];
+  __nv_bfloat16* mid[XKV_MAX_BATCH];
+  __nv_bfloat16* lo[XKV_MAX_BATCH];
+  int rows, cols;
+  long long ld, ldo;
+};
+__global__ void __launch_bounds__(256) normalize_rows_kernel(const __grid_constant__ NormParams p) {
+  __shared__ float red[8];
+  __shared__ float scale_s;
+  float* row = p.Y[blockIdx.y] + static_cast<long long>(blockIdx.x) * p.ld;
+  const int cols4 = p.cols >> 2;
+  float acc = 0.f;
+  for (int c = threadIdx.x; c < cols4; c += blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(row)[c];
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    scale_s = t > 0.f ? rsqrtf(t) : 0.f;
+  }
+  __syncthreads();
+  const float sc = scale_s;
+  __nv_bfloat16* hi = p.hi[blockIdx.y];
+  __nv_bfloat16* mid = p.mid[blockIdx.y];
+  __nv_bfloat16* lo = p.lo[blockIdx.y];
+  const long long o0 = static_cast<long long>(blockIdx.x) * p.ldo;
+  for (int c = threadIdx.x; c < cols4; c += blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(row)[c];
+    v.x *= sc;
+    v.y *= sc;
+    v.z *= sc;
+    v.w *= sc;
+    reinterpret_cast<float4*>(row)[c] = v;
+    if (hi) {
+      __nv_bfloat16 h[4], m[4], l[4];
+      split3(v.x, h[0], m[0], l[0]);
+      split3(v.y, h[1], m[1], l[1]);
+      split3(v.z, h[2], m[2], l[2]);
+      split3(v.w, h[3], m[3], l[3]);
+      *reinterpret_cast<uint2*>(hi + o0 + 4 * c) = *reinterpret_cast<uint2*>(h);
+      if (mid) *reinterpret_cast<uint2*>(mid + o0 + 4 * c) = *reinterpret_cast<uint2*>(m);
+      if (lo) *reinterpret_cast<uint2*>(lo + o0 + 4 * c) = *reinterpret_cast<uint2*>(l);
+    }
+  }
+}
+
+// =============================================================================================
+// Blocked Cholesky S = L L^T with explicit inverse Linv = L^{-1} (batched over blockIdx.y)
+//
+// Right-looking, NB = 64.  Step k launches
+//   panel  : CTA i >= k factors the diagonal block (every CTA redundantly, in shared memory,
+//            so there is no inter-CTA dependency inside a launch), inverts it, and solves its
+//            own block  L[i,k] = S[i,k] * L[k,k]^{-T}.
+//   update : trailing tiles S[i,j] -= L[i,k] L[j,k]^T (k < j <= i), plus the blocks of row k of
+//            the inverse  Linv[k,j] = -Linv[k,k] * sum_{t=j}^{k-1} L[k,t] Linv[t,j]  (j < k).
+// Pivots are floored at `pivot_floor` (inputs have unit diagonal: the columns were normalised),
+// so the factorisation never breaks down; CholeskyQR is simply repeated.
+// =============================================================================================
+constexpr int NB = 64;
+constexpr int NBP = NB + 1;
+
+struct CholParams {
+  float* S[XKV_MAX_BATCH];
+  float* Linv[XKV_MAX_BATCH];
+  int l, nblk, k;
+  long long ld;
+  float pivot_floor;
+};
+
+// C(64x64, 4x4 per thread) += A(64x64) * B(64x64)^T  [TRANSB=1]  or  A * B  [TRANSB=0]; operands in smem
+template <int TRANSB>
+__device__ __forceinline__ void block_mma(float (&acc)[4][4], const float (*As)[NBP], const float (*Bs)[NBP],
+                                          int kmax = NB) {
+  const int tr = (threadIdx.x >> 4) * 4;  // row base
+  const int tc = (threadIdx.x & 15) * 4;  // col base
+  for (int k = 0; k < kmax; ++k) {
+    float a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = As[tr + i][k];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = TRANSB ? Bs[tc + j][k] : Bs[k][tc + j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+}
+__device__ __forceinline__ void load_block(float (*dst)[NBP], const float* src, long long ld) {
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+    const int r = e >> 6, c = e & 63;
+    dst[r][c] = src[static_cast<long long>(r) * ld + c];
+  }
+}
+
+__global__ void __launch_bounds__(256) chol_panel_kernel(const __grid_constant__ CholParams p) {
+  __shared__ float D[NB][NBP];
+  __shared__ float Di[NB][NBP];
+  float* S = p.S[blockIdx.y];
+  float* Linv = p.Linv[blockIdx.y];
+  const int k = p.k;
+  const int i = k + blockIdx.x;
+  const int tid = threadIdx.x;
+  const float* dblk = S + (static_cast<long long>(k) * NB) * p.ld + k * NB;
+  load_block(D, dblk, p.ld);
+  __syncthreads();
+  // --- in-place lower Cholesky of D ---
+  for (int j = 0; j < NB; ++j) {
+    if (tid < 32) {
+      float d = D[j][j];
+      d = fmaxf(d, p.pivot_floor);
+      const float inv = rsqrtf(d);
+      for (int r = j + 1 + tid; r < NB; r += 32) D[r][j] *= inv;
+      __syncwarp();
+      if (tid == 0) D[j][j] = d * inv;  // sqrt(d)
+    }
+    __syncthreads();
+    // rank-1 update of the trailing lower triangle (16 x 16 thread grid, no div/mod)
+    for (int r = j + 1 + (tid >> 4); r < NB; r += 16) {
+      const float lr = D[r][j];
+      for (int c = j + 1 + (tid & 15); c <= r; c += 16) D[r][c] -= lr * D[c][j];
+    }
+    __syncthreads();
+  }
+  // --- Di = D^{-1} (lower): thread c solves column c by forward substitution ---
+  if (tid < NB) {
+    const int c = tid;
+    for (int r = 0; r < NB; ++r) {
+      float x = (r == c) ? 1.f : 0.f;
+      if (r >= c) {
+        for (int t = c; t < r; ++t) x -= D[r][t] * Di[t][c];
+        x /= D[r][r];
+      } else {
+        x = 0.f;
+      }
+      Di[r][c] = x;
+    }
+  }
+  __syncthreads();
+  if (i == k) {
+    // Only the inverse of the diagonal block is published: L[k,k] itself is never read again, and
+    // writing it over S[k,k] would race with the other CTAs of this launch still loading that block.
+    float* iblk = Linv + (static_cast<long long>(k) * NB) * p.ld + k * NB;
+    for (int e = tid; e < NB * NB; e += blockDim.x) {
+      const int r = e >> 6, c = e & 63;
+      iblk[static_cast<long long>(r) * p.ld + c] = Di[r][c];
+    }
+  } else {
+    // L[i,k] = S[i,k] * Di^T  (the factor D is no longer needed: reuse its buffer for the panel block)
+    load_block(D, S + (static_cast<long long>(i) * NB) * p.ld + k * NB, p.ld);
+    __syncthreads();
+    float acc[4][4] = {};
+    block_mma<1>(acc, D, Di);
+    float* oblk = S + (static_cast<long long>(i) * NB) * p.ld + k * NB;
+    const int tr = (tid >> 4) * 4, tc = (tid & 15) * 4;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) oblk[static_cast<long long>(tr + a) * p.ld + tc + b] = acc[a][b];
+  }
+}
+
+__global__ void __launch_bounds__(256) chol_update_kernel(const __grid_constant__ CholParams p) {
+  __shared__ float As[NB][NBP];
+  __shared__ float Bs[NB][NBP];
+  float* S = p.S[blockIdx.y];
+  float* Linv = p.Linv[blockIdx.y];
+  const int k = p.k;
+  const int nt = p.nblk - k - 1;       // trailing block rows/cols
+  const int ntrail = nt * (nt + 1) / 2;
+  const int tid = threadIdx.x;
+  const int tr = (tid >> 4) * 4, tc = (tid & 15) * 4;
+  int b = blockIdx.x;
+  if (b < ntrail) {
+    // tile (i, j) of the trailing lower triangle, k < j <= i
+    int ii = 0;
+    while (b >= ii + 1) {
+      b -= ii + 1;
+      ++ii;
+    }
+    const int i = k + 1 + ii, j = k + 1 + b;
+    load_block(As, S + (static_cast<long long>(i) * NB) * p.ld + k * NB, p.ld);
+    load_block(Bs, S + (static_cast<long long>(j) * NB) * p.ld + k * NB, p.ld);
+    __syncthreads();
+    float acc[4][4] = {};
+    block_mma<1>(acc, As, Bs);
+    float* o = S + (static_cast<long long>(i) * NB) * p.ld + j * NB;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[static_cast<long long>(tr + a) * p.ld + tc + c] -= acc[a][c];
+  } else {
+    // inverse block (k, j), j < k
+    const int j = b - ntrail;
+    float acc[4][4] = {};
+    for (int t = j; t < k; ++t) {
+      __syncthreads();
+      load_block(As, S + (static_cast<long long>(k) * NB) * p.ld + t * NB, p.ld);      // L[k,t]
+      load_block(Bs, Linv + (static_cast<long long>(t) * NB) * p.ld + j * NB, p.ld);   // Linv[t,j]
+      __syncthreads();
+      block_mma<0>(acc, As, Bs);
+    }
+    __syncthreads();
+    // stage acc in Bs, load Linv[k,k] into As, then out = -As * Bs
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) Bs[tr + a][tc + c] = acc[a][c];
+    load_block(As, Linv + (static_cast<long long>(k) * NB) * p.ld + k * NB, p.ld);
+    __syncthreads();
+    float out[4][4] = {};
+    block_mma<0>(out, As, Bs);
+    float* o = Linv + (static_cast<long long>(k) * NB) * p.ld + j * NB;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[static_cast<long long>(tr + a) * p.ld + tc + c] = -out[a][c];
+  }
+}
+
+// zero the strict upper block triangle of Linv (the GEMM consumes Linv as a dense matrix)
+__global__ void __launch_bounds__(256) zero_upper_kernel(const __grid_constant__ CholParams p) {
+  float* Linv = p.Linv[blockIdx.y];
+  const long long total = static_cast<long long>(p.l) * p.l;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(e / p.l), c = static_cast<int>(e - static_cast<long long>(r) * p.l);
+    if ((c / NB) > (r / NB)) Linv[static_cast<long long>(r) * p.ld + c] = 0.f;
+  }
+}
+
+// =============================================================================================
+// Shared-memory two-sided Jacobi eigen-solver for the Rayleigh-Ritz window (W <= 160, W even)
+// One CTA per matrix; A and the eigenvector accumulator V both live in shared memory.
+// Parallel cyclic ordering (round-robin tournament): W/2 disjoint rotations per round.
+// Output: eigenvalues sorted descending, eigenvectors as ROWS of Wt in the same order.
+// =============================================================================================
+struct JacobiParams {
+  const float* T[2 * XKV_MAX_BATCH];  // W x W symmetric inputs (ld)
+  float* evals[2 * XKV_MAX_BATCH];    // W
+  float* Wt[2 * XKV_MAX_BATCH];       // W x W (ld_w), may be null (values only)
+  int W, sweeps;
+  long long ld, ld_w;
+};
+constexpr int JAC_THREADS = 512;
+
+__global__ void __launch_bounds__(JAC_THREADS, 1) jacobi_kernel(const __grid_constant__ JacobiParams p) {
+  extern __shared__ float jsm[];
+  const int W = p.W, WP = W + 1, H = W / 2;
+  float* A = jsm;                 // W x WP
+  float* V = A + W * WP;          // W x WP
+  float* cs = V + W * WP;         // 2 * H
+  int* pij = reinterpret_cast<int*>(cs + 2 * H);  // 2 * H
+  const int tid = threadIdx.x;
+  const float* T = p.T[blockIdx.x];
+  const bool want_vec = p.Wt[blockIdx.x] != nullptr;
+  for (int e = tid; e < W * W; e += JAC_THREADS) {
+    const int r = e / W, c = e - r * W;
+    // symmetrise on load: use the average of the two triangles
+    A[r * WP + c] = 0.5f * (T[static_cast<long long>(r) * p.ld + c] + T[static_cast<long long>(c) * p.ld + r]);
+    V[r * WP + c] = (r == c) ? 1.f : 0.f;
+  }
+  __syncthreads();
+  for (int sweep = 0; sweep < p.sweeps; ++sweep) {
+    for (int round = 0; round < W - 1; ++round) {
+      if (tid < H) {
+        const int q = tid;
+        int a = (round + q) % (W - 1);
+        int b = (q == 0) ? (W - 1) : (round - q + (W - 1)) % (W - 1);
+        const int i = min(a, b), j = max(a, b);
+        const float aii = A[i * WP + i], ajj = A[j * WP + j], aij = A[i * WP + j];
+        float c = 1.f, s = 0.f;
+        if (fabsf(aij) > 1e-12f * sqrtf(fabsf(aii * ajj)) && aij != 0.f) {
+          const float tau = (ajj - aii) / (2.f * aij);
+          const float t = (tau >= 0.f ? 1.f : -1.f) / (fabsf(tau) + sqrtf(1.f + tau * tau));
+          c = rsqrtf(1.f + t * t);
+          s = t * c;
+        }
+        cs[2 * q] = c;
+        cs[2 * q + 1] = s;
+        pij[2 * q] = i;
+        pij[2 * q + 1] = j;
+      }
+      __syncthreads();
+      // column rotations: A <- A J, V <- V J
+      for (int e = tid; e < W * H; e += JAC_THREADS) {
+        const int x = e / H, q = e - x * H;
+        const float c = cs[2 * q], s = cs[2 * q + 1];
+        const int i = pij[2 * q], j = pij[2 * q + 1];
+        const float ai = A[x * WP + i], aj = A[x * WP + j];
+        A[x * WP + i] = c * ai - s * aj;
+        A[x * WP + j] = s * ai + c * aj;
+        if (want_vec) {
+          const float vi = V[x * WP + i], vj = V[x * WP + j];
+          V[x * WP + i] = c * vi - s * vj;
+          V[x * WP + j] = s * vi + c * vj;
+        }
+      }
+      __syncthreads();
+      // row rotations: A <- J^T A
+      for (int e = tid; e < W * H; e += JAC_THREADS) {
+        const int q = e / W, y = e - q * W;
+        const float c = cs[2 * q], s = cs[2 * q + 1];
+        const int i = pij[2 * q], j = pij[2 * q + 1];
+        const float ai = A[i * WP + y], aj = A[j * WP + y];
+        A[i * WP + y] = c * ai - s * aj;
+        A[j * WP + y] = s * ai + c * aj;
+      }
+      __syncthreads();
+    }
+  }
+  // sort eigenvalues descending by rank counting; emit eigenvectors as rows of Wt
+  if (tid < W) {
+    const float d = A[tid * WP + tid];
+    int rank = 0;
+    for (int u = 0; u < W; ++u) {
+      const float du = A[u * WP + u];
+      rank += (du > d) || (du == d && u < tid);
+    }
+    pij[tid] = rank;  // W == 2H entries
+    p.evals[blockIdx.x][rank] = d;
+  }
+  __syncthreads();
+  if (want_vec) {
+    float* Wt = p.Wt[blockIdx.x];
+    for (int e = tid; e < W * W; e += JAC_THREADS) {
+      const int t = e / W, x = e - t * W;  // eigenvector t (column of V), component x
+      Wt[static_cast<long long>(pij[t]) * p.ld_w + x] = V[x * WP + t];
+    }
+  }
+}
+
+// =============================================================================================
+// fp32 -> bf16 conversion with optional transposed copy (right factor: Vt (r x n) and V (n x r))
+// =============================================================================================
+__global__ void __launch_bounds__(256) convert_bf16_kernel(const float* __restrict__ src, int rows, int cols,
+                                                           long long ld, __nv_bfloat16* __restrict__ dst, long long ldd,
+                                                           __nv_bfloat16* __restrict__ dstT, long long lddT) {
+  __shared__ float tile[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi * 32 + r, j = bj * 32 + tx;
+    float v = 0.f;
+    if (i < rows && j < cols) {
+      v = src[static_cast<long long>(i) * ld + j];
+      if (dst) dst[static_cast<long long>(i) * ldd + j] = __float2bfloat16_rn(v);
+    }
+    tile[r][tx] = v;
+  }
+  if (dstT) {
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+      const int j = bj * 32 + r, i = bi * 32 + tx;  // dstT[j][i] = src[i][j]
+      if (i < rows && j < cols) dstT[static_cast<long long>(j) * lddT + i] = __float2bfloat16_rn(tile[tx][r]);
+    }
+  }
+}
+
+static int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      sms = 148;
+  }
+  return sms;
+}
+
+}  // namespace xkv
+
+using namespace xkv;
+
+extern "C" int xkv_reduce_slabs(const float* slabs, int num_slabs, int64_t slab_stride, int rows, int cols, int64_t ld,
+                                int symmetrize, float* out, int64_t ld_out, void* stream) {
+  XKV_REQUIRE(slabs && out && num_slabs >= 1 && rows > 0 && cols > 0, "reduce_slabs: bad arguments");
+  const int tr = (rows + 31) / 32, tc = (cols + 31) / 32;
+  if (symmetrize) {
+    XKV_REQUIRE(rows == cols, "reduce_slabs: symmetrize needs a square matrix");
+    const int grid = tr * (tr + 1) / 2;
+    reduce_slabs_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(slabs, num_slabs, slab_stride, rows, cols, ld, out,
+                                                                ld_out, tr);
+  } else {
+    reduce_slabs_kernel<0><<<tr * tc, 256, 0, as_stream(stream)>>>(slabs, num_slabs, slab_stride, rows, cols, ld, out,
+                                                                   ld_out, tc);
+  }
+  XKV_LAUNCHED();
+  return 0;
+}
+
+extern "C" int xkv_split_bf16(const float* x, int rows, int cols, int64_t ld, void* hi, void* mid, void* lo,
+                              int64_t ld_out, void* stream) {
+  XKV_REQUIRE(x && hi && rows > 0 && cols > 0, "split_bf16: bad arguments");
+  XKV_REQUIRE(cols % 4 == 0 && ld % 4 == 0 && ld_out % 4 == 0, "split_bf16: cols/ld must be multiples of 4");
+  const long long total = static_cast<long long>(rows) * (cols / 4);
+  long long grid = (total + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (grid > cap) grid = cap;
+  split_bf16_kernel<<<static_cast<int>(grid), 256, 0, as_stream(stream)>>>(
+      x, rows, cols, ld, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(mid),
+      static_cast<__nv_bfloat16*>(lo), ld_out);
+  XKV_LAUNCHED();
+  return 0;
+}
+
+extern "C" int xkv_fill_gaussian_bf16(void* out, int rows, int cols, int64_t ld, uint64_t seed, void* stream) {
+  XKV_REQUIRE(out && rows > 0 && cols > 0 && cols % 2 == 0 && ld % 2 == 0, "fill_gaussian: bad arguments");
+  const long long total = static_cast<long long>(rows) * (cols / 2);
+  long long grid = (total + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (grid > cap) grid = cap;
+  fill_gaussian_kernel<<<static_cast<int>(grid), 256, 0, as_stream(stream)>>>(static_cast<__nv_bfloat16*>(out), rows,
+                                                                              cols, ld, seed);
+  XKV_LAUNCHED();
+  return 0;
+}
+
+extern "C" int xkv_normalize_rows(float* const* Y_host, void* const* hi_host, void* const* mid_host,
+                                  void* const* lo_host, int batch, int rows, int cols, int64_t ld, int64_t ld_out,
+                                  void* stream) {
+  XKV_REQUIRE(Y_host && batch >= 1 && batch <= XKV_MAX_BATCH, "normalize_rows: bad batch");
+  XKV_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0 && ld % 4 == 0 && ld_out % 4 == 0,
+              "normalize_rows: cols/ld must be multiples of 4");
+  NormParams p;
+  std::memset(&p, 0, sizeof(p));
+  for (int b = 0; b < batch; ++b) {
+    p.Y[b] = Y_host[b];
+    p.hi[b] = hi_host ? static_cast<__nv_bfloat16*>(hi_host[b]) : nullptr;
+    p.mid[b] = mid_host ? static_cast<__nv_bfloat16*>(mid_host[b]) : nullptr;
+    p.lo[b] = lo_host ? static_cast<__nv_bfloat16*>(lo_host[b]) : nullptr;
+  }
+  p.rows = rows;
+  p.cols = cols;
+  p.ld = ld;
+  p.ldo = ld_out;
+  normalize_rows_kernel<<<dim3(rows, batch), 256, 0, as_stream(stream)>>>(p);
+  XKV_LAUNCHED();
+  return 0;
+}
+
+extern "C" int xkv_cholesky_inverse(float* const* S_host, float* const* Linv_host, int batch, int l, int64_t ld,
+                                    float pivot_floor, void* stream) {
+  XKV_REQUIRE(S_host && Linv_host && batch >= 1 && batch <= XKV_MAX_BATCH, "cholesky: bad batch");
+  XKV_REQUIRE(l > 0 && l % NB == 0, "cholesky: l=%d must be a positive multiple of %d", l, NB);
+  CholParams p;
+  std::memset(&p, 0, sizeof(p));
+  for (int b = 0; b < batch; ++b) {
+    XKV_REQUIRE(S_host[b] && Linv_host[b], "cholesky: null matrix %d", b);
+    p.S[b] = S_host[b];
+    p.Linv[b] = Linv_host[b];
+  }
+  p.l = l;
+  p.nblk = l / NB;
+  p.ld = ld;
+  p.pivot_floor = pivot_floor;
+  cudaStream_t st = as_stream(stream);
+  zero_upper_kernel<<<dim3(64, batch), 256, 0, st>>>(p);
+  XKV_LAUNCHED();
+  for (int k = 0; k < p.nblk; ++k) {
+    p.k = k;
+    chol_panel_kernel<<<dim3(p.nblk - k, batch), 256, 0, st>>>(p);
+    XKV_LAUNCHED();
+    const int nt = p.nblk - k - 1;
+    const int nblocks = nt * (nt + 1) / 2 + k;
+    if (nblocks > 0) {
+      chol_update_kernel<<<dim3(nblocks, batch), 256, 0, st>>>(p);
+      XKV_LAUNCHED();
+    }
+  }
+  return 0;
+}
+
+extern "C" int xkv_jacobi_eigh(const float* const* T_host, float* const* evals_host, float* const* Wt_host, int count,
+                               int W, int64_t ld, int64_t ld_w, int sweeps, void* stream) {
+  XKV_REQUIRE(T_host && evals_host && count >= 1 && count <= 2 * XKV_MAX_BATCH, "jacobi: bad count");
+  XKV_REQUIRE(W >= 2 && W <= 160 && W % 2 == 0, "jacobi: window W=%d must be even and <= 160", W);
+  JacobiParams p;
+  std::memset(&p, 0, sizeof(p));
+  for (int b = 0; b < count; ++b) {
+    XKV_REQUIRE(T_host[b] && evals_host[b], "jacobi: null matrix %d", b);
+    p.T[b] = T_host[b];
+    p.evals[b] = evals_host[b];
+    p.Wt[b] = Wt_host ? Wt_host[b] : nullptr;
+  }
+  p.W = W;
+  p.sweeps = sweeps;
+  p.ld = ld;
+  p.ld_w = ld_w;
+  const size_t smem = static_cast<size_t>(2 * W * (W + 1) + 2 * W) * sizeof(float) + 64;
+  static bool configured = false;
+  if (!configured) {
+    XKV_CHECK_CUDA(cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    configured = true;
+  }
+  jacobi_kernel<<<count, JAC_THREADS, smem, as_stream(stream)>>>(p);
+  XKV_LAUNCHED();
+  return 0;
+}
+
+extern "C" int xkv_convert_bf16(const float* src, int rows, int cols, int64_t ld, void* dst, int64_t ld_dst, void* dstT,
+                                int64_t ld_dstT, void* stream) {
+  XKV_REQUIRE(src && (dst || dstT) && rows > 0 && cols > 0, "convert_bf16: bad arguments");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  convert_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, rows, cols, ld, static_cast<__nv_bfloat16*>(dst),
+                                                           ld_dst, static_cast<__nv_bfloat16*>(dstT), ld_dstT);
+  XKV_LAUNCHED();
+  return 0;
+}

@@ -125,3 +125,80 @@ def gemm_grouped(problems: Sequence[GemmProblem]) -> None:
     lib = _lib.load()
     arr = (GemmProblem * len(problems))(*problems)
     check(lib.xkv_gemm_grouped(arr, len(problems), _stream()))
+
+
+# ---------------------------------------------------------------------------------------------
+# small fp32 helpers of the factorisation
+# ---------------------------------------------------------------------------------------------
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr() if t is not None else None)
+
+
+def _ptr_array(ts: Optional[Sequence[Optional[torch.Tensor]]]):
+    if ts is None:
+        return None
+    return (C.c_void_p * len(ts))(*[(t.data_ptr() if t is not None else None) for t in ts])
+
+
+def reduce_slabs(slabs: torch.Tensor, out: torch.Tensor, symmetrize: bool = False) -> None:
+    """out = slabs.sum(0); with symmetrize the strictly-lower triangle mirrors the upper one.
+    `slabs` is (S, rows, cols) fp32 (only upper-triangle tiles need be valid when symmetrize)."""
+    _require_cuda(slabs, out)
+    s, rows, cols = slabs.shape
+    check(_lib.load().xkv_reduce_slabs(_ptr(slabs), s, slabs.stride(0), rows, cols, slabs.stride(1), int(symmetrize),
+                                       _ptr(out), out.stride(0), _stream()))
+
+
+def split_bf16(x: torch.Tensor, hi: torch.Tensor, mid: Optional[torch.Tensor] = None,
+               lo: Optional[torch.Tensor] = None) -> None:
+    """hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid) for a 2-D fp32 matrix."""
+    _require_cuda(x, hi)
+    rows, cols = x.shape
+    check(_lib.load().xkv_split_bf16(_ptr(x), rows, cols, x.stride(0), _ptr(hi), _ptr(mid), _ptr(lo), hi.stride(0),
+                                     _stream()))
+
+
+def fill_gaussian_bf16(out: torch.Tensor, seed: int) -> None:
+    _require_cuda(out)
+    rows, cols = out.shape
+    check(_lib.load().xkv_fill_gaussian_bf16(_ptr(out), rows, cols, out.stride(0), C.c_uint64(seed), _stream()))
+
+
+def normalize_rows(ys: Sequence[torch.Tensor], hi=None, mid=None, lo=None) -> None:
+    """Scale every row of each fp32 matrix to unit norm in place, optionally emitting bf16 limbs."""
+    _require_cuda(*ys)
+    rows, cols = ys[0].shape
+    ldo = hi[0].stride(0) if hi is not None else cols
+    check(_lib.load().xkv_normalize_rows(_ptr_array(ys), _ptr_array(hi), _ptr_array(mid), _ptr_array(lo), len(ys),
+                                         rows, cols, ys[0].stride(0), ldo, _stream()))
+
+
+def cholesky_inverse(ss: Sequence[torch.Tensor], linvs: Sequence[torch.Tensor], pivot_floor: float = 1e-6) -> None:
+    """Batched S = L L^T and Linv = L^{-1} (see include/xkv_b200.h for what is left in S)."""
+    _require_cuda(*ss, *linvs)
+    l = ss[0].shape[0]
+    check(_lib.load().xkv_cholesky_inverse(_ptr_array(ss), _ptr_array(linvs), len(ss), l, ss[0].stride(0),
+                                           C.c_float(pivot_floor), _stream()))
+
+
+def jacobi_eigh(ts: Sequence[torch.Tensor], evals: Sequence[torch.Tensor],
+                wts: Optional[Sequence[Optional[torch.Tensor]]] = None, sweeps: int = 8) -> None:
+    """Eigen-decomposition of small symmetric windows (W <= 160): evals descending, eigenvectors as rows."""
+    _require_cuda(*ts, *evals)
+    w = ts[0].shape[0]
+    ldw = w
+    if wts is not None:
+        for t in wts:
+            if t is not None:
+                ldw = t.stride(0)
+    check(_lib.load().xkv_jacobi_eigh(_ptr_array(ts), _ptr_array(evals), _ptr_array(wts), len(ts), w, ts[0].stride(0),
+                                      ldw, sweeps, _stream()))
+
+
+def convert_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None, dst_t: Optional[torch.Tensor] = None) -> None:
+    """fp32 (rows, cols) -> bf16 copy and/or transposed bf16 copy (cols, rows)."""
+    _require_cuda(src)
+    rows, cols = src.shape
+    check(_lib.load().xkv_convert_bf16(_ptr(src), rows, cols, src.stride(0), _ptr(dst),
+                                       dst.stride(0) if dst is not None else 0, _ptr(dst_t),
+                                       dst_t.stride(0) if dst_t is not None else 0, _stream()))
