@@ -99,10 +99,11 @@ XKV_API int xkv_normalize_rows(float* const* Y_host, void* const* hi_host, void*
                                void* stream);
 /* Batched blocked Cholesky S = L L^T of l x l fp32 matrices (l % 64 == 0, unit diagonal expected) with
  * explicit inverse Linv = L^{-1} (dense l x l, zero above the diagonal). S is overwritten: its strictly
- * lower 64-blocks hold L, its diagonal blocks are left untouched. Pivots below pivot_floor are clamped,
- * so the factorisation never fails (CholeskyQR is repeated instead). */
+ * lower 64-blocks hold L, its diagonal blocks are left untouched. `shift` is added to the diagonal
+ * (shifted CholeskyQR: the Gram of an ill-conditioned sketch is indefinite in fp32); pivots below
+ * pivot_floor are clamped, so the factorisation never fails (CholeskyQR is repeated instead). */
 XKV_API int xkv_cholesky_inverse(float* const* S_host, float* const* Linv_host, int batch, int l, int64_t ld,
-                                 float pivot_floor, void* stream);
+                                 float shift, float pivot_floor, void* stream);
 /* Shared-memory two-sided Jacobi eigen-solver for the Rayleigh-Ritz windows: `count` symmetric W x W
  * fp32 matrices (W even, <= 160), one CTA each. evals: eigenvalues sorted descending; Wt (optional):
  * eigenvectors as rows, same order. */

@@ -102,7 +102,7 @@ def test_transposed_and_bf16_outputs():
     _check(got, ref, exact=True)
     got, ref = _run(256, 512, 256, False, False, out_bf16=True)
     _check(got, ref, exact=False, out_bf16=True)
-    got, ref = _run(200, 300, 128, False, True, out_bf16=True, transposed=True)
+    got, ref = _run(200, 304, 128, False, True, out_bf16=True, transposed=True)
     _check(got, ref, exact=False, out_bf16=True)
 
 
@@ -116,10 +116,11 @@ def test_grouped_launch():
     from xkv_b200 import ops
 
     torch.manual_seed(1)
-    probs, refs, outs = [], [], []
+    probs, refs, outs, keep = [], [], [], []
     for (M, N, K) in [(128, 256, 128), (300, 100, 256), (640, 640, 512)]:
         A = torch.randint(-3, 4, (M, K), device="cuda").to(torch.bfloat16)
         B = torch.randint(-3, 4, (N, K), device="cuda").to(torch.bfloat16)
+        keep += [A, B]  # problems hold raw pointers: the operands must outlive the launch
         out = torch.full((M, N), float("nan"), device="cuda")
         probs.append(ops.make_problem([A], [B], out, M=M, N=N, K=K))
         refs.append(A.float() @ B.float().t())

@@ -80,7 +80,7 @@ def test_cholesky_inverse(l, cond):
         refs.append(s)
         ss.append(s.float().contiguous())
         linvs.append(torch.full((l, l), float("nan"), device="cuda"))
-    ops.cholesky_inverse(ss, linvs, pivot_floor=1e-9)
+    ops.cholesky_inverse(ss, linvs, shift=0.0, pivot_floor=1e-9)
     torch.cuda.synchronize()
     for s64, li in zip(refs, linvs):
         assert not torch.isnan(li).any()
@@ -88,6 +88,28 @@ def test_cholesky_inverse(l, cond):
         eye = li.double() @ s64 @ li.double().t()
         err = (eye - torch.eye(l, device="cuda", dtype=torch.float64)).abs().max().item()
         assert err < 5e-3 * max(1.0, cond / 1e3), f"Linv S Linv^T deviates from I by {err}"
+
+
+def test_cholesky_shift_keeps_indefinite_gram_finite():
+    """The fp32 Gram of a nearly rank-deficient sketch is indefinite; the shifted factorisation must stay
+    finite and equal the factor of S + shift*I."""
+    from xkv_b200 import ops
+
+    torch.manual_seed(3)
+    l = 192
+    u = torch.randn(l, 6, device="cuda", dtype=torch.float64)
+    s = u @ u.t()
+    d = s.diagonal().rsqrt()
+    s = s * d[:, None] * d[None, :] + 1e-6 * torch.randn(l, l, device="cuda", dtype=torch.float64)
+    s = 0.5 * (s + s.t())
+    s32 = s.float().contiguous()
+    linv = torch.full((l, l), float("nan"), device="cuda")
+    shift = 1e-3
+    ops.cholesky_inverse([s32.clone()], [linv], shift=shift, pivot_floor=1e-12)
+    torch.cuda.synchronize()
+    assert torch.isfinite(linv).all()
+    ref = torch.linalg.inv(torch.linalg.cholesky(s32.double() + shift * torch.eye(l, device="cuda", dtype=torch.float64)))
+    assert ((linv.double() - ref).norm() / ref.norm()).item() < 1e-2
 
 
 @pytest.mark.parametrize("w", [32, 128, 160])

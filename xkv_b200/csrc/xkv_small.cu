@@ -192,6 +192,7 @@ struct CholParams {
   int l, nblk, k;
   long long ld;
   float pivot_floor;
+  float shift;  // added to the diagonal (shifted Cholesky): S + shift*I
 };
 
 // C(64x64, 4x4 per thread) += A(64x64) * B(64x64)^T  [TRANSB=1]  or  A * B  [TRANSB=0]; operands in smem
@@ -229,6 +230,8 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(const __grid_constant__
   const int tid = threadIdx.x;
   const float* dblk = S + (static_cast<long long>(k) * NB) * p.ld + k * NB;
   load_block(D, dblk, p.ld);
+  __syncthreads();
+  if (tid < NB) D[tid][tid] += p.shift;
   __syncthreads();
   // --- in-place lower Cholesky of D ---
   for (int j = 0; j < NB; ++j) {
@@ -567,7 +570,7 @@ extern "C" int xkv_normalize_rows(float* const* Y_host, void* const* hi_host, vo
 }
 
 extern "C" int xkv_cholesky_inverse(float* const* S_host, float* const* Linv_host, int batch, int l, int64_t ld,
-                                    float pivot_floor, void* stream) {
+                                    float shift, float pivot_floor, void* stream) {
   XKV_REQUIRE(S_host && Linv_host && batch >= 1 && batch <= XKV_MAX_BATCH, "cholesky: bad batch");
   XKV_REQUIRE(l > 0 && l % NB == 0, "cholesky: l=%d must be a positive multiple of %d", l, NB);
   CholParams p;
@@ -581,6 +584,7 @@ extern "C" int xkv_cholesky_inverse(float* const* S_host, float* const* Linv_hos
   p.nblk = l / NB;
   p.ld = ld;
   p.pivot_floor = pivot_floor;
+  p.shift = shift;
   cudaStream_t st = as_stream(stream);
   zero_upper_kernel<<<dim3(64, batch), 256, 0, st>>>(p);
   XKV_LAUNCHED();

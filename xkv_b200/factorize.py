@@ -49,7 +49,8 @@ class FactorizeOptions:
     want_sigma: bool = True    # also diagonalise the leading window to report singular values
     gram_split_k: int = 1
     small_split_k: int = 8
-    pivot_floor: float = 1e-6
+    shifts: tuple = (3e-4, 1e-6, 1e-7)   # diagonal shift of CholeskyQR pass 0, 1, 2, ...
+    pivot_floor: float = 1e-12
     seed: int = 1234
     profile: bool = False
 
@@ -166,7 +167,7 @@ def factorize_batch(xs: Sequence[torch.Tensor], rank: int, opts: Optional[Factor
     def cholqr(npass: int) -> None:
         """f_cur <- orth(f_cur) by `npass` rounds of row-normalised CholeskyQR (rows = basis vectors)."""
         nonlocal f_cur, f_nxt
-        for _ in range(npass):
+        for ipass in range(npass):
             ops.normalize_rows(f_cur, lh, lm, ll)
             _gemm([
                 ops.make_problem([lh[b], lm[b], ll[b]], [lh[b], lm[b], ll[b]], s_slabs[b, 0], M=l, N=l, K=n,
@@ -176,7 +177,8 @@ def factorize_batch(xs: Sequence[torch.Tensor], rank: int, opts: Optional[Factor
             for b in range(B):
                 ops.reduce_slabs(s_slabs[b], s_mat[b], symmetrize=True)
             for chunk in _chunks(list(range(B)), 16):
-                ops.cholesky_inverse([s_mat[b] for b in chunk], [linv[b] for b in chunk], opts.pivot_floor)
+                ops.cholesky_inverse([s_mat[b] for b in chunk], [linv[b] for b in chunk],
+                                     opts.shifts[min(ipass, len(opts.shifts) - 1)], opts.pivot_floor)
             for b in range(B):
                 ops.split_bf16(linv[b], *linv_l[b])
             # Qt = Linv * Ys   (A: Linv limbs K-major;  B: Ys limbs as [K = l][N = n], MN-major)

@@ -173,12 +173,13 @@ def normalize_rows(ys: Sequence[torch.Tensor], hi=None, mid=None, lo=None) -> No
                                          rows, cols, ys[0].stride(0), ldo, _stream()))
 
 
-def cholesky_inverse(ss: Sequence[torch.Tensor], linvs: Sequence[torch.Tensor], pivot_floor: float = 1e-6) -> None:
-    """Batched S = L L^T and Linv = L^{-1} (see include/xkv_b200.h for what is left in S)."""
+def cholesky_inverse(ss: Sequence[torch.Tensor], linvs: Sequence[torch.Tensor], shift: float = 0.0,
+                     pivot_floor: float = 1e-12) -> None:
+    """Batched (S + shift*I) = L L^T and Linv = L^{-1} (see include/xkv_b200.h for what is left in S)."""
     _require_cuda(*ss, *linvs)
     l = ss[0].shape[0]
     check(_lib.load().xkv_cholesky_inverse(_ptr_array(ss), _ptr_array(linvs), len(ss), l, ss[0].stride(0),
-                                           C.c_float(pivot_floor), _stream()))
+                                           C.c_float(shift), C.c_float(pivot_floor), _stream()))
 
 
 def jacobi_eigh(ts: Sequence[torch.Tensor], evals: Sequence[torch.Tensor],
