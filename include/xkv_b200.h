@@ -113,6 +113,39 @@ XKV_API int xkv_jacobi_eigh(const float* const* T_host, float* const* evals_host
 XKV_API int xkv_convert_bf16(const float* src, int rows, int cols, int64_t ld, void* dst, int64_t ld_dst, void* dstT,
                              int64_t ld_dstT, void* stream);
 
+/* out[i] = sqrt(max(in[i], 0)) (Ritz values -> singular values) */
+XKV_API int xkv_sqrt_clamp(const float* in, float* out, int count, void* stream);
+
+/* ---- (2) the factorisation driver: replaces fake_svd (cache:11-29) for a batch ------------------
+ * X[b] (m x n bf16, row stride ldx)  ~=  A[b] (m x rank bf16) * Vt[b] (rank x n bf16); V[b] (n x rank) is
+ * Vt transposed (the layout the decode kernel reads). sigma[b] (optional) receives
+ * xkv_factorize_sigma_count() leading singular-value estimates. Pure host code: enqueues the kernels
+ * above on `stream`. stage_events_host (optional): 6 cudaEvent_t recorded at start / after Gram /
+ * range finder / power iterations / Rayleigh-Ritz / projection. */
+typedef struct xkv_factorize_options {
+  int32_t power_iters;    /* power steps on G after the range finder (default 6) */
+  int32_t oversample;     /* extra sketch columns; sketch width l = round_up(rank + oversample, 64) */
+  int32_t first_passes;   /* CholeskyQR passes after the range finder (3) */
+  int32_t passes;         /* CholeskyQR passes after a power step (2) */
+  int32_t final_passes;   /* CholeskyQR passes after the last power step (3) */
+  int32_t window;         /* Rayleigh-Ritz window width, <= 160 */
+  int32_t jacobi_sweeps;
+  int32_t rayleigh_ritz;  /* 0: keep the first `rank` basis vectors as they are */
+  int32_t want_sigma;     /* also diagonalise the leading window to report singular values */
+  int32_t gram_split_k;
+  int32_t small_split_k;
+  float shifts[4];        /* diagonal shift of CholeskyQR pass 0,1,2,3+ */
+  float pivot_floor;
+  uint64_t seed;
+} xkv_factorize_options;
+XKV_API void xkv_factorize_default_options(xkv_factorize_options* opts);
+XKV_API size_t xkv_factorize_workspace_bytes(int batch, int m, int n, int rank, const xkv_factorize_options* opts);
+XKV_API int xkv_factorize_sigma_count(int rank, const xkv_factorize_options* opts);
+XKV_API int xkv_factorize_batch(const void* const* X_host, int batch, int m, int n, int64_t ldx, int rank,
+                                const xkv_factorize_options* opts, void* const* A_host, void* const* Vt_host,
+                                void* const* V_host, float* const* sigma_host, void* workspace,
+                                size_t workspace_bytes, void* const* stage_events_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

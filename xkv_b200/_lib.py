@@ -47,6 +47,27 @@ class GemmProblem(C.Structure):
     ]
 
 
+class FactorizeOptions(C.Structure):
+    """Mirror of ``xkv_factorize_options`` (include/xkv_b200.h)."""
+
+    _fields_ = [
+        ("power_iters", C.c_int32),
+        ("oversample", C.c_int32),
+        ("first_passes", C.c_int32),
+        ("passes", C.c_int32),
+        ("final_passes", C.c_int32),
+        ("window", C.c_int32),
+        ("jacobi_sweeps", C.c_int32),
+        ("rayleigh_ritz", C.c_int32),
+        ("want_sigma", C.c_int32),
+        ("gram_split_k", C.c_int32),
+        ("small_split_k", C.c_int32),
+        ("shifts", C.c_float * 4),
+        ("pivot_floor", C.c_float),
+        ("seed", C.c_uint64),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/xkv_b200.h declares must appear here
 _vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 _pp = C.POINTER(C.c_void_p)
@@ -64,6 +85,12 @@ SIGNATURES = {
     "xkv_cholesky_inverse": (_i, [_pp, _pp, _i, _i, _i64, _f, _f, _vp]),
     "xkv_jacobi_eigh": (_i, [_pp, _pp, _pp, _i, _i, _i64, _i64, _i, _vp]),
     "xkv_convert_bf16": (_i, [_vp, _i, _i, _i64, _vp, _i64, _vp, _i64, _vp]),
+    "xkv_sqrt_clamp": (_i, [_vp, _vp, _i, _vp]),
+    "xkv_factorize_default_options": (None, [C.POINTER(FactorizeOptions)]),
+    "xkv_factorize_workspace_bytes": (_sz, [_i, _i, _i, _i, C.POINTER(FactorizeOptions)]),
+    "xkv_factorize_sigma_count": (_i, [_i, C.POINTER(FactorizeOptions)]),
+    "xkv_factorize_batch": (_i, [_pp, _i, _i, _i, _i64, _i, C.POINTER(FactorizeOptions), _pp, _pp, _pp, _pp, _vp, _sz,
+                                 _pp, _vp]),
 }
 
 

@@ -1,0 +1,395 @@
+// xkv_b200 — stream-ordered driver of the low-rank factorisation (replaces fake_svd,
+// fake_layer_merge_dynamic_cache.py:11-29, for a batch of equally-shaped group matrices).
+//
+//   X (m x n bf16)  ~=  A (m x r bf16) * Vt (r x n bf16),   A = X V
+//
+// Pure host code: it carves the caller's workspace and enqueues the kernels of xkv_gemm.cu /
+// xkv_small.cu on the caller's stream (no allocation, no synchronisation).  The algorithm is
+// documented in xkv_b200/factorize.py and DESIGN.md: Gram -> Gaussian range finder -> shifted
+// CholeskyQR -> power steps on G -> windowed Rayleigh-Ritz (shared-memory Jacobi) -> A = X V.
+#include <cuda_bf16.h>
+
+#include <vector>
+
+#include "xkv_host.h"
+
+namespace xkv {
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int round_up_int(int x, int k) { return (x + k - 1) / k * k; }
+
+struct Bump {
+  char* base;
+  size_t off, cap;
+  bool overflow;
+  void* take(size_t bytes) {
+    off = align_up(off, 1024);
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    if (base && off > cap) overflow = true;
+    return p;
+  }
+  float* f32(size_t n) { return static_cast<float*>(take(n * 4)); }
+  void* bf16(size_t n) { return take(n * 2); }
+};
+
+struct Plan {
+  int B, m, n, r, l, W, wl, wr, r0, nw, sk, skw, gs;
+  bool rr;
+  // per-matrix buffers
+  void* g_limb[XKV_MAX_BATCH][3];
+  float* f_a[XKV_MAX_BATCH];
+  float* f_b[XKV_MAX_BATCH];
+  void* lh[XKV_MAX_BATCH];
+  void* lm[XKV_MAX_BATCH];
+  void* ll[XKV_MAX_BATCH];
+  float* s_slabs[XKV_MAX_BATCH];
+  float* s_mat[XKV_MAX_BATCH];
+  float* linv[XKV_MAX_BATCH];
+  void* linv_l[XKV_MAX_BATCH][3];
+  float* yw[XKV_MAX_BATCH][2];
+  void* yw_l[XKV_MAX_BATCH][2][3];
+  float* t_slabs[XKV_MAX_BATCH][2];
+  float* t_mat[XKV_MAX_BATCH][2];
+  float* evals[XKV_MAX_BATCH][2];
+  float* wt[XKV_MAX_BATCH];
+  void* wsel_l[XKV_MAX_BATCH][3];
+  // shared
+  float* gram_slabs;  // [B][gs][n][n]
+  float* g32;
+  size_t bytes;
+};
+
+static int make_plan(Plan& P, Bump& bump, int B, int m, int n, int rank, const xkv_factorize_options& o) {
+  XKV_REQUIRE(B >= 1 && B <= XKV_MAX_BATCH, "factorize: batch %d out of range (1..%d)", B, XKV_MAX_BATCH);
+  XKV_REQUIRE(n % 8 == 0, "factorize: n=%d must be a multiple of 8", n);
+  P.B = B;
+  P.m = m;
+  P.n = n;
+  P.r = rank;
+  P.l = round_up_int(rank + o.oversample, 64);
+  XKV_REQUIRE(rank > 0 && rank <= m && P.l <= n, "factorize: rank %d (sketch %d) does not fit a %d x %d matrix", rank,
+              P.l, m, n);
+  P.gs = o.gram_split_k < 1 ? 1 : o.gram_split_k;
+  const int nkb = (n + 63) / 64;
+  P.sk = o.small_split_k < 1 ? 1 : (o.small_split_k > nkb ? nkb : o.small_split_k);
+  P.skw = nkb < 16 ? nkb : 16;
+  // Rayleigh-Ritz window [r0, r0 + W) straddling column r
+  P.wr = P.l - rank;
+  int W = o.window < P.l ? o.window : P.l;
+  if (W > 160) W = 160;
+  W -= W % 2;
+  int wl = W - P.wr;
+  if (wl > rank) wl = rank;
+  P.rr = o.rayleigh_ritz && wl > 0;
+  if (P.rr) {
+    W = wl + P.wr;
+    if (W % 2) {
+      --wl;
+      --W;
+    }
+    P.rr = wl > 0;
+  }
+  P.W = W;
+  P.wl = wl;
+  P.r0 = rank - wl;
+  P.nw = P.rr ? (o.want_sigma ? 2 : 1) : 0;
+  const size_t l = P.l, nn = n;
+  for (int b = 0; b < B; ++b) {
+    for (int i = 0; i < 3; ++i) P.g_limb[b][i] = bump.bf16(nn * nn);
+    P.f_a[b] = bump.f32(l * nn);
+    P.f_b[b] = bump.f32(l * nn);
+    P.lh[b] = bump.bf16(l * nn);
+    P.lm[b] = bump.bf16(l * nn);
+    P.ll[b] = bump.bf16(l * nn);
+    P.s_slabs[b] = bump.f32(static_cast<size_t>(P.sk) * l * l);
+    P.s_mat[b] = bump.f32(l * l);
+    P.linv[b] = bump.f32(l * l);
+    for (int i = 0; i < 3; ++i) P.linv_l[b][i] = bump.bf16(l * l);
+    for (int w = 0; w < P.nw; ++w) {
+      P.yw[b][w] = bump.f32(static_cast<size_t>(W) * nn);
+      for (int i = 0; i < 3; ++i) P.yw_l[b][w][i] = bump.bf16(static_cast<size_t>(W) * nn);
+      P.t_slabs[b][w] = bump.f32(static_cast<size_t>(P.skw) * W * W);
+      P.t_mat[b][w] = bump.f32(static_cast<size_t>(W) * W);
+      P.evals[b][w] = bump.f32(W);
+    }
+    if (P.rr) {
+      P.wt[b] = bump.f32(static_cast<size_t>(W) * W);
+      for (int i = 0; i < 3; ++i) P.wsel_l[b][i] = bump.bf16(static_cast<size_t>(wl) * W);
+    }
+  }
+  P.gram_slabs = bump.f32(static_cast<size_t>(B) * P.gs * nn * nn);
+  P.g32 = bump.f32(nn * nn);
+  P.bytes = align_up(bump.off, 1024);
+  return 0;
+}
+
+static const uint8_t T6A[6] = {0, 0, 1, 1, 0, 2}, T6B[6] = {0, 1, 0, 1, 2, 0};
+
+static xkv_gemm_problem problem(const void* a0, const void* a1, const void* a2, long long lda, int a_mn,
+                                const void* b0, const void* b1, const void* b2, long long ldb, int b_mn, void* D,
+                                long long ldd, int M, int N, int K, int nterms) {
+  xkv_gemm_problem p;
+  std::memset(&p, 0, sizeof(p));
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.num_terms = nterms;
+  p.a_mn_major = a_mn;
+  p.b_mn_major = b_mn;
+  p.A[0] = a0;
+  p.A[1] = a1;
+  p.A[2] = a2;
+  p.B[0] = b0;
+  p.B[1] = b1;
+  p.B[2] = b2;
+  p.lda = lda;
+  p.ldb = ldb;
+  for (int t = 0; t < nterms; ++t) {
+    p.term_a[t] = T6A[t];
+    p.term_b[t] = T6B[t];
+  }
+  p.D = D;
+  p.ldd = ldd;
+  p.split_k = 1;
+  return p;
+}
+
+static int run_gemms(std::vector<xkv_gemm_problem>& ps, void* stream) {
+  for (size_t i = 0; i < ps.size(); i += XKV_MAX_GEMM_PROBLEMS) {
+    const int cnt = static_cast<int>(ps.size() - i < XKV_MAX_GEMM_PROBLEMS ? ps.size() - i : XKV_MAX_GEMM_PROBLEMS);
+    int rc = xkv_gemm_grouped(ps.data() + i, cnt, stream);
+    if (rc) return rc;
+  }
+  ps.clear();
+  return 0;
+}
+
+#define XKV_TRY(expr)      \
+  do {                     \
+    int _rc = (expr);      \
+    if (_rc) return _rc;   \
+  } while (0)
+
+static inline const __nv_bfloat16* row_bf16(const void* base, long long row, long long ld) {
+  return static_cast<const __nv_bfloat16*>(base) + row * ld;
+}
+
+}  // namespace xkv
+
+using namespace xkv;
+
+extern "C" void xkv_factorize_default_options(xkv_factorize_options* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->power_iters = 6;
+  o->oversample = 64;
+  o->first_passes = 3;
+  o->passes = 2;
+  o->final_passes = 3;
+  o->window = 160;
+  o->jacobi_sweeps = 8;
+  o->rayleigh_ritz = 1;
+  o->want_sigma = 1;
+  o->gram_split_k = 1;
+  o->small_split_k = 8;
+  o->shifts[0] = 3e-4f;
+  o->shifts[1] = 1e-6f;
+  o->shifts[2] = 1e-7f;
+  o->shifts[3] = 1e-7f;
+  o->pivot_floor = 1e-12f;
+  o->seed = 1234;
+}
+
+extern "C" size_t xkv_factorize_workspace_bytes(int batch, int m, int n, int rank, const xkv_factorize_options* opts) {
+  xkv_factorize_options o;
+  if (opts)
+    o = *opts;
+  else
+    xkv_factorize_default_options(&o);
+  Plan P;
+  Bump bump{nullptr, 0, 0, false};
+  if (make_plan(P, bump, batch, m, n, rank, o)) return 0;
+  return P.bytes;
+}
+
+extern "C" int xkv_factorize_sigma_count(int rank, const xkv_factorize_options* opts) {
+  xkv_factorize_options o;
+  if (opts)
+    o = *opts;
+  else
+    xkv_factorize_default_options(&o);
+  Plan P;
+  Bump bump{nullptr, 0, 0, false};
+  // m, n large enough not to trip the fit check: only the window arithmetic matters here
+  if (make_plan(P, bump, 1, 1 << 20, 1 << 20, rank, o)) return 0;
+  return (P.rr && o.want_sigma) ? P.W : 0;
+}
+
+extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, int n, int64_t ldx, int rank,
+                                   const xkv_factorize_options* opts, void* const* A_host, void* const* Vt_host,
+                                   void* const* V_host, float* const* sigma_host, void* workspace,
+                                   size_t workspace_bytes, void* const* stage_events_host, void* stream) {
+  xkv_factorize_options o;
+  if (opts)
+    o = *opts;
+  else
+    xkv_factorize_default_options(&o);
+  XKV_REQUIRE(X_host && A_host && Vt_host && V_host && workspace, "factorize: null argument");
+  static thread_local Plan P;
+  Bump bump{static_cast<char*>(workspace), 0, workspace_bytes, false};
+  XKV_TRY(make_plan(P, bump, batch, m, n, rank, o));
+  XKV_REQUIRE(!bump.overflow && P.bytes <= workspace_bytes, "factorize: workspace too small (%zu < %zu bytes)",
+              workspace_bytes, P.bytes);
+  XKV_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "factorize: workspace must be 1024-byte aligned");
+  const int B = batch, l = P.l, r = rank, W = P.W, wl = P.wl, r0 = P.r0;
+  const long long nn = n;
+  cudaStream_t st = as_stream(stream);
+  int ev = 0;
+  auto mark = [&]() -> int {
+    if (stage_events_host && stage_events_host[ev])
+      XKV_CHECK_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(stage_events_host[ev]), st));
+    ++ev;
+    return 0;
+  };
+  std::vector<xkv_gemm_problem> ps;
+  XKV_TRY(mark());  // 0: start
+
+  // ---- 1. Gram matrices and their bf16 limbs ----
+  for (int b = 0; b < B; ++b) {
+    xkv_gemm_problem p = problem(X_host[b], nullptr, nullptr, ldx, 1, X_host[b], nullptr, nullptr, ldx, 1,
+                                 P.gram_slabs + static_cast<size_t>(b) * P.gs * nn * nn, nn, n, n, m, 1);
+    p.sym_upper = 1;
+    p.split_k = P.gs;
+    p.split_stride = nn * nn;
+    ps.push_back(p);
+  }
+  XKV_TRY(run_gemms(ps, stream));
+  for (int b = 0; b < B; ++b) {
+    XKV_TRY(xkv_reduce_slabs(P.gram_slabs + static_cast<size_t>(b) * P.gs * nn * nn, P.gs, nn * nn, n, n, nn, 1, P.g32,
+                             nn, stream));
+    XKV_TRY(xkv_split_bf16(P.g32, n, n, nn, P.g_limb[b][0], P.g_limb[b][1], P.g_limb[b][2], nn, stream));
+  }
+  XKV_TRY(mark());  // 1: gram
+
+  float** cur = P.f_a;
+  float** nxt = P.f_b;
+  auto swap_bufs = [&]() {
+    float** t = cur;
+    cur = nxt;
+    nxt = t;
+  };
+  // cur <- orth(cur): row-normalised, shifted CholeskyQR
+  auto cholqr = [&](int npass) -> int {
+    for (int ip = 0; ip < npass; ++ip) {
+      XKV_TRY(xkv_normalize_rows(cur, P.lh, P.lm, P.ll, B, l, n, nn, nn, stream));
+      for (int b = 0; b < B; ++b) {
+        xkv_gemm_problem p = problem(P.lh[b], P.lm[b], P.ll[b], nn, 0, P.lh[b], P.lm[b], P.ll[b], nn, 0, P.s_slabs[b], l,
+                                     l, l, n, 6);
+        p.sym_upper = 1;
+        p.split_k = P.sk;
+        p.split_stride = static_cast<long long>(l) * l;
+        ps.push_back(p);
+      }
+      XKV_TRY(run_gemms(ps, stream));
+      for (int b = 0; b < B; ++b)
+        XKV_TRY(xkv_reduce_slabs(P.s_slabs[b], P.sk, static_cast<long long>(l) * l, l, l, l, 1, P.s_mat[b], l, stream));
+      XKV_TRY(xkv_cholesky_inverse(P.s_mat, P.linv, B, l, l, o.shifts[ip < 3 ? ip : 3], o.pivot_floor, stream));
+      for (int b = 0; b < B; ++b)
+        XKV_TRY(xkv_split_bf16(P.linv[b], l, l, l, P.linv_l[b][0], P.linv_l[b][1], P.linv_l[b][2], l, stream));
+      for (int b = 0; b < B; ++b)
+        ps.push_back(problem(P.linv_l[b][0], P.linv_l[b][1], P.linv_l[b][2], l, 0, P.lh[b], P.lm[b], P.ll[b], nn, 1,
+                             nxt[b], nn, l, n, l, 6));
+      XKV_TRY(run_gemms(ps, stream));
+      swap_bufs();
+    }
+    return 0;
+  };
+  // cur <- (limbs lh/lm of the current basis) * G
+  auto apply_gram = [&](int nterms) -> int {
+    for (int b = 0; b < B; ++b)
+      ps.push_back(problem(P.lh[b], P.lm[b], P.ll[b], nn, 0, P.g_limb[b][0], P.g_limb[b][1], P.g_limb[b][2], nn, 0,
+                           nxt[b], nn, l, n, n, nterms));
+    XKV_TRY(run_gemms(ps, stream));
+    swap_bufs();
+    return 0;
+  };
+
+  // ---- 2-3. Gaussian range finder ----
+  for (int b = 0; b < B; ++b) XKV_TRY(xkv_fill_gaussian_bf16(P.lh[b], l, n, nn, o.seed + 7919ull * b, stream));
+  XKV_TRY(apply_gram(1));
+  XKV_TRY(cholqr(o.first_passes));
+  XKV_TRY(mark());  // 2: range finder
+
+  // ---- 4. power steps ----
+  for (int it = 0; it < o.power_iters; ++it) {
+    for (int b = 0; b < B; ++b) XKV_TRY(xkv_split_bf16(cur[b], l, n, nn, P.lh[b], P.lm[b], nullptr, nn, stream));
+    XKV_TRY(apply_gram(3));
+    XKV_TRY(cholqr(it == o.power_iters - 1 ? o.final_passes : o.passes));
+  }
+  XKV_TRY(mark());  // 3: power iterations
+
+  // ---- 5. windowed Rayleigh-Ritz ----
+  if (P.rr) {
+    const int nw = P.nw;
+    const int w0s[2] = {r0, 0};
+    for (int b = 0; b < B; ++b) XKV_TRY(xkv_split_bf16(cur[b], l, n, nn, P.lh[b], P.lm[b], P.ll[b], nn, stream));
+    for (int b = 0; b < B; ++b)
+      for (int w = 0; w < nw; ++w)
+        ps.push_back(problem(row_bf16(P.lh[b], w0s[w], nn), row_bf16(P.lm[b], w0s[w], nn), row_bf16(P.ll[b], w0s[w], nn),
+                             nn, 0, P.g_limb[b][0], P.g_limb[b][1], P.g_limb[b][2], nn, 0, P.yw[b][w], nn, W, n, n, 6));
+    XKV_TRY(run_gemms(ps, stream));
+    for (int b = 0; b < B; ++b)
+      for (int w = 0; w < nw; ++w)
+        XKV_TRY(xkv_split_bf16(P.yw[b][w], W, n, nn, P.yw_l[b][w][0], P.yw_l[b][w][1], P.yw_l[b][w][2], nn, stream));
+    for (int b = 0; b < B; ++b)
+      for (int w = 0; w < nw; ++w) {
+        xkv_gemm_problem p =
+            problem(row_bf16(P.lh[b], w0s[w], nn), row_bf16(P.lm[b], w0s[w], nn), row_bf16(P.ll[b], w0s[w], nn), nn, 0,
+                    P.yw_l[b][w][0], P.yw_l[b][w][1], P.yw_l[b][w][2], nn, 0, P.t_slabs[b][w], W, W, W, n, 6);
+        p.split_k = P.skw;
+        p.split_stride = static_cast<long long>(W) * W;
+        ps.push_back(p);
+      }
+    XKV_TRY(run_gemms(ps, stream));
+    const float* tptr[2 * XKV_MAX_BATCH];
+    float* eptr[2 * XKV_MAX_BATCH];
+    float* wptr[2 * XKV_MAX_BATCH];
+    int cnt = 0;
+    for (int b = 0; b < B; ++b)
+      for (int w = 0; w < nw; ++w) {
+        XKV_TRY(xkv_reduce_slabs(P.t_slabs[b][w], P.skw, static_cast<long long>(W) * W, W, W, W, 0, P.t_mat[b][w], W,
+                                 stream));
+        tptr[cnt] = P.t_mat[b][w];
+        eptr[cnt] = P.evals[b][w];
+        wptr[cnt] = (w == 0) ? P.wt[b] : nullptr;
+        ++cnt;
+      }
+    XKV_TRY(xkv_jacobi_eigh(tptr, eptr, wptr, cnt, W, W, W, o.jacobi_sweeps, stream));
+    // rows [r0, r) of the basis <- top-wl Ritz vectors of the window: Vw = Wsel * Qw
+    for (int b = 0; b < B; ++b)
+      XKV_TRY(xkv_split_bf16(P.wt[b], wl, W, W, P.wsel_l[b][0], P.wsel_l[b][1], P.wsel_l[b][2], W, stream));
+    for (int b = 0; b < B; ++b)
+      ps.push_back(problem(P.wsel_l[b][0], P.wsel_l[b][1], P.wsel_l[b][2], W, 0, row_bf16(P.lh[b], r0, nn),
+                           row_bf16(P.lm[b], r0, nn), row_bf16(P.ll[b], r0, nn), nn, 1, cur[b] + static_cast<size_t>(r0) * nn,
+                           nn, wl, n, W, 6));
+    XKV_TRY(run_gemms(ps, stream));
+    if (o.want_sigma && sigma_host)
+      for (int b = 0; b < B; ++b)
+        if (sigma_host[b]) XKV_TRY(xkv_sqrt_clamp(P.evals[b][1], sigma_host[b], W, stream));
+  }
+  XKV_TRY(mark());  // 4: Rayleigh-Ritz
+
+  // ---- 6. right factor in bf16, both layouts ----
+  for (int b = 0; b < B; ++b) XKV_TRY(xkv_convert_bf16(cur[b], r, n, nn, Vt_host[b], nn, V_host[b], r, stream));
+  // ---- 7. projection A = X V ----
+  for (int b = 0; b < B; ++b) {
+    xkv_gemm_problem p =
+        problem(X_host[b], nullptr, nullptr, ldx, 0, Vt_host[b], nullptr, nullptr, nn, 0, A_host[b], r, m, r, n, 1);
+    p.out_bf16 = 1;
+    ps.push_back(p);
+  }
+  XKV_TRY(run_gemms(ps, stream));
+  XKV_TRY(mark());  // 5: projection
+  return 0;
+}

@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ PackP
 static int launch_pack(int dir, const void* const* layer_ptrs, int num_layers, int bs, int heads, int seq,
                        int head_dim, long long stride_b, long long stride_h, long long stride_s, void* X,
                        void* stream) {
+  if (seq == 0 && num_layers >= 1) return 0;  // empty prefill: nothing to gather (pointers may be null)
   XKV_REQUIRE(layer_ptrs != nullptr && X != nullptr, "pack: null pointer");
   XKV_REQUIRE(num_layers >= 1 && num_layers <= XKV_MAX_GROUP_LAYERS, "pack: num_layers=%d (max %d)", num_layers,
               XKV_MAX_GROUP_LAYERS);

@@ -488,6 +488,11 @@ __global__ void __launch_bounds__(256) convert_bf16_kernel(const float* __restri
   }
 }
 
+__global__ void sqrt_clamp_kernel(const float* __restrict__ in, float* __restrict__ out, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = sqrtf(fmaxf(in[i], 0.f));
+}
+
 static int sm_count() {
   static int sms = 0;
   if (sms == 0) {
@@ -635,6 +640,13 @@ extern "C" int xkv_convert_bf16(const float* src, int rows, int cols, int64_t ld
   dim3 grid((cols + 31) / 32, (rows + 31) / 32);
   convert_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, rows, cols, ld, static_cast<__nv_bfloat16*>(dst),
                                                            ld_dst, static_cast<__nv_bfloat16*>(dstT), ld_dstT);
+  XKV_LAUNCHED();
+  return 0;
+}
+
+extern "C" int xkv_sqrt_clamp(const float* in, float* out, int count, void* stream) {
+  XKV_REQUIRE(in && out && count > 0, "sqrt_clamp: bad arguments");
+  sqrt_clamp_kernel<<<(count + 255) / 256, 256, 0, as_stream(stream)>>>(in, out, count);
   XKV_LAUNCHED();
   return 0;
 }

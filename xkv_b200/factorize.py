@@ -30,9 +30,11 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
+import ctypes as C
+
 import torch
 
-from . import ops
+from . import _lib, ops
 from ._lib import XkvError
 
 
@@ -110,8 +112,91 @@ class _Timer:
         return out
 
 
-def factorize_batch(xs: Sequence[torch.Tensor], rank: int, opts: Optional[FactorizeOptions] = None) -> List[Factors]:
-    """Factorise a batch of equally-shaped token-major matrices (m x n bf16) at rank `rank`."""
+_STAGES = ("gram", "range_finder", "power_iters", "rayleigh_ritz", "project")
+
+
+def _c_options(opts: FactorizeOptions) -> "_lib.FactorizeOptions":
+    o = _lib.FactorizeOptions()
+    _lib.load().xkv_factorize_default_options(C.byref(o))
+    o.power_iters, o.oversample = opts.power_iters, opts.oversample
+    o.first_passes, o.passes, o.final_passes = opts.first_passes, opts.passes, opts.final_passes
+    o.window, o.jacobi_sweeps = opts.window, opts.jacobi_sweeps
+    o.rayleigh_ritz, o.want_sigma = int(opts.rayleigh_ritz), int(opts.want_sigma)
+    o.gram_split_k, o.small_split_k = opts.gram_split_k, opts.small_split_k
+    for i in range(4):
+        o.shifts[i] = opts.shifts[min(i, len(opts.shifts) - 1)]
+    o.pivot_floor = opts.pivot_floor
+    o.seed = opts.seed
+    return o
+
+
+def workspace_bytes(batch: int, m: int, n: int, rank: int, opts: Optional[FactorizeOptions] = None) -> int:
+    o = _c_options(opts or FactorizeOptions())
+    return int(_lib.load().xkv_factorize_workspace_bytes(batch, m, n, rank, C.byref(o)))
+
+
+def factorize_batch(xs: Sequence[torch.Tensor], rank: int, opts: Optional[FactorizeOptions] = None,
+                    workspace: Optional[torch.Tensor] = None) -> List[Factors]:
+    """Factorise a batch of equally-shaped token-major matrices (m x n bf16) at rank `rank`.
+
+    One call into the library's stream-ordered driver (xkv_factorize_batch); batches larger than the
+    C-ABI's per-call limit are processed in chunks that reuse one workspace."""
+    opts = opts or FactorizeOptions()
+    if len(xs) == 0:
+        return []
+    lib = _lib.load()
+    m, n = xs[0].shape
+    dev = xs[0].device
+    for x in xs:
+        if not x.is_cuda:
+            raise XkvError("factorize: CUDA tensors required (no CPU path)")
+        if x.dtype != torch.bfloat16 or tuple(x.shape) != (m, n) or x.stride(1) != 1 or x.stride(0) != xs[0].stride(0):
+            raise XkvError("factorize: inputs must be equally-shaped row-major bf16 matrices")
+    r = int(rank)
+    co = _c_options(opts)
+    chunk = min(len(xs), _lib.MAX_BATCH)
+    need = int(lib.xkv_factorize_workspace_bytes(chunk, m, n, r, C.byref(co)))
+    if need == 0:
+        raise XkvError(lib.xkv_last_error().decode() or "factorize: invalid problem")
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    nsig = int(lib.xkv_factorize_sigma_count(r, C.byref(co)))
+    out: List[Factors] = []
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    all_events = []
+    for lo in range(0, len(xs), chunk):
+        part = xs[lo:lo + chunk]
+        nb = len(part)
+        a = [torch.empty(m, r, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
+        vt = [torch.empty(r, n, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
+        v = [torch.empty(n, r, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
+        sig = [torch.empty(nsig, dtype=torch.float32, device=dev) if nsig else None for _ in range(nb)]
+        events = [torch.cuda.Event(enable_timing=True) for _ in range(6)] if opts.profile else None
+        ev_arr = None
+        if events is not None:
+            for e in events:
+                e.record()  # torch creates the cudaEvent lazily; recording materialises the handle
+            ev_arr = (C.c_void_p * 6)(*[e.cuda_event for e in events])
+            all_events.append(events)
+        _lib.check(lib.xkv_factorize_batch(
+            ops._ptr_array(part), nb, m, n, part[0].stride(0), r, C.byref(co), ops._ptr_array(a), ops._ptr_array(vt),
+            ops._ptr_array(v), ops._ptr_array(sig) if nsig else None, C.c_void_p(workspace.data_ptr()),
+            workspace.numel() * workspace.element_size(), ev_arr, stream))
+        for b in range(nb):
+            out.append(Factors(A=a[b], Vt=vt[b], V=v[b], rank=r, sigma_lead=sig[b]))
+    if opts.profile:
+        torch.cuda.synchronize()
+        timings: Dict[str, float] = {}
+        for events in all_events:
+            for i, name in enumerate(_STAGES):
+                timings[name] = timings.get(name, 0.0) + events[i].elapsed_time(events[i + 1])
+        for f in out:
+            f.timings = timings
+    return out
+
+
+def factorize_batch_py(xs: Sequence[torch.Tensor], rank: int, opts: Optional[FactorizeOptions] = None) -> List[Factors]:
+    """Same pipeline orchestrated from Python, kernel by kernel (debug aid and cross-check of the C driver)."""
     opts = opts or FactorizeOptions()
     if len(xs) == 0:
         return []
