@@ -120,8 +120,8 @@ XKV_API int xkv_sqrt_clamp(const float* in, float* out, int count, void* stream)
  * X[b] (m x n bf16, row stride ldx)  ~=  A[b] (m x rank bf16) * Vt[b] (rank x n bf16); V[b] (n x rank) is
  * Vt transposed (the layout the decode kernel reads). sigma[b] (optional) receives
  * xkv_factorize_sigma_count() leading singular-value estimates. Pure host code: enqueues the kernels
- * above on `stream`. stage_events_host (optional): 6 cudaEvent_t recorded at start / after Gram /
- * range finder / power iterations / Rayleigh-Ritz / projection. */
+ * above on `stream`. stage_events_host (optional): 7 cudaEvent_t recorded at start / after the Gram
+ * GEMM / Gram reduce+split / range finder / power iterations / Rayleigh-Ritz / projection. */
 typedef struct xkv_factorize_options {
   int32_t power_iters;    /* power steps on G after the range finder (default 6) */
   int32_t oversample;     /* extra sketch columns; sketch width l = round_up(rank + oversample, 64) */

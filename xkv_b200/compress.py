@@ -1,0 +1,90 @@
+"""Prefill compression of whole layer groups: gather (pack) + factorise, K and V on separate streams.
+
+This is the device-side body of ``FakeLayerMergingCache.grouped_layer_merging``
+(reference fake_layer_merge_dynamic_cache.py:155-208) for many groups at once: where the reference
+loops ``cat -> fake_svd(K) -> fake_svd(V) -> split`` per group with host synchronisation after each
+(:205-208), all groups' K matrices form one batch and all V matrices another, the two batches run
+concurrently on two CUDA streams, and nothing synchronises with the host.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import factorize, ops
+from ._lib import XkvError
+
+
+@dataclass
+class GroupFactors:
+    """Compressed form of one layer group (either slot may stay dense when its merge flag is off)."""
+
+    layers: List[int]
+    key: Optional[factorize.Factors]
+    value: Optional[factorize.Factors]
+
+
+_side_streams = {}
+
+
+def _side_stream(device: torch.device) -> torch.cuda.Stream:
+    key = (device.type, device.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
+def pack_groups(groups: Sequence[Sequence[torch.Tensor]], out: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
+    """One token-major matrix (S, G*H*D) per group (batch size 1)."""
+    xs = []
+    for i, layers in enumerate(groups):
+        if layers[0].shape[0] != 1:
+            raise XkvError("compress: batch size 1 per call (the reference's batched SVD is one SVD per sample)")
+        x = ops.pack_group(layers, out=None if out is None else out[i][None])
+        xs.append(x[0])
+    return xs
+
+
+def compress_groups(
+    keys: Sequence[Sequence[torch.Tensor]],
+    values: Sequence[Sequence[torch.Tensor]],
+    rank_k: Optional[int],
+    rank_v: Optional[int],
+    merge_key: bool = True,
+    merge_value: bool = True,
+    opts: Optional[factorize.FactorizeOptions] = None,
+    layer_ids: Optional[Sequence[Sequence[int]]] = None,
+    two_streams: bool = True,
+) -> List[GroupFactors]:
+    """Compress equally-shaped layer groups. keys[g][i] / values[g][i]: (1, H, S, D) bf16 of layer i of
+    group g (keys PRE-RoPE, as the reference hands them over, llama.py:49)."""
+    ng = len(keys)
+    if ng == 0:
+        return []
+    dev = keys[0][0].device
+    main = torch.cuda.current_stream(dev)
+    kf: List[Optional[factorize.Factors]] = [None] * ng
+    vf: List[Optional[factorize.Factors]] = [None] * ng
+    side = _side_stream(dev) if (two_streams and merge_key and merge_value) else None
+    if merge_value:
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                xv = pack_groups(values)
+                vf = factorize.factorize_batch(xv, rank_v, opts)
+                for x in xv:
+                    x.record_stream(side)
+        else:
+            vf = factorize.factorize_batch(pack_groups(values), rank_v, opts)
+    if merge_key:
+        kf = factorize.factorize_batch(pack_groups(keys), rank_k, opts)
+    if side is not None:
+        main.wait_stream(side)
+        for f in vf:
+            for t in (f.A, f.Vt, f.V, f.sigma_lead):
+                if t is not None:
+                    t.record_stream(main)
+    ids = layer_ids if layer_ids is not None else [list(range(len(g))) for g in keys]
+    return [GroupFactors(layers=list(ids[g]), key=kf[g], value=vf[g]) for g in range(ng)]

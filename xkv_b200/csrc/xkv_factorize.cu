@@ -265,12 +265,13 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
     ps.push_back(p);
   }
   XKV_TRY(run_gemms(ps, stream));
+  XKV_TRY(mark());  // 1: Gram GEMM (the dominant kernel, timed on its own for the roofline)
   for (int b = 0; b < B; ++b) {
     XKV_TRY(xkv_reduce_slabs(P.gram_slabs + static_cast<size_t>(b) * P.gs * nn * nn, P.gs, nn * nn, n, n, nn, 1, P.g32,
                              nn, stream));
     XKV_TRY(xkv_split_bf16(P.g32, n, n, nn, P.g_limb[b][0], P.g_limb[b][1], P.g_limb[b][2], nn, stream));
   }
-  XKV_TRY(mark());  // 1: gram
+  XKV_TRY(mark());  // 2: Gram reduce + limb split
 
   float** cur = P.f_a;
   float** nxt = P.f_b;
@@ -319,7 +320,7 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
   for (int b = 0; b < B; ++b) XKV_TRY(xkv_fill_gaussian_bf16(P.lh[b], l, n, nn, o.seed + 7919ull * b, stream));
   XKV_TRY(apply_gram(1));
   XKV_TRY(cholqr(o.first_passes));
-  XKV_TRY(mark());  // 2: range finder
+  XKV_TRY(mark());  // 3: range finder
 
   // ---- 4. power steps ----
   for (int it = 0; it < o.power_iters; ++it) {
@@ -327,7 +328,7 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
     XKV_TRY(apply_gram(3));
     XKV_TRY(cholqr(it == o.power_iters - 1 ? o.final_passes : o.passes));
   }
-  XKV_TRY(mark());  // 3: power iterations
+  XKV_TRY(mark());  // 4: power iterations
 
   // ---- 5. windowed Rayleigh-Ritz ----
   if (P.rr) {
@@ -378,7 +379,7 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
       for (int b = 0; b < B; ++b)
         if (sigma_host[b]) XKV_TRY(xkv_sqrt_clamp(P.evals[b][1], sigma_host[b], W, stream));
   }
-  XKV_TRY(mark());  // 4: Rayleigh-Ritz
+  XKV_TRY(mark());  // 5: Rayleigh-Ritz
 
   // ---- 6. right factor in bf16, both layouts ----
   for (int b = 0; b < B; ++b) XKV_TRY(xkv_convert_bf16(cur[b], r, n, nn, Vt_host[b], nn, V_host[b], r, stream));
@@ -390,6 +391,6 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
     ps.push_back(p);
   }
   XKV_TRY(run_gemms(ps, stream));
-  XKV_TRY(mark());  // 5: projection
+  XKV_TRY(mark());  // 6: projection
   return 0;
 }

@@ -112,7 +112,7 @@ class _Timer:
         return out
 
 
-_STAGES = ("gram", "range_finder", "power_iters", "rayleigh_ritz", "project")
+_STAGES = ("gram_gemm", "gram_reduce_split", "range_finder", "power_iters", "rayleigh_ritz", "project")
 
 
 def _c_options(opts: FactorizeOptions) -> "_lib.FactorizeOptions":
@@ -171,12 +171,12 @@ def factorize_batch(xs: Sequence[torch.Tensor], rank: int, opts: Optional[Factor
         vt = [torch.empty(r, n, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
         v = [torch.empty(n, r, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
         sig = [torch.empty(nsig, dtype=torch.float32, device=dev) if nsig else None for _ in range(nb)]
-        events = [torch.cuda.Event(enable_timing=True) for _ in range(6)] if opts.profile else None
+        events = [torch.cuda.Event(enable_timing=True) for _ in range(7)] if opts.profile else None
         ev_arr = None
         if events is not None:
             for e in events:
                 e.record()  # torch creates the cudaEvent lazily; recording materialises the handle
-            ev_arr = (C.c_void_p * 6)(*[e.cuda_event for e in events])
+            ev_arr = (C.c_void_p * 7)(*[e.cuda_event for e in events])
             all_events.append(events)
         _lib.check(lib.xkv_factorize_batch(
             ops._ptr_array(part), nb, m, n, part[0].stride(0), r, C.byref(co), ops._ptr_array(a), ops._ptr_array(vt),
