@@ -128,7 +128,7 @@ typedef struct xkv_factorize_options {
   int32_t first_passes;   /* CholeskyQR passes after the range finder (3) */
   int32_t passes;         /* CholeskyQR passes after a power step (2) */
   int32_t final_passes;   /* CholeskyQR passes after the last power step (3) */
-  int32_t window;         /* Rayleigh-Ritz window width, <= 160 */
+  int32_t window;         /* Rayleigh-Ritz window width, <= 160 (default 128) */
   int32_t jacobi_sweeps;
   int32_t rayleigh_ritz;  /* 0: keep the first `rank` basis vectors as they are */
   int32_t want_sigma;     /* also diagonalise the leading window to report singular values */

@@ -187,8 +187,8 @@ extern "C" void xkv_factorize_default_options(xkv_factorize_options* o) {
   o->first_passes = 3;
   o->passes = 2;
   o->final_passes = 3;
-  o->window = 160;
-  o->jacobi_sweeps = 8;
+  o->window = 128;
+  o->jacobi_sweeps = 6;
   o->rayleigh_ritz = 1;
   o->want_sigma = 1;
   o->gram_split_k = 1;

@@ -172,179 +172,202 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const __grid_consta
 }
 
 // =============================================================================================
-// Blocked Cholesky S = L L^T with explicit inverse Linv = L^{-1} (batched over blockIdx.y)
+// Blocked Cholesky (S + shift*I) = L L^T with explicit inverse Linv = L^{-1}, batched over blockIdx.y
 //
-// Right-looking, NB = 64.  Step k launches
-//   panel  : CTA i >= k factors the diagonal block (every CTA redundantly, in shared memory,
-//            so there is no inter-CTA dependency inside a launch), inverts it, and solves its
-//            own block  L[i,k] = S[i,k] * L[k,k]^{-T}.
-//   update : trailing tiles S[i,j] -= L[i,k] L[j,k]^T (k < j <= i), plus the blocks of row k of
-//            the inverse  Linv[k,j] = -Linv[k,k] * sum_{t=j}^{k-1} L[k,t] Linv[t,j]  (j < k).
-// Pivots are floored at `pivot_floor` (inputs have unit diagonal: the columns were normalised),
-// so the factorisation never breaks down; CholeskyQR is simply repeated.
+// NB = 64, right-looking.  Phase F, step k (two launches):
+//   panel  : CTA i >= k factors the diagonal block in shared memory (every CTA redundantly, so no
+//            inter-CTA dependency inside a launch).  The inverse of the diagonal factor is accumulated
+//            by the same rank-1 sweeps that update the trailing triangle (forward substitution in
+//            right-looking form), so it costs no extra synchronisation.  CTA k publishes the inverse to
+//            Linv[k,k]; CTA i > k solves its block  L[i,k] = S[i,k] * L[k,k]^{-T}.
+//   update : trailing tiles  S[i,j] -= L[i,k] L[j,k]^T  (k < j <= i).
+// Phase I (recursive doubling, two launches per level s = 1, 2, 4, ... blocks): for each aligned pair of
+//   diagonal super-blocks [A 0; B C]:  T = B A^{-1}  (staged in the unused upper triangle of S), then
+//   Linv[C,A] = -C^{-1} T.  Critical path: 2s block products per level instead of k per step.
+// All block products read their operands from shared memory in k-major layout (one LDS.128 per operand
+// per k step).  Pivots are floored at `pivot_floor`; with `shift` the factorisation of the fp32 Gram of an
+// ill-conditioned sketch stays finite, and CholeskyQR is simply repeated.
 // =============================================================================================
 constexpr int NB = 64;
-constexpr int NBP = NB + 1;
+constexpr int NBP = NB + 1;   // natural layout [r][c], conflict-free column walks
+constexpr int NBK = NB + 4;   // k-major layout [k][idx], rows 16-byte aligned for LDS.128
+constexpr int TILE_FLOATS = NB * NBK;
 
 struct CholParams {
   float* S[XKV_MAX_BATCH];
   float* Linv[XKV_MAX_BATCH];
-  int l, nblk, k;
+  int l, nblk, k;   // k: panel step (phase F) or super-block size s (phase I)
   long long ld;
   float pivot_floor;
-  float shift;  // added to the diagonal (shifted Cholesky): S + shift*I
+  float shift;      // added to the diagonal (shifted Cholesky): S + shift*I
 };
 
-// C(64x64, 4x4 per thread) += A(64x64) * B(64x64)^T  [TRANSB=1]  or  A * B  [TRANSB=0]; operands in smem
-template <int TRANSB>
-__device__ __forceinline__ void block_mma(float (&acc)[4][4], const float (*As)[NBP], const float (*Bs)[NBP],
-                                          int kmax = NB) {
-  const int tr = (threadIdx.x >> 4) * 4;  // row base
-  const int tc = (threadIdx.x & 15) * 4;  // col base
-  for (int k = 0; k < kmax; ++k) {
-    float a[4], b[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = As[tr + i][k];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = TRANSB ? Bs[tc + j][k] : Bs[k][tc + j];
+// C(64x64, 4x4 per thread) += sum_k Ak[k][r] * Bk[k][c]   (both operands k-major in shared memory)
+__device__ __forceinline__ void block_mma(float (&acc)[4][4], const float* Ak, const float* Bk) {
+  const int tr = (threadIdx.x >> 4) * 4;
+  const int tc = (threadIdx.x & 15) * 4;
+#pragma unroll 8
+  for (int k = 0; k < NB; ++k) {
+    const float4 a = *reinterpret_cast<const float4*>(Ak + k * NBK + tr);
+    const float4 b = *reinterpret_cast<const float4*>(Bk + k * NBK + tc);
+    const float av[4] = {a.x, a.y, a.z, a.w};
+    const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
   }
 }
-__device__ __forceinline__ void load_block(float (*dst)[NBP], const float* src, long long ld) {
+// dst[k][r] = src[r][k]  (operand used as  X[r][k]  with k the contraction index)
+__device__ __forceinline__ void load_tile_T(float* dst, const float* src, long long ld) {
   for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-    const int r = e >> 6, c = e & 63;
-    dst[r][c] = src[static_cast<long long>(r) * ld + c];
+    const int r = e >> 6, k = e & 63;
+    dst[k * NBK + r] = src[static_cast<long long>(r) * ld + k];
   }
+}
+// dst[k][c] = src[k][c]   (operand used as  X[k][c])
+__device__ __forceinline__ void load_tile_N(float* dst, const float* src, long long ld) {
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+    const int k = e >> 6, c = e & 63;
+    dst[k * NBK + c] = src[static_cast<long long>(k) * ld + c];
+  }
+}
+__device__ __forceinline__ float* block_ptr(float* base, int bi, int bj, long long ld) {
+  return base + (static_cast<long long>(bi) * NB) * ld + static_cast<long long>(bj) * NB;
 }
 
 __global__ void __launch_bounds__(256) chol_panel_kernel(const __grid_constant__ CholParams p) {
-  __shared__ float D[NB][NBP];
-  __shared__ float Di[NB][NBP];
+  __shared__ __align__(16) float buf0[TILE_FLOATS];  // D (natural, stride NBP) during the factor, then Di^T (k-major)
+  __shared__ __align__(16) float buf1[TILE_FLOATS];  // X = D^{-1} (natural, stride NBP), then the panel block (k-major)
   float* S = p.S[blockIdx.y];
   float* Linv = p.Linv[blockIdx.y];
   const int k = p.k;
   const int i = k + blockIdx.x;
   const int tid = threadIdx.x;
-  const float* dblk = S + (static_cast<long long>(k) * NB) * p.ld + k * NB;
-  load_block(D, dblk, p.ld);
+  float* D = buf0;
+  float* X = buf1;
+  const float* dblk = block_ptr(S, k, k, p.ld);
+  for (int e = tid; e < NB * NB; e += blockDim.x) {
+    const int r = e >> 6, c = e & 63;
+    D[r * NBP + c] = dblk[static_cast<long long>(r) * p.ld + c] + (r == c ? p.shift : 0.f);
+    X[r * NBP + c] = (r == c) ? 1.f : 0.f;  // residual of the forward substitution L X = I
+  }
   __syncthreads();
-  if (tid < NB) D[tid][tid] += p.shift;
-  __syncthreads();
-  // --- in-place lower Cholesky of D ---
+  const int ur = tid >> 4, uc = tid & 15;
   for (int j = 0; j < NB; ++j) {
     if (tid < 32) {
-      float d = D[j][j];
-      d = fmaxf(d, p.pivot_floor);
+      const float d = fmaxf(D[j * NBP + j], p.pivot_floor);
       const float inv = rsqrtf(d);
-      for (int r = j + 1 + tid; r < NB; r += 32) D[r][j] *= inv;
       __syncwarp();
-      if (tid == 0) D[j][j] = d * inv;  // sqrt(d)
+      for (int r = j + 1 + tid; r < NB; r += 32) D[r * NBP + j] *= inv;     // column j of L
+      for (int c = tid; c <= j; c += 32) X[j * NBP + c] *= inv;            // row j of L^{-1} is final
+      if (tid == 0) D[j * NBP + j] = d * inv;
     }
     __syncthreads();
-    // rank-1 update of the trailing lower triangle (16 x 16 thread grid, no div/mod)
-    for (int r = j + 1 + (tid >> 4); r < NB; r += 16) {
-      const float lr = D[r][j];
-      for (int c = j + 1 + (tid & 15); c <= r; c += 16) D[r][c] -= lr * D[c][j];
+    // rank-1 sweeps: trailing triangle of D, and the residual rows of X below j
+    for (int r = j + 1 + ur; r < NB; r += 16) {
+      const float lr = D[r * NBP + j];
+      for (int c = j + 1 + uc; c <= r; c += 16) D[r * NBP + c] -= lr * D[c * NBP + j];
+      for (int c = uc; c <= j; c += 16) X[r * NBP + c] -= lr * X[j * NBP + c];
     }
     __syncthreads();
   }
-  // --- Di = D^{-1} (lower): thread c solves column c by forward substitution ---
-  if (tid < NB) {
-    const int c = tid;
-    for (int r = 0; r < NB; ++r) {
-      float x = (r == c) ? 1.f : 0.f;
-      if (r >= c) {
-        for (int t = c; t < r; ++t) x -= D[r][t] * Di[t][c];
-        x /= D[r][r];
-      } else {
-        x = 0.f;
-      }
-      Di[r][c] = x;
-    }
-  }
-  __syncthreads();
   if (i == k) {
     // Only the inverse of the diagonal block is published: L[k,k] itself is never read again, and
     // writing it over S[k,k] would race with the other CTAs of this launch still loading that block.
-    float* iblk = Linv + (static_cast<long long>(k) * NB) * p.ld + k * NB;
+    float* iblk = block_ptr(Linv, k, k, p.ld);
     for (int e = tid; e < NB * NB; e += blockDim.x) {
       const int r = e >> 6, c = e & 63;
-      iblk[static_cast<long long>(r) * p.ld + c] = Di[r][c];
+      iblk[static_cast<long long>(r) * p.ld + c] = (c <= r) ? X[r * NBP + c] : 0.f;
     }
-  } else {
-    // L[i,k] = S[i,k] * Di^T  (the factor D is no longer needed: reuse its buffer for the panel block)
-    load_block(D, S + (static_cast<long long>(i) * NB) * p.ld + k * NB, p.ld);
-    __syncthreads();
-    float acc[4][4] = {};
-    block_mma<1>(acc, D, Di);
-    float* oblk = S + (static_cast<long long>(i) * NB) * p.ld + k * NB;
-    const int tr = (tid >> 4) * 4, tc = (tid & 15) * 4;
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) oblk[static_cast<long long>(tr + a) * p.ld + tc + b] = acc[a][b];
+    return;
   }
+  // L[i,k][r][c] = sum_kk S[i,k][r][kk] * Di[c][kk]:  Ak[kk][r] = S[i,k][r][kk],  Bk[kk][c] = Di[c][kk]
+  float* Bk = buf0;  // D is dead
+  for (int e = tid; e < NB * NB; e += blockDim.x) {
+    const int c = e >> 6, kk = e & 63;
+    Bk[kk * NBK + c] = (kk <= c) ? X[c * NBP + kk] : 0.f;
+  }
+  __syncthreads();   // X fully consumed before its buffer is reused
+  float* Ak = buf1;
+  float* pblk = block_ptr(S, i, k, p.ld);
+  load_tile_T(Ak, pblk, p.ld);
+  __syncthreads();
+  float acc[4][4] = {};
+  block_mma(acc, Ak, Bk);
+  const int tr = (tid >> 4) * 4, tc = (tid & 15) * 4;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+    *reinterpret_cast<float4*>(pblk + static_cast<long long>(tr + a) * p.ld + tc) =
+        make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
 }
 
 __global__ void __launch_bounds__(256) chol_update_kernel(const __grid_constant__ CholParams p) {
-  __shared__ float As[NB][NBP];
-  __shared__ float Bs[NB][NBP];
+  __shared__ __align__(16) float Ak[TILE_FLOATS];
+  __shared__ __align__(16) float Bk[TILE_FLOATS];
+  float* S = p.S[blockIdx.y];
+  const int k = p.k;
+  // tile (i, j) of the trailing lower triangle, k < j <= i
+  int b = blockIdx.x, ii = 0;
+  while (b >= ii + 1) {
+    b -= ii + 1;
+    ++ii;
+  }
+  const int i = k + 1 + ii, j = k + 1 + b;
+  load_tile_T(Ak, block_ptr(S, i, k, p.ld), p.ld);
+  load_tile_T(Bk, block_ptr(S, j, k, p.ld), p.ld);
+  __syncthreads();
+  float acc[4][4] = {};
+  block_mma(acc, Ak, Bk);
+  float* o = block_ptr(S, i, j, p.ld);
+  const int tr = (threadIdx.x >> 4) * 4, tc = (threadIdx.x & 15) * 4;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    float4* q = reinterpret_cast<float4*>(o + static_cast<long long>(tr + a) * p.ld + tc);
+    float4 v = *q;
+    v.x -= acc[a][0];
+    v.y -= acc[a][1];
+    v.z -= acc[a][2];
+    v.w -= acc[a][3];
+    *q = v;
+  }
+}
+
+// Phase I.  PASS 0:  T[i,j] = sum_{t=j}^{a+s-1} L[i,t] Linv[t,j]      -> staged at S block (j,i)
+//           PASS 1:  Linv[i,j] = - sum_{t=a+s}^{i} Linv[i,t] T[t,j]    (T[t,j] read from S block (j,t))
+// for i in the C rows [a+s, a+2s) and j in the A columns [a, a+s) of the aligned pair that contains them.
+template <int PASS>
+__global__ void __launch_bounds__(256) chol_inverse_kernel(const __grid_constant__ CholParams p) {
+  __shared__ __align__(16) float Ak[TILE_FLOATS];
+  __shared__ __align__(16) float Bk[TILE_FLOATS];
+  const int s = p.k;
+  const int i = blockIdx.x / p.nblk, j = blockIdx.x - i * p.nblk;
+  const int a = (j / (2 * s)) * 2 * s;
+  if (!(j < a + s && i >= a + s && i < a + 2 * s)) return;  // uniform per CTA
   float* S = p.S[blockIdx.y];
   float* Linv = p.Linv[blockIdx.y];
-  const int k = p.k;
-  const int nt = p.nblk - k - 1;       // trailing block rows/cols
-  const int ntrail = nt * (nt + 1) / 2;
-  const int tid = threadIdx.x;
-  const int tr = (tid >> 4) * 4, tc = (tid & 15) * 4;
-  int b = blockIdx.x;
-  if (b < ntrail) {
-    // tile (i, j) of the trailing lower triangle, k < j <= i
-    int ii = 0;
-    while (b >= ii + 1) {
-      b -= ii + 1;
-      ++ii;
-    }
-    const int i = k + 1 + ii, j = k + 1 + b;
-    load_block(As, S + (static_cast<long long>(i) * NB) * p.ld + k * NB, p.ld);
-    load_block(Bs, S + (static_cast<long long>(j) * NB) * p.ld + k * NB, p.ld);
+  float acc[4][4] = {};
+  const int t0 = PASS == 0 ? j : a + s;
+  const int t1 = PASS == 0 ? a + s : i + 1;
+  for (int t = t0; t < t1; ++t) {
     __syncthreads();
-    float acc[4][4] = {};
-    block_mma<1>(acc, As, Bs);
-    float* o = S + (static_cast<long long>(i) * NB) * p.ld + j * NB;
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) o[static_cast<long long>(tr + a) * p.ld + tc + c] -= acc[a][c];
-  } else {
-    // inverse block (k, j), j < k
-    const int j = b - ntrail;
-    float acc[4][4] = {};
-    for (int t = j; t < k; ++t) {
-      __syncthreads();
-      load_block(As, S + (static_cast<long long>(k) * NB) * p.ld + t * NB, p.ld);      // L[k,t]
-      load_block(Bs, Linv + (static_cast<long long>(t) * NB) * p.ld + j * NB, p.ld);   // Linv[t,j]
-      __syncthreads();
-      block_mma<0>(acc, As, Bs);
+    if (PASS == 0) {
+      load_tile_T(Ak, block_ptr(S, i, t, p.ld), p.ld);      // L[i,t][r][kk]
+      load_tile_N(Bk, block_ptr(Linv, t, j, p.ld), p.ld);   // Linv[t,j][kk][c]
+    } else {
+      load_tile_T(Ak, block_ptr(Linv, i, t, p.ld), p.ld);   // Linv[i,t][r][kk]
+      load_tile_N(Bk, block_ptr(S, j, t, p.ld), p.ld);      // T[t,j][kk][c], staged at (j,t)
     }
     __syncthreads();
-    // stage acc in Bs, load Linv[k,k] into As, then out = -As * Bs
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) Bs[tr + a][tc + c] = acc[a][c];
-    load_block(As, Linv + (static_cast<long long>(k) * NB) * p.ld + k * NB, p.ld);
-    __syncthreads();
-    float out[4][4] = {};
-    block_mma<0>(out, As, Bs);
-    float* o = Linv + (static_cast<long long>(k) * NB) * p.ld + j * NB;
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) o[static_cast<long long>(tr + a) * p.ld + tc + c] = -out[a][c];
+    block_mma(acc, Ak, Bk);
   }
+  float* o = PASS == 0 ? block_ptr(S, j, i, p.ld) : block_ptr(Linv, i, j, p.ld);
+  const float sgn = PASS == 0 ? 1.f : -1.f;
+  const int tr = (threadIdx.x >> 4) * 4, tc = (threadIdx.x & 15) * 4;
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    *reinterpret_cast<float4*>(o + static_cast<long long>(tr + r) * p.ld + tc) =
+        make_float4(sgn * acc[r][0], sgn * acc[r][1], sgn * acc[r][2], sgn * acc[r][3]);
 }
 
 // zero the strict upper block triangle of Linv (the GEMM consumes Linv as a dense matrix)
@@ -578,6 +601,7 @@ extern "C" int xkv_cholesky_inverse(float* const* S_host, float* const* Linv_hos
                                     float shift, float pivot_floor, void* stream) {
   XKV_REQUIRE(S_host && Linv_host && batch >= 1 && batch <= XKV_MAX_BATCH, "cholesky: bad batch");
   XKV_REQUIRE(l > 0 && l % NB == 0, "cholesky: l=%d must be a positive multiple of %d", l, NB);
+  XKV_REQUIRE(ld % 4 == 0, "cholesky: ld must be a multiple of 4");
   CholParams p;
   std::memset(&p, 0, sizeof(p));
   for (int b = 0; b < batch; ++b) {
@@ -593,16 +617,24 @@ extern "C" int xkv_cholesky_inverse(float* const* S_host, float* const* Linv_hos
   cudaStream_t st = as_stream(stream);
   zero_upper_kernel<<<dim3(64, batch), 256, 0, st>>>(p);
   XKV_LAUNCHED();
+  // phase F: factorisation, diagonal inverses
   for (int k = 0; k < p.nblk; ++k) {
     p.k = k;
     chol_panel_kernel<<<dim3(p.nblk - k, batch), 256, 0, st>>>(p);
     XKV_LAUNCHED();
     const int nt = p.nblk - k - 1;
-    const int nblocks = nt * (nt + 1) / 2 + k;
-    if (nblocks > 0) {
-      chol_update_kernel<<<dim3(nblocks, batch), 256, 0, st>>>(p);
+    if (nt > 0) {
+      chol_update_kernel<<<dim3(nt * (nt + 1) / 2, batch), 256, 0, st>>>(p);
       XKV_LAUNCHED();
     }
+  }
+  // phase I: off-diagonal blocks of the inverse by recursive doubling
+  for (int s = 1; s < p.nblk; s *= 2) {
+    p.k = s;
+    chol_inverse_kernel<0><<<dim3(p.nblk * p.nblk, batch), 256, 0, st>>>(p);
+    XKV_LAUNCHED();
+    chol_inverse_kernel<1><<<dim3(p.nblk * p.nblk, batch), 256, 0, st>>>(p);
+    XKV_LAUNCHED();
   }
   return 0;
 }

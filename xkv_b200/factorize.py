@@ -45,8 +45,8 @@ class FactorizeOptions:
     first_passes: int = 3      # CholeskyQR passes after the range finder (ill-conditioned sketch)
     passes: int = 2            # CholeskyQR passes after each power step
     final_passes: int = 3      # passes after the last power step (orthonormal to ~1e-5)
-    window: int = 160          # Rayleigh-Ritz window width (<= 160: A and V live in shared memory)
-    jacobi_sweeps: int = 8
+    window: int = 128          # Rayleigh-Ritz window width (<= 160: A and V live in shared memory)
+    jacobi_sweeps: int = 6
     rayleigh_ritz: bool = True
     want_sigma: bool = True    # also diagonalise the leading window to report singular values
     gram_split_k: int = 1
