@@ -146,6 +146,29 @@ XKV_API int xkv_factorize_batch(const void* const* X_host, int batch, int m, int
                                 void* const* V_host, float* const* sigma_host, void* workspace,
                                 size_t workspace_bytes, void* const* stage_events_host, void* stream);
 
+/* ---- (3) decode-time attention over the factored cache: replaces the SDPA call over dense K^/V^ --------
+ * llama.py:58-69 with the reconstruction of cache:26-27 and the RoPE of cache:142-148 fused in.
+ *   q          (Hq, D) bf16, post-RoPE query of ONE layer, batch 1
+ *   A_k, A_v   (S, rk) / (S, rv) bf16 token factors of the layer's group
+ *   Vk_layer   (H*D, rk) bf16: rows [layer_in_group*H*D, +H*D) of the group's right factor V_k (n x rk);
+ *   Vv_layer   (H*D, rv) likewise for values
+ *   cos, sin   (S, D) bf16 RoPE tables of the prefill positions (half-split convention), or NULL when the
+ *              keys were compressed post-RoPE / need none (re_apply_rope=False, deepseek_v2.py:226)
+ *   k_tail, v_tail  (H, T, D) bf16 dense decode tokens appended after prefill (keys post-RoPE), T may be 0
+ *   out        (Hq, D) bf16 = softmax(scale * q [K^;K_tail]^T) [V^;V_tail] with GQA (Hq/H query heads per kv head)
+ * Full-rank K^/V^ are never written to HBM. D in {64, 128}; Hq/H <= 8. */
+XKV_API size_t xkv_decode_workspace_bytes(int Hq, int S, int T, int rv);
+XKV_API int xkv_decode_attention(const void* q, int Hq, int H, int D, const void* A_k, int64_t lda_k, int rk,
+                                 const void* Vk_layer, int64_t ldv_k, const void* A_v, int64_t lda_v, int rv,
+                                 const void* Vv_layer, int64_t ldv_v, int S, const void* cos, const void* sin,
+                                 int64_t ld_cs, const void* k_tail, const void* v_tail, int T, int64_t tail_stride_h,
+                                 int64_t tail_stride_t, float scale, void* out, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+/* RoPE on materialised keys x (rows, H, D) bf16 in place, in the reference's bf16 arithmetic
+ * (apply_rotary_pos_emb as called at cache:148,152): x*cos + rotate_half(x)*sin, cos/sin (rows, D). */
+XKV_API int xkv_rope_bf16(void* x, int64_t ld_row, int rows, int H, int D, const void* cos, const void* sin,
+                          int64_t ld_cs, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,78 @@
+"""GPU parity of the fused decode attention (reconstruct + RoPE + GQA softmax over the factored cache)
+against the oracle: dense K^ = bf16(A Vk_l^T), HF RoPE in bf16 (cache:142-148), cat-append of the decode
+tokens (cache:129) and SDPA with repeat_kv (llama.py:58-69).  Tolerance: bf16 (2e-2 of the output scale)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(S, H, D, qpk, rk, rv, T, layers_in_group, layer, rope, seed=0):
+    from oracle import xkv_oracle as O
+    from xkv_b200 import ops, synthetic
+
+    g = torch.Generator().manual_seed(seed)
+    n = layers_in_group * H * D
+    Hq = H * qpk
+    a_k = (torch.randn(S, rk, generator=g) * 0.6).bfloat16()
+    a_v = torch.randn(S, rv, generator=g).bfloat16()
+    v_k = torch.linalg.qr(torch.randn(n, rk, generator=g))[0].bfloat16()
+    v_v = torch.linalg.qr(torch.randn(n, rv, generator=g))[0].bfloat16()
+    q = torch.randn(Hq, D, generator=g).bfloat16()
+    k_tail = torch.randn(H, max(T, 1), D, generator=g).bfloat16()[:, :T]
+    v_tail = torch.randn(H, max(T, 1), D, generator=g).bfloat16()[:, :T]
+    cos, sin = synthetic.llama3_rope(S, D)
+    cos, sin = cos[0], sin[0]
+    rows = slice(layer * H * D, (layer + 1) * H * D)
+    # ---- oracle on the CPU ----
+    k_hat = (a_k.float() @ v_k[rows].float().t()).bfloat16().view(S, H, D).permute(1, 0, 2)[None]   # (1,H,S,D)
+    v_hat = (a_v.float() @ v_v[rows].float().t()).bfloat16().view(S, H, D).permute(1, 0, 2)[None]
+    if rope:
+        k_hat = O.apply_rope(k_hat, cos[None], sin[None])
+    kt = k_tail[None] if T else None
+    vt = v_tail[None] if T else None
+    ref = O.decode_attention(q[None, :, None, :].float(), k_hat.float(), v_hat.float(),
+                             kt.float() if T else None, vt.float() if T else None, scaling=1.0 / math.sqrt(D))[0, :, 0]
+    # ---- CUDA path ----
+    dev = "cuda"
+    out = ops.decode_attention(q.to(dev), a_k.to(dev), v_k.to(dev)[rows], a_v.to(dev), v_v.to(dev)[rows], H,
+                               cos.to(dev) if rope else None, sin.to(dev) if rope else None,
+                               k_tail.to(dev) if T else None, v_tail.to(dev) if T else None, 1.0 / math.sqrt(D))
+    torch.cuda.synchronize()
+    got = out.float().cpu()
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    print(f"S={S} H={H} D={D} qpk={qpk} rk={rk} rv={rv} T={T} rope={rope}: max|diff|={err:.4f} (out scale {scale:.3f})")
+    assert torch.isfinite(got).all()
+    assert err <= 2e-2 * max(scale, 1e-3)
+
+
+@pytest.mark.parametrize(
+    "S,H,D,qpk,rk,rv,T,G,layer,rope",
+    [
+        (512, 2, 128, 4, 64, 128, 0, 2, 1, True),      # smallest: two token tiles... one n-tile
+        (1000, 8, 128, 4, 128, 192, 7, 4, 2, True),    # ragged token count, Llama head layout, decode tail
+        (4096, 8, 128, 4, 512, 768, 33, 4, 3, True),   # config-1 ranks
+        (777, 4, 64, 2, 64, 64, 3, 1, 0, True),        # head_dim 64, single-layer group
+        (2048, 1, 128, 8, 128, 128, 5, 4, 1, False),   # one kv head, 8 q heads, no RoPE re-application
+        (300, 3, 128, 1, 96, 160, 1, 2, 0, True),      # MHA (qpk 1), 3 heads: second n-tile half empty, rank not /64
+    ],
+)
+def test_decode_attention_matches_oracle(S, H, D, qpk, rk, rv, T, G, layer, rope):
+    _case(S, H, D, qpk, rk, rv, T, G, layer, rope)
+
+
+def test_rope_bf16_matches_hf_formula():
+    from oracle import xkv_oracle as O
+    from xkv_b200 import ops, synthetic
+
+    torch.manual_seed(0)
+    S, H, D = 257, 8, 128
+    x = torch.randn(S, H, D).bfloat16()
+    cos, sin = synthetic.llama3_rope(S, D)
+    ref = O.apply_rope(x.permute(1, 0, 2)[None], cos, sin)[0].permute(1, 0, 2)
+    got = ops.rope_bf16_(x.cuda().clone(), cos[0].cuda(), sin[0].cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(got.cpu(), ref)

@@ -89,6 +89,10 @@ SIGNATURES = {
     "xkv_factorize_default_options": (None, [C.POINTER(FactorizeOptions)]),
     "xkv_factorize_workspace_bytes": (_sz, [_i, _i, _i, _i, C.POINTER(FactorizeOptions)]),
     "xkv_factorize_sigma_count": (_i, [_i, C.POINTER(FactorizeOptions)]),
+    "xkv_decode_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "xkv_decode_attention": (_i, [_vp, _i, _i, _i, _vp, _i64, _i, _vp, _i64, _vp, _i64, _i, _vp, _i64, _i, _vp, _vp, _i64,
+                                  _vp, _vp, _i, _i64, _i64, _f, _vp, _vp, _sz, _vp]),
+    "xkv_rope_bf16": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "xkv_factorize_batch": (_i, [_pp, _i, _i, _i, _i64, _i, C.POINTER(FactorizeOptions), _pp, _pp, _pp, _pp, _vp, _sz,
                                  _pp, _vp]),
 }

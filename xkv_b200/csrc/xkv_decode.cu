@@ -1,0 +1,445 @@
+// xkv_b200 — decode-time attention over the factored cache (north-star step 3).
+//
+// The reference stores dense K^ = bf16(U_r S_r V_r^T) (fake_layer_merge_dynamic_cache.py:26-27,176),
+// applies RoPE to it (:142-148) and runs SDPA with GQA over [K^ ; decode tokens] (llama.py:51-69).
+// Here the factors stay factored:
+//
+//   scores   K^ tile = A_k[128 tokens, r_k] * Bk_l^T is formed by tcgen05.mma in TMEM, rounded to bf16,
+//            rotated (RoPE in the reference's bf16 arithmetic) and contracted with q in the epilogue;
+//            only the (Hq x S) fp32 scores go to HBM, the full-rank keys never do.
+//   softmax  one pass per q-head: max, exp, row sum; probabilities written once as bf16.
+//   values   absorbed form  o = ((P A_v) Bv_l^T) / rowsum : P A_v is a tensor-core GEMM over the token
+//            dimension (xkv_gemm.cu, split-K), Bv_l is applied to the (Hq x r_v) result; no V^ tile is
+//            ever formed.
+//   tail     decode tokens appended after prefill stay dense and exact (reference: mode='decode' skips
+//            merging, cache:131); their scores / values join the same softmax.
+#include "xkv_common.cuh"
+#include "xkv_host.h"
+
+namespace xkv {
+
+constexpr int DBM = 128;  // tokens per tile
+constexpr int DBN = 256;  // K^ columns per tile (256 / head_dim kv heads)
+constexpr int DBK = 64;
+constexpr int DSTAGES = 2;  // 2 x 48 KiB stages -> two CTAs per SM: one CTA's epilogue overlaps the other's MMA
+constexpr int D_A_BYTES = DBM * DBK * 2;
+constexpr int D_B_BYTES = DBN * DBK * 2;
+constexpr int D_STAGE_BYTES = D_A_BYTES + D_B_BYTES;
+constexpr int D_THREADS = 192;
+constexpr int D_TMEM_COLS = 256;
+constexpr int D_MAX_QPK = 8;  // q heads per kv head
+constexpr size_t D_SMEM_BYTES = DSTAGES * D_STAGE_BYTES + 1024 + 256 + DBN * D_MAX_QPK * sizeof(float);
+
+struct alignas(64) ScoreParams {
+  CUtensorMap a_map;  // A_k  (S x r_k), box {64, 128}
+  CUtensorMap b_map;  // Bk_l (H*D x r_k), box {64, 256}
+  const __nv_bfloat16* q;    // (Hq, D)
+  const __nv_bfloat16* cos;  // (S, D) or null
+  const __nv_bfloat16* sin;
+  float* scores;             // (Hq, ld_scores)
+  long long ld_cs, ld_scores;
+  int S, rk, H, qpk, tiles_n, nkb;
+  float scale;
+};
+
+__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+template <int D>
+__global__ void __launch_bounds__(D_THREADS, 2) decode_scores_kernel(const __grid_constant__ ScoreParams P) {
+  constexpr int HPT = DBN / D;        // kv heads per tile
+  constexpr int NCH = D / 32;         // 32-column chunks per head
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + DSTAGES * D_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + DSTAGES;
+  uint64_t* tmem_full_bar = empty_bar + DSTAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* q_s = reinterpret_cast<float*>(smem + DSTAGES * D_STAGE_BYTES + 256);  // [HPT * qpk][D]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tm = blockIdx.x / P.tiles_n, tn = blockIdx.x - tm * P.tiles_n;
+  const int m0 = tm * DBM, n0 = tn * DBN;
+  const int h0 = n0 / D;  // first kv head of this tile
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < DSTAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&P.a_map);
+    tma_prefetch_desc(&P.b_map);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, D_TMEM_COLS);
+  if (warp >= 2) {
+    // stage this tile's query heads as fp32: q_s[(hh * qpk + g) * D + d]
+    const int nq = HPT * P.qpk * D;
+    for (int e = threadIdx.x - 64; e < nq; e += 128) {
+      const int d = e % D, hg = e / D;
+      const int hh = hg / P.qpk, g = hg - hh * P.qpk;
+      const int h = h0 + hh;
+      q_s[e] = (h < P.H) ? __bfloat162float(P.q[static_cast<long long>(h * P.qpk + g) * D + d]) : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < P.nkb; ++kb) {
+        uint8_t* sA = smem + s * D_STAGE_BYTES;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], D_STAGE_BYTES);
+        tma_load_2d(sA, &P.a_map, &full_bar[s], kb * DBK, m0);
+        tma_load_2d(sA + D_A_BYTES, &P.b_map, &full_bar[s], kb * DBK, n0);
+        if (++s == DSTAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(DBM, DBN, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < P.nkb; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + s * D_STAGE_BYTES);
+        const uint32_t b_base = a_base + D_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < DBK / 16; ++k)
+          umma_bf16_ss(tmem_base, umma_desc_sw128(a_base + k * 32, 16, 1024), umma_desc_sw128(b_base + k * 32, 16, 1024),
+                       idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+        if (++s == DSTAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ============ epilogue: K^ row (this thread's token) -> bf16 -> RoPE -> dot with the q heads ============
+    const int qd = warp & 3;
+    const int tok = m0 + qd * 32 + lane;
+    const bool tok_ok = tok < P.S;
+    const bool rope = P.cos != nullptr;
+    float acc[HPT][D_MAX_QPK];
+#pragma unroll
+    for (int hh = 0; hh < HPT; ++hh)
+#pragma unroll
+      for (int g = 0; g < D_MAX_QPK; ++g) acc[hh][g] = 0.f;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < NCH / 2; ++c) {
+      // cos/sin of dims [32c, 32c+32) (identical for the partner dims +D/2 in the half-split convention)
+      uint32_t cs[16], sn[16];
+      if (rope && tok_ok) {
+        const uint4* cp = reinterpret_cast<const uint4*>(P.cos + static_cast<long long>(tok) * P.ld_cs + c * 32);
+        const uint4* sp = reinterpret_cast<const uint4*>(P.sin + static_cast<long long>(tok) * P.ld_cs + c * 32);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const uint4 cv = cp[v], sv = sp[v];
+          cs[4 * v] = cv.x, cs[4 * v + 1] = cv.y, cs[4 * v + 2] = cv.z, cs[4 * v + 3] = cv.w;
+          sn[4 * v] = sv.x, sn[4 * v + 1] = sv.y, sn[4 * v + 2] = sv.z, sn[4 * v + 3] = sv.w;
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < 16; ++v) cs[v] = 0x3F803F80u, sn[v] = 0u;  // cos = 1, sin = 0
+      }
+#pragma unroll
+      for (int hh = 0; hh < HPT; ++hh) {
+        uint32_t x1[32], x2[32];
+        __syncwarp();
+        tmem_ld_32x32(lane_addr + static_cast<uint32_t>(hh * D + c * 32), x1);
+        tmem_ld_32x32(lane_addr + static_cast<uint32_t>(hh * D + (c + NCH / 2) * 32), x2);
+        tmem_ld_wait();
+        const float* qh = q_s + (hh * P.qpk) * D;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float k1 = bf16r(__uint_as_float(x1[j]));
+          const float k2 = bf16r(__uint_as_float(x2[j]));
+          float o1 = k1, o2 = k2;
+          if (rope) {
+            const uint32_t cw = cs[j >> 1], sw = sn[j >> 1];
+            const float cf = __uint_as_float((j & 1) ? (cw & 0xFFFF0000u) : (cw << 16));
+            const float sf = __uint_as_float((j & 1) ? (sw & 0xFFFF0000u) : (sw << 16));
+            // HF apply_rotary_pos_emb in bf16: k*cos + rotate_half(k)*sin, every op rounded to bf16
+            o1 = bf16r(bf16r(k1 * cf) + bf16r(-k2 * sf));
+            o2 = bf16r(bf16r(k2 * cf) + bf16r(k1 * sf));
+          }
+          const int d1 = c * 32 + j, d2 = d1 + D / 2;
+#pragma unroll
+          for (int g = 0; g < D_MAX_QPK; ++g)
+            if (g < P.qpk) acc[hh][g] = fmaf(qh[g * D + d1], o1, fmaf(qh[g * D + d2], o2, acc[hh][g]));
+        }
+      }
+    }
+    if (tok_ok) {
+#pragma unroll
+      for (int hh = 0; hh < HPT; ++hh) {
+        const int h = h0 + hh;
+        if (h < P.H) {
+#pragma unroll
+          for (int g = 0; g < D_MAX_QPK; ++g)
+            if (g < P.qpk) P.scores[static_cast<long long>(h * P.qpk + g) * P.ld_scores + tok] = acc[hh][g] * P.scale;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, D_TMEM_COLS);
+  }
+}
+
+// scores of the dense tail tokens: scores[hq][S + t] = scale * q[hq] . k_tail[h][t]
+__global__ void __launch_bounds__(128) tail_scores_kernel(const __nv_bfloat16* __restrict__ q,
+                                                          const __nv_bfloat16* __restrict__ k_tail, long long sh,
+                                                          long long st, int Hq, int qpk, int D, int T, int S,
+                                                          float scale, float* __restrict__ scores, long long ld) {
+  const int t = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int hq = warp; hq < Hq; hq += 4) {
+    const int h = hq / qpk;
+    const __nv_bfloat16* kr = k_tail + h * sh + t * st;
+    float acc = 0.f;
+    for (int d = lane; d < D; d += 32) acc += __bfloat162float(q[hq * D + d]) * __bfloat162float(kr[d]);
+    acc = warp_sum(acc);
+    if (lane == 0) scores[hq * ld + S + t] = acc * scale;
+  }
+}
+
+// softmax over L = S + T scores of one q-head: p = exp(s - max) as bf16 (the GEMM operand), rowsum in fp32
+__global__ void __launch_bounds__(1024) softmax_kernel(const float* __restrict__ scores, long long ld, int L,
+                                                       __nv_bfloat16* __restrict__ prob, long long ldp,
+                                                       float* __restrict__ rowsum) {
+  __shared__ float red[32];
+  __shared__ float bcast;
+  const float* s = scores + blockIdx.x * ld;
+  __nv_bfloat16* p = prob + blockIdx.x * ldp;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float m = -INFINITY;
+  for (int i = tid; i < L; i += 1024) m = fmaxf(m, s[i]);
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  if (warp == 0) {
+    float v = red[lane];
+    v = warp_max(v);
+    if (lane == 0) bcast = v;
+  }
+  __syncthreads();
+  m = bcast;
+  float sum = 0.f;
+  for (int i = tid; i < L; i += 1024) {
+    const float e = __expf(s[i] - m);
+    sum += e;
+    p[i] = __float2bfloat16_rn(e);
+  }
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (warp == 0) {
+    float v = red[lane];
+    v = warp_sum(v);
+    if (lane == 0) rowsum[blockIdx.x] = v;
+  }
+}
+
+// o[hq][d] = ( sum_j U[hq][j] * Bv[(h*D + d)][j]  +  sum_t p_tail[hq][t] * v_tail[h][t][d] ) / rowsum[hq]
+__global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ U, long long ldu, int rv,
+                                                      const __nv_bfloat16* __restrict__ Bv, long long ldb,
+                                                      const __nv_bfloat16* __restrict__ prob, long long ldp, int S, int T,
+                                                      const __nv_bfloat16* __restrict__ v_tail, long long sh, long long st,
+                                                      const float* __restrict__ rowsum, int qpk, int D,
+                                                      __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float u_s[];  // rv floats
+  const int hq = blockIdx.x, h = hq / qpk;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = threadIdx.x; j < rv; j += blockDim.x) u_s[j] = U[hq * ldu + j];
+  __syncthreads();
+  const float inv = 1.f / rowsum[hq];
+  for (int d = warp; d < D; d += 8) {
+    const __nv_bfloat16* row = Bv + static_cast<long long>(h * D + d) * ldb;
+    float acc = 0.f;
+    for (int j = lane * 2; j < rv; j += 64) {
+      const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(row + j);
+      acc = fmaf(u_s[j], __bfloat162float(b2.x), fmaf(u_s[j + 1], __bfloat162float(b2.y), acc));
+    }
+    for (int t = lane; t < T; t += 32)
+      acc = fmaf(__bfloat162float(prob[hq * ldp + S + t]), __bfloat162float(v_tail[h * sh + t * st + d]), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[hq * D + d] = __float2bfloat16_rn(acc * inv);
+  }
+}
+
+// RoPE on materialised keys, in the reference's bf16 arithmetic (cache:142-152): x (rows, H, D) in place
+__global__ void __launch_bounds__(256) rope_bf16_kernel(__nv_bfloat16* __restrict__ x, long long ld_row, int rows, int H,
+                                                        int D, const __nv_bfloat16* __restrict__ cos,
+                                                        const __nv_bfloat16* __restrict__ sin, long long ld_cs) {
+  const int half = D / 2;
+  const long long total = static_cast<long long>(rows) * H * half;
+  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int d = static_cast<int>(e % half);
+    const long long rh = e / half;
+    const int h = static_cast<int>(rh % H);
+    const long long row = rh / H;
+    __nv_bfloat16* p = x + row * ld_row + h * D;
+    const float k1 = __bfloat162float(p[d]), k2 = __bfloat162float(p[d + half]);
+    const float c1 = __bfloat162float(cos[row * ld_cs + d]), s1 = __bfloat162float(sin[row * ld_cs + d]);
+    const float c2 = __bfloat162float(cos[row * ld_cs + d + half]), s2 = __bfloat162float(sin[row * ld_cs + d + half]);
+    p[d] = __float2bfloat16_rn(bf16r(k1 * c1) + bf16r(-k2 * s1));
+    p[d + half] = __float2bfloat16_rn(bf16r(k2 * c2) + bf16r(k1 * s2));
+  }
+}
+
+static inline size_t al(size_t x) { return (x + 1023) / 1024 * 1024; }
+
+}  // namespace xkv
+
+using namespace xkv;
+
+extern "C" size_t xkv_decode_workspace_bytes(int Hq, int S, int T, int rv) {
+  const size_t L = static_cast<size_t>(S) + T;
+  const size_t ldl = (L + 63) / 64 * 64;
+  const int nkb = (S + 63) / 64;
+  int split = nkb < 64 ? nkb : 64;
+  if (split < 1) split = 1;
+  size_t b = 0;
+  b += al(Hq * ldl * 4);            // scores
+  b += al(128 * ldl * 2);           // probabilities (bf16), padded to a full 128-row tile
+  b += al(Hq * 4);                  // row sums
+  b += al(static_cast<size_t>(split) * Hq * rv * 4);  // split-K slabs of U
+  b += al(static_cast<size_t>(Hq) * rv * 4);          // U
+  return b + 1024;
+}
+
+extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const void* A_k, int64_t lda_k, int rk,
+                                    const void* Vk_layer, int64_t ldv_k, const void* A_v, int64_t lda_v, int rv,
+                                    const void* Vv_layer, int64_t ldv_v, int S, const void* cos, const void* sin,
+                                    int64_t ld_cs, const void* k_tail, const void* v_tail, int T, int64_t tail_stride_h,
+                                    int64_t tail_stride_t, float scale, void* out, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  XKV_REQUIRE(q && A_k && Vk_layer && A_v && Vv_layer && out && workspace, "decode: null argument");
+  XKV_REQUIRE(D == 64 || D == 128, "decode: head_dim %d not supported (64 or 128)", D);
+  XKV_REQUIRE(H >= 1 && Hq % H == 0 && Hq / H <= D_MAX_QPK && Hq <= 128, "decode: unsupported head counts Hq=%d H=%d", Hq, H);
+  XKV_REQUIRE(S >= 1 && T >= 0 && rk >= 1 && rv >= 1 && rv % 2 == 0, "decode: bad sizes");
+  XKV_REQUIRE(T == 0 || (k_tail && v_tail), "decode: tail pointers missing");
+  XKV_REQUIRE((cos == nullptr) == (sin == nullptr), "decode: cos and sin must both be given or both be null");
+  XKV_REQUIRE(cos == nullptr || ld_cs % 8 == 0, "decode: cos/sin row stride must be a multiple of 8");
+  XKV_REQUIRE(workspace_bytes >= xkv_decode_workspace_bytes(Hq, S, T, rv), "decode: workspace too small");
+  XKV_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "decode: workspace must be 1024-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  const int qpk = Hq / H;
+  const size_t L = static_cast<size_t>(S) + T;
+  const long long ldl = static_cast<long long>((L + 63) / 64 * 64);
+  const int nkb_s = (S + 63) / 64;
+  const int split = nkb_s < 64 ? nkb_s : 64;
+  char* w = static_cast<char*>(workspace);
+  float* scores = reinterpret_cast<float*>(w);
+  w += al(Hq * ldl * 4);
+  __nv_bfloat16* prob = reinterpret_cast<__nv_bfloat16*>(w);
+  w += al(128 * ldl * 2);
+  float* rowsum = reinterpret_cast<float*>(w);
+  w += al(Hq * 4);
+  float* u_slabs = reinterpret_cast<float*>(w);
+  w += al(static_cast<size_t>(split) * Hq * rv * 4);
+  float* U = reinterpret_cast<float*>(w);
+
+  // ---- scores of the compressed prefix: fused reconstruct + RoPE + q.K ----
+  static thread_local ScoreParams sp;
+  std::memset(&sp, 0, sizeof(sp));
+  int rc = encode_tmap_2d_bf16(&sp.a_map, A_k, rk, S, lda_k, DBK, DBM);
+  if (rc) return rc;
+  rc = encode_tmap_2d_bf16(&sp.b_map, Vk_layer, rk, static_cast<uint64_t>(H) * D, ldv_k, DBK, DBN);
+  if (rc) return rc;
+  sp.q = static_cast<const __nv_bfloat16*>(q);
+  sp.cos = static_cast<const __nv_bfloat16*>(cos);
+  sp.sin = static_cast<const __nv_bfloat16*>(sin);
+  sp.scores = scores;
+  sp.ld_cs = ld_cs;
+  sp.ld_scores = ldl;
+  sp.S = S;
+  sp.rk = rk;
+  sp.H = H;
+  sp.qpk = qpk;
+  sp.tiles_n = (H * D + DBN - 1) / DBN;
+  sp.nkb = (rk + DBK - 1) / DBK;
+  sp.scale = scale;
+  const int grid = ((S + DBM - 1) / DBM) * sp.tiles_n;
+  static bool configured = false;
+  if (!configured) {
+    XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(D_SMEM_BYTES)));
+    XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(D_SMEM_BYTES)));
+    configured = true;
+  }
+  if (D == 128)
+    decode_scores_kernel<128><<<grid, D_THREADS, D_SMEM_BYTES, st>>>(sp);
+  else
+    decode_scores_kernel<64><<<grid, D_THREADS, D_SMEM_BYTES, st>>>(sp);
+  XKV_LAUNCHED();
+  // ---- scores of the dense tail ----
+  if (T > 0) {
+    tail_scores_kernel<<<T, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k_tail),
+                                          tail_stride_h, tail_stride_t, Hq, qpk, D, T, S, scale, scores, ldl);
+    XKV_LAUNCHED();
+  }
+  // ---- softmax ----
+  softmax_kernel<<<Hq, 1024, 0, st>>>(scores, ldl, static_cast<int>(L), prob, ldl, rowsum);
+  XKV_LAUNCHED();
+  // ---- U = P[:, :S] * A_v  (tokens are the contraction: P K-major, A_v MN-major) ----
+  xkv_gemm_problem gp;
+  std::memset(&gp, 0, sizeof(gp));
+  gp.M = Hq;
+  gp.N = rv;
+  gp.K = S;
+  gp.num_terms = 1;
+  gp.a_mn_major = 0;
+  gp.b_mn_major = 1;
+  gp.A[0] = prob;
+  gp.B[0] = A_v;
+  gp.lda = ldl;
+  gp.ldb = lda_v;
+  gp.D = u_slabs;
+  gp.ldd = rv;
+  gp.split_k = split;
+  gp.split_stride = static_cast<long long>(Hq) * rv;
+  rc = xkv_gemm_grouped(&gp, 1, stream);
+  if (rc) return rc;
+  rc = xkv_reduce_slabs(u_slabs, split, static_cast<long long>(Hq) * rv, Hq, rv, rv, 0, U, rv, stream);
+  if (rc) return rc;
+  // ---- o = (U Bv_l^T + P_tail V_tail) / rowsum ----
+  combine_kernel<<<Hq, 256, rv * sizeof(float), st>>>(U, rv, rv, static_cast<const __nv_bfloat16*>(Vv_layer), ldv_v, prob,
+                                                      ldl, S, T, static_cast<const __nv_bfloat16*>(v_tail), tail_stride_h,
+                                                      tail_stride_t, rowsum, qpk, D, static_cast<__nv_bfloat16*>(out));
+  XKV_LAUNCHED();
+  return 0;
+}
+
+extern "C" int xkv_rope_bf16(void* x, int64_t ld_row, int rows, int H, int D, const void* cos, const void* sin,
+                             int64_t ld_cs, void* stream) {
+  XKV_REQUIRE(x && cos && sin && rows > 0 && H > 0 && D % 2 == 0, "rope: bad arguments");
+  const long long total = static_cast<long long>(rows) * H * (D / 2);
+  long long grid = (total + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  rope_bf16_kernel<<<static_cast<int>(grid), 256, 0, as_stream(stream)>>>(
+      static_cast<__nv_bfloat16*>(x), ld_row, rows, H, D, static_cast<const __nv_bfloat16*>(cos),
+      static_cast<const __nv_bfloat16*>(sin), ld_cs);
+  XKV_LAUNCHED();
+  return 0;
+}

@@ -203,3 +203,58 @@ def convert_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None, dst_t: O
     check(_lib.load().xkv_convert_bf16(_ptr(src), rows, cols, src.stride(0), _ptr(dst),
                                        dst.stride(0) if dst is not None else 0, _ptr(dst_t),
                                        dst_t.stride(0) if dst_t is not None else 0, _stream()))
+
+
+# ---------------------------------------------------------------------------------------------
+# (3) decode-time attention over the factored cache
+# ---------------------------------------------------------------------------------------------
+def decode_workspace_bytes(hq: int, s: int, t: int, rv: int) -> int:
+    return int(_lib.load().xkv_decode_workspace_bytes(hq, s, t, rv))
+
+
+def decode_attention(q: torch.Tensor, a_k: torch.Tensor, vk_layer: torch.Tensor, a_v: torch.Tensor,
+                     vv_layer: torch.Tensor, num_kv_heads: int, cos: Optional[torch.Tensor],
+                     sin: Optional[torch.Tensor], k_tail: Optional[torch.Tensor], v_tail: Optional[torch.Tensor],
+                     scale: float, out: Optional[torch.Tensor] = None,
+                     workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(scale * q [K^; K_tail]^T) [V^; V_tail] for one layer, batch 1, with K^ = rope(bf16(A_k Vk_l^T)) and
+    V^ = A_v Vv_l^T never materialised.  q (Hq, D); a_k (S, rk); vk_layer (H*D, rk); a_v (S, rv);
+    vv_layer (H*D, rv); cos/sin (S, D) or None; k_tail/v_tail (H, T, D) or None.  Returns (Hq, D) bf16."""
+    _require_cuda(q, a_k, vk_layer, a_v, vv_layer)
+    hq, d = q.shape
+    s, rk = a_k.shape
+    rv = a_v.shape[1]
+    t = 0 if k_tail is None else k_tail.shape[1]
+    need = decode_workspace_bytes(hq, s, t, rv)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=q.device)
+    if out is None:
+        out = torch.empty(hq, d, dtype=torch.bfloat16, device=q.device)
+    for name, x in (("q", q), ("a_k", a_k), ("vk_layer", vk_layer), ("a_v", a_v), ("vv_layer", vv_layer)):
+        if x.dtype != torch.bfloat16 or x.stride(-1) != 1:
+            raise _lib.XkvError(f"decode_attention: {name} must be bf16 with unit inner stride")
+    if not q.is_contiguous():
+        q = q.contiguous()
+    if cos is not None and (cos.dtype != torch.bfloat16 or cos.stride(-1) != 1 or cos.shape[0] < s):
+        raise _lib.XkvError("decode_attention: cos/sin must be bf16 (S, D) tables")
+    sh = st = 0
+    if t > 0:
+        if k_tail.stride() != v_tail.stride() or k_tail.stride(-1) != 1:
+            raise _lib.XkvError("decode_attention: k_tail / v_tail must share strides, unit inner stride")
+        sh, st = k_tail.stride(0), k_tail.stride(1)
+    check(_lib.load().xkv_decode_attention(
+        _ptr(q), hq, num_kv_heads, d, _ptr(a_k), a_k.stride(0), rk, _ptr(vk_layer), vk_layer.stride(0),
+        _ptr(a_v), a_v.stride(0), rv, _ptr(vv_layer), vv_layer.stride(0), s, _ptr(cos), _ptr(sin),
+        cos.stride(0) if cos is not None else 0, _ptr(k_tail if t else None), _ptr(v_tail if t else None), t, sh, st,
+        C.c_float(scale), _ptr(out), C.c_void_p(workspace.data_ptr()), workspace.numel(), _stream()))
+    return out
+
+
+def rope_bf16_(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
+    """In-place RoPE on token-major keys x (rows, H, D) bf16 with cos/sin (rows, D) bf16 (HF half-split)."""
+    _require_cuda(x, cos, sin)
+    rows, h, d = x.shape
+    if x.stride(2) != 1 or x.stride(1) != d:
+        raise _lib.XkvError("rope_bf16_: x must be (rows, H, D) with contiguous (H, D)")
+    check(_lib.load().xkv_rope_bf16(_ptr(x), x.stride(0), rows, h, d, _ptr(cos), _ptr(sin), cos.stride(0), _stream()))
+    return x
