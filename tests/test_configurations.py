@@ -96,14 +96,17 @@ def test_shipped_configs_load(path):
 @pytest.mark.skipif(not os.path.isdir("/root/reference/configs"), reason="reference tree only exists in the build container")
 @pytest.mark.parametrize("name", ["example.yaml", "example_xkv_config.yaml", "grouped_layers.yaml"])
 def test_reference_yaml_files_load_unchanged(name):
-    import sys
+    import importlib.util
 
     cfg = xKVConfig.from_yaml(os.path.join("/root/reference/configs", name))
-    sys.path.insert(0, "/root/reference")
-    try:
-        from xKV.configurations import xKVConfig as RefConfig  # the reference class, executed as the checker
-    finally:
-        sys.path.pop(0)
+    # the reference class, executed as the checker (loaded by path so it does not shadow the repo's xKV shim)
+    spec = importlib.util.spec_from_file_location("_ref_xkv_configurations", "/root/reference/xKV/configurations.py")
+    mod = importlib.util.module_from_spec(spec)
+    import sys
+
+    sys.modules[spec.name] = mod      # dataclasses resolves string annotations through sys.modules
+    spec.loader.exec_module(mod)
+    RefConfig = mod.xKVConfig
     ref = RefConfig.from_yaml(os.path.join("/root/reference/configs", name))
     assert cfg.to_dict() == ref.to_dict()
     assert [(g.layers, g.rank_k, g.rank_v, g.slerp_t, g.slerp_gamma) for g in cfg.layer_groups] == \

@@ -18,8 +18,8 @@ def _case(S, H, D, qpk, rk, rv, T, layers_in_group, layer, rope, seed=0):
     Hq = H * qpk
     a_k = (torch.randn(S, rk, generator=g) * 0.6).bfloat16()
     a_v = torch.randn(S, rv, generator=g).bfloat16()
-    v_k = torch.linalg.qr(torch.randn(n, rk, generator=g))[0].bfloat16()
-    v_v = torch.linalg.qr(torch.randn(n, rv, generator=g))[0].bfloat16()
+    v_k = torch.linalg.qr(torch.randn(n, rk, generator=g))[0].contiguous().bfloat16()
+    v_v = torch.linalg.qr(torch.randn(n, rv, generator=g))[0].contiguous().bfloat16()
     q = torch.randn(Hq, D, generator=g).bfloat16()
     k_tail = torch.randn(H, max(T, 1), D, generator=g).bfloat16()[:, :T]
     v_tail = torch.randn(H, max(T, 1), D, generator=g).bfloat16()[:, :T]

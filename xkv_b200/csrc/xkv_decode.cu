@@ -341,7 +341,7 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
   XKV_REQUIRE((cos == nullptr) == (sin == nullptr), "decode: cos and sin must both be given or both be null");
   XKV_REQUIRE(cos == nullptr || ld_cs % 8 == 0, "decode: cos/sin row stride must be a multiple of 8");
   XKV_REQUIRE(workspace_bytes >= xkv_decode_workspace_bytes(Hq, S, T, rv), "decode: workspace too small");
-  XKV_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "decode: workspace must be 1024-byte aligned");
+  XKV_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "decode: workspace must be 256-byte aligned");
   cudaStream_t st = as_stream(stream);
   const int qpk = Hq / H;
   const size_t L = static_cast<size_t>(S) + T;

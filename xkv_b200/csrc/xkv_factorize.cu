@@ -241,7 +241,7 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
   XKV_TRY(make_plan(P, bump, batch, m, n, rank, o));
   XKV_REQUIRE(!bump.overflow && P.bytes <= workspace_bytes, "factorize: workspace too small (%zu < %zu bytes)",
               workspace_bytes, P.bytes);
-  XKV_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "factorize: workspace must be 1024-byte aligned");
+  XKV_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "factorize: workspace must be 256-byte aligned");
   const int B = batch, l = P.l, r = rank, W = P.W, wl = P.wl, r0 = P.r0;
   const long long nn = n;
   cudaStream_t st = as_stream(stream);

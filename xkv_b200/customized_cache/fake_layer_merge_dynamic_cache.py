@@ -1,0 +1,259 @@
+"""``FakeLayerMergingCache`` on the B200 kernels.
+
+Same public surface as the reference class (fake_layer_merge_dynamic_cache.py:103-213) —
+``FakeLayerMergingCache(merge_setup)``, ``update(key, value, layer_idx, mode='prefill', cos=None, sin=None,
+re_apply_rope=True)``, ``is_key_merged``/``is_value_merged``, ``grouped_layer_merging``, ``update_cache`` —
+written against the installed transformers (layer-object caches).  What differs is what it *stores*:
+
+* the reference multiplies the truncated SVD back and keeps dense K^/V^ for every layer;
+* this cache keeps, per layer group, the factors ``A (S x r)`` and ``V (n x r)`` produced by
+  :func:`xkv_b200.compress.compress_groups`, plus a dense tail of the tokens appended during decode
+  (the reference never compresses those either: ``mode != 'prefill'`` skips merging, cache:131).
+
+Dense per-layer tensors are only produced on request (``update`` must return them for API parity, and the
+MLA caller uses the return value): ``K^_l = rope(bf16(A_k V_k[l]^T))`` through the tcgen05 GEMM engine and
+the bf16 RoPE kernel.  The decode hot path does not go through that: the patched attention forward calls
+:meth:`FakeLayerMergingCache.attend`, which runs the fused reconstruct+attention kernel.
+
+Only the SVD branch lives on the GPU path; ``layer_merge_impl='slerp'`` raises ``NotImplementedError``
+(next row).  Batch size 1 (the configs of BASELINE.json); larger batches raise.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from transformers.cache_utils import DynamicCache, DynamicLayer
+
+from .. import compress, factorize, ops
+from .._lib import XkvError
+from ..configurations import LayerGroup, xKVConfig
+
+
+class _XkvLayer(DynamicLayer):
+    """One layer's slot: dense prefill K/V until its group is compressed, then (group factors, dense tail)."""
+
+    def __init__(self):
+        super().__init__()
+        self.group: Optional["_GroupState"] = None   # set once the layer's group has been compressed
+        self.index_in_group = 0
+        self.prefill_len = 0
+        self.tail_k: Optional[torch.Tensor] = None   # (1, H, T, D) post-RoPE keys appended during decode
+        self.tail_v: Optional[torch.Tensor] = None
+        self.tail_len = 0
+        self.dense_k: Optional[torch.Tensor] = None  # a slot of a compressed group that stayed dense (merge flag off)
+        self.dense_v: Optional[torch.Tensor] = None
+
+    # --- sequence bookkeeping used by transformers' mask / position logic ---
+    def get_seq_length(self) -> int:
+        if self.group is None:
+            return super().get_seq_length()
+        return self.prefill_len + self.tail_len
+
+    def append_tail(self, k: torch.Tensor, v: torch.Tensor) -> None:
+        t = k.shape[-2]
+        need = self.tail_len + t
+        if self.tail_k is None or self.tail_k.shape[-2] < need:
+            cap = max(64, 2 * need)
+            new_k = torch.empty(k.shape[0], k.shape[1], cap, k.shape[3], dtype=k.dtype, device=k.device)
+            new_v = torch.empty_like(new_k)
+            if self.tail_len:
+                new_k[:, :, : self.tail_len] = self.tail_k[:, :, : self.tail_len]
+                new_v[:, :, : self.tail_len] = self.tail_v[:, :, : self.tail_len]
+            self.tail_k, self.tail_v = new_k, new_v
+        self.tail_k[:, :, self.tail_len:need] = k
+        self.tail_v[:, :, self.tail_len:need] = v
+        self.tail_len = need
+
+
+class _GroupState:
+    """Factors of one compressed group and the RoPE tables of its prefill positions."""
+
+    def __init__(self, info: LayerGroup, factors: compress.GroupFactors, heads: int, head_dim: int,
+                 cos: Optional[torch.Tensor], sin: Optional[torch.Tensor], re_apply_rope: bool):
+        self.info = info
+        self.factors = factors
+        self.heads = heads
+        self.head_dim = head_dim
+        self.cos = cos      # (S, D) bf16 or None
+        self.sin = sin
+        self.re_apply_rope = re_apply_rope
+
+
+class FakeLayerMergingCache(DynamicCache):
+    def __init__(self, merge_setup: xKVConfig, factorize_options: Optional[factorize.FactorizeOptions] = None):
+        super().__init__()
+        self.layer_class_to_replicate = _XkvLayer
+        self.num_layers = merge_setup.num_layers
+        self.merge_setup = merge_setup
+        self.factorize_options = factorize_options
+        self._groups: Dict[int, _GroupState] = {}
+        self._workspace: Optional[torch.Tensor] = None
+        self.num_heads: Optional[int] = None
+        self.head_dim: Optional[int] = None
+
+    # ------------------------------------------------------------------ reference surface
+    def _should_merge(self, layer_idx: int) -> bool:
+        """True when ``layer_idx`` is the last layer of its group (reference cache:113-119)."""
+        info = self.merge_setup.get_group_for_layer(layer_idx)
+        return info is not None and layer_idx == info.layers[-1]
+
+    def is_value_merged(self) -> bool:
+        return self.merge_setup.merge_value
+
+    def is_key_merged(self) -> bool:
+        return self.merge_setup.merge_key
+
+    def _layer(self, layer_idx: int) -> _XkvLayer:
+        while len(self.layers) <= layer_idx:
+            self.layers.append(_XkvLayer())
+        return self.layers[layer_idx]
+
+    def update(self, key, value, layer_idx, mode="prefill", cos=None, sin=None, re_apply_rope=True,
+               return_dense=True):
+        """Reference cache:127-153.  Prefill: stash the layer's (pre-RoPE) K and V; when the last layer of a
+        group arrives, compress the group; keys of un-grouped layers get RoPE immediately.  Decode: append
+        the (post-RoPE) token to the dense tail.  Returns dense (K_l, V_l) as the reference does;
+        ``return_dense=False`` (an extension used by callers that ignore the return, llama.py:46-49) skips
+        the materialisation."""
+        layer = self._layer(layer_idx)
+        if mode != "prefill":
+            if layer.group is None:
+                return DynamicLayer.update(layer, key, value)
+            layer.append_tail(key, value)
+            return self.materialize(layer_idx) if return_dense else (None, None)
+        if key.shape[0] != 1:
+            raise XkvError("FakeLayerMergingCache: batch size 1 only on the B200 path")
+        self.num_heads = key.shape[1]
+        self.head_dim = key.shape[3]
+        info = self.merge_setup.get_group_for_layer(layer_idx)
+        if info is None:
+            # un-grouped layer: exact cache, RoPE applied now (reference cache:149-152)
+            if re_apply_rope:
+                key = self._rope_dense(key, cos, sin)
+            return DynamicLayer.update(layer, key, value)
+        DynamicLayer.update(layer, key, value)
+        if self._should_merge(layer_idx):
+            self._merge_cos_sin = (cos, sin, re_apply_rope)
+            self.grouped_layer_merging(layer_idx)
+        if not return_dense:
+            return None, None
+        return self.materialize(layer_idx) if layer.group is not None else (layer.keys, layer.values)
+
+    @torch.no_grad()
+    def grouped_layer_merging(self, last_layer_idx: int) -> None:
+        """Reference cache:155-208 (svd branch): gather the group's layers, factorise K and V, drop the dense
+        copies.  Stream-ordered; no host synchronisation (the reference's cuda.synchronize/gc at :205-208 is
+        not a contract)."""
+        info = self.merge_setup.get_group_for_layer(last_layer_idx)
+        if info is None:
+            return
+        if self.merge_setup.layer_merge_impl != "svd":
+            raise NotImplementedError(
+                f"layer_merge_impl={self.merge_setup.layer_merge_impl!r}: only 'svd' runs on the B200 path")
+        first, last = info.layers[0], info.layers[-1]
+        ids = list(range(first, last + 1))            # the reference assumes contiguous groups (cache:165)
+        layers = [self._layer(i) for i in ids]
+        keys = [l.keys for l in layers]
+        values = [l.values for l in layers]
+        seq = keys[0].shape[-2]
+        merge_k = self.merge_setup.merge_key and self._rank_fits(info.rank_k, seq, len(ids))
+        merge_v = self.merge_setup.merge_value and self._rank_fits(info.rank_v, seq, len(ids))
+        if not (merge_k or merge_v):
+            cos, sin, re_rope = self._merge_cos_sin
+            if re_rope:       # nothing to compress (rank >= min(m, n) is a no-op in the reference, §9.6)
+                for l in layers:
+                    l.keys = self._rope_dense(l.keys, cos, sin)
+            return
+        (gf,) = compress.compress_groups([keys], [values], info.rank_k, info.rank_v, merge_key=merge_k,
+                                         merge_value=merge_v, opts=self.factorize_options, layer_ids=[ids])
+        cos, sin, re_rope = self._merge_cos_sin
+        cs = sn = None
+        if re_rope and cos is not None:
+            cs = cos[0].to(torch.bfloat16).contiguous()
+            sn = sin[0].to(torch.bfloat16).contiguous()
+        state = _GroupState(info, gf, self.num_heads, self.head_dim, cs, sn, bool(re_rope))
+        self._groups[first] = state
+        for pos, l in enumerate(layers):
+            l.group = state
+            l.index_in_group = pos
+            l.prefill_len = seq
+            # dense copies of whatever was factorised are released; a slot that stayed dense keeps its tensor
+            if gf.key is None:
+                l.dense_k = self._rope_dense(keys[pos], cos, sin) if re_rope else keys[pos]
+            l.dense_v = values[pos] if gf.value is None else None
+            l.keys = l.values = None
+
+    def _rank_fits(self, rank: Optional[int], seq: int, nlayers: int) -> bool:
+        if rank is None:
+            return False
+        n = nlayers * self.num_heads * self.head_dim
+        return 0 < rank <= seq and factorize.sketch_width(rank) <= n
+
+    def update_cache(self, layer_idx, key_approx, value_approx):
+        """Reference cache:210-213: overwrite a layer's dense tensors (kept for API parity; a layer whose
+        group has been factorised becomes dense again)."""
+        layer = self._layer(layer_idx)
+        layer.group = None
+        layer.keys, layer.values = key_approx, value_approx
+        layer.is_initialized = True
+
+    # ------------------------------------------------------------------ dense views (API parity path)
+    def _rope_dense(self, k: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
+        """HF apply_rotary_pos_emb on (1, H, S, D) keys via the bf16 RoPE kernel."""
+        bs, h, s, d = k.shape
+        x = k.transpose(1, 2).contiguous().view(s, h, d)          # token-major copy
+        ops.rope_bf16_(x, cos[0].to(torch.bfloat16).contiguous(), sin[0].to(torch.bfloat16).contiguous())
+        return x.view(1, s, h, d).transpose(1, 2)
+
+    @torch.no_grad()
+    def materialize(self, layer_idx: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Dense (K_l, V_l) of a compressed layer: rope(bf16(A_k V_k[l]^T)) || tail — what the reference keeps
+        in ``key_cache[l]`` / ``value_cache[l]`` after prefill."""
+        layer = self._layer(layer_idx)
+        st = layer.group
+        if st is None:
+            return layer.keys, layer.values
+        h, d, s = st.heads, st.head_dim, layer.prefill_len
+        rows = slice(layer.index_in_group * h * d, (layer.index_in_group + 1) * h * d)
+
+        def dense(f: Optional[factorize.Factors], kept: Optional[torch.Tensor], rope: bool) -> torch.Tensor:
+            if f is None:
+                return kept
+            x = torch.empty(s, h * d, dtype=torch.bfloat16, device=f.A.device)
+            ops.gemm_grouped([ops.make_problem([f.A], [f.V[rows]], x, M=s, N=h * d, K=f.rank)])
+            if rope and st.cos is not None:
+                ops.rope_bf16_(x.view(s, h, d), st.cos, st.sin)
+            return x.view(1, s, h, d).transpose(1, 2)
+
+        k = dense(st.factors.key, layer.dense_k, st.re_apply_rope)
+        v = dense(st.factors.value, layer.dense_v, False)
+        if layer.tail_len:
+            k = torch.cat([k, layer.tail_k[:, :, : layer.tail_len]], dim=-2)
+            v = torch.cat([v, layer.tail_v[:, :, : layer.tail_len]], dim=-2)
+        return k, v
+
+    # ------------------------------------------------------------------ decode hot path
+    @torch.no_grad()
+    def attend(self, query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, layer_idx: int,
+               scaling: float) -> Optional[torch.Tensor]:
+        """Decode step of one layer: append the new (post-RoPE) token and attend over the factored cache with
+        the fused kernel.  query (1, Hq, 1, D) -> (1, Hq, 1, D).  Returns None when the layer is not factored on
+        both sides (the caller then uses the dense path)."""
+        layer = self._layer(layer_idx)
+        st = layer.group
+        if st is None or st.factors.key is None or st.factors.value is None or query.shape[2] != 1:
+            return None
+        layer.append_tail(key, value)
+        h, d = st.heads, st.head_dim
+        rows = slice(layer.index_in_group * h * d, (layer.index_in_group + 1) * h * d)
+        fk, fv = st.factors.key, st.factors.value
+        need = ops.decode_workspace_bytes(query.shape[1], layer.prefill_len, layer.tail_len, fv.rank)
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = torch.empty(int(need * 1.25) + 4096, dtype=torch.uint8, device=query.device)
+        out = ops.decode_attention(
+            query[0, :, 0, :], fk.A, fk.V[rows], fv.A, fv.V[rows], h,
+            st.cos if st.re_apply_rope else None, st.sin if st.re_apply_rope else None,
+            layer.tail_k[0, :, : layer.tail_len], layer.tail_v[0, :, : layer.tail_len], scaling,
+            workspace=self._workspace)
+        return out[None, :, None, :]
