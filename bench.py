@@ -251,6 +251,58 @@ def run_xkv_arm(args):
         "gpu_launches": launches, "roofline": roofline,
     }
 
+    # ---- decode: fused reconstruct + RoPE + attention over the factors, all 32 layers = one token ----
+    if not args.no_decode:
+        import math
+
+        cos, sin = synthetic.llama3_rope(S, HEAD_DIM, device=dev)
+        cos, sin = cos[0].contiguous(), sin[0].contiguous()
+        hq = 32
+        gen = torch.Generator(device=dev).manual_seed(7)
+        q = torch.randn(LAYERS, hq, HEAD_DIM, device=dev, generator=gen).bfloat16()
+        kt = torch.randn(LAYERS, HEADS, 1, HEAD_DIM, device=dev, generator=gen).bfloat16()
+        vt = torch.randn(LAYERS, HEADS, 1, HEAD_DIM, device=dev, generator=gen).bfloat16()
+        ws = torch.empty(ops.decode_workspace_bytes(hq, S, 1, RANK_V) + 4096, dtype=torch.uint8, device=dev)
+        o = torch.empty(hq, HEAD_DIM, dtype=torch.bfloat16, device=dev)
+        hd = HEADS * HEAD_DIM
+
+        def one_token():
+            for l in range(LAYERS):
+                gf = out[l // GROUP]
+                i = l % GROUP
+                ops.decode_attention(q[l], gf.key.A, gf.key.V[i * hd:(i + 1) * hd], gf.value.A,
+                                     gf.value.V[i * hd:(i + 1) * hd], HEADS, cos, sin, kt[l], vt[l],
+                                     1.0 / math.sqrt(HEAD_DIM), out=o, workspace=ws)
+
+        for _ in range(3):
+            one_token()
+        barrier()
+        ntok = 8
+        l0 = ops.launch_count()
+        e0.record()
+        for _ in range(ntok):
+            one_token()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_tok = t.item() / ntok
+        flops_k = 2.0 * S * RANK_K * HEADS * HEAD_DIM * LAYERS          # K^ reconstruction, the tensor-bound part
+        bytes_a = float(S) * (RANK_K + RANK_V) * 2 * LAYERS             # token factors streamed once per layer
+        peak_hbm = float(peaks.get("hbm_gbs", 6550.0))
+        line["decode"] = {
+            "metric": "decode tok/s reconstructed (attention over the factored cache, 32 layers, batch 1, 64K context)",
+            "tok_s": world * 1e3 / ms_tok, "ms_per_token": ms_tok, "us_per_layer": 1e3 * ms_tok / LAYERS,
+            "equiv_dense_kv_GBps": world * LAYERS * 2.0 * S * HEADS * HEAD_DIM * 2 / (ms_tok * 1e-3) / 1e9,
+            "gpu_launches_per_token": (ops.launch_count() - l0) // ntok,
+            "roofline": {"bound": "tensor", "achieved": flops_k / (ms_tok * 1e-3) / 1e12, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": flops_k / (ms_tok * 1e-3) / 1e12 / peak_tf,
+                         "hbm_frac": bytes_a / (ms_tok * 1e-3) / 1e9 / peak_hbm,
+                         "note": "whole decode step (scores + softmax + P*A_v + combine) against the K^ reconstruction flops"},
+        }
+        del ws
+
     # ---- end to end through the public API with HOST buffers ----
     if not args.no_e2e:
         h_keys = [[t.transpose(1, 2).contiguous().cpu().pin_memory() for t in grp] for grp in keys]

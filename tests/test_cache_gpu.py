@@ -145,4 +145,7 @@ def test_ungrouped_layers_and_full_rank_groups_stay_exact():
     torch.cuda.synchronize()
     for l in range(3):   # layer 0 is un-grouped; group [1,2] has rank >= min(m, n): a no-op in the reference
         k, v = cache.materialize(l)
-        assert torch.equal(k, O.apply_rope(keys[l], cos, sin)) and torch.equal(v, vals[l])
+        k_ref = O.apply_rope(keys[l], cos, sin)
+        assert torch.equal(v, vals[l]), f"layer {l}: values changed"
+        assert k.shape == k_ref.shape and k.dtype == k_ref.dtype
+        assert torch.equal(k, k_ref), f"layer {l}: keys differ by {(k.float() - k_ref.float()).abs().max().item()}"

@@ -29,8 +29,8 @@ class GroupFactors:
 _side_streams = {}
 
 
-def _side_stream(device: torch.device) -> torch.cuda.Stream:
-    key = (device.type, device.index)
+def _side_stream(device: torch.device, index: int = 0) -> torch.cuda.Stream:
+    key = (device.type, device.index, index)
     if key not in _side_streams:
         _side_streams[key] = torch.cuda.Stream(device=device)
     return _side_streams[key]
@@ -56,10 +56,14 @@ def compress_groups(
     merge_value: bool = True,
     opts: Optional[factorize.FactorizeOptions] = None,
     layer_ids: Optional[Sequence[Sequence[int]]] = None,
-    two_streams: bool = True,
+    num_streams: int = 4,
 ) -> List[GroupFactors]:
     """Compress equally-shaped layer groups. keys[g][i] / values[g][i]: (1, H, S, D) bf16 of layer i of
-    group g (keys PRE-RoPE, as the reference hands them over, llama.py:49)."""
+    group g (keys PRE-RoPE, as the reference hands them over, llama.py:49).
+
+    The K matrices and the V matrices are independent factorisations; they are cut into up to
+    `num_streams` batches that run on separate CUDA streams, so that the latency-bound stages of one batch
+    (Cholesky panels, Jacobi) overlap the tensor-core GEMMs of another."""
     ng = len(keys)
     if ng == 0:
         return []
@@ -67,24 +71,34 @@ def compress_groups(
     main = torch.cuda.current_stream(dev)
     kf: List[Optional[factorize.Factors]] = [None] * ng
     vf: List[Optional[factorize.Factors]] = [None] * ng
-    side = _side_stream(dev) if (two_streams and merge_key and merge_value) else None
-    if merge_value:
-        if side is not None:
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                xv = pack_groups(values)
-                vf = factorize.factorize_batch(xv, rank_v, opts)
-                for x in xv:
-                    x.record_stream(side)
-        else:
-            vf = factorize.factorize_batch(pack_groups(values), rank_v, opts)
-    if merge_key:
-        kf = factorize.factorize_batch(pack_groups(keys), rank_k, opts)
-    if side is not None:
-        main.wait_stream(side)
-        for f in vf:
-            for t in (f.A, f.Vt, f.V, f.sigma_lead):
-                if t is not None:
-                    t.record_stream(main)
+    jobs = []   # (target list, first group, groups, rank)
+    sides = (["k"] if merge_key else []) + (["v"] if merge_value else [])
+    per_side = max(1, num_streams // max(len(sides), 1))
+    for side in sides:
+        src, dst, rank = (keys, kf, rank_k) if side == "k" else (values, vf, rank_v)
+        nchunk = min(per_side, ng)
+        size = (ng + nchunk - 1) // nchunk
+        for lo in range(0, ng, size):
+            jobs.append((dst, lo, src[lo:lo + size], rank))
+    used = []
+    for j, (dst, lo, groups, rank) in enumerate(jobs):
+        stream = main if (j == len(jobs) - 1 or num_streams <= 1) else _side_stream(dev, j)
+        if stream is not main:
+            stream.wait_stream(main)
+            used.append(stream)
+        with torch.cuda.stream(stream):
+            xs = pack_groups(groups)
+            fs = factorize.factorize_batch(xs, rank, opts)
+            if stream is not main:
+                for x in xs:
+                    x.record_stream(stream)
+        for i, f in enumerate(fs):
+            dst[lo + i] = f
+            if stream is not main:
+                for t in (f.A, f.Vt, f.V, f.sigma_lead):
+                    if t is not None:
+                        t.record_stream(main)
+    for stream in used:
+        main.wait_stream(stream)
     ids = layer_ids if layer_ids is not None else [list(range(len(g))) for g in keys]
     return [GroupFactors(layers=list(ids[g]), key=kf[g], value=vf[g]) for g in range(ng)]
