@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from the host instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -181,7 +182,13 @@ def run_xkv_arm(args):
 
     opts = factorize.FactorizeOptions()
 
+    graphed = None
+    if not args.no_graph:
+        graphed = compress.GraphedCompressor(keys, vals, RANK_K, RANK_V, opts=opts)
+
     def step():
+        if graphed is not None:
+            return graphed.replay()
         return compress.compress_groups(keys, vals, RANK_K, RANK_V, opts=opts)
 
     def barrier():
@@ -196,6 +203,14 @@ def run_xkv_arm(args):
     if rank == 0:
         sampler.start()
     launches0 = ops.launch_count()
+    launches_per_step = None
+    if graphed is not None:
+        # a replayed graph launches the captured kernels without passing through the library's counter
+        c0 = ops.launch_count()
+        compress.compress_groups(keys, vals, RANK_K, RANK_V, opts=opts)
+        launches_per_step = ops.launch_count() - c0
+        barrier()
+        launches0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -205,6 +220,8 @@ def run_xkv_arm(args):
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = ops.launch_count() - launches0
+    if launches_per_step is not None:
+        launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], device=dev)
     if world > 1:
@@ -249,6 +266,7 @@ def run_xkv_arm(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
         "gpu_launches": launches, "roofline": roofline,
+        "launch_mode": "cuda-graph replay" if graphed is not None else "host enqueue",
     }
 
     # ---- decode: fused reconstruct + RoPE + attention over the factors, all 32 layers = one token ----

@@ -102,3 +102,26 @@ def compress_groups(
         main.wait_stream(stream)
     ids = layer_ids if layer_ids is not None else [list(range(len(g))) for g in keys]
     return [GroupFactors(layers=list(ids[g]), key=kf[g], value=vf[g]) for g in range(ng)]
+
+
+class GraphedCompressor:
+    """compress_groups captured once into a CUDA graph and replayed (static input buffers).
+
+    The factorisation enqueues a few thousand small kernels per step; replaying a captured graph removes the
+    per-launch host cost, which otherwise leaves the GPU waiting during the latency-bound stages.  Inputs must
+    keep their addresses between replays (a serving loop that reuses its KV buffers, or bench.py)."""
+
+    def __init__(self, keys, values, rank_k, rank_v, merge_key=True, merge_value=True, opts=None, num_streams=4):
+        self._args = (keys, values, rank_k, rank_v, merge_key, merge_value, opts)
+        self._num_streams = num_streams
+        dev = keys[0][0].device
+        # warm-up outside capture: first-use attribute setting, allocator pools of the side streams
+        compress_groups(*self._args, num_streams=num_streams)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.result = compress_groups(*self._args, num_streams=num_streams)
+
+    def replay(self) -> List[GroupFactors]:
+        self.graph.replay()
+        return self.result

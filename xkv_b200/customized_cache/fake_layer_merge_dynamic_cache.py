@@ -202,7 +202,9 @@ class FakeLayerMergingCache(DynamicCache):
     def _rope_dense(self, k: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
         """HF apply_rotary_pos_emb on (1, H, S, D) keys via the bf16 RoPE kernel."""
         bs, h, s, d = k.shape
-        x = k.transpose(1, 2).contiguous().view(s, h, d)          # token-major copy
+        # token-major COPY: the caller's tensor must stay pre-RoPE (llama.py:50 rotates it again for prefill attention)
+        x = torch.empty(s, h, d, dtype=k.dtype, device=k.device)
+        x.copy_(k[0].transpose(0, 1))
         ops.rope_bf16_(x, cos[0].to(torch.bfloat16).contiguous(), sin[0].to(torch.bfloat16).contiguous())
         return x.view(1, s, h, d).transpose(1, 2)
 
