@@ -121,7 +121,11 @@ XKV_API int xkv_sqrt_clamp(const float* in, float* out, int count, void* stream)
  * Vt transposed (the layout the decode kernel reads). sigma[b] (optional) receives
  * xkv_factorize_sigma_count() leading singular-value estimates. Pure host code: enqueues the kernels
  * above on `stream`. stage_events_host (optional): 7 cudaEvent_t recorded at start / after the Gram
- * GEMM / Gram reduce+split / range finder / power iterations / Rayleigh-Ritz / projection. */
+ * GEMM / Gram reduce+split / range finder / power iterations / Rayleigh-Ritz / projection.
+ * Token-sharded use (rows of X split over GPUs): phase 1 writes each matrix's LOCAL Gram X_p^T X_p (n x n fp32,
+ * symmetric) to gram_host[b] and returns; the caller all-reduces those buffers (NCCL) and calls again with
+ * phase 2, which resumes from the reduced Gram and projects the local rows A_p = X_p V. phase 0 (gram_host may
+ * be NULL) does everything on one device. */
 typedef struct xkv_factorize_options {
   int32_t power_iters;    /* power steps on G after the range finder (default 6) */
   int32_t oversample;     /* extra sketch columns; sketch width l = round_up(rank + oversample, 64) */
@@ -143,8 +147,9 @@ XKV_API size_t xkv_factorize_workspace_bytes(int batch, int m, int n, int rank, 
 XKV_API int xkv_factorize_sigma_count(int rank, const xkv_factorize_options* opts);
 XKV_API int xkv_factorize_batch(const void* const* X_host, int batch, int m, int n, int64_t ldx, int rank,
                                 const xkv_factorize_options* opts, void* const* A_host, void* const* Vt_host,
-                                void* const* V_host, float* const* sigma_host, void* workspace,
-                                size_t workspace_bytes, void* const* stage_events_host, void* stream);
+                                void* const* V_host, float* const* sigma_host, float* const* gram_host,
+                                int phase, void* workspace, size_t workspace_bytes,
+                                void* const* stage_events_host, void* stream);
 
 /* ---- (3) decode-time attention over the factored cache: replaces the SDPA call over dense K^/V^ --------
  * llama.py:58-69 with the reconstruction of cache:26-27 and the RoPE of cache:142-148 fused in.

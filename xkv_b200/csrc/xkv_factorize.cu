@@ -228,14 +228,17 @@ extern "C" int xkv_factorize_sigma_count(int rank, const xkv_factorize_options* 
 
 extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, int n, int64_t ldx, int rank,
                                    const xkv_factorize_options* opts, void* const* A_host, void* const* Vt_host,
-                                   void* const* V_host, float* const* sigma_host, void* workspace,
-                                   size_t workspace_bytes, void* const* stage_events_host, void* stream) {
+                                   void* const* V_host, float* const* sigma_host, float* const* gram_host,
+                                   int phase, void* workspace, size_t workspace_bytes,
+                                   void* const* stage_events_host, void* stream) {
   xkv_factorize_options o;
   if (opts)
     o = *opts;
   else
     xkv_factorize_default_options(&o);
   XKV_REQUIRE(X_host && A_host && Vt_host && V_host && workspace, "factorize: null argument");
+  XKV_REQUIRE(phase >= 0 && phase <= 2, "factorize: phase must be 0 (all), 1 (Gram only) or 2 (resume from Gram)");
+  XKV_REQUIRE(phase == 0 || gram_host != nullptr, "factorize: phases 1/2 need the per-matrix Gram buffers");
   static thread_local Plan P;
   Bump bump{static_cast<char*>(workspace), 0, workspace_bytes, false};
   XKV_TRY(make_plan(P, bump, batch, m, n, rank, o));
@@ -256,22 +259,30 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
   XKV_TRY(mark());  // 0: start
 
   // ---- 1. Gram matrices and their bf16 limbs ----
-  for (int b = 0; b < B; ++b) {
-    xkv_gemm_problem p = problem(X_host[b], nullptr, nullptr, ldx, 1, X_host[b], nullptr, nullptr, ldx, 1,
-                                 P.gram_slabs + static_cast<size_t>(b) * P.gs * nn * nn, nn, n, n, m, 1);
-    p.sym_upper = 1;
-    p.split_k = P.gs;
-    p.split_stride = nn * nn;
-    ps.push_back(p);
+  // phase 1 stops after the (local) Gram so that token-sharded callers can all-reduce it; phase 2 resumes
+  // from the caller's reduced Gram.
+  if (phase != 2) {
+    for (int b = 0; b < B; ++b) {
+      xkv_gemm_problem p = problem(X_host[b], nullptr, nullptr, ldx, 1, X_host[b], nullptr, nullptr, ldx, 1,
+                                   P.gram_slabs + static_cast<size_t>(b) * P.gs * nn * nn, nn, n, n, m, 1);
+      p.sym_upper = 1;
+      p.split_k = P.gs;
+      p.split_stride = nn * nn;
+      ps.push_back(p);
+    }
+    XKV_TRY(run_gemms(ps, stream));
   }
-  XKV_TRY(run_gemms(ps, stream));
   XKV_TRY(mark());  // 1: Gram GEMM (the dominant kernel, timed on its own for the roofline)
   for (int b = 0; b < B; ++b) {
-    XKV_TRY(xkv_reduce_slabs(P.gram_slabs + static_cast<size_t>(b) * P.gs * nn * nn, P.gs, nn * nn, n, n, nn, 1, P.g32,
-                             nn, stream));
-    XKV_TRY(xkv_split_bf16(P.g32, n, n, nn, P.g_limb[b][0], P.g_limb[b][1], P.g_limb[b][2], nn, stream));
+    float* g = phase == 0 ? P.g32 : gram_host[b];
+    XKV_REQUIRE(g != nullptr, "factorize: null Gram buffer %d", b);
+    if (phase != 2)
+      XKV_TRY(xkv_reduce_slabs(P.gram_slabs + static_cast<size_t>(b) * P.gs * nn * nn, P.gs, nn * nn, n, n, nn, 1, g, nn,
+                               stream));
+    if (phase != 1) XKV_TRY(xkv_split_bf16(g, n, n, nn, P.g_limb[b][0], P.g_limb[b][1], P.g_limb[b][2], nn, stream));
   }
   XKV_TRY(mark());  // 2: Gram reduce + limb split
+  if (phase == 1) return 0;
 
   float** cur = P.f_a;
   float** nxt = P.f_b;

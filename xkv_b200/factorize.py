@@ -136,11 +136,15 @@ def workspace_bytes(batch: int, m: int, n: int, rank: int, opts: Optional[Factor
 
 
 def factorize_batch(xs: Sequence[torch.Tensor], rank: int, opts: Optional[FactorizeOptions] = None,
-                    workspace: Optional[torch.Tensor] = None) -> List[Factors]:
+                    workspace: Optional[torch.Tensor] = None, process_group=None) -> List[Factors]:
     """Factorise a batch of equally-shaped token-major matrices (m x n bf16) at rank `rank`.
 
     One call into the library's stream-ordered driver (xkv_factorize_batch); batches larger than the
-    C-ABI's per-call limit are processed in chunks that reuse one workspace."""
+    C-ABI's per-call limit are processed in chunks that reuse one workspace.
+
+    With `process_group` (torch.distributed, NCCL) the inputs are the LOCAL token shards of matrices whose
+    rows are split over the group's ranks: the local Gram matrices are summed with one all-reduce, every
+    rank derives the same right factor, and `A` holds the local rows only."""
     opts = opts or FactorizeOptions()
     if len(xs) == 0:
         return []
@@ -178,10 +182,22 @@ def factorize_batch(xs: Sequence[torch.Tensor], rank: int, opts: Optional[Factor
                 e.record()  # torch creates the cudaEvent lazily; recording materialises the handle
             ev_arr = (C.c_void_p * 7)(*[e.cuda_event for e in events])
             all_events.append(events)
-        _lib.check(lib.xkv_factorize_batch(
-            ops._ptr_array(part), nb, m, n, part[0].stride(0), r, C.byref(co), ops._ptr_array(a), ops._ptr_array(vt),
-            ops._ptr_array(v), ops._ptr_array(sig) if nsig else None, C.c_void_p(workspace.data_ptr()),
-            workspace.numel() * workspace.element_size(), ev_arr, stream))
+        def call(phase, grams):
+            _lib.check(lib.xkv_factorize_batch(
+                ops._ptr_array(part), nb, m, n, part[0].stride(0), r, C.byref(co), ops._ptr_array(a),
+                ops._ptr_array(vt), ops._ptr_array(v), ops._ptr_array(sig) if nsig else None,
+                ops._ptr_array(grams) if grams is not None else None, phase, C.c_void_p(workspace.data_ptr()),
+                workspace.numel() * workspace.element_size(), ev_arr, stream))
+
+        if process_group is None:
+            call(0, None)
+        else:
+            import torch.distributed as dist
+
+            grams = torch.empty(nb, n, n, dtype=torch.float32, device=dev)
+            call(1, list(grams))
+            dist.all_reduce(grams, op=dist.ReduceOp.SUM, group=process_group)
+            call(2, list(grams))
         for b in range(nb):
             out.append(Factors(A=a[b], Vt=vt[b], V=v[b], rank=r, sigma_lead=sig[b]))
     if opts.profile:
