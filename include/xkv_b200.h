@@ -174,6 +174,13 @@ XKV_API int xkv_decode_attention(const void* q, int Hq, int H, int D, const void
 XKV_API int xkv_rope_bf16(void* x, int64_t ld_row, int rows, int H, int D, const void* cos, const void* sin,
                           int64_t ld_cs, void* stream);
 
+/* ---- (4) append: project new token rows onto a group's right factor -------------------------------
+ * a_out (T x r bf16) = x_new (T x n bf16, the group's token-major rows from xkv_pack_group) * V (n x r bf16).
+ * An extension: the reference keeps decode tokens uncompressed (cache:131), so this is opt-in. */
+XKV_API size_t xkv_append_workspace_bytes(int T, int n, int r);
+XKV_API int xkv_append_project(const void* x_new, int64_t ldx, int T, const void* V, int64_t ldv, int n, int r,
+                               void* a_out, int64_t lda, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

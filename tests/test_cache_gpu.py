@@ -149,3 +149,41 @@ def test_ungrouped_layers_and_full_rank_groups_stay_exact():
         assert torch.equal(v, vals[l]), f"layer {l}: values changed"
         assert k.shape == k_ref.shape and k.dtype == k_ref.dtype
         assert torch.equal(k, k_ref), f"layer {l}: keys differ by {(k.float() - k_ref.float()).abs().max().item()}"
+
+
+def test_folding_decode_tokens_into_the_factors():
+    """Extension (north-star step 4, off by default): decode tokens are projected onto the group basis once
+    every layer of the group has seen them. Attention must stay close to the exact-tail result."""
+    from oracle import xkv_oracle as O
+    from tests.oracle_cache import OracleCache
+    from xkv_b200 import synthetic
+    from xkv_b200.customized_cache import FakeLayerMergingCache
+
+    G, H, S, D, qpk, steps = 4, 2, 640, 64, 4, 5
+    cfg, keys, vals, cos, sin = _setup(G=G, H=H, S=S + steps, D=D, layers=4)
+    cos_all, sin_all = synthetic.llama3_rope(S + steps, D, device="cuda")
+    ours = FakeLayerMergingCache(cfg, compress_decode_tokens=True, decode_capacity=64)
+    ref = OracleCache(cfg)
+    for l in range(4):
+        ours.update(keys[l][:, :, :S], vals[l][:, :, :S], l, mode="prefill", cos=cos_all[:, :S], sin=sin_all[:, :S],
+                    return_dense=False)
+        ref.update(keys[l][:, :, :S], vals[l][:, :, :S], l, mode="prefill", cos=cos_all[:, :S], sin=sin_all[:, :S])
+    g = torch.Generator(device="cuda").manual_seed(11)
+    worst = 0.0
+    for t in range(steps):
+        c, s_ = cos_all[:, S + t: S + t + 1], sin_all[:, S + t: S + t + 1]
+        for l in range(4):
+            q = torch.randn(1, H * qpk, 1, D, device="cuda", generator=g).bfloat16()
+            k_pre = keys[l][:, :, S + t: S + t + 1]          # decode tokens drawn from the same group model
+            v_new = vals[l][:, :, S + t: S + t + 1]
+            k_post = O.apply_rope(k_pre, c, s_)
+            out = ours.attend(q, k_post, v_new, l, 1.0 / math.sqrt(D), key_pre_rope=k_pre, cos=c, sin=s_)
+            k_all, v_all = ref.update(k_post, v_new, l, mode="decode")
+            exp = O.decode_attention(q.float(), k_all.float(), v_all.float(), scaling=1.0 / math.sqrt(D))
+            worst = max(worst, (out.float() - exp).abs().max().item() / exp.abs().max().item())
+    torch.cuda.synchronize()
+    st = ours._layer(0).group
+    assert st.length == S + steps and all(ours._layer(l).tail_len == 0 for l in range(4))
+    assert ours.get_seq_length() == S + steps
+    print(f"folded decode tokens: worst attention deviation {worst:.4f} of output scale")
+    assert worst < 5e-2

@@ -52,10 +52,12 @@ def xKV_llama_forward(  # noqa: N802
                          return_dense=False)
             key_states, _ = apply_rotary_pos_emb(key_states, key_states, cos, sin)
         else:
+            key_pre_rope = key_states
             key_states, _ = apply_rotary_pos_emb(key_states, key_states, cos, sin)
             fused = None
             if isinstance(cache, FakeLayerMergingCache) and getattr(self, "xkv_fused_decode", True):
-                fused = cache.attend(query_states, key_states, value_states, self.layer_idx, self.scaling)
+                fused = cache.attend(query_states, key_states, value_states, self.layer_idx, self.scaling,
+                                     key_pre_rope=key_pre_rope, cos=cos, sin=sin)
             if fused is not None:
                 attn_output = fused.transpose(1, 2).reshape(*input_shape, -1).contiguous()
                 return self.o_proj(attn_output), None

@@ -57,6 +57,7 @@ def compress_groups(
     opts: Optional[factorize.FactorizeOptions] = None,
     layer_ids: Optional[Sequence[Sequence[int]]] = None,
     num_streams: int = 4,
+    extra_rows: int = 0,
 ) -> List[GroupFactors]:
     """Compress equally-shaped layer groups. keys[g][i] / values[g][i]: (1, H, S, D) bf16 of layer i of
     group g (keys PRE-RoPE, as the reference hands them over, llama.py:49).
@@ -88,14 +89,14 @@ def compress_groups(
             used.append(stream)
         with torch.cuda.stream(stream):
             xs = pack_groups(groups)
-            fs = factorize.factorize_batch(xs, rank, opts)
+            fs = factorize.factorize_batch(xs, rank, opts, extra_rows=extra_rows)
             if stream is not main:
                 for x in xs:
                     x.record_stream(stream)
         for i, f in enumerate(fs):
             dst[lo + i] = f
             if stream is not main:
-                for t in (f.A, f.Vt, f.V, f.sigma_lead):
+                for t in (f.A_storage, f.Vt, f.V, f.sigma_lead):
                     if t is not None:
                         t.record_stream(main)
     for stream in used:

@@ -204,31 +204,30 @@ __global__ void __launch_bounds__(D_THREADS, 2) decode_scores_kernel(const __gri
   }
 }
 
-// scores of the dense tail tokens: scores[hq][S + t] = scale * q[hq] . k_tail[h][t]
-__global__ void __launch_bounds__(128) tail_scores_kernel(const __nv_bfloat16* __restrict__ q,
-                                                          const __nv_bfloat16* __restrict__ k_tail, long long sh,
-                                                          long long st, int Hq, int qpk, int D, int T, int S,
-                                                          float scale, float* __restrict__ scores, long long ld) {
-  const int t = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int hq = warp; hq < Hq; hq += 4) {
-    const int h = hq / qpk;
-    const __nv_bfloat16* kr = k_tail + h * sh + t * st;
-    float acc = 0.f;
-    for (int d = lane; d < D; d += 32) acc += __bfloat162float(q[hq * D + d]) * __bfloat162float(kr[d]);
-    acc = warp_sum(acc);
-    if (lane == 0) scores[hq * ld + S + t] = acc * scale;
-  }
-}
-
-// softmax over L = S + T scores of one q-head: p = exp(s - max) as bf16 (the GEMM operand), rowsum in fp32
-__global__ void __launch_bounds__(1024) softmax_kernel(const float* __restrict__ scores, long long ld, int L,
+// softmax over L = S + T scores of one q-head: p = exp(s - max) as bf16 (the GEMM operand), rowsum in fp32.
+// The scores of the T dense tail tokens (scale * q . k_tail) are computed here first.
+__global__ void __launch_bounds__(1024) softmax_kernel(float* __restrict__ scores, long long ld, int S, int T,
+                                                       const __nv_bfloat16* __restrict__ q,
+                                                       const __nv_bfloat16* __restrict__ k_tail, long long sh,
+                                                       long long st, int qpk, int D, float scale,
                                                        __nv_bfloat16* __restrict__ prob, long long ldp,
                                                        float* __restrict__ rowsum) {
   __shared__ float red[32];
   __shared__ float bcast;
-  const float* s = scores + blockIdx.x * ld;
-  __nv_bfloat16* p = prob + blockIdx.x * ldp;
+  const int hq = blockIdx.x;
+  float* s = scores + hq * ld;
+  __nv_bfloat16* p = prob + hq * ldp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int L = S + T;
+  const int h = hq / qpk;
+  for (int t = warp; t < T; t += 32) {
+    const __nv_bfloat16* kr = k_tail + h * sh + t * st;
+    float acc = 0.f;
+    for (int d = lane; d < D; d += 32) acc += __bfloat162float(q[hq * D + d]) * __bfloat162float(kr[d]);
+    acc = warp_sum(acc);
+    if (lane == 0) s[S + t] = acc * scale;
+  }
+  __syncthreads();
   float m = -INFINITY;
   for (int i = tid; i < L; i += 1024) m = fmaxf(m, s[i]);
   m = warp_max(m);
@@ -254,13 +253,14 @@ __global__ void __launch_bounds__(1024) softmax_kernel(const float* __restrict__
   if (warp == 0) {
     float v = red[lane];
     v = warp_sum(v);
-    if (lane == 0) rowsum[blockIdx.x] = v;
+    if (lane == 0) rowsum[hq] = v;
   }
 }
 
 // o[hq][d] = ( sum_j U[hq][j] * Bv[(h*D + d)][j]  +  sum_t p_tail[hq][t] * v_tail[h][t][d] ) / rowsum[hq]
-__global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ U, long long ldu, int rv,
-                                                      const __nv_bfloat16* __restrict__ Bv, long long ldb,
+// U = sum over the split-K slabs of P A_v (reduced here); grid (Hq, D / 32), 8 warps x 4 output dims.
+__global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ slabs, int nslabs, long long slab_stride,
+                                                      int rv, const __nv_bfloat16* __restrict__ Bv, long long ldb,
                                                       const __nv_bfloat16* __restrict__ prob, long long ldp, int S, int T,
                                                       const __nv_bfloat16* __restrict__ v_tail, long long sh, long long st,
                                                       const float* __restrict__ rowsum, int qpk, int D,
@@ -268,10 +268,15 @@ __global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ 
   extern __shared__ float u_s[];  // rv floats
   const int hq = blockIdx.x, h = hq / qpk;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int j = threadIdx.x; j < rv; j += blockDim.x) u_s[j] = U[hq * ldu + j];
+  for (int j = threadIdx.x; j < rv; j += blockDim.x) {
+    float acc = 0.f;
+    const float* p = slabs + static_cast<long long>(hq) * rv + j;
+    for (int sl = 0; sl < nslabs; ++sl) acc += p[sl * slab_stride];
+    u_s[j] = acc;
+  }
   __syncthreads();
   const float inv = 1.f / rowsum[hq];
-  for (int d = warp; d < D; d += 8) {
+  for (int d = blockIdx.y * 32 + warp; d < min(D, blockIdx.y * 32 + 32); d += 8) {
     const __nv_bfloat16* row = Bv + static_cast<long long>(h * D + d) * ldb;
     float acc = 0.f;
     for (int j = lane * 2; j < rv; j += 64) {
@@ -357,7 +362,6 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
   w += al(Hq * 4);
   float* u_slabs = reinterpret_cast<float*>(w);
   w += al(static_cast<size_t>(split) * Hq * rv * 4);
-  float* U = reinterpret_cast<float*>(w);
 
   // ---- scores of the compressed prefix: fused reconstruct + RoPE + q.K ----
   static thread_local ScoreParams sp;
@@ -393,14 +397,10 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
   else
     decode_scores_kernel<64><<<grid, D_THREADS, D_SMEM_BYTES, st>>>(sp);
   XKV_LAUNCHED();
-  // ---- scores of the dense tail ----
-  if (T > 0) {
-    tail_scores_kernel<<<T, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k_tail),
-                                          tail_stride_h, tail_stride_t, Hq, qpk, D, T, S, scale, scores, ldl);
-    XKV_LAUNCHED();
-  }
-  // ---- softmax ----
-  softmax_kernel<<<Hq, 1024, 0, st>>>(scores, ldl, static_cast<int>(L), prob, ldl, rowsum);
+  // ---- softmax (also scores the dense tail) ----
+  softmax_kernel<<<Hq, 1024, 0, st>>>(scores, ldl, S, T, static_cast<const __nv_bfloat16*>(q),
+                                      static_cast<const __nv_bfloat16*>(k_tail), tail_stride_h, tail_stride_t, qpk, D, scale,
+                                      prob, ldl, rowsum);
   XKV_LAUNCHED();
   // ---- U = P[:, :S] * A_v  (tokens are the contraction: P K-major, A_v MN-major) ----
   xkv_gemm_problem gp;
@@ -421,12 +421,11 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
   gp.split_stride = static_cast<long long>(Hq) * rv;
   rc = xkv_gemm_grouped(&gp, 1, stream);
   if (rc) return rc;
-  rc = xkv_reduce_slabs(u_slabs, split, static_cast<long long>(Hq) * rv, Hq, rv, rv, 0, U, rv, stream);
-  if (rc) return rc;
-  // ---- o = (U Bv_l^T + P_tail V_tail) / rowsum ----
-  combine_kernel<<<Hq, 256, rv * sizeof(float), st>>>(U, rv, rv, static_cast<const __nv_bfloat16*>(Vv_layer), ldv_v, prob,
-                                                      ldl, S, T, static_cast<const __nv_bfloat16*>(v_tail), tail_stride_h,
-                                                      tail_stride_t, rowsum, qpk, D, static_cast<__nv_bfloat16*>(out));
+  // ---- o = (U Bv_l^T + P_tail V_tail) / rowsum, U reduced over the split-K slabs on the fly ----
+  combine_kernel<<<dim3(Hq, (D + 31) / 32), 256, rv * sizeof(float), st>>>(
+      u_slabs, split, static_cast<long long>(Hq) * rv, rv, static_cast<const __nv_bfloat16*>(Vv_layer), ldv_v, prob, ldl, S,
+      T, static_cast<const __nv_bfloat16*>(v_tail), tail_stride_h, tail_stride_t, rowsum, qpk, D,
+      static_cast<__nv_bfloat16*>(out));
   XKV_LAUNCHED();
   return 0;
 }

@@ -40,6 +40,7 @@ class _XkvLayer(DynamicLayer):
         self.prefill_len = 0
         self.tail_k: Optional[torch.Tensor] = None   # (1, H, T, D) post-RoPE keys appended during decode
         self.tail_v: Optional[torch.Tensor] = None
+        self.tail_kpre: Optional[torch.Tensor] = None  # pre-RoPE copies, kept only when decode tokens get folded
         self.tail_len = 0
         self.dense_k: Optional[torch.Tensor] = None  # a slot of a compressed group that stayed dense (merge flag off)
         self.dense_v: Optional[torch.Tensor] = None
@@ -50,19 +51,24 @@ class _XkvLayer(DynamicLayer):
             return super().get_seq_length()
         return self.prefill_len + self.tail_len
 
-    def append_tail(self, k: torch.Tensor, v: torch.Tensor) -> None:
+    def append_tail(self, k: torch.Tensor, v: torch.Tensor, k_pre: Optional[torch.Tensor] = None) -> None:
         t = k.shape[-2]
         need = self.tail_len + t
         if self.tail_k is None or self.tail_k.shape[-2] < need:
             cap = max(64, 2 * need)
             new_k = torch.empty(k.shape[0], k.shape[1], cap, k.shape[3], dtype=k.dtype, device=k.device)
             new_v = torch.empty_like(new_k)
+            new_p = torch.empty_like(new_k) if k_pre is not None else None
             if self.tail_len:
                 new_k[:, :, : self.tail_len] = self.tail_k[:, :, : self.tail_len]
                 new_v[:, :, : self.tail_len] = self.tail_v[:, :, : self.tail_len]
-            self.tail_k, self.tail_v = new_k, new_v
+                if new_p is not None and self.tail_kpre is not None:
+                    new_p[:, :, : self.tail_len] = self.tail_kpre[:, :, : self.tail_len]
+            self.tail_k, self.tail_v, self.tail_kpre = new_k, new_v, new_p
         self.tail_k[:, :, self.tail_len:need] = k
         self.tail_v[:, :, self.tail_len:need] = v
+        if k_pre is not None:
+            self.tail_kpre[:, :, self.tail_len:need] = k_pre
         self.tail_len = need
 
 
@@ -81,8 +87,15 @@ class _GroupState:
 
 
 class FakeLayerMergingCache(DynamicCache):
-    def __init__(self, merge_setup: xKVConfig, factorize_options: Optional[factorize.FactorizeOptions] = None):
+    def __init__(self, merge_setup: xKVConfig, factorize_options: Optional[factorize.FactorizeOptions] = None,
+                 compress_decode_tokens: bool = False, decode_capacity: int = 4096):
+        """``compress_decode_tokens`` (extension, off by default: the reference keeps decode tokens exact,
+        cache:131): once every layer of a group has seen a decode token, its pre-RoPE key / value rows are
+        projected onto the group's right factors (xkv_append_project) and leave the dense tail.  Up to
+        ``decode_capacity`` tokens can be folded per group."""
         super().__init__()
+        self.compress_decode_tokens = compress_decode_tokens
+        self.decode_capacity = decode_capacity if compress_decode_tokens else 0
         self.layer_class_to_replicate = _XkvLayer
         self.num_layers = merge_setup.num_layers
         self.merge_setup = merge_setup
@@ -166,13 +179,18 @@ class FakeLayerMergingCache(DynamicCache):
                     l.keys = self._rope_dense(l.keys, cos, sin)
             return
         (gf,) = compress.compress_groups([keys], [values], info.rank_k, info.rank_v, merge_key=merge_k,
-                                         merge_value=merge_v, opts=self.factorize_options, layer_ids=[ids])
+                                         merge_value=merge_v, opts=self.factorize_options, layer_ids=[ids],
+                                         extra_rows=self.decode_capacity)
         cos, sin, re_rope = self._merge_cos_sin
         cs = sn = None
         if re_rope and cos is not None:
-            cs = cos[0].to(torch.bfloat16).contiguous()
-            sn = sin[0].to(torch.bfloat16).contiguous()
+            cs = torch.empty(seq + self.decode_capacity, cos.shape[-1], dtype=torch.bfloat16, device=cos.device)
+            sn = torch.empty_like(cs)
+            cs[:seq] = cos[0]
+            sn[:seq] = sin[0]
         state = _GroupState(info, gf, self.num_heads, self.head_dim, cs, sn, bool(re_rope))
+        state.length = seq
+        state.layer_ids = ids
         self._groups[first] = state
         for pos, l in enumerate(layers):
             l.group = state
@@ -223,9 +241,9 @@ class FakeLayerMergingCache(DynamicCache):
             if f is None:
                 return kept
             x = torch.empty(s, h * d, dtype=torch.bfloat16, device=f.A.device)
-            ops.gemm_grouped([ops.make_problem([f.A], [f.V[rows]], x, M=s, N=h * d, K=f.rank)])
+            ops.gemm_grouped([ops.make_problem([f.A_storage[:s]], [f.V[rows]], x, M=s, N=h * d, K=f.rank)])
             if rope and st.cos is not None:
-                ops.rope_bf16_(x.view(s, h, d), st.cos, st.sin)
+                ops.rope_bf16_(x.view(s, h, d), st.cos[:s], st.sin[:s])
             return x.view(1, s, h, d).transpose(1, 2)
 
         k = dense(st.factors.key, layer.dense_k, st.re_apply_rope)
@@ -238,24 +256,54 @@ class FakeLayerMergingCache(DynamicCache):
     # ------------------------------------------------------------------ decode hot path
     @torch.no_grad()
     def attend(self, query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, layer_idx: int,
-               scaling: float) -> Optional[torch.Tensor]:
+               scaling: float, key_pre_rope: Optional[torch.Tensor] = None, cos: Optional[torch.Tensor] = None,
+               sin: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         """Decode step of one layer: append the new (post-RoPE) token and attend over the factored cache with
         the fused kernel.  query (1, Hq, 1, D) -> (1, Hq, 1, D).  Returns None when the layer is not factored on
-        both sides (the caller then uses the dense path)."""
+        both sides (the caller then uses the dense path).  key_pre_rope / cos / sin of the new position are
+        only needed when decode tokens are folded into the factors (compress_decode_tokens)."""
         layer = self._layer(layer_idx)
         st = layer.group
         if st is None or st.factors.key is None or st.factors.value is None or query.shape[2] != 1:
             return None
-        layer.append_tail(key, value)
+        fold = self.compress_decode_tokens and key_pre_rope is not None
+        layer.append_tail(key, value, key_pre_rope if fold else None)
         h, d = st.heads, st.head_dim
         rows = slice(layer.index_in_group * h * d, (layer.index_in_group + 1) * h * d)
         fk, fv = st.factors.key, st.factors.value
         need = ops.decode_workspace_bytes(query.shape[1], layer.prefill_len, layer.tail_len, fv.rank)
         if self._workspace is None or self._workspace.numel() < need:
             self._workspace = torch.empty(int(need * 1.25) + 4096, dtype=torch.uint8, device=query.device)
+        n_tok = layer.prefill_len
         out = ops.decode_attention(
-            query[0, :, 0, :], fk.A, fk.V[rows], fv.A, fv.V[rows], h,
-            st.cos if st.re_apply_rope else None, st.sin if st.re_apply_rope else None,
+            query[0, :, 0, :], fk.A_storage[:n_tok], fk.V[rows], fv.A_storage[:n_tok], fv.V[rows], h,
+            st.cos[:n_tok] if st.re_apply_rope else None, st.sin[:n_tok] if st.re_apply_rope else None,
             layer.tail_k[0, :, : layer.tail_len], layer.tail_v[0, :, : layer.tail_len], scaling,
             workspace=self._workspace)
+        if fold and layer_idx == st.layer_ids[-1]:
+            self._fold_tail(st, cos, sin)
         return out[None, :, None, :]
+
+    @torch.no_grad()
+    def _fold_tail(self, st: "_GroupState", cos: Optional[torch.Tensor], sin: Optional[torch.Tensor]) -> None:
+        """North-star step 4: every layer of the group has now seen the same T tail tokens; gather their
+        pre-RoPE keys / values into the group's token-major rows, project them onto the right factors and
+        append the result to A_k / A_v.  The tokens leave the dense tails."""
+        layers = [self._layer(i) for i in st.layer_ids]
+        t = layers[0].tail_len
+        if t == 0 or any(l.tail_len != t or l.tail_kpre is None for l in layers):
+            return
+        fk, fv = st.factors.key, st.factors.value
+        if st.length + t > fk.A_storage.shape[0]:
+            return   # capacity exhausted: keep the tokens dense (still exact)
+        xk = ops.pack_group([l.tail_kpre[:, :, :t] for l in layers])[0]
+        xv = ops.pack_group([l.tail_v[:, :, :t] for l in layers])[0]
+        ops.append_project(xk, fk.V, out=fk.A_storage[st.length: st.length + t])
+        ops.append_project(xv, fv.V, out=fv.A_storage[st.length: st.length + t])
+        if st.re_apply_rope and cos is not None:
+            st.cos[st.length: st.length + t] = cos.reshape(-1, cos.shape[-1])[-t:]
+            st.sin[st.length: st.length + t] = sin.reshape(-1, sin.shape[-1])[-t:]
+        st.length += t
+        for l in layers:
+            l.prefill_len = st.length
+            l.tail_len = 0

@@ -66,6 +66,7 @@ class Factors:
     V: torch.Tensor                     # (n, r)  bf16  same, transposed (layout the decode kernel reads)
     rank: int
     sigma_lead: Optional[torch.Tensor] = None   # leading singular values (Ritz estimates), fp32
+    A_storage: Optional[torch.Tensor] = None    # A plus spare rows for appended tokens (A is a view of it)
     timings: Dict[str, float] = field(default_factory=dict)
 
     def reconstruct(self) -> torch.Tensor:
@@ -136,7 +137,7 @@ def workspace_bytes(batch: int, m: int, n: int, rank: int, opts: Optional[Factor
 
 
 def factorize_batch(xs: Sequence[torch.Tensor], rank: int, opts: Optional[FactorizeOptions] = None,
-                    workspace: Optional[torch.Tensor] = None, process_group=None) -> List[Factors]:
+                    workspace: Optional[torch.Tensor] = None, process_group=None, extra_rows: int = 0) -> List[Factors]:
     """Factorise a batch of equally-shaped token-major matrices (m x n bf16) at rank `rank`.
 
     One call into the library's stream-ordered driver (xkv_factorize_batch); batches larger than the
@@ -171,7 +172,9 @@ def factorize_batch(xs: Sequence[torch.Tensor], rank: int, opts: Optional[Factor
     for lo in range(0, len(xs), chunk):
         part = xs[lo:lo + chunk]
         nb = len(part)
-        a = [torch.empty(m, r, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
+        # `extra_rows` spare token rows behind A (for tokens appended later by xkv_append_project)
+        a_store = [torch.empty(m + extra_rows, r, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
+        a = [t[:m] for t in a_store]
         vt = [torch.empty(r, n, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
         v = [torch.empty(n, r, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
         sig = [torch.empty(nsig, dtype=torch.float32, device=dev) if nsig else None for _ in range(nb)]
@@ -199,7 +202,7 @@ def factorize_batch(xs: Sequence[torch.Tensor], rank: int, opts: Optional[Factor
             dist.all_reduce(grams, op=dist.ReduceOp.SUM, group=process_group)
             call(2, list(grams))
         for b in range(nb):
-            out.append(Factors(A=a[b], Vt=vt[b], V=v[b], rank=r, sigma_lead=sig[b]))
+            out.append(Factors(A=a[b], Vt=vt[b], V=v[b], rank=r, sigma_lead=sig[b], A_storage=a_store[b]))
     if opts.profile:
         torch.cuda.synchronize()
         timings: Dict[str, float] = {}

@@ -258,3 +258,25 @@ def rope_bf16_(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.T
         raise _lib.XkvError("rope_bf16_: x must be (rows, H, D) with contiguous (H, D)")
     check(_lib.load().xkv_rope_bf16(_ptr(x), x.stride(0), rows, h, d, _ptr(cos), _ptr(sin), cos.stride(0), _stream()))
     return x
+
+
+# ---------------------------------------------------------------------------------------------
+# (4) append: project new token rows onto a group's right factor
+# ---------------------------------------------------------------------------------------------
+def append_project(x_new: torch.Tensor, v: torch.Tensor, out: Optional[torch.Tensor] = None,
+                   workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """a_new (T, r) = x_new (T, n) @ V (n, r), bf16 in / fp32 accumulate / bf16 out."""
+    _require_cuda(x_new, v)
+    t, n = x_new.shape
+    r = v.shape[1]
+    if x_new.dtype != torch.bfloat16 or v.dtype != torch.bfloat16 or x_new.stride(1) != 1 or v.stride(1) != 1:
+        raise _lib.XkvError("append_project: bf16 operands with unit inner stride required")
+    lib = _lib.load()
+    need = int(lib.xkv_append_workspace_bytes(t, n, r))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=v.device)
+    if out is None:
+        out = torch.empty(t, r, dtype=torch.bfloat16, device=v.device)
+    check(lib.xkv_append_project(_ptr(x_new), x_new.stride(0), t, _ptr(v), v.stride(0), n, r, _ptr(out), out.stride(0),
+                                 C.c_void_p(workspace.data_ptr()), workspace.numel(), _stream()))
+    return out
