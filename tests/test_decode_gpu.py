@@ -60,8 +60,22 @@ def _case(S, H, D, qpk, rk, rv, T, layers_in_group, layer, rope, seed=0):
         (300, 3, 128, 1, 96, 160, 1, 2, 0, True),      # MHA (qpk 1), 3 heads: second n-tile half empty, rank not /64
     ],
 )
-def test_decode_attention_matches_oracle(S, H, D, qpk, rk, rv, T, G, layer, rope):
-    _case(S, H, D, qpk, rk, rv, T, G, layer, rope)
+@pytest.mark.parametrize("tiled", [False, True])
+def test_decode_attention_matches_oracle(S, H, D, qpk, rk, rv, T, G, layer, rope, tiled):
+    """tiled=False: persistent scores kernel (right-factor slice resident in shared memory);
+    tiled=True: the tile-per-CTA kernel used when that slice does not fit."""
+    from xkv_b200 import _lib
+
+    _lib.load().xkv_decode_force_tiled(int(tiled))
+    try:
+        _case(S, H, D, qpk, rk, rv, T, G, layer, rope)
+    finally:
+        _lib.load().xkv_decode_force_tiled(0)
+
+
+def test_decode_large_rank_falls_back_to_tiled_kernel():
+    # r_k = 1024: one head's slice is 256 KiB > 128 KiB of shared memory
+    _case(1024, 2, 128, 4, 1024, 256, 2, 2, 1, True)
 
 
 def test_rope_bf16_matches_hf_formula():

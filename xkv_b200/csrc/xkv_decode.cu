@@ -33,6 +33,7 @@ constexpr size_t D_SMEM_BYTES = DSTAGES * D_STAGE_BYTES + 1024 + 256 + DBN * D_M
 struct alignas(64) ScoreParams {
   CUtensorMap a_map;  // A_k  (S x r_k), box {64, 128}
   CUtensorMap b_map;  // Bk_l (H*D x r_k), box {64, 256}
+  CUtensorMap b_head_map;  // Bk_l, box {64, D}: one kv head (persistent kernel)
   const __nv_bfloat16* q;    // (Hq, D)
   const __nv_bfloat16* cos;  // (S, D) or null
   const __nv_bfloat16* sin;
@@ -204,6 +205,186 @@ __global__ void __launch_bounds__(D_THREADS, 2) decode_scores_kernel(const __gri
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM owns ONE kv head, keeps that head's slice of the right factor
+// (D x r_k bf16, <= 128 KiB) resident in shared memory for the whole launch and streams A_k token tiles
+// through a 4-stage TMA ring.  Two TMEM accumulators (2 x D columns) let the epilogue of tile i overlap the
+// MMAs of tile i+1.  Compared with the tile-per-CTA kernel above it never re-reads the right factor
+// (L2 -> SM traffic per layer 786 MB -> 536 MB at config 2) and has no per-tile prologue.
+// ---------------------------------------------------------------------------------------------
+constexpr int PA_STAGES = 4;
+constexpr int P_THREADS = 192;
+constexpr int PB_MAX_BYTES = 128 * 1024;
+constexpr size_t P_SMEM_BYTES = PB_MAX_BYTES + PA_STAGES * D_A_BYTES + 1024 + 256 + 128 * D_MAX_QPK * sizeof(float);
+
+template <int D>
+__global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(const __grid_constant__ ScoreParams P) {
+  constexpr int NCH = D / 32;
+  constexpr int B_KB_BYTES = D * DBK * 2;  // one 64-wide K block of the head's right factor
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + PB_MAX_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + PA_STAGES * D_A_BYTES);
+  uint64_t* empty_bar = full_bar + PA_STAGES;
+  uint64_t* tfull_bar = empty_bar + PA_STAGES;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;          // [2]
+  uint64_t* b_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_bar + 1);
+  float* q_s = reinterpret_cast<float*>(sA + PA_STAGES * D_A_BYTES + 256);  // [qpk][D]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x % P.H;
+  const int slot = blockIdx.x / P.H;
+  const int nslots = (gridDim.x - h + P.H - 1) / P.H;   // CTAs that share this head
+  const int ntiles = (P.S + DBM - 1) / DBM;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < PA_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);   // one arrive per epilogue warp
+    }
+    mbar_init(b_bar, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&P.a_map);
+    tma_prefetch_desc(&P.b_head_map);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * D < 32 ? 32 : 2 * D);
+  if (warp >= 2) {
+    for (int e = threadIdx.x - 64; e < P.qpk * D; e += 128)
+      q_s[e] = __bfloat162float(P.q[static_cast<long long>(h * P.qpk) * D + e]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(b_bar, static_cast<uint32_t>(P.nkb) * B_KB_BYTES);
+      for (int kb = 0; kb < P.nkb; ++kb) tma_load_2d(sB + kb * B_KB_BYTES, &P.b_head_map, b_bar, kb * DBK, h * D);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = slot; tile < ntiles; tile += nslots) {
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], D_A_BYTES);
+          tma_load_2d(sA + s * D_A_BYTES, &P.a_map, &full_bar[s], kb * DBK, tile * DBM);
+          if (++s == PA_STAGES) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(DBM, D, 0, 0);
+      mbar_wait(b_bar, 0);
+      int s = 0, acc = 0;
+      uint32_t ph = 0, acc_ph[2] = {0u, 0u};
+      const uint32_t b_base = smem_u32(sB);
+      for (int tile = slot; tile < ntiles; tile += nslots) {
+        mbar_wait(&tempty_bar[acc], acc_ph[acc] ^ 1u);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * D);
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + s * D_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < DBK / 16; ++k)
+            umma_bf16_ss(d_addr, umma_desc_sw128(a_base + k * 32, 16, 1024),
+                         umma_desc_sw128(b_base + kb * B_KB_BYTES + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+          if (++s == PA_STAGES) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc_ph[acc] ^= 1u;
+        acc ^= 1;
+      }
+    }
+  } else {
+    const int qd = warp & 3;
+    const bool rope = P.cos != nullptr;
+    int acc = 0;
+    uint32_t acc_ph[2] = {0u, 0u};
+    for (int tile = slot; tile < ntiles; tile += nslots) {
+      const int tok = tile * DBM + qd * 32 + lane;
+      const bool tok_ok = tok < P.S;
+      float sc[D_MAX_QPK];
+#pragma unroll
+      for (int g = 0; g < D_MAX_QPK; ++g) sc[g] = 0.f;
+      mbar_wait(&tfull_bar[acc], acc_ph[acc]);
+      acc_ph[acc] ^= 1u;
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + static_cast<uint32_t>(acc * D);
+#pragma unroll 1
+      for (int c = 0; c < NCH / 2; ++c) {
+        uint32_t cs[16], sn[16];
+        if (rope && tok_ok) {
+          const uint4* cp = reinterpret_cast<const uint4*>(P.cos + static_cast<long long>(tok) * P.ld_cs + c * 32);
+          const uint4* sp = reinterpret_cast<const uint4*>(P.sin + static_cast<long long>(tok) * P.ld_cs + c * 32);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const uint4 cv = cp[v], sv = sp[v];
+            cs[4 * v] = cv.x, cs[4 * v + 1] = cv.y, cs[4 * v + 2] = cv.z, cs[4 * v + 3] = cv.w;
+            sn[4 * v] = sv.x, sn[4 * v + 1] = sv.y, sn[4 * v + 2] = sv.z, sn[4 * v + 3] = sv.w;
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < 16; ++v) cs[v] = 0x3F803F80u, sn[v] = 0u;
+        }
+        uint32_t x1[32], x2[32];
+        __syncwarp();
+        tmem_ld_32x32(lane_addr + static_cast<uint32_t>(c * 32), x1);
+        tmem_ld_32x32(lane_addr + static_cast<uint32_t>((c + NCH / 2) * 32), x2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float k1 = bf16r(__uint_as_float(x1[j]));
+          const float k2 = bf16r(__uint_as_float(x2[j]));
+          float o1 = k1, o2 = k2;
+          if (rope) {
+            const uint32_t cw = cs[j >> 1], sw = sn[j >> 1];
+            const float cf = __uint_as_float((j & 1) ? (cw & 0xFFFF0000u) : (cw << 16));
+            const float sf = __uint_as_float((j & 1) ? (sw & 0xFFFF0000u) : (sw << 16));
+            o1 = bf16r(bf16r(k1 * cf) + bf16r(-k2 * sf));
+            o2 = bf16r(bf16r(k2 * cf) + bf16r(k1 * sf));
+          }
+          const int d1 = c * 32 + j, d2 = d1 + D / 2;
+#pragma unroll
+          for (int g = 0; g < D_MAX_QPK; ++g)
+            if (g < P.qpk) sc[g] = fmaf(q_s[g * D + d1], o1, fmaf(q_s[g * D + d2], o2, sc[g]));
+        }
+      }
+      // accumulator fully read: hand it back to the MMA warp before the (slow) global stores
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (tok_ok) {
+#pragma unroll
+        for (int g = 0; g < D_MAX_QPK; ++g)
+          if (g < P.qpk) P.scores[static_cast<long long>(h * P.qpk + g) * P.ld_scores + tok] = sc[g] * P.scale;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * D < 32 ? 32 : 2 * D);
+  }
+}
+
 // softmax over L = S + T scores of one q-head: p = exp(s - max) as bf16 (the GEMM operand), rowsum in fp32.
 // The scores of the T dense tail tokens (scale * q . k_tail) are computed here first.
 __global__ void __launch_bounds__(1024) softmax_kernel(float* __restrict__ scores, long long ld, int S, int T,
@@ -312,6 +493,7 @@ __global__ void __launch_bounds__(256) rope_bf16_kernel(__nv_bfloat16* __restric
 }
 
 static inline size_t al(size_t x) { return (x + 1023) / 1024 * 1024; }
+static bool g_force_tiled_scores = false;  // test hook: exercise the tile-per-CTA scores kernel
 
 }  // namespace xkv
 
@@ -370,6 +552,8 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
   if (rc) return rc;
   rc = encode_tmap_2d_bf16(&sp.b_map, Vk_layer, rk, static_cast<uint64_t>(H) * D, ldv_k, DBK, DBN);
   if (rc) return rc;
+  rc = encode_tmap_2d_bf16(&sp.b_head_map, Vk_layer, rk, static_cast<uint64_t>(H) * D, ldv_k, DBK, D);
+  if (rc) return rc;
   sp.q = static_cast<const __nv_bfloat16*>(q);
   sp.cos = static_cast<const __nv_bfloat16*>(cos);
   sp.sin = static_cast<const __nv_bfloat16*>(sin);
@@ -392,10 +576,32 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
                                         static_cast<int>(D_SMEM_BYTES)));
     configured = true;
   }
-  if (D == 128)
+  // persistent kernel when one head's slice of the right factor fits in shared memory
+  const bool persistent = static_cast<size_t>(sp.nkb) * D * DBK * 2 <= PB_MAX_BYTES && !g_force_tiled_scores;
+  if (persistent) {
+    static bool pconf = false;
+    if (!pconf) {
+      XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_persistent_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(P_SMEM_BYTES)));
+      XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_persistent_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(P_SMEM_BYTES)));
+      pconf = true;
+    }
+    int dev = 0, sms = 148;
+    XKV_CHECK_CUDA(cudaGetDevice(&dev));
+    XKV_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int ntiles = (S + DBM - 1) / DBM;
+    int pgrid = sms < ntiles * H ? sms : ntiles * H;
+    if (pgrid < H) pgrid = H;   // every head needs at least one CTA
+    if (D == 128)
+      decode_scores_persistent_kernel<128><<<pgrid, P_THREADS, P_SMEM_BYTES, st>>>(sp);
+    else
+      decode_scores_persistent_kernel<64><<<pgrid, P_THREADS, P_SMEM_BYTES, st>>>(sp);
+  } else if (D == 128) {
     decode_scores_kernel<128><<<grid, D_THREADS, D_SMEM_BYTES, st>>>(sp);
-  else
+  } else {
     decode_scores_kernel<64><<<grid, D_THREADS, D_SMEM_BYTES, st>>>(sp);
+  }
   XKV_LAUNCHED();
   // ---- softmax (also scores the dense tail) ----
   softmax_kernel<<<Hq, 1024, 0, st>>>(scores, ldl, S, T, static_cast<const __nv_bfloat16*>(q),
@@ -442,3 +648,6 @@ extern "C" int xkv_rope_bf16(void* x, int64_t ld_row, int rows, int H, int D, co
   XKV_LAUNCHED();
   return 0;
 }
+
+/* test hook: 1 forces the tile-per-CTA scores kernel, 0 restores the automatic choice */
+extern "C" void xkv_decode_force_tiled(int on) { g_force_tiled_scores = on != 0; }
