@@ -12,6 +12,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """The C-ABI library is a build artefact (git-ignored): compile it once if the tree has none.
+    nvcc cross-compiles sm_100a without a GPU; the product has no fallback if this fails."""
+    lib = os.path.join(ROOT, "xkv_b200", "libxkv_b200.so")
+    if not os.path.exists(lib):
+        import subprocess
+
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "xkv_b200", "csrc"), "-j8"])
+
+
 def pytest_collection_modifyitems(config, items):
     # GPU tests must never silently pass without a device
     try:

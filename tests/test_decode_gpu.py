@@ -75,7 +75,7 @@ def test_decode_attention_matches_oracle(S, H, D, qpk, rk, rv, T, G, layer, rope
 
 def test_decode_large_rank_falls_back_to_tiled_kernel():
     # r_k = 1024: one head's slice is 256 KiB > 128 KiB of shared memory
-    _case(1024, 2, 128, 4, 1024, 256, 2, 2, 1, True)
+    _case(1024, 2, 128, 4, 1024, 256, 2, 4, 1, True)
 
 
 def test_rope_bf16_matches_hf_formula():

@@ -213,9 +213,11 @@ __global__ void __launch_bounds__(D_THREADS, 2) decode_scores_kernel(const __gri
 // (L2 -> SM traffic per layer 786 MB -> 536 MB at config 2) and has no per-tile prologue.
 // ---------------------------------------------------------------------------------------------
 constexpr int PA_STAGES = 4;
-constexpr int P_THREADS = 192;
+constexpr int P_EPI_WARPS = 8;                    // two warps per TMEM lane quarter: each takes half of the dims
+constexpr int P_THREADS = 64 + 32 * P_EPI_WARPS;  // TMA warp + MMA warp + epilogue warps
 constexpr int PB_MAX_BYTES = 128 * 1024;
-constexpr size_t P_SMEM_BYTES = PB_MAX_BYTES + PA_STAGES * D_A_BYTES + 1024 + 256 + 128 * D_MAX_QPK * sizeof(float);
+constexpr size_t P_SMEM_BYTES = PB_MAX_BYTES + PA_STAGES * D_A_BYTES + 1024 + 256 + 128 * D_MAX_QPK * sizeof(float) +
+                                2 * DBM * D_MAX_QPK * sizeof(float);
 
 template <int D>
 __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(const __grid_constant__ ScoreParams P) {
@@ -231,7 +233,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
   uint64_t* tempty_bar = tfull_bar + 2;          // [2]
   uint64_t* b_bar = tempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_bar + 1);
-  float* q_s = reinterpret_cast<float*>(sA + PA_STAGES * D_A_BYTES + 256);  // [qpk][D]
+  float* q_s = reinterpret_cast<float*>(sA + PA_STAGES * D_A_BYTES + 256);  // [D][8]: q heads of this kv head, dim-major
+  float* part = q_s + 128 * D_MAX_QPK;                                      // [2][128 tokens][8] partial scores
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x % P.H;
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);   // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], P_EPI_WARPS);   // one arrive per epilogue warp
     }
     mbar_init(b_bar, 1);
     mbar_fence_init();
@@ -255,8 +258,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
   }
   if (warp == 1) tmem_alloc(tmem_slot, 2 * D < 32 ? 32 : 2 * D);
   if (warp >= 2) {
-    for (int e = threadIdx.x - 64; e < P.qpk * D; e += 128)
-      q_s[e] = __bfloat162float(P.q[static_cast<long long>(h * P.qpk) * D + e]);
+    for (int e = threadIdx.x - 64; e < D * D_MAX_QPK; e += 32 * P_EPI_WARPS) {
+      const int d = e / D_MAX_QPK, g = e - d * D_MAX_QPK;
+      q_s[e] = g < P.qpk ? __bfloat162float(P.q[static_cast<long long>(h * P.qpk + g) * D + d]) : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -286,10 +291,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
       constexpr uint32_t idesc = umma_idesc_bf16(DBM, D, 0, 0);
       mbar_wait(b_bar, 0);
       int s = 0, acc = 0;
-      uint32_t ph = 0, acc_ph[2] = {0u, 0u};
+      uint32_t ph = 0, ph_acc0 = 0u, ph_acc1 = 0u;
       const uint32_t b_base = smem_u32(sB);
       for (int tile = slot; tile < ntiles; tile += nslots) {
-        mbar_wait(&tempty_bar[acc], acc_ph[acc] ^ 1u);   // epilogue has drained this accumulator
+        const uint32_t aph = acc ? ph_acc1 : ph_acc0;
+        mbar_wait(&tempty_bar[acc], aph ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * D);
         for (int kb = 0; kb < P.nkb; ++kb) {
@@ -307,27 +313,31 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
           }
         }
         umma_commit(&tfull_bar[acc]);
-        acc_ph[acc] ^= 1u;
+        if (acc) ph_acc1 ^= 1u; else ph_acc0 ^= 1u;
         acc ^= 1;
       }
     }
   } else {
-    const int qd = warp & 3;
+    // ===== epilogue: 8 warps; warps 2-5 take the chunk pairs with even index, warps 6-9 the odd ones =====
+    const int ew = warp - 2;
+    const int qd = warp & 3;             // TMEM lane quarter (hardware: warp id mod 4)
+    const int half = ew >> 2;
+    const int row = qd * 32 + lane;      // token row inside the tile
     const bool rope = P.cos != nullptr;
     int acc = 0;
-    uint32_t acc_ph[2] = {0u, 0u};
+    uint32_t ph_acc0 = 0u, ph_acc1 = 0u;
     for (int tile = slot; tile < ntiles; tile += nslots) {
-      const int tok = tile * DBM + qd * 32 + lane;
+      const int tok = tile * DBM + row;
       const bool tok_ok = tok < P.S;
       float sc[D_MAX_QPK];
 #pragma unroll
       for (int g = 0; g < D_MAX_QPK; ++g) sc[g] = 0.f;
-      mbar_wait(&tfull_bar[acc], acc_ph[acc]);
-      acc_ph[acc] ^= 1u;
+      mbar_wait(&tfull_bar[acc], acc ? ph_acc1 : ph_acc0);
+      if (acc) ph_acc1 ^= 1u; else ph_acc0 ^= 1u;
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + static_cast<uint32_t>(acc * D);
 #pragma unroll 1
-      for (int c = 0; c < NCH / 2; ++c) {
+      for (int c = half; c < NCH / 2; c += 2) {
         uint32_t cs[16], sn[16];
         if (rope && tok_ok) {
           const uint4* cp = reinterpret_cast<const uint4*>(P.cos + static_cast<long long>(tok) * P.ld_cs + c * 32);
@@ -360,21 +370,39 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
             o2 = bf16r(bf16r(k2 * cf) + bf16r(k1 * sf));
           }
           const int d1 = c * 32 + j, d2 = d1 + D / 2;
-#pragma unroll
-          for (int g = 0; g < D_MAX_QPK; ++g)
-            if (g < P.qpk) sc[g] = fmaf(q_s[g * D + d1], o1, fmaf(q_s[g * D + d2], o2, sc[g]));
+          const float4 qa = *reinterpret_cast<const float4*>(q_s + d1 * D_MAX_QPK);
+          const float4 qb = *reinterpret_cast<const float4*>(q_s + d2 * D_MAX_QPK);
+          sc[0] = fmaf(qa.x, o1, fmaf(qb.x, o2, sc[0]));
+          sc[1] = fmaf(qa.y, o1, fmaf(qb.y, o2, sc[1]));
+          sc[2] = fmaf(qa.z, o1, fmaf(qb.z, o2, sc[2]));
+          sc[3] = fmaf(qa.w, o1, fmaf(qb.w, o2, sc[3]));
+          if (P.qpk > 4) {
+            const float4 qc = *reinterpret_cast<const float4*>(q_s + d1 * D_MAX_QPK + 4);
+            const float4 qe = *reinterpret_cast<const float4*>(q_s + d2 * D_MAX_QPK + 4);
+            sc[4] = fmaf(qc.x, o1, fmaf(qe.x, o2, sc[4]));
+            sc[5] = fmaf(qc.y, o1, fmaf(qe.y, o2, sc[5]));
+            sc[6] = fmaf(qc.z, o1, fmaf(qe.z, o2, sc[6]));
+            sc[7] = fmaf(qc.w, o1, fmaf(qe.w, o2, sc[7]));
+          }
         }
       }
-      // accumulator fully read: hand it back to the MMA warp before the (slow) global stores
+      // accumulator fully read by this warp: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      acc ^= 1;
-      if (tok_ok) {
+      // combine the two halves' partial scores through shared memory (double-buffered by accumulator)
+      float* pt = part + (acc * DBM + row) * D_MAX_QPK;
+      if (half == 1) {
+#pragma unroll
+        for (int g = 0; g < D_MAX_QPK; ++g) pt[g] = sc[g];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * P_EPI_WARPS) : "memory");   // epilogue warps only
+      if (half == 0 && tok_ok) {
 #pragma unroll
         for (int g = 0; g < D_MAX_QPK; ++g)
-          if (g < P.qpk) P.scores[static_cast<long long>(h * P.qpk + g) * P.ld_scores + tok] = sc[g] * P.scale;
+          if (g < P.qpk) P.scores[static_cast<long long>(h * P.qpk + g) * P.ld_scores + tok] = (sc[g] + pt[g]) * P.scale;
       }
+      acc ^= 1;
     }
   }
   tc_fence_before();

@@ -253,22 +253,61 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(const __grid_constant__
     X[r * NBP + c] = (r == c) ? 1.f : 0.f;  // residual of the forward substitution L X = I
   }
   __syncthreads();
+  // Blocked right-looking factorisation, panels of PB columns: warp 0 factors a panel with warp-level
+  // synchronisation only (and finishes the matching rows of X = L^{-1} by forward substitution), then all
+  // threads apply the rank-PB update to the trailing triangle of D and to the residual rows of X.
+  // 2 block-wide barriers per panel (16 in total) instead of 2 per column.
+  constexpr int PB = 8;
   const int ur = tid >> 4, uc = tid & 15;
-  for (int j = 0; j < NB; ++j) {
+  const int lane = tid & 31;
+  for (int jb = 0; jb < NB; jb += PB) {
     if (tid < 32) {
-      const float d = fmaxf(D[j * NBP + j], p.pivot_floor);
-      const float inv = rsqrtf(d);
-      __syncwarp();
-      for (int r = j + 1 + tid; r < NB; r += 32) D[r * NBP + j] *= inv;     // column j of L
-      for (int c = tid; c <= j; c += 32) X[j * NBP + c] *= inv;            // row j of L^{-1} is final
-      if (tid == 0) D[j * NBP + j] = d * inv;
+      for (int jj = 0; jj < PB; ++jj) {
+        const int j = jb + jj;
+        const float d = fmaxf(D[j * NBP + j], p.pivot_floor);
+        const float inv = rsqrtf(d);
+        __syncwarp();
+        for (int r = j + 1 + lane; r < NB; r += 32) D[r * NBP + j] *= inv;   // column j of L
+        if (lane == 0) D[j * NBP + j] = d * inv;
+        __syncwarp();
+        // update the remaining columns of the panel
+        for (int r = j + 1 + lane; r < NB; r += 32) {
+          const float lr = D[r * NBP + j];
+          for (int c = j + 1; c < jb + PB; ++c)
+            if (c <= r) D[r * NBP + c] -= lr * D[c * NBP + j];
+        }
+        __syncwarp();
+      }
+      // rows jb..jb+PB-1 of X: X[j][c] = (R[j][c] - sum_{t=jb}^{j-1} L[j][t] X[t][c]) / L[j][j],  c <= j
+      for (int jj = 0; jj < PB; ++jj) {
+        const int j = jb + jj;
+        const float invd = 1.f / D[j * NBP + j];
+        for (int c = lane; c <= j; c += 32) {
+          float v = X[j * NBP + c];
+          for (int t = jb; t < j; ++t) v -= D[j * NBP + t] * X[t * NBP + c];
+          X[j * NBP + c] = v * invd;
+        }
+        __syncwarp();
+      }
     }
     __syncthreads();
-    // rank-1 sweeps: trailing triangle of D, and the residual rows of X below j
-    for (int r = j + 1 + ur; r < NB; r += 16) {
-      const float lr = D[r * NBP + j];
-      for (int c = j + 1 + uc; c <= r; c += 16) D[r * NBP + c] -= lr * D[c * NBP + j];
-      for (int c = uc; c <= j; c += 16) X[r * NBP + c] -= lr * X[j * NBP + c];
+    const int c0 = jb + PB;
+    for (int r = c0 + ur; r < NB; r += 16) {
+      float lr[PB];
+#pragma unroll
+      for (int t = 0; t < PB; ++t) lr[t] = D[r * NBP + jb + t];
+      for (int c = c0 + uc; c <= r; c += 16) {
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < PB; ++t) acc = fmaf(lr[t], D[c * NBP + jb + t], acc);
+        D[r * NBP + c] -= acc;
+      }
+      for (int c = uc; c < c0; c += 16) {
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < PB; ++t) acc = fmaf(lr[t], X[(jb + t) * NBP + c], acc);
+        X[r * NBP + c] -= acc;
+      }
     }
     __syncthreads();
   }
