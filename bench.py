@@ -248,7 +248,9 @@ def run_xkv_arm(args):
     achieved = alg_flops / (gram_ms * 1e-3) / 1e12
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "gram_traffic.json"))).get("dram_bytes_per_launch")
+        per_matrix = json.load(open(os.path.join(ROOT, "profiles", "gram_traffic.json"))).get("dram_bytes_per_matrix")
+        if per_matrix is not None and S == 65536:
+            traffic = per_matrix * ng      # one launch covers the ng matrices of the batch
     except Exception:
         pass
     roofline = {

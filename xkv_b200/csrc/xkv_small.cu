@@ -236,6 +236,40 @@ __device__ __forceinline__ float* block_ptr(float* base, int bi, int bj, long lo
   return base + (static_cast<long long>(bi) * NB) * ld + static_cast<long long>(bj) * NB;
 }
 
+// ---- warp-level 32x32 Cholesky and triangular inverse, matrix rows held in registers (lane = row) ----
+// a[c] = row `lane` of the symmetric block (entries c <= lane are used).  On return a[c] = L[lane][c], c <= lane.
+__device__ __forceinline__ void warp_chol32(float (&a)[32], float pivot_floor) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float d = __shfl_sync(0xffffffffu, a[j], j);
+    d = fmaxf(d, pivot_floor);
+    const float inv = rsqrtf(d);
+    const float lij = lane > j ? a[j] * inv : (lane == j ? d * inv : 0.f);
+    a[j] = lij;
+#pragma unroll
+    for (int c = j + 1; c < 32; ++c) {
+      const float lcj = __shfl_sync(0xffffffffu, lij, c);
+      a[c] = fmaf(-lij, lcj, a[c]);
+    }
+  }
+}
+// x[r] = (L^{-1})[r][lane] (column `lane` of the inverse), L given as register rows a[] (lane = row).
+__device__ __forceinline__ void warp_triinv32(const float (&a)[32], float (&x)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    float s = lane == r ? 1.f : 0.f;
+#pragma unroll
+    for (int t = 0; t < r; ++t) {
+      const float lrt = __shfl_sync(0xffffffffu, a[t], r);
+      s = fmaf(-lrt, x[t], s);
+    }
+    const float lrr = __shfl_sync(0xffffffffu, a[r], r);
+    x[r] = lane <= r ? s / lrr : 0.f;
+  }
+}
+
 __global__ void __launch_bounds__(256) chol_panel_kernel(const __grid_constant__ CholParams p) {
   __shared__ __align__(16) float buf0[TILE_FLOATS];  // D (natural, stride NBP) during the factor, then Di^T (k-major)
   __shared__ __align__(16) float buf1[TILE_FLOATS];  // X = D^{-1} (natural, stride NBP), then the panel block (k-major)
@@ -250,67 +284,87 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(const __grid_constant__
   for (int e = tid; e < NB * NB; e += blockDim.x) {
     const int r = e >> 6, c = e & 63;
     D[r * NBP + c] = dblk[static_cast<long long>(r) * p.ld + c] + (r == c ? p.shift : 0.f);
-    X[r * NBP + c] = (r == c) ? 1.f : 0.f;  // residual of the forward substitution L X = I
+    X[r * NBP + c] = 0.f;
   }
   __syncthreads();
-  // Blocked right-looking factorisation, panels of PB columns: warp 0 factors a panel with warp-level
-  // synchronisation only (and finishes the matching rows of X = L^{-1} by forward substitution), then all
-  // threads apply the rank-PB update to the trailing triangle of D and to the residual rows of X.
-  // 2 block-wide barriers per panel (16 in total) instead of 2 per column.
-  constexpr int PB = 8;
-  const int ur = tid >> 4, uc = tid & 15;
+  // 64x64 = 2x2 blocks of 32.  Warp 0 factors and inverts the diagonal 32x32 blocks in registers
+  // (warp_chol32 / warp_triinv32: shuffles only, no block barriers); the off-diagonal work between them
+  // is four small block products done by all threads.  X accumulates D^{-1} in natural layout.
   const int lane = tid & 31;
-  for (int jb = 0; jb < NB; jb += PB) {
+  // X starts as zero here (the identity written above is not used by this scheme)
+  auto diag_block = [&](int o) {
     if (tid < 32) {
-      for (int jj = 0; jj < PB; ++jj) {
-        const int j = jb + jj;
-        const float d = fmaxf(D[j * NBP + j], p.pivot_floor);
-        const float inv = rsqrtf(d);
-        __syncwarp();
-        for (int r = j + 1 + lane; r < NB; r += 32) D[r * NBP + j] *= inv;   // column j of L
-        if (lane == 0) D[j * NBP + j] = d * inv;
-        __syncwarp();
-        // update the remaining columns of the panel
-        for (int r = j + 1 + lane; r < NB; r += 32) {
-          const float lr = D[r * NBP + j];
-          for (int c = j + 1; c < jb + PB; ++c)
-            if (c <= r) D[r * NBP + c] -= lr * D[c * NBP + j];
-        }
-        __syncwarp();
-      }
-      // rows jb..jb+PB-1 of X: X[j][c] = (R[j][c] - sum_{t=jb}^{j-1} L[j][t] X[t][c]) / L[j][j],  c <= j
-      for (int jj = 0; jj < PB; ++jj) {
-        const int j = jb + jj;
-        const float invd = 1.f / D[j * NBP + j];
-        for (int c = lane; c <= j; c += 32) {
-          float v = X[j * NBP + c];
-          for (int t = jb; t < j; ++t) v -= D[j * NBP + t] * X[t * NBP + c];
-          X[j * NBP + c] = v * invd;
-        }
-        __syncwarp();
-      }
+      float a[32], x[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) a[c] = D[(o + lane) * NBP + o + c];
+      warp_chol32(a, p.pivot_floor);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) D[(o + lane) * NBP + o + c] = c <= lane ? a[c] : 0.f;
+      warp_triinv32(a, x);
+#pragma unroll
+      for (int r = 0; r < 32; ++r) X[(o + r) * NBP + o + lane] = x[r];
+    }
+  };
+  diag_block(0);
+  __syncthreads();
+  // L21 = A21 * X11^T : L21[i][j] = sum_c A21[i][c] X11[j][c]      (i in 32..63; j, c < 32)
+  float l21[4];
+  {
+    const int i = 32 + (tid >> 3), j0 = (tid & 7) * 4;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float acc = 0.f;
+      for (int c = 0; c <= j0 + u; ++c) acc = fmaf(D[i * NBP + c], X[(j0 + u) * NBP + c], acc);
+      l21[u] = acc;
     }
     __syncthreads();
-    const int c0 = jb + PB;
-    for (int r = c0 + ur; r < NB; r += 16) {
-      float lr[PB];
 #pragma unroll
-      for (int t = 0; t < PB; ++t) lr[t] = D[r * NBP + jb + t];
-      for (int c = c0 + uc; c <= r; c += 16) {
-        float acc = 0.f;
-#pragma unroll
-        for (int t = 0; t < PB; ++t) acc = fmaf(lr[t], D[c * NBP + jb + t], acc);
-        D[r * NBP + c] -= acc;
-      }
-      for (int c = uc; c < c0; c += 16) {
-        float acc = 0.f;
-#pragma unroll
-        for (int t = 0; t < PB; ++t) acc = fmaf(lr[t], X[(jb + t) * NBP + c], acc);
-        X[r * NBP + c] -= acc;
-      }
-    }
-    __syncthreads();
+    for (int u = 0; u < 4; ++u) D[i * NBP + j0 + u] = l21[u];
   }
+  __syncthreads();
+  // A22 -= L21 L21^T (lower triangle of the trailing 32x32 block)
+  {
+    const int i = 32 + (tid >> 3), j0 = 32 + (tid & 7) * 4;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u;
+      if (j <= i) {
+        float acc = 0.f;
+        for (int c = 0; c < 32; ++c) acc = fmaf(D[i * NBP + c], D[j * NBP + c], acc);
+        D[i * NBP + j] -= acc;
+      }
+    }
+  }
+  __syncthreads();
+  diag_block(32);
+  __syncthreads();
+  // X21 = -X22 * (L21 * X11):  first T = L21 * X11 (T[i][j] = sum_{c>=j} L21[i][c] X11[c][j]) ...
+  float tacc[4];
+  {
+    const int i = 32 + (tid >> 3), j0 = (tid & 7) * 4;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float acc = 0.f;
+      for (int c = j0 + u; c < 32; ++c) acc = fmaf(D[i * NBP + c], X[c * NBP + j0 + u], acc);
+      tacc[u] = acc;
+    }
+    __syncthreads();
+    // stage T in the (unused) upper-right corner of D: rows 0..31, columns 32..63 hold T^T
+#pragma unroll
+    for (int u = 0; u < 4; ++u) D[(j0 + u) * NBP + i] = tacc[u];
+  }
+  __syncthreads();
+  // ... then X21[i][j] = - sum_{t<=i} X22[i][t] T[t][j]
+  {
+    const int i = 32 + (tid >> 3), j0 = (tid & 7) * 4;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float acc = 0.f;
+      for (int t = 32; t <= i; ++t) acc = fmaf(X[i * NBP + t], D[(j0 + u) * NBP + t], acc);
+      X[i * NBP + j0 + u] = -acc;
+    }
+  }
+  __syncthreads();
   if (i == k) {
     // Only the inverse of the diagonal block is published: L[k,k] itself is never read again, and
     // writing it over S[k,k] would race with the other CTAs of this launch still loading that block.
