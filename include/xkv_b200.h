@@ -85,10 +85,16 @@ XKV_API int xkv_gemm_grouped(const xkv_gemm_problem* problems_host, int num_prob
  * from the upper one (Gram). rows x cols, ld in elements. */
 XKV_API int xkv_reduce_slabs(const float* slabs, int num_slabs, int64_t slab_stride, int rows, int cols, int64_t ld,
                      int symmetrize, float* out, int64_t ld_out, void* stream);
+XKV_API int xkv_reduce_slabs_batched(const float* const* slabs_host, float* const* out_host, int batch, int num_slabs,
+                                     int64_t slab_stride, int rows, int cols, int64_t ld, int symmetrize,
+                                     int64_t ld_out, void* stream);
 /* split an fp32 matrix into bf16 limbs: hi = bf16(x), mid = bf16(x-hi), lo = bf16(x-hi-mid).
  * mid / lo may be NULL. */
 XKV_API int xkv_split_bf16(const float* x, int rows, int cols, int64_t ld, void* hi, void* mid, void* lo,
                    int64_t ld_out, void* stream);
+XKV_API int xkv_split_bf16_batched(const float* const* x_host, void* const* hi_host, void* const* mid_host,
+                                   void* const* lo_host, int batch, int rows, int cols, int64_t ld, int64_t ld_out,
+                                   void* stream);
 /* deterministic N(0,1) test matrix rounded to bf16 (counter-based generator) */
 XKV_API int xkv_fill_gaussian_bf16(void* out, int rows, int cols, int64_t ld, uint64_t seed, void* stream);
 /* Batched row normalisation: every row of Y[b] (rows x cols fp32, each row is a column of the sketch)

@@ -79,6 +79,8 @@ SIGNATURES = {
     "xkv_unpack_group": (_i, [_vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _pp, _vp]),
     "xkv_gemm_grouped": (_i, [C.POINTER(GemmProblem), _i, _vp]),
     "xkv_reduce_slabs": (_i, [_vp, _i, _i64, _i, _i, _i64, _i, _vp, _i64, _vp]),
+    "xkv_reduce_slabs_batched": (_i, [_pp, _pp, _i, _i, _i64, _i, _i, _i64, _i, _i64, _vp]),
+    "xkv_split_bf16_batched": (_i, [_pp, _pp, _pp, _pp, _i, _i, _i, _i64, _i64, _vp]),
     "xkv_split_bf16": (_i, [_vp, _i, _i, _i64, _vp, _vp, _vp, _i64, _vp]),
     "xkv_fill_gaussian_bf16": (_i, [_vp, _i, _i, _i64, C.c_uint64, _vp]),
     "xkv_normalize_rows": (_i, [_pp, _pp, _pp, _pp, _i, _i, _i, _i64, _i64, _vp]),

@@ -304,11 +304,13 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
         ps.push_back(p);
       }
       XKV_TRY(run_gemms(ps, stream));
-      for (int b = 0; b < B; ++b)
-        XKV_TRY(xkv_reduce_slabs(P.s_slabs[b], P.sk, static_cast<long long>(l) * l, l, l, l, 1, P.s_mat[b], l, stream));
+      XKV_TRY(xkv_reduce_slabs_batched(P.s_slabs, P.s_mat, B, P.sk, static_cast<long long>(l) * l, l, l, l, 1, l, stream));
       XKV_TRY(xkv_cholesky_inverse(P.s_mat, P.linv, B, l, l, o.shifts[ip < 3 ? ip : 3], o.pivot_floor, stream));
-      for (int b = 0; b < B; ++b)
-        XKV_TRY(xkv_split_bf16(P.linv[b], l, l, l, P.linv_l[b][0], P.linv_l[b][1], P.linv_l[b][2], l, stream));
+      {
+        void *h0[XKV_MAX_BATCH], *h1[XKV_MAX_BATCH], *h2[XKV_MAX_BATCH];
+        for (int b = 0; b < B; ++b) h0[b] = P.linv_l[b][0], h1[b] = P.linv_l[b][1], h2[b] = P.linv_l[b][2];
+        XKV_TRY(xkv_split_bf16_batched(P.linv, h0, h1, h2, B, l, l, l, l, stream));
+      }
       for (int b = 0; b < B; ++b)
         ps.push_back(problem(P.linv_l[b][0], P.linv_l[b][1], P.linv_l[b][2], l, 0, P.lh[b], P.lm[b], P.ll[b], nn, 1,
                              nxt[b], nn, l, n, l, 6));
@@ -335,7 +337,7 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
 
   // ---- 4. power steps ----
   for (int it = 0; it < o.power_iters; ++it) {
-    for (int b = 0; b < B; ++b) XKV_TRY(xkv_split_bf16(cur[b], l, n, nn, P.lh[b], P.lm[b], nullptr, nn, stream));
+    XKV_TRY(xkv_split_bf16_batched(cur, P.lh, P.lm, nullptr, B, l, n, nn, nn, stream));
     XKV_TRY(apply_gram(3));
     XKV_TRY(cholqr(it == o.power_iters - 1 ? o.final_passes : o.passes));
   }
@@ -345,7 +347,7 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
   if (P.rr) {
     const int nw = P.nw;
     const int w0s[2] = {r0, 0};
-    for (int b = 0; b < B; ++b) XKV_TRY(xkv_split_bf16(cur[b], l, n, nn, P.lh[b], P.lm[b], P.ll[b], nn, stream));
+    XKV_TRY(xkv_split_bf16_batched(cur, P.lh, P.lm, P.ll, B, l, n, nn, nn, stream));
     for (int b = 0; b < B; ++b)
       for (int w = 0; w < nw; ++w)
         ps.push_back(problem(row_bf16(P.lh[b], w0s[w], nn), row_bf16(P.lm[b], w0s[w], nn), row_bf16(P.ll[b], w0s[w], nn),

@@ -9,14 +9,22 @@
 
 namespace xkv {
 
+static int sm_count();
+
 // =============================================================================================
 // split-K slab reduction (+ symmetrisation of the Gram matrix)
 // =============================================================================================
+struct ReduceParams {
+  const float* slabs[XKV_MAX_BATCH];
+  float* out[XKV_MAX_BATCH];
+};
 template <int SYM>
-__global__ void __launch_bounds__(256) reduce_slabs_kernel(const float* __restrict__ slabs, int num_slabs,
+__global__ void __launch_bounds__(256) reduce_slabs_kernel(const __grid_constant__ ReduceParams rp, int num_slabs,
                                                            long long slab_stride, int rows, int cols, long long ld,
-                                                           float* __restrict__ out, long long ldo, int tiles_per_row) {
+                                                           long long ldo, int tiles_per_row) {
   __shared__ float tile[32][33];
+  const float* __restrict__ slabs = rp.slabs[blockIdx.y];
+  float* __restrict__ out = rp.out[blockIdx.y];
   int bi, bj;
   if (SYM) {
     // linear index over tile pairs bi <= bj
@@ -67,9 +75,18 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16&
   l = __float2bfloat16_rn(r2);
 }
 
-__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, int rows, int cols, long long ld,
-                                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
-                                                         __nv_bfloat16* __restrict__ lo, long long ldo) {
+struct SplitParams {
+  const float* x[XKV_MAX_BATCH];
+  __nv_bfloat16* hi[XKV_MAX_BATCH];
+  __nv_bfloat16* mid[XKV_MAX_BATCH];
+  __nv_bfloat16* lo[XKV_MAX_BATCH];
+};
+__global__ void __launch_bounds__(256) split_bf16_kernel(const __grid_constant__ SplitParams sp, int rows, int cols,
+                                                         long long ld, long long ldo) {
+  const float* __restrict__ x = sp.x[blockIdx.y];
+  __nv_bfloat16* __restrict__ hi = sp.hi[blockIdx.y];
+  __nv_bfloat16* __restrict__ mid = sp.mid[blockIdx.y];
+  __nv_bfloat16* __restrict__ lo = sp.lo[blockIdx.y];
   const int cols4 = cols >> 2;  // host guarantees cols % 4 == 0
   const long long total = static_cast<long long>(rows) * cols4;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -489,9 +506,11 @@ struct JacobiParams {
 };
 constexpr int JAC_THREADS = 512;
 
+// WT > 0: window width known at compile time (index arithmetic becomes shifts / multiplies); WT == 0: p.W
+template <int WT>
 __global__ void __launch_bounds__(JAC_THREADS, 1) jacobi_kernel(const __grid_constant__ JacobiParams p) {
   extern __shared__ float jsm[];
-  const int W = p.W, WP = W + 1, H = W / 2;
+  const int W = WT > 0 ? WT : p.W, WP = W + 1, H = W / 2;
   float* A = jsm;                 // W x WP
   float* V = A + W * WP;          // W x WP
   float* cs = V + W * WP;         // 2 * H
@@ -623,36 +642,65 @@ static int sm_count() {
 
 using namespace xkv;
 
-extern "C" int xkv_reduce_slabs(const float* slabs, int num_slabs, int64_t slab_stride, int rows, int cols, int64_t ld,
-                                int symmetrize, float* out, int64_t ld_out, void* stream) {
-  XKV_REQUIRE(slabs && out && num_slabs >= 1 && rows > 0 && cols > 0, "reduce_slabs: bad arguments");
+extern "C" int xkv_reduce_slabs_batched(const float* const* slabs_host, float* const* out_host, int batch, int num_slabs,
+                                        int64_t slab_stride, int rows, int cols, int64_t ld, int symmetrize,
+                                        int64_t ld_out, void* stream) {
+  XKV_REQUIRE(slabs_host && out_host && batch >= 1 && batch <= XKV_MAX_BATCH, "reduce_slabs: bad batch");
+  XKV_REQUIRE(num_slabs >= 1 && rows > 0 && cols > 0, "reduce_slabs: bad arguments");
+  ReduceParams rp;
+  std::memset(&rp, 0, sizeof(rp));
+  for (int b = 0; b < batch; ++b) {
+    XKV_REQUIRE(slabs_host[b] && out_host[b], "reduce_slabs: null matrix %d", b);
+    rp.slabs[b] = slabs_host[b];
+    rp.out[b] = out_host[b];
+  }
   const int tr = (rows + 31) / 32, tc = (cols + 31) / 32;
   if (symmetrize) {
     XKV_REQUIRE(rows == cols, "reduce_slabs: symmetrize needs a square matrix");
-    const int grid = tr * (tr + 1) / 2;
-    reduce_slabs_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(slabs, num_slabs, slab_stride, rows, cols, ld, out,
-                                                                ld_out, tr);
+    reduce_slabs_kernel<1><<<dim3(tr * (tr + 1) / 2, batch), 256, 0, as_stream(stream)>>>(rp, num_slabs, slab_stride, rows,
+                                                                                      cols, ld, ld_out, tr);
   } else {
-    reduce_slabs_kernel<0><<<tr * tc, 256, 0, as_stream(stream)>>>(slabs, num_slabs, slab_stride, rows, cols, ld, out,
-                                                                   ld_out, tc);
+    reduce_slabs_kernel<0><<<dim3(tr * tc, batch), 256, 0, as_stream(stream)>>>(rp, num_slabs, slab_stride, rows, cols, ld,
+                                                                                ld_out, tc);
   }
+  XKV_LAUNCHED();
+  return 0;
+}
+
+extern "C" int xkv_reduce_slabs(const float* slabs, int num_slabs, int64_t slab_stride, int rows, int cols, int64_t ld,
+                                int symmetrize, float* out, int64_t ld_out, void* stream) {
+  XKV_REQUIRE(slabs && out, "reduce_slabs: bad arguments");
+  return xkv_reduce_slabs_batched(&slabs, &out, 1, num_slabs, slab_stride, rows, cols, ld, symmetrize, ld_out, stream);
+}
+
+extern "C" int xkv_split_bf16_batched(const float* const* x_host, void* const* hi_host, void* const* mid_host,
+                                      void* const* lo_host, int batch, int rows, int cols, int64_t ld, int64_t ld_out,
+                                      void* stream) {
+  XKV_REQUIRE(x_host && hi_host && batch >= 1 && batch <= XKV_MAX_BATCH, "split_bf16: bad batch");
+  XKV_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0 && ld % 4 == 0 && ld_out % 4 == 0,
+              "split_bf16: cols/ld must be multiples of 4");
+  SplitParams sp;
+  std::memset(&sp, 0, sizeof(sp));
+  for (int b = 0; b < batch; ++b) {
+    XKV_REQUIRE(x_host[b] && hi_host[b], "split_bf16: null matrix %d", b);
+    sp.x[b] = x_host[b];
+    sp.hi[b] = static_cast<__nv_bfloat16*>(hi_host[b]);
+    sp.mid[b] = mid_host ? static_cast<__nv_bfloat16*>(mid_host[b]) : nullptr;
+    sp.lo[b] = lo_host ? static_cast<__nv_bfloat16*>(lo_host[b]) : nullptr;
+  }
+  const long long total = static_cast<long long>(rows) * (cols / 4);
+  long long grid = (total + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 16 / batch + 1;
+  if (grid > cap) grid = cap;
+  split_bf16_kernel<<<dim3(static_cast<int>(grid), batch), 256, 0, as_stream(stream)>>>(sp, rows, cols, ld, ld_out);
   XKV_LAUNCHED();
   return 0;
 }
 
 extern "C" int xkv_split_bf16(const float* x, int rows, int cols, int64_t ld, void* hi, void* mid, void* lo,
                               int64_t ld_out, void* stream) {
-  XKV_REQUIRE(x && hi && rows > 0 && cols > 0, "split_bf16: bad arguments");
-  XKV_REQUIRE(cols % 4 == 0 && ld % 4 == 0 && ld_out % 4 == 0, "split_bf16: cols/ld must be multiples of 4");
-  const long long total = static_cast<long long>(rows) * (cols / 4);
-  long long grid = (total + 255) / 256;
-  const long long cap = static_cast<long long>(sm_count()) * 16;
-  if (grid > cap) grid = cap;
-  split_bf16_kernel<<<static_cast<int>(grid), 256, 0, as_stream(stream)>>>(
-      x, rows, cols, ld, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(mid),
-      static_cast<__nv_bfloat16*>(lo), ld_out);
-  XKV_LAUNCHED();
-  return 0;
+  XKV_REQUIRE(x && hi, "split_bf16: bad arguments");
+  return xkv_split_bf16_batched(&x, &hi, mid ? &mid : nullptr, lo ? &lo : nullptr, 1, rows, cols, ld, ld_out, stream);
 }
 
 extern "C" int xkv_fill_gaussian_bf16(void* out, int rows, int cols, int64_t ld, uint64_t seed, void* stream) {
@@ -751,10 +799,17 @@ extern "C" int xkv_jacobi_eigh(const float* const* T_host, float* const* evals_h
   const size_t smem = static_cast<size_t>(2 * W * (W + 1) + 2 * W) * sizeof(float) + 64;
   static bool configured = false;
   if (!configured) {
-    XKV_CHECK_CUDA(cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    XKV_CHECK_CUDA(cudaFuncSetAttribute(jacobi_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    XKV_CHECK_CUDA(cudaFuncSetAttribute(jacobi_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    XKV_CHECK_CUDA(cudaFuncSetAttribute(jacobi_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     configured = true;
   }
-  jacobi_kernel<<<count, JAC_THREADS, smem, as_stream(stream)>>>(p);
+  if (W == 128)
+    jacobi_kernel<128><<<count, JAC_THREADS, smem, as_stream(stream)>>>(p);
+  else if (W == 160)
+    jacobi_kernel<160><<<count, JAC_THREADS, smem, as_stream(stream)>>>(p);
+  else
+    jacobi_kernel<0><<<count, JAC_THREADS, smem, as_stream(stream)>>>(p);
   XKV_LAUNCHED();
   return 0;
 }
