@@ -135,9 +135,9 @@ XKV_API int xkv_sqrt_clamp(const float* in, float* out, int count, void* stream)
 typedef struct xkv_factorize_options {
   int32_t power_iters;    /* power steps on G after the range finder (default 6) */
   int32_t oversample;     /* extra sketch columns; sketch width l = round_up(rank + oversample, 64) */
-  int32_t first_passes;   /* CholeskyQR passes after the range finder (3) */
+  int32_t first_passes;   /* CholeskyQR passes after the range finder (2) */
   int32_t passes;         /* CholeskyQR passes after a power step (2) */
-  int32_t final_passes;   /* CholeskyQR passes after the last power step (3) */
+  int32_t final_passes;   /* CholeskyQR passes after the last power step (2) */
   int32_t window;         /* Rayleigh-Ritz window width, <= 160 (default 128) */
   int32_t jacobi_sweeps;
   int32_t rayleigh_ritz;  /* 0: keep the first `rank` basis vectors as they are */

@@ -68,3 +68,41 @@ def test_generate_through_the_patch():
     torch.cuda.synchronize()
     assert out.shape == (1, 305)
     assert ops.launch_count() > before      # the CUDA path ran (no silent eager fallback)
+
+
+def _mla_model():
+    from transformers import DeepseekV2Config, DeepseekV2ForCausalLM
+
+    cfg = DeepseekV2Config(hidden_size=256, intermediate_size=512, moe_intermediate_size=128, num_hidden_layers=3,
+                           num_attention_heads=4, num_key_value_heads=4, kv_lora_rank=512, q_lora_rank=None,
+                           qk_nope_head_dim=64, qk_rope_head_dim=64, v_head_dim=64, head_dim=64, vocab_size=512,
+                           n_routed_experts=4, n_shared_experts=1, num_experts_per_tok=2, first_k_dense_replace=3,
+                           max_position_embeddings=4096)
+    cfg._attn_implementation = "sdpa"
+    torch.manual_seed(0)
+    return DeepseekV2ForCausalLM(cfg).to(device="cuda", dtype=torch.bfloat16).eval()
+
+
+def test_patched_deepseek_v2_mla_matches_oracle_cache():
+    """latent-slot caching (kv_lora_rank 512 in the key slot, k_pe in the value slot,
+    re_apply_rope=False, merge_value=False), prefill AND decode see the cache's return."""
+    from tests.oracle_cache import OracleCache
+    from xkv_b200.configurations import generate_consecutive_xKV_config
+    from xkv_b200.customized_cache import FakeLayerMergingCache
+    from xkv_b200.patch import KVCompress
+
+    model = _mla_model()
+    cfg = generate_consecutive_xKV_config(num_layers=3, end_layer=-1, group_size=3, rank_k=256, rank_v=None,
+                                          merge_value=False)
+    KVCompress(xKV_config=cfg)(model)
+    ids = torch.randint(0, 512, (1, 600), device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+    lg_ours, _ = _decode_logits(model, FakeLayerMergingCache(cfg), ids, steps=4)
+    lg_ref, _ = _decode_logits(model, OracleCache(cfg), ids, steps=4)
+    torch.cuda.synchronize()
+    dev = (lg_ours - lg_ref).abs().max().item()
+    scale = lg_ref.abs().max().item()
+    print(f"MLA logits: max |ours - oracle| = {dev:.4f} (logit scale {scale:.3f})")
+    assert dev <= 5e-2 * scale
+    bad = generate_consecutive_xKV_config(num_layers=3, end_layer=-1, group_size=3, rank_k=256, rank_v=64)
+    with pytest.raises(ValueError, match="merge_v"):
+        model(input_ids=ids[:, :300], past_key_values=FakeLayerMergingCache(bad), use_cache=True)

@@ -58,8 +58,8 @@ def test_unknown_method_and_model_type():
     model.config.model_type = "gpt_neox"
     with pytest.raises(ValueError, match="Model type not supported"):
         KVCompress(xKV_config=generate_consecutive_xKV_config(num_layers=2, end_layer=1))(model)
-    model.config.model_type = "deepseek_v2"
-    with pytest.raises(NotImplementedError):
+    model.config.model_type = "deepseek_v2"      # dispatches to the MLA patch, which rejects Llama attention modules
+    with pytest.raises(ValueError, match="DeepseekV2Attention"):
         KVCompress(xKV_config=generate_consecutive_xKV_config(num_layers=2, end_layer=1))(model)
 
 

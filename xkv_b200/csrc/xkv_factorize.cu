@@ -184,9 +184,9 @@ extern "C" void xkv_factorize_default_options(xkv_factorize_options* o) {
   std::memset(o, 0, sizeof(*o));
   o->power_iters = 6;
   o->oversample = 64;
-  o->first_passes = 3;
+  o->first_passes = 2;
   o->passes = 2;
-  o->final_passes = 3;
+  o->final_passes = 2;
   o->window = 128;
   o->jacobi_sweeps = 6;
   o->rayleigh_ritz = 1;

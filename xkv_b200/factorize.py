@@ -42,9 +42,9 @@ from ._lib import XkvError
 class FactorizeOptions:
     power_iters: int = 6
     oversample: int = 64
-    first_passes: int = 3      # CholeskyQR passes after the range finder (ill-conditioned sketch)
+    first_passes: int = 2      # CholeskyQR passes after the range finder (ill-conditioned sketch)
     passes: int = 2            # CholeskyQR passes after each power step
-    final_passes: int = 3      # passes after the last power step (orthonormal to ~1e-5)
+    final_passes: int = 2      # passes after the last power step (orthonormal to ~1e-5 after two)
     window: int = 128          # Rayleigh-Ritz window width (<= 160: A and V live in shared memory)
     jacobi_sweeps: int = 6
     rayleigh_ritz: bool = True
