@@ -190,6 +190,14 @@ XKV_API size_t xkv_append_workspace_bytes(int T, int n, int r);
 XKV_API int xkv_append_project(const void* x_new, int64_t ldx, int T, const void* V, int64_t ldv, int n, int r,
                                void* a_out, int64_t lda, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- SLERP / MiniCache branch (layer_merge_impl == "slerp"): replaces fake_minicache_merge -----------
+ * cache:32-100, called at cache:183-197 on two layers' rows (rows x d bf16, row stride ld). e1 / e2 receive the
+ * merged rows of layer 1 / layer 2 (rows whose angle exceeds d_min + (d_max - d_min) * gamma are replaced by the
+ * SLERP direction rescaled to each layer's norm; the others are copied, as the reference does). */
+XKV_API size_t xkv_slerp_workspace_bytes(int64_t rows);
+XKV_API int xkv_slerp_merge(const void* x1, const void* x2, int64_t rows, int d, int64_t ld, float t, float gamma,
+                            void* e1, void* e2, int64_t ld_out, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -187,3 +187,38 @@ def test_folding_decode_tokens_into_the_factors():
     assert ours.get_seq_length() == S + steps
     print(f"folded decode tokens: worst attention deviation {worst:.4f} of output scale")
     assert worst < 5e-2
+
+
+def test_slerp_branch_matches_oracle_cache():
+    """layer_merge_impl='slerp' (SURVEY.md §8 f3): MiniCache merge of 2-layer groups, RoPE afterwards, dense
+    storage; compared with the oracle cache running the reference's own formulae."""
+    from oracle import xkv_oracle as O
+    from xkv_b200 import synthetic
+    from xkv_b200.configurations import generate_consecutive_xKV_config
+    from xkv_b200.customized_cache import FakeLayerMergingCache
+
+    H, S, D = 2, 256, 64
+    cfg = generate_consecutive_xKV_config(layer_merge_impl="slerp", num_layers=2, end_layer=-1, group_size=2,
+                                          slerp_t=0.5, slerp_gamma=0.05)
+    keys = synthetic.make_group_kv(2, H, S, D, 1.0, 21, device="cuda")
+    vals = synthetic.make_group_kv(2, H, S, D, 0.7, 22, device="cuda")
+    cos, sin = synthetic.llama3_rope(S, D, device="cuda")
+    cache = FakeLayerMergingCache(cfg)
+    for l in range(2):
+        cache.update(keys[l], vals[l], l, mode="prefill", cos=cos, sin=sin)
+    torch.cuda.synchronize()
+    flat = lambda t: t.float().reshape(-1, D)
+    k1, k2 = O.fake_minicache_merge(flat(keys[0]), flat(keys[1]), t=0.5, gamma=0.05)
+    v1, v2 = O.fake_minicache_merge(flat(vals[0]), flat(vals[1]), t=0.5, gamma=0.05)
+    for l, (kr, vr) in enumerate(((k1, v1), (k2, v2))):
+        k, v = cache.materialize(l)
+        k_ref = O.apply_rope(kr.reshape(1, H, S, D).bfloat16(), cos, sin)
+        assert (k.float() - k_ref.float()).abs().max().item() <= 3e-2 * k_ref.float().abs().max().item()
+        assert (v.float() - vr.reshape(1, H, S, D)).abs().max().item() <= 2e-2 * vr.abs().max().item()
+    # group size 3 is rejected like the reference does (cache:184)
+    bad = generate_consecutive_xKV_config(layer_merge_impl="slerp", num_layers=3, end_layer=-1, group_size=3)
+    c2 = FakeLayerMergingCache(bad)
+    k3 = synthetic.make_group_kv(3, H, S, D, 1.0, 23, device="cuda")
+    with pytest.raises(AssertionError, match="group size 2"):
+        for l in range(3):
+            c2.update(k3[l], k3[l], l, mode="prefill", cos=cos, sin=sin)

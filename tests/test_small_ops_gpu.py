@@ -147,3 +147,26 @@ def test_convert_bf16_and_transpose():
     torch.cuda.synchronize()
     assert torch.equal(d, x.bfloat16())
     assert torch.equal(dt, x.bfloat16().t())
+
+
+def test_slerp_merge_matches_reference_function():
+    """SLERP / MiniCache branch against the oracle's restatement of fake_minicache_merge (pinned to the
+    reference by tests/golden) on bf16 rows; the kernel computes in fp32, the reference in the tensor dtype."""
+    from oracle import xkv_oracle as O
+    from xkv_b200 import ops
+
+    torch.manual_seed(4)
+    rows, d = 4096, 128
+    x1 = torch.randn(rows, d, device="cuda").bfloat16()
+    x2 = (x1.float() + 0.4 * torch.randn(rows, d, device="cuda")).bfloat16()
+    x2[7] = (x1[7].float() * 2.0).bfloat16()          # a parallel row -> linear-interpolation branch
+    e1, e2 = ops.slerp_merge(x1, x2, 0.6, 0.05)
+    torch.cuda.synchronize()
+    r1, r2 = O.fake_minicache_merge(x1.float(), x2.float(), t=0.6, gamma=0.05)
+    for got, ref in ((e1, r1), (e2, r2)):
+        err = (got.float() - ref).abs().max().item() / ref.abs().max().item()
+        assert err < 2e-2
+    # rows below the divergence threshold are copied through untouched (reference cache:96-99)
+    _, mask, _, _ = O.slerp_merge_rows_batch(x1.float(), x2.float(), t=0.6, gamma=0.05)
+    keep = ~mask.squeeze(-1)
+    assert keep.any() and torch.equal(e1[keep], x1[keep]) and torch.equal(e2[keep], x2[keep])

@@ -98,6 +98,8 @@ SIGNATURES = {
     "xkv_rope_bf16": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "xkv_append_workspace_bytes": (_sz, [_i, _i, _i]),
     "xkv_append_project": (_i, [_vp, _i64, _i, _vp, _i64, _i, _i, _vp, _i64, _vp, _sz, _vp]),
+    "xkv_slerp_workspace_bytes": (_sz, [_i64]),
+    "xkv_slerp_merge": (_i, [_vp, _vp, _i64, _i, _i64, _f, _f, _vp, _vp, _i64, _vp, _sz, _vp]),
     "xkv_factorize_batch": (_i, [_pp, _i, _i, _i, _i64, _i, C.POINTER(FactorizeOptions), _pp, _pp, _pp, _pp, _pp, _i,
                                  _vp, _sz, _pp, _vp]),
 }

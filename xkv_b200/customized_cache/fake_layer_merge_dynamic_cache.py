@@ -57,7 +57,7 @@ class _XkvLayer(DynamicLayer):
         if self.tail_k is None or self.tail_k.shape[-2] < need:
             cap = max(64, 2 * need)
             new_k = torch.empty(k.shape[0], k.shape[1], cap, k.shape[3], dtype=k.dtype, device=k.device)
-            new_v = torch.empty_like(new_k)
+            new_v = torch.empty(v.shape[0], v.shape[1], cap, v.shape[3], dtype=v.dtype, device=v.device)  # MLA: other width
             new_p = torch.empty_like(new_k) if k_pre is not None else None
             if self.tail_len:
                 new_k[:, :, : self.tail_len] = self.tail_k[:, :, : self.tail_len]
@@ -161,15 +161,17 @@ class FakeLayerMergingCache(DynamicCache):
         info = self.merge_setup.get_group_for_layer(last_layer_idx)
         if info is None:
             return
-        if self.merge_setup.layer_merge_impl != "svd":
-            raise NotImplementedError(
-                f"layer_merge_impl={self.merge_setup.layer_merge_impl!r}: only 'svd' runs on the B200 path")
         first, last = info.layers[0], info.layers[-1]
         ids = list(range(first, last + 1))            # the reference assumes contiguous groups (cache:165)
         layers = [self._layer(i) for i in ids]
         keys = [l.keys for l in layers]
         values = [l.values for l in layers]
         seq = keys[0].shape[-2]
+        if self.merge_setup.layer_merge_impl == "slerp":
+            self._slerp_merge(info, layers, keys, values)
+            return
+        if self.merge_setup.layer_merge_impl != "svd":
+            raise NotImplementedError(f"Unknown implementation: {self.merge_setup.layer_merge_impl}")
         merge_k = self.merge_setup.merge_key and self._rank_fits(info.rank_k, seq, len(ids))
         merge_v = self.merge_setup.merge_value and self._rank_fits(info.rank_v, seq, len(ids))
         if not (merge_k or merge_v):
@@ -201,6 +203,26 @@ class FakeLayerMergingCache(DynamicCache):
                 l.dense_k = self._rope_dense(keys[pos], cos, sin) if re_rope else keys[pos]
             l.dense_v = values[pos] if gf.value is None else None
             l.keys = l.values = None
+
+    def _slerp_merge(self, info: LayerGroup, layers, keys, values) -> None:
+        """MiniCache baseline (reference cache:183-197, fake_minicache_merge :93-100): row-wise SLERP of the two
+        layers of a group. The result is dense (nothing is compressed in storage), so these layers stay on the
+        dense cache path; keys get RoPE afterwards like every merged group (cache:142-148)."""
+        assert len(keys) == 2 and len(values) == 2, "SLERP only supports group size 2"
+        cos, sin, re_rope = self._merge_cos_sin
+
+        def merge(pair):
+            bs, h, s, d = pair[0].shape
+            rows = [t.transpose(1, 2).reshape(bs * s * h, d) for t in pair]     # token-major rows (view when possible)
+            rows = [r if r.stride(1) == 1 and r.stride(0) == d else r.contiguous() for r in rows]
+            e1, e2 = ops.slerp_merge(rows[0], rows[1], float(info.slerp_t), float(info.slerp_gamma))
+            return [e.view(bs, s, h, d).transpose(1, 2) for e in (e1, e2)]
+
+        new_k = merge(keys) if self.merge_setup.merge_key else list(keys)
+        new_v = merge(values) if self.merge_setup.merge_value else list(values)
+        for l, k, v in zip(layers, new_k, new_v):
+            l.keys = self._rope_dense(k, cos, sin) if re_rope else k
+            l.values = v
 
     def _rank_fits(self, rank: Optional[int], seq: int, nlayers: int) -> bool:
         if rank is None:

@@ -280,3 +280,23 @@ def append_project(x_new: torch.Tensor, v: torch.Tensor, out: Optional[torch.Ten
     check(lib.xkv_append_project(_ptr(x_new), x_new.stride(0), t, _ptr(v), v.stride(0), n, r, _ptr(out), out.stride(0),
                                  C.c_void_p(workspace.data_ptr()), workspace.numel(), _stream()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# SLERP / MiniCache branch
+# ---------------------------------------------------------------------------------------------
+def slerp_merge(x1: torch.Tensor, x2: torch.Tensor, t: float, gamma: float):
+    """fake_minicache_merge (reference cache:93-100) on two (rows, d) bf16 matrices -> (e1, e2) bf16."""
+    _require_cuda(x1, x2)
+    if x1.dtype != torch.bfloat16 or x2.dtype != torch.bfloat16 or x1.shape != x2.shape or x1.stride() != x2.stride():
+        raise _lib.XkvError("slerp_merge: two equally-shaped bf16 matrices required")
+    if x1.stride(1) != 1:
+        raise _lib.XkvError("slerp_merge: unit inner stride required")
+    rows, d = x1.shape
+    lib = _lib.load()
+    ws = torch.empty(int(lib.xkv_slerp_workspace_bytes(rows)), dtype=torch.uint8, device=x1.device)
+    e1 = torch.empty(rows, d, dtype=torch.bfloat16, device=x1.device)
+    e2 = torch.empty_like(e1)
+    check(lib.xkv_slerp_merge(_ptr(x1), _ptr(x2), rows, d, x1.stride(0), C.c_float(t), C.c_float(gamma), _ptr(e1),
+                              _ptr(e2), e1.stride(0), C.c_void_p(ws.data_ptr()), ws.numel(), _stream()))
+    return e1, e2
