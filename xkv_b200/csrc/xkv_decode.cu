@@ -358,31 +358,37 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
         tmem_ld_32x32(lane_addr + static_cast<uint32_t>((c + NCH / 2) * 32), x2);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float k1 = bf16r(__uint_as_float(x1[j]));
-          const float k2 = bf16r(__uint_as_float(x2[j]));
-          float o1 = k1, o2 = k2;
+        for (int jp = 0; jp < 16; ++jp) {
+          // two dims at a time in packed bf16: the reference's RoPE is bf16 arithmetic (each product and the sum
+          // rounded to bf16), which is exactly what HMUL2.BF16 / HADD2.BF16 compute
+          const __nv_bfloat162 k1 = __floats2bfloat162_rn(__uint_as_float(x1[2 * jp]), __uint_as_float(x1[2 * jp + 1]));
+          const __nv_bfloat162 k2 = __floats2bfloat162_rn(__uint_as_float(x2[2 * jp]), __uint_as_float(x2[2 * jp + 1]));
+          __nv_bfloat162 o1 = k1, o2 = k2;
           if (rope) {
-            const uint32_t cw = cs[j >> 1], sw = sn[j >> 1];
-            const float cf = __uint_as_float((j & 1) ? (cw & 0xFFFF0000u) : (cw << 16));
-            const float sf = __uint_as_float((j & 1) ? (sw & 0xFFFF0000u) : (sw << 16));
-            o1 = bf16r(bf16r(k1 * cf) + bf16r(-k2 * sf));
-            o2 = bf16r(bf16r(k2 * cf) + bf16r(k1 * sf));
+            const __nv_bfloat162 cw = *reinterpret_cast<const __nv_bfloat162*>(&cs[jp]);
+            const __nv_bfloat162 sw = *reinterpret_cast<const __nv_bfloat162*>(&sn[jp]);
+            o1 = __hadd2(__hmul2(k1, cw), __hmul2(__hneg2(k2), sw));
+            o2 = __hadd2(__hmul2(k2, cw), __hmul2(k1, sw));
           }
-          const int d1 = c * 32 + j, d2 = d1 + D / 2;
-          const float4 qa = *reinterpret_cast<const float4*>(q_s + d1 * D_MAX_QPK);
-          const float4 qb = *reinterpret_cast<const float4*>(q_s + d2 * D_MAX_QPK);
-          sc[0] = fmaf(qa.x, o1, fmaf(qb.x, o2, sc[0]));
-          sc[1] = fmaf(qa.y, o1, fmaf(qb.y, o2, sc[1]));
-          sc[2] = fmaf(qa.z, o1, fmaf(qb.z, o2, sc[2]));
-          sc[3] = fmaf(qa.w, o1, fmaf(qb.w, o2, sc[3]));
-          if (P.qpk > 4) {
-            const float4 qc = *reinterpret_cast<const float4*>(q_s + d1 * D_MAX_QPK + 4);
-            const float4 qe = *reinterpret_cast<const float4*>(q_s + d2 * D_MAX_QPK + 4);
-            sc[4] = fmaf(qc.x, o1, fmaf(qe.x, o2, sc[4]));
-            sc[5] = fmaf(qc.y, o1, fmaf(qe.y, o2, sc[5]));
-            sc[6] = fmaf(qc.z, o1, fmaf(qe.z, o2, sc[6]));
-            sc[7] = fmaf(qc.w, o1, fmaf(qe.w, o2, sc[7]));
+          const float o1v[2] = {__low2float(o1), __high2float(o1)};
+          const float o2v[2] = {__low2float(o2), __high2float(o2)};
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int d1 = c * 32 + 2 * jp + u, d2 = d1 + D / 2;
+            const float4 qa = *reinterpret_cast<const float4*>(q_s + d1 * D_MAX_QPK);
+            const float4 qb = *reinterpret_cast<const float4*>(q_s + d2 * D_MAX_QPK);
+            sc[0] = fmaf(qa.x, o1v[u], fmaf(qb.x, o2v[u], sc[0]));
+            sc[1] = fmaf(qa.y, o1v[u], fmaf(qb.y, o2v[u], sc[1]));
+            sc[2] = fmaf(qa.z, o1v[u], fmaf(qb.z, o2v[u], sc[2]));
+            sc[3] = fmaf(qa.w, o1v[u], fmaf(qb.w, o2v[u], sc[3]));
+            if (P.qpk > 4) {
+              const float4 qc = *reinterpret_cast<const float4*>(q_s + d1 * D_MAX_QPK + 4);
+              const float4 qe = *reinterpret_cast<const float4*>(q_s + d2 * D_MAX_QPK + 4);
+              sc[4] = fmaf(qc.x, o1v[u], fmaf(qe.x, o2v[u], sc[4]));
+              sc[5] = fmaf(qc.y, o1v[u], fmaf(qe.y, o2v[u], sc[5]));
+              sc[6] = fmaf(qc.z, o1v[u], fmaf(qe.z, o2v[u], sc[6]));
+              sc[7] = fmaf(qc.w, o1v[u], fmaf(qe.w, o2v[u], sc[7]));
+            }
           }
         }
       }
@@ -466,8 +472,25 @@ __global__ void __launch_bounds__(1024) softmax_kernel(float* __restrict__ score
   }
 }
 
+// U[e] = sum over the split-K slabs of (P A_v)[e]
+__global__ void __launch_bounds__(256) reduce_u_kernel(const float* __restrict__ slabs, int nslabs, long long slab_stride,
+                                                       int total, float* __restrict__ U) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int sl = 0;
+  for (; sl + 4 <= nslabs; sl += 4) {
+    a0 += slabs[(sl + 0) * slab_stride + e];
+    a1 += slabs[(sl + 1) * slab_stride + e];
+    a2 += slabs[(sl + 2) * slab_stride + e];
+    a3 += slabs[(sl + 3) * slab_stride + e];
+  }
+  for (; sl < nslabs; ++sl) a0 += slabs[sl * slab_stride + e];
+  U[e] = (a0 + a1) + (a2 + a3);
+}
+
 // o[hq][d] = ( sum_j U[hq][j] * Bv[(h*D + d)][j]  +  sum_t p_tail[hq][t] * v_tail[h][t][d] ) / rowsum[hq]
-// U = sum over the split-K slabs of P A_v (reduced here); grid (Hq, D / 32), 8 warps x 4 output dims.
+// grid (Hq, D / 32), 8 warps x 4 output dims.
 __global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ slabs, int nslabs, long long slab_stride,
                                                       int rv, const __nv_bfloat16* __restrict__ Bv, long long ldb,
                                                       const __nv_bfloat16* __restrict__ prob, long long ldp, int S, int T,
@@ -477,12 +500,9 @@ __global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ 
   extern __shared__ float u_s[];  // rv floats
   const int hq = blockIdx.x, h = hq / qpk;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int j = threadIdx.x; j < rv; j += blockDim.x) {
-    float acc = 0.f;
-    const float* p = slabs + static_cast<long long>(hq) * rv + j;
-    for (int sl = 0; sl < nslabs; ++sl) acc += p[sl * slab_stride];
-    u_s[j] = acc;
-  }
+  for (int j = threadIdx.x; j < rv; j += blockDim.x) u_s[j] = slabs[static_cast<long long>(hq) * rv + j];
+  (void)nslabs;
+  (void)slab_stride;
   __syncthreads();
   const float inv = 1.f / rowsum[hq];
   for (int d = blockIdx.y * 32 + warp; d < min(D, blockIdx.y * 32 + 32); d += 8) {
@@ -537,8 +557,7 @@ extern "C" size_t xkv_decode_workspace_bytes(int Hq, int S, int T, int rv) {
   b += al(Hq * ldl * 4);            // scores
   b += al(128 * ldl * 2);           // probabilities (bf16), padded to a full 128-row tile
   b += al(Hq * 4);                  // row sums
-  b += al(static_cast<size_t>(split) * Hq * rv * 4);  // split-K slabs of U
-  b += al(static_cast<size_t>(Hq) * rv * 4);          // U
+  b += al(static_cast<size_t>(split + 1) * Hq * rv * 4);  // split-K slabs of U, then U itself
   return b + 1024;
 }
 
@@ -571,7 +590,7 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
   float* rowsum = reinterpret_cast<float*>(w);
   w += al(Hq * 4);
   float* u_slabs = reinterpret_cast<float*>(w);
-  w += al(static_cast<size_t>(split) * Hq * rv * 4);
+  w += al(static_cast<size_t>(split + 1) * Hq * rv * 4);
 
   // ---- scores of the compressed prefix: fused reconstruct + RoPE + q.K ----
   static thread_local ScoreParams sp;
@@ -656,8 +675,11 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
   rc = xkv_gemm_grouped(&gp, 1, stream);
   if (rc) return rc;
   // ---- o = (U Bv_l^T + P_tail V_tail) / rowsum, U reduced over the split-K slabs on the fly ----
+  float* U = u_slabs + static_cast<size_t>(split) * Hq * rv;
+  reduce_u_kernel<<<(Hq * rv + 255) / 256, 256, 0, st>>>(u_slabs, split, static_cast<long long>(Hq) * rv, Hq * rv, U);
+  XKV_LAUNCHED();
   combine_kernel<<<dim3(Hq, (D + 31) / 32), 256, rv * sizeof(float), st>>>(
-      u_slabs, split, static_cast<long long>(Hq) * rv, rv, static_cast<const __nv_bfloat16*>(Vv_layer), ldv_v, prob, ldl, S,
+      U, 1, 0, rv, static_cast<const __nv_bfloat16*>(Vv_layer), ldv_v, prob, ldl, S,
       T, static_cast<const __nv_bfloat16*>(v_tail), tail_stride_h, tail_stride_t, rowsum, qpk, D,
       static_cast<__nv_bfloat16*>(out));
   XKV_LAUNCHED();
