@@ -253,29 +253,34 @@ __device__ __forceinline__ float* block_ptr(float* base, int bi, int bj, long lo
   return base + (static_cast<long long>(bi) * NB) * ld + static_cast<long long>(bj) * NB;
 }
 
-// ---- warp-level 32x32 Cholesky and triangular inverse, matrix rows held in registers (lane = row) ----
-// a[c] = row `lane` of the symmetric block (entries c <= lane are used).  On return a[c] = L[lane][c], c <= lane.
-__device__ __forceinline__ void warp_chol32(float (&a)[32], float pivot_floor) {
-  const int lane = threadIdx.x & 31;
+// ---- warp-level 16x16 Cholesky + triangular inverse with the block's rows held in registers ----
+// Executed by one full warp (lanes 16..31 mirror lanes 0..15 and only take part in the shuffles).
+// D, X: 64x64 natural layout (stride NBP) in shared memory; o = offset of the diagonal block.
+// On return D[o+i][o+c] = L[i][c] (zero above the diagonal) and X[o+r][o+c] = (L^{-1})[r][c].
+// Kept out of line on purpose: a fully unrolled 32x32 version inlined twice grew the kernel to 23k SASS
+// instructions and ran out of the instruction cache (ncu: 2/3 of the kernel stalled behind warp 0).
+__device__ __noinline__ void warp_chol16_inv16(float* D, float* X, int o, float pivot_floor) {
+  const int lane = threadIdx.x & 15;
+  const bool owner = (threadIdx.x & 31) < 16;
+  float a[16], x[16];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int c = 0; c < 16; ++c) a[c] = D[(o + lane) * NBP + o + c];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
     float d = __shfl_sync(0xffffffffu, a[j], j);
     d = fmaxf(d, pivot_floor);
     const float inv = rsqrtf(d);
     const float lij = lane > j ? a[j] * inv : (lane == j ? d * inv : 0.f);
     a[j] = lij;
 #pragma unroll
-    for (int c = j + 1; c < 32; ++c) {
+    for (int c = j + 1; c < 16; ++c) {
       const float lcj = __shfl_sync(0xffffffffu, lij, c);
       a[c] = fmaf(-lij, lcj, a[c]);
     }
   }
-}
-// x[r] = (L^{-1})[r][lane] (column `lane` of the inverse), L given as register rows a[] (lane = row).
-__device__ __forceinline__ void warp_triinv32(const float (&a)[32], float (&x)[32]) {
-  const int lane = threadIdx.x & 31;
+  // x[r] = (L^{-1})[r][lane]: forward substitution, L rows broadcast by shuffle
 #pragma unroll
-  for (int r = 0; r < 32; ++r) {
+  for (int r = 0; r < 16; ++r) {
     float s = lane == r ? 1.f : 0.f;
 #pragma unroll
     for (int t = 0; t < r; ++t) {
@@ -283,7 +288,14 @@ __device__ __forceinline__ void warp_triinv32(const float (&a)[32], float (&x)[3
       s = fmaf(-lrt, x[t], s);
     }
     const float lrr = __shfl_sync(0xffffffffu, a[r], r);
-    x[r] = lane <= r ? s / lrr : 0.f;
+    x[r] = lane <= r ? __fdividef(s, lrr) : 0.f;
+  }
+  if (owner) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      D[(o + lane) * NBP + o + c] = c <= lane ? a[c] : 0.f;
+      X[(o + c) * NBP + o + lane] = x[c];
+    }
   }
 }
 
@@ -304,84 +316,69 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(const __grid_constant__
     X[r * NBP + c] = 0.f;
   }
   __syncthreads();
-  // 64x64 = 2x2 blocks of 32.  Warp 0 factors and inverts the diagonal 32x32 blocks in registers
-  // (warp_chol32 / warp_triinv32: shuffles only, no block barriers); the off-diagonal work between them
-  // is four small block products done by all threads.  X accumulates D^{-1} in natural layout.
-  const int lane = tid & 31;
-  // X starts as zero here (the identity written above is not used by this scheme)
-  auto diag_block = [&](int o) {
-    if (tid < 32) {
-      float a[32], x[32];
-#pragma unroll
-      for (int c = 0; c < 32; ++c) a[c] = D[(o + lane) * NBP + o + c];
-      warp_chol32(a, p.pivot_floor);
-#pragma unroll
-      for (int c = 0; c < 32; ++c) D[(o + lane) * NBP + o + c] = c <= lane ? a[c] : 0.f;
-      warp_triinv32(a, x);
-#pragma unroll
-      for (int r = 0; r < 32; ++r) X[(o + r) * NBP + o + lane] = x[r];
-    }
-  };
-  diag_block(0);
-  __syncthreads();
-  // L21 = A21 * X11^T : L21[i][j] = sum_c A21[i][c] X11[j][c]      (i in 32..63; j, c < 32)
-  float l21[4];
-  {
-    const int i = 32 + (tid >> 3), j0 = (tid & 7) * 4;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
+  // 64x64 = 4x4 blocks of 16, right-looking.  Warp 0 factors and inverts each diagonal block in registers
+  // (shuffles only); the panel solve, the rank-16 trailing update and the off-diagonal blocks of the inverse
+  // (block forward substitution) are small smem-resident products spread over all 256 threads.
+  constexpr int BS = 16;
+  for (int jb = 0; jb < NB; jb += BS) {
+    if (tid < 32) warp_chol16_inv16(D, X, jb, p.pivot_floor);
+    __syncthreads();
+    const int below = NB - jb - BS;                 // rows under the diagonal block
+    // panel: L[i][jb+c] = sum_{t<=c} A[i][jb+t] * Xd[c][t]   (Xd = inverse of the diagonal factor, lower)
+    float pv[3];
+    int nmine = 0;
+    for (int e = tid; e < below * BS; e += 256) {
+      const int i = jb + BS + e / BS, c = e % BS;
       float acc = 0.f;
-      for (int c = 0; c <= j0 + u; ++c) acc = fmaf(D[i * NBP + c], X[(j0 + u) * NBP + c], acc);
-      l21[u] = acc;
+      for (int t = 0; t <= c; ++t) acc = fmaf(D[i * NBP + jb + t], X[(jb + c) * NBP + jb + t], acc);
+      pv[nmine++] = acc;
     }
     __syncthreads();
-#pragma unroll
-    for (int u = 0; u < 4; ++u) D[i * NBP + j0 + u] = l21[u];
-  }
-  __syncthreads();
-  // A22 -= L21 L21^T (lower triangle of the trailing 32x32 block)
-  {
-    const int i = 32 + (tid >> 3), j0 = 32 + (tid & 7) * 4;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = j0 + u;
+    nmine = 0;
+    for (int e = tid; e < below * BS; e += 256) {
+      const int i = jb + BS + e / BS, c = e % BS;
+      D[i * NBP + jb + c] = pv[nmine++];
+    }
+    __syncthreads();
+    // trailing update: D[i][j] -= sum_t L[i][jb+t] L[j][jb+t],  jb+16 <= j <= i
+    for (int e = tid; e < below * below; e += 256) {
+      const int i = jb + BS + e / below, j = jb + BS + e % below;
       if (j <= i) {
         float acc = 0.f;
-        for (int c = 0; c < 32; ++c) acc = fmaf(D[i * NBP + c], D[j * NBP + c], acc);
+#pragma unroll
+        for (int t = 0; t < BS; ++t) acc = fmaf(D[i * NBP + jb + t], D[j * NBP + jb + t], acc);
         D[i * NBP + j] -= acc;
       }
     }
+    __syncthreads();
   }
-  __syncthreads();
-  diag_block(32);
-  __syncthreads();
-  // X21 = -X22 * (L21 * X11):  first T = L21 * X11 (T[i][j] = sum_{c>=j} L21[i][c] X11[c][j]) ...
-  float tacc[4];
-  {
-    const int i = 32 + (tid >> 3), j0 = (tid & 7) * 4;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
+  // off-diagonal blocks of X = L^{-1}: X[bi][bj] = -Xd_bi * sum_{t=bj}^{bi-1} L[bi][t] X[t][bj]
+  for (int bi = 1; bi < NB / BS; ++bi) {
+    float tv[3];
+    int nmine = 0;
+    const int ncols = bi * BS;                      // columns 0 .. 16*bi-1
+    for (int e = tid; e < BS * ncols; e += 256) {
+      const int r = bi * BS + e / ncols, c = e % ncols;
       float acc = 0.f;
-      for (int c = j0 + u; c < 32; ++c) acc = fmaf(D[i * NBP + c], X[c * NBP + j0 + u], acc);
-      tacc[u] = acc;
+      for (int t = c; t < ncols; ++t) acc = fmaf(D[r * NBP + t], X[t * NBP + c], acc);   // X[t][c] = 0 for t < c
+      tv[nmine++] = acc;
     }
     __syncthreads();
-    // stage T in the (unused) upper-right corner of D: rows 0..31, columns 32..63 hold T^T
-#pragma unroll
-    for (int u = 0; u < 4; ++u) D[(j0 + u) * NBP + i] = tacc[u];
-  }
-  __syncthreads();
-  // ... then X21[i][j] = - sum_{t<=i} X22[i][t] T[t][j]
-  {
-    const int i = 32 + (tid >> 3), j0 = (tid & 7) * 4;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float acc = 0.f;
-      for (int t = 32; t <= i; ++t) acc = fmaf(X[i * NBP + t], D[(j0 + u) * NBP + t], acc);
-      X[i * NBP + j0 + u] = -acc;
+    // stage T in the unused upper triangle of D (rows < 16*bi, columns of block bi), transposed
+    nmine = 0;
+    for (int e = tid; e < BS * ncols; e += 256) {
+      const int r = bi * BS + e / ncols, c = e % ncols;
+      D[c * NBP + r] = tv[nmine++];
     }
+    __syncthreads();
+    for (int e = tid; e < BS * ncols; e += 256) {
+      const int r = bi * BS + e / ncols, c = e % ncols;
+      float acc = 0.f;
+      for (int t = bi * BS; t <= r; ++t) acc = fmaf(X[r * NBP + t], D[c * NBP + t], acc);
+      X[r * NBP + c] = -acc;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   if (i == k) {
     // Only the inverse of the diagonal block is published: L[k,k] itself is never read again, and
     // writing it over S[k,k] would race with the other CTAs of this launch still loading that block.
