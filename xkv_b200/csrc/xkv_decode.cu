@@ -419,56 +419,72 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
   }
 }
 
-// softmax over L = S + T scores of one q-head: p = exp(s - max) as bf16 (the GEMM operand), rowsum in fp32.
-// The scores of the T dense tail tokens (scale * q . k_tail) are computed here first.
-__global__ void __launch_bounds__(1024) softmax_kernel(float* __restrict__ scores, long long ld, int S, int T,
-                                                       const __nv_bfloat16* __restrict__ q,
-                                                       const __nv_bfloat16* __restrict__ k_tail, long long sh,
-                                                       long long st, int qpk, int D, float scale,
-                                                       __nv_bfloat16* __restrict__ prob, long long ldp,
-                                                       float* __restrict__ rowsum) {
-  __shared__ float red[32];
-  __shared__ float bcast;
-  const int hq = blockIdx.x;
+// Softmax over L = S + T scores of one q-head, two launches, SM_CHUNKS CTAs per head:
+//   pass 1: per-chunk max (the CTA of the last chunk first scores the T dense tail tokens: scale * q . k_tail)
+//   pass 2: global max from the chunk maxima, p = exp(s - max) written as bf16 (the GEMM operand),
+//           per-chunk sums of p in fp32 (added up by the combine kernel).
+constexpr int SM_CHUNKS = 16;
+
+__global__ void __launch_bounds__(256) softmax_max_kernel(float* __restrict__ scores, long long ld, int S, int T,
+                                                          const __nv_bfloat16* __restrict__ q,
+                                                          const __nv_bfloat16* __restrict__ k_tail, long long sh,
+                                                          long long st, int qpk, int D, float scale,
+                                                          float* __restrict__ chunk_max) {
+  __shared__ float red[8];
+  const int hq = blockIdx.x, ch = blockIdx.y;
   float* s = scores + hq * ld;
-  __nv_bfloat16* p = prob + hq * ldp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = S + T;
-  const int h = hq / qpk;
-  for (int t = warp; t < T; t += 32) {
-    const __nv_bfloat16* kr = k_tail + h * sh + t * st;
-    float acc = 0.f;
-    for (int d = lane; d < D; d += 32) acc += __bfloat162float(q[hq * D + d]) * __bfloat162float(kr[d]);
-    acc = warp_sum(acc);
-    if (lane == 0) s[S + t] = acc * scale;
+  if (ch == SM_CHUNKS - 1 && T > 0) {
+    const int h = hq / qpk;
+    for (int t = warp; t < T; t += 8) {
+      const __nv_bfloat16* kr = k_tail + h * sh + t * st;
+      float acc = 0.f;
+      for (int d = lane; d < D; d += 32) acc += __bfloat162float(q[hq * D + d]) * __bfloat162float(kr[d]);
+      acc = warp_sum(acc);
+      if (lane == 0) s[S + t] = acc * scale;
+    }
+    __syncthreads();
   }
-  __syncthreads();
+  const int per = (L + SM_CHUNKS - 1) / SM_CHUNKS;
+  const int i0 = ch * per, i1 = min(L, i0 + per);
   float m = -INFINITY;
-  for (int i = tid; i < L; i += 1024) m = fmaxf(m, s[i]);
+  for (int i = i0 + tid; i < i1; i += 256) m = fmaxf(m, s[i]);
   m = warp_max(m);
   if (lane == 0) red[warp] = m;
   __syncthreads();
-  if (warp == 0) {
-    float v = red[lane];
-    v = warp_max(v);
-    if (lane == 0) bcast = v;
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    chunk_max[hq * SM_CHUNKS + ch] = m;
   }
-  __syncthreads();
-  m = bcast;
+}
+
+__global__ void __launch_bounds__(256) softmax_exp_kernel(const float* __restrict__ scores, long long ld, int L,
+                                                          const float* __restrict__ chunk_max,
+                                                          __nv_bfloat16* __restrict__ prob, long long ldp,
+                                                          float* __restrict__ chunk_sum) {
+  __shared__ float red[8];
+  const int hq = blockIdx.x, ch = blockIdx.y;
+  const float* s = scores + hq * ld;
+  __nv_bfloat16* p = prob + hq * ldp;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float m = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < SM_CHUNKS; ++c) m = fmaxf(m, chunk_max[hq * SM_CHUNKS + c]);
+  const int per = (L + SM_CHUNKS - 1) / SM_CHUNKS;
+  const int i0 = ch * per, i1 = min(L, i0 + per);
   float sum = 0.f;
-  for (int i = tid; i < L; i += 1024) {
+  for (int i = i0 + tid; i < i1; i += 256) {
     const float e = __expf(s[i] - m);
     sum += e;
     p[i] = __float2bfloat16_rn(e);
   }
   sum = warp_sum(sum);
-  __syncthreads();
   if (lane == 0) red[warp] = sum;
   __syncthreads();
-  if (warp == 0) {
-    float v = red[lane];
-    v = warp_sum(v);
-    if (lane == 0) rowsum[hq] = v;
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) sum += red[w];
+    chunk_sum[hq * SM_CHUNKS + ch] = sum;
   }
 }
 
@@ -504,7 +520,10 @@ __global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ 
   (void)nslabs;
   (void)slab_stride;
   __syncthreads();
-  const float inv = 1.f / rowsum[hq];
+  float rs = 0.f;
+#pragma unroll
+  for (int c = 0; c < SM_CHUNKS; ++c) rs += rowsum[hq * SM_CHUNKS + c];
+  const float inv = 1.f / rs;
   for (int d = blockIdx.y * 32 + warp; d < min(D, blockIdx.y * 32 + 32); d += 8) {
     const __nv_bfloat16* row = Bv + static_cast<long long>(h * D + d) * ldb;
     float acc = 0.f;
@@ -556,7 +575,7 @@ extern "C" size_t xkv_decode_workspace_bytes(int Hq, int S, int T, int rv) {
   size_t b = 0;
   b += al(Hq * ldl * 4);            // scores
   b += al(128 * ldl * 2);           // probabilities (bf16), padded to a full 128-row tile
-  b += al(Hq * 4);                  // row sums
+  b += al(2 * Hq * 16 * 4);         // per-chunk max / sum of the softmax
   b += al(static_cast<size_t>(split + 1) * Hq * rv * 4);  // split-K slabs of U, then U itself
   return b + 1024;
 }
@@ -587,8 +606,9 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
   w += al(Hq * ldl * 4);
   __nv_bfloat16* prob = reinterpret_cast<__nv_bfloat16*>(w);
   w += al(128 * ldl * 2);
-  float* rowsum = reinterpret_cast<float*>(w);
-  w += al(Hq * 4);
+  float* rowsum = reinterpret_cast<float*>(w);        // per-chunk sums of p
+  float* chunk_max = rowsum + Hq * SM_CHUNKS;
+  w += al(2 * Hq * SM_CHUNKS * 4);
   float* u_slabs = reinterpret_cast<float*>(w);
   w += al(static_cast<size_t>(split + 1) * Hq * rv * 4);
 
@@ -651,9 +671,11 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
   }
   XKV_LAUNCHED();
   // ---- softmax (also scores the dense tail) ----
-  softmax_kernel<<<Hq, 1024, 0, st>>>(scores, ldl, S, T, static_cast<const __nv_bfloat16*>(q),
-                                      static_cast<const __nv_bfloat16*>(k_tail), tail_stride_h, tail_stride_t, qpk, D, scale,
-                                      prob, ldl, rowsum);
+  softmax_max_kernel<<<dim3(Hq, SM_CHUNKS), 256, 0, st>>>(scores, ldl, S, T, static_cast<const __nv_bfloat16*>(q),
+                                                          static_cast<const __nv_bfloat16*>(k_tail), tail_stride_h,
+                                                          tail_stride_t, qpk, D, scale, chunk_max);
+  XKV_LAUNCHED();
+  softmax_exp_kernel<<<dim3(Hq, SM_CHUNKS), 256, 0, st>>>(scores, ldl, static_cast<int>(L), chunk_max, prob, ldl, rowsum);
   XKV_LAUNCHED();
   // ---- U = P[:, :S] * A_v  (tokens are the contraction: P K-major, A_v MN-major) ----
   xkv_gemm_problem gp;

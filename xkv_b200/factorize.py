@@ -273,9 +273,11 @@ def factorize_batch_py(xs: Sequence[torch.Tensor], rank: int, opts: Optional[Fac
         nonlocal f_cur, f_nxt
         for ipass in range(npass):
             ops.normalize_rows(f_cur, lh, lm, ll)
+            # pass 0 is regularised by the large shift: the 3-term product is accurate enough there (as in the C driver)
+            terms = ops.TERMS_3 if ipass == 0 else ops.TERMS_6
             _gemm([
                 ops.make_problem([lh[b], lm[b], ll[b]], [lh[b], lm[b], ll[b]], s_slabs[b, 0], M=l, N=l, K=n,
-                                 terms=ops.TERMS_6, sym_upper=True, split_k=sk, split_stride=s_slabs.stride(1))
+                                 terms=terms, sym_upper=True, split_k=sk, split_stride=s_slabs.stride(1))
                 for b in range(B)
             ])
             for b in range(B):
@@ -288,7 +290,7 @@ def factorize_batch_py(xs: Sequence[torch.Tensor], rank: int, opts: Optional[Fac
             # Qt = Linv * Ys   (A: Linv limbs K-major;  B: Ys limbs as [K = l][N = n], MN-major)
             _gemm([
                 ops.make_problem(linv_l[b], [lh[b], lm[b], ll[b]], f_nxt[b], M=l, N=n, K=l, b_mn_major=True,
-                                 terms=ops.TERMS_6)
+                                 terms=terms)
                 for b in range(B)
             ])
             f_cur, f_nxt = f_nxt, f_cur
