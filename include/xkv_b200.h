@@ -103,6 +103,20 @@ XKV_API int xkv_fill_gaussian_bf16(void* out, int rows, int cols, int64_t ld, ui
 XKV_API int xkv_normalize_rows(float* const* Y_host, void* const* hi_host, void* const* mid_host,
                                void* const* lo_host, int batch, int rows, int cols, int64_t ld, int64_t ld_out,
                                void* stream);
+/* Spectrally shifted power steps (G - c I).  xkv_shift_normalize_rows: Y <- Y - c[b] Q (when Q_host != NULL;
+ * Y = Q G just computed, Q the previous orthonormal basis), then row-normalise as xkv_normalize_rows; when
+ * rdiag_host != NULL the row norms are recorded (rdiag_first) or multiplied into rdiag[b][0..rows).
+ * xkv_rdiag_update: rdiag[b][j] /= Linv[b][j][j] after a Cholesky pass, so that rdiag accumulates diag(R) of
+ * Y = R^T Q_new, whose trailing entries converge to lambda_l - c.  xkv_ritz_shift_update:
+ * c[b] <- shift_scale * (mean of the last tail_rows entries of rdiag[b] + c[b]). */
+XKV_API int xkv_shift_normalize_rows(float* const* Y_host, const float* const* Q_host, float* shift_dev,
+                                     float* const* rdiag_host, int rdiag_first, void* const* hi_host,
+                                     void* const* mid_host, void* const* lo_host, int batch, int rows, int cols,
+                                     int64_t ld, int64_t ld_out, void* stream);
+XKV_API int xkv_ritz_shift_update(float* const* rdiag_host, int batch, int rows, int tail_rows, float shift_scale,
+                                  float* shift_dev, void* stream);
+XKV_API int xkv_rdiag_update(float* const* rdiag_host, const float* const* Linv_host, int batch, int rows,
+                             int64_t ld_linv, void* stream);
 /* Batched blocked Cholesky S = L L^T of l x l fp32 matrices (l % 64 == 0, unit diagonal expected) with
  * explicit inverse Linv = L^{-1} (dense l x l, zero above the diagonal). S is overwritten: its strictly
  * lower 64-blocks hold L, its diagonal blocks are left untouched. `shift` is added to the diagonal
@@ -133,7 +147,7 @@ XKV_API int xkv_sqrt_clamp(const float* in, float* out, int count, void* stream)
  * phase 2, which resumes from the reduced Gram and projects the local rows A_p = X_p V. phase 0 (gram_host may
  * be NULL) does everything on one device. */
 typedef struct xkv_factorize_options {
-  int32_t power_iters;    /* power steps on G after the range finder (default 6) */
+  int32_t power_iters;    /* power steps on G after the range finder (default 4) */
   int32_t oversample;     /* extra sketch columns; sketch width l = round_up(rank + oversample, 64) */
   int32_t first_passes;   /* CholeskyQR passes after the range finder (2) */
   int32_t passes;         /* CholeskyQR passes after a power step (2) */
@@ -146,6 +160,8 @@ typedef struct xkv_factorize_options {
   int32_t small_split_k;
   float shifts[4];        /* diagonal shift of CholeskyQR pass 0,1,2,3+ */
   float pivot_floor;
+  float spectral_shift;   /* power steps after the first iterate with G - c I, c = spectral_shift * (estimate of lambda_l); 0 = off (0.5) */
+  int32_t shift_tail;     /* trailing entries of diag(R) of the previous step that estimate lambda_l (8) */
   uint64_t seed;
 } xkv_factorize_options;
 XKV_API void xkv_factorize_default_options(xkv_factorize_options* opts);

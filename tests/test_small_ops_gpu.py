@@ -64,6 +64,41 @@ def test_normalize_rows_with_limbs():
         assert (h.float() + m.float() + l.float() - y).abs().max().item() < 1e-7
 
 
+def test_shift_normalize_rows_and_rdiag():
+    """Y <- Y - c Q, unit rows + limbs, diag(R) bookkeeping and the shift update."""
+    from xkv_b200 import ops
+
+    torch.manual_seed(3)
+    qs = [torch.linalg.qr(torch.randn(512, 64, device="cuda"))[0].t().contiguous() for _ in range(3)]
+    ys = [q * torch.linspace(5.0, 1.0, 64, device="cuda")[:, None] + 0.01 * torch.randn(64, 512, device="cuda") for q in qs]
+    shifts = torch.tensor([0.25, 0.5, 0.0], device="cuda")
+    zs = [y - c * q for y, q, c in zip(ys, qs, shifts)]
+    norms = [z.norm(dim=1) for z in zs]
+    refs = [z / nz[:, None] for z, nz in zip(zs, norms)]
+    hi = [torch.empty(64, 512, device="cuda", dtype=torch.bfloat16) for _ in ys]
+    mid = [torch.empty_like(h) for h in hi]
+    rdiag = [torch.full((64,), 7.0, device="cuda") for _ in ys]
+    ops.shift_normalize_rows(ys, qs, shifts, rdiag, True, hi, mid, None)
+    torch.cuda.synchronize()
+    for y, r, h, m, rd, nz in zip(ys, refs, hi, mid, rdiag, norms):
+        assert torch.allclose(y, r, atol=1e-6)
+        assert (h.float() + m.float() - y).abs().max().item() < 1e-4
+        assert torch.allclose(rd, nz, rtol=1e-5)
+    # second pass multiplies the norms in; the Cholesky diagonal divides by Linv_jj
+    ys2 = [torch.randn(64, 512, device="cuda") for _ in ys]
+    n2 = [y.norm(dim=1) for y in ys2]
+    ops.shift_normalize_rows(ys2, None, None, rdiag, False)
+    linvs = [torch.rand(64, 64, device="cuda") + 0.5 for _ in ys]
+    ops.rdiag_update(rdiag, linvs)
+    torch.cuda.synchronize()
+    for rd, a, b, li in zip(rdiag, norms, n2, linvs):
+        assert torch.allclose(rd, a * b / li.diagonal(), rtol=1e-5)
+    c_ref = torch.stack([0.5 * (rd[-8:].mean() + c) for rd, c in zip(rdiag, shifts)])
+    ops.ritz_shift_update(rdiag, shifts, 8, 0.5)
+    torch.cuda.synchronize()
+    assert torch.allclose(shifts, c_ref, rtol=1e-5)
+
+
 @pytest.mark.parametrize("l,cond", [(64, 10.0), (192, 1e3), (576, 1e4), (832, 1e2)])
 def test_cholesky_inverse(l, cond):
     from xkv_b200 import ops

@@ -64,6 +64,8 @@ class FactorizeOptions(C.Structure):
         ("small_split_k", C.c_int32),
         ("shifts", C.c_float * 4),
         ("pivot_floor", C.c_float),
+        ("spectral_shift", C.c_float),
+        ("shift_tail", C.c_int32),
         ("seed", C.c_uint64),
     ]
 
@@ -84,6 +86,9 @@ SIGNATURES = {
     "xkv_split_bf16": (_i, [_vp, _i, _i, _i64, _vp, _vp, _vp, _i64, _vp]),
     "xkv_fill_gaussian_bf16": (_i, [_vp, _i, _i, _i64, C.c_uint64, _vp]),
     "xkv_normalize_rows": (_i, [_pp, _pp, _pp, _pp, _i, _i, _i, _i64, _i64, _vp]),
+    "xkv_shift_normalize_rows": (_i, [_pp, _pp, _vp, _pp, _i, _pp, _pp, _pp, _i, _i, _i, _i64, _i64, _vp]),
+    "xkv_ritz_shift_update": (_i, [_pp, _i, _i, _i, _f, _vp, _vp]),
+    "xkv_rdiag_update": (_i, [_pp, _pp, _i, _i, _i64, _vp]),
     "xkv_cholesky_inverse": (_i, [_pp, _pp, _i, _i, _i64, _f, _f, _vp]),
     "xkv_jacobi_eigh": (_i, [_pp, _pp, _pp, _i, _i, _i64, _i64, _i, _vp]),
     "xkv_convert_bf16": (_i, [_vp, _i, _i, _i64, _vp, _i64, _vp, _i64, _vp]),

@@ -46,6 +46,7 @@ struct Plan {
   float* s_slabs[XKV_MAX_BATCH];
   float* s_mat[XKV_MAX_BATCH];
   float* linv[XKV_MAX_BATCH];
+  float* rdiag[XKV_MAX_BATCH];   // running diag(R) of the current power step
   void* linv_l[XKV_MAX_BATCH][3];
   float* yw[XKV_MAX_BATCH][2];
   void* yw_l[XKV_MAX_BATCH][2][3];
@@ -56,6 +57,7 @@ struct Plan {
   void* wsel_l[XKV_MAX_BATCH][3];
   // shared
   float* gram_slabs;  // [B][gs][n][n]
+  float* shift_dev;   // [B] spectral shifts of the current power step
   float* g32;
   size_t bytes;
 };
@@ -105,6 +107,7 @@ static int make_plan(Plan& P, Bump& bump, int B, int m, int n, int rank, const x
     P.s_slabs[b] = bump.f32(static_cast<size_t>(P.sk) * l * l);
     P.s_mat[b] = bump.f32(l * l);
     P.linv[b] = bump.f32(l * l);
+    P.rdiag[b] = bump.f32(l);
     for (int i = 0; i < 3; ++i) P.linv_l[b][i] = bump.bf16(l * l);
     for (int w = 0; w < P.nw; ++w) {
       P.yw[b][w] = bump.f32(static_cast<size_t>(W) * nn);
@@ -120,6 +123,7 @@ static int make_plan(Plan& P, Bump& bump, int B, int m, int n, int rank, const x
   }
   P.gram_slabs = bump.f32(static_cast<size_t>(B) * P.gs * nn * nn);
   P.g32 = bump.f32(nn * nn);
+  P.shift_dev = bump.f32(XKV_MAX_BATCH);
   P.bytes = align_up(bump.off, 1024);
   return 0;
 }
@@ -182,7 +186,9 @@ using namespace xkv;
 extern "C" void xkv_factorize_default_options(xkv_factorize_options* o) {
   if (!o) return;
   std::memset(o, 0, sizeof(*o));
-  o->power_iters = 6;
+  o->power_iters = 4;
+  o->spectral_shift = 0.5f;
+  o->shift_tail = 8;
   o->oversample = 64;
   o->first_passes = 2;
   o->passes = 2;
@@ -292,9 +298,12 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
     nxt = t;
   };
   // cur <- orth(cur): row-normalised, shifted CholeskyQR
-  auto cholqr = [&](int npass) -> int {
+  // With `shifted`, cur = Q_prev G and nxt still holds Q_prev: the first pass first forms Q_prev (G - c I).
+  // With `track`, diag(R) of the step is accumulated in P.rdiag (row norms x Cholesky diagonals).
+  auto cholqr = [&](int npass, bool shifted, bool track) -> int {
     for (int ip = 0; ip < npass; ++ip) {
-      XKV_TRY(xkv_normalize_rows(cur, P.lh, P.lm, P.ll, B, l, n, nn, nn, stream));
+      XKV_TRY(xkv_shift_normalize_rows(cur, (ip == 0 && shifted) ? nxt : nullptr, P.shift_dev, track ? P.rdiag : nullptr,
+                                       ip == 0, P.lh, P.lm, P.ll, B, l, n, nn, nn, stream));
       // pass 0 is regularised by a 3e-4 shift, so the 3-term product (error ~1e-5) is accurate enough there
       const int nt = ip == 0 ? 3 : 6;
       for (int b = 0; b < B; ++b) {
@@ -308,6 +317,7 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
       XKV_TRY(run_gemms(ps, stream));
       XKV_TRY(xkv_reduce_slabs_batched(P.s_slabs, P.s_mat, B, P.sk, static_cast<long long>(l) * l, l, l, l, 1, l, stream));
       XKV_TRY(xkv_cholesky_inverse(P.s_mat, P.linv, B, l, l, o.shifts[ip < 3 ? ip : 3], o.pivot_floor, stream));
+      if (track) XKV_TRY(xkv_rdiag_update(P.rdiag, P.linv, B, l, l, stream));
       {
         void *h0[XKV_MAX_BATCH], *h1[XKV_MAX_BATCH], *h2[XKV_MAX_BATCH];
         for (int b = 0; b < B; ++b) h0[b] = P.linv_l[b][0], h1[b] = P.linv_l[b][1], h2[b] = P.linv_l[b][2];
@@ -334,14 +344,22 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
   // ---- 2-3. Gaussian range finder ----
   for (int b = 0; b < B; ++b) XKV_TRY(xkv_fill_gaussian_bf16(P.lh[b], l, n, nn, o.seed + 7919ull * b, stream));
   XKV_TRY(apply_gram(1));
-  XKV_TRY(cholqr(o.first_passes));
+  XKV_TRY(cholqr(o.first_passes, false, false));
   XKV_TRY(mark());  // 3: range finder
 
   // ---- 4. power steps ----
+  // The first step is plain (the range finder's triangular factor says nothing about eigenvalues); from the
+  // second step on the shift c = spectral_shift * lambda_l comes from diag(R) of the step before.
+  const bool use_shift = o.spectral_shift > 0.f && o.shift_tail > 0 && o.power_iters > 1;
+  if (use_shift) XKV_CHECK_CUDA(cudaMemsetAsync(P.shift_dev, 0, XKV_MAX_BATCH * sizeof(float), st));
   for (int it = 0; it < o.power_iters; ++it) {
     XKV_TRY(xkv_split_bf16_batched(cur, P.lh, P.lm, nullptr, B, l, n, nn, nn, stream));
     XKV_TRY(apply_gram(3));
-    XKV_TRY(cholqr(it == o.power_iters - 1 ? o.final_passes : o.passes));
+    const bool shifted = use_shift && it > 0;
+    if (shifted)
+      XKV_TRY(xkv_ritz_shift_update(P.rdiag, B, l, o.shift_tail < l ? o.shift_tail : l, o.spectral_shift, P.shift_dev,
+                                    stream));
+    XKV_TRY(cholqr(it == o.power_iters - 1 ? o.final_passes : o.passes, shifted, use_shift && it + 1 < o.power_iters));
   }
   XKV_TRY(mark());  // 4: power iterations
 

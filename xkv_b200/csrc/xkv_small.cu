@@ -138,18 +138,68 @@ __global__ void __launch_bounds__(256) fill_gaussian_kernel(__nv_bfloat16* __res
 // =============================================================================================
 struct NormParams {
   float* Y[XKV_MAX_BATCH];
+  const float* Q[XKV_MAX_BATCH];   // optional: previous orthonormal basis, Y <- Y - c[b] * Q before normalising
   __nv_bfloat16* hi[XKV_MAX_BATCH];
   __nv_bfloat16* mid[XKV_MAX_BATCH];
   __nv_bfloat16* lo[XKV_MAX_BATCH];
-  int rows, cols;
-  long long ld, ldo;
+  float* rdiag[XKV_MAX_BATCH];     // optional: running diagonal of the triangular factor R of Y = R^T Q_new
+  const float* Linv[XKV_MAX_BATCH];
+  float* c;                        // per-matrix spectral shift (device), used when Q != null
+  int rows, cols, tail, rdiag_first;
+  float shift_scale;
+  long long ld, ldo, ld_linv;
 };
+
+// Spectral shift of the power steps.  Orthogonal iteration Y = Q (G - c I) = R^T Q_new makes diag(R) converge
+// to the eigenvalues lambda_j - c, so the trailing `tail` entries of diag(R) of the previous step estimate
+// lambda_l, the largest unwanted eigenvalue: c_new = shift_scale * (mean_tail diag(R) + c_old).  With
+// c = lambda_l / 2 the unwanted spectrum [0, lambda_l] maps to [-c, c] and the convergence ratio of direction i
+// drops from lambda_l / lambda_i to (lambda_l / 2) / (lambda_i - lambda_l / 2).  diag(R) is accumulated over
+// the CholeskyQR passes: row norm (normalize_rows_kernel) times the Cholesky diagonal 1 / Linv_jj (below).
+// Unlike Rayleigh quotients it is insensitive to trailing basis vectors that are still polluted by the
+// dominant directions (the Gram-Schmidt step removes those before the norm is taken).
+__global__ void __launch_bounds__(256) ritz_shift_kernel(const __grid_constant__ NormParams p) {
+  __shared__ float red[8];
+  const float* rd = p.rdiag[blockIdx.x];
+  float acc = 0.f;
+  for (int j = p.rows - p.tail + threadIdx.x; j < p.rows; j += blockDim.x) acc += rd[j];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    p.c[blockIdx.x] = fmaxf(p.shift_scale * (t / static_cast<float>(p.tail) + p.c[blockIdx.x]), 0.f);
+  }
+}
+// rdiag[j] /= Linv[j][j]  (the Cholesky diagonal L_jj = 1 / Linv_jj of the pass that just finished)
+__global__ void __launch_bounds__(256) rdiag_update_kernel(const __grid_constant__ NormParams p) {
+  float* rd = p.rdiag[blockIdx.y];
+  const float* li = p.Linv[blockIdx.y];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < p.rows) rd[j] = rd[j] / li[static_cast<long long>(j) * p.ld_linv + j];
+}
+
 __global__ void __launch_bounds__(256) normalize_rows_kernel(const __grid_constant__ NormParams p) {
   __shared__ float red[8];
   __shared__ float scale_s;
   float* row = p.Y[blockIdx.y] + static_cast<long long>(blockIdx.x) * p.ld;
   const int cols4 = p.cols >> 2;
   float acc = 0.f;
+  if (p.Q[blockIdx.y] != nullptr) {
+    const float* qrow = p.Q[blockIdx.y] + static_cast<long long>(blockIdx.x) * p.ld;
+    const float cshift = p.c[blockIdx.y];
+    for (int c = threadIdx.x; c < cols4; c += blockDim.x) {
+      float4 v = reinterpret_cast<const float4*>(row)[c];
+      const float4 q = reinterpret_cast<const float4*>(qrow)[c];
+      v.x = fmaf(-cshift, q.x, v.x);
+      v.y = fmaf(-cshift, q.y, v.y);
+      v.z = fmaf(-cshift, q.z, v.z);
+      v.w = fmaf(-cshift, q.w, v.w);
+      reinterpret_cast<float4*>(row)[c] = v;   // re-read below by the same thread
+      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+  } else
   for (int c = threadIdx.x; c < cols4; c += blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(row)[c];
     acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
@@ -161,6 +211,10 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const __grid_consta
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += red[i];
     scale_s = t > 0.f ? rsqrtf(t) : 0.f;
+    if (p.rdiag[blockIdx.y] != nullptr) {
+      float* rd = p.rdiag[blockIdx.y] + blockIdx.x;
+      *rd = (p.rdiag_first ? 1.f : *rd) * sqrtf(t);
+    }
   }
   __syncthreads();
   const float sc = scale_s;
@@ -731,6 +785,68 @@ extern "C" int xkv_normalize_rows(float* const* Y_host, void* const* hi_host, vo
   p.ld = ld;
   p.ldo = ld_out;
   normalize_rows_kernel<<<dim3(rows, batch), 256, 0, as_stream(stream)>>>(p);
+  XKV_LAUNCHED();
+  return 0;
+}
+
+extern "C" int xkv_shift_normalize_rows(float* const* Y_host, const float* const* Q_host, float* shift_dev,
+                                        float* const* rdiag_host, int rdiag_first, void* const* hi_host,
+                                        void* const* mid_host, void* const* lo_host, int batch, int rows, int cols,
+                                        int64_t ld, int64_t ld_out, void* stream) {
+  XKV_REQUIRE(Y_host && batch >= 1 && batch <= XKV_MAX_BATCH, "shift_normalize_rows: bad batch");
+  XKV_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0 && ld % 4 == 0 && ld_out % 4 == 0,
+              "shift_normalize_rows: cols/ld must be multiples of 4");
+  XKV_REQUIRE(!Q_host || shift_dev, "shift_normalize_rows: a shifted step needs the device shifts");
+  NormParams p;
+  std::memset(&p, 0, sizeof(p));
+  for (int b = 0; b < batch; ++b) {
+    XKV_REQUIRE(Y_host[b] && (!Q_host || Q_host[b]), "shift_normalize_rows: null matrix %d", b);
+    p.Y[b] = Y_host[b];
+    p.Q[b] = Q_host ? Q_host[b] : nullptr;
+    p.rdiag[b] = rdiag_host ? rdiag_host[b] : nullptr;
+    p.hi[b] = hi_host ? static_cast<__nv_bfloat16*>(hi_host[b]) : nullptr;
+    p.mid[b] = mid_host ? static_cast<__nv_bfloat16*>(mid_host[b]) : nullptr;
+    p.lo[b] = lo_host ? static_cast<__nv_bfloat16*>(lo_host[b]) : nullptr;
+  }
+  p.c = shift_dev;
+  p.rows = rows;
+  p.cols = cols;
+  p.rdiag_first = rdiag_first;
+  p.ld = ld;
+  p.ldo = ld_out;
+  normalize_rows_kernel<<<dim3(rows, batch), 256, 0, as_stream(stream)>>>(p);
+  XKV_LAUNCHED();
+  return 0;
+}
+
+extern "C" int xkv_ritz_shift_update(float* const* rdiag_host, int batch, int rows, int tail_rows, float shift_scale,
+                                     float* shift_dev, void* stream) {
+  XKV_REQUIRE(rdiag_host && shift_dev && batch >= 1 && batch <= XKV_MAX_BATCH, "ritz_shift_update: bad arguments");
+  XKV_REQUIRE(tail_rows >= 1 && tail_rows <= rows, "ritz_shift_update: tail_rows out of range");
+  NormParams p;
+  std::memset(&p, 0, sizeof(p));
+  for (int b = 0; b < batch; ++b) p.rdiag[b] = rdiag_host[b];
+  p.c = shift_dev;
+  p.rows = rows;
+  p.tail = tail_rows;
+  p.shift_scale = shift_scale;
+  ritz_shift_kernel<<<batch, 256, 0, as_stream(stream)>>>(p);
+  XKV_LAUNCHED();
+  return 0;
+}
+
+extern "C" int xkv_rdiag_update(float* const* rdiag_host, const float* const* Linv_host, int batch, int rows,
+                                int64_t ld_linv, void* stream) {
+  XKV_REQUIRE(rdiag_host && Linv_host && batch >= 1 && batch <= XKV_MAX_BATCH, "rdiag_update: bad arguments");
+  NormParams p;
+  std::memset(&p, 0, sizeof(p));
+  for (int b = 0; b < batch; ++b) {
+    p.rdiag[b] = rdiag_host[b];
+    p.Linv[b] = Linv_host[b];
+  }
+  p.rows = rows;
+  p.ld_linv = ld_linv;
+  rdiag_update_kernel<<<dim3((rows + 255) / 256, batch), 256, 0, as_stream(stream)>>>(p);
   XKV_LAUNCHED();
   return 0;
 }

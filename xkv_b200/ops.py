@@ -173,6 +173,31 @@ def normalize_rows(ys: Sequence[torch.Tensor], hi=None, mid=None, lo=None) -> No
                                          rows, cols, ys[0].stride(0), ldo, _stream()))
 
 
+def shift_normalize_rows(ys: Sequence[torch.Tensor], qs: Optional[Sequence[torch.Tensor]] = None,
+                         shifts: Optional[torch.Tensor] = None, rdiag: Optional[Sequence[torch.Tensor]] = None,
+                         rdiag_first: bool = True, hi=None, mid=None, lo=None) -> None:
+    """Y <- Y - shifts[b] * Q (when `qs` is given), then row-normalise like normalize_rows; the row norms are
+    recorded in (rdiag_first) or multiplied into `rdiag` (running diagonal of the triangular factor)."""
+    _require_cuda(*ys)
+    rows, cols = ys[0].shape
+    ldo = hi[0].stride(0) if hi is not None else cols
+    check(_lib.load().xkv_shift_normalize_rows(_ptr_array(ys), _ptr_array(qs), _ptr(shifts) if shifts is not None else None,
+                                               _ptr_array(rdiag), int(rdiag_first), _ptr_array(hi), _ptr_array(mid),
+                                               _ptr_array(lo), len(ys), rows, cols, ys[0].stride(0), ldo, _stream()))
+
+
+def ritz_shift_update(rdiag: Sequence[torch.Tensor], shifts: torch.Tensor, tail_rows: int = 8, shift_scale: float = 0.5) -> None:
+    """shifts[b] <- shift_scale * (mean of the last tail_rows entries of rdiag[b] + shifts[b])."""
+    check(_lib.load().xkv_ritz_shift_update(_ptr_array(rdiag), len(rdiag), rdiag[0].numel(), tail_rows,
+                                            C.c_float(shift_scale), _ptr(shifts), _stream()))
+
+
+def rdiag_update(rdiag: Sequence[torch.Tensor], linvs: Sequence[torch.Tensor]) -> None:
+    """rdiag[b][j] /= Linv[b][j][j]."""
+    check(_lib.load().xkv_rdiag_update(_ptr_array(rdiag), _ptr_array(linvs), len(rdiag), rdiag[0].numel(),
+                                       linvs[0].stride(0), _stream()))
+
+
 def cholesky_inverse(ss: Sequence[torch.Tensor], linvs: Sequence[torch.Tensor], shift: float = 0.0,
                      pivot_floor: float = 1e-12) -> None:
     """Batched (S + shift*I) = L L^T and Linv = L^{-1} (see include/xkv_b200.h for what is left in S)."""
