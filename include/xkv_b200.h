@@ -117,13 +117,17 @@ XKV_API int xkv_ritz_shift_update(float* const* rdiag_host, int batch, int rows,
                                   float* shift_dev, void* stream);
 XKV_API int xkv_rdiag_update(float* const* rdiag_host, const float* const* Linv_host, int batch, int rows,
                              int64_t ld_linv, void* stream);
-/* Batched blocked Cholesky S = L L^T of l x l fp32 matrices (l % 64 == 0, unit diagonal expected) with
- * explicit inverse Linv = L^{-1} (dense l x l, zero above the diagonal). S is overwritten: its strictly
- * lower 64-blocks hold L, its diagonal blocks are left untouched. `shift` is added to the diagonal
- * (shifted CholeskyQR: the Gram of an ill-conditioned sketch is indefinite in fp32); pivots below
- * pivot_floor are clamped, so the factorisation never fails (CholeskyQR is repeated instead). */
+/* Batched blocked Cholesky (S + shift*I) = L L^T of l x l fp32 matrices (l % 64 == 0, symmetric, both
+ * triangles present, unit diagonal expected) with explicit inverse Linv = L^{-1} (dense l x l, zero above the
+ * diagonal).  One launch: a thread-block cluster per matrix (xkv_chol.cu).  S is scratch and is destroyed.
+ * Pivots below pivot_floor are clamped, so the factorisation never fails (CholeskyQR is repeated instead; the
+ * shift keeps the fp32 Gram of an ill-conditioned sketch positive).  The _limbs variant also writes the bf16
+ * limbs hi + mid + lo ~= Linv (row stride ld_limb) that the tensor-core GEMM Q = Linv Y consumes. */
 XKV_API int xkv_cholesky_inverse(float* const* S_host, float* const* Linv_host, int batch, int l, int64_t ld,
                                  float shift, float pivot_floor, void* stream);
+XKV_API int xkv_cholesky_inverse_limbs(float* const* S_host, float* const* Linv_host, void* const* hi_host,
+                                       void* const* mid_host, void* const* lo_host, int batch, int l, int64_t ld,
+                                       int64_t ld_limb, float shift, float pivot_floor, void* stream);
 /* Shared-memory two-sided Jacobi eigen-solver for the Rayleigh-Ritz windows: `count` symmetric W x W
  * fp32 matrices (W even, <= 160), one CTA each. evals: eigenvalues sorted descending; Wt (optional):
  * eigenvectors as rows, same order. */

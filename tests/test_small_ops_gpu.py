@@ -125,6 +125,34 @@ def test_cholesky_inverse(l, cond):
         assert err < 5e-3 * max(1.0, cond / 1e3), f"Linv S Linv^T deviates from I by {err}"
 
 
+@pytest.mark.parametrize("l,batch", [(128, 1), (320, 2), (576, 8), (1088, 2)])
+def test_cholesky_inverse_limbs_match_fp32_inverse(l, batch):
+    """The fused kernel's bf16 limbs of Linv (the GEMM operand) add up to the fp32 Linv it writes; the inverse
+    agrees with torch's Cholesky + triangular solve in fp64."""
+    from xkv_b200 import ops
+
+    torch.manual_seed(l + batch)
+    ss, refs = [], []
+    for b in range(batch):
+        y = torch.randn(l, 3 * l, device="cuda", dtype=torch.float64)
+        y = y / y.norm(dim=1, keepdim=True)
+        s = y @ y.t()
+        refs.append(torch.linalg.inv(torch.linalg.cholesky(s + 1e-6 * torch.eye(l, device="cuda", dtype=torch.float64))))
+        ss.append(s.float().contiguous())
+    linvs = [torch.full((l, l), float("nan"), device="cuda") for _ in range(batch)]
+    limbs = [[torch.full((l, l), float("nan"), device="cuda", dtype=torch.bfloat16) for _ in range(batch)] for _ in range(3)]
+    ops.cholesky_inverse(ss, linvs, shift=1e-6, pivot_floor=1e-12, limbs=limbs)
+    torch.cuda.synchronize()
+    for b in range(batch):
+        li = linvs[b]
+        assert not torch.isnan(li).any()
+        assert torch.equal(torch.triu(li, 1), torch.zeros_like(li))
+        rel = (li.double() - refs[b]).abs().max().item() / refs[b].abs().max().item()
+        assert rel < 1e-4, f"Linv deviates from the fp64 inverse by {rel}"
+        total = limbs[0][b].float() + limbs[1][b].float() + limbs[2][b].float()
+        assert (total - li).abs().max().item() <= 1e-6 * li.abs().max().item()
+
+
 def test_cholesky_shift_keeps_indefinite_gram_finite():
     """The fp32 Gram of a nearly rank-deficient sketch is indefinite; the shifted factorisation must stay
     finite and equal the factor of S + shift*I."""

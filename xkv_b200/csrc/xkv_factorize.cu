@@ -316,13 +316,13 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
       }
       XKV_TRY(run_gemms(ps, stream));
       XKV_TRY(xkv_reduce_slabs_batched(P.s_slabs, P.s_mat, B, P.sk, static_cast<long long>(l) * l, l, l, l, 1, l, stream));
-      XKV_TRY(xkv_cholesky_inverse(P.s_mat, P.linv, B, l, l, o.shifts[ip < 3 ? ip : 3], o.pivot_floor, stream));
-      if (track) XKV_TRY(xkv_rdiag_update(P.rdiag, P.linv, B, l, l, stream));
       {
         void *h0[XKV_MAX_BATCH], *h1[XKV_MAX_BATCH], *h2[XKV_MAX_BATCH];
         for (int b = 0; b < B; ++b) h0[b] = P.linv_l[b][0], h1[b] = P.linv_l[b][1], h2[b] = P.linv_l[b][2];
-        XKV_TRY(xkv_split_bf16_batched(P.linv, h0, h1, h2, B, l, l, l, l, stream));
+        XKV_TRY(xkv_cholesky_inverse_limbs(P.s_mat, P.linv, h0, h1, nt > 3 ? h2 : nullptr, B, l, l, l,
+                                           o.shifts[ip < 3 ? ip : 3], o.pivot_floor, stream));
       }
+      if (track) XKV_TRY(xkv_rdiag_update(P.rdiag, P.linv, B, l, l, stream));
       for (int b = 0; b < B; ++b)
         ps.push_back(problem(P.linv_l[b][0], P.linv_l[b][1], P.linv_l[b][2], l, 0, P.lh[b], P.lm[b], P.ll[b], nn, 1,
                              nxt[b], nn, l, n, l, nt));

@@ -1,6 +1,6 @@
 // xkv_b200 — the small fp32 kernels around the tensor-core GEMMs of the factorisation:
 // split-K reduction / Gram symmetrisation, fp32 -> bf16 limb splitting, the Gaussian test matrix,
-// row normalisation, blocked Cholesky with explicit triangular inverse (CholeskyQR), the
+// row normalisation (the Cholesky of CholeskyQR lives in xkv_chol.cu), the
 // shared-memory Jacobi eigen-solver for the Rayleigh-Ritz window, and bf16 conversion/transposition
 // of the right factor.  Together with xkv_gemm.cu they replace torch.linalg.svd
 // (fake_layer_merge_dynamic_cache.py:20).
@@ -239,306 +239,6 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(const __grid_consta
       if (mid) *reinterpret_cast<uint2*>(mid + o0 + 4 * c) = *reinterpret_cast<uint2*>(m);
       if (lo) *reinterpret_cast<uint2*>(lo + o0 + 4 * c) = *reinterpret_cast<uint2*>(l);
     }
-  }
-}
-
-// =============================================================================================
-// Blocked Cholesky (S + shift*I) = L L^T with explicit inverse Linv = L^{-1}, batched over blockIdx.y
-//
-// NB = 64, right-looking.  Phase F, step k (two launches):
-//   panel  : CTA i >= k factors the diagonal block in shared memory (every CTA redundantly, so no
-//            inter-CTA dependency inside a launch).  The inverse of the diagonal factor is accumulated
-//            by the same rank-1 sweeps that update the trailing triangle (forward substitution in
-//            right-looking form), so it costs no extra synchronisation.  CTA k publishes the inverse to
-//            Linv[k,k]; CTA i > k solves its block  L[i,k] = S[i,k] * L[k,k]^{-T}.
-//   update : trailing tiles  S[i,j] -= L[i,k] L[j,k]^T  (k < j <= i).
-// Phase I (recursive doubling, two launches per level s = 1, 2, 4, ... blocks): for each aligned pair of
-//   diagonal super-blocks [A 0; B C]:  T = B A^{-1}  (staged in the unused upper triangle of S), then
-//   Linv[C,A] = -C^{-1} T.  Critical path: 2s block products per level instead of k per step.
-// All block products read their operands from shared memory in k-major layout (one LDS.128 per operand
-// per k step).  Pivots are floored at `pivot_floor`; with `shift` the factorisation of the fp32 Gram of an
-// ill-conditioned sketch stays finite, and CholeskyQR is simply repeated.
-// =============================================================================================
-constexpr int NB = 64;
-constexpr int NBP = NB + 1;   // natural layout [r][c], conflict-free column walks
-constexpr int NBK = NB + 4;   // k-major layout [k][idx], rows 16-byte aligned for LDS.128
-constexpr int TILE_FLOATS = NB * NBK;
-
-struct CholParams {
-  float* S[XKV_MAX_BATCH];
-  float* Linv[XKV_MAX_BATCH];
-  int l, nblk, k;   // k: panel step (phase F) or super-block size s (phase I)
-  long long ld;
-  float pivot_floor;
-  float shift;      // added to the diagonal (shifted Cholesky): S + shift*I
-};
-
-// C(64x64, 4x4 per thread) += sum_k Ak[k][r] * Bk[k][c]   (both operands k-major in shared memory)
-__device__ __forceinline__ void block_mma(float (&acc)[4][4], const float* Ak, const float* Bk) {
-  const int tr = (threadIdx.x >> 4) * 4;
-  const int tc = (threadIdx.x & 15) * 4;
-#pragma unroll 8
-  for (int k = 0; k < NB; ++k) {
-    const float4 a = *reinterpret_cast<const float4*>(Ak + k * NBK + tr);
-    const float4 b = *reinterpret_cast<const float4*>(Bk + k * NBK + tc);
-    const float av[4] = {a.x, a.y, a.z, a.w};
-    const float bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-  }
-}
-// dst[k][r] = src[r][k]  (operand used as  X[r][k]  with k the contraction index)
-__device__ __forceinline__ void load_tile_T(float* dst, const float* src, long long ld) {
-  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-    const int r = e >> 6, k = e & 63;
-    dst[k * NBK + r] = src[static_cast<long long>(r) * ld + k];
-  }
-}
-// dst[k][c] = src[k][c]   (operand used as  X[k][c])
-__device__ __forceinline__ void load_tile_N(float* dst, const float* src, long long ld) {
-  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
-    const int k = e >> 6, c = e & 63;
-    dst[k * NBK + c] = src[static_cast<long long>(k) * ld + c];
-  }
-}
-__device__ __forceinline__ float* block_ptr(float* base, int bi, int bj, long long ld) {
-  return base + (static_cast<long long>(bi) * NB) * ld + static_cast<long long>(bj) * NB;
-}
-
-// ---- warp-level 16x16 Cholesky + triangular inverse with the block's rows held in registers ----
-// Executed by one full warp (lanes 16..31 mirror lanes 0..15 and only take part in the shuffles).
-// D, X: 64x64 natural layout (stride NBP) in shared memory; o = offset of the diagonal block.
-// On return D[o+i][o+c] = L[i][c] (zero above the diagonal) and X[o+r][o+c] = (L^{-1})[r][c].
-// Kept out of line on purpose: a fully unrolled 32x32 version inlined twice grew the kernel to 23k SASS
-// instructions and ran out of the instruction cache (ncu: 2/3 of the kernel stalled behind warp 0).
-__device__ __noinline__ void warp_chol16_inv16(float* D, float* X, int o, float pivot_floor) {
-  const int lane = threadIdx.x & 15;
-  const bool owner = (threadIdx.x & 31) < 16;
-  float a[16], x[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) a[c] = D[(o + lane) * NBP + o + c];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    float d = __shfl_sync(0xffffffffu, a[j], j);
-    d = fmaxf(d, pivot_floor);
-    const float inv = rsqrtf(d);
-    const float lij = lane > j ? a[j] * inv : (lane == j ? d * inv : 0.f);
-    a[j] = lij;
-#pragma unroll
-    for (int c = j + 1; c < 16; ++c) {
-      const float lcj = __shfl_sync(0xffffffffu, lij, c);
-      a[c] = fmaf(-lij, lcj, a[c]);
-    }
-  }
-  // x[r] = (L^{-1})[r][lane]: forward substitution, L rows broadcast by shuffle
-#pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    float s = lane == r ? 1.f : 0.f;
-#pragma unroll
-    for (int t = 0; t < r; ++t) {
-      const float lrt = __shfl_sync(0xffffffffu, a[t], r);
-      s = fmaf(-lrt, x[t], s);
-    }
-    const float lrr = __shfl_sync(0xffffffffu, a[r], r);
-    x[r] = lane <= r ? __fdividef(s, lrr) : 0.f;
-  }
-  if (owner) {
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      D[(o + lane) * NBP + o + c] = c <= lane ? a[c] : 0.f;
-      X[(o + c) * NBP + o + lane] = x[c];
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256) chol_panel_kernel(const __grid_constant__ CholParams p) {
-  __shared__ __align__(16) float buf0[TILE_FLOATS];  // D (natural, stride NBP) during the factor, then Di^T (k-major)
-  __shared__ __align__(16) float buf1[TILE_FLOATS];  // X = D^{-1} (natural, stride NBP), then the panel block (k-major)
-  float* S = p.S[blockIdx.y];
-  float* Linv = p.Linv[blockIdx.y];
-  const int k = p.k;
-  const int i = k + blockIdx.x;
-  const int tid = threadIdx.x;
-  float* D = buf0;
-  float* X = buf1;
-  const float* dblk = block_ptr(S, k, k, p.ld);
-  for (int e = tid; e < NB * NB; e += blockDim.x) {
-    const int r = e >> 6, c = e & 63;
-    D[r * NBP + c] = dblk[static_cast<long long>(r) * p.ld + c] + (r == c ? p.shift : 0.f);
-    X[r * NBP + c] = 0.f;
-  }
-  __syncthreads();
-  // 64x64 = 4x4 blocks of 16, right-looking.  Warp 0 factors and inverts each diagonal block in registers
-  // (shuffles only); the panel solve, the rank-16 trailing update and the off-diagonal blocks of the inverse
-  // (block forward substitution) are small smem-resident products spread over all 256 threads.
-  constexpr int BS = 16;
-  for (int jb = 0; jb < NB; jb += BS) {
-    if (tid < 32) warp_chol16_inv16(D, X, jb, p.pivot_floor);
-    __syncthreads();
-    const int below = NB - jb - BS;                 // rows under the diagonal block
-    // panel: L[i][jb+c] = sum_{t<=c} A[i][jb+t] * Xd[c][t]   (Xd = inverse of the diagonal factor, lower)
-    float pv[3];
-    int nmine = 0;
-    for (int e = tid; e < below * BS; e += 256) {
-      const int i = jb + BS + e / BS, c = e % BS;
-      float acc = 0.f;
-      for (int t = 0; t <= c; ++t) acc = fmaf(D[i * NBP + jb + t], X[(jb + c) * NBP + jb + t], acc);
-      pv[nmine++] = acc;
-    }
-    __syncthreads();
-    nmine = 0;
-    for (int e = tid; e < below * BS; e += 256) {
-      const int i = jb + BS + e / BS, c = e % BS;
-      D[i * NBP + jb + c] = pv[nmine++];
-    }
-    __syncthreads();
-    // trailing update: D[i][j] -= sum_t L[i][jb+t] L[j][jb+t],  jb+16 <= j <= i
-    for (int e = tid; e < below * below; e += 256) {
-      const int i = jb + BS + e / below, j = jb + BS + e % below;
-      if (j <= i) {
-        float acc = 0.f;
-#pragma unroll
-        for (int t = 0; t < BS; ++t) acc = fmaf(D[i * NBP + jb + t], D[j * NBP + jb + t], acc);
-        D[i * NBP + j] -= acc;
-      }
-    }
-    __syncthreads();
-  }
-  // off-diagonal blocks of X = L^{-1}: X[bi][bj] = -Xd_bi * sum_{t=bj}^{bi-1} L[bi][t] X[t][bj]
-  for (int bi = 1; bi < NB / BS; ++bi) {
-    float tv[3];
-    int nmine = 0;
-    const int ncols = bi * BS;                      // columns 0 .. 16*bi-1
-    for (int e = tid; e < BS * ncols; e += 256) {
-      const int r = bi * BS + e / ncols, c = e % ncols;
-      float acc = 0.f;
-      for (int t = c; t < ncols; ++t) acc = fmaf(D[r * NBP + t], X[t * NBP + c], acc);   // X[t][c] = 0 for t < c
-      tv[nmine++] = acc;
-    }
-    __syncthreads();
-    // stage T in the unused upper triangle of D (rows < 16*bi, columns of block bi), transposed
-    nmine = 0;
-    for (int e = tid; e < BS * ncols; e += 256) {
-      const int r = bi * BS + e / ncols, c = e % ncols;
-      D[c * NBP + r] = tv[nmine++];
-    }
-    __syncthreads();
-    for (int e = tid; e < BS * ncols; e += 256) {
-      const int r = bi * BS + e / ncols, c = e % ncols;
-      float acc = 0.f;
-      for (int t = bi * BS; t <= r; ++t) acc = fmaf(X[r * NBP + t], D[c * NBP + t], acc);
-      X[r * NBP + c] = -acc;
-    }
-    __syncthreads();
-  }
-  if (i == k) {
-    // Only the inverse of the diagonal block is published: L[k,k] itself is never read again, and
-    // writing it over S[k,k] would race with the other CTAs of this launch still loading that block.
-    float* iblk = block_ptr(Linv, k, k, p.ld);
-    for (int e = tid; e < NB * NB; e += blockDim.x) {
-      const int r = e >> 6, c = e & 63;
-      iblk[static_cast<long long>(r) * p.ld + c] = (c <= r) ? X[r * NBP + c] : 0.f;
-    }
-    return;
-  }
-  // L[i,k][r][c] = sum_kk S[i,k][r][kk] * Di[c][kk]:  Ak[kk][r] = S[i,k][r][kk],  Bk[kk][c] = Di[c][kk]
-  float* Bk = buf0;  // D is dead
-  for (int e = tid; e < NB * NB; e += blockDim.x) {
-    const int c = e >> 6, kk = e & 63;
-    Bk[kk * NBK + c] = (kk <= c) ? X[c * NBP + kk] : 0.f;
-  }
-  __syncthreads();   // X fully consumed before its buffer is reused
-  float* Ak = buf1;
-  float* pblk = block_ptr(S, i, k, p.ld);
-  load_tile_T(Ak, pblk, p.ld);
-  __syncthreads();
-  float acc[4][4] = {};
-  block_mma(acc, Ak, Bk);
-  const int tr = (tid >> 4) * 4, tc = (tid & 15) * 4;
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-    *reinterpret_cast<float4*>(pblk + static_cast<long long>(tr + a) * p.ld + tc) =
-        make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
-}
-
-__global__ void __launch_bounds__(256) chol_update_kernel(const __grid_constant__ CholParams p) {
-  __shared__ __align__(16) float Ak[TILE_FLOATS];
-  __shared__ __align__(16) float Bk[TILE_FLOATS];
-  float* S = p.S[blockIdx.y];
-  const int k = p.k;
-  // tile (i, j) of the trailing lower triangle, k < j <= i
-  int b = blockIdx.x, ii = 0;
-  while (b >= ii + 1) {
-    b -= ii + 1;
-    ++ii;
-  }
-  const int i = k + 1 + ii, j = k + 1 + b;
-  load_tile_T(Ak, block_ptr(S, i, k, p.ld), p.ld);
-  load_tile_T(Bk, block_ptr(S, j, k, p.ld), p.ld);
-  __syncthreads();
-  float acc[4][4] = {};
-  block_mma(acc, Ak, Bk);
-  float* o = block_ptr(S, i, j, p.ld);
-  const int tr = (threadIdx.x >> 4) * 4, tc = (threadIdx.x & 15) * 4;
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    float4* q = reinterpret_cast<float4*>(o + static_cast<long long>(tr + a) * p.ld + tc);
-    float4 v = *q;
-    v.x -= acc[a][0];
-    v.y -= acc[a][1];
-    v.z -= acc[a][2];
-    v.w -= acc[a][3];
-    *q = v;
-  }
-}
-
-// Phase I.  PASS 0:  T[i,j] = sum_{t=j}^{a+s-1} L[i,t] Linv[t,j]      -> staged at S block (j,i)
-//           PASS 1:  Linv[i,j] = - sum_{t=a+s}^{i} Linv[i,t] T[t,j]    (T[t,j] read from S block (j,t))
-// for i in the C rows [a+s, a+2s) and j in the A columns [a, a+s) of the aligned pair that contains them.
-template <int PASS>
-__global__ void __launch_bounds__(256) chol_inverse_kernel(const __grid_constant__ CholParams p) {
-  __shared__ __align__(16) float Ak[TILE_FLOATS];
-  __shared__ __align__(16) float Bk[TILE_FLOATS];
-  const int s = p.k;
-  const int i = blockIdx.x / p.nblk, j = blockIdx.x - i * p.nblk;
-  const int a = (j / (2 * s)) * 2 * s;
-  if (!(j < a + s && i >= a + s && i < a + 2 * s)) return;  // uniform per CTA
-  float* S = p.S[blockIdx.y];
-  float* Linv = p.Linv[blockIdx.y];
-  float acc[4][4] = {};
-  const int t0 = PASS == 0 ? j : a + s;
-  const int t1 = PASS == 0 ? a + s : i + 1;
-  for (int t = t0; t < t1; ++t) {
-    __syncthreads();
-    if (PASS == 0) {
-      load_tile_T(Ak, block_ptr(S, i, t, p.ld), p.ld);      // L[i,t][r][kk]
-      load_tile_N(Bk, block_ptr(Linv, t, j, p.ld), p.ld);   // Linv[t,j][kk][c]
-    } else {
-      load_tile_T(Ak, block_ptr(Linv, i, t, p.ld), p.ld);   // Linv[i,t][r][kk]
-      load_tile_N(Bk, block_ptr(S, j, t, p.ld), p.ld);      // T[t,j][kk][c], staged at (j,t)
-    }
-    __syncthreads();
-    block_mma(acc, Ak, Bk);
-  }
-  float* o = PASS == 0 ? block_ptr(S, j, i, p.ld) : block_ptr(Linv, i, j, p.ld);
-  const float sgn = PASS == 0 ? 1.f : -1.f;
-  const int tr = (threadIdx.x >> 4) * 4, tc = (threadIdx.x & 15) * 4;
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-    *reinterpret_cast<float4*>(o + static_cast<long long>(tr + r) * p.ld + tc) =
-        make_float4(sgn * acc[r][0], sgn * acc[r][1], sgn * acc[r][2], sgn * acc[r][3]);
-}
-
-// zero the strict upper block triangle of Linv (the GEMM consumes Linv as a dense matrix)
-__global__ void __launch_bounds__(256) zero_upper_kernel(const __grid_constant__ CholParams p) {
-  float* Linv = p.Linv[blockIdx.y];
-  const long long total = static_cast<long long>(p.l) * p.l;
-  for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-       e += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(e / p.l), c = static_cast<int>(e - static_cast<long long>(r) * p.l);
-    if ((c / NB) > (r / NB)) Linv[static_cast<long long>(r) * p.ld + c] = 0.f;
   }
 }
 
@@ -848,48 +548,6 @@ extern "C" int xkv_rdiag_update(float* const* rdiag_host, const float* const* Li
   p.ld_linv = ld_linv;
   rdiag_update_kernel<<<dim3((rows + 255) / 256, batch), 256, 0, as_stream(stream)>>>(p);
   XKV_LAUNCHED();
-  return 0;
-}
-
-extern "C" int xkv_cholesky_inverse(float* const* S_host, float* const* Linv_host, int batch, int l, int64_t ld,
-                                    float shift, float pivot_floor, void* stream) {
-  XKV_REQUIRE(S_host && Linv_host && batch >= 1 && batch <= XKV_MAX_BATCH, "cholesky: bad batch");
-  XKV_REQUIRE(l > 0 && l % NB == 0, "cholesky: l=%d must be a positive multiple of %d", l, NB);
-  XKV_REQUIRE(ld % 4 == 0, "cholesky: ld must be a multiple of 4");
-  CholParams p;
-  std::memset(&p, 0, sizeof(p));
-  for (int b = 0; b < batch; ++b) {
-    XKV_REQUIRE(S_host[b] && Linv_host[b], "cholesky: null matrix %d", b);
-    p.S[b] = S_host[b];
-    p.Linv[b] = Linv_host[b];
-  }
-  p.l = l;
-  p.nblk = l / NB;
-  p.ld = ld;
-  p.pivot_floor = pivot_floor;
-  p.shift = shift;
-  cudaStream_t st = as_stream(stream);
-  zero_upper_kernel<<<dim3(64, batch), 256, 0, st>>>(p);
-  XKV_LAUNCHED();
-  // phase F: factorisation, diagonal inverses
-  for (int k = 0; k < p.nblk; ++k) {
-    p.k = k;
-    chol_panel_kernel<<<dim3(p.nblk - k, batch), 256, 0, st>>>(p);
-    XKV_LAUNCHED();
-    const int nt = p.nblk - k - 1;
-    if (nt > 0) {
-      chol_update_kernel<<<dim3(nt * (nt + 1) / 2, batch), 256, 0, st>>>(p);
-      XKV_LAUNCHED();
-    }
-  }
-  // phase I: off-diagonal blocks of the inverse by recursive doubling
-  for (int s = 1; s < p.nblk; s *= 2) {
-    p.k = s;
-    chol_inverse_kernel<0><<<dim3(p.nblk * p.nblk, batch), 256, 0, st>>>(p);
-    XKV_LAUNCHED();
-    chol_inverse_kernel<1><<<dim3(p.nblk * p.nblk, batch), 256, 0, st>>>(p);
-    XKV_LAUNCHED();
-  }
   return 0;
 }
 

@@ -199,12 +199,19 @@ def rdiag_update(rdiag: Sequence[torch.Tensor], linvs: Sequence[torch.Tensor]) -
 
 
 def cholesky_inverse(ss: Sequence[torch.Tensor], linvs: Sequence[torch.Tensor], shift: float = 0.0,
-                     pivot_floor: float = 1e-12) -> None:
-    """Batched (S + shift*I) = L L^T and Linv = L^{-1} (see include/xkv_b200.h for what is left in S)."""
+                     pivot_floor: float = 1e-12, limbs=None) -> None:
+    """Batched (S + shift*I) = L L^T and Linv = L^{-1} in one cluster launch (S is destroyed); `limbs` =
+    (hi, mid, lo) lists of bf16 matrices that receive the limb split of Linv."""
     _require_cuda(*ss, *linvs)
     l = ss[0].shape[0]
-    check(_lib.load().xkv_cholesky_inverse(_ptr_array(ss), _ptr_array(linvs), len(ss), l, ss[0].stride(0),
-                                           C.c_float(shift), C.c_float(pivot_floor), _stream()))
+    if limbs is None:
+        check(_lib.load().xkv_cholesky_inverse(_ptr_array(ss), _ptr_array(linvs), len(ss), l, ss[0].stride(0),
+                                               C.c_float(shift), C.c_float(pivot_floor), _stream()))
+    else:
+        hi, mid, lo = limbs
+        check(_lib.load().xkv_cholesky_inverse_limbs(_ptr_array(ss), _ptr_array(linvs), _ptr_array(hi), _ptr_array(mid),
+                                                     _ptr_array(lo), len(ss), l, ss[0].stride(0), hi[0].stride(0),
+                                                     C.c_float(shift), C.c_float(pivot_floor), _stream()))
 
 
 def jacobi_eigh(ts: Sequence[torch.Tensor], evals: Sequence[torch.Tensor],
