@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the K / V batches are spread over")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from the host instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -184,12 +185,12 @@ def run_xkv_arm(args):
 
     graphed = None
     if not args.no_graph:
-        graphed = compress.GraphedCompressor(keys, vals, RANK_K, RANK_V, opts=opts)
+        graphed = compress.GraphedCompressor(keys, vals, RANK_K, RANK_V, opts=opts, num_streams=args.streams)
 
     def step():
         if graphed is not None:
             return graphed.replay()
-        return compress.compress_groups(keys, vals, RANK_K, RANK_V, opts=opts)
+        return compress.compress_groups(keys, vals, RANK_K, RANK_V, opts=opts, num_streams=args.streams)
 
     def barrier():
         if world > 1:

@@ -253,6 +253,7 @@ struct JacobiParams {
   float* evals[2 * XKV_MAX_BATCH];    // W
   float* Wt[2 * XKV_MAX_BATCH];       // W x W (ld_w), may be null (values only)
   int W, sweeps;
+  float tol;
   long long ld, ld_w;
 };
 constexpr int JAC_THREADS = 512;
@@ -275,6 +276,8 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jacobi_kernel(const __grid_con
     A[r * WP + c] = 0.5f * (T[static_cast<long long>(r) * p.ld + c] + T[static_cast<long long>(c) * p.ld + r]);
     V[r * WP + c] = (r == c) ? 1.f : 0.f;
   }
+  __shared__ unsigned int off_max;   // largest |a_ij| / sqrt(a_ii a_jj) rotated away in the current sweep
+  if (tid == 0) off_max = 0u;
   __syncthreads();
   for (int sweep = 0; sweep < p.sweeps; ++sweep) {
     for (int round = 0; round < W - 1; ++round) {
@@ -285,11 +288,14 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jacobi_kernel(const __grid_con
         const int i = min(a, b), j = max(a, b);
         const float aii = A[i * WP + i], ajj = A[j * WP + j], aij = A[i * WP + j];
         float c = 1.f, s = 0.f;
-        if (fabsf(aij) > 1e-12f * sqrtf(fabsf(aii * ajj)) && aij != 0.f) {
+        const float scale = sqrtf(fabsf(aii * ajj));
+        if (fabsf(aij) > 1e-12f * scale && aij != 0.f) {
           const float tau = (ajj - aii) / (2.f * aij);
           const float t = (tau >= 0.f ? 1.f : -1.f) / (fabsf(tau) + sqrtf(1.f + tau * tau));
           c = rsqrtf(1.f + t * t);
           s = t * c;
+          // non-negative floats order like their bit patterns
+          atomicMax(&off_max, __float_as_uint(fminf(fabsf(aij) / fmaxf(scale, 1e-30f), 1e30f)));
         }
         cs[2 * q] = c;
         cs[2 * q + 1] = s;
@@ -323,6 +329,14 @@ __global__ void __launch_bounds__(JAC_THREADS, 1) jacobi_kernel(const __grid_con
       }
       __syncthreads();
     }
+    // The window of T = Q^T G Q is close to diagonal after the power steps (orthogonal iteration converges to
+    // Schur form), so Jacobi converges quadratically from the first sweep: stop as soon as a whole sweep met
+    // no off-diagonal element above p.tol (relative); one more sweep would change the vectors by O(tol^2).
+    const float swept = __uint_as_float(off_max);
+    __syncthreads();
+    if (swept < p.tol) break;
+    if (tid == 0) off_max = 0u;
+    __syncthreads();
   }
   // sort eigenvalues descending by rank counting; emit eigenvectors as rows of Wt
   if (tid < W) {
@@ -565,6 +579,7 @@ extern "C" int xkv_jacobi_eigh(const float* const* T_host, float* const* evals_h
   }
   p.W = W;
   p.sweeps = sweeps;
+  p.tol = 1e-4f;   // a sweep whose largest rotated element is below this leaves off-diagonals of O(tol^2)
   p.ld = ld;
   p.ld_w = ld_w;
   const size_t smem = static_cast<size_t>(2 * W * (W + 1) + 2 * W) * sizeof(float) + 64;
