@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams the K / V batches are spread over")
+    ap.add_argument("--e2e-chunk", type=int, default=1, help="layer groups per pipelined chunk of the host-buffer path")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from the host instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -326,21 +327,27 @@ def run_xkv_arm(args):
 
     # ---- end to end through the public API with HOST buffers ----
     if not args.no_e2e:
+        # the synthetic cache is moved to pinned host memory and the device copies are dropped: every e2e step
+        # starts from HOST buffers and ends with the factors back in HOST buffers
         h_keys = [[t.transpose(1, 2).contiguous().cpu().pin_memory() for t in grp] for grp in keys]
         h_vals = [[t.transpose(1, 2).contiguous().cpu().pin_memory() for t in grp] for grp in vals]
-        h_out = None
+        r_k, r_v, n_cols = RANK_K, RANK_V, GROUP * HEADS * HEAD_DIM
+        h_out = []
+        for _ in range(ng):
+            for r in (r_k, r_v):
+                h_out.append(torch.empty(S, r, dtype=torch.bfloat16).pin_memory())
+                h_out.append(torch.empty(r, n_cols, dtype=torch.bfloat16).pin_memory())
+        d2h_bytes = sum(t.numel() * t.element_size() for t in h_out)
+        if graphed is not None:
+            del graphed, out
+            graphed = None
+        del keys, vals
+        torch.cuda.empty_cache()
 
         def e2e_step():
-            nonlocal h_out
-            dk = [[h.to(dev, non_blocking=True).transpose(1, 2) for h in grp] for grp in h_keys]
-            dv = [[h.to(dev, non_blocking=True).transpose(1, 2) for h in grp] for grp in h_vals]
-            res = compress.compress_groups(dk, dv, RANK_K, RANK_V, opts=opts)
-            tens = [t for gf in res for f in (gf.key, gf.value) for t in (f.A, f.Vt)]
-            if h_out is None:
-                h_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in tens]
-            for h, t in zip(h_out, tens):
-                h.copy_(t, non_blocking=True)
-            return sum(t.numel() * t.element_size() for t in tens)
+            compress.compress_groups_from_host(h_keys, h_vals, RANK_K, RANK_V, dev, chunk_groups=args.e2e_chunk,
+                                               opts=opts, host_out=h_out)
+            return d2h_bytes
 
         d2h = e2e_step()
         barrier()

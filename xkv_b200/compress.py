@@ -105,6 +105,70 @@ def compress_groups(
     return [GroupFactors(layers=list(ids[g]), key=kf[g], value=vf[g]) for g in range(ng)]
 
 
+def compress_groups_from_host(
+    h_keys: Sequence[Sequence[torch.Tensor]],
+    h_values: Sequence[Sequence[torch.Tensor]],
+    rank_k: Optional[int],
+    rank_v: Optional[int],
+    device: torch.device,
+    chunk_groups: int = 1,
+    opts: Optional[factorize.FactorizeOptions] = None,
+    host_out: Optional[List[torch.Tensor]] = None,
+    num_streams: int = 2,
+):
+    """Compress a KV cache that lives in (pinned) HOST memory, pipelined by chunks of `chunk_groups` layer groups:
+    the host->device copy of chunk c+1 runs on a copy stream while chunk c is factorised, and the factors of chunk
+    c-1 go back to the host on a third stream, so that the step costs about one pass of the KV over PCIe plus the
+    factorisation of the last chunk instead of copy + compute + copy in sequence.
+
+    h_keys[g][i] / h_values[g][i]: pinned (1, S, H, D) bf16 tensors (token-major, as HF produces K/V before the
+    (bs, H, S, D) view).  Returns (factors per group, host tensors [A_k, Vt_k, A_v, Vt_v per group] or None)."""
+    ng = len(h_keys)
+    main = torch.cuda.current_stream(device)
+    copy_s = _side_stream(device, 101)
+    back_s = _side_stream(device, 102)
+    # device staging for every group, allocated on the main stream (the copy stream only writes into it)
+    dk = [[torch.empty(h.shape, dtype=h.dtype, device=device) for h in grp] for grp in h_keys]
+    dv = [[torch.empty(h.shape, dtype=h.dtype, device=device) for h in grp] for grp in h_values]
+    copy_s.wait_stream(main)
+    ready = []
+    with torch.cuda.stream(copy_s):
+        for lo in range(0, ng, chunk_groups):
+            for g in range(lo, min(lo + chunk_groups, ng)):
+                for d, h in zip(dk[g], h_keys[g]):
+                    d.copy_(h, non_blocking=True)
+                for d, h in zip(dv[g], h_values[g]):
+                    d.copy_(h, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_s)
+            ready.append(ev)
+    out: List[GroupFactors] = []
+    host_tensors: Optional[List[torch.Tensor]] = [] if host_out is not None else None
+    k = 0
+    for c, lo in enumerate(range(0, ng, chunk_groups)):
+        hi = min(lo + chunk_groups, ng)
+        main.wait_event(ready[c])
+        keys = [[t.transpose(1, 2) for t in dk[g]] for g in range(lo, hi)]
+        vals = [[t.transpose(1, 2) for t in dv[g]] for g in range(lo, hi)]
+        res = compress_groups(keys, vals, rank_k, rank_v, opts=opts, num_streams=num_streams)
+        out.extend(res)
+        if host_out is not None:
+            done = torch.cuda.Event()
+            done.record(main)
+            back_s.wait_event(done)
+            with torch.cuda.stream(back_s):
+                for gf in res:
+                    for f in (gf.key, gf.value):
+                        for t in (f.A, f.Vt):
+                            host_out[k].copy_(t, non_blocking=True)
+                            t.record_stream(back_s)
+                            host_tensors.append(host_out[k])
+                            k += 1
+    main.wait_stream(back_s)
+    main.wait_stream(copy_s)
+    return out, host_tensors
+
+
 class GraphedCompressor:
     """compress_groups captured once into a CUDA graph and replayed (static input buffers).
 

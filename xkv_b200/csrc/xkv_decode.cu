@@ -15,6 +15,7 @@
 //            merging, cache:131); their scores / values join the same softmax.
 #include "xkv_common.cuh"
 #include "xkv_host.h"
+#include <cstdlib>
 
 namespace xkv {
 
@@ -213,11 +214,12 @@ __global__ void __launch_bounds__(D_THREADS, 2) decode_scores_kernel(const __gri
 // (L2 -> SM traffic per layer 786 MB -> 536 MB at config 2) and has no per-tile prologue.
 // ---------------------------------------------------------------------------------------------
 constexpr int PA_STAGES = 4;
-constexpr int P_EPI_WARPS = 8;                    // two warps per TMEM lane quarter: each takes half of the dims
+constexpr int P_EPI_WARPS = 16;                   // four warps per TMEM lane quarter: each takes a quarter of the dims
+constexpr int P_PARTS = P_EPI_WARPS / 4;
 constexpr int P_THREADS = 64 + 32 * P_EPI_WARPS;  // TMA warp + MMA warp + epilogue warps
 constexpr int PB_MAX_BYTES = 128 * 1024;
 constexpr size_t P_SMEM_BYTES = PB_MAX_BYTES + PA_STAGES * D_A_BYTES + 1024 + 256 + 128 * D_MAX_QPK * sizeof(float) +
-                                2 * DBM * D_MAX_QPK * sizeof(float);
+                                (P_PARTS - 1) * 2 * DBM * D_MAX_QPK * sizeof(float);
 
 template <int D>
 __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(const __grid_constant__ ScoreParams P) {
@@ -318,49 +320,315 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
       }
     }
   } else {
-    // ===== epilogue: 8 warps; warps 2-5 take the chunk pairs with even index, warps 6-9 the odd ones =====
+    // ===== epilogue: 16 warps, four per TMEM lane quarter; each thread owns one token and PP rotation pairs
+    // (d, d + D/2) of it.  ncu on the 8-warp version: the epilogue, not the MMA or the TMA ring, set the pace
+    // (two warps per scheduler cannot hide the LDS / convert / FMA dependency chains), hence more, lighter warps,
+    // packed FFMA2 for the q dot products, and the cos/sin words fetched one tile ahead. =====
+    constexpr int PP = D / 2 / P_PARTS;   // rotation pairs per thread: 16 (D = 128) or 8 (D = 64)
+    constexpr int CW = PP / 2;            // packed bf16x2 words of cos (and of sin) per thread
     const int ew = warp - 2;
-    const int qd = warp & 3;             // TMEM lane quarter (hardware: warp id mod 4)
-    const int half = ew >> 2;
-    const int row = qd * 32 + lane;      // token row inside the tile
+    const int qd = warp & 3;              // TMEM lane quarter (hardware: warp id mod 4)
+    const int prt = ew >> 2;              // which quarter of the rotation pairs
+    const int row = qd * 32 + lane;       // token row inside the tile
+    const int d0 = prt * PP;              // first dim of the low half; partners are d0 + D/2 ...
     const bool rope = P.cos != nullptr;
     int acc = 0;
     uint32_t ph_acc0 = 0u, ph_acc1 = 0u;
+    uint32_t cs_next[CW], sn_next[CW];
+    auto fetch_cs = [&](int tile_idx) {
+      const int t = tile_idx * DBM + row;
+      if (rope && tile_idx < ntiles && t < P.S) {
+        const uint4* cp = reinterpret_cast<const uint4*>(P.cos + static_cast<long long>(t) * P.ld_cs + d0);
+        const uint4* sp = reinterpret_cast<const uint4*>(P.sin + static_cast<long long>(t) * P.ld_cs + d0);
+#pragma unroll
+        for (int v = 0; v < CW / 4; ++v) {
+          const uint4 cv = __ldg(cp + v), sv = __ldg(sp + v);
+          cs_next[4 * v] = cv.x, cs_next[4 * v + 1] = cv.y, cs_next[4 * v + 2] = cv.z, cs_next[4 * v + 3] = cv.w;
+          sn_next[4 * v] = sv.x, sn_next[4 * v + 1] = sv.y, sn_next[4 * v + 2] = sv.z, sn_next[4 * v + 3] = sv.w;
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < CW; ++v) cs_next[v] = 0x3F803F80u, sn_next[v] = 0u;   // cos = 1, sin = 0
+      }
+    };
+    fetch_cs(slot);
     for (int tile = slot; tile < ntiles; tile += nslots) {
       const int tok = tile * DBM + row;
       const bool tok_ok = tok < P.S;
-      float sc[D_MAX_QPK];
+      float2 sc01 = make_float2(0.f, 0.f), sc23 = sc01, sc45 = sc01, sc67 = sc01;
+      uint32_t cs[CW], sn[CW];
 #pragma unroll
-      for (int g = 0; g < D_MAX_QPK; ++g) sc[g] = 0.f;
+      for (int v = 0; v < CW; ++v) cs[v] = cs_next[v], sn[v] = sn_next[v];
+      fetch_cs(tile + nslots);
       mbar_wait(&tfull_bar[acc], acc ? ph_acc1 : ph_acc0);
       if (acc) ph_acc1 ^= 1u; else ph_acc0 ^= 1u;
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + static_cast<uint32_t>(acc * D);
-#pragma unroll 1
-      for (int c = half; c < NCH / 2; c += 2) {
-        uint32_t cs[16], sn[16];
-        if (rope && tok_ok) {
-          const uint4* cp = reinterpret_cast<const uint4*>(P.cos + static_cast<long long>(tok) * P.ld_cs + c * 32);
-          const uint4* sp = reinterpret_cast<const uint4*>(P.sin + static_cast<long long>(tok) * P.ld_cs + c * 32);
+      uint32_t x1[PP], x2[PP];
+      __syncwarp();
+      tmem_ld_cols<PP>(lane_addr + static_cast<uint32_t>(d0), x1);
+      tmem_ld_cols<PP>(lane_addr + static_cast<uint32_t>(D / 2 + d0), x2);
+      tmem_ld_wait();
+      // accumulator columns of this thread are in registers: hand the buffer back to the MMA warp right away
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const uint4 cv = cp[v], sv = sp[v];
-            cs[4 * v] = cv.x, cs[4 * v + 1] = cv.y, cs[4 * v + 2] = cv.z, cs[4 * v + 3] = cv.w;
-            sn[4 * v] = sv.x, sn[4 * v + 1] = sv.y, sn[4 * v + 2] = sv.z, sn[4 * v + 3] = sv.w;
-          }
-        } else {
-#pragma unroll
-          for (int v = 0; v < 16; ++v) cs[v] = 0x3F803F80u, sn[v] = 0u;
+      for (int jp = 0; jp < PP / 2; ++jp) {
+        // two dims at a time in packed bf16: the reference's RoPE is bf16 arithmetic (each product and the sum
+        // rounded to bf16), which is exactly what HMUL2.BF16 / HADD2.BF16 compute
+        const __nv_bfloat162 k1 = __floats2bfloat162_rn(__uint_as_float(x1[2 * jp]), __uint_as_float(x1[2 * jp + 1]));
+        const __nv_bfloat162 k2 = __floats2bfloat162_rn(__uint_as_float(x2[2 * jp]), __uint_as_float(x2[2 * jp + 1]));
+        __nv_bfloat162 o1 = k1, o2 = k2;
+        if (rope) {
+          const __nv_bfloat162 cw = *reinterpret_cast<const __nv_bfloat162*>(&cs[jp]);
+          const __nv_bfloat162 sw = *reinterpret_cast<const __nv_bfloat162*>(&sn[jp]);
+          o1 = __hadd2(__hmul2(k1, cw), __hmul2(__hneg2(k2), sw));
+          o2 = __hadd2(__hmul2(k2, cw), __hmul2(k1, sw));
         }
-        uint32_t x1[32], x2[32];
-        __syncwarp();
-        tmem_ld_32x32(lane_addr + static_cast<uint32_t>(c * 32), x1);
-        tmem_ld_32x32(lane_addr + static_cast<uint32_t>((c + NCH / 2) * 32), x2);
-        tmem_ld_wait();
+        const float o1v[2] = {__low2float(o1), __high2float(o1)};
+        const float o2v[2] = {__low2float(o2), __high2float(o2)};
 #pragma unroll
-        for (int jp = 0; jp < 16; ++jp) {
-          // two dims at a time in packed bf16: the reference's RoPE is bf16 arithmetic (each product and the sum
-          // rounded to bf16), which is exactly what HMUL2.BF16 / HADD2.BF16 compute
+        for (int u = 0; u < 2; ++u) {
+          const int d1 = d0 + 2 * jp + u, d2 = d1 + D / 2;
+          const float2 a = make_float2(o1v[u], o1v[u]), b = make_float2(o2v[u], o2v[u]);
+          const float4 qa = *reinterpret_cast<const float4*>(q_s + d1 * D_MAX_QPK);
+          const float4 qb = *reinterpret_cast<const float4*>(q_s + d2 * D_MAX_QPK);
+          sc01 = __ffma2_rn(make_float2(qa.x, qa.y), a, __ffma2_rn(make_float2(qb.x, qb.y), b, sc01));
+          sc23 = __ffma2_rn(make_float2(qa.z, qa.w), a, __ffma2_rn(make_float2(qb.z, qb.w), b, sc23));
+          if (P.qpk > 4) {
+            const float4 qc = *reinterpret_cast<const float4*>(q_s + d1 * D_MAX_QPK + 4);
+            const float4 qe = *reinterpret_cast<const float4*>(q_s + d2 * D_MAX_QPK + 4);
+            sc45 = __ffma2_rn(make_float2(qc.x, qc.y), a, __ffma2_rn(make_float2(qe.x, qe.y), b, sc45));
+            sc67 = __ffma2_rn(make_float2(qc.z, qc.w), a, __ffma2_rn(make_float2(qe.z, qe.w), b, sc67));
+          }
+        }
+      }
+      const float sc[D_MAX_QPK] = {sc01.x, sc01.y, sc23.x, sc23.y, sc45.x, sc45.y, sc67.x, sc67.y};
+      // combine the partial scores of the four dim quarters through shared memory (double-buffered by accumulator)
+      if (prt > 0) {
+        float* pt = part + (((prt - 1) * 2 + acc) * DBM + row) * D_MAX_QPK;
+        *reinterpret_cast<float4*>(pt) = make_float4(sc[0], sc[1], sc[2], sc[3]);
+        if (P.qpk > 4) *reinterpret_cast<float4*>(pt + 4) = make_float4(sc[4], sc[5], sc[6], sc[7]);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * P_EPI_WARPS) : "memory");   // epilogue warps only
+      if (prt == 0 && tok_ok) {
+        float tot[D_MAX_QPK];
+#pragma unroll
+        for (int g = 0; g < D_MAX_QPK; ++g) tot[g] = sc[g];
+#pragma unroll
+        for (int o = 0; o < P_PARTS - 1; ++o) {
+          const float* pt = part + ((o * 2 + acc) * DBM + row) * D_MAX_QPK;
+          const float4 lo4 = *reinterpret_cast<const float4*>(pt);
+          tot[0] += lo4.x, tot[1] += lo4.y, tot[2] += lo4.z, tot[3] += lo4.w;
+          if (P.qpk > 4) {
+            const float4 hi4 = *reinterpret_cast<const float4*>(pt + 4);
+            tot[4] += hi4.x, tot[5] += hi4.y, tot[6] += hi4.z, tot[7] += hi4.w;
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < D_MAX_QPK; ++g)
+          if (g < P.qpk) P.scores[static_cast<long long>(h * P.qpk + g) * P.ld_scores + tok] = tot[g] * P.scale;
+      }
+      acc ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * D < 32 ? 32 : 2 * D);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2, head_dim 128, even number of kv heads): the two CTAs of a cluster own two
+// ADJACENT kv heads; each keeps ITS head's slice of the right factor resident (D x r_k, <= 128 KiB) and streams
+// ITS OWN 128-token tile of A_k, and one tcgen05.mma of M = 256, N = 256 multiplies both token tiles with both
+// heads.  Every A_k tile that reaches an SM is therefore used for two heads: the L2 -> SM traffic of the
+// single-CTA kernel (one A tile per (tile, head), 556 MB per layer at config 2, the measured bound: the kernel ran
+// at the same speed with the MMAs or the epilogue arithmetic removed) is halved, and each MMA reads 8 KiB of
+// shared memory per 128 tensor cycles instead of per 64.
+//   TMEM: 2 accumulators x 256 columns (head 0 | head 1) per CTA, rows = the CTA's own 128 tokens.
+//   Barriers: both CTAs' TMA loads complete on the leader's full barrier; the leader's commits are multicast to
+//   both CTAs' empty / accumulator-full barriers; both CTAs' epilogue warps arrive on the leader's
+//   accumulator-empty barrier.
+// ---------------------------------------------------------------------------------------------
+constexpr int Q_D = 128;
+constexpr int Q_STAGES = 4;
+constexpr int Q_EPI_WARPS = 16;
+constexpr int Q_PARTS = Q_EPI_WARPS / 4;
+constexpr int Q_THREADS = 64 + 32 * Q_EPI_WARPS;
+constexpr int Q_TMEM_COLS = 512;
+constexpr size_t Q_SMEM_BYTES = PB_MAX_BYTES + Q_STAGES * D_A_BYTES + 1024 + 256 + 2 * Q_D * D_MAX_QPK * sizeof(float) +
+                                (Q_PARTS - 1) * 2 * DBM * D_MAX_QPK * sizeof(float);
+
+__global__ void __launch_bounds__(Q_THREADS, 1) decode_scores_pair_kernel(const __grid_constant__ ScoreParams P) {
+  constexpr int D = Q_D;
+  constexpr int B_KB_BYTES = D * DBK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + PB_MAX_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + Q_STAGES * D_A_BYTES);
+  uint64_t* empty_bar = full_bar + Q_STAGES;
+  uint64_t* tfull_bar = empty_bar + Q_STAGES;    // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;          // [2]  (the leader's copy is the one in use)
+  uint64_t* b_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_bar + 1);
+  float* q_s = reinterpret_cast<float*>(sA + Q_STAGES * D_A_BYTES + 256);   // [2 heads][D][8], dim-major
+  float* part = q_s + 2 * D * D_MAX_QPK;                                    // [3 parts][2 heads][128 tokens][8]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();       // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+  const int nhp = P.H >> 1;                      // head pairs
+  const int hp = pair % nhp;
+  const int slot = pair / nhp;
+  const int nslots = (npairs - hp + nhp - 1) / nhp;   // CTA pairs that share this head pair
+  const int ntp = (P.S + 2 * DBM - 1) / (2 * DBM);    // 256-token tile pairs
+  const int h_mine = 2 * hp + static_cast<int>(rank); // the head whose right-factor slice this CTA holds
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < Q_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 2 * Q_EPI_WARPS);   // one arrive per epilogue warp of BOTH CTAs
+    }
+    mbar_init(b_bar, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&P.a_map);
+    tma_prefetch_desc(&P.b_head_map);
+  }
+  if (warp >= 2) {
+    for (int e = threadIdx.x - 64; e < 2 * D * D_MAX_QPK; e += 32 * Q_EPI_WARPS) {
+      const int hh = e / (D * D_MAX_QPK), r = e - hh * D * D_MAX_QPK;
+      const int d = r / D_MAX_QPK, g = r - d * D_MAX_QPK;
+      q_s[e] = g < P.qpk ? __bfloat162float(P.q[static_cast<long long>((2 * hp + hh) * P.qpk + g) * D + d]) : 0.f;
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();                               // barrier initialisation visible to the peer before any remote use
+  if (warp == 1) tmem_alloc_pair(tmem_slot, Q_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // this CTA's head slice; the bytes of both CTAs are counted on the leader's barrier
+      if (rank == 0) mbar_expect_tx(b_bar, 2u * static_cast<uint32_t>(P.nkb) * B_KB_BYTES);
+      for (int kb = 0; kb < P.nkb; ++kb) tma_load_2d_pair(sB + kb * B_KB_BYTES, &P.b_head_map, b_bar, kb * DBK, h_mine * D);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tp = slot; tp < ntp; tp += nslots) {
+        const int m0 = tp * 2 * DBM + static_cast<int>(rank) * DBM;
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2u * D_A_BYTES);
+          tma_load_2d_pair(sA + s * D_A_BYTES, &P.a_map, &full_bar[s], kb * DBK, m0);
+          if (++s == Q_STAGES) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * DBM, 2 * D, 0, 0);
+      mbar_wait(b_bar, 0);
+      int s = 0, acc = 0;
+      uint32_t ph = 0, ph_acc0 = 0u, ph_acc1 = 0u;
+      const uint32_t b_base = smem_u32(sB);
+      for (int tp = slot; tp < ntp; tp += nslots) {
+        const uint32_t aph = acc ? ph_acc1 : ph_acc0;
+        mbar_wait(&tempty_bar[acc], aph ^ 1u);     // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * 2 * D);
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + s * D_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < DBK / 16; ++k)
+            umma_bf16_ss_pair(d_addr, umma_desc_sw128(a_base + k * 32, 16, 1024),
+                              umma_desc_sw128(b_base + kb * B_KB_BYTES + k * 32, 16, 1024), idesc,
+                              (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_pair(&empty_bar[s]);
+          if (++s == Q_STAGES) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+        umma_commit_pair(&tfull_bar[acc]);
+        if (acc) ph_acc1 ^= 1u; else ph_acc0 ^= 1u;
+        acc ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): thread = one token of this CTA's tile x 16 rotation pairs, both heads in turn =====
+    constexpr int PP = D / 2 / Q_PARTS;   // 16
+    constexpr int CW = PP / 2;            // 8
+    const int ew = warp - 2;
+    const int qd = warp & 3;
+    const int prt = ew >> 2;
+    const int row = qd * 32 + lane;
+    const int d0 = prt * PP;
+    const bool rope = P.cos != nullptr;
+    int acc = 0;
+    uint32_t ph_acc0 = 0u, ph_acc1 = 0u;
+    uint32_t cs_next[CW], sn_next[CW];
+    auto fetch_cs = [&](int tp_idx) {
+      const int t = tp_idx * 2 * DBM + static_cast<int>(rank) * DBM + row;
+      if (rope && tp_idx < ntp && t < P.S) {
+        const uint4* cp = reinterpret_cast<const uint4*>(P.cos + static_cast<long long>(t) * P.ld_cs + d0);
+        const uint4* sp = reinterpret_cast<const uint4*>(P.sin + static_cast<long long>(t) * P.ld_cs + d0);
+#pragma unroll
+        for (int v = 0; v < CW / 4; ++v) {
+          const uint4 cv = __ldg(cp + v), sv = __ldg(sp + v);
+          cs_next[4 * v] = cv.x, cs_next[4 * v + 1] = cv.y, cs_next[4 * v + 2] = cv.z, cs_next[4 * v + 3] = cv.w;
+          sn_next[4 * v] = sv.x, sn_next[4 * v + 1] = sv.y, sn_next[4 * v + 2] = sv.z, sn_next[4 * v + 3] = sv.w;
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < CW; ++v) cs_next[v] = 0x3F803F80u, sn_next[v] = 0u;
+      }
+    };
+    fetch_cs(slot);
+    for (int tp = slot; tp < ntp; tp += nslots) {
+      const int tok = tp * 2 * DBM + static_cast<int>(rank) * DBM + row;
+      const bool tok_ok = tok < P.S;
+      uint32_t cs[CW], sn[CW];
+#pragma unroll
+      for (int v = 0; v < CW; ++v) cs[v] = cs_next[v], sn[v] = sn_next[v];
+      fetch_cs(tp + nslots);
+      mbar_wait(&tfull_bar[acc], acc ? ph_acc1 : ph_acc0);
+      if (acc) ph_acc1 ^= 1u; else ph_acc0 ^= 1u;
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + static_cast<uint32_t>(acc * 2 * D);
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t x1[PP], x2[PP];
+        __syncwarp();
+        tmem_ld_cols<PP>(lane_addr + static_cast<uint32_t>(hh * D + d0), x1);
+        tmem_ld_cols<PP>(lane_addr + static_cast<uint32_t>(hh * D + D / 2 + d0), x2);
+        tmem_ld_wait();
+        if (hh == 1) {
+          // both heads' columns of this thread are in registers: hand the accumulator back to the leader's MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+        }
+        const float* qh = q_s + hh * D * D_MAX_QPK;
+        float2 sc01 = make_float2(0.f, 0.f), sc23 = sc01, sc45 = sc01, sc67 = sc01;
+  #pragma unroll
+        for (int jp = 0; jp < PP / 2; ++jp) {
           const __nv_bfloat162 k1 = __floats2bfloat162_rn(__uint_as_float(x1[2 * jp]), __uint_as_float(x1[2 * jp + 1]));
           const __nv_bfloat162 k2 = __floats2bfloat162_rn(__uint_as_float(x2[2 * jp]), __uint_as_float(x2[2 * jp + 1]));
           __nv_bfloat162 o1 = k1, o2 = k2;
@@ -374,48 +642,58 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
           const float o2v[2] = {__low2float(o2), __high2float(o2)};
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const int d1 = c * 32 + 2 * jp + u, d2 = d1 + D / 2;
-            const float4 qa = *reinterpret_cast<const float4*>(q_s + d1 * D_MAX_QPK);
-            const float4 qb = *reinterpret_cast<const float4*>(q_s + d2 * D_MAX_QPK);
-            sc[0] = fmaf(qa.x, o1v[u], fmaf(qb.x, o2v[u], sc[0]));
-            sc[1] = fmaf(qa.y, o1v[u], fmaf(qb.y, o2v[u], sc[1]));
-            sc[2] = fmaf(qa.z, o1v[u], fmaf(qb.z, o2v[u], sc[2]));
-            sc[3] = fmaf(qa.w, o1v[u], fmaf(qb.w, o2v[u], sc[3]));
+            const int d1 = d0 + 2 * jp + u, d2 = d1 + D / 2;
+            const float2 a = make_float2(o1v[u], o1v[u]), b = make_float2(o2v[u], o2v[u]);
+            const float4 qa = *reinterpret_cast<const float4*>(qh + d1 * D_MAX_QPK);
+            const float4 qb = *reinterpret_cast<const float4*>(qh + d2 * D_MAX_QPK);
+            sc01 = __ffma2_rn(make_float2(qa.x, qa.y), a, __ffma2_rn(make_float2(qb.x, qb.y), b, sc01));
+            sc23 = __ffma2_rn(make_float2(qa.z, qa.w), a, __ffma2_rn(make_float2(qb.z, qb.w), b, sc23));
             if (P.qpk > 4) {
-              const float4 qc = *reinterpret_cast<const float4*>(q_s + d1 * D_MAX_QPK + 4);
-              const float4 qe = *reinterpret_cast<const float4*>(q_s + d2 * D_MAX_QPK + 4);
-              sc[4] = fmaf(qc.x, o1v[u], fmaf(qe.x, o2v[u], sc[4]));
-              sc[5] = fmaf(qc.y, o1v[u], fmaf(qe.y, o2v[u], sc[5]));
-              sc[6] = fmaf(qc.z, o1v[u], fmaf(qe.z, o2v[u], sc[6]));
-              sc[7] = fmaf(qc.w, o1v[u], fmaf(qe.w, o2v[u], sc[7]));
+              const float4 qc = *reinterpret_cast<const float4*>(qh + d1 * D_MAX_QPK + 4);
+              const float4 qe = *reinterpret_cast<const float4*>(qh + d2 * D_MAX_QPK + 4);
+              sc45 = __ffma2_rn(make_float2(qc.x, qc.y), a, __ffma2_rn(make_float2(qe.x, qe.y), b, sc45));
+              sc67 = __ffma2_rn(make_float2(qc.z, qc.w), a, __ffma2_rn(make_float2(qe.z, qe.w), b, sc67));
             }
           }
         }
-      }
-      // accumulator fully read by this warp: hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      // combine the two halves' partial scores through shared memory (double-buffered by accumulator)
-      float* pt = part + (acc * DBM + row) * D_MAX_QPK;
-      if (half == 1) {
+        const float sc[D_MAX_QPK] = {sc01.x, sc01.y, sc23.x, sc23.y, sc45.x, sc45.y, sc67.x, sc67.y};
+        // combine the four dim quarters through shared memory; the buffer of head hh is reused every tile: the
+        // barrier of the other head's round separates its readers from the next writers
+        if (prt > 0) {
+          float* pt = part + (((prt - 1) * 2 + hh) * DBM + row) * D_MAX_QPK;
+          *reinterpret_cast<float4*>(pt) = make_float4(sc[0], sc[1], sc[2], sc[3]);
+          if (P.qpk > 4) *reinterpret_cast<float4*>(pt + 4) = make_float4(sc[4], sc[5], sc[6], sc[7]);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * Q_EPI_WARPS) : "memory");
+        if (prt == 0 && tok_ok) {
+          float tot[D_MAX_QPK];
 #pragma unroll
-        for (int g = 0; g < D_MAX_QPK; ++g) pt[g] = sc[g];
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * P_EPI_WARPS) : "memory");   // epilogue warps only
-      if (half == 0 && tok_ok) {
+          for (int g = 0; g < D_MAX_QPK; ++g) tot[g] = sc[g];
 #pragma unroll
-        for (int g = 0; g < D_MAX_QPK; ++g)
-          if (g < P.qpk) P.scores[static_cast<long long>(h * P.qpk + g) * P.ld_scores + tok] = (sc[g] + pt[g]) * P.scale;
+          for (int o = 0; o < Q_PARTS - 1; ++o) {
+            const float* pt = part + ((o * 2 + hh) * DBM + row) * D_MAX_QPK;
+            const float4 lo4 = *reinterpret_cast<const float4*>(pt);
+            tot[0] += lo4.x, tot[1] += lo4.y, tot[2] += lo4.z, tot[3] += lo4.w;
+            if (P.qpk > 4) {
+              const float4 hi4 = *reinterpret_cast<const float4*>(pt + 4);
+              tot[4] += hi4.x, tot[5] += hi4.y, tot[6] += hi4.z, tot[7] += hi4.w;
+            }
+          }
+          const int h = 2 * hp + hh;
+#pragma unroll
+          for (int g = 0; g < D_MAX_QPK; ++g)
+            if (g < P.qpk) P.scores[static_cast<long long>(h * P.qpk + g) * P.ld_scores + tok] = tot[g] * P.scale;
+        }
       }
       acc ^= 1;
     }
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer may still signal its barriers / read its smem
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * D < 32 ? 32 : 2 * D);
+    tmem_dealloc_pair(tmem_base, Q_TMEM_COLS);
   }
 }
 
@@ -660,7 +938,34 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
     const int ntiles = (S + DBM - 1) / DBM;
     int pgrid = sms < ntiles * H ? sms : ntiles * H;
     if (pgrid < H) pgrid = H;   // every head needs at least one CTA
-    if (D == 128)
+    static const bool pair_off = getenv("XKV_DECODE_PAIR") == nullptr;   // opt-in: see the kernel's header comment
+    const int ntp = (S + 2 * DBM - 1) / (2 * DBM);
+    if (D == 128 && H % 2 == 0 && !pair_off && sms >= H) {
+      // CTA pairs: one cluster of 2 per (head pair, slot)
+      static bool qconf = false;
+      if (!qconf) {
+        XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(Q_SMEM_BYTES)));
+        qconf = true;
+      }
+      int npairs = sms / 2;
+      if (npairs > ntp * (H / 2)) npairs = ntp * (H / 2);
+      if (npairs < H / 2) npairs = H / 2;
+      cudaLaunchConfig_t cfg;
+      std::memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(2 * npairs, 1, 1);
+      cfg.blockDim = dim3(Q_THREADS, 1, 1);
+      cfg.dynamicSmemBytes = Q_SMEM_BYTES;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      XKV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_scores_pair_kernel, sp));
+    } else if (D == 128)
       decode_scores_persistent_kernel<128><<<pgrid, P_THREADS, P_SMEM_BYTES, st>>>(sp);
     else
       decode_scores_persistent_kernel<64><<<pgrid, P_THREADS, P_SMEM_BYTES, st>>>(sp);
