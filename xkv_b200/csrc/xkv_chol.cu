@@ -35,7 +35,7 @@ constexpr int CB = 64;             // block size
 constexpr int CBK = CB + 4;        // shared-memory row stride of a k-major tile (rows stay 16-byte aligned)
 constexpr int CTILE = CB * CBK;
 constexpr int CH_THREADS = 256;
-constexpr int CH_SMEM_FLOATS = 3 * CTILE + 2 * 128 + 2 * 64;
+constexpr int CH_SMEM_FLOATS = 5 * CTILE + 2 * 128 + 2 * 64;
 
 struct CholFusedParams {
   float* S[XKV_MAX_BATCH];
@@ -150,82 +150,209 @@ __device__ __forceinline__ void diag_factor(const float* D, long long ld, float 
   }
 }
 
+// ---- software pipeline over 64x64x64 block products ------------------------------------------------------
+// A CTA's share of a phase is a list of products (A tile, B tile) -> output tile.  The operand tiles of product
+// t+1 are in flight (cp.async, L2 -> shared, two buffers) while product t runs on the FFMA pipe: measured on the
+// first version, a tile product cost ~4 us of which ~1.4 us was arithmetic, the rest exposed L2 round trips.
+struct Prod {
+  const float* a;   // row-major global tile, used as Ak[kk][r]
+  const float* b;   // row-major global tile, used as Bk[kk][c]; nullptr: the resident Xt tile
+  int oi, oj;       // output block
+  bool first, last; // first / last product of its output tile
+};
+__device__ __forceinline__ void prefetch_tile(float* dst, const float* src, long long ld) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int e = threadIdx.x + it * CH_THREADS;
+    const int row = e >> 4, c4 = (e & 15) * 4;
+    const uint32_t d = smem_u32(dst + row * CBK + c4);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + static_cast<long long>(row) * ld + c4)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+enum { EPI_PANEL = 0, EPI_UPDATE = 1, EPI_STORE = 2, EPI_INV = 3 };
+
+// Gen: bool next(Prod&).  Buffers: bufA[2], bufB[2] (CTILE floats each), Xt resident.
+template <int EPI, class Gen>
+__device__ __forceinline__ void run_products(Gen& gen, float* bufs, const float* Xt, float* S, float* Li, long long ld) {
+  const int tid = threadIdx.x, tr = (tid >> 4) * 4, tc = (tid & 15) * 4;
+  auto blk = [&](float* base, int bi, int bj) -> float* {
+    return base + static_cast<long long>(bi) * CB * ld + static_cast<long long>(bj) * CB;
+  };
+  Prod cur, nxt;
+  bool has = gen.next(cur);
+  if (!has) return;
+  int st = 0;
+  prefetch_tile(bufs + 0 * CTILE, cur.a, ld);
+  if (cur.b) prefetch_tile(bufs + 2 * CTILE, cur.b, ld);
+  cp_async_commit();
+  float acc[4][4];
+  while (has) {
+    const bool has_n = gen.next(nxt);
+    if (has_n) {
+      prefetch_tile(bufs + (st ^ 1) * CTILE, nxt.a, ld);
+      if (nxt.b) prefetch_tile(bufs + (2 + (st ^ 1)) * CTILE, nxt.b, ld);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (cur.first) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    }
+    float4 cin[4];
+    if (EPI == EPI_UPDATE) {   // the output tile is read-modify-write: fetch it under the arithmetic
+      const float* g = blk(S, cur.oi, cur.oj);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) cin[a] = __ldcg(reinterpret_cast<const float4*>(g + static_cast<long long>(tr + a) * ld + tc));
+    }
+    tile_mma(acc, bufs + st * CTILE, cur.b ? bufs + (2 + st) * CTILE : Xt);
+    if (cur.last) {
+      if (EPI == EPI_PANEL) {          // S(oi,oj)[c'][r] = acc[r][c']  (transposed store of L[i,k])
+        float* g = blk(S, cur.oi, cur.oj);
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          *reinterpret_cast<float4*>(g + static_cast<long long>(tc + b) * ld + tr) =
+              make_float4(acc[0][b], acc[1][b], acc[2][b], acc[3][b]);
+      } else if (EPI == EPI_UPDATE) {  // S(oi,oj) -= acc
+        float* g = blk(S, cur.oi, cur.oj);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          *reinterpret_cast<float4*>(g + static_cast<long long>(tr + a) * ld + tc) =
+              make_float4(cin[a].x - acc[a][0], cin[a].y - acc[a][1], cin[a].z - acc[a][2], cin[a].w - acc[a][3]);
+      } else if (EPI == EPI_STORE) {   // S(oi,oj) = acc
+        float* g = blk(S, cur.oi, cur.oj);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          *reinterpret_cast<float4*>(g + static_cast<long long>(tr + a) * ld + tc) =
+              make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+      } else {                         // Linv(oi,oj) = -acc, Linv(oj,oi) = -acc^T
+        float* g = blk(Li, cur.oi, cur.oj);
+        float* gt = blk(Li, cur.oj, cur.oi);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+          *reinterpret_cast<float4*>(g + static_cast<long long>(tr + a) * ld + tc) =
+              make_float4(-acc[a][0], -acc[a][1], -acc[a][2], -acc[a][3]);
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          *reinterpret_cast<float4*>(gt + static_cast<long long>(tc + b) * ld + tr) =
+              make_float4(-acc[0][b], -acc[1][b], -acc[2][b], -acc[3][b]);
+      }
+    }
+    __syncthreads();   // everybody is done with buffer `st` before the prefetch of the next-but-one product refills it
+    cur = nxt;
+    has = has_n;
+    st ^= 1;
+  }
+}
+
 __global__ void __launch_bounds__(CH_THREADS, 1) chol_cluster_kernel(const __grid_constant__ CholFusedParams p) {
   extern __shared__ __align__(16) float chol_sm[];
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = static_cast<int>(cluster.num_blocks());
   const int c = static_cast<int>(cluster.block_rank());
-  float* Ak = chol_sm;
-  float* Bk = Ak + CTILE;
-  float* Xt = Bk + CTILE;
+  float* bufs = chol_sm;               // [A0 | A1 | B0 | B1]
+  float* Xt = bufs + 4 * CTILE;
   float* rowj = Xt + CTILE;
   float* lraw = rowj + 2 * 128;
   float* S = p.S[blockIdx.y];
   float* Li = p.Linv[blockIdx.y];
   const long long ld = p.ld;
   const int nblk = p.nblk;
-  const int tid = threadIdx.x, tr = (tid >> 4) * 4, tc = (tid & 15) * 4;
+  const int tid = threadIdx.x;
   auto blk = [&](float* base, int bi, int bj) -> float* {
     return base + static_cast<long long>(bi) * CB * ld + static_cast<long long>(bj) * CB;
   };
+  auto publish_xt = [&](int k) {   // S(k,k) <- X_k^T: the k-major operand of the inverse products
+    float* g = blk(S, k, k);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int e = tid + it * CH_THREADS;
+      const int row = e >> 4, c4 = (e & 15) * 4;
+      *reinterpret_cast<float4*>(g + static_cast<long long>(row) * ld + c4) =
+          *reinterpret_cast<const float4*>(Xt + row * CBK + c4);
+    }
+  };
 
   // ---------------- phase F ----------------
+  // Look-ahead: the diagonal factorisation of step k+1 (a serial 64-column sweep, ~8 us) is taken off the
+  // critical path.  Its owner updates tile (k+1, k+1) first, factors it and publishes X_{k+1}^T in S(k+1, k+1)
+  // while the other CTAs work through the rest of the trailing update; after the barrier everybody just loads it.
+  constexpr int kSkipRounds = 3;   // update rounds the look-ahead owner sits out (~ T_diag / T_tile)
   for (int k = 0; k < nblk; ++k) {
-    const bool owner = (c == k % CL);
-    diag_factor(blk(S, k, k), ld, p.shift, p.pivot_floor, Xt, rowj, lraw, owner ? blk(Li, k, k) : nullptr);
+    if (k == 0) {
+      diag_factor(blk(S, 0, 0), ld, p.shift, p.pivot_floor, Xt, rowj, lraw, c == 0 ? blk(Li, 0, 0) : nullptr);
+    } else {
+      load_tile(Xt, blk(S, k, k), ld);   // X_k^T, published by the look-ahead owner during step k-1
+    }
     __syncthreads();
-    for (int i = k + 1 + c; i < nblk; i += CL) {
-      float* g = blk(S, k, i);
-      load_tile(Ak, g, ld);
-      __syncthreads();
-      float acc[4][4] = {};
-      tile_mma(acc, Ak, Xt);   // P[r][c'] = sum_kk S[i,k][r][kk] X[c'][kk]
-#pragma unroll
-      for (int b = 0; b < 4; ++b)   // stored transposed: S(k,i)[c'][r] = L[i,k][r][c']
-        *reinterpret_cast<float4*>(g + static_cast<long long>(tc + b) * ld + tr) =
-            make_float4(acc[0][b], acc[1][b], acc[2][b], acc[3][b]);
-      __syncthreads();
+    {
+      // panel: L[i,k] = S[i,k] X_k^T, stored transposed over S(k,i)
+      struct PanelGen {
+        float* S; long long ld; int k, i, nblk, CL;
+        __device__ bool next(Prod& q) {
+          if (i >= nblk) return false;
+          q.a = S + static_cast<long long>(k) * CB * ld + static_cast<long long>(i) * CB;
+          q.b = nullptr;
+          q.oi = k; q.oj = i; q.first = q.last = true;
+          i += CL;
+          return true;
+        }
+      } gen{S, ld, k, k + 1 + c, nblk, CL};
+      run_products<EPI_PANEL>(gen, bufs, Xt, S, Li, ld);
     }
     cluster.sync();
-    if (owner) {
-      // X_k^T, the k-major operand of the inverse products, replaces the (now dead) diagonal block of S.  Written
-      // only after the barrier: before it other CTAs may still be loading S(k,k) for their own factorisation.
-      float* g = blk(S, k, k);
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int e = tid + it * CH_THREADS;
-        const int row = e >> 4, c4 = (e & 15) * 4;
-        *reinterpret_cast<float4*>(g + static_cast<long long>(row) * ld + c4) =
-            *reinterpret_cast<const float4*>(Xt + row * CBK + c4);
-      }
-    }
+    if (k == 0 && c == 0) publish_xt(0);   // only after the barrier: peers were still reading S(0,0) before it
     const int nt = nblk - k - 1;
-    const int ntiles = nt * (nt + 1) / 2;
-    int ii = 0, base = 0;   // tile e = ii (ii + 1) / 2 + jj,  0 <= jj <= ii < nt
-    for (int e = (c + CL - (k % CL)) % CL; e < ntiles; e += CL) {
-      while (e >= base + ii + 1) {
-        base += ii + 1;
-        ++ii;
+    const int ntiles = nt * (nt + 1) / 2;     // tile e = ii (ii + 1) / 2 + jj, 0 <= jj <= ii < nt; e = 0 is (k+1, k+1)
+    const int own = (k + 1) % CL;             // look-ahead owner of step k+1
+    struct UpdateGen {
+      float* S; long long ld; int k, e, e_end, early, others, CL, rel;
+      __device__ bool next(Prod& q) {
+        for (; e < e_end; ++e) {
+          if (e > 0) {
+            const int t = e - 1;
+            const int who = t < early ? t % others : (t - early) % CL;
+            if (who != rel) continue;
+          }
+          int ii = static_cast<int>((sqrtf(8.f * static_cast<float>(e) + 1.f) - 1.f) * 0.5f);
+          while (ii * (ii + 1) / 2 > e) --ii;
+          while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
+          const int jj = e - ii * (ii + 1) / 2;
+          const int i = k + 1 + ii, j = k + 1 + jj;
+          q.a = S + static_cast<long long>(k) * CB * ld + static_cast<long long>(j) * CB;
+          q.b = S + static_cast<long long>(k) * CB * ld + static_cast<long long>(i) * CB;
+          q.oi = j; q.oj = i; q.first = q.last = true;
+          ++e;
+          return true;
+        }
+        return false;
       }
-      const int jj = e - base;
-      const int i = k + 1 + ii, j = k + 1 + jj;
-      load_tile(Ak, blk(S, k, j), ld);
-      load_tile(Bk, blk(S, k, i), ld);
+    };
+    const int others = CL - 1;
+    const int early = others > 0 ? kSkipRounds * others : 0;
+    const int rel = (c - own - 1 + 2 * CL) % CL;   // 0 .. CL-2 for the others (ring order), CL-1 for the owner
+    if (ntiles > 0 && c == own) {
+      UpdateGen g0{S, ld, k, 0, 1, early, others > 0 ? others : 1, CL, rel};
+      run_products<EPI_UPDATE>(g0, bufs, Xt, S, Li, ld);
+      diag_factor(blk(S, k + 1, k + 1), ld, p.shift, p.pivot_floor, Xt, rowj, lraw, blk(Li, k + 1, k + 1));
       __syncthreads();
-      float acc[4][4] = {};
-      tile_mma(acc, Ak, Bk);   // (L[j,k] L[i,k]^T)[r][c']
-      float* g = blk(S, j, i);
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        float4* q = reinterpret_cast<float4*>(g + static_cast<long long>(tr + a) * ld + tc);
-        float4 v = __ldcg(q);
-        v.x -= acc[a][0];
-        v.y -= acc[a][1];
-        v.z -= acc[a][2];
-        v.w -= acc[a][3];
-        *q = v;
-      }
+      publish_xt(k + 1);
       __syncthreads();
+    }
+    {
+      UpdateGen g1{S, ld, k, 1, ntiles, early, others > 0 ? others : 1, CL, rel};
+      run_products<EPI_UPDATE>(g1, bufs, Xt, S, Li, ld);
     }
     cluster.sync();
   }
@@ -234,47 +361,51 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chol_cluster_kernel(const __gri
   for (int s = 1; s < nblk; s <<= 1) {
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-      int cnt = 0;
-      for (int i = 0; i < nblk; ++i) {
-        const int a = (i / (2 * s)) * 2 * s;       // pair containing row i
-        if (i < a + s) continue;                   // i must lie in the C half
-        for (int j = a; j < a + s; ++j, ++cnt) {
-          if ((cnt + i) % CL != c) continue;
-          float acc[4][4] = {};
-          const int t0 = pass == 0 ? j : a + s;
-          const int t1 = pass == 0 ? a + s : i + 1;
-          for (int t = t0; t < t1; ++t) {
-            if (pass == 0) {
-              load_tile(Ak, blk(S, t, i), ld);                          // L[i,t]^T
-              load_tile(Bk, blk(Li, t, j), ld);                         // Linv[t,j]  (t == j: X_j, zero upper)
-            } else {
-              load_tile(Ak, t < i ? blk(Li, t, i) : blk(S, i, i), ld);  // Linv[i,t]^T  (t == i: X_i^T)
-              load_tile(Bk, blk(S, t, j), ld);                          // T[t,j]
+      // pass 0: T(i,j) = sum_{t=j}^{a+s-1} L[i,t] Linv[t,j]      (staged at the lower block S(i,j))
+      // pass 1: Linv(i,j) = -sum_{t=a+s}^{i} Linv[i,t] T[t,j]
+      struct InvGen {
+        float* S; float* Li; long long ld; int nblk, s, pass, CL, c;
+        int i, j, t, cnt; bool open;
+        __device__ const float* at(const float* base, int bi, int bj) const {
+          return base + static_cast<long long>(bi) * CB * ld + static_cast<long long>(bj) * CB;
+        }
+        __device__ bool next(Prod& q) {
+          for (;;) {
+            if (i >= nblk) return false;
+            const int a = (i / (2 * s)) * 2 * s;
+            if (i < a + s) { ++i; j = -1; open = false; continue; }   // row i must lie in the C half of its pair
+            if (!open) {
+              // advance to the next tile (i, j) of this row that belongs to this CTA
+              j = (j < 0) ? a : j + 1;
+              bool found = false;
+              for (; j < a + s; ++j, ++cnt)
+                if ((cnt + i) % CL == c) { found = true; break; }
+              if (!found) { ++i; j = -1; continue; }
+              ++cnt;
+              t = pass == 0 ? j : a + s;
+              open = true;
             }
-            __syncthreads();
-            tile_mma(acc, Ak, Bk);
-            __syncthreads();
-          }
-          if (pass == 0) {
-            float* g = blk(S, i, j);
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-              *reinterpret_cast<float4*>(g + static_cast<long long>(tr + r) * ld + tc) =
-                  make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-          } else {
-            float* g = blk(Li, i, j);
-            float* gt = blk(Li, j, i);
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-              *reinterpret_cast<float4*>(g + static_cast<long long>(tr + r) * ld + tc) =
-                  make_float4(-acc[r][0], -acc[r][1], -acc[r][2], -acc[r][3]);
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-              *reinterpret_cast<float4*>(gt + static_cast<long long>(tc + b) * ld + tr) =
-                  make_float4(-acc[0][b], -acc[1][b], -acc[2][b], -acc[3][b]);
+            const int t1 = pass == 0 ? a + s : i + 1;
+            q.oi = i; q.oj = j;
+            q.first = (t == (pass == 0 ? j : a + s));
+            q.last = (t + 1 == t1);
+            if (pass == 0) {
+              q.a = at(S, t, i);                       // L[i,t]^T
+              q.b = at(Li, t, j);                      // Linv[t,j]  (t == j: X_j, zero upper)
+            } else {
+              q.a = t < i ? at(Li, t, i) : at(S, i, i);   // Linv[i,t]^T  (t == i: X_i^T)
+              q.b = at(S, t, j);                       // T[t,j]
+            }
+            ++t;
+            if (q.last) open = false;
+            return true;
           }
         }
-      }
+      } gen{S, Li, ld, nblk, s, pass, CL, c, 0, -1, 0, 0, false};
+      if (pass == 0)
+        run_products<EPI_STORE>(gen, bufs, Xt, S, Li, ld);
+      else
+        run_products<EPI_INV>(gen, bufs, Xt, S, Li, ld);
       cluster.sync();
     }
   }

@@ -194,7 +194,7 @@ extern "C" void xkv_factorize_default_options(xkv_factorize_options* o) {
   o->passes = 2;
   o->final_passes = 2;
   o->window = 128;
-  o->jacobi_sweeps = 6;
+  o->jacobi_sweeps = 3;
   o->rayleigh_ritz = 1;
   o->want_sigma = 1;
   o->gram_split_k = 1;
