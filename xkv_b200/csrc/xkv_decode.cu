@@ -223,7 +223,6 @@ constexpr size_t P_SMEM_BYTES = PB_MAX_BYTES + PA_STAGES * D_A_BYTES + 1024 + 25
 
 template <int D>
 __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(const __grid_constant__ ScoreParams P) {
-  constexpr int NCH = D / 32;
   constexpr int B_KB_BYTES = D * DBK * 2;  // one 64-wide K block of the head's right factor
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -766,21 +765,19 @@ __global__ void __launch_bounds__(256) softmax_exp_kernel(const float* __restric
   }
 }
 
-// U[e] = sum over the split-K slabs of (P A_v)[e]
+// U[e] = sum over the split-K slabs of (P A_v)[e]  (8 independent partial sums: the loop is a chain of L2 round trips)
 __global__ void __launch_bounds__(256) reduce_u_kernel(const float* __restrict__ slabs, int nslabs, long long slab_stride,
                                                        int total, float* __restrict__ U) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   int sl = 0;
-  for (; sl + 4 <= nslabs; sl += 4) {
-    a0 += slabs[(sl + 0) * slab_stride + e];
-    a1 += slabs[(sl + 1) * slab_stride + e];
-    a2 += slabs[(sl + 2) * slab_stride + e];
-    a3 += slabs[(sl + 3) * slab_stride + e];
+  for (; sl + 8 <= nslabs; sl += 8) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] += slabs[(sl + u) * slab_stride + e];
   }
-  for (; sl < nslabs; ++sl) a0 += slabs[sl * slab_stride + e];
-  U[e] = (a0 + a1) + (a2 + a3);
+  for (; sl < nslabs; ++sl) a[0] += slabs[sl * slab_stride + e];
+  U[e] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
 }
 
 // o[hq][d] = ( sum_j U[hq][j] * Bv[(h*D + d)][j]  +  sum_t p_tail[hq][t] * v_tail[h][t][d] ) / rowsum[hq]
@@ -838,6 +835,25 @@ __global__ void __launch_bounds__(256) rope_bf16_kernel(__nv_bfloat16* __restric
 }
 
 static inline size_t al(size_t x) { return (x + 1023) / 1024 * 1024; }
+// Split-K factor of U = P A_v: as many K slices as make tiles_n x split CTAs fill the SMs ONCE (a 64-way split of
+// 3 column tiles is 192 CTAs = 1.3 waves on 148 SMs: the second wave runs at a third of the machine).
+static inline int decode_split_k(int S, int rv) {
+  const int nkb = (S + 63) / 64;
+  const int tiles_n = (rv + 255) / 256;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      sms = 148;
+  }
+  int split = sms / (tiles_n < 1 ? 1 : tiles_n);
+  if (split > nkb) split = nkb;
+  if (split > 64) split = 64;
+  if (split < 1) split = 1;
+  const int per = (nkb + split - 1) / split;   // K blocks per slice, as the GEMM cuts them
+  return (nkb + per - 1) / per;                // drop slices that would be empty
+}
+
 static bool g_force_tiled_scores = false;  // test hook: exercise the tile-per-CTA scores kernel
 
 }  // namespace xkv
@@ -848,8 +864,8 @@ extern "C" size_t xkv_decode_workspace_bytes(int Hq, int S, int T, int rv) {
   const size_t L = static_cast<size_t>(S) + T;
   const size_t ldl = (L + 63) / 64 * 64;
   const int nkb = (S + 63) / 64;
-  int split = nkb < 64 ? nkb : 64;
-  if (split < 1) split = 1;
+  (void)nkb;
+  const int split = 64;   // upper bound of decode_split_k
   size_t b = 0;
   b += al(Hq * ldl * 4);            // scores
   b += al(128 * ldl * 2);           // probabilities (bf16), padded to a full 128-row tile
@@ -878,7 +894,8 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
   const size_t L = static_cast<size_t>(S) + T;
   const long long ldl = static_cast<long long>((L + 63) / 64 * 64);
   const int nkb_s = (S + 63) / 64;
-  const int split = nkb_s < 64 ? nkb_s : 64;
+  (void)nkb_s;
+  const int split = decode_split_k(S, rv);
   char* w = static_cast<char*>(workspace);
   float* scores = reinterpret_cast<float*>(w);
   w += al(Hq * ldl * 4);
