@@ -35,6 +35,7 @@ def _rel_err(x, xh):
         (4096, 4096, 768, 0.5),    # config 1, V rank
         (4096, 4096, 512, None),   # i.i.d. Gaussian: worst case for any low-rank method
         (1536, 2048, 512, 1.0),    # fewer tokens than columns
+        (2048, 8192, 1024, 0.5),   # config 4 columns (xKV-8 on 8 kv heads x 128): sketch width 1088, 17 Cholesky blocks
     ],
 )
 def test_reconstruction_matches_reference_svd(tokens, cols, rank, alpha):
@@ -59,6 +60,23 @@ def test_reconstruction_matches_reference_svd(tokens, cols, rank, alpha):
         rel = ((f.sigma_lead[:k] - s_ref[:k]).abs() / s_ref[:k]).max().item()
         print(f"   leading singular values: max rel dev {rel:.2e}")
         assert rel < 1e-3
+
+
+def test_steep_spectrum_at_high_rank_meets_the_bf16_storage_floor():
+    """Where the reference's own error drops below ~2 % (steep spectrum, high rank: config 4 columns at alpha = 1,
+    rank 1024) the 1 % criterion is tighter than what factors STORED in bf16 can deliver: rounding A and V adds
+    ~0.3 % of ||X|| in quadrature ("known floor"; the reference rounds the dense product once).
+    The algorithmic part must still be within 1 %: the excess over the reference is bounded by that floor."""
+    from xkv_b200 import factorize, synthetic
+
+    x = synthetic.group_matrix(2048, 8192, 1.0, seed=1234, device="cuda")
+    ref_hat, _ = _ref_fake_svd(x, 1024)
+    (f,) = factorize.factorize_batch([x], 1024)
+    torch.cuda.synchronize()
+    e_ref, e_ours = _rel_err(x, ref_hat), _rel_err(x, f.reconstruct())
+    print(f"steep/high-rank: err ref={e_ref:.6f} ours={e_ours:.6f} ratio={e_ours / e_ref:.5f}")
+    assert e_ref < 0.02
+    assert e_ours ** 2 <= (1.01 * e_ref) ** 2 + 3e-3 ** 2
 
 
 def test_batch_of_two_ranks_shapes_and_determinism():

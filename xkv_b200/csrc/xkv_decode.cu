@@ -209,13 +209,14 @@ __global__ void __launch_bounds__(D_THREADS, 2) decode_scores_kernel(const __gri
 // ---------------------------------------------------------------------------------------------
 // Persistent variant: one CTA per SM owns ONE kv head, keeps that head's slice of the right factor
 // (D x r_k bf16, <= 128 KiB) resident in shared memory for the whole launch and streams A_k token tiles
-// through a 4-stage TMA ring.  Two TMEM accumulators (2 x D columns) let the epilogue of tile i overlap the
-// MMAs of tile i+1.  Compared with the tile-per-CTA kernel above it never re-reads the right factor
+// through a 4-stage TMA ring.  Four TMEM accumulators (4 x D columns) let the MMAs run up to three tiles ahead of
+// the epilogue.  Compared with the tile-per-CTA kernel above it never re-reads the right factor
 // (L2 -> SM traffic per layer 786 MB -> 536 MB at config 2) and has no per-tile prologue.
 // ---------------------------------------------------------------------------------------------
 constexpr int PA_STAGES = 4;
 constexpr int P_EPI_WARPS = 16;                   // four warps per TMEM lane quarter: each takes a quarter of the dims
 constexpr int P_PARTS = P_EPI_WARPS / 4;
+constexpr int P_NACC = 4;                         // TMEM accumulators (4 x 128 columns = all of TMEM at head_dim 128)
 constexpr int P_THREADS = 64 + 32 * P_EPI_WARPS;  // TMA warp + MMA warp + epilogue warps
 constexpr int PB_MAX_BYTES = 128 * 1024;
 constexpr size_t P_SMEM_BYTES = PB_MAX_BYTES + PA_STAGES * D_A_BYTES + 1024 + 256 + 128 * D_MAX_QPK * sizeof(float) +
@@ -230,9 +231,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
   uint8_t* sA = smem + PB_MAX_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + PA_STAGES * D_A_BYTES);
   uint64_t* empty_bar = full_bar + PA_STAGES;
-  uint64_t* tfull_bar = empty_bar + PA_STAGES;   // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;          // [2]
-  uint64_t* b_bar = tempty_bar + 2;
+  uint64_t* tfull_bar = empty_bar + PA_STAGES;   // [P_NACC]
+  uint64_t* tempty_bar = tfull_bar + P_NACC;     // [P_NACC]
+  uint64_t* b_bar = tempty_bar + P_NACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_bar + 1);
   float* q_s = reinterpret_cast<float*>(sA + PA_STAGES * D_A_BYTES + 256);  // [D][8]: q heads of this kv head, dim-major
   float* part = q_s + 128 * D_MAX_QPK;                                      // [2][128 tokens][8] partial scores
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < P_NACC; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], P_EPI_WARPS);   // one arrive per epilogue warp
     }
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
     tma_prefetch_desc(&P.a_map);
     tma_prefetch_desc(&P.b_head_map);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * D < 32 ? 32 : 2 * D);
+  if (warp == 1) tmem_alloc(tmem_slot, P_NACC * D);
   if (warp >= 2) {
     for (int e = threadIdx.x - 64; e < D * D_MAX_QPK; e += 32 * P_EPI_WARPS) {
       const int d = e / D_MAX_QPK, g = e - d * D_MAX_QPK;
@@ -292,11 +293,10 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
       constexpr uint32_t idesc = umma_idesc_bf16(DBM, D, 0, 0);
       mbar_wait(b_bar, 0);
       int s = 0, acc = 0;
-      uint32_t ph = 0, ph_acc0 = 0u, ph_acc1 = 0u;
+      uint32_t ph = 0, acc_ph = 0u;   // acc_ph: one phase bit per accumulator
       const uint32_t b_base = smem_u32(sB);
       for (int tile = slot; tile < ntiles; tile += nslots) {
-        const uint32_t aph = acc ? ph_acc1 : ph_acc0;
-        mbar_wait(&tempty_bar[acc], aph ^ 1u);   // epilogue has drained this accumulator
+        mbar_wait(&tempty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * D);
         for (int kb = 0; kb < P.nkb; ++kb) {
@@ -314,8 +314,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
           }
         }
         umma_commit(&tfull_bar[acc]);
-        if (acc) ph_acc1 ^= 1u; else ph_acc0 ^= 1u;
-        acc ^= 1;
+        acc_ph ^= 1u << acc;
+        acc = (acc + 1) % P_NACC;
       }
     }
   } else {
@@ -331,8 +331,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
     const int row = qd * 32 + lane;       // token row inside the tile
     const int d0 = prt * PP;              // first dim of the low half; partners are d0 + D/2 ...
     const bool rope = P.cos != nullptr;
-    int acc = 0;
-    uint32_t ph_acc0 = 0u, ph_acc1 = 0u;
+    int acc = 0, pb = 0;            // accumulator in use; parity of the partial-score buffer
+    uint32_t acc_ph = 0u;
     uint32_t cs_next[CW], sn_next[CW];
     auto fetch_cs = [&](int tile_idx) {
       const int t = tile_idx * DBM + row;
@@ -359,8 +359,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
 #pragma unroll
       for (int v = 0; v < CW; ++v) cs[v] = cs_next[v], sn[v] = sn_next[v];
       fetch_cs(tile + nslots);
-      mbar_wait(&tfull_bar[acc], acc ? ph_acc1 : ph_acc0);
-      if (acc) ph_acc1 ^= 1u; else ph_acc0 ^= 1u;
+      mbar_wait(&tfull_bar[acc], (acc_ph >> acc) & 1u);
+      acc_ph ^= 1u << acc;
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + static_cast<uint32_t>(acc * D);
       uint32_t x1[PP], x2[PP];
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
       const float sc[D_MAX_QPK] = {sc01.x, sc01.y, sc23.x, sc23.y, sc45.x, sc45.y, sc67.x, sc67.y};
       // combine the partial scores of the four dim quarters through shared memory (double-buffered by accumulator)
       if (prt > 0) {
-        float* pt = part + (((prt - 1) * 2 + acc) * DBM + row) * D_MAX_QPK;
+        float* pt = part + (((prt - 1) * 2 + pb) * DBM + row) * D_MAX_QPK;
         *reinterpret_cast<float4*>(pt) = make_float4(sc[0], sc[1], sc[2], sc[3]);
         if (P.qpk > 4) *reinterpret_cast<float4*>(pt + 4) = make_float4(sc[4], sc[5], sc[6], sc[7]);
       }
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
         for (int g = 0; g < D_MAX_QPK; ++g) tot[g] = sc[g];
 #pragma unroll
         for (int o = 0; o < P_PARTS - 1; ++o) {
-          const float* pt = part + ((o * 2 + acc) * DBM + row) * D_MAX_QPK;
+          const float* pt = part + ((o * 2 + pb) * DBM + row) * D_MAX_QPK;
           const float4 lo4 = *reinterpret_cast<const float4*>(pt);
           tot[0] += lo4.x, tot[1] += lo4.y, tot[2] += lo4.z, tot[3] += lo4.w;
           if (P.qpk > 4) {
@@ -429,14 +429,15 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
         for (int g = 0; g < D_MAX_QPK; ++g)
           if (g < P.qpk) P.scores[static_cast<long long>(h * P.qpk + g) * P.ld_scores + tok] = tot[g] * P.scale;
       }
-      acc ^= 1;
+      acc = (acc + 1) % P_NACC;
+      pb ^= 1;
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * D < 32 ? 32 : 2 * D);
+    tmem_dealloc(tmem_base, P_NACC * D);
   }
 }
 
