@@ -35,6 +35,7 @@ struct alignas(64) ScoreParams {
   CUtensorMap a_map;  // A_k  (S x r_k), box {64, 128}
   CUtensorMap b_map;  // Bk_l (H*D x r_k), box {64, 256}
   CUtensorMap b_head_map;  // Bk_l, box {64, D}: one kv head (persistent kernel)
+  CUtensorMap q_map;       // q (Hq x D), box {64, 16}: the q rows of one kv head (score MMA)
   const __nv_bfloat16* q;    // (Hq, D)
   const __nv_bfloat16* cos;  // (S, D) or null
   const __nv_bfloat16* sin;
@@ -438,6 +439,261 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, P_NACC * D);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent variant with the q contraction on the tensor core (head_dim 128, the default):
+// the epilogue of the kernel above spends three quarters of its instructions on the q . k^ dot products
+// (LDS of q, unpack to fp32, FFMA2, partial sums through shared memory), and the bisect in
+// profiles/r01_decode_scores_ncu_full.md shows that those instructions, not the MMAs, set the pace.  Here the
+// epilogue only rounds the reconstructed keys to bf16, rotates them (packed bf16, the reference's arithmetic) and
+// writes them back to TENSOR MEMORY as packed bf16 (tcgen05.st: lane = token, column c = dims 2c, 2c+1); a second
+// tcgen05.mma with the A operand in TMEM (TS form) contracts them with the head's q vectors (a 16 x 128 bf16 tile
+// in shared memory, loaded once by TMA):  scores[128 tokens x 16] = K^rot[128 x 128] * Q^T.  Both products are
+// exact bf16 x bf16 with fp32 accumulation, as before.  Warp roles: 0 TMA, 1 MMA (reconstruction), 2 MMA (scores),
+// 4..11 epilogue (two per TMEM lane quarter: dims [0,32)+[64,96) and [32,64)+[96,128)), 12..15 score read-out.
+//   TMEM: 2 x 128 columns reconstruction accumulators | 2 x 64 columns K^rot (bf16x2) | 2 x 32 columns scores.
+// ---------------------------------------------------------------------------------------------
+constexpr int R_STAGES = 5;
+constexpr int R_EPI_WARPS = 8;
+constexpr int R_OUT_WARPS = 4;
+constexpr int R_THREADS = 32 * (4 + R_EPI_WARPS + R_OUT_WARPS);
+constexpr int R_QROWS = 16;                 // q rows of the score MMA (N = 16 >= q heads per kv head)
+constexpr int R_Q_BYTES = 2 * R_QROWS * 128;  // two 64-dim chunks of 16 rows x 128 B
+constexpr int R_TMEM_COLS = 512;
+constexpr uint32_t R_COL_A2 = 256, R_COL_D2 = 384;
+constexpr size_t R_SMEM_BYTES = PB_MAX_BYTES + R_STAGES * D_A_BYTES + R_Q_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const __grid_constant__ ScoreParams P) {
+  constexpr int D = 128;
+  constexpr int B_KB_BYTES = D * DBK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + PB_MAX_BYTES;
+  uint8_t* sQ = sA + R_STAGES * D_A_BYTES;         // 1024-byte aligned (all sizes above are multiples of 1024)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sQ + R_Q_BYTES);
+  uint64_t* empty_bar = full_bar + R_STAGES;
+  uint64_t* tfull_bar = empty_bar + R_STAGES;      // [2] reconstruction accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2] ... drained by the epilogue warps
+  uint64_t* a2full_bar = tempty_bar + 2;           // [2] rotated keys written to TMEM
+  uint64_t* a2empty_bar = a2full_bar + 2;          // [2] ... consumed by the score MMAs
+  uint64_t* d2full_bar = a2empty_bar + 2;          // [2] scores ready in TMEM
+  uint64_t* d2empty_bar = d2full_bar + 2;          // [2] ... read out
+  uint64_t* b_bar = d2empty_bar + 2;
+  uint64_t* q_bar = b_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x % P.H;
+  const int slot = blockIdx.x / P.H;
+  const int nslots = (gridDim.x - h + P.H - 1) / P.H;
+  const int ntiles = (P.S + DBM - 1) / DBM;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < R_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], R_EPI_WARPS);
+      mbar_init(&a2full_bar[i], R_EPI_WARPS);
+      mbar_init(&a2empty_bar[i], 1);
+      mbar_init(&d2full_bar[i], 1);
+      mbar_init(&d2empty_bar[i], R_OUT_WARPS);
+    }
+    mbar_init(b_bar, 1);
+    mbar_init(q_bar, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&P.a_map);
+    tma_prefetch_desc(&P.b_head_map);
+    tma_prefetch_desc(&P.q_map);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, R_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_bar, R_Q_BYTES);
+      tma_load_2d(sQ, &P.q_map, q_bar, 0, h * P.qpk);            // dims 0..63 of q rows [h qpk, h qpk + 16)
+      tma_load_2d(sQ + R_Q_BYTES / 2, &P.q_map, q_bar, 64, h * P.qpk);
+      mbar_expect_tx(b_bar, static_cast<uint32_t>(P.nkb) * B_KB_BYTES);
+      for (int kb = 0; kb < P.nkb; ++kb) tma_load_2d(sB + kb * B_KB_BYTES, &P.b_head_map, b_bar, kb * DBK, h * D);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = slot; tile < ntiles; tile += nslots) {
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], D_A_BYTES);
+          tma_load_2d(sA + s * D_A_BYTES, &P.a_map, &full_bar[s], kb * DBK, tile * DBM);
+          if (++s == R_STAGES) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(DBM, D, 0, 0);
+      mbar_wait(b_bar, 0);
+      int s = 0, acc = 0;
+      uint32_t ph = 0, acc_ph = 0u;
+      const uint32_t b_base = smem_u32(sB);
+      for (int tile = slot; tile < ntiles; tile += nslots) {
+        mbar_wait(&tempty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * D);
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + s * D_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < DBK / 16; ++k)
+            umma_bf16_ss(d_addr, umma_desc_sw128(a_base + k * 32, 16, 1024),
+                         umma_desc_sw128(b_base + kb * B_KB_BYTES + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+          if (++s == R_STAGES) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc_ph ^= 1u << acc;
+        acc ^= 1;
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      // scores[128 x 16] = K^rot (TMEM, 64 packed columns) * Q^T (shared memory, K-major)
+      constexpr uint32_t idesc2 = umma_idesc_bf16(DBM, R_QROWS, 0, 0);
+      mbar_wait(q_bar, 0);
+      const uint32_t q_base = smem_u32(sQ);
+      int b = 0;
+      uint32_t bph = 0u;
+      for (int tile = slot; tile < ntiles; tile += nslots) {
+        mbar_wait(&a2full_bar[b], (bph >> b) & 1u);                 // rotated keys of this tile are in TMEM
+        mbar_wait(&d2empty_bar[b], ((bph >> b) & 1u) ^ 1u);         // score buffer read out
+        tc_fence_after();
+        const uint32_t a2 = tmem_base + R_COL_A2 + static_cast<uint32_t>(b * 64);
+        const uint32_t d2 = tmem_base + R_COL_D2 + static_cast<uint32_t>(b * 32);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          umma_bf16_ts(d2, a2 + static_cast<uint32_t>(k * 8),
+                       umma_desc_sw128(q_base + (k >> 2) * (R_Q_BYTES / 2) + (k & 3) * 32, 16, 1024), idesc2, k > 0 ? 1u : 0u);
+        umma_commit(&d2full_bar[b]);
+        umma_commit(&a2empty_bar[b]);
+        bph ^= 1u << b;
+        b ^= 1;
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + R_EPI_WARPS) {
+    // ===== epilogue: K^ row -> bf16 -> RoPE (packed bf16) -> back to TMEM as the A operand of the score MMA =====
+    const int qd = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int row = qd * 32 + lane;
+    const int d0 = half * 32;           // this thread rotates the pairs (d, d + 64), d in [d0, d0 + 32)
+    const bool rope = P.cos != nullptr;
+    int acc = 0;
+    uint32_t acc_ph = 0u;
+    for (int tile = slot; tile < ntiles; tile += nslots) {
+      const int tok = tile * DBM + row;
+      // cos/sin words of this token: issued before the wait on the accumulator, consumed after it
+      uint32_t cs[16], sn[16];
+      if (rope && tok < P.S) {
+        const uint4* cp = reinterpret_cast<const uint4*>(P.cos + static_cast<long long>(tok) * P.ld_cs + d0);
+        const uint4* sp = reinterpret_cast<const uint4*>(P.sin + static_cast<long long>(tok) * P.ld_cs + d0);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const uint4 cv = __ldg(cp + v), sv = __ldg(sp + v);
+          cs[4 * v] = cv.x, cs[4 * v + 1] = cv.y, cs[4 * v + 2] = cv.z, cs[4 * v + 3] = cv.w;
+          sn[4 * v] = sv.x, sn[4 * v + 1] = sv.y, sn[4 * v + 2] = sv.z, sn[4 * v + 3] = sv.w;
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < 16; ++v) cs[v] = 0x3F803F80u, sn[v] = 0u;   // cos = 1, sin = 0
+      }
+      mbar_wait(&tfull_bar[acc], (acc_ph >> acc) & 1u);
+      tc_fence_after();
+      const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
+      const uint32_t lane_addr = lane_base + static_cast<uint32_t>(acc * D);
+      uint32_t lo_w[16], hi_w[16];      // packed bf16x2: dims d0 + 2j, d0 + 2j + 1 and their partners + 64
+#pragma unroll
+      for (int sc = 0; sc < 2; ++sc) {
+        uint32_t x1[16], x2[16];
+        __syncwarp();
+        tmem_ld_32x16(lane_addr + static_cast<uint32_t>(d0 + sc * 16), x1);
+        tmem_ld_32x16(lane_addr + static_cast<uint32_t>(D / 2 + d0 + sc * 16), x2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jp = 0; jp < 8; ++jp) {
+          const __nv_bfloat162 k1 = __floats2bfloat162_rn(__uint_as_float(x1[2 * jp]), __uint_as_float(x1[2 * jp + 1]));
+          const __nv_bfloat162 k2 = __floats2bfloat162_rn(__uint_as_float(x2[2 * jp]), __uint_as_float(x2[2 * jp + 1]));
+          __nv_bfloat162 o1 = k1, o2 = k2;
+          if (rope) {
+            const __nv_bfloat162 cw = *reinterpret_cast<const __nv_bfloat162*>(&cs[sc * 8 + jp]);
+            const __nv_bfloat162 sw = *reinterpret_cast<const __nv_bfloat162*>(&sn[sc * 8 + jp]);
+            o1 = __hadd2(__hmul2(k1, cw), __hmul2(__hneg2(k2), sw));
+            o2 = __hadd2(__hmul2(k2, cw), __hmul2(k1, sw));
+          }
+          lo_w[sc * 8 + jp] = *reinterpret_cast<const uint32_t*>(&o1);
+          hi_w[sc * 8 + jp] = *reinterpret_cast<const uint32_t*>(&o2);
+        }
+      }
+      // the accumulator is in registers: hand it back to the reconstruction MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      // K^rot -> TMEM (column c = dims 2c, 2c+1): wait until the score MMAs of two tiles ago released the buffer
+      mbar_wait(&a2empty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t a2 = lane_base + R_COL_A2 + static_cast<uint32_t>(acc * 64);
+      __syncwarp();
+      tmem_st_32x16(a2 + static_cast<uint32_t>(d0 / 2), lo_w);
+      tmem_st_32x16(a2 + static_cast<uint32_t>(32 + d0 / 2), hi_w);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a2full_bar[acc]);
+      acc_ph ^= 1u << acc;
+      acc ^= 1;
+    }
+  } else if (warp >= 4 + R_EPI_WARPS) {
+    // ===== score read-out: one warp per TMEM lane quarter, thread = token =====
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    int b = 0;
+    uint32_t bph = 0u;
+    for (int tile = slot; tile < ntiles; tile += nslots) {
+      const int tok = tile * DBM + row;
+      mbar_wait(&d2full_bar[b], (bph >> b) & 1u);
+      tc_fence_after();
+      uint32_t v[8];
+      __syncwarp();
+      tmem_ld_32x8(tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + R_COL_D2 + static_cast<uint32_t>(b * 32), v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&d2empty_bar[b]);
+      if (tok < P.S) {
+#pragma unroll
+        for (int g = 0; g < D_MAX_QPK; ++g)
+          if (g < P.qpk) P.scores[static_cast<long long>(h * P.qpk + g) * P.ld_scores + tok] = __uint_as_float(v[g]) * P.scale;
+      }
+      bph ^= 1u << b;
+      b ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, R_TMEM_COLS);
   }
 }
 
@@ -917,6 +1173,11 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
   if (rc) return rc;
   rc = encode_tmap_2d_bf16(&sp.b_head_map, Vk_layer, rk, static_cast<uint64_t>(H) * D, ldv_k, DBK, D);
   if (rc) return rc;
+  const bool q_tma_ok = D == 128 && (reinterpret_cast<uintptr_t>(q) & 15) == 0;
+  if (q_tma_ok) {
+    rc = encode_tmap_2d_bf16(&sp.q_map, q, D, Hq, D, 64, R_QROWS);
+    if (rc) return rc;
+  }
   sp.q = static_cast<const __nv_bfloat16*>(q);
   sp.cos = static_cast<const __nv_bfloat16*>(cos);
   sp.sin = static_cast<const __nv_bfloat16*>(sin);
@@ -983,6 +1244,14 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       XKV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_scores_pair_kernel, sp));
+    } else if (D == 128 && q_tma_ok && getenv("XKV_DECODE_FFMA") == nullptr) {
+      static bool rconf = false;
+      if (!rconf) {
+        XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(R_SMEM_BYTES)));
+        rconf = true;
+      }
+      decode_scores_mma2_kernel<<<pgrid, R_THREADS, R_SMEM_BYTES, st>>>(sp);
     } else if (D == 128)
       decode_scores_persistent_kernel<128><<<pgrid, P_THREADS, P_SMEM_BYTES, st>>>(sp);
     else
