@@ -198,6 +198,9 @@ XKV_API int xkv_decode_attention(const void* q, int Hq, int H, int D, const void
 /* test hook: 1 forces the tile-per-CTA scores kernel (otherwise chosen only when one head's slice of the right
  * factor exceeds 128 KiB of shared memory), 0 restores the automatic choice */
 XKV_API void xkv_decode_force_tiled(int on);
+/* test hook: persistent scores kernel to use where several apply: 0 automatic (score MMA for head_dim 128),
+ * 1 FFMA epilogue, 2 score MMA (tcgen05.mma with the rotated keys in TMEM), 3 CTA pair (cta_group::2) */
+XKV_API void xkv_decode_set_variant(int variant);
 /* RoPE on materialised keys x (rows, H, D) bf16 in place, in the reference's bf16 arithmetic
  * (apply_rotary_pos_emb as called at cache:148,152): x*cos + rotate_half(x)*sin, cos/sin (rows, D). */
 XKV_API int xkv_rope_bf16(void* x, int64_t ld_row, int rows, int H, int D, const void* cos, const void* sin,

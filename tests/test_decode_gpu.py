@@ -60,17 +60,21 @@ def _case(S, H, D, qpk, rk, rv, T, layers_in_group, layer, rope, seed=0):
         (300, 3, 128, 1, 96, 160, 1, 2, 0, True),      # MHA (qpk 1), 3 heads: second n-tile half empty, rank not /64
     ],
 )
-@pytest.mark.parametrize("tiled", [False, True])
-def test_decode_attention_matches_oracle(S, H, D, qpk, rk, rv, T, G, layer, rope, tiled):
-    """tiled=False: persistent scores kernel (right-factor slice resident in shared memory);
-    tiled=True: the tile-per-CTA kernel used when that slice does not fit."""
+@pytest.mark.parametrize("variant", ["auto", "tiled", "ffma", "pair"])
+def test_decode_attention_matches_oracle(S, H, D, qpk, rk, rv, T, G, layer, rope, variant):
+    """auto: persistent scores kernel (right-factor slice resident in shared memory; for head_dim 128 the rotated
+    keys go back to TMEM and a second MMA contracts them with q); tiled: the tile-per-CTA kernel used when that slice
+    does not fit; ffma: persistent kernel with the FFMA epilogue (head_dim 64 path); pair: cta_group::2 CTA pairs."""
     from xkv_b200 import _lib
 
-    _lib.load().xkv_decode_force_tiled(int(tiled))
+    lib = _lib.load()
+    lib.xkv_decode_force_tiled(int(variant == "tiled"))
+    lib.xkv_decode_set_variant({"auto": 0, "tiled": 0, "ffma": 1, "pair": 3}[variant])
     try:
         _case(S, H, D, qpk, rk, rv, T, G, layer, rope)
     finally:
-        _lib.load().xkv_decode_force_tiled(0)
+        lib.xkv_decode_force_tiled(0)
+        lib.xkv_decode_set_variant(0)
 
 
 def test_decode_large_rank_falls_back_to_tiled_kernel():

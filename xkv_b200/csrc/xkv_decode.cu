@@ -36,6 +36,8 @@ struct alignas(64) ScoreParams {
   CUtensorMap b_map;  // Bk_l (H*D x r_k), box {64, 256}
   CUtensorMap b_head_map;  // Bk_l, box {64, D}: one kv head (persistent kernel)
   CUtensorMap q_map;       // q (Hq x D), box {64, 16}: the q rows of one kv head (score MMA)
+  CUtensorMap q8_map;      // q, box {64, 8}: one CTA's half of the score MMA's N rows (pair kernel)
+  CUtensorMap b_half_map;  // Bk_l, box {64, 64}: one CTA's half of a head's rows (pair kernel)
   const __nv_bfloat16* q;    // (Hq, D)
   const __nv_bfloat16* cos;  // (S, D) or null
   const __nv_bfloat16* sin;
@@ -698,53 +700,58 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// CTA-pair variant (cta_group::2, head_dim 128, even number of kv heads): the two CTAs of a cluster own two
-// ADJACENT kv heads; each keeps ITS head's slice of the right factor resident (D x r_k, <= 128 KiB) and streams
-// ITS OWN 128-token tile of A_k, and one tcgen05.mma of M = 256, N = 256 multiplies both token tiles with both
-// heads.  Every A_k tile that reaches an SM is therefore used for two heads: the L2 -> SM traffic of the
-// single-CTA kernel (one A tile per (tile, head), 556 MB per layer at config 2, the measured bound: the kernel ran
-// at the same speed with the MMAs or the epilogue arithmetic removed) is halved, and each MMA reads 8 KiB of
-// shared memory per 128 tensor cycles instead of per 64.
-//   TMEM: 2 accumulators x 256 columns (head 0 | head 1) per CTA, rows = the CTA's own 128 tokens.
-//   Barriers: both CTAs' TMA loads complete on the leader's full barrier; the leader's commits are multicast to
-//   both CTAs' empty / accumulator-full barriers; both CTAs' epilogue warps arrive on the leader's
-//   accumulator-empty barrier.
+// CTA-pair variant of the kernel above (cta_group::2, head_dim 128): the two CTAs of a cluster work on the SAME kv
+// head with DIFFERENT 128-token tiles.  One tcgen05.mma of M = 256, N = 128 reconstructs both tiles; the head's
+// right-factor slice is split between the CTAs (64 of its 128 rows each, 64 KiB instead of 128 KiB), which
+//   * halves the shared-memory bytes an MMA reads per tensor cycle (the N = 128 single-CTA MMA sits exactly at the
+//     128 B/clk shared-memory limit, before counting the TMA writes), and
+//   * frees 64 KiB per SM for the A_k ring: 9 stages x 16 KiB in flight instead of 5 (the A_k stream is bound by
+//     latency x bytes in flight, profiles/r01_decode_scores_ncu_full.md).
+// The score MMA is the pair form too (M = 256, N = 16: 8 q rows per CTA; tcgen05 instructions of one kernel must
+// agree on the cta_group).  Barriers that gate the leader's MMA issue live in the leader CTA and are arrived on by
+// both CTAs (TMA bytes via the .cta_group::2 load form, epilogue warps via remote mbarrier.arrive); barriers that
+// gate a CTA's own warps are signalled by the leader's multicast commits.
+// Measured (config 2, one layer): 99 us against 92 us for the single-CTA kernel above - the cross-CTA barrier round
+// trips cost more than the deeper ring and the lighter MMAs gain, so this variant is opt-in (XKV_DECODE_PAIR=1);
+// it is parity-tested like the default.
 // ---------------------------------------------------------------------------------------------
-constexpr int Q_D = 128;
-constexpr int Q_STAGES = 4;
-constexpr int Q_EPI_WARPS = 16;
-constexpr int Q_PARTS = Q_EPI_WARPS / 4;
-constexpr int Q_THREADS = 64 + 32 * Q_EPI_WARPS;
+constexpr int Q_STAGES = 9;
+constexpr int Q_EPI_WARPS = 8;
+constexpr int Q_OUT_WARPS = 4;
+constexpr int Q_THREADS = 32 * (4 + Q_EPI_WARPS + Q_OUT_WARPS);
+constexpr int Q_BHALF_BYTES = 64 * 1024;           // 64 rows x r_k <= 512 bf16
+constexpr int Q_Q_BYTES = 2 * 8 * 128;             // two 64-dim chunks of 8 q rows x 128 B
 constexpr int Q_TMEM_COLS = 512;
-constexpr size_t Q_SMEM_BYTES = PB_MAX_BYTES + Q_STAGES * D_A_BYTES + 1024 + 256 + 2 * Q_D * D_MAX_QPK * sizeof(float) +
-                                (Q_PARTS - 1) * 2 * DBM * D_MAX_QPK * sizeof(float);
+constexpr size_t Q_SMEM_BYTES = Q_BHALF_BYTES + Q_STAGES * D_A_BYTES + Q_Q_BYTES + 1024 + 512;
 
 __global__ void __launch_bounds__(Q_THREADS, 1) decode_scores_pair_kernel(const __grid_constant__ ScoreParams P) {
-  constexpr int D = Q_D;
-  constexpr int B_KB_BYTES = D * DBK * 2;
+  constexpr int D = 128;
+  constexpr int BH_KB_BYTES = (D / 2) * DBK * 2;   // one 64-wide K block of this CTA's 64 rows of the right factor
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem;
-  uint8_t* sA = smem + PB_MAX_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sA + Q_STAGES * D_A_BYTES);
-  uint64_t* empty_bar = full_bar + Q_STAGES;
-  uint64_t* tfull_bar = empty_bar + Q_STAGES;    // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;          // [2]  (the leader's copy is the one in use)
-  uint64_t* b_bar = tempty_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_bar + 1);
-  float* q_s = reinterpret_cast<float*>(sA + Q_STAGES * D_A_BYTES + 256);   // [2 heads][D][8], dim-major
-  float* part = q_s + 2 * D * D_MAX_QPK;                                    // [3 parts][2 heads][128 tokens][8]
+  uint8_t* sA = smem + Q_BHALF_BYTES;
+  uint8_t* sQ = sA + Q_STAGES * D_A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sQ + Q_Q_BYTES);   // leader: bytes of both CTAs
+  uint64_t* empty_bar = full_bar + Q_STAGES;        // local, multicast commit
+  uint64_t* tfull_bar = empty_bar + Q_STAGES;       // [2] local, multicast commit
+  uint64_t* tempty_bar = tfull_bar + 2;             // [2] leader, 2 x epilogue warps
+  uint64_t* a2full_bar = tempty_bar + 2;            // [2] leader, 2 x epilogue warps
+  uint64_t* a2empty_bar = a2full_bar + 2;           // [2] local, multicast commit
+  uint64_t* d2full_bar = a2empty_bar + 2;           // [2] local, multicast commit
+  uint64_t* d2empty_bar = d2full_bar + 2;           // [2] leader, 2 x read-out warps
+  uint64_t* b_bar = d2empty_bar + 2;                // leader
+  uint64_t* q_bar = b_bar + 1;                      // leader
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();       // 0 = leader
+  const uint32_t rank = cluster_ctarank();          // 0 = leader
   const int pair = blockIdx.x >> 1;
   const int npairs = gridDim.x >> 1;
-  const int nhp = P.H >> 1;                      // head pairs
-  const int hp = pair % nhp;
-  const int slot = pair / nhp;
-  const int nslots = (npairs - hp + nhp - 1) / nhp;   // CTA pairs that share this head pair
-  const int ntp = (P.S + 2 * DBM - 1) / (2 * DBM);    // 256-token tile pairs
-  const int h_mine = 2 * hp + static_cast<int>(rank); // the head whose right-factor slice this CTA holds
+  const int h = pair % P.H;
+  const int slot = pair / P.H;
+  const int nslots = (npairs - h + P.H - 1) / P.H;  // CTA pairs that share this head
+  const int ntp = (P.S + 2 * DBM - 1) / (2 * DBM);  // 256-token tile pairs
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < Q_STAGES; ++i) {
@@ -753,19 +760,18 @@ __global__ void __launch_bounds__(Q_THREADS, 1) decode_scores_pair_kernel(const 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 2 * Q_EPI_WARPS);   // one arrive per epilogue warp of BOTH CTAs
+      mbar_init(&tempty_bar[i], 2 * Q_EPI_WARPS);
+      mbar_init(&a2full_bar[i], 2 * Q_EPI_WARPS);
+      mbar_init(&a2empty_bar[i], 1);
+      mbar_init(&d2full_bar[i], 1);
+      mbar_init(&d2empty_bar[i], 2 * Q_OUT_WARPS);
     }
     mbar_init(b_bar, 1);
+    mbar_init(q_bar, 1);
     mbar_fence_init();
     tma_prefetch_desc(&P.a_map);
-    tma_prefetch_desc(&P.b_head_map);
-  }
-  if (warp >= 2) {
-    for (int e = threadIdx.x - 64; e < 2 * D * D_MAX_QPK; e += 32 * Q_EPI_WARPS) {
-      const int hh = e / (D * D_MAX_QPK), r = e - hh * D * D_MAX_QPK;
-      const int d = r / D_MAX_QPK, g = r - d * D_MAX_QPK;
-      q_s[e] = g < P.qpk ? __bfloat162float(P.q[static_cast<long long>((2 * hp + hh) * P.qpk + g) * D + d]) : 0.f;
-    }
+    tma_prefetch_desc(&P.b_half_map);
+    tma_prefetch_desc(&P.q8_map);
   }
   __syncthreads();
   cluster_sync_all();                               // barrier initialisation visible to the peer before any remote use
@@ -777,9 +783,13 @@ __global__ void __launch_bounds__(Q_THREADS, 1) decode_scores_pair_kernel(const 
 
   if (warp == 0) {
     if (lane == 0) {
-      // this CTA's head slice; the bytes of both CTAs are counted on the leader's barrier
-      if (rank == 0) mbar_expect_tx(b_bar, 2u * static_cast<uint32_t>(P.nkb) * B_KB_BYTES);
-      for (int kb = 0; kb < P.nkb; ++kb) tma_load_2d_pair(sB + kb * B_KB_BYTES, &P.b_head_map, b_bar, kb * DBK, h_mine * D);
+      // this CTA's q rows, this CTA's half of the head's right factor; bytes of both CTAs land on the leader's barriers
+      if (rank == 0) mbar_expect_tx(q_bar, 2u * Q_Q_BYTES);
+      tma_load_2d_pair(sQ, &P.q8_map, q_bar, 0, h * P.qpk + static_cast<int>(rank) * 8);
+      tma_load_2d_pair(sQ + Q_Q_BYTES / 2, &P.q8_map, q_bar, 64, h * P.qpk + static_cast<int>(rank) * 8);
+      if (rank == 0) mbar_expect_tx(b_bar, 2u * static_cast<uint32_t>(P.nkb) * BH_KB_BYTES);
+      for (int kb = 0; kb < P.nkb; ++kb)
+        tma_load_2d_pair(sB + kb * BH_KB_BYTES, &P.b_half_map, b_bar, kb * DBK, h * D + static_cast<int>(rank) * (D / 2));
       int s = 0;
       uint32_t ph = 0;
       for (int tp = slot; tp < ntp; tp += nslots) {
@@ -797,24 +807,23 @@ __global__ void __launch_bounds__(Q_THREADS, 1) decode_scores_pair_kernel(const 
     }
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * DBM, 2 * D, 0, 0);
-      mbar_wait(b_bar, 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * DBM, D, 0, 0);
+      mbar_wait_cluster(b_bar, 0);
       int s = 0, acc = 0;
-      uint32_t ph = 0, ph_acc0 = 0u, ph_acc1 = 0u;
+      uint32_t ph = 0, acc_ph = 0u;
       const uint32_t b_base = smem_u32(sB);
       for (int tp = slot; tp < ntp; tp += nslots) {
-        const uint32_t aph = acc ? ph_acc1 : ph_acc0;
-        mbar_wait(&tempty_bar[acc], aph ^ 1u);     // both CTAs' epilogues have drained this accumulator
+        mbar_wait_cluster(&tempty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * 2 * D);
+        const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * D);
         for (int kb = 0; kb < P.nkb; ++kb) {
-          mbar_wait(&full_bar[s], ph);
+          mbar_wait_cluster(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t a_base = smem_u32(sA + s * D_A_BYTES);
 #pragma unroll
           for (int k = 0; k < DBK / 16; ++k)
             umma_bf16_ss_pair(d_addr, umma_desc_sw128(a_base + k * 32, 16, 1024),
-                              umma_desc_sw128(b_base + kb * B_KB_BYTES + k * 32, 16, 1024), idesc,
+                              umma_desc_sw128(b_base + kb * BH_KB_BYTES + k * 32, 16, 1024), idesc,
                               (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit_pair(&empty_bar[s]);
           if (++s == Q_STAGES) {
@@ -823,130 +832,131 @@ __global__ void __launch_bounds__(Q_THREADS, 1) decode_scores_pair_kernel(const 
           }
         }
         umma_commit_pair(&tfull_bar[acc]);
-        if (acc) ph_acc1 ^= 1u; else ph_acc0 ^= 1u;
+        acc_ph ^= 1u << acc;
         acc ^= 1;
       }
     }
-  } else {
-    // ===== epilogue (both CTAs): thread = one token of this CTA's tile x 16 rotation pairs, both heads in turn =====
-    constexpr int PP = D / 2 / Q_PARTS;   // 16
-    constexpr int CW = PP / 2;            // 8
-    const int ew = warp - 2;
+  } else if (warp == 2) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc2 = umma_idesc_bf16(2 * DBM, 16, 0, 0);
+      mbar_wait_cluster(q_bar, 0);
+      const uint32_t q_base = smem_u32(sQ);
+      int b = 0;
+      uint32_t bph = 0u;
+      for (int tp = slot; tp < ntp; tp += nslots) {
+        mbar_wait_cluster(&a2full_bar[b], (bph >> b) & 1u);          // both CTAs' rotated keys are in TMEM
+        mbar_wait_cluster(&d2empty_bar[b], ((bph >> b) & 1u) ^ 1u);  // both CTAs' score buffers read out
+        tc_fence_after();
+        const uint32_t a2 = tmem_base + R_COL_A2 + static_cast<uint32_t>(b * 64);
+        const uint32_t d2 = tmem_base + R_COL_D2 + static_cast<uint32_t>(b * 32);
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          umma_bf16_ts_pair(d2, a2 + static_cast<uint32_t>(k * 8),
+                            umma_desc_sw128(q_base + (k >> 2) * (Q_Q_BYTES / 2) + (k & 3) * 32, 16, 1024), idesc2,
+                            k > 0 ? 1u : 0u);
+        umma_commit_pair(&d2full_bar[b]);
+        umma_commit_pair(&a2empty_bar[b]);
+        bph ^= 1u << b;
+        b ^= 1;
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + Q_EPI_WARPS) {
+    // ===== epilogue (both CTAs, own tokens): K^ row -> bf16 -> RoPE -> TMEM =====
     const int qd = warp & 3;
-    const int prt = ew >> 2;
+    const int half = (warp - 4) >> 2;
     const int row = qd * 32 + lane;
-    const int d0 = prt * PP;
+    const int d0 = half * 32;
     const bool rope = P.cos != nullptr;
     int acc = 0;
-    uint32_t ph_acc0 = 0u, ph_acc1 = 0u;
-    uint32_t cs_next[CW], sn_next[CW];
-    auto fetch_cs = [&](int tp_idx) {
-      const int t = tp_idx * 2 * DBM + static_cast<int>(rank) * DBM + row;
-      if (rope && tp_idx < ntp && t < P.S) {
-        const uint4* cp = reinterpret_cast<const uint4*>(P.cos + static_cast<long long>(t) * P.ld_cs + d0);
-        const uint4* sp = reinterpret_cast<const uint4*>(P.sin + static_cast<long long>(t) * P.ld_cs + d0);
+    uint32_t acc_ph = 0u;
+    for (int tp = slot; tp < ntp; tp += nslots) {
+      const int tok = tp * 2 * DBM + static_cast<int>(rank) * DBM + row;
+      uint32_t cs[16], sn[16];
+      if (rope && tok < P.S) {
+        const uint4* cp = reinterpret_cast<const uint4*>(P.cos + static_cast<long long>(tok) * P.ld_cs + d0);
+        const uint4* sp = reinterpret_cast<const uint4*>(P.sin + static_cast<long long>(tok) * P.ld_cs + d0);
 #pragma unroll
-        for (int v = 0; v < CW / 4; ++v) {
+        for (int v = 0; v < 4; ++v) {
           const uint4 cv = __ldg(cp + v), sv = __ldg(sp + v);
-          cs_next[4 * v] = cv.x, cs_next[4 * v + 1] = cv.y, cs_next[4 * v + 2] = cv.z, cs_next[4 * v + 3] = cv.w;
-          sn_next[4 * v] = sv.x, sn_next[4 * v + 1] = sv.y, sn_next[4 * v + 2] = sv.z, sn_next[4 * v + 3] = sv.w;
+          cs[4 * v] = cv.x, cs[4 * v + 1] = cv.y, cs[4 * v + 2] = cv.z, cs[4 * v + 3] = cv.w;
+          sn[4 * v] = sv.x, sn[4 * v + 1] = sv.y, sn[4 * v + 2] = sv.z, sn[4 * v + 3] = sv.w;
         }
       } else {
 #pragma unroll
-        for (int v = 0; v < CW; ++v) cs_next[v] = 0x3F803F80u, sn_next[v] = 0u;
+        for (int v = 0; v < 16; ++v) cs[v] = 0x3F803F80u, sn[v] = 0u;
       }
-    };
-    fetch_cs(slot);
-    for (int tp = slot; tp < ntp; tp += nslots) {
-      const int tok = tp * 2 * DBM + static_cast<int>(rank) * DBM + row;
-      const bool tok_ok = tok < P.S;
-      uint32_t cs[CW], sn[CW];
-#pragma unroll
-      for (int v = 0; v < CW; ++v) cs[v] = cs_next[v], sn[v] = sn_next[v];
-      fetch_cs(tp + nslots);
-      mbar_wait(&tfull_bar[acc], acc ? ph_acc1 : ph_acc0);
-      if (acc) ph_acc1 ^= 1u; else ph_acc0 ^= 1u;
+      mbar_wait(&tfull_bar[acc], (acc_ph >> acc) & 1u);
       tc_fence_after();
-      const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + static_cast<uint32_t>(acc * 2 * D);
-#pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t x1[PP], x2[PP];
+      const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
+      const uint32_t lane_addr = lane_base + static_cast<uint32_t>(acc * D);
+      uint32_t lo_w[16], hi_w[16];
+#pragma unroll
+      for (int sc = 0; sc < 2; ++sc) {
+        uint32_t x1[16], x2[16];
         __syncwarp();
-        tmem_ld_cols<PP>(lane_addr + static_cast<uint32_t>(hh * D + d0), x1);
-        tmem_ld_cols<PP>(lane_addr + static_cast<uint32_t>(hh * D + D / 2 + d0), x2);
+        tmem_ld_32x16(lane_addr + static_cast<uint32_t>(d0 + sc * 16), x1);
+        tmem_ld_32x16(lane_addr + static_cast<uint32_t>(D / 2 + d0 + sc * 16), x2);
         tmem_ld_wait();
-        if (hh == 1) {
-          // both heads' columns of this thread are in registers: hand the accumulator back to the leader's MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
-        }
-        const float* qh = q_s + hh * D * D_MAX_QPK;
-        float2 sc01 = make_float2(0.f, 0.f), sc23 = sc01, sc45 = sc01, sc67 = sc01;
-  #pragma unroll
-        for (int jp = 0; jp < PP / 2; ++jp) {
+#pragma unroll
+        for (int jp = 0; jp < 8; ++jp) {
           const __nv_bfloat162 k1 = __floats2bfloat162_rn(__uint_as_float(x1[2 * jp]), __uint_as_float(x1[2 * jp + 1]));
           const __nv_bfloat162 k2 = __floats2bfloat162_rn(__uint_as_float(x2[2 * jp]), __uint_as_float(x2[2 * jp + 1]));
           __nv_bfloat162 o1 = k1, o2 = k2;
           if (rope) {
-            const __nv_bfloat162 cw = *reinterpret_cast<const __nv_bfloat162*>(&cs[jp]);
-            const __nv_bfloat162 sw = *reinterpret_cast<const __nv_bfloat162*>(&sn[jp]);
+            const __nv_bfloat162 cw = *reinterpret_cast<const __nv_bfloat162*>(&cs[sc * 8 + jp]);
+            const __nv_bfloat162 sw = *reinterpret_cast<const __nv_bfloat162*>(&sn[sc * 8 + jp]);
             o1 = __hadd2(__hmul2(k1, cw), __hmul2(__hneg2(k2), sw));
             o2 = __hadd2(__hmul2(k2, cw), __hmul2(k1, sw));
           }
-          const float o1v[2] = {__low2float(o1), __high2float(o1)};
-          const float o2v[2] = {__low2float(o2), __high2float(o2)};
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int d1 = d0 + 2 * jp + u, d2 = d1 + D / 2;
-            const float2 a = make_float2(o1v[u], o1v[u]), b = make_float2(o2v[u], o2v[u]);
-            const float4 qa = *reinterpret_cast<const float4*>(qh + d1 * D_MAX_QPK);
-            const float4 qb = *reinterpret_cast<const float4*>(qh + d2 * D_MAX_QPK);
-            sc01 = __ffma2_rn(make_float2(qa.x, qa.y), a, __ffma2_rn(make_float2(qb.x, qb.y), b, sc01));
-            sc23 = __ffma2_rn(make_float2(qa.z, qa.w), a, __ffma2_rn(make_float2(qb.z, qb.w), b, sc23));
-            if (P.qpk > 4) {
-              const float4 qc = *reinterpret_cast<const float4*>(qh + d1 * D_MAX_QPK + 4);
-              const float4 qe = *reinterpret_cast<const float4*>(qh + d2 * D_MAX_QPK + 4);
-              sc45 = __ffma2_rn(make_float2(qc.x, qc.y), a, __ffma2_rn(make_float2(qe.x, qe.y), b, sc45));
-              sc67 = __ffma2_rn(make_float2(qc.z, qc.w), a, __ffma2_rn(make_float2(qe.z, qe.w), b, sc67));
-            }
-          }
-        }
-        const float sc[D_MAX_QPK] = {sc01.x, sc01.y, sc23.x, sc23.y, sc45.x, sc45.y, sc67.x, sc67.y};
-        // combine the four dim quarters through shared memory; the buffer of head hh is reused every tile: the
-        // barrier of the other head's round separates its readers from the next writers
-        if (prt > 0) {
-          float* pt = part + (((prt - 1) * 2 + hh) * DBM + row) * D_MAX_QPK;
-          *reinterpret_cast<float4*>(pt) = make_float4(sc[0], sc[1], sc[2], sc[3]);
-          if (P.qpk > 4) *reinterpret_cast<float4*>(pt + 4) = make_float4(sc[4], sc[5], sc[6], sc[7]);
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * Q_EPI_WARPS) : "memory");
-        if (prt == 0 && tok_ok) {
-          float tot[D_MAX_QPK];
-#pragma unroll
-          for (int g = 0; g < D_MAX_QPK; ++g) tot[g] = sc[g];
-#pragma unroll
-          for (int o = 0; o < Q_PARTS - 1; ++o) {
-            const float* pt = part + ((o * 2 + hh) * DBM + row) * D_MAX_QPK;
-            const float4 lo4 = *reinterpret_cast<const float4*>(pt);
-            tot[0] += lo4.x, tot[1] += lo4.y, tot[2] += lo4.z, tot[3] += lo4.w;
-            if (P.qpk > 4) {
-              const float4 hi4 = *reinterpret_cast<const float4*>(pt + 4);
-              tot[4] += hi4.x, tot[5] += hi4.y, tot[6] += hi4.z, tot[7] += hi4.w;
-            }
-          }
-          const int h = 2 * hp + hh;
-#pragma unroll
-          for (int g = 0; g < D_MAX_QPK; ++g)
-            if (g < P.qpk) P.scores[static_cast<long long>(h * P.qpk + g) * P.ld_scores + tok] = tot[g] * P.scale;
+          lo_w[sc * 8 + jp] = *reinterpret_cast<const uint32_t*>(&o1);
+          hi_w[sc * 8 + jp] = *reinterpret_cast<const uint32_t*>(&o2);
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+      mbar_wait(&a2empty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t a2 = lane_base + R_COL_A2 + static_cast<uint32_t>(acc * 64);
+      __syncwarp();
+      tmem_st_32x16(a2 + static_cast<uint32_t>(d0 / 2), lo_w);
+      tmem_st_32x16(a2 + static_cast<uint32_t>(32 + d0 / 2), hi_w);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&a2full_bar[acc]);
+      acc_ph ^= 1u << acc;
       acc ^= 1;
+    }
+  } else if (warp >= 4 + Q_EPI_WARPS) {
+    // ===== score read-out (both CTAs, own tokens) =====
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    int b = 0;
+    uint32_t bph = 0u;
+    for (int tp = slot; tp < ntp; tp += nslots) {
+      const int tok = tp * 2 * DBM + static_cast<int>(rank) * DBM + row;
+      mbar_wait(&d2full_bar[b], (bph >> b) & 1u);
+      tc_fence_after();
+      uint32_t v[8];
+      __syncwarp();
+      tmem_ld_32x8(tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + R_COL_D2 + static_cast<uint32_t>(b * 32), v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&d2empty_bar[b]);
+      if (tok < P.S) {
+#pragma unroll
+        for (int g = 0; g < D_MAX_QPK; ++g)
+          if (g < P.qpk) P.scores[static_cast<long long>(h * P.qpk + g) * P.ld_scores + tok] = __uint_as_float(v[g]) * P.scale;
+      }
+      bph ^= 1u << b;
+      b ^= 1;
     }
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer may still signal its barriers / read its smem
+  cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, Q_TMEM_COLS);
@@ -1112,6 +1122,7 @@ static inline int decode_split_k(int S, int rv) {
 }
 
 static bool g_force_tiled_scores = false;  // test hook: exercise the tile-per-CTA scores kernel
+static int g_scores_variant = 0;           // test hook: 0 automatic, 1 FFMA epilogue, 2 score-MMA, 3 CTA pair
 
 }  // namespace xkv
 
@@ -1177,6 +1188,10 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
   if (q_tma_ok) {
     rc = encode_tmap_2d_bf16(&sp.q_map, q, D, Hq, D, 64, R_QROWS);
     if (rc) return rc;
+    rc = encode_tmap_2d_bf16(&sp.q8_map, q, D, Hq, D, 64, 8);
+    if (rc) return rc;
+    rc = encode_tmap_2d_bf16(&sp.b_half_map, Vk_layer, rk, static_cast<uint64_t>(H) * D, ldv_k, DBK, 64);
+    if (rc) return rc;
   }
   sp.q = static_cast<const __nv_bfloat16*>(q);
   sp.cos = static_cast<const __nv_bfloat16*>(cos);
@@ -1217,10 +1232,12 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
     const int ntiles = (S + DBM - 1) / DBM;
     int pgrid = sms < ntiles * H ? sms : ntiles * H;
     if (pgrid < H) pgrid = H;   // every head needs at least one CTA
-    static const bool pair_off = getenv("XKV_DECODE_PAIR") == nullptr;   // opt-in: see the kernel's header comment
+    static const bool pair_env = getenv("XKV_DECODE_PAIR") != nullptr;   // opt-in: measured 99 us vs 92 us for the single-CTA kernel
+    const bool pair_off = !(pair_env || g_scores_variant == 3);
     const int ntp = (S + 2 * DBM - 1) / (2 * DBM);
-    if (D == 128 && H % 2 == 0 && !pair_off && sms >= H) {
-      // CTA pairs: one cluster of 2 per (head pair, slot)
+    if (D == 128 && q_tma_ok && qpk <= 8 && !pair_off && sms >= 2 * H &&
+        static_cast<size_t>(sp.nkb) * 64 * DBK * 2 <= static_cast<size_t>(Q_BHALF_BYTES)) {
+      // CTA pairs: one cluster of 2 per (head, slot)
       static bool qconf = false;
       if (!qconf) {
         XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1228,8 +1245,8 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
         qconf = true;
       }
       int npairs = sms / 2;
-      if (npairs > ntp * (H / 2)) npairs = ntp * (H / 2);
-      if (npairs < H / 2) npairs = H / 2;
+      if (npairs > ntp * H) npairs = ntp * H;
+      if (npairs < H) npairs = H;
       cudaLaunchConfig_t cfg;
       std::memset(&cfg, 0, sizeof(cfg));
       cfg.gridDim = dim3(2 * npairs, 1, 1);
@@ -1244,7 +1261,7 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       XKV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_scores_pair_kernel, sp));
-    } else if (D == 128 && q_tma_ok && getenv("XKV_DECODE_FFMA") == nullptr) {
+    } else if (D == 128 && q_tma_ok && qpk <= 8 && g_scores_variant != 1) {
       static bool rconf = false;
       if (!rconf) {
         XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1315,3 +1332,5 @@ extern "C" int xkv_rope_bf16(void* x, int64_t ld_row, int rows, int H, int D, co
 
 /* test hook: 1 forces the tile-per-CTA scores kernel, 0 restores the automatic choice */
 extern "C" void xkv_decode_force_tiled(int on) { g_force_tiled_scores = on != 0; }
+/* test hook: which persistent scores kernel to use when several apply (0 automatic) */
+extern "C" void xkv_decode_set_variant(int variant) { g_scores_variant = variant; }
