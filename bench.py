@@ -299,11 +299,26 @@ def run_xkv_arm(args):
         for _ in range(3):
             one_token()
         barrier()
-        ntok = 8
         l0 = ops.launch_count()
+        one_token()
+        launches_per_token = ops.launch_count() - l0
+        # one decode token = 32 layers x 5 kernels: replayed as a CUDA graph (static q / factors / workspace), like the
+        # compress step, unless --no-graph
+        token_graph = None
+        if not args.no_graph:
+            torch.cuda.synchronize()
+            token_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(token_graph):
+                one_token()
+            token_graph.replay()
+        barrier()
+        ntok = 8
         e0.record()
         for _ in range(ntok):
-            one_token()
+            if token_graph is not None:
+                token_graph.replay()
+            else:
+                one_token()
         e1.record()
         barrier()
         t = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -317,7 +332,8 @@ def run_xkv_arm(args):
             "metric": "decode tok/s reconstructed (attention over the factored cache, 32 layers, batch 1, 64K context)",
             "tok_s": world * 1e3 / ms_tok, "ms_per_token": ms_tok, "us_per_layer": 1e3 * ms_tok / LAYERS,
             "equiv_dense_kv_GBps": world * LAYERS * 2.0 * S * HEADS * HEAD_DIM * 2 / (ms_tok * 1e-3) / 1e9,
-            "gpu_launches_per_token": (ops.launch_count() - l0) // ntok,
+            "gpu_launches_per_token": launches_per_token,
+            "launch_mode": "cuda-graph replay" if token_graph is not None else "host enqueue",
             "roofline": {"bound": "tensor", "achieved": flops_k / (ms_tok * 1e-3) / 1e12, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": flops_k / (ms_tok * 1e-3) / 1e12 / peak_tf,
                          "hbm_frac": bytes_a / (ms_tok * 1e-3) / 1e9 / peak_hbm,
