@@ -166,6 +166,8 @@ typedef struct xkv_factorize_options {
   float pivot_floor;
   float spectral_shift;   /* power steps after the first iterate with G - c I, c = spectral_shift * (estimate of lambda_l); 0 = off (0.5) */
   int32_t shift_tail;     /* trailing entries of diag(R) of the previous step that estimate lambda_l (8) */
+  int32_t single_pass_from; /* power steps with index >= this (> 0) orthonormalise with ONE CholeskyQR pass (small shift, 6-term Gram); 0 = never */
+  int32_t single_pass_last; /* 1: the last power step may use the single pass too */
   uint64_t seed;
 } xkv_factorize_options;
 XKV_API void xkv_factorize_default_options(xkv_factorize_options* opts);

@@ -8,7 +8,7 @@ import torch
 from xkv_b200 import factorize, synthetic
 
 CASES = [(1024, 1024, 128, 1.0), (1024, 1024, 192, 0.5), (2048, 2048, 256, 1.0), (4096, 4096, 512, 1.0),
-         (4096, 4096, 768, 0.5), (4096, 4096, 512, None), (1536, 2048, 512, 1.0)]
+         (4096, 4096, 768, 0.5), (4096, 4096, 512, None), (1536, 2048, 512, 1.0), (2048, 8192, 1024, 0.5)]
 
 
 def rel(x, xh):

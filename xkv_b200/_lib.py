@@ -66,6 +66,8 @@ class FactorizeOptions(C.Structure):
         ("pivot_floor", C.c_float),
         ("spectral_shift", C.c_float),
         ("shift_tail", C.c_int32),
+        ("single_pass_from", C.c_int32),
+        ("single_pass_last", C.c_int32),
         ("seed", C.c_uint64),
     ]
 

@@ -189,6 +189,8 @@ extern "C" void xkv_factorize_default_options(xkv_factorize_options* o) {
   o->power_iters = 4;
   o->spectral_shift = 0.5f;
   o->shift_tail = 8;
+  o->single_pass_from = 1;
+  o->single_pass_last = 1;
   o->oversample = 64;
   o->first_passes = 2;
   o->passes = 2;
@@ -300,12 +302,13 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
   // cur <- orth(cur): row-normalised, shifted CholeskyQR
   // With `shifted`, cur = Q_prev G and nxt still holds Q_prev: the first pass first forms Q_prev (G - c I).
   // With `track`, diag(R) of the step is accumulated in P.rdiag (row norms x Cholesky diagonals).
-  auto cholqr = [&](int npass, bool shifted, bool track) -> int {
+  auto cholqr = [&](int npass, bool shifted, bool track, int p0) -> int {
     for (int ip = 0; ip < npass; ++ip) {
+      const int pp = ip + p0;  // index into the per-pass parameters (shift, limb terms)
       XKV_TRY(xkv_shift_normalize_rows(cur, (ip == 0 && shifted) ? nxt : nullptr, P.shift_dev, track ? P.rdiag : nullptr,
                                        ip == 0, P.lh, P.lm, P.ll, B, l, n, nn, nn, stream));
       // pass 0 is regularised by a 3e-4 shift, so the 3-term product (error ~1e-5) is accurate enough there
-      const int nt = ip == 0 ? 3 : 6;
+      const int nt = pp == 0 ? 3 : 6;
       for (int b = 0; b < B; ++b) {
         xkv_gemm_problem p = problem(P.lh[b], P.lm[b], P.ll[b], nn, 0, P.lh[b], P.lm[b], P.ll[b], nn, 0, P.s_slabs[b], l,
                                      l, l, n, nt);
@@ -320,7 +323,7 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
         void *h0[XKV_MAX_BATCH], *h1[XKV_MAX_BATCH], *h2[XKV_MAX_BATCH];
         for (int b = 0; b < B; ++b) h0[b] = P.linv_l[b][0], h1[b] = P.linv_l[b][1], h2[b] = P.linv_l[b][2];
         XKV_TRY(xkv_cholesky_inverse_limbs(P.s_mat, P.linv, h0, h1, nt > 3 ? h2 : nullptr, B, l, l, l,
-                                           o.shifts[ip < 3 ? ip : 3], o.pivot_floor, stream));
+                                           o.shifts[pp < 3 ? pp : 3], o.pivot_floor, stream));
       }
       if (track) XKV_TRY(xkv_rdiag_update(P.rdiag, P.linv, B, l, l, stream));
       for (int b = 0; b < B; ++b)
@@ -344,7 +347,7 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
   // ---- 2-3. Gaussian range finder ----
   for (int b = 0; b < B; ++b) XKV_TRY(xkv_fill_gaussian_bf16(P.lh[b], l, n, nn, o.seed + 7919ull * b, stream));
   XKV_TRY(apply_gram(1));
-  XKV_TRY(cholqr(o.first_passes, false, false));
+  XKV_TRY(cholqr(o.first_passes, false, false, 0));
   XKV_TRY(mark());  // 3: range finder
 
   // ---- 4. power steps ----
@@ -359,7 +362,13 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
     if (shifted)
       XKV_TRY(xkv_ritz_shift_update(P.rdiag, B, l, o.shift_tail < l ? o.shift_tail : l, o.spectral_shift, P.shift_dev,
                                     stream));
-    XKV_TRY(cholqr(it == o.power_iters - 1 ? o.final_passes : o.passes, shifted, use_shift && it + 1 < o.power_iters));
+    // From step `single_pass_from` on the basis entering the step is orthonormal to ~1e-5 and ordered by dominance,
+    // so the row-normalised product is well conditioned: ONE pass with the second pass's parameters (small shift,
+    // 6-term Gram) orthonormalises it; the first, heavily shifted pass is only needed while the sketch is raw.
+    const bool last = it == o.power_iters - 1;
+    const bool single = o.single_pass_from > 0 && it >= o.single_pass_from && !(last && o.final_passes > 1 && o.single_pass_last == 0);
+    XKV_TRY(cholqr(single ? 1 : (last ? o.final_passes : o.passes), shifted, use_shift && it + 1 < o.power_iters,
+                   single ? 1 : 0));
   }
   XKV_TRY(mark());  // 4: power iterations
 

@@ -15,7 +15,8 @@ caller's stream; nothing synchronises):
   2. range finder    Y = G Omega           Omega Gaussian n x l, l = r + oversample
   3. CholeskyQR      Q = orth(Y)           row-normalise, S = Y^T Y (6-term bf16-limb product ~ fp32),
                                            blocked Cholesky + explicit inverse, Q = Y L^-T; repeated
-  4. power steps     Y = (G - c I) Q; CholeskyQR   `power_iters` times (3-term limb product); from the second
+  4. power steps     Y = (G - c I) Q; CholeskyQR   `power_iters` times (3-term limb product; two CholeskyQR passes
+                     after the first step, ONE accurate pass after the others); from the second
                      step on c ~ lambda_l / 2 (lambda_l read off the diagonal of the previous step's
                      triangular factor), which does the work of ~6 plain steps in 4
   5. Rayleigh-Ritz   shared-memory Jacobi on the window of T = Q^T G Q that straddles column r: the
@@ -57,6 +58,9 @@ class FactorizeOptions:
     pivot_floor: float = 1e-12
     spectral_shift: float = 0.5   # c = spectral_shift * (estimate of lambda_l from diag(R)); 0 disables the shift
     shift_tail: int = 8
+    single_pass_from: int = 1     # power steps with index >= this (> 0; 0 = never) use ONE CholeskyQR pass (small
+                                  # shift, 6-term Gram): their input basis is already orthonormal and ordered
+    single_pass_last: bool = True   # ... including the last step
     seed: int = 1234
     profile: bool = False
 
@@ -101,6 +105,7 @@ def _c_options(opts: FactorizeOptions) -> "_lib.FactorizeOptions":
         o.shifts[i] = opts.shifts[min(i, len(opts.shifts) - 1)]
     o.pivot_floor = opts.pivot_floor
     o.spectral_shift, o.shift_tail = opts.spectral_shift, opts.shift_tail
+    o.single_pass_from, o.single_pass_last = int(opts.single_pass_from), int(opts.single_pass_last)
     o.seed = opts.seed
     return o
 
