@@ -9,7 +9,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _case(S, H, D, qpk, rk, rv, T, layers_in_group, layer, rope, seed=0):
+def _case(S, H, D, qpk, rk, rv, T, layers_in_group, layer, rope, seed=0, dim_major_tables=True):
     from oracle import xkv_oracle as O
     from xkv_b200 import ops, synthetic
 
@@ -37,9 +37,11 @@ def _case(S, H, D, qpk, rk, rv, T, layers_in_group, layer, rope, seed=0):
                              kt.float() if T else None, vt.float() if T else None, scaling=1.0 / math.sqrt(D))[0, :, 0]
     # ---- CUDA path ----
     dev = "cuda"
+    rope_t = ops.rope_tables_dim_major(cos.to(dev), sin.to(dev)) if (rope and dim_major_tables and D == 128) else None
     out = ops.decode_attention(q.to(dev), a_k.to(dev), v_k.to(dev)[rows], a_v.to(dev), v_v.to(dev)[rows], H,
                                cos.to(dev) if rope else None, sin.to(dev) if rope else None,
-                               k_tail.to(dev) if T else None, v_tail.to(dev) if T else None, 1.0 / math.sqrt(D))
+                               k_tail.to(dev) if T else None, v_tail.to(dev) if T else None, 1.0 / math.sqrt(D),
+                               rope_t=rope_t)
     torch.cuda.synchronize()
     got = out.float().cpu()
     scale = ref.abs().max().item()
@@ -60,18 +62,20 @@ def _case(S, H, D, qpk, rk, rv, T, layers_in_group, layer, rope, seed=0):
         (300, 3, 128, 1, 96, 160, 1, 2, 0, True),      # MHA (qpk 1), 3 heads: second n-tile half empty, rank not /64
     ],
 )
-@pytest.mark.parametrize("variant", ["auto", "tiled", "ffma", "pair"])
+@pytest.mark.parametrize("variant", ["auto", "tr", "tiled", "ffma", "pair"])
 def test_decode_attention_matches_oracle(S, H, D, qpk, rk, rv, T, G, layer, rope, variant):
-    """auto: persistent scores kernel (right-factor slice resident in shared memory; for head_dim 128 the rotated
-    keys go back to TMEM and a second MMA contracts them with q); tiled: the tile-per-CTA kernel used when that slice
+    """auto: persistent scores kernel with the right-factor slice resident in shared memory (for head_dim 128 the rotated
+    keys go back to TMEM and a second MMA contracts them with q); tr: the transposed persistent kernel (right-factor
+    slice resident in TENSOR memory, token stream as the shared-memory operand, RoPE partners meet by a warp shuffle,
+    dim-major RoPE tables; head_dim 128 and r_k <= 512); tiled: the tile-per-CTA kernel used when that slice
     does not fit; ffma: persistent kernel with the FFMA epilogue (head_dim 64 path); pair: cta_group::2 CTA pairs."""
     from xkv_b200 import _lib
 
     lib = _lib.load()
     lib.xkv_decode_force_tiled(int(variant == "tiled"))
-    lib.xkv_decode_set_variant({"auto": 0, "tiled": 0, "ffma": 1, "pair": 3}[variant])
+    lib.xkv_decode_set_variant({"auto": 0, "tr": 4, "tiled": 0, "ffma": 1, "pair": 3}[variant])
     try:
-        _case(S, H, D, qpk, rk, rv, T, G, layer, rope)
+        _case(S, H, D, qpk, rk, rv, T, G, layer, rope, dim_major_tables=(variant in ("auto", "tr")))
     finally:
         lib.xkv_decode_force_tiled(0)
         lib.xkv_decode_set_variant(0)
@@ -80,6 +84,38 @@ def test_decode_attention_matches_oracle(S, H, D, qpk, rk, rv, T, G, layer, rope
 def test_decode_large_rank_falls_back_to_tiled_kernel():
     # r_k = 1024: one head's slice is 256 KiB > 128 KiB of shared memory
     _case(1024, 2, 128, 4, 1024, 256, 2, 4, 1, True)
+
+
+def test_transposed_kernel_all_k_blocks_in_tensor_memory_and_the_eighth_in_shared_memory():
+    # r_k = 448: seven 64-wide K blocks, all in TMEM; r_k = 512: the eighth block goes through shared memory (SS form);
+    # r_k = 456: ragged last block; several token tiles per CTA at 148 CTAs needs S > 148 * 128 / H
+    from xkv_b200 import _lib
+
+    _lib.load().xkv_decode_set_variant(4)
+    try:
+        _tr_cases()
+    finally:
+        _lib.load().xkv_decode_set_variant(0)
+
+
+def _tr_cases():
+    _case(3000, 8, 128, 4, 448, 192, 2, 4, 1, True)
+    _case(3000, 8, 128, 4, 456, 192, 0, 4, 0, True)
+    _case(40000, 8, 128, 4, 512, 256, 3, 4, 2, True)
+    _case(5000, 2, 128, 8, 512, 128, 1, 2, 1, False)
+
+
+def test_rope_tables_dim_major():
+    from xkv_b200 import ops, synthetic
+
+    S, D = 1000, 128
+    cos, sin = synthetic.llama3_rope(S, D)
+    cos, sin = cos[0].cuda(), sin[0].cuda()
+    ct, st = ops.rope_tables_dim_major(cos, sin, capacity=1100)
+    torch.cuda.synchronize()
+    assert ct.shape == (64, 1152) and st.shape == (64, 1152)
+    assert torch.equal(ct[:, :S], cos[:, :64].t()) and torch.equal(st[:, :S], sin[:, :64].t())
+    assert ct[:, S:].abs().max().item() == 0 and st[:, S:].abs().max().item() == 0
 
 
 def test_rope_bf16_matches_hf_formula():

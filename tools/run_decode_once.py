@@ -19,9 +19,13 @@ v_k = torch.randn(n, RK, device=dev).bfloat16()
 v_v = torch.randn(n, RV, device=dev).bfloat16()
 cos, sin = synthetic.llama3_rope(S, D, device=dev)
 cos, sin = cos[0].contiguous(), sin[0].contiguous()
+rope_t = None if os.environ.get("XKV_NO_ROPE_T") else ops.rope_tables_dim_major(cos, sin)
 q = torch.randn(HQ, D, device=dev).bfloat16()
 kt = torch.randn(H, 1, D, device=dev).bfloat16()
 vt = torch.randn(H, 1, D, device=dev).bfloat16()
+if os.environ.get("XKV_VARIANT"):
+    from xkv_b200 import _lib
+    _lib.load().xkv_decode_set_variant(int(os.environ["XKV_VARIANT"]))
 ws = torch.empty(ops.decode_workspace_bytes(HQ, S, 1, RV) + 4096, dtype=torch.uint8, device=dev)
 
 
@@ -29,7 +33,7 @@ def run():
     for l in range(layers):
         i = l % G
         ops.decode_attention(q, a_k, v_k[i * H * D:(i + 1) * H * D], a_v, v_v[i * H * D:(i + 1) * H * D], H, cos, sin,
-                             kt, vt, 1.0 / math.sqrt(D), workspace=ws)
+                             kt, vt, 1.0 / math.sqrt(D), workspace=ws, rope_t=rope_t)
 
 
 run()

@@ -41,9 +41,13 @@ struct alignas(64) ScoreParams {
   const __nv_bfloat16* q;    // (Hq, D)
   const __nv_bfloat16* cos;  // (S, D) or null
   const __nv_bfloat16* sin;
+  const __nv_bfloat16* cos_t;  // (D/2, ld_t) dim-major copies of the first D/2 columns of cos / sin, zero padded to
+  const __nv_bfloat16* sin_t;  //   a multiple of 128 tokens (xkv_rope_tables_dim_major), or null
+  const __nv_bfloat16* bk;     // Bk_l (H*D x r_k), the layer's rows of the right factor (transposed kernel)
   float* scores;             // (Hq, ld_scores)
-  long long ld_cs, ld_scores;
+  long long ld_cs, ld_scores, ld_t, ld_bk;
   int S, rk, H, qpk, tiles_n, nkb;
+  int dbg;   // bisect switches of the transposed kernel (XKV_DECODE_DBG, profiling only; 0 in production)
   float scale;
 };
 
@@ -963,6 +967,350 @@ __global__ void __launch_bounds__(Q_THREADS, 1) decode_scores_pair_kernel(const 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Transposed variant (head_dim 128, r_k <= 512: the default where it applies): the kernels above keep the head's
+// right-factor slice (128 KiB) in shared memory, which leaves room for only 5 stages of the A_k stream and makes
+// every reconstruction MMA read BOTH operands from shared memory (N = 128: 128 B/clk, the shared-memory limit).
+// Here the roles of the operands are swapped:
+//
+//     K^T tile [128 dims x 128 tokens] = Bk_head [128 dims x r_k] (TENSOR MEMORY, A operand, TS form)
+//                                        * A_k tile [128 tokens x r_k]^T (shared memory, B operand, TMA ring)
+//
+//   * the right-factor slice is written to TMEM once per CTA (tcgen05.st, 32 columns per 64-wide K block; the
+//     first 7 K blocks = 224 columns; an 8th block, if any, stays in shared memory and is applied in SS form),
+//     so shared memory holds only the token stream: 8 stages x 16 KiB in flight instead of 5, and an MMA reads
+//     half as many shared-memory bytes per tensor cycle;
+//   * the accumulator has lane = head dim, column = token.  The rows of the slice are PERMUTED over the TMEM lanes
+//     (lane 2i = dim i, lane 2i+1 = dim i + 64) so that the two RoPE partners of a pair sit in neighbouring lanes of
+//     one warp and meet by a shuffle; the rotation runs in packed bf16 over two TOKENS at a time with cos / sin read
+//     from dim-major tables (cos_t[i][token]); the rounding sequence is the reference's, as in the kernels above;
+//   * the rotated keys go to shared memory as an MN-major A operand (row = dim, 128 B = 64 tokens, SWIZZLE_128B) and
+//     a second tcgen05.mma (SS form, M = 128 tokens, N = 16 q rows, K = 128 dims) contracts them with q.
+//   TMEM: [0,224) right factor | [224,480) two K^T accumulators | [480,512) two score blocks.
+// Warp roles: 0 TMA, 1 reconstruction MMAs, 2 score MMAs, 4..11 epilogue (lane quarter x token half), 12..15 read-out.
+// ---------------------------------------------------------------------------------------------
+constexpr int T_STAGES = 8;
+constexpr int T_EPI_WARPS = 8;
+constexpr int T_OUT_WARPS = 4;
+constexpr int T_THREADS = 32 * (4 + T_EPI_WARPS + T_OUT_WARPS);
+constexpr int T_MAX_KB_TMEM = 7;                 // 64-wide K blocks of the right factor held in TMEM (32 columns each)
+constexpr int T_BS_BYTES = 128 * DBK * 2;        // the 8th K block (K-major, 128 permuted rows x 128 B)
+constexpr int T_KROT_BYTES = 128 * 128 * 2;      // rotated keys of one tile: two 64-token chunks of 128 rows x 128 B
+constexpr int T_TMEM_COLS = 512;
+constexpr uint32_t T_COL_ACC = 224, T_COL_D2 = 480;
+constexpr size_t T_SMEM_BYTES = T_BS_BYTES + T_STAGES * D_A_BYTES + 2 * T_KROT_BYTES + R_Q_BYTES + 1024 + 512;
+
+__global__ void __launch_bounds__(T_THREADS, 1) decode_scores_tr_kernel(const __grid_constant__ ScoreParams P) {
+  constexpr int D = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sBs = smem;
+  uint8_t* sA = sBs + T_BS_BYTES;
+  uint8_t* sK = sA + T_STAGES * D_A_BYTES;
+  uint8_t* sQ = sK + 2 * T_KROT_BYTES;             // 1024-byte aligned (all sizes above are multiples of 1024)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sQ + R_Q_BYTES);
+  uint64_t* empty_bar = full_bar + T_STAGES;
+  uint64_t* tfull_bar = empty_bar + T_STAGES;      // [2] K^T accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2] ... drained by the epilogue warps
+  uint64_t* kfull_bar = tempty_bar + 2;            // [2] rotated keys written to shared memory
+  uint64_t* kempty_bar = kfull_bar + 2;            // [2] ... consumed by the score MMAs
+  uint64_t* d2full_bar = kempty_bar + 2;           // [2] scores ready in TMEM
+  uint64_t* d2empty_bar = d2full_bar + 2;          // [2] ... read out
+  uint64_t* bready_bar = d2empty_bar + 2;          // right factor in TMEM / shared memory
+  uint64_t* q_bar = bready_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x % P.H;
+  const int slot = blockIdx.x / P.H;
+  const int nslots = (gridDim.x - h + P.H - 1) / P.H;
+  const int ntiles = (P.S + DBM - 1) / DBM;
+  const int nkb_t = P.nkb < T_MAX_KB_TMEM ? P.nkb : T_MAX_KB_TMEM;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < T_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], T_EPI_WARPS);
+      mbar_init(&kfull_bar[i], T_EPI_WARPS);
+      mbar_init(&kempty_bar[i], 1);
+      mbar_init(&d2full_bar[i], 1);
+      mbar_init(&d2empty_bar[i], T_OUT_WARPS);
+    }
+    mbar_init(bready_bar, T_EPI_WARPS);
+    mbar_init(q_bar, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&P.a_map);
+    tma_prefetch_desc(&P.q_map);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, T_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_bar, R_Q_BYTES);
+      tma_load_2d(sQ, &P.q_map, q_bar, 0, h * P.qpk);            // dims 0..63 of q rows [h qpk, h qpk + 16)
+      tma_load_2d(sQ + R_Q_BYTES / 2, &P.q_map, q_bar, 64, h * P.qpk);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = slot; tile < ntiles; tile += nslots) {
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          if (P.dbg & 32) {
+            mbar_arrive(&full_bar[s]);
+          } else {
+          mbar_expect_tx(&full_bar[s], D_A_BYTES);
+          tma_load_2d(sA + s * D_A_BYTES, &P.a_map, &full_bar[s], kb * DBK, tile * DBM);
+          }
+          if (++s == T_STAGES) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // K^T[128 dims x 128 tokens] += Bk_head (TMEM, or shared memory for the 8th K block) * A_k tile^T
+      constexpr uint32_t idesc = umma_idesc_bf16(D, DBM, 0, 0);
+      mbar_wait(bready_bar, 0);
+      tc_fence_after();
+      int s = 0, acc = 0;
+      uint32_t ph = 0, acc_ph = 0u;
+      const uint32_t bs_base = smem_u32(sBs);
+      for (int tile = slot; tile < ntiles; tile += nslots) {
+        if (!(P.dbg & 128)) mbar_wait(&tempty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + T_COL_ACC + static_cast<uint32_t>(acc * DBM);
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + s * D_A_BYTES);
+          if (P.dbg & 1) {
+          } else if (kb < nkb_t) {
+#pragma unroll
+            for (int k = 0; k < ((P.dbg & 64) ? 1 : DBK / 16); ++k)
+              umma_bf16_ts(d_addr, tmem_base + static_cast<uint32_t>(kb * 32 + k * 8),
+                           umma_desc_sw128(a_base + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < DBK / 16; ++k)
+              umma_bf16_ss(d_addr, umma_desc_sw128(bs_base + k * 32, 16, 1024), umma_desc_sw128(a_base + k * 32, 16, 1024),
+                           idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (++s == T_STAGES) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc_ph ^= 1u << acc;
+        acc ^= 1;
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      // scores[128 tokens x 16] = K^rot (shared memory, MN-major: row = dim, 64 tokens per 128 B) * Q^T (K-major)
+      constexpr uint32_t idesc2 = umma_idesc_bf16(DBM, R_QROWS, 1, 0);
+      mbar_wait(q_bar, 0);
+      const uint32_t q_base = smem_u32(sQ);
+      int b = 0;
+      uint32_t bph = 0u;
+      for (int tile = slot; tile < ntiles; tile += nslots) {
+        mbar_wait(&kfull_bar[b], (bph >> b) & 1u);                  // rotated keys of this tile are in shared memory
+        mbar_wait(&d2empty_bar[b], ((bph >> b) & 1u) ^ 1u);         // score buffer read out
+        tc_fence_after();
+        const uint32_t k_base = smem_u32(sK + b * T_KROT_BYTES);
+        const uint32_t d2 = tmem_base + T_COL_D2 + static_cast<uint32_t>(b * 16);
+        if (!(P.dbg & 4))
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          umma_bf16_ss(d2, umma_desc_sw128(k_base + k * 2048, T_KROT_BYTES / 2, 1024),
+                       umma_desc_sw128(q_base + (k >> 2) * (R_Q_BYTES / 2) + (k & 3) * 32, 16, 1024), idesc2, k > 0 ? 1u : 0u);
+        umma_commit(&d2full_bar[b]);
+        umma_commit(&kempty_bar[b]);
+        bph ^= 1u << b;
+        b ^= 1;
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + T_EPI_WARPS) {
+    const int qd = warp & 3;
+    const int half = (warp - 4) >> 2;                 // token half of the tile (and K-block parity of the prologue)
+    const int L = qd * 32 + lane;                     // TMEM lane
+    const int fi = L >> 1;                            // RoPE frequency index
+    const int dim = fi + ((L & 1) << 6);              // head dim held by this lane
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
+    // ===== prologue: this lane's row of the head's right-factor slice -> TMEM (A operand: column c = k 2c, 2c+1) =====
+    {
+      const __nv_bfloat16* brow = P.bk + static_cast<long long>(h * D + dim) * P.ld_bk;
+      for (int kb = half; kb < P.nkb; kb += 2) {
+        uint4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k0 = kb * DBK + j * 8;
+          v[j] = (k0 + 8 <= P.rk) ? __ldg(reinterpret_cast<const uint4*>(brow + k0)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (kb < nkb_t) {
+          uint32_t w0[16], w1[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            w0[4 * j] = v[j].x, w0[4 * j + 1] = v[j].y, w0[4 * j + 2] = v[j].z, w0[4 * j + 3] = v[j].w;
+            w1[4 * j] = v[4 + j].x, w1[4 * j + 1] = v[4 + j].y, w1[4 * j + 2] = v[4 + j].z, w1[4 * j + 3] = v[4 + j].w;
+          }
+          __syncwarp();
+          tmem_st_32x16(lane_base + static_cast<uint32_t>(kb * 32), w0);
+          tmem_st_32x16(lane_base + static_cast<uint32_t>(kb * 32 + 16), w1);
+        } else {
+          uint8_t* rowp = sBs + (L >> 3) * 1024 + (L & 7) * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(rowp + ((j ^ (L & 7)) << 4)) = v[j];
+        }
+      }
+      tmem_st_wait();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bready_bar);
+    }
+    // ===== epilogue: K^T row -> bf16 -> RoPE with the partner lane -> shared memory (A operand of the score MMA) =====
+    const bool rope = P.cos_t != nullptr && !(P.dbg & 8);
+    const uint32_t sgn = (L & 1) ? 0u : 0x80008000u;  // dims < 64 take -partner * sin, dims >= 64 take +partner * sin
+    const __nv_bfloat16* crow = rope ? P.cos_t + static_cast<long long>(fi) * P.ld_t : nullptr;
+    const __nv_bfloat16* srow = rope ? P.sin_t + static_cast<long long>(fi) * P.ld_t : nullptr;
+    uint8_t* krow = sK + half * (T_KROT_BYTES / 2) + (dim >> 3) * 1024 + (dim & 7) * 128;
+    const int dsw = dim & 7;
+    int acc = 0;
+    uint32_t acc_ph = 0u;
+    for (int tile = slot; tile < ntiles; tile += nslots) {
+      const long long tok0 = static_cast<long long>(tile) * DBM + half * 64;
+      uint4 cq[2][2], sq[2][2];    // cos / sin words of 16 tokens, double buffered
+      if (rope) {
+        cq[0][0] = __ldg(reinterpret_cast<const uint4*>(crow + tok0));
+        cq[0][1] = __ldg(reinterpret_cast<const uint4*>(crow + tok0) + 1);
+        sq[0][0] = __ldg(reinterpret_cast<const uint4*>(srow + tok0));
+        sq[0][1] = __ldg(reinterpret_cast<const uint4*>(srow + tok0) + 1);
+      }
+      mbar_wait(&tfull_bar[acc], (acc_ph >> acc) & 1u);
+      if (!(P.dbg & 256)) mbar_wait(&kempty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);   // score MMAs of two tiles ago released the buffer
+      tc_fence_after();
+      const uint32_t col0 = lane_base + T_COL_ACC + static_cast<uint32_t>(acc * DBM + half * 64);
+      uint8_t* kdst = krow + acc * T_KROT_BYTES;
+#pragma unroll
+      for (int sc = 0; sc < 4; ++sc) {
+        uint32_t x[16];
+        __syncwarp();
+        if (P.dbg & 16) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[j] = 0u;
+        } else
+        tmem_ld_32x16(col0 + static_cast<uint32_t>(sc * 16), x);
+        if (rope && sc < 3) {
+          cq[(sc + 1) & 1][0] = __ldg(reinterpret_cast<const uint4*>(crow + tok0 + (sc + 1) * 16));
+          cq[(sc + 1) & 1][1] = __ldg(reinterpret_cast<const uint4*>(crow + tok0 + (sc + 1) * 16) + 1);
+          sq[(sc + 1) & 1][0] = __ldg(reinterpret_cast<const uint4*>(srow + tok0 + (sc + 1) * 16));
+          sq[(sc + 1) & 1][1] = __ldg(reinterpret_cast<const uint4*>(srow + tok0 + (sc + 1) * 16) + 1);
+        }
+        tmem_ld_wait();
+        uint32_t o[8];
+        const uint32_t* cw = reinterpret_cast<const uint32_t*>(&cq[sc & 1][0]);
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(&sq[sc & 1][0]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t own = pack_bf16x2(__uint_as_float(x[2 * j]), __uint_as_float(x[2 * j + 1]));
+          uint32_t res = own;
+          if (rope) {
+            const uint32_t par = __shfl_xor_sync(0xffffffffu, own, 1) ^ sgn;
+            const __nv_bfloat162 r = __hadd2(__hmul2(*reinterpret_cast<const __nv_bfloat162*>(&own),
+                                                     *reinterpret_cast<const __nv_bfloat162*>(&cw[j])),
+                                             __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&par),
+                                                     *reinterpret_cast<const __nv_bfloat162*>(&sw[j])));
+            res = *reinterpret_cast<const uint32_t*>(&r);
+          }
+          o[j] = res;
+        }
+        if (!(P.dbg & 2)) {
+        *reinterpret_cast<uint4*>(kdst + (((2 * sc) ^ dsw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(kdst + (((2 * sc + 1) ^ dsw) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      }
+      // the accumulator is drained: hand it back to the reconstruction MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      // rotated keys visible to the tensor core's (async proxy) reads
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&kfull_bar[acc]);
+      acc_ph ^= 1u << acc;
+      acc ^= 1;
+    }
+  } else if (warp >= 4 + T_EPI_WARPS) {
+    // ===== score read-out: one warp per TMEM lane quarter, thread = token =====
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    int b = 0;
+    uint32_t bph = 0u;
+    for (int tile = slot; tile < ntiles; tile += nslots) {
+      const int tok = tile * DBM + row;
+      mbar_wait(&d2full_bar[b], (bph >> b) & 1u);
+      tc_fence_after();
+      uint32_t v[8];
+      __syncwarp();
+      tmem_ld_32x8(tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + T_COL_D2 + static_cast<uint32_t>(b * 16), v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&d2empty_bar[b]);
+      if (tok < P.S) {
+#pragma unroll
+        for (int g = 0; g < D_MAX_QPK; ++g)
+          if (g < P.qpk) P.scores[static_cast<long long>(h * P.qpk + g) * P.ld_scores + tok] = __uint_as_float(v[g]) * P.scale;
+      }
+      bph ^= 1u << b;
+      b ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, T_TMEM_COLS);
+  }
+}
+
+// cos_t[i][t] = cos[t][i], sin_t likewise, for i < D/2 (HF tables repeat the D/2 frequencies in both halves) and
+// t < S; columns [S, ld_t) are zeroed.  32 x 32 tiles through shared memory.
+__global__ void __launch_bounds__(256) rope_tables_dim_major_kernel(const __nv_bfloat16* __restrict__ cos,
+                                                                    const __nv_bfloat16* __restrict__ sin, long long ld_cs,
+                                                                    int S, int half_d, __nv_bfloat16* __restrict__ cos_t,
+                                                                    __nv_bfloat16* __restrict__ sin_t, long long ld_t) {
+  __shared__ __nv_bfloat16 tc[32][33], ts[32][33];
+  const int t0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + r, i = i0 + tx;
+    const bool ok = t < S && i < half_d;
+    tc[r][tx] = ok ? cos[static_cast<long long>(t) * ld_cs + i] : __float2bfloat16(0.f);
+    ts[r][tx] = ok ? sin[static_cast<long long>(t) * ld_cs + i] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r, t = t0 + tx;
+    if (i < half_d && t < ld_t) {
+      cos_t[static_cast<long long>(i) * ld_t + t] = tc[tx][r];
+      sin_t[static_cast<long long>(i) * ld_t + t] = ts[tx][r];
+    }
+  }
+}
+
 // Softmax over L = S + T scores of one q-head, two launches, SM_CHUNKS CTAs per head:
 //   pass 1: per-chunk max (the CTA of the last chunk first scores the T dense tail tokens: scale * q . k_tail)
 //   pass 2: global max from the chunk maxima, p = exp(s - max) written as bf16 (the GEMM operand),
@@ -1147,8 +1495,13 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
                                     const void* Vv_layer, int64_t ldv_v, int S, const void* cos, const void* sin,
                                     int64_t ld_cs, const void* k_tail, const void* v_tail, int T, int64_t tail_stride_h,
                                     int64_t tail_stride_t, float scale, void* out, void* workspace,
-                                    size_t workspace_bytes, void* stream) {
+                                    size_t workspace_bytes, const void* cos_t, const void* sin_t, int64_t ld_t,
+                                    void* stream) {
   XKV_REQUIRE(q && A_k && Vk_layer && A_v && Vv_layer && out && workspace, "decode: null argument");
+  XKV_REQUIRE((cos_t == nullptr) == (sin_t == nullptr), "decode: cos_t and sin_t must both be given or both be null");
+  XKV_REQUIRE(cos_t == nullptr || (cos != nullptr && ld_t % 128 == 0 && ld_t >= S &&
+                                   (reinterpret_cast<uintptr_t>(cos_t) & 15) == 0 && (reinterpret_cast<uintptr_t>(sin_t) & 15) == 0),
+              "decode: dim-major RoPE tables need cos/sin, 16-byte alignment and a row stride that is a multiple of 128 >= S");
   XKV_REQUIRE(D == 64 || D == 128, "decode: head_dim %d not supported (64 or 128)", D);
   XKV_REQUIRE(H >= 1 && Hq % H == 0 && Hq / H <= D_MAX_QPK && Hq <= 128, "decode: unsupported head counts Hq=%d H=%d", Hq, H);
   XKV_REQUIRE(S >= 1 && T >= 0 && rk >= 1 && rv >= 1 && rv % 2 == 0, "decode: bad sizes");
@@ -1196,6 +1549,11 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
   sp.q = static_cast<const __nv_bfloat16*>(q);
   sp.cos = static_cast<const __nv_bfloat16*>(cos);
   sp.sin = static_cast<const __nv_bfloat16*>(sin);
+  sp.cos_t = static_cast<const __nv_bfloat16*>(cos_t);
+  sp.sin_t = static_cast<const __nv_bfloat16*>(sin_t);
+  sp.ld_t = ld_t;
+  sp.bk = static_cast<const __nv_bfloat16*>(Vk_layer);
+  sp.ld_bk = ldv_k;
   sp.scores = scores;
   sp.ld_cs = ld_cs;
   sp.ld_scores = ldl;
@@ -1206,6 +1564,10 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
   sp.tiles_n = (H * D + DBN - 1) / DBN;
   sp.nkb = (rk + DBK - 1) / DBK;
   sp.scale = scale;
+  {
+    const char* e = getenv("XKV_DECODE_DBG");
+    sp.dbg = e ? atoi(e) : 0;
+  }
   const int grid = ((S + DBM - 1) / DBM) * sp.tiles_n;
   static bool configured = false;
   if (!configured) {
@@ -1234,6 +1596,7 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
     if (pgrid < H) pgrid = H;   // every head needs at least one CTA
     static const bool pair_env = getenv("XKV_DECODE_PAIR") != nullptr;   // opt-in: measured 99 us vs 92 us for the single-CTA kernel
     const bool pair_off = !(pair_env || g_scores_variant == 3);
+    static const bool tr_default = getenv("XKV_DECODE_TR") != nullptr;   // transposed kernel: opt-in while it is slower
     const int ntp = (S + 2 * DBM - 1) / (2 * DBM);
     if (D == 128 && q_tma_ok && qpk <= 8 && !pair_off && sms >= 2 * H &&
         static_cast<size_t>(sp.nkb) * 64 * DBK * 2 <= static_cast<size_t>(Q_BHALF_BYTES)) {
@@ -1261,6 +1624,17 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       XKV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_scores_pair_kernel, sp));
+    } else if (D == 128 && q_tma_ok && qpk <= 8 && (g_scores_variant == 4 || (g_scores_variant == 0 && tr_default)) &&
+               sp.nkb <= T_MAX_KB_TMEM + 1 && rk % 8 == 0 && ldv_k % 8 == 0 &&
+               (reinterpret_cast<uintptr_t>(Vk_layer) & 15) == 0 && (cos == nullptr || cos_t != nullptr)) {
+      // right factor resident in TMEM, token stream as the shared-memory operand
+      static bool tconf = false;
+      if (!tconf) {
+        XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_tr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(T_SMEM_BYTES)));
+        tconf = true;
+      }
+      decode_scores_tr_kernel<<<pgrid, T_THREADS, T_SMEM_BYTES, st>>>(sp);
     } else if (D == 128 && q_tma_ok && qpk <= 8 && g_scores_variant != 1) {
       static bool rconf = false;
       if (!rconf) {
@@ -1331,6 +1705,19 @@ extern "C" int xkv_rope_bf16(void* x, int64_t ld_row, int rows, int H, int D, co
 }
 
 /* test hook: 1 forces the tile-per-CTA scores kernel, 0 restores the automatic choice */
+extern "C" int xkv_rope_tables_dim_major(const void* cos, const void* sin, int64_t ld_cs, int S, int D, void* cos_t,
+                                         void* sin_t, int64_t ld_t, void* stream) {
+  XKV_REQUIRE(cos && sin && cos_t && sin_t, "rope tables: null argument");
+  XKV_REQUIRE(S >= 1 && D >= 2 && D % 2 == 0 && ld_t >= S, "rope tables: bad sizes");
+  dim3 grid(static_cast<unsigned>((ld_t + 31) / 32), static_cast<unsigned>((D / 2 + 31) / 32));
+  rope_tables_dim_major_kernel<<<grid, 256, 0, as_stream(stream)>>>(
+      static_cast<const __nv_bfloat16*>(cos), static_cast<const __nv_bfloat16*>(sin), ld_cs, S, D / 2,
+      static_cast<__nv_bfloat16*>(cos_t), static_cast<__nv_bfloat16*>(sin_t), ld_t);
+  XKV_LAUNCHED();
+  XKV_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" void xkv_decode_force_tiled(int on) { g_force_tiled_scores = on != 0; }
 /* test hook: which persistent scores kernel to use when several apply (0 automatic) */
 extern "C" void xkv_decode_set_variant(int variant) { g_scores_variant = variant; }

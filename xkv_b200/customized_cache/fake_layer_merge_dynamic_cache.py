@@ -76,7 +76,7 @@ class _GroupState:
     """Factors of one compressed group and the RoPE tables of its prefill positions."""
 
     def __init__(self, info: LayerGroup, factors: compress.GroupFactors, heads: int, head_dim: int,
-                 cos: Optional[torch.Tensor], sin: Optional[torch.Tensor], re_apply_rope: bool):
+                 cos: Optional[torch.Tensor], sin: Optional[torch.Tensor], re_apply_rope: bool, prefill_len: int = 0):
         self.info = info
         self.factors = factors
         self.heads = heads
@@ -84,6 +84,10 @@ class _GroupState:
         self.cos = cos      # (S, D) bf16 or None
         self.sin = sin
         self.re_apply_rope = re_apply_rope
+        # dim-major copies of the tables for the decode kernel that keeps the right factor in tensor memory
+        self.rope_t = None
+        if re_apply_rope and cos is not None and head_dim == 128:
+            self.rope_t = ops.rope_tables_dim_major(cos[:prefill_len], sin[:prefill_len], capacity=cos.shape[0])
 
 
 class FakeLayerMergingCache(DynamicCache):
@@ -190,7 +194,7 @@ class FakeLayerMergingCache(DynamicCache):
             sn = torch.empty_like(cs)
             cs[:seq] = cos[0]
             sn[:seq] = sin[0]
-        state = _GroupState(info, gf, self.num_heads, self.head_dim, cs, sn, bool(re_rope))
+        state = _GroupState(info, gf, self.num_heads, self.head_dim, cs, sn, bool(re_rope), prefill_len=seq)
         state.length = seq
         state.layer_ids = ids
         self._groups[first] = state
@@ -301,7 +305,7 @@ class FakeLayerMergingCache(DynamicCache):
             query[0, :, 0, :], fk.A_storage[:n_tok], fk.V[rows], fv.A_storage[:n_tok], fv.V[rows], h,
             st.cos[:n_tok] if st.re_apply_rope else None, st.sin[:n_tok] if st.re_apply_rope else None,
             layer.tail_k[0, :, : layer.tail_len], layer.tail_v[0, :, : layer.tail_len], scaling,
-            workspace=self._workspace)
+            workspace=self._workspace, rope_t=st.rope_t if st.re_apply_rope else None)
         if fold and layer_idx == st.layer_ids[-1]:
             self._fold_tail(st, cos, sin)
         return out[None, :, None, :]
@@ -325,6 +329,10 @@ class FakeLayerMergingCache(DynamicCache):
         if st.re_apply_rope and cos is not None:
             st.cos[st.length: st.length + t] = cos.reshape(-1, cos.shape[-1])[-t:]
             st.sin[st.length: st.length + t] = sin.reshape(-1, sin.shape[-1])[-t:]
+            if st.rope_t is not None:
+                half = st.head_dim // 2
+                st.rope_t[0][:, st.length: st.length + t] = st.cos[st.length: st.length + t, :half].t()
+                st.rope_t[1][:, st.length: st.length + t] = st.sin[st.length: st.length + t, :half].t()
         st.length += t
         for l in layers:
             l.prefill_len = st.length
