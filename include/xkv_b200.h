@@ -77,6 +77,9 @@ typedef struct xkv_gemm_problem {
   int32_t sym_upper;       /* 1: compute only tiles that intersect the upper triangle (Gram) */
   int32_t split_k;         /* >= 1: split s accumulates k-blocks of its slice into D + s*split_stride */
   int64_t split_stride;    /* elements */
+  int32_t accum_phases;    /* > 1: the k range of a CTA is accumulated in this many sequential pieces that are summed in
+                            * fp32 outside the tensor core (long reductions: the Gram over 64K tokens); fp32 output only */
+  const int32_t* run_if;   /* optional DEVICE flag (NULL = always): the problem is skipped when *run_if == 0 at run time */
 } xkv_gemm_problem;
 XKV_API int xkv_gemm_grouped(const xkv_gemm_problem* problems_host, int num_problems, void* stream);
 
@@ -117,6 +120,14 @@ XKV_API int xkv_ritz_shift_update(float* const* rdiag_host, int batch, int rows,
                                   float* shift_dev, void* stream);
 XKV_API int xkv_rdiag_update(float* const* rdiag_host, const float* const* Linv_host, int batch, int rows,
                              int64_t ld_linv, void* stream);
+/* Device-side conditional passes.  xkv_pass_flags: flags_dev[b] = 1 when the Cholesky pass that produced Linv[b] met
+ * a pivot L_jj^2 < min_pivot (or a NaN), else 0.  xkv_set_launch_predicate(flags_dev): until reset with NULL, the
+ * calling thread's batched launches of xkv_shift_normalize_rows, xkv_reduce_slabs_batched,
+ * xkv_cholesky_inverse(_limbs) and xkv_rdiag_update skip matrix b when flags_dev[b] == 0 at run time (GEMM problems
+ * carry their own xkv_gemm_problem.run_if).  No host synchronisation: the kernels are always enqueued. */
+XKV_API int xkv_pass_flags(const float* const* Linv_host, int batch, int rows, int64_t ld_linv, float min_pivot,
+                           int32_t* flags_dev, void* stream);
+XKV_API void xkv_set_launch_predicate(const int32_t* flags_dev);
 /* Batched blocked Cholesky (S + shift*I) = L L^T of l x l fp32 matrices (l % 64 == 0, symmetric, both
  * triangles present, unit diagonal expected) with explicit inverse Linv = L^{-1} (dense l x l, zero above the
  * diagonal).  One launch: a thread-block cluster per matrix (xkv_chol.cu).  S is scratch and is destroyed.
@@ -161,6 +172,8 @@ typedef struct xkv_factorize_options {
   int32_t rayleigh_ritz;  /* 0: keep the first `rank` basis vectors as they are */
   int32_t want_sigma;     /* also diagonalise the leading window to report singular values */
   int32_t gram_split_k;
+  int32_t gram_chunk_tokens; /* the Gram is accumulated on the tensor core over pieces of this many tokens which are summed
+                              * in fp32 by the epilogue (xkv_gemm_problem.accum_phases); 0 = one piece (default 16384) */
   int32_t small_split_k;
   float shifts[4];        /* diagonal shift of CholeskyQR pass 0,1,2,3+ */
   float pivot_floor;
@@ -168,6 +181,9 @@ typedef struct xkv_factorize_options {
   int32_t shift_tail;     /* trailing entries of diag(R) of the previous step that estimate lambda_l (8) */
   int32_t single_pass_from; /* power steps with index >= this (> 0) orthonormalise with ONE CholeskyQR pass (small shift, 6-term Gram); 0 = never */
   int32_t single_pass_last; /* 1: the last power step may use the single pass too */
+  float second_pass_min_pivot; /* a single-pass step runs a second pass ON DEVICE DECISION for every matrix whose first
+                                * pass met a Cholesky pivot below this (ill-conditioned: steep spectrum at high rank);
+                                * 0 = never (default 0.05) */
   uint64_t seed;
 } xkv_factorize_options;
 XKV_API void xkv_factorize_default_options(xkv_factorize_options* opts);

@@ -79,6 +79,23 @@ def test_steep_spectrum_at_high_rank_meets_the_bf16_storage_floor():
     assert e_ours ** 2 <= (1.01 * e_ref) ** 2 + 3e-3 ** 2
 
 
+@pytest.mark.parametrize("min_pivot", [0.0, 0.05, 2.0])
+def test_device_decided_second_pass(min_pivot):
+    """Single-pass power steps add a second CholeskyQR pass per matrix on a DEVICE decision (Cholesky pivot below
+    `second_pass_min_pivot`).  0 = never, 2.0 = always (pivots of a unit-diagonal Gram are <= 1), 0.05 = the default.
+    A batch mixing a benign and a steep matrix must meet the bar for both under the default; the benign one under all."""
+    from xkv_b200 import factorize, synthetic
+
+    xs = [synthetic.group_matrix(2048, 4096, a, seed=77 + i, device="cuda") for i, a in enumerate((0.5, 1.0))]
+    fs = factorize.factorize_batch(xs, 512, factorize.FactorizeOptions(second_pass_min_pivot=min_pivot))
+    torch.cuda.synchronize()
+    for x, f, a in zip(xs, fs, (0.5, 1.0)):
+        ref_hat, _ = _ref_fake_svd(x, 512)
+        e_ref, e_ours = _rel_err(x, ref_hat), _rel_err(x, f.reconstruct())
+        print(f"min_pivot={min_pivot} alpha={a}: err ref={e_ref:.6f} ours={e_ours:.6f} ratio={e_ours / e_ref:.5f}")
+        assert e_ours <= 1.01 * e_ref
+
+
 def test_batch_of_two_ranks_shapes_and_determinism():
     from xkv_b200 import factorize, synthetic
 

@@ -16,7 +16,8 @@ def _mk(rows, cols, ints, seed):
     return torch.randn(rows, cols, device="cuda", generator=g).bfloat16()
 
 
-def _run(M, N, K, a_mn, b_mn, ints=False, terms=None, transposed=False, out_bf16=False, split_k=1, sym=False):
+def _run(M, N, K, a_mn, b_mn, ints=False, terms=None, transposed=False, out_bf16=False, split_k=1, sym=False,
+         phases=1):
     from xkv_b200 import ops
 
     terms = terms or ops.TERMS_1
@@ -36,7 +37,7 @@ def _run(M, N, K, a_mn, b_mn, ints=False, terms=None, transposed=False, out_bf16
     out = torch.full((split_k,) + shape, float("nan"), device="cuda", dtype=dt)
     p = ops.make_problem(A, B, out[0], M=M, N=N, K=K, a_mn_major=a_mn, b_mn_major=b_mn, terms=terms,
                          out_transposed=transposed, sym_upper=sym, split_k=split_k,
-                         split_stride=out.stride(0))
+                         split_stride=out.stride(0), accum_phases=phases)
     ops.gemm_grouped([p])
     torch.cuda.synchronize()
     got = out.float().sum(0)
@@ -110,6 +111,45 @@ def test_symmetric_gram_tiles():
     # G = X^T X with X (K x n) row-major: both operands MN-major views of the same matrix
     got, ref = _run(768, 768, 1024, True, True, ints=True, sym=True, split_k=2)
     _check(got, ref, exact=True, sym=True)
+
+
+@pytest.mark.parametrize("phases", [2, 3, 5, 64])
+def test_accumulation_phases_exact(phases):
+    """The k range cut into pieces that alternate between two TMEM accumulators and are summed by the epilogue
+    (the Gram over long token ranges): exact on integer data for even / odd piece counts, more pieces than k-blocks
+    (K = 1100 -> 18 k-blocks), ragged tiles, the symmetric tile set and split-K on top."""
+    got, ref = _run(200, 328, 1100, True, True, ints=True, phases=phases)
+    _check(got, ref, exact=True)
+    got, ref = _run(768, 768, 2048, True, True, ints=True, sym=True, split_k=2, phases=phases)
+    _check(got, ref, exact=True, sym=True)
+    from xkv_b200 import ops
+
+    got, ref = _run(256, 256, 1024, False, False, ints=True, terms=ops.TERMS_6, phases=phases)
+    _check(got, ref, exact=True)
+
+
+def test_accumulation_phases_need_fp32_output():
+    from xkv_b200 import _lib
+
+    with pytest.raises(_lib.XkvError):
+        _run(256, 512, 256, False, False, out_bf16=True, phases=2)
+
+
+def test_run_if_predicate_skips_a_problem():
+    from xkv_b200 import ops
+
+    a, b = _mk(128, 64, True, 1), _mk(256, 64, True, 2)
+    flags = torch.tensor([0, 1], device="cuda", dtype=torch.int32)
+    outs = [torch.full((128, 256), float("nan"), device="cuda") for _ in range(2)]
+    ps = []
+    for i, o in enumerate(outs):
+        p = ops.make_problem([a], [b], o, M=128, N=256, K=64)
+        p.run_if = flags[i:].data_ptr()
+        ps.append(p)
+    ops.gemm_grouped(ps)
+    torch.cuda.synchronize()
+    assert torch.isnan(outs[0]).all()                       # flag 0: untouched
+    assert torch.equal(outs[1], a.float() @ b.float().t())  # flag 1: computed
 
 
 def test_grouped_launch():

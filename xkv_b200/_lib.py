@@ -44,6 +44,8 @@ class GemmProblem(C.Structure):
         ("sym_upper", C.c_int32),
         ("split_k", C.c_int32),
         ("split_stride", C.c_int64),
+        ("accum_phases", C.c_int32),
+        ("run_if", C.c_void_p),
     ]
 
 
@@ -61,6 +63,7 @@ class FactorizeOptions(C.Structure):
         ("rayleigh_ritz", C.c_int32),
         ("want_sigma", C.c_int32),
         ("gram_split_k", C.c_int32),
+        ("gram_chunk_tokens", C.c_int32),
         ("small_split_k", C.c_int32),
         ("shifts", C.c_float * 4),
         ("pivot_floor", C.c_float),
@@ -68,6 +71,7 @@ class FactorizeOptions(C.Structure):
         ("shift_tail", C.c_int32),
         ("single_pass_from", C.c_int32),
         ("single_pass_last", C.c_int32),
+        ("second_pass_min_pivot", C.c_float),
         ("seed", C.c_uint64),
     ]
 
@@ -91,6 +95,8 @@ SIGNATURES = {
     "xkv_shift_normalize_rows": (_i, [_pp, _pp, _vp, _pp, _i, _pp, _pp, _pp, _i, _i, _i, _i64, _i64, _vp]),
     "xkv_ritz_shift_update": (_i, [_pp, _i, _i, _i, _f, _vp, _vp]),
     "xkv_rdiag_update": (_i, [_pp, _pp, _i, _i, _i64, _vp]),
+    "xkv_pass_flags": (_i, [_pp, _i, _i, _i64, C.c_float, _vp, _vp]),
+    "xkv_set_launch_predicate": (None, [_vp]),
     "xkv_cholesky_inverse": (_i, [_pp, _pp, _i, _i, _i64, _f, _f, _vp]),
     "xkv_cholesky_inverse_limbs": (_i, [_pp, _pp, _pp, _pp, _pp, _i, _i, _i64, _i64, _f, _f, _vp]),
     "xkv_jacobi_eigh": (_i, [_pp, _pp, _pp, _i, _i, _i64, _i64, _i, _vp]),

@@ -46,6 +46,7 @@ struct CholFusedParams {
   int l, nblk;
   long long ld, ld_limb;
   float pivot_floor, shift;
+  const int* run_if;   // optional per-matrix device predicate (xkv_set_launch_predicate): the whole cluster exits
 };
 
 __device__ __forceinline__ void split3f(float x, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
@@ -258,6 +259,7 @@ __device__ __forceinline__ void run_products(Gen& gen, float* bufs, const float*
 
 __global__ void __launch_bounds__(CH_THREADS, 1) chol_cluster_kernel(const __grid_constant__ CholFusedParams p) {
   extern __shared__ __align__(16) float chol_sm[];
+  if (p.run_if != nullptr && p.run_if[blockIdx.y] == 0) return;   // uniform over the cluster, before any barrier
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = static_cast<int>(cluster.num_blocks());
   const int c = static_cast<int>(cluster.block_rank());
@@ -469,6 +471,7 @@ extern "C" int xkv_cholesky_inverse_limbs(float* const* S_host, float* const* Li
   p.ld_limb = ld_limb;
   p.pivot_floor = pivot_floor;
   p.shift = shift;
+  p.run_if = launch_predicate();
   const int smem = CH_SMEM_FLOATS * static_cast<int>(sizeof(float));
   static bool attr_set = false;
   if (!attr_set) {

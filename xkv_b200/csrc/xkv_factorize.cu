@@ -58,6 +58,7 @@ struct Plan {
   // shared
   float* gram_slabs;  // [B][gs][n][n]
   float* shift_dev;   // [B] spectral shifts of the current power step
+  int* pass_flags;    // [B] device decision: this matrix needs a second CholeskyQR pass in the current step
   float* g32;
   size_t bytes;
 };
@@ -124,6 +125,7 @@ static int make_plan(Plan& P, Bump& bump, int B, int m, int n, int rank, const x
   P.gram_slabs = bump.f32(static_cast<size_t>(B) * P.gs * nn * nn);
   P.g32 = bump.f32(nn * nn);
   P.shift_dev = bump.f32(XKV_MAX_BATCH);
+  P.pass_flags = reinterpret_cast<int*>(bump.f32(XKV_MAX_BATCH));
   P.bytes = align_up(bump.off, 1024);
   return 0;
 }
@@ -191,6 +193,7 @@ extern "C" void xkv_factorize_default_options(xkv_factorize_options* o) {
   o->shift_tail = 8;
   o->single_pass_from = 1;
   o->single_pass_last = 1;
+  o->second_pass_min_pivot = 0.05f;
   o->oversample = 64;
   o->first_passes = 2;
   o->passes = 2;
@@ -200,6 +203,7 @@ extern "C" void xkv_factorize_default_options(xkv_factorize_options* o) {
   o->rayleigh_ritz = 1;
   o->want_sigma = 1;
   o->gram_split_k = 1;
+  o->gram_chunk_tokens = 16384;
   o->small_split_k = 8;
   o->shifts[0] = 3e-4f;
   o->shifts[1] = 1e-6f;
@@ -276,6 +280,11 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
       p.sym_upper = 1;
       p.split_k = P.gs;
       p.split_stride = nn * nn;
+      if (o.gram_chunk_tokens > 0) {
+        const int per_split = (m + P.gs - 1) / P.gs;
+        const int ph = (per_split + o.gram_chunk_tokens - 1) / o.gram_chunk_tokens;
+        p.accum_phases = ph > 64 ? 64 : ph;
+      }
       ps.push_back(p);
     }
     XKV_TRY(run_gemms(ps, stream));
@@ -302,35 +311,54 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
   // cur <- orth(cur): row-normalised, shifted CholeskyQR
   // With `shifted`, cur = Q_prev G and nxt still holds Q_prev: the first pass first forms Q_prev (G - c I).
   // With `track`, diag(R) of the step is accumulated in P.rdiag (row norms x Cholesky diagonals).
-  auto cholqr = [&](int npass, bool shifted, bool track, int p0) -> int {
-    for (int ip = 0; ip < npass; ++ip) {
+  // `conditional_extra`: after the npass passes the device decides per matrix (xkv_pass_flags on the last pass's
+  // Cholesky pivots) whether one more pass runs; its kernels are always enqueued and exit at once for the matrices
+  // that do not need it.  That pass writes its result over `cur` (its operands are the limb copies), so the
+  // buffers are where the following stages expect them either way.
+  auto cholqr = [&](int npass, bool shifted, bool track, int p0, bool conditional_extra) -> int {
+    const int total = npass + (conditional_extra ? 1 : 0);
+    for (int ip = 0; ip < total; ++ip) {
       const int pp = ip + p0;  // index into the per-pass parameters (shift, limb terms)
-      XKV_TRY(xkv_shift_normalize_rows(cur, (ip == 0 && shifted) ? nxt : nullptr, P.shift_dev, track ? P.rdiag : nullptr,
-                                       ip == 0, P.lh, P.lm, P.ll, B, l, n, nn, nn, stream));
-      // pass 0 is regularised by a 3e-4 shift, so the 3-term product (error ~1e-5) is accurate enough there
-      const int nt = pp == 0 ? 3 : 6;
-      for (int b = 0; b < B; ++b) {
-        xkv_gemm_problem p = problem(P.lh[b], P.lm[b], P.ll[b], nn, 0, P.lh[b], P.lm[b], P.ll[b], nn, 0, P.s_slabs[b], l,
-                                     l, l, n, nt);
-        p.sym_upper = 1;
-        p.split_k = P.sk;
-        p.split_stride = static_cast<long long>(l) * l;
-        ps.push_back(p);
+      const bool cond = conditional_extra && ip == npass;
+      if (cond) {
+        XKV_TRY(xkv_pass_flags(P.linv, B, l, l, o.second_pass_min_pivot, P.pass_flags, stream));
+        xkv_set_launch_predicate(P.pass_flags);
       }
-      XKV_TRY(run_gemms(ps, stream));
-      XKV_TRY(xkv_reduce_slabs_batched(P.s_slabs, P.s_mat, B, P.sk, static_cast<long long>(l) * l, l, l, l, 1, l, stream));
-      {
-        void *h0[XKV_MAX_BATCH], *h1[XKV_MAX_BATCH], *h2[XKV_MAX_BATCH];
-        for (int b = 0; b < B; ++b) h0[b] = P.linv_l[b][0], h1[b] = P.linv_l[b][1], h2[b] = P.linv_l[b][2];
-        XKV_TRY(xkv_cholesky_inverse_limbs(P.s_mat, P.linv, h0, h1, nt > 3 ? h2 : nullptr, B, l, l, l,
-                                           o.shifts[pp < 3 ? pp : 3], o.pivot_floor, stream));
-      }
-      if (track) XKV_TRY(xkv_rdiag_update(P.rdiag, P.linv, B, l, l, stream));
-      for (int b = 0; b < B; ++b)
-        ps.push_back(problem(P.linv_l[b][0], P.linv_l[b][1], P.linv_l[b][2], l, 0, P.lh[b], P.lm[b], P.ll[b], nn, 1,
-                             nxt[b], nn, l, n, l, nt));
-      XKV_TRY(run_gemms(ps, stream));
-      swap_bufs();
+      int rc = [&]() -> int {
+        XKV_TRY(xkv_shift_normalize_rows(cur, (ip == 0 && shifted) ? nxt : nullptr, P.shift_dev,
+                                         track ? P.rdiag : nullptr, ip == 0, P.lh, P.lm, P.ll, B, l, n, nn, nn, stream));
+        // pass 0 is regularised by a 3e-4 shift, so the 3-term product (error ~1e-5) is accurate enough there
+        const int nt = pp == 0 ? 3 : 6;
+        for (int b = 0; b < B; ++b) {
+          xkv_gemm_problem p = problem(P.lh[b], P.lm[b], P.ll[b], nn, 0, P.lh[b], P.lm[b], P.ll[b], nn, 0, P.s_slabs[b],
+                                       l, l, l, n, nt);
+          p.sym_upper = 1;
+          p.split_k = P.sk;
+          p.split_stride = static_cast<long long>(l) * l;
+          p.run_if = cond ? P.pass_flags + b : nullptr;
+          ps.push_back(p);
+        }
+        XKV_TRY(run_gemms(ps, stream));
+        XKV_TRY(xkv_reduce_slabs_batched(P.s_slabs, P.s_mat, B, P.sk, static_cast<long long>(l) * l, l, l, l, 1, l, stream));
+        {
+          void *h0[XKV_MAX_BATCH], *h1[XKV_MAX_BATCH], *h2[XKV_MAX_BATCH];
+          for (int b = 0; b < B; ++b) h0[b] = P.linv_l[b][0], h1[b] = P.linv_l[b][1], h2[b] = P.linv_l[b][2];
+          XKV_TRY(xkv_cholesky_inverse_limbs(P.s_mat, P.linv, h0, h1, nt > 3 ? h2 : nullptr, B, l, l, l,
+                                             o.shifts[pp < 3 ? pp : 3], o.pivot_floor, stream));
+        }
+        if (track) XKV_TRY(xkv_rdiag_update(P.rdiag, P.linv, B, l, l, stream));
+        for (int b = 0; b < B; ++b) {
+          xkv_gemm_problem p = problem(P.linv_l[b][0], P.linv_l[b][1], P.linv_l[b][2], l, 0, P.lh[b], P.lm[b], P.ll[b], nn,
+                                       1, cond ? cur[b] : nxt[b], nn, l, n, l, nt);
+          p.run_if = cond ? P.pass_flags + b : nullptr;
+          ps.push_back(p);
+        }
+        XKV_TRY(run_gemms(ps, stream));
+        return 0;
+      }();
+      if (cond) xkv_set_launch_predicate(nullptr);
+      if (rc) return rc;
+      if (!cond) swap_bufs();
     }
     return 0;
   };
@@ -347,7 +375,7 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
   // ---- 2-3. Gaussian range finder ----
   for (int b = 0; b < B; ++b) XKV_TRY(xkv_fill_gaussian_bf16(P.lh[b], l, n, nn, o.seed + 7919ull * b, stream));
   XKV_TRY(apply_gram(1));
-  XKV_TRY(cholqr(o.first_passes, false, false, 0));
+  XKV_TRY(cholqr(o.first_passes, false, false, 0, false));
   XKV_TRY(mark());  // 3: range finder
 
   // ---- 4. power steps ----
@@ -368,7 +396,7 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
     const bool last = it == o.power_iters - 1;
     const bool single = o.single_pass_from > 0 && it >= o.single_pass_from && !(last && o.final_passes > 1 && o.single_pass_last == 0);
     XKV_TRY(cholqr(single ? 1 : (last ? o.final_passes : o.passes), shifted, use_shift && it + 1 < o.power_iters,
-                   single ? 1 : 0));
+                   single ? 1 : 0, single && o.second_pass_min_pivot > 0.f));
   }
   XKV_TRY(mark());  // 4: power iterations
 

@@ -18,6 +18,10 @@ char* error_buffer();
 int set_error(const char* fmt, ...);
 extern std::atomic<long long> g_launch_count;
 
+// Device predicate of the calling thread's next batched launches (normalise, batched slab reduction, Cholesky,
+// rdiag update): matrix b is skipped when flags[b] == 0.  nullptr (the default) = unconditional.
+const int*& launch_predicate();
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 #define XKV_CHECK_CUDA(expr)                                                                        \

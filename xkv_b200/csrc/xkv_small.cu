@@ -17,12 +17,14 @@ static int sm_count();
 struct ReduceParams {
   const float* slabs[XKV_MAX_BATCH];
   float* out[XKV_MAX_BATCH];
+  const int* run_if;   // optional per-matrix device predicate (xkv_set_launch_predicate)
 };
 template <int SYM>
 __global__ void __launch_bounds__(256) reduce_slabs_kernel(const __grid_constant__ ReduceParams rp, int num_slabs,
                                                            long long slab_stride, int rows, int cols, long long ld,
                                                            long long ldo, int tiles_per_row) {
   __shared__ float tile[32][33];
+  if (rp.run_if != nullptr && rp.run_if[blockIdx.y] == 0) return;
   const float* __restrict__ slabs = rp.slabs[blockIdx.y];
   float* __restrict__ out = rp.out[blockIdx.y];
   int bi, bj;
@@ -148,6 +150,9 @@ struct NormParams {
   int rows, cols, tail, rdiag_first;
   float shift_scale;
   long long ld, ldo, ld_linv;
+  const int* run_if;               // optional per-matrix device predicate (xkv_set_launch_predicate)
+  int* flags;                      // pass_flag_kernel output
+  float inv_min_pivot;
 };
 
 // Spectral shift of the power steps.  Orthogonal iteration Y = Q (G - c I) = R^T Q_new makes diag(R) converge
@@ -174,15 +179,32 @@ __global__ void __launch_bounds__(256) ritz_shift_kernel(const __grid_constant__
 }
 // rdiag[j] /= Linv[j][j]  (the Cholesky diagonal L_jj = 1 / Linv_jj of the pass that just finished)
 __global__ void __launch_bounds__(256) rdiag_update_kernel(const __grid_constant__ NormParams p) {
+  if (p.run_if != nullptr && p.run_if[blockIdx.y] == 0) return;
   float* rd = p.rdiag[blockIdx.y];
   const float* li = p.Linv[blockIdx.y];
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < p.rows) rd[j] = rd[j] / li[static_cast<long long>(j) * p.ld_linv + j];
 }
 
+// flags[b] = 1 when the Cholesky pass that just finished met a pivot L_jj^2 < min_pivot (S has a unit diagonal, so the
+// pivot is the squared sine of the angle between row j and the span of the rows before it): the pass was then
+// ill-conditioned, its output is orthonormal only to ~ eps / pivot, and a second pass is worth its cost.  A NaN
+// diagonal raises the flag too.
+__global__ void __launch_bounds__(256) pass_flag_kernel(const __grid_constant__ NormParams p) {
+  const float* li = p.Linv[blockIdx.x];
+  int bad = 0;
+  for (int j = threadIdx.x; j < p.rows; j += blockDim.x) {
+    const float d = li[static_cast<long long>(j) * p.ld_linv + j];   // 1 / L_jj
+    if (!(d * d <= p.inv_min_pivot)) bad = 1;
+  }
+  bad = __syncthreads_or(bad);
+  if (threadIdx.x == 0) p.flags[blockIdx.x] = bad ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(256) normalize_rows_kernel(const __grid_constant__ NormParams p) {
   __shared__ float red[8];
   __shared__ float scale_s;
+  if (p.run_if != nullptr && p.run_if[blockIdx.y] == 0) return;
   float* row = p.Y[blockIdx.y] + static_cast<long long>(blockIdx.x) * p.ld;
   const int cols4 = p.cols >> 2;
   float acc = 0.f;
@@ -403,9 +425,32 @@ static int sm_count() {
   return sms;
 }
 
+const int*& launch_predicate() {
+  static thread_local const int* pred = nullptr;
+  return pred;
+}
+
 }  // namespace xkv
 
 using namespace xkv;
+
+extern "C" void xkv_set_launch_predicate(const int32_t* flags_dev) { launch_predicate() = flags_dev; }
+
+extern "C" int xkv_pass_flags(const float* const* Linv_host, int batch, int rows, int64_t ld_linv, float min_pivot,
+                              int32_t* flags_dev, void* stream) {
+  XKV_REQUIRE(Linv_host && flags_dev && batch >= 1 && batch <= XKV_MAX_BATCH, "pass_flags: bad arguments");
+  XKV_REQUIRE(min_pivot > 0.f, "pass_flags: min_pivot must be positive");
+  NormParams p;
+  std::memset(&p, 0, sizeof(p));
+  for (int b = 0; b < batch; ++b) p.Linv[b] = Linv_host[b];
+  p.rows = rows;
+  p.ld_linv = ld_linv;
+  p.flags = flags_dev;
+  p.inv_min_pivot = 1.f / min_pivot;
+  pass_flag_kernel<<<batch, 256, 0, as_stream(stream)>>>(p);
+  XKV_LAUNCHED();
+  return 0;
+}
 
 extern "C" int xkv_reduce_slabs_batched(const float* const* slabs_host, float* const* out_host, int batch, int num_slabs,
                                         int64_t slab_stride, int rows, int cols, int64_t ld, int symmetrize,
@@ -419,6 +464,7 @@ extern "C" int xkv_reduce_slabs_batched(const float* const* slabs_host, float* c
     rp.slabs[b] = slabs_host[b];
     rp.out[b] = out_host[b];
   }
+  rp.run_if = launch_predicate();
   const int tr = (rows + 31) / 32, tc = (cols + 31) / 32;
   if (symmetrize) {
     XKV_REQUIRE(rows == cols, "reduce_slabs: symmetrize needs a square matrix");
@@ -528,6 +574,7 @@ extern "C" int xkv_shift_normalize_rows(float* const* Y_host, const float* const
   p.rdiag_first = rdiag_first;
   p.ld = ld;
   p.ldo = ld_out;
+  p.run_if = launch_predicate();
   normalize_rows_kernel<<<dim3(rows, batch), 256, 0, as_stream(stream)>>>(p);
   XKV_LAUNCHED();
   return 0;
@@ -560,6 +607,7 @@ extern "C" int xkv_rdiag_update(float* const* rdiag_host, const float* const* Li
   }
   p.rows = rows;
   p.ld_linv = ld_linv;
+  p.run_if = launch_predicate();
   rdiag_update_kernel<<<dim3((rows + 255) / 256, batch), 256, 0, as_stream(stream)>>>(p);
   XKV_LAUNCHED();
   return 0;

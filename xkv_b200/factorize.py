@@ -53,6 +53,7 @@ class FactorizeOptions:
     rayleigh_ritz: bool = True
     want_sigma: bool = True    # also diagonalise the leading window to report singular values
     gram_split_k: int = 1
+    gram_chunk_tokens: int = 16384  # tensor-core accumulation length of the Gram; pieces are summed in fp32 by the epilogue
     small_split_k: int = 8
     shifts: tuple = (3e-4, 1e-6, 1e-7)   # diagonal shift of CholeskyQR pass 0, 1, 2, ...
     pivot_floor: float = 1e-12
@@ -61,6 +62,8 @@ class FactorizeOptions:
     single_pass_from: int = 1     # power steps with index >= this (> 0; 0 = never) use ONE CholeskyQR pass (small
                                   # shift, 6-term Gram): their input basis is already orthonormal and ordered
     single_pass_last: bool = True   # ... including the last step
+    second_pass_min_pivot: float = 0.05   # single-pass steps: the DEVICE adds a second pass for every matrix whose first
+                                          # pass met a Cholesky pivot below this (steep spectrum at high rank); 0 = never
     seed: int = 1234
     profile: bool = False
 
@@ -101,11 +104,13 @@ def _c_options(opts: FactorizeOptions) -> "_lib.FactorizeOptions":
     o.window, o.jacobi_sweeps = opts.window, opts.jacobi_sweeps
     o.rayleigh_ritz, o.want_sigma = int(opts.rayleigh_ritz), int(opts.want_sigma)
     o.gram_split_k, o.small_split_k = opts.gram_split_k, opts.small_split_k
+    o.gram_chunk_tokens = int(opts.gram_chunk_tokens)
     for i in range(4):
         o.shifts[i] = opts.shifts[min(i, len(opts.shifts) - 1)]
     o.pivot_floor = opts.pivot_floor
     o.spectral_shift, o.shift_tail = opts.spectral_shift, opts.shift_tail
     o.single_pass_from, o.single_pass_last = int(opts.single_pass_from), int(opts.single_pass_last)
+    o.second_pass_min_pivot = float(opts.second_pass_min_pivot)
     o.seed = opts.seed
     return o
 

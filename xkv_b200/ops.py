@@ -89,10 +89,12 @@ def make_problem(
     sym_upper: bool = False,
     split_k: int = 1,
     split_stride: int = 0,
+    accum_phases: int = 1,
 ) -> GemmProblem:
     """Describe D = sum_t A[ta] @ B[tb]^T.  A limbs: (M, K) row-major, or (K, M) if a_mn_major;
     B limbs: (N, K) row-major, or (K, N) if b_mn_major. `out`: fp32/bf16, (M, N) or (N, M) if transposed;
-    with split_k > 1 `out` is the first of split_k slabs `split_stride` elements apart."""
+    with split_k > 1 `out` is the first of split_k slabs `split_stride` elements apart.  accum_phases > 1: every
+    CTA accumulates its k range in that many pieces on the tensor core and sums the pieces in fp32 (fp32 output)."""
     p = GemmProblem()
     p.M, p.N, p.K = M, N, K
     p.num_terms = len(terms)
@@ -118,6 +120,7 @@ def make_problem(
     p.sym_upper = int(sym_upper)
     p.split_k = split_k
     p.split_stride = split_stride
+    p.accum_phases = accum_phases
     return p
 
 
