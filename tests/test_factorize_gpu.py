@@ -79,6 +79,34 @@ def test_steep_spectrum_at_high_rank_meets_the_bf16_storage_floor():
     assert e_ours ** 2 <= (1.01 * e_ref) ** 2 + 3e-3 ** 2
 
 
+@pytest.mark.parametrize(
+    "tokens,cols,rank,alpha",
+    [
+        (520, 4096, 512, 1.0),    # short prompt: fewer tokens than the sketch is wide (576): rank-deficient Gram
+        (577, 2048, 512, 0.5),    # odd token count
+        (1000, 1024, 128, 1.0),   # tokens < columns, not a multiple of the tile
+        (130, 1024, 128, 1.0),    # rank just below the token count
+        (4096, 4096, 500, 1.0),   # rank not a multiple of 64 (ragged Rayleigh-Ritz window)
+        (4096, 4096, 1, 1.0),     # rank 1
+        (3000, 4096, 37, 0.5),
+    ],
+)
+def test_ragged_short_and_odd_inputs(tokens, cols, rank, alpha):
+    """Edge cases of the reference's slicing semantics (cache:21-23): any 0 < rank < min(tokens, columns) must give the
+    truncated SVD.  Where the reference's error is tiny (rank close to the token count) the bf16 storage of the factors
+    enters in quadrature, as in the steep-spectrum test below."""
+    from xkv_b200 import factorize, synthetic
+
+    x = synthetic.group_matrix(tokens, cols, alpha, seed=5, device="cuda")
+    ref_hat, _ = _ref_fake_svd(x, rank)
+    (f,) = factorize.factorize_batch([x], rank)
+    torch.cuda.synchronize()
+    e_ref, e_ours = _rel_err(x, ref_hat), _rel_err(x, f.reconstruct())
+    print(f"tokens={tokens} cols={cols} r={rank}: err ref={e_ref:.6f} ours={e_ours:.6f}")
+    assert torch.isfinite(f.A).all() and torch.isfinite(f.Vt).all()
+    assert e_ours ** 2 <= (1.01 * e_ref) ** 2 + 3e-3 ** 2
+
+
 @pytest.mark.parametrize("min_pivot", [0.0, 0.05, 2.0])
 def test_device_decided_second_pass(min_pivot):
     """Single-pass power steps add a second CholeskyQR pass per matrix on a DEVICE decision (Cholesky pivot below

@@ -232,7 +232,8 @@ class FakeLayerMergingCache(DynamicCache):
         if rank is None:
             return False
         n = nlayers * self.num_heads * self.head_dim
-        return 0 < rank <= seq and factorize.sketch_width(rank) <= n
+        # rank >= min(m, n) is a no-op in the reference (slicing past the end, cache:21-23): the slot stays dense
+        return 0 < rank < min(seq, n) and factorize.sketch_width(rank) <= n
 
     def update_cache(self, layer_idx, key_approx, value_approx):
         """Reference cache:210-213: overwrite a layer's dense tensors (kept for API parity; a layer whose
