@@ -187,6 +187,9 @@ typedef struct xkv_factorize_options {
   uint64_t seed;
 } xkv_factorize_options;
 XKV_API void xkv_factorize_default_options(xkv_factorize_options* opts);
+/* sizeof(xkv_factorize_options) of this build: foreign-language bindings can hold the options as an opaque, zeroed blob
+ * of this many bytes filled in by xkv_factorize_default_options instead of mirroring the struct */
+XKV_API size_t xkv_factorize_options_size(void);
 XKV_API size_t xkv_factorize_workspace_bytes(int batch, int m, int n, int rank, const xkv_factorize_options* opts);
 XKV_API int xkv_factorize_sigma_count(int rank, const xkv_factorize_options* opts);
 XKV_API int xkv_factorize_batch(const void* const* X_host, int batch, int m, int n, int64_t ldx, int rank,

@@ -34,3 +34,7 @@ def test_version_and_error_channel():
     assert lib.xkv_factorize_workspace_bytes(1, 64, 4096, 512, None) == 0      # rank > tokens
     assert b"rank" in lib.xkv_last_error()
     assert lib.xkv_decode_workspace_bytes(32, 65536, 16, 768) > 0
+    # the ctypes mirrors have the library's struct layout
+    import ctypes as C
+
+    assert lib.xkv_factorize_options_size() == C.sizeof(_lib.FactorizeOptions)

@@ -95,6 +95,7 @@ SIGNATURES = {
     "xkv_shift_normalize_rows": (_i, [_pp, _pp, _vp, _pp, _i, _pp, _pp, _pp, _i, _i, _i, _i64, _i64, _vp]),
     "xkv_ritz_shift_update": (_i, [_pp, _i, _i, _i, _f, _vp, _vp]),
     "xkv_rdiag_update": (_i, [_pp, _pp, _i, _i, _i64, _vp]),
+    "xkv_factorize_options_size": (C.c_size_t, []),
     "xkv_pass_flags": (_i, [_pp, _i, _i, _i64, C.c_float, _vp, _vp]),
     "xkv_set_launch_predicate": (None, [_vp]),
     "xkv_cholesky_inverse": (_i, [_pp, _pp, _i, _i, _i64, _f, _f, _vp]),

@@ -213,6 +213,8 @@ extern "C" void xkv_factorize_default_options(xkv_factorize_options* o) {
   o->seed = 1234;
 }
 
+extern "C" size_t xkv_factorize_options_size(void) { return sizeof(xkv_factorize_options); }
+
 extern "C" size_t xkv_factorize_workspace_bytes(int batch, int m, int n, int rank, const xkv_factorize_options* opts) {
   xkv_factorize_options o;
   if (opts)
