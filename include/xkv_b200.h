@@ -98,6 +98,12 @@ XKV_API int xkv_split_bf16(const float* x, int rows, int cols, int64_t ld, void*
 XKV_API int xkv_split_bf16_batched(const float* const* x_host, void* const* hi_host, void* const* mid_host,
                                    void* const* lo_host, int batch, int rows, int cols, int64_t ld, int64_t ld_out,
                                    void* stream);
+/* Gram post-processing in one pass: hi/mid/lo[b] = bf16 limbs of the full symmetric n x n matrix whose upper-triangle
+ * tiles are sum_s slabs[b][s] (split-K slabs `slab_stride` elements apart, as xkv_gemm_grouped writes them with
+ * sym_upper = 1).  Equivalent to xkv_reduce_slabs(symmetrize = 1) followed by xkv_split_bf16, without the fp32 round trip. */
+XKV_API int xkv_symmetrize_split_bf16(const float* const* slabs_host, int batch, int num_slabs, int64_t slab_stride,
+                                      int n, int64_t ld, void* const* hi_host, void* const* mid_host,
+                                      void* const* lo_host, int64_t ld_out, void* stream);
 /* deterministic N(0,1) test matrix rounded to bf16 (counter-based generator) */
 XKV_API int xkv_fill_gaussian_bf16(void* out, int rows, int cols, int64_t ld, uint64_t seed, void* stream);
 /* Batched row normalisation: every row of Y[b] (rows x cols fp32, each row is a column of the sketch)
@@ -181,6 +187,14 @@ typedef struct xkv_factorize_options {
   int32_t shift_tail;     /* trailing entries of diag(R) of the previous step that estimate lambda_l (8) */
   int32_t single_pass_from; /* power steps with index >= this (> 0) orthonormalise with ONE CholeskyQR pass (small shift, 6-term Gram); 0 = never */
   int32_t single_pass_last; /* 1: the last power step may use the single pass too */
+  int32_t pass0_terms;      /* bf16-limb terms (3 or 6) of S = Y Y^T and Q = L^-1 Y in the heavily shifted first pass.  3 is only safe
+                             * when the rounding errors of the limbs are incoherent (energy spread over many columns); with a few
+                             * dominant channels they add up coherently to ~l * 2^-16 > the shift and the Cholesky breaks down
+                             * (default 6) */
+  int32_t heavy_redo;       /* 1 (default): a lightly shifted pass whose Cholesky met a pivot below twice its shift (the Gram of the
+                             * basis was numerically indefinite: extreme outlier channels) is redone ON DEVICE DECISION with the
+                             * heavy shift of pass 0 instead of producing NaN */
+  int32_t power_terms;      /* bf16-limb terms (3 or 6) of the power-step product Y = Q G (default 3) */
   float second_pass_min_pivot; /* a single-pass step runs a second pass ON DEVICE DECISION for every matrix whose first
                                 * pass met a Cholesky pivot below this (ill-conditioned: steep spectrum at high rank);
                                 * 0 = never (default 0.05) */

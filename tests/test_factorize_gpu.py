@@ -107,6 +107,52 @@ def test_ragged_short_and_odd_inputs(tokens, cols, rank, alpha):
     assert e_ours ** 2 <= (1.01 * e_ref) ** 2 + 3e-3 ** 2
 
 
+def _colscale(m, n, p):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(m, n, device="cuda", generator=g)
+    x *= torch.arange(1, n + 1, device="cuda") ** -p
+    return x.to(torch.bfloat16)
+
+
+def _outliers(m, n, alpha, k, gain):
+    from xkv_b200 import synthetic
+
+    x = synthetic.group_matrix(m, n, alpha, seed=3, device="cuda").float()
+    x[:, torch.arange(k, device="cuda") * 97 % n] *= gain
+    return (x * (4.0 / x.abs().max())).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize(
+    "name,make,rank",
+    [
+        ("unmixed columns, scales i^-0.7", lambda: _colscale(4096, 2048, 0.7), 448),
+        ("unmixed columns, scales i^-1", lambda: _colscale(4096, 2048, 1.0), 512),
+        ("4 outlier channels x30, alpha 1", lambda: _outliers(4096, 4096, 1.0, 4, 30.0), 512),
+        ("4 outlier channels x30, alpha 0.5", lambda: _outliers(4096, 4096, 0.5, 4, 30.0), 768),
+        ("8 outlier channels x300", lambda: _outliers(4096, 4096, 1.0, 8, 300.0), 512),
+    ],
+)
+def test_energy_concentrated_in_a_few_channels(name, make, rank):
+    """KV caches of real models carry a few massive channels.  With the energy in a few columns the rounding errors of
+    the bf16 limbs add up coherently (a 3-term first pass broke down -> NaN on every one of these inputs; it is 6-term
+    now), and with a gain of 300 the Gram of the once-orthogonalised sketch is numerically indefinite: the lightly
+    shifted Cholesky is then redone heavily shifted on a device decision.  The bf16 storage of A and V is relative to the
+    outlier channels' magnitude and enters in quadrature (4e-3: two factor roundings + the product's, vs the
+    reference's single rounding of the dense product)."""
+    from xkv_b200 import factorize
+
+    x = make()
+    ref_hat, s_ref = _ref_fake_svd(x, rank)
+    (f,) = factorize.factorize_batch([x], rank)
+    torch.cuda.synchronize()
+    assert torch.isfinite(f.A).all() and torch.isfinite(f.Vt).all(), name
+    e_ref, e_ours = _rel_err(x, ref_hat), _rel_err(x, f.reconstruct())
+    print(f"{name}: err ref={e_ref:.6f} ours={e_ours:.6f}")
+    assert e_ours ** 2 <= (1.01 * e_ref) ** 2 + 4e-3 ** 2
+    rel = ((f.sigma_lead[:16] - s_ref[:16]).abs() / s_ref[:16]).max().item()
+    assert rel < 2e-3
+
+
 @pytest.mark.parametrize("min_pivot", [0.0, 0.05, 2.0])
 def test_device_decided_second_pass(min_pivot):
     """Single-pass power steps add a second CholeskyQR pass per matrix on a DEVICE decision (Cholesky pivot below

@@ -21,6 +21,35 @@ def test_reduce_slabs_and_symmetrize():
     assert torch.allclose(out, ref, atol=1e-5)
 
 
+@pytest.mark.parametrize("n,slabs_n", [(200, 3), (256, 1), (40, 2)])
+def test_symmetrize_split_equals_reduce_then_split(n, slabs_n):
+    """One-pass Gram post-processing = reduce_slabs(symmetrize) followed by split_bf16, bit for bit; garbage below the
+    diagonal of the slabs (tiles the symmetric GEMM never writes) must not leak."""
+    from xkv_b200 import ops
+
+    torch.manual_seed(1)
+    batch = 3
+    slabs = [torch.randn(slabs_n, n, n, device="cuda") * 11.0 for _ in range(batch)]
+    ref = []
+    for sl in slabs:
+        g = torch.empty(n, n, device="cuda")
+        ops.reduce_slabs(sl, g, symmetrize=True)
+        limbs = [torch.empty(n, n, device="cuda", dtype=torch.bfloat16) for _ in range(3)]
+        ops.split_bf16(g, *limbs)
+        ref.append(limbs)
+    poisoned = []
+    for sl in slabs:
+        p = sl.clone()
+        low = torch.tril(torch.ones(n, n, device="cuda", dtype=torch.bool), -32)   # strictly below the diagonal tiles
+        p[:, low] = float("nan")
+        poisoned.append(p)
+    hi, mid, lo = ([torch.full((n, n), 7.0, device="cuda", dtype=torch.bfloat16) for _ in range(batch)] for _ in range(3))
+    ops.symmetrize_split_bf16(poisoned, hi, mid, lo)
+    torch.cuda.synchronize()
+    for b in range(batch):
+        assert torch.equal(hi[b], ref[b][0]) and torch.equal(mid[b], ref[b][1]) and torch.equal(lo[b], ref[b][2])
+
+
 def test_split_bf16_limbs_reconstruct_fp32():
     from xkv_b200 import ops
 

@@ -21,7 +21,18 @@ def main():
     m = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
     r = int(sys.argv[3]) if len(sys.argv) > 3 else 128
-    x = synthetic.group_matrix(m, n, 1.0, seed=1234, device="cuda")
+    if len(sys.argv) > 4 and sys.argv[4] == "colscale":   # unmixed columns with decaying scales: near-diagonal Gram
+        g = torch.Generator(device="cuda").manual_seed(1)
+        x = torch.randn(m, n, device="cuda", generator=g)
+        x *= (torch.arange(1, n + 1, device="cuda") ** -0.7)
+        x = x.to(torch.bfloat16)
+    elif len(sys.argv) > 4 and sys.argv[4].startswith("outliers"):   # a few channels with a huge gain
+        gain = float(sys.argv[4][len("outliers"):] or 300)
+        x = synthetic.group_matrix(m, n, 1.0, seed=3, device="cuda").float()
+        x[:, torch.arange(8) * 97 % n] *= gain
+        x = (x * (4.0 / x.abs().max())).to(torch.bfloat16)
+    else:
+        x = synthetic.group_matrix(m, n, 1.0, seed=1234, device="cuda")
     l = sketch_width(r)
     dev = "cuda"
     f32, bf = torch.float32, torch.bfloat16

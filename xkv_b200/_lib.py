@@ -71,6 +71,9 @@ class FactorizeOptions(C.Structure):
         ("shift_tail", C.c_int32),
         ("single_pass_from", C.c_int32),
         ("single_pass_last", C.c_int32),
+        ("pass0_terms", C.c_int32),
+        ("heavy_redo", C.c_int32),
+        ("power_terms", C.c_int32),
         ("second_pass_min_pivot", C.c_float),
         ("seed", C.c_uint64),
     ]
@@ -88,6 +91,7 @@ SIGNATURES = {
     "xkv_gemm_grouped": (_i, [C.POINTER(GemmProblem), _i, _vp]),
     "xkv_reduce_slabs": (_i, [_vp, _i, _i64, _i, _i, _i64, _i, _vp, _i64, _vp]),
     "xkv_reduce_slabs_batched": (_i, [_pp, _pp, _i, _i, _i64, _i, _i, _i64, _i, _i64, _vp]),
+    "xkv_symmetrize_split_bf16": (_i, [_pp, _i, _i, _i64, _i, _i64, _pp, _pp, _pp, _i64, _vp]),
     "xkv_split_bf16_batched": (_i, [_pp, _pp, _pp, _pp, _i, _i, _i, _i64, _i64, _vp]),
     "xkv_split_bf16": (_i, [_vp, _i, _i, _i64, _vp, _vp, _vp, _i64, _vp]),
     "xkv_fill_gaussian_bf16": (_i, [_vp, _i, _i, _i64, C.c_uint64, _vp]),

@@ -59,7 +59,7 @@ struct Plan {
   float* gram_slabs;  // [B][gs][n][n]
   float* shift_dev;   // [B] spectral shifts of the current power step
   int* pass_flags;    // [B] device decision: this matrix needs a second CholeskyQR pass in the current step
-  float* g32;
+  int* redo_flags;    // [B] device decision: the lightly shifted Cholesky of this matrix broke down, redo it heavily shifted
   size_t bytes;
 };
 
@@ -123,9 +123,9 @@ static int make_plan(Plan& P, Bump& bump, int B, int m, int n, int rank, const x
     }
   }
   P.gram_slabs = bump.f32(static_cast<size_t>(B) * P.gs * nn * nn);
-  P.g32 = bump.f32(nn * nn);
   P.shift_dev = bump.f32(XKV_MAX_BATCH);
   P.pass_flags = reinterpret_cast<int*>(bump.f32(XKV_MAX_BATCH));
+  P.redo_flags = reinterpret_cast<int*>(bump.f32(XKV_MAX_BATCH));
   P.bytes = align_up(bump.off, 1024);
   return 0;
 }
@@ -194,6 +194,9 @@ extern "C" void xkv_factorize_default_options(xkv_factorize_options* o) {
   o->single_pass_from = 1;
   o->single_pass_last = 1;
   o->second_pass_min_pivot = 0.05f;
+  o->pass0_terms = 6;
+  o->power_terms = 3;
+  o->heavy_redo = 1;
   o->oversample = 64;
   o->first_passes = 2;
   o->passes = 2;
@@ -292,13 +295,24 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
     XKV_TRY(run_gemms(ps, stream));
   }
   XKV_TRY(mark());  // 1: Gram GEMM (the dominant kernel, timed on its own for the roofline)
-  for (int b = 0; b < B; ++b) {
-    float* g = phase == 0 ? P.g32 : gram_host[b];
-    XKV_REQUIRE(g != nullptr, "factorize: null Gram buffer %d", b);
-    if (phase != 2)
-      XKV_TRY(xkv_reduce_slabs(P.gram_slabs + static_cast<size_t>(b) * P.gs * nn * nn, P.gs, nn * nn, n, n, nn, 1, g, nn,
-                               stream));
-    if (phase != 1) XKV_TRY(xkv_split_bf16(g, n, n, nn, P.g_limb[b][0], P.g_limb[b][1], P.g_limb[b][2], nn, stream));
+  if (phase == 0) {
+    // slabs -> symmetric bf16 limbs in one pass (no fp32 Gram round trip)
+    const float* sl[XKV_MAX_BATCH];
+    void *h0[XKV_MAX_BATCH], *h1[XKV_MAX_BATCH], *h2[XKV_MAX_BATCH];
+    for (int b = 0; b < B; ++b) {
+      sl[b] = P.gram_slabs + static_cast<size_t>(b) * P.gs * nn * nn;
+      h0[b] = P.g_limb[b][0], h1[b] = P.g_limb[b][1], h2[b] = P.g_limb[b][2];
+    }
+    XKV_TRY(xkv_symmetrize_split_bf16(sl, B, P.gs, nn * nn, n, nn, h0, h1, h2, nn, stream));
+  } else {
+    for (int b = 0; b < B; ++b) {
+      float* g = gram_host[b];
+      XKV_REQUIRE(g != nullptr, "factorize: null Gram buffer %d", b);
+      if (phase != 2)
+        XKV_TRY(xkv_reduce_slabs(P.gram_slabs + static_cast<size_t>(b) * P.gs * nn * nn, P.gs, nn * nn, n, n, nn, 1, g, nn,
+                                 stream));
+      if (phase != 1) XKV_TRY(xkv_split_bf16(g, n, n, nn, P.g_limb[b][0], P.g_limb[b][1], P.g_limb[b][2], nn, stream));
+    }
   }
   XKV_TRY(mark());  // 2: Gram reduce + limb split
   if (phase == 1) return 0;
@@ -329,8 +343,9 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
       int rc = [&]() -> int {
         XKV_TRY(xkv_shift_normalize_rows(cur, (ip == 0 && shifted) ? nxt : nullptr, P.shift_dev,
                                          track ? P.rdiag : nullptr, ip == 0, P.lh, P.lm, P.ll, B, l, n, nn, nn, stream));
-        // pass 0 is regularised by a 3e-4 shift, so the 3-term product (error ~1e-5) is accurate enough there
-        const int nt = pp == 0 ? 3 : 6;
+        // pass 0 is regularised by a 3e-4 shift; a 3-term product (error ~1e-5 per entry) is accurate enough there
+        // only if those errors are incoherent -- see xkv_factorize_options.pass0_terms
+        const int nt = (pp == 0 && o.pass0_terms == 3) ? 3 : 6;
         for (int b = 0; b < B; ++b) {
           xkv_gemm_problem p = problem(P.lh[b], P.lm[b], P.ll[b], nn, 0, P.lh[b], P.lm[b], P.ll[b], nn, 0, P.s_slabs[b],
                                        l, l, l, n, nt);
@@ -345,8 +360,23 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
         {
           void *h0[XKV_MAX_BATCH], *h1[XKV_MAX_BATCH], *h2[XKV_MAX_BATCH];
           for (int b = 0; b < B; ++b) h0[b] = P.linv_l[b][0], h1[b] = P.linv_l[b][1], h2[b] = P.linv_l[b][2];
-          XKV_TRY(xkv_cholesky_inverse_limbs(P.s_mat, P.linv, h0, h1, nt > 3 ? h2 : nullptr, B, l, l, l,
-                                             o.shifts[pp < 3 ? pp : 3], o.pivot_floor, stream));
+          const float shift = o.shifts[pp < 3 ? pp : 3];
+          XKV_TRY(xkv_cholesky_inverse_limbs(P.s_mat, P.linv, h0, h1, nt > 3 ? h2 : nullptr, B, l, l, l, shift,
+                                             o.pivot_floor, stream));
+          if (o.heavy_redo && pp > 0 && shift < o.shifts[0]) {
+            // A pivot below twice the shift means the fp32 Gram of the basis was numerically indefinite (the pass before
+            // left it too ill-conditioned: extreme outlier channels).  Such matrices redo the Cholesky with the heavy
+            // shift of pass 0 -- the slabs still hold S -- which costs orthogonality (later passes restore it) but never
+            // produces the overflow -> NaN cascade of a clamped pivot.
+            XKV_TRY(xkv_pass_flags(P.linv, B, l, l, 2.f * shift, P.redo_flags, stream));
+            xkv_set_launch_predicate(P.redo_flags);
+            int rc2 = xkv_reduce_slabs_batched(P.s_slabs, P.s_mat, B, P.sk, static_cast<long long>(l) * l, l, l, l, 1, l, stream);
+            if (!rc2)
+              rc2 = xkv_cholesky_inverse_limbs(P.s_mat, P.linv, h0, h1, nt > 3 ? h2 : nullptr, B, l, l, l, o.shifts[0],
+                                               o.pivot_floor, stream);
+            xkv_set_launch_predicate(cond ? P.pass_flags : nullptr);
+            if (rc2) return rc2;
+          }
         }
         if (track) XKV_TRY(xkv_rdiag_update(P.rdiag, P.linv, B, l, l, stream));
         for (int b = 0; b < B; ++b) {
@@ -386,8 +416,9 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
   const bool use_shift = o.spectral_shift > 0.f && o.shift_tail > 0 && o.power_iters > 1;
   if (use_shift) XKV_CHECK_CUDA(cudaMemsetAsync(P.shift_dev, 0, XKV_MAX_BATCH * sizeof(float), st));
   for (int it = 0; it < o.power_iters; ++it) {
-    XKV_TRY(xkv_split_bf16_batched(cur, P.lh, P.lm, nullptr, B, l, n, nn, nn, stream));
-    XKV_TRY(apply_gram(3));
+    const int pterms = o.power_terms == 6 ? 6 : 3;
+    XKV_TRY(xkv_split_bf16_batched(cur, P.lh, P.lm, pterms == 6 ? P.ll : nullptr, B, l, n, nn, nn, stream));
+    XKV_TRY(apply_gram(pterms));
     const bool shifted = use_shift && it > 0;
     if (shifted)
       XKV_TRY(xkv_ritz_shift_update(P.rdiag, B, l, o.shift_tail < l ? o.shift_tail : l, o.spectral_shift, P.shift_dev,
@@ -412,9 +443,22 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
         ps.push_back(problem(row_bf16(P.lh[b], w0s[w], nn), row_bf16(P.lm[b], w0s[w], nn), row_bf16(P.ll[b], w0s[w], nn),
                              nn, 0, P.g_limb[b][0], P.g_limb[b][1], P.g_limb[b][2], nn, 0, P.yw[b][w], nn, W, n, n, 6));
     XKV_TRY(run_gemms(ps, stream));
-    for (int b = 0; b < B; ++b)
-      for (int w = 0; w < nw; ++w)
-        XKV_TRY(xkv_split_bf16(P.yw[b][w], W, n, nn, P.yw_l[b][w][0], P.yw_l[b][w][1], P.yw_l[b][w][2], nn, stream));
+    {
+      // all windows' limbs in launches of up to XKV_MAX_BATCH matrices
+      const float* xs[2 * XKV_MAX_BATCH];
+      void *h0[2 * XKV_MAX_BATCH], *h1[2 * XKV_MAX_BATCH], *h2[2 * XKV_MAX_BATCH];
+      int cntw = 0;
+      for (int b = 0; b < B; ++b)
+        for (int w = 0; w < nw; ++w) {
+          xs[cntw] = P.yw[b][w];
+          h0[cntw] = P.yw_l[b][w][0], h1[cntw] = P.yw_l[b][w][1], h2[cntw] = P.yw_l[b][w][2];
+          ++cntw;
+        }
+      for (int lo = 0; lo < cntw; lo += XKV_MAX_BATCH) {
+        const int c = cntw - lo < XKV_MAX_BATCH ? cntw - lo : XKV_MAX_BATCH;
+        XKV_TRY(xkv_split_bf16_batched(xs + lo, h0 + lo, h1 + lo, h2 + lo, c, W, n, nn, nn, stream));
+      }
+    }
     for (int b = 0; b < B; ++b)
       for (int w = 0; w < nw; ++w) {
         xkv_gemm_problem p =
@@ -426,22 +470,35 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
       }
     XKV_TRY(run_gemms(ps, stream));
     const float* tptr[2 * XKV_MAX_BATCH];
+    const float* sptr[2 * XKV_MAX_BATCH];
+    float* toutp[2 * XKV_MAX_BATCH];
     float* eptr[2 * XKV_MAX_BATCH];
     float* wptr[2 * XKV_MAX_BATCH];
     int cnt = 0;
     for (int b = 0; b < B; ++b)
       for (int w = 0; w < nw; ++w) {
-        XKV_TRY(xkv_reduce_slabs(P.t_slabs[b][w], P.skw, static_cast<long long>(W) * W, W, W, W, 0, P.t_mat[b][w], W,
-                                 stream));
+        sptr[cnt] = P.t_slabs[b][w];
+        toutp[cnt] = P.t_mat[b][w];
         tptr[cnt] = P.t_mat[b][w];
         eptr[cnt] = P.evals[b][w];
         wptr[cnt] = (w == 0) ? P.wt[b] : nullptr;
         ++cnt;
       }
+    for (int lo = 0; lo < cnt; lo += XKV_MAX_BATCH) {
+      const int c = cnt - lo < XKV_MAX_BATCH ? cnt - lo : XKV_MAX_BATCH;
+      XKV_TRY(xkv_reduce_slabs_batched(sptr + lo, toutp + lo, c, P.skw, static_cast<long long>(W) * W, W, W, W, 0, W, stream));
+    }
     XKV_TRY(xkv_jacobi_eigh(tptr, eptr, wptr, cnt, W, W, W, o.jacobi_sweeps, stream));
     // rows [r0, r) of the basis <- top-wl Ritz vectors of the window: Vw = Wsel * Qw
-    for (int b = 0; b < B; ++b)
-      XKV_TRY(xkv_split_bf16(P.wt[b], wl, W, W, P.wsel_l[b][0], P.wsel_l[b][1], P.wsel_l[b][2], W, stream));
+    {
+      const float* xs[XKV_MAX_BATCH];
+      void *h0[XKV_MAX_BATCH], *h1[XKV_MAX_BATCH], *h2[XKV_MAX_BATCH];
+      for (int b = 0; b < B; ++b) {
+        xs[b] = P.wt[b];
+        h0[b] = P.wsel_l[b][0], h1[b] = P.wsel_l[b][1], h2[b] = P.wsel_l[b][2];
+      }
+      XKV_TRY(xkv_split_bf16_batched(xs, h0, h1, h2, B, wl, W, W, W, stream));
+    }
     for (int b = 0; b < B; ++b)
       ps.push_back(problem(P.wsel_l[b][0], P.wsel_l[b][1], P.wsel_l[b][2], W, 0, row_bf16(P.lh[b], r0, nn),
                            row_bf16(P.lm[b], r0, nn), row_bf16(P.ll[b], r0, nn), nn, 1, cur[b] + static_cast<size_t>(r0) * nn,

@@ -108,6 +108,68 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const __grid_constant__
   }
 }
 
+
+// =============================================================================================
+// Gram post-processing in one pass: sum the split-K slabs of the upper-triangle tiles, mirror them, and write the
+// three bf16 limbs of the full symmetric matrix (replaces reduce_slabs<1> + split_bf16: the fp32 Gram is read once
+// and never written back).  One CTA per 32x32 tile pair bi <= bj, batch in blockIdx.y.
+// =============================================================================================
+struct SymSplitParams {
+  const float* slabs[XKV_MAX_BATCH];
+  __nv_bfloat16* hi[XKV_MAX_BATCH];
+  __nv_bfloat16* mid[XKV_MAX_BATCH];
+  __nv_bfloat16* lo[XKV_MAX_BATCH];
+};
+__global__ void __launch_bounds__(256) sym_split_kernel(const __grid_constant__ SymSplitParams sp, int num_slabs,
+                                                        long long slab_stride, int n, long long ld, long long ldo,
+                                                        int tiles_per_row) {
+  __shared__ float tile[32][33];
+  const float* __restrict__ slabs = sp.slabs[blockIdx.y];
+  __nv_bfloat16* __restrict__ hi = sp.hi[blockIdx.y];
+  __nv_bfloat16* __restrict__ mid = sp.mid[blockIdx.y];
+  __nv_bfloat16* __restrict__ lo = sp.lo[blockIdx.y];
+  int t = blockIdx.x, bi = 0, cnt = tiles_per_row;
+  while (t >= cnt) {
+    t -= cnt;
+    ++bi;
+    --cnt;
+  }
+  const int bj = bi + t;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi * 32 + r, j = bj * 32 + tx;
+    float acc = 0.f;
+    if (i < n && j < n) {
+      const float* p = slabs + static_cast<long long>(i) * ld + j;
+      for (int s = 0; s < num_slabs; ++s) acc += p[static_cast<long long>(s) * slab_stride];
+      if (j >= i) {
+        __nv_bfloat16 h, m, l;
+        split3(acc, h, m, l);
+        const long long o = static_cast<long long>(i) * ldo + j;
+        hi[o] = h;
+        mid[o] = m;
+        lo[o] = l;
+      }
+    }
+    tile[r][tx] = acc;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    // mirrored element (i, j) = (bj*32 + r, bi*32 + tx) takes the value computed at (bi*32 + tx, bj*32 + r)
+    const int i = bj * 32 + r, j = bi * 32 + tx;
+    if (i < n && j < n && i > j) {
+      __nv_bfloat16 h, m, l;
+      split3(tile[tx][r], h, m, l);
+      const long long o = static_cast<long long>(i) * ldo + j;
+      hi[o] = h;
+      mid[o] = m;
+      lo[o] = l;
+    }
+  }
+}
+
 // =============================================================================================
 // deterministic Gaussian test matrix (counter-based: value depends only on seed and position)
 // =============================================================================================
@@ -191,6 +253,10 @@ __global__ void __launch_bounds__(256) rdiag_update_kernel(const __grid_constant
 // ill-conditioned, its output is orthonormal only to ~ eps / pivot, and a second pass is worth its cost.  A NaN
 // diagonal raises the flag too.
 __global__ void __launch_bounds__(256) pass_flag_kernel(const __grid_constant__ NormParams p) {
+  if (p.run_if != nullptr && p.run_if[blockIdx.x] == 0) {   // gated by the launch predicate: a skipped matrix raises no flag
+    if (threadIdx.x == 0) p.flags[blockIdx.x] = 0;
+    return;
+  }
   const float* li = p.Linv[blockIdx.x];
   int bad = 0;
   for (int j = threadIdx.x; j < p.rows; j += blockDim.x) {
@@ -447,6 +513,7 @@ extern "C" int xkv_pass_flags(const float* const* Linv_host, int batch, int rows
   p.ld_linv = ld_linv;
   p.flags = flags_dev;
   p.inv_min_pivot = 1.f / min_pivot;
+  p.run_if = launch_predicate();
   pass_flag_kernel<<<batch, 256, 0, as_stream(stream)>>>(p);
   XKV_LAUNCHED();
   return 0;
@@ -482,6 +549,28 @@ extern "C" int xkv_reduce_slabs(const float* slabs, int num_slabs, int64_t slab_
                                 int symmetrize, float* out, int64_t ld_out, void* stream) {
   XKV_REQUIRE(slabs && out, "reduce_slabs: bad arguments");
   return xkv_reduce_slabs_batched(&slabs, &out, 1, num_slabs, slab_stride, rows, cols, ld, symmetrize, ld_out, stream);
+}
+
+extern "C" int xkv_symmetrize_split_bf16(const float* const* slabs_host, int batch, int num_slabs, int64_t slab_stride,
+                                         int n, int64_t ld, void* const* hi_host, void* const* mid_host,
+                                         void* const* lo_host, int64_t ld_out, void* stream) {
+  XKV_REQUIRE(slabs_host && hi_host && mid_host && lo_host && batch >= 1 && batch <= XKV_MAX_BATCH,
+              "symmetrize_split: bad arguments");
+  XKV_REQUIRE(num_slabs >= 1 && n > 0, "symmetrize_split: bad sizes");
+  SymSplitParams sp;
+  std::memset(&sp, 0, sizeof(sp));
+  for (int b = 0; b < batch; ++b) {
+    XKV_REQUIRE(slabs_host[b] && hi_host[b] && mid_host[b] && lo_host[b], "symmetrize_split: null matrix %d", b);
+    sp.slabs[b] = slabs_host[b];
+    sp.hi[b] = static_cast<__nv_bfloat16*>(hi_host[b]);
+    sp.mid[b] = static_cast<__nv_bfloat16*>(mid_host[b]);
+    sp.lo[b] = static_cast<__nv_bfloat16*>(lo_host[b]);
+  }
+  const int tr = (n + 31) / 32;
+  sym_split_kernel<<<dim3(tr * (tr + 1) / 2, batch), 256, 0, as_stream(stream)>>>(sp, num_slabs, slab_stride, n, ld, ld_out,
+                                                                              tr);
+  XKV_LAUNCHED();
+  return 0;
 }
 
 extern "C" int xkv_split_bf16_batched(const float* const* x_host, void* const* hi_host, void* const* mid_host,

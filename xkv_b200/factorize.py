@@ -62,6 +62,10 @@ class FactorizeOptions:
     single_pass_from: int = 1     # power steps with index >= this (> 0; 0 = never) use ONE CholeskyQR pass (small
                                   # shift, 6-term Gram): their input basis is already orthonormal and ordered
     single_pass_last: bool = True   # ... including the last step
+    pass0_terms: int = 6            # limb terms of the heavily shifted first pass; 3 breaks down on inputs with a few dominant
+                                    # channels (coherent limb rounding errors exceed the shift), 6 is ~fp32
+    heavy_redo: bool = True         # redo a lightly shifted pass with the heavy shift when its Cholesky broke down (device decision)
+    power_terms: int = 3            # limb terms of the power-step product Y = Q G
     second_pass_min_pivot: float = 0.05   # single-pass steps: the DEVICE adds a second pass for every matrix whose first
                                           # pass met a Cholesky pivot below this (steep spectrum at high rank); 0 = never
     seed: int = 1234
@@ -111,6 +115,9 @@ def _c_options(opts: FactorizeOptions) -> "_lib.FactorizeOptions":
     o.spectral_shift, o.shift_tail = opts.spectral_shift, opts.shift_tail
     o.single_pass_from, o.single_pass_last = int(opts.single_pass_from), int(opts.single_pass_last)
     o.second_pass_min_pivot = float(opts.second_pass_min_pivot)
+    o.pass0_terms = int(opts.pass0_terms)
+    o.power_terms = int(opts.power_terms)
+    o.heavy_redo = int(opts.heavy_redo)
     o.seed = opts.seed
     return o
 

@@ -161,6 +161,16 @@ def split_bf16(x: torch.Tensor, hi: torch.Tensor, mid: Optional[torch.Tensor] = 
                                      _stream()))
 
 
+def symmetrize_split_bf16(slabs: Sequence[torch.Tensor], hi: Sequence[torch.Tensor], mid: Sequence[torch.Tensor],
+                          lo: Sequence[torch.Tensor]) -> None:
+    """For each (S, n, n) fp32 slab stack (upper-triangle tiles valid): bf16 limbs of the full symmetric sum, one pass."""
+    _require_cuda(*slabs, *hi)
+    s, n, _ = slabs[0].shape
+    check(_lib.load().xkv_symmetrize_split_bf16(_ptr_array(slabs), len(slabs), s, slabs[0].stride(0), n,
+                                                slabs[0].stride(1), _ptr_array(hi), _ptr_array(mid), _ptr_array(lo),
+                                                hi[0].stride(0), _stream()))
+
+
 def fill_gaussian_bf16(out: torch.Tensor, seed: int) -> None:
     _require_cuda(out)
     rows, cols = out.shape
