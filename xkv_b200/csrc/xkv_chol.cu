@@ -24,6 +24,8 @@
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "xkv_common.cuh"
 #include "xkv_host.h"
 
@@ -478,20 +480,36 @@ extern "C" int xkv_cholesky_inverse_limbs(float* const* S_host, float* const* Li
     XKV_CHECK_CUDA(cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  const int CL = p.nblk >= 6 ? 8 : (p.nblk >= 3 ? 4 : (p.nblk == 2 ? 2 : 1));
+  int CL = p.nblk >= 6 ? 8 : (p.nblk >= 3 ? 4 : (p.nblk == 2 ? 2 : 1));
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(CL, batch, 1);
   cfg.blockDim = dim3(CH_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = as_stream(stream);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // Wide factors (>= 20 blocks: sketch width 1280 and up, config 4 values) have enough tiles per step for 16 CTAs -- a non-portable cluster
+  // size, used only when the device can keep one such cluster per matrix resident at once.
+  static int cl16_clusters = -1;   // resident 16-CTA clusters of this kernel on this device (0: unsupported)
+  if (cl16_clusters < 0) {
+    cl16_clusters = 0;
+    const char* e = getenv("XKV_CHOL_CL16");
+    if (!(e && e[0] == '0') &&
+        cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+      cfg.gridDim = dim3(16, 1, 1);
+      attr[0].val.clusterDim.x = 16;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, chol_cluster_kernel, &cfg) == cudaSuccess) cl16_clusters = n;
+    }
+    (void)cudaGetLastError();
+  }
+  if (p.nblk >= 20 && cl16_clusters >= batch) CL = 16;
+  cfg.gridDim = dim3(CL, batch, 1);
+  attr[0].val.clusterDim.x = CL;
   XKV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, chol_cluster_kernel, p));
   XKV_LAUNCHED();
   return 0;
