@@ -232,6 +232,17 @@ XKV_API int xkv_decode_attention(const void* q, int Hq, int H, int D, const void
                                  int64_t tail_stride_t, float scale, void* out, void* workspace,
                                  size_t workspace_bytes, const void* cos_t, const void* sin_t, int64_t ld_t,
                                  void* stream);
+/* Same, and lse_out[hq] (Hq floats, may be NULL) = log sum_t exp(scale * q_hq . k_t) over the S + T tokens of THIS call.
+ * Token shards of a long context (each rank holds the rows of A_k / A_v of its tokens and the RoPE rows
+ * of their positions) each call this on their rows and merge flash-decoding style:
+ *   out = sum_p exp(lse_p - lse) out_p,  lse = log sum_p exp(lse_p)      (xkv_b200.parallel.merge_token_shards). */
+XKV_API int xkv_decode_attention_lse(const void* q, int Hq, int H, int D, const void* A_k, int64_t lda_k, int rk,
+                                     const void* Vk_layer, int64_t ldv_k, const void* A_v, int64_t lda_v, int rv,
+                                     const void* Vv_layer, int64_t ldv_v, int S, const void* cos, const void* sin,
+                                     int64_t ld_cs, const void* k_tail, const void* v_tail, int T, int64_t tail_stride_h,
+                                     int64_t tail_stride_t, float scale, void* out, void* workspace,
+                                     size_t workspace_bytes, const void* cos_t, const void* sin_t, int64_t ld_t,
+                                     void* stream, float* lse_out);
 /* Dim-major copies of the RoPE tables for the decode kernel that keeps the right factor in tensor memory:
  * cos_t[i][t] = cos[t][i] for i < D/2 (the HF tables repeat the D/2 frequencies in both halves), t < S; columns
  * [S, ld_t) are zeroed.  ld_t must be a multiple of 128 and >= S.  Built once per prefill (the tables depend on the

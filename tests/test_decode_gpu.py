@@ -105,6 +105,46 @@ def _tr_cases():
     _case(5000, 2, 128, 8, 512, 128, 1, 2, 1, False)
 
 
+def test_token_shards_merge_to_the_unsharded_attention():
+    """SURVEY section 8e, decode with token shards: each shard runs the fused kernel on ITS rows of A_k / A_v with the RoPE
+    rows of its positions and returns (normalised output, log-sum-exp); the flash-decoding merge must reproduce the
+    kernel's own output over the whole context.  The dense decode tail lives on the last shard."""
+    from xkv_b200 import ops, parallel, synthetic
+
+    S, H, D, qpk, rk, rv, T = 5000, 8, 128, 4, 256, 384, 3
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(11)
+    a_k = (torch.randn(S, rk, generator=g, device=dev) * 0.6).bfloat16()
+    a_v = torch.randn(S, rv, generator=g, device=dev).bfloat16()
+    v_k = torch.linalg.qr(torch.randn(H * D, rk, generator=g, device=dev))[0].contiguous().bfloat16()
+    v_v = torch.linalg.qr(torch.randn(H * D, rv, generator=g, device=dev))[0].contiguous().bfloat16()
+    q = torch.randn(H * qpk, D, generator=g, device=dev).bfloat16()
+    k_tail = torch.randn(H, T, D, generator=g, device=dev).bfloat16()
+    v_tail = torch.randn(H, T, D, generator=g, device=dev).bfloat16()
+    cos, sin = synthetic.llama3_rope(S, D, device=dev)
+    cos, sin = cos[0].contiguous(), sin[0].contiguous()
+    scale = 1.0 / math.sqrt(D)
+    lse_full = torch.empty(H * qpk, device=dev)
+    full = ops.decode_attention(q, a_k, v_k, a_v, v_v, H, cos, sin, k_tail, v_tail, scale, lse_out=lse_full)
+    world = 3
+    outs, lses = [], []
+    for rank in range(world):
+        b, e = parallel.token_shard(S, world, rank)
+        last = rank == world - 1
+        lse = torch.empty(H * qpk, device=dev)
+        o = ops.decode_attention(q, a_k[b:e], v_k, a_v[b:e], v_v, H, cos[b:e], sin[b:e], k_tail if last else None,
+                                 v_tail if last else None, scale, lse_out=lse)
+        outs.append(o)
+        lses.append(lse)
+    merged, lse = parallel.merge_partial_attention(torch.stack(outs), torch.stack(lses))
+    torch.cuda.synchronize()
+    scale_out = full.float().abs().max().item()
+    err = (merged - full.float()).abs().max().item()
+    print(f"token shards x{world}: max|diff| = {err:.5f} (output scale {scale_out:.3f}), lse diff {(lse - lse_full).abs().max().item():.2e}")
+    assert err <= 2e-2 * scale_out
+    assert (lse - lse_full).abs().max().item() < 1e-3
+
+
 def test_rope_tables_dim_major():
     from xkv_b200 import ops, synthetic
 

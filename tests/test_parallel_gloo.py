@@ -75,3 +75,52 @@ def test_world_size_two_gram_allreduce_and_timing():
         assert ok_gram and ok_proj
         assert slow == 11.0          # max over ranks, on both ranks
         assert total == 8
+
+
+def test_merge_partial_attention_equals_softmax_over_the_union():
+    torch.manual_seed(1)
+    hq, d, s = 8, 16, 300
+    scores = torch.randn(hq, s) * 3
+    v = torch.randn(s, d)
+    ref = torch.softmax(scores, dim=1) @ v
+    cuts = [0, 128, 128, 300]             # three shards, the middle one empty
+    outs, lses = [], []
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        if e > b:
+            outs.append(torch.softmax(scores[:, b:e], dim=1) @ v[b:e])
+            lses.append(torch.logsumexp(scores[:, b:e], dim=1))
+        else:
+            outs.append(torch.zeros(hq, d))
+            lses.append(torch.full((hq,), float("-inf")))
+    out, lse = parallel.merge_partial_attention(torch.stack(outs), torch.stack(lses))
+    assert torch.allclose(out, ref, atol=1e-5)
+    assert torch.allclose(lse, torch.logsumexp(scores, dim=1), atol=1e-5)
+
+
+def _decode_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        hq, d, s = 8, 32, 1000
+        scores = torch.randn(hq, s) * 2                      # identical on every rank
+        v = torch.randn(s, d)
+        b, e = parallel.token_shard(s, world, rank)
+        out_local = (torch.softmax(scores[:, b:e], dim=1) @ v[b:e]).bfloat16()   # stand-in for the decode kernel
+        lse_local = torch.logsumexp(scores[:, b:e], dim=1)
+        merged = parallel.merge_token_shards(out_local, lse_local)
+        ref = torch.softmax(scores, dim=1) @ v
+        ret[rank] = (merged.dtype == torch.bfloat16, float((merged.float() - ref).abs().max()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_two_token_sharded_decode_merge():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_decode_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for rank in range(world):
+        same_dtype, err = ret[rank]
+        assert same_dtype and err < 2e-2

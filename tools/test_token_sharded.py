@@ -1,5 +1,7 @@
 """torchrun --nproc-per-node 2: token-sharded factorisation (Gram all-reduce over NCCL) against the
-single-GPU factorisation of the whole matrix. Run on a 2-GPU box: gpurun --gpus 2."""
+single-GPU factorisation of the whole matrix, then token-sharded DECODE over the sharded factors (each rank attends
+over its own rows of A_k / A_v, one all-gather of (Hq x (D+1)) floats, flash-decoding merge) against the fused kernel
+over the whole context. Run on a 2-GPU box: gpurun --gpus 2."""
 import os
 import sys
 
@@ -29,5 +31,39 @@ ok = err_shard <= 1.002 * err_full
 if rank == 0:
     print(f"token-sharded x{world}: rel err {err_shard:.6f} vs single-GPU {err_full:.6f}; max|Vt diff| {same_v:.3e}; "
           f"{'OK' if ok else 'FAIL'}")
+# ---- decode over the token shards: K and V factors of one 4-layer group (8 kv heads x 64), layer 1 of the group ----
+import math
+from xkv_b200 import ops
+
+H, D, qpk, layer = 8, 64, 4, 1
+xv = synthetic.group_matrix(S, n, 0.5, seed=43, device=dev)
+(fk_s,) = [f_shard]
+(fv_s,) = factorize.factorize_batch([xv[b:e].contiguous()], r, process_group=dist.group.WORLD)
+g = torch.Generator(device=dev).manual_seed(5)
+q = torch.randn(H * qpk, D, generator=g, device=dev).bfloat16()
+k_tail = torch.randn(H, 2, D, generator=g, device=dev).bfloat16()
+v_tail = torch.randn(H, 2, D, generator=g, device=dev).bfloat16()
+cos, sin = synthetic.llama3_rope(S, D, device=dev)
+cos, sin = cos[0].contiguous(), sin[0].contiguous()
+rows = slice(layer * H * D, (layer + 1) * H * D)
+last = rank == world - 1
+lse = torch.empty(H * qpk, device=dev)
+o_local = ops.decode_attention(q, fk_s.A, fk_s.V[rows], fv_s.A, fv_s.V[rows], H, cos[b:e], sin[b:e],
+                               k_tail if last else None, v_tail if last else None, 1.0 / math.sqrt(D), lse_out=lse)
+merged = parallel.merge_token_shards(o_local, lse, dist.group.WORLD)
+# reference: all rows gathered on every rank, one fused call over the whole context
+def gather_rows(t):
+    parts = [torch.empty(parallel.token_shard(S, world, p)[1] - parallel.token_shard(S, world, p)[0], t.shape[1],
+                         dtype=t.dtype, device=dev) for p in range(world)]
+    dist.all_gather(parts, t.contiguous())
+    return torch.cat(parts)
+a_k_all, a_v_all = gather_rows(fk_s.A), gather_rows(fv_s.A)
+full = ops.decode_attention(q, a_k_all, fk_s.V[rows], a_v_all, fv_s.V[rows], H, cos, sin, k_tail, v_tail, 1.0 / math.sqrt(D))
+torch.cuda.synchronize()
+derr = (merged.float() - full.float()).abs().max().item()
+dscale = full.float().abs().max().item()
+ok_dec = derr <= 2e-2 * dscale
+if rank == 0:
+    print(f"token-sharded decode x{world}: max|diff| {derr:.5f} (output scale {dscale:.3f}); {'OK' if ok_dec else 'FAIL'}")
 dist.destroy_process_group()
-sys.exit(0 if ok else 1)
+sys.exit(0 if (ok and ok_dec) else 1)

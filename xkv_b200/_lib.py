@@ -113,6 +113,8 @@ SIGNATURES = {
     "xkv_decode_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "xkv_decode_attention": (_i, [_vp, _i, _i, _i, _vp, _i64, _i, _vp, _i64, _vp, _i64, _i, _vp, _i64, _i, _vp, _vp, _i64,
                                   _vp, _vp, _i, _i64, _i64, _f, _vp, _vp, _sz, _vp, _vp, _i64, _vp]),
+    "xkv_decode_attention_lse": (_i, [_vp, _i, _i, _i, _vp, _i64, _i, _vp, _i64, _vp, _i64, _i, _vp, _i64, _i, _vp, _vp,
+                                      _i64, _vp, _vp, _i, _i64, _i64, _f, _vp, _vp, _sz, _vp, _vp, _i64, _vp, _vp]),
     "xkv_rope_tables_dim_major": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _i64, _vp]),
     "xkv_decode_force_tiled": (None, [_i]),
     "xkv_decode_set_variant": (None, [_i]),

@@ -1402,7 +1402,8 @@ __global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ 
                                                       const __nv_bfloat16* __restrict__ prob, long long ldp, int S, int T,
                                                       const __nv_bfloat16* __restrict__ v_tail, long long sh, long long st,
                                                       const float* __restrict__ rowsum, int qpk, int D,
-                                                      __nv_bfloat16* __restrict__ out) {
+                                                      __nv_bfloat16* __restrict__ out,
+                                                      const float* __restrict__ chunk_max, float* __restrict__ lse_out) {
   extern __shared__ float u_s[];  // rv floats
   const int hq = blockIdx.x, h = hq / qpk;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1414,6 +1415,14 @@ __global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ 
 #pragma unroll
   for (int c = 0; c < SM_CHUNKS; ++c) rs += rowsum[hq * SM_CHUNKS + c];
   const float inv = 1.f / rs;
+  if (lse_out != nullptr && blockIdx.y == 0 && threadIdx.x == 0) {
+    // log-sum-exp of this head's scaled scores over the tokens of THIS call: what a flash-decoding style merge of
+    // token shards needs besides the normalised output
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < SM_CHUNKS; ++c) m = fmaxf(m, chunk_max[hq * SM_CHUNKS + c]);
+    lse_out[hq] = m + logf(rs);
+  }
   for (int d = blockIdx.y * 32 + warp; d < min(D, blockIdx.y * 32 + 32); d += 8) {
     const __nv_bfloat16* row = Bv + static_cast<long long>(h * D + d) * ldb;
     float acc = 0.f;
@@ -1490,13 +1499,13 @@ extern "C" size_t xkv_decode_workspace_bytes(int Hq, int S, int T, int rv) {
   return b + 1024;
 }
 
-extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const void* A_k, int64_t lda_k, int rk,
+extern "C" int xkv_decode_attention_lse(const void* q, int Hq, int H, int D, const void* A_k, int64_t lda_k, int rk,
                                     const void* Vk_layer, int64_t ldv_k, const void* A_v, int64_t lda_v, int rv,
                                     const void* Vv_layer, int64_t ldv_v, int S, const void* cos, const void* sin,
                                     int64_t ld_cs, const void* k_tail, const void* v_tail, int T, int64_t tail_stride_h,
                                     int64_t tail_stride_t, float scale, void* out, void* workspace,
                                     size_t workspace_bytes, const void* cos_t, const void* sin_t, int64_t ld_t,
-                                    void* stream) {
+                                    void* stream, float* lse_out) {
   XKV_REQUIRE(q && A_k && Vk_layer && A_v && Vv_layer && out && workspace, "decode: null argument");
   XKV_REQUIRE((cos_t == nullptr) == (sin_t == nullptr), "decode: cos_t and sin_t must both be given or both be null");
   XKV_REQUIRE(cos_t == nullptr || (cos != nullptr && ld_t % 128 == 0 && ld_t >= S &&
@@ -1686,7 +1695,7 @@ extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const v
   combine_kernel<<<dim3(Hq, (D + 31) / 32), 256, rv * sizeof(float), st>>>(
       U, 1, 0, rv, static_cast<const __nv_bfloat16*>(Vv_layer), ldv_v, prob, ldl, S,
       T, static_cast<const __nv_bfloat16*>(v_tail), tail_stride_h, tail_stride_t, rowsum, qpk, D,
-      static_cast<__nv_bfloat16*>(out));
+      static_cast<__nv_bfloat16*>(out), chunk_max, lse_out);
   XKV_LAUNCHED();
   return 0;
 }
@@ -1721,3 +1730,13 @@ extern "C" int xkv_rope_tables_dim_major(const void* cos, const void* sin, int64
 extern "C" void xkv_decode_force_tiled(int on) { g_force_tiled_scores = on != 0; }
 /* test hook: which persistent scores kernel to use when several apply (0 automatic) */
 extern "C" void xkv_decode_set_variant(int variant) { g_scores_variant = variant; }
+
+extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const void* A_k, int64_t lda_k, int rk,
+                                    const void* Vk_layer, int64_t ldv_k, const void* A_v, int64_t lda_v, int rv,
+                                    const void* Vv_layer, int64_t ldv_v, int S, const void* cos, const void* sin,
+                                    int64_t ld_cs, const void* k_tail, const void* v_tail, int T, int64_t tail_stride_h,
+                                    int64_t tail_stride_t, float scale, void* out, void* workspace,
+                                    size_t workspace_bytes, const void* cos_t, const void* sin_t, int64_t ld_t,
+                                    void* stream) {
+  return xkv_decode_attention_lse(q, Hq, H, D, A_k, lda_k, rk, Vk_layer, ldv_k, A_v, lda_v, rv, Vv_layer, ldv_v, S, cos, sin, ld_cs, k_tail, v_tail, T, tail_stride_h, tail_stride_t, scale, out, workspace, workspace_bytes, cos_t, sin_t, ld_t, stream, nullptr);
+}

@@ -52,3 +52,32 @@ def allreduce_gram(local_grams: Sequence[torch.Tensor], group=None) -> None:
 
     for g in local_grams:
         dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+
+
+def merge_partial_attention(outs: torch.Tensor, lses: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Flash-decoding merge of P partial attentions over disjoint token sets.
+
+    outs: (P, Hq, D) normalised partial outputs (softmax over each shard's own tokens), lses: (P, Hq) log-sum-exp of each
+    shard's scaled scores.  Returns (out (Hq, D) fp32, lse (Hq,)) of the softmax over the union of the tokens:
+        lse = log sum_p exp(lse_p),   out = sum_p exp(lse_p - lse) out_p.
+    A shard without tokens contributes lse_p = -inf (weight 0)."""
+    lses = lses.float()
+    lse = torch.logsumexp(lses, dim=0)
+    w = torch.exp(lses - lse[None]).nan_to_num(0.0)
+    return (w[:, :, None] * outs.float()).sum(0), lse
+
+
+def merge_token_shards(out_local: torch.Tensor, lse_local: torch.Tensor, group=None) -> torch.Tensor:
+    """Decode over a token-sharded factored cache: every rank has run
+    ``ops.decode_attention(..., lse_out=lse_local)`` over ITS token rows of A_k / A_v (the decode tail lives on one rank,
+    the others pass none); one all-gather of (Hq x (D + 1)) floats per layer and a local merge give every rank the
+    attention output over the whole context.  Returns (Hq, D) in out_local's dtype."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    packed = torch.cat([out_local.float(), lse_local.float()[:, None]], dim=1).contiguous()   # (Hq, D + 1)
+    gathered = [torch.empty_like(packed) for _ in range(world)]
+    dist.all_gather(gathered, packed, group=group)
+    allp = torch.stack(gathered)
+    out, _ = merge_partial_attention(allp[:, :, :-1], allp[:, :, -1])
+    return out.to(out_local.dtype)
