@@ -215,11 +215,13 @@ def run_xkv_arm(args):
         launches0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    torch.cuda.profiler.start()      # no-op unless run under `ncu --profile-from-start off` (launch list of the timed steps)
     e0.record()
     for _ in range(args.steps):
         out = step()
     e1.record()
     barrier()
+    torch.cuda.profiler.stop()
     ms_total = e0.elapsed_time(e1)
     launches = ops.launch_count() - launches0
     if launches_per_step is not None:
