@@ -1,4 +1,5 @@
-"""Robustness probe: inputs whose energy sits in a few channels (unmixed columns with decaying scales; outlier channels)."""
+"""Robustness probe: inputs whose energy sits in a few channels (unmixed columns with decaying scales; outlier channels)
+against the reference SVD, per option set.  usage: [ONLY=substr] python tools/probe_outlier_inputs.py '[{}, {"pass0_terms": 3}]'"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
