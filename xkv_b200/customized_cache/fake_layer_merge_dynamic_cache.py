@@ -15,8 +15,10 @@ MLA caller uses the return value): ``K^_l = rope(bf16(A_k V_k[l]^T))`` through t
 the bf16 RoPE kernel.  The decode hot path does not go through that: the patched attention forward calls
 :meth:`FakeLayerMergingCache.attend`, which runs the fused reconstruct+attention kernel.
 
-Only the SVD branch lives on the GPU path; ``layer_merge_impl='slerp'`` raises ``NotImplementedError``
-(next row).  Batch size 1 (the configs of BASELINE.json); larger batches raise.
+``layer_merge_impl='slerp'`` (the MiniCache baseline, reference cache:183-197) runs the row-wise SLERP kernel and
+keeps the merged layers dense, as the reference does.  Batch size 1 (every configuration of BASELINE.json); larger
+batches raise ``XkvError``: the reference's batched SVD is one SVD per sample, and padded batches would need an
+attention mask in the fused decode kernel.
 """
 from __future__ import annotations
 
