@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
-    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the K / V batches are spread over")
+    ap.add_argument("--streams", type=int, default=6, help="CUDA streams the K / V batches are spread over")
     ap.add_argument("--e2e-chunk", type=int, default=1, help="layer groups per pipelined chunk of the host-buffer path")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from the host instead of replaying a CUDA graph")
     return ap.parse_args()
@@ -103,7 +103,7 @@ def workload_config(args):
         "workload": f"Llama-3.1-8B-shaped KV, {LAYERS} layers x {HEADS} KV heads x {HEAD_DIM}, {args.tokens} tokens, "
                     f"batch 1, xKV-{GROUP} ({LAYERS // GROUP} groups), rank_k {RANK_K} / rank_v {RANK_V}",
         "tokens": args.tokens, "groups_per_gpu": LAYERS // GROUP, "parallelism": f"layer-groups x{args.gpus}",
-        "l2": "inputs (8.6 GB per step) exceed L2",
+        "l2": "inputs (8.6 GB per step) exceed L2", "cuda_streams": args.streams,
     }
 
 
