@@ -1,1 +1,5 @@
-from xkv_b200.customized_cache import FakeLayerMergingCache, method_to_cache_obj  # noqa: F401
+"""Import shim: ``xKV.customized_cache`` resolves to the B200 implementation."""
+import xkv_b200.customized_cache as _impl
+
+FakeLayerMergingCache = _impl.FakeLayerMergingCache
+method_to_cache_obj = _impl.method_to_cache_obj

@@ -23,6 +23,23 @@ from transformers.models.llama.modeling_llama import LlamaAttention, apply_rotar
 from ..customized_cache.fake_layer_merge_dynamic_cache import FakeLayerMergingCache
 
 
+def _heads(proj, hidden_states: torch.Tensor, head_dim: int) -> torch.Tensor:
+    """(bs, q_len, hidden) -> (bs, heads, q_len, head_dim) view of a projection's output."""
+    bs, q_len = hidden_states.shape[:2]
+    return proj(hidden_states).view(bs, q_len, -1, head_dim).transpose(1, 2)
+
+
+def _rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
+    return apply_rotary_pos_emb(x, x, cos, sin)[0]
+
+
+def _dense_attention(module, q, k, v, attention_mask, **kwargs):
+    if module.config._attn_implementation != "sdpa":
+        raise ValueError("Only sdpa is supported for now")
+    return ALL_ATTENTION_FUNCTIONS["sdpa"](module, q, k, v, attention_mask, scaling=module.scaling,
+                                           dropout=module.attention_dropout if module.training else 0.0, **kwargs)
+
+
 def xKV_llama_forward(  # noqa: N802
     self,
     hidden_states: torch.Tensor,
@@ -33,52 +50,28 @@ def xKV_llama_forward(  # noqa: N802
     cache_position: Optional[torch.LongTensor] = None,
     **kwargs,
 ):
-    cache = past_key_values if past_key_values is not None else past_key_value
-    input_shape = hidden_states.shape[:-1]
-    q_len = hidden_states.shape[1]
-    hidden_shape = (*input_shape, -1, self.head_dim)
-    query_states = self.q_proj(hidden_states).view(hidden_shape).transpose(1, 2)
-    key_states = self.k_proj(hidden_states).view(hidden_shape).transpose(1, 2)
-    value_states = self.v_proj(hidden_states).view(hidden_shape).transpose(1, 2)
-
+    cache = past_key_value if past_key_values is None else past_key_values
+    out_shape = (*hidden_states.shape[:-1], -1)
     cos, sin = position_embeddings
-    is_prefill = q_len > 1  # auto-regressive use, as in the reference
-    query_states, _ = apply_rotary_pos_emb(query_states, query_states, cos, sin)
+    q = _rope(_heads(self.q_proj, hidden_states, self.head_dim), cos, sin)
+    k_pre = _heads(self.k_proj, hidden_states, self.head_dim)       # PRE-RoPE: what the cache compresses
+    v = _heads(self.v_proj, hidden_states, self.head_dim)
+    k = _rope(k_pre, cos, sin)
 
-    if cache is not None:
-        if is_prefill:
-            assert isinstance(cache, FakeLayerMergingCache)
-            cache.update(key_states, value_states, self.layer_idx, mode="prefill", cos=cos, sin=sin,
-                         return_dense=False)
-            key_states, _ = apply_rotary_pos_emb(key_states, key_states, cos, sin)
-        else:
-            key_pre_rope = key_states
-            key_states, _ = apply_rotary_pos_emb(key_states, key_states, cos, sin)
-            fused = None
-            if isinstance(cache, FakeLayerMergingCache) and getattr(self, "xkv_fused_decode", True):
-                fused = cache.attend(query_states, key_states, value_states, self.layer_idx, self.scaling,
-                                     key_pre_rope=key_pre_rope, cos=cos, sin=sin)
+    if cache is not None and hidden_states.shape[1] > 1:
+        # prefill: the cache gets the pre-RoPE keys and the tables; attention below runs on the ORIGINAL K / V
+        assert isinstance(cache, FakeLayerMergingCache)
+        cache.update(k_pre, v, self.layer_idx, mode="prefill", cos=cos, sin=sin, return_dense=False)
+    elif cache is not None:
+        # decode: fused attention over the factored cache when the layer's group is factored, else the dense path
+        if isinstance(cache, FakeLayerMergingCache) and getattr(self, "xkv_fused_decode", True):
+            fused = cache.attend(q, k, v, self.layer_idx, self.scaling, key_pre_rope=k_pre, cos=cos, sin=sin)
             if fused is not None:
-                attn_output = fused.transpose(1, 2).reshape(*input_shape, -1).contiguous()
-                return self.o_proj(attn_output), None
-            key_states, value_states = cache.update(key_states, value_states, self.layer_idx, mode="decode")
+                return self.o_proj(fused.transpose(1, 2).reshape(out_shape).contiguous()), None
+        k, v = cache.update(k, v, self.layer_idx, mode="decode")
 
-    if self.config._attn_implementation != "sdpa":
-        raise ValueError("Only sdpa is supported for now")
-    attention_interface = ALL_ATTENTION_FUNCTIONS["sdpa"]
-    attn_output, attn_weights = attention_interface(
-        self,
-        query_states,
-        key_states,
-        value_states,
-        attention_mask,
-        dropout=0.0 if not self.training else self.attention_dropout,
-        scaling=self.scaling,
-        **kwargs,
-    )
-    attn_output = attn_output.reshape(*input_shape, -1).contiguous()
-    attn_output = self.o_proj(attn_output)
-    return attn_output, attn_weights
+    attn_output, attn_weights = _dense_attention(self, q, k, v, attention_mask, **kwargs)
+    return self.o_proj(attn_output.reshape(out_shape).contiguous()), attn_weights
 
 
 def _bind(model, expected_cls, forward, what: str):

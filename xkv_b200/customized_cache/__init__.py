@@ -1,6 +1,9 @@
-"""Cache classes of the xKV path (mirror of the reference's ``xKV/customized_cache/__init__.py:4-6``)."""
-from .fake_layer_merge_dynamic_cache import FakeLayerMergingCache  # noqa: F401
+"""Cache classes of the xKV path, keyed by method name (the registry ``prepare_cache`` looks classes up in; the
+reference keeps the same mapping in ``xKV/customized_cache/__init__.py:4-6``)."""
+from . import fake_layer_merge_dynamic_cache as _fake
 
-method_to_cache_obj = {
-    "xKV": FakeLayerMergingCache,
-}
+FakeLayerMergingCache = _fake.FakeLayerMergingCache
+
+method_to_cache_obj = dict(xKV=FakeLayerMergingCache)
+
+__all__ = ["FakeLayerMergingCache", "method_to_cache_obj"]
