@@ -343,6 +343,30 @@ def run_xkv_arm(args):
                          "note": "whole decode step (scores + softmax + P*A_v + combine) against the K^ reconstruction flops"},
         }
         del ws
+        # context, not a target: the library attention (torch SDPA, GQA) over an UNCOMPRESSED bf16 cache of one layer of
+        # the same shape -- what the reference's decode costs once its dense K^ / V^ exist (llama.py:58-69).  It reads
+        # 268 MB per layer against the factored cache's 168 MB per layer (and 5.7x less resident memory).
+        if rank == 0:
+            try:
+                import torch.nn.functional as F
+
+                kd = torch.randn(1, HEADS, S, HEAD_DIM, device=dev, dtype=torch.bfloat16)
+                vd = torch.randn(1, HEADS, S, HEAD_DIM, device=dev, dtype=torch.bfloat16)
+                qd = torch.randn(1, hq, 1, HEAD_DIM, device=dev, dtype=torch.bfloat16)
+                for _ in range(3):
+                    F.scaled_dot_product_attention(qd, kd, vd, enable_gqa=True)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(32):
+                    F.scaled_dot_product_attention(qd, kd, vd, enable_gqa=True)
+                e1.record()
+                torch.cuda.synchronize()
+                line["decode"]["dense_sdpa_us_per_layer"] = 1e3 * e0.elapsed_time(e1) / 32
+                line["decode"]["dense_sdpa_note"] = ("torch SDPA over an uncompressed bf16 cache of the same shape "
+                                                     "(library kernel, reported for context)")
+                del kd, vd, qd
+            except Exception as ex:   # an older torch without enable_gqa: the context number is optional
+                line["decode"]["dense_sdpa_note"] = f"not measured: {type(ex).__name__}"
 
     # ---- end to end through the public API with HOST buffers ----
     if not args.no_e2e:
