@@ -81,6 +81,15 @@ def test_decode_attention_matches_oracle(S, H, D, qpk, rk, rv, T, G, layer, rope
         lib.xkv_decode_set_variant(0)
 
 
+@pytest.mark.parametrize("S,T", [(300, 700), (256, 90), (1024, 3000)])
+def test_dense_tail_longer_than_a_softmax_chunk(S, T):
+    """Long generations after a short prompt: the dense decode tail spans several of the softmax's 16 chunks (each CTA
+    scores the tail tokens of its own chunk; an earlier version let the last chunk's CTA score all of them while the other
+    CTAs were already reading those scores)."""
+    _case(S, 2, 128, 4, 64, 64, T, 2, 1, True)
+    _case(S, 4, 64, 2, 32, 64, T, 1, 0, False)
+
+
 def test_decode_large_rank_falls_back_to_tiled_kernel():
     # r_k = 1024: one head's slice is 256 KiB > 128 KiB of shared memory
     _case(1024, 2, 128, 4, 1024, 256, 2, 4, 1, True)

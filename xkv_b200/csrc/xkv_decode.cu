@@ -1312,7 +1312,7 @@ __global__ void __launch_bounds__(256) rope_tables_dim_major_kernel(const __nv_b
 }
 
 // Softmax over L = S + T scores of one q-head, two launches, SM_CHUNKS CTAs per head:
-//   pass 1: per-chunk max (the CTA of the last chunk first scores the T dense tail tokens: scale * q . k_tail)
+//   pass 1: per-chunk max (a CTA first scores the dense tail tokens that fall into its chunk: scale * q . k_tail)
 //   pass 2: global max from the chunk maxima, p = exp(s - max) written as bf16 (the GEMM operand),
 //           per-chunk sums of p in fp32 (added up by the combine kernel).
 constexpr int SM_CHUNKS = 16;
@@ -1327,9 +1327,13 @@ __global__ void __launch_bounds__(256) softmax_max_kernel(float* __restrict__ sc
   float* s = scores + hq * ld;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = S + T;
-  if (ch == SM_CHUNKS - 1 && T > 0) {
+  const int per = ((L + SM_CHUNKS - 1) / SM_CHUNKS + 3) & ~3;   // multiple of 4: chunk starts stay 16-byte aligned
+  const int i0 = ch * per, i1 = min(L, i0 + per);
+  // every CTA scores the dense tail tokens that fall into ITS OWN chunk (no CTA reads a score another CTA writes)
+  const int t0 = max(i0, S) - S, t1 = i1 - S;
+  if (T > 0 && t1 > t0) {
     const int h = hq / qpk;
-    for (int t = warp; t < T; t += 8) {
+    for (int t = t0 + warp; t < t1; t += 8) {
       const __nv_bfloat16* kr = k_tail + h * sh + t * st;
       float acc = 0.f;
       for (int d = lane; d < D; d += 32) acc += __bfloat162float(q[hq * D + d]) * __bfloat162float(kr[d]);
@@ -1338,10 +1342,13 @@ __global__ void __launch_bounds__(256) softmax_max_kernel(float* __restrict__ sc
     }
     __syncthreads();
   }
-  const int per = (L + SM_CHUNKS - 1) / SM_CHUNKS;
-  const int i0 = ch * per, i1 = min(L, i0 + per);
   float m = -INFINITY;
-  for (int i = i0 + tid; i < i1; i += 256) m = fmaxf(m, s[i]);
+  const int nvec = max(i1 - i0, 0) >> 2;                        // rows are 256-byte aligned (ld is a multiple of 64)
+  for (int v = tid; v < nvec; v += 256) {
+    const float4 x = *reinterpret_cast<const float4*>(s + i0 + 4 * v);
+    m = fmaxf(fmaxf(m, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
+  }
+  for (int i = i0 + 4 * nvec + tid; i < i1; i += 256) m = fmaxf(m, s[i]);
   m = warp_max(m);
   if (lane == 0) red[warp] = m;
   __syncthreads();
@@ -1363,10 +1370,20 @@ __global__ void __launch_bounds__(256) softmax_exp_kernel(const float* __restric
   float m = -INFINITY;
 #pragma unroll
   for (int c = 0; c < SM_CHUNKS; ++c) m = fmaxf(m, chunk_max[hq * SM_CHUNKS + c]);
-  const int per = (L + SM_CHUNKS - 1) / SM_CHUNKS;
+  const int per = ((L + SM_CHUNKS - 1) / SM_CHUNKS + 3) & ~3;
   const int i0 = ch * per, i1 = min(L, i0 + per);
   float sum = 0.f;
-  for (int i = i0 + tid; i < i1; i += 256) {
+  const int nvec = max(i1 - i0, 0) >> 2;
+  for (int v = tid; v < nvec; v += 256) {
+    const float4 x = *reinterpret_cast<const float4*>(s + i0 + 4 * v);
+    const float e0 = __expf(x.x - m), e1 = __expf(x.y - m), e2 = __expf(x.z - m), e3 = __expf(x.w - m);
+    sum += (e0 + e1) + (e2 + e3);
+    uint2 w;
+    w.x = pack_bf16x2(e0, e1);
+    w.y = pack_bf16x2(e2, e3);
+    *reinterpret_cast<uint2*>(p + i0 + 4 * v) = w;
+  }
+  for (int i = i0 + 4 * nvec + tid; i < i1; i += 256) {
     const float e = __expf(s[i] - m);
     sum += e;
     p[i] = __float2bfloat16_rn(e);
@@ -1380,23 +1397,30 @@ __global__ void __launch_bounds__(256) softmax_exp_kernel(const float* __restric
   }
 }
 
-// U[e] = sum over the split-K slabs of (P A_v)[e]  (8 independent partial sums: the loop is a chain of L2 round trips)
+// U[e] = sum over the split-K slabs of (P A_v)[e].  The sum over ~50 slabs is a chain of L2 round trips, so it is cut four
+// ways: thread (e, g) adds the slabs g, g + 4, ... (all loads independent: one or two round trips), shared memory adds
+// the four partial sums.
 __global__ void __launch_bounds__(256) reduce_u_kernel(const float* __restrict__ slabs, int nslabs, long long slab_stride,
                                                        int total, float* __restrict__ U) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= total) return;
-  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  int sl = 0;
-  for (; sl + 8 <= nslabs; sl += 8) {
+  __shared__ float part[4][64];
+  const int el = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int e = blockIdx.x * 64 + el;
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  if (e < total) {
+    int sl = g;
+    for (; sl + 12 < nslabs; sl += 16) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) a[u] += slabs[(sl + u) * slab_stride + e];
+      for (int u = 0; u < 4; ++u) a[u] += slabs[(sl + 4 * u) * slab_stride + e];
+    }
+    for (; sl < nslabs; sl += 4) a[0] += slabs[sl * slab_stride + e];
   }
-  for (; sl < nslabs; ++sl) a[0] += slabs[sl * slab_stride + e];
-  U[e] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  part[g][el] = (a[0] + a[1]) + (a[2] + a[3]);
+  __syncthreads();
+  if (g == 0 && e < total) U[e] = (part[0][el] + part[1][el]) + (part[2][el] + part[3][el]);
 }
 
 // o[hq][d] = ( sum_j U[hq][j] * Bv[(h*D + d)][j]  +  sum_t p_tail[hq][t] * v_tail[h][t][d] ) / rowsum[hq]
-// grid (Hq, D / 32), 8 warps x 4 output dims.
+// grid (Hq, D / 8), 8 warps x 1 output dim (a short dependency chain per warp; U is re-read by the D / 8 blocks of a head).
 __global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ slabs, int nslabs, long long slab_stride,
                                                       int rv, const __nv_bfloat16* __restrict__ Bv, long long ldb,
                                                       const __nv_bfloat16* __restrict__ prob, long long ldp, int S, int T,
@@ -1423,7 +1447,7 @@ __global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ 
     for (int c = 0; c < SM_CHUNKS; ++c) m = fmaxf(m, chunk_max[hq * SM_CHUNKS + c]);
     lse_out[hq] = m + logf(rs);
   }
-  for (int d = blockIdx.y * 32 + warp; d < min(D, blockIdx.y * 32 + 32); d += 8) {
+  for (int d = blockIdx.y * 8 + warp; d < min(D, blockIdx.y * 8 + 8); d += 8) {
     const __nv_bfloat16* row = Bv + static_cast<long long>(h * D + d) * ldb;
     float acc = 0.f;
     for (int j = lane * 2; j < rv; j += 64) {
@@ -1690,9 +1714,9 @@ extern "C" int xkv_decode_attention_lse(const void* q, int Hq, int H, int D, con
   if (rc) return rc;
   // ---- o = (U Bv_l^T + P_tail V_tail) / rowsum, U reduced over the split-K slabs on the fly ----
   float* U = u_slabs + static_cast<size_t>(split) * Hq * rv;
-  reduce_u_kernel<<<(Hq * rv + 255) / 256, 256, 0, st>>>(u_slabs, split, static_cast<long long>(Hq) * rv, Hq * rv, U);
+  reduce_u_kernel<<<(Hq * rv + 63) / 64, 256, 0, st>>>(u_slabs, split, static_cast<long long>(Hq) * rv, Hq * rv, U);
   XKV_LAUNCHED();
-  combine_kernel<<<dim3(Hq, (D + 31) / 32), 256, rv * sizeof(float), st>>>(
+  combine_kernel<<<dim3(Hq, (D + 7) / 8), 256, rv * sizeof(float), st>>>(
       U, 1, 0, rv, static_cast<const __nv_bfloat16*>(Vv_layer), ldv_v, prob, ldl, S,
       T, static_cast<const __nv_bfloat16*>(v_tail), tail_stride_h, tail_stride_t, rowsum, qpk, D,
       static_cast<__nv_bfloat16*>(out), chunk_max, lse_out);
