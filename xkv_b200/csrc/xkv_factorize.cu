@@ -273,6 +273,7 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
     return 0;
   };
   std::vector<xkv_gemm_problem> ps;
+  xkv_set_launch_predicate(nullptr);   // a call that failed half-way must not leave this thread's launches predicated
   XKV_TRY(mark());  // 0: start
 
   // ---- 1. Gram matrices and their bf16 limbs ----
