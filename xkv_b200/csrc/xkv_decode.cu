@@ -1311,29 +1311,35 @@ __global__ void __launch_bounds__(256) rope_tables_dim_major_kernel(const __nv_b
   }
 }
 
-// Softmax over L = S + T scores of one q-head, two launches, SM_CHUNKS CTAs per head:
-//   pass 1: per-chunk max (a CTA first scores the dense tail tokens that fall into its chunk: scale * q . k_tail)
-//   pass 2: global max from the chunk maxima, p = exp(s - max) written as bf16 (the GEMM operand),
-//           per-chunk sums of p in fp32 (added up by the combine kernel).
-constexpr int SM_CHUNKS = 16;
+// Softmax over L = S + T scores of one q-head in ONE launch, with chunk-local maxima (flash-decoding style): chunk c of
+// the compressed prefix is exactly the token range of split-K slab c of U = P A_v (kps k-blocks of 64 tokens), chunk
+// `nchunk_s` is the dense tail.  A CTA takes the maximum m_c of its chunk, writes p = exp(s - m_c) as bf16 (the GEMM
+// operand) and the fp32 sum l_c; the slab reduction and the combine kernel rescale by exp(m_c - m).  One pass over
+// the scores instead of a max launch and an exp launch, and p keeps full bf16 precision inside every chunk.
+// The tail chunk's CTA first scores its tokens (scale * q . k_tail): nobody else reads those scores.
+constexpr int SM_MAX_CHUNKS = 72;   // >= 64 split-K slabs + the tail chunk
 
-__global__ void __launch_bounds__(256) softmax_max_kernel(float* __restrict__ scores, long long ld, int S, int T,
-                                                          const __nv_bfloat16* __restrict__ q,
-                                                          const __nv_bfloat16* __restrict__ k_tail, long long sh,
-                                                          long long st, int qpk, int D, float scale,
-                                                          float* __restrict__ chunk_max) {
+__global__ void __launch_bounds__(256) softmax_chunk_kernel(float* __restrict__ scores, long long ld, int S, int T,
+                                                            int kps, int nchunk_s, const __nv_bfloat16* __restrict__ q,
+                                                            const __nv_bfloat16* __restrict__ k_tail, long long sh,
+                                                            long long st, int qpk, int D, float scale,
+                                                            __nv_bfloat16* __restrict__ prob, long long ldp,
+                                                            float* __restrict__ chunk_max, float* __restrict__ chunk_sum) {
   __shared__ float red[8];
+  __shared__ float bcast;
   const int hq = blockIdx.x, ch = blockIdx.y;
   float* s = scores + hq * ld;
+  __nv_bfloat16* p = prob + hq * ldp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int L = S + T;
-  const int per = ((L + SM_CHUNKS - 1) / SM_CHUNKS + 3) & ~3;   // multiple of 4: chunk starts stay 16-byte aligned
-  const int i0 = ch * per, i1 = min(L, i0 + per);
-  // every CTA scores the dense tail tokens that fall into ITS OWN chunk (no CTA reads a score another CTA writes)
-  const int t0 = max(i0, S) - S, t1 = i1 - S;
-  if (T > 0 && t1 > t0) {
+  int i0, i1;
+  if (ch < nchunk_s) {
+    i0 = min(S, ch * kps * 64);
+    i1 = min(S, (ch + 1) * kps * 64);
+  } else {
+    i0 = S;
+    i1 = S + T;
     const int h = hq / qpk;
-    for (int t = t0 + warp; t < t1; t += 8) {
+    for (int t = warp; t < T; t += 8) {
       const __nv_bfloat16* kr = k_tail + h * sh + t * st;
       float acc = 0.f;
       for (int d = lane; d < D; d += 32) acc += __bfloat162float(q[hq * D + d]) * __bfloat162float(kr[d]);
@@ -1342,8 +1348,10 @@ __global__ void __launch_bounds__(256) softmax_max_kernel(float* __restrict__ sc
     }
     __syncthreads();
   }
+  // ---- chunk maximum (prefix chunks start at multiples of 64 tokens: 16-byte aligned rows) ----
+  const bool vec = ch < nchunk_s;
+  const int nvec = vec ? max(i1 - i0, 0) >> 2 : 0;
   float m = -INFINITY;
-  const int nvec = max(i1 - i0, 0) >> 2;                        // rows are 256-byte aligned (ld is a multiple of 64)
   for (int v = tid; v < nvec; v += 256) {
     const float4 x = *reinterpret_cast<const float4*>(s + i0 + 4 * v);
     m = fmaxf(fmaxf(m, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
@@ -1354,26 +1362,13 @@ __global__ void __launch_bounds__(256) softmax_max_kernel(float* __restrict__ sc
   __syncthreads();
   if (tid == 0) {
     for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
-    chunk_max[hq * SM_CHUNKS + ch] = m;
+    bcast = m;
+    chunk_max[hq * SM_MAX_CHUNKS + ch] = m;
   }
-}
-
-__global__ void __launch_bounds__(256) softmax_exp_kernel(const float* __restrict__ scores, long long ld, int L,
-                                                          const float* __restrict__ chunk_max,
-                                                          __nv_bfloat16* __restrict__ prob, long long ldp,
-                                                          float* __restrict__ chunk_sum) {
-  __shared__ float red[8];
-  const int hq = blockIdx.x, ch = blockIdx.y;
-  const float* s = scores + hq * ld;
-  __nv_bfloat16* p = prob + hq * ldp;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float m = -INFINITY;
-#pragma unroll
-  for (int c = 0; c < SM_CHUNKS; ++c) m = fmaxf(m, chunk_max[hq * SM_CHUNKS + c]);
-  const int per = ((L + SM_CHUNKS - 1) / SM_CHUNKS + 3) & ~3;
-  const int i0 = ch * per, i1 = min(L, i0 + per);
+  __syncthreads();
+  m = bcast;
+  // ---- p = exp(s - m_c), l_c = sum p (second pass over a few KB that are in L1 / L2) ----
   float sum = 0.f;
-  const int nvec = max(i1 - i0, 0) >> 2;
   for (int v = tid; v < nvec; v += 256) {
     const float4 x = *reinterpret_cast<const float4*>(s + i0 + 4 * v);
     const float e0 = __expf(x.x - m), e1 = __expf(x.y - m), e2 = __expf(x.z - m), e3 = __expf(x.w - m);
@@ -1389,34 +1384,81 @@ __global__ void __launch_bounds__(256) softmax_exp_kernel(const float* __restric
     p[i] = __float2bfloat16_rn(e);
   }
   sum = warp_sum(sum);
+  __syncthreads();
   if (lane == 0) red[warp] = sum;
   __syncthreads();
   if (tid == 0) {
     for (int w = 1; w < 8; ++w) sum += red[w];
-    chunk_sum[hq * SM_CHUNKS + ch] = sum;
+    chunk_sum[hq * SM_MAX_CHUNKS + ch] = sum;
   }
 }
 
-// U[e] = sum over the split-K slabs of (P A_v)[e].  The sum over ~50 slabs is a chain of L2 round trips, so it is cut four
-// ways: thread (e, g) adds the slabs g, g + 4, ... (all loads independent: one or two round trips), shared memory adds
-// the four partial sums.
-__global__ void __launch_bounds__(256) reduce_u_kernel(const float* __restrict__ slabs, int nslabs, long long slab_stride,
-                                                       int total, float* __restrict__ U) {
-  __shared__ float part[4][64];
-  const int el = threadIdx.x & 63, g = threadIdx.x >> 6;
-  const int e = blockIdx.x * 64 + el;
-  float a[4] = {0.f, 0.f, 0.f, 0.f};
-  if (e < total) {
-    int sl = g;
-    for (; sl + 12 < nslabs; sl += 16) {
+// Weights of the chunks in the global softmax of head hq: w_s[c] = exp(m_c - m), m = max_c m_c (0 for an empty chunk,
+// m_c = -inf), stats = {m, sum_c w_c l_c}.  Warp 0 does it in parallel (three chunks per lane); ends with a barrier.
+__device__ __forceinline__ void head_weights(const float* __restrict__ chunk_max, const float* __restrict__ chunk_sum,
+                                             int hq, int nchunks, float* w_s, float* stats) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const float* cm = chunk_max + hq * SM_MAX_CHUNKS;
+    float v[3];
+    float m = -INFINITY;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) a[u] += slabs[(sl + 4 * u) * slab_stride + e];
+    for (int k = 0; k < 3; ++k) {
+      const int c = lane + 32 * k;
+      v[k] = c < nchunks ? cm[c] : -INFINITY;
+      m = fmaxf(m, v[k]);
     }
-    for (; sl < nslabs; sl += 4) a[0] += slabs[sl * slab_stride + e];
+    m = warp_max(m);
+    float rs = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int c = lane + 32 * k;
+      if (c < nchunks) {
+        const float w = __expf(v[k] - m);
+        w_s[c] = w;
+        rs = fmaf(w, chunk_sum[hq * SM_MAX_CHUNKS + c], rs);
+      }
+    }
+    rs = warp_sum(rs);
+    if (lane == 0) {
+      stats[0] = m;
+      stats[1] = rs;
+    }
+  }
+  __syncthreads();
+}
+
+// U[e] = sum over the split-K slabs s of exp(m_s - m) * (P_s A_v)[e]  (P_s is relative to its chunk's maximum m_s).
+// The sum over ~50 slabs is a chain of L2 round trips, so it is cut four ways: thread (e, g) adds the slabs g, g + 4, ...
+// (all loads independent), shared memory adds the four partial sums.
+__global__ void __launch_bounds__(256) reduce_u_kernel(const float* __restrict__ slabs, int nslabs, long long slab_stride,
+                                                       int rv, const float* __restrict__ chunk_max,
+                                                       const float* __restrict__ chunk_sum, int nchunks,
+                                                       float* __restrict__ U) {
+  __shared__ float part[4][64];
+  __shared__ float w_s[SM_MAX_CHUNKS];
+  __shared__ float stats[2];
+  const int hq = blockIdx.y;
+  const int el = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int j = blockIdx.x * 64 + el;
+  const long long e = static_cast<long long>(hq) * rv + j;
+  // the slab values do not depend on the weights: they are in flight while warp 0 works the weights out
+  float v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int sl = g + 4 * k;
+    v[k] = (j < rv && sl < nslabs) ? slabs[sl * slab_stride + e] : 0.f;
+  }
+  head_weights(chunk_max, chunk_sum, hq, nchunks, w_s, stats);
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int sl = g + 4 * k;
+    if (sl < nslabs) a[k & 3] = fmaf(w_s[sl], v[k], a[k & 3]);
   }
   part[g][el] = (a[0] + a[1]) + (a[2] + a[3]);
   __syncthreads();
-  if (g == 0 && e < total) U[e] = (part[0][el] + part[1][el]) + (part[2][el] + part[3][el]);
+  if (g == 0 && j < rv) U[e] = (part[0][el] + part[1][el]) + (part[2][el] + part[3][el]);
 }
 
 // o[hq][d] = ( sum_j U[hq][j] * Bv[(h*D + d)][j]  +  sum_t p_tail[hq][t] * v_tail[h][t][d] ) / rowsum[hq]
@@ -1427,7 +1469,8 @@ __global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ 
                                                       const __nv_bfloat16* __restrict__ v_tail, long long sh, long long st,
                                                       const float* __restrict__ rowsum, int qpk, int D,
                                                       __nv_bfloat16* __restrict__ out,
-                                                      const float* __restrict__ chunk_max, float* __restrict__ lse_out) {
+                                                      const float* __restrict__ chunk_max, int nchunks,
+                                                      float* __restrict__ lse_out) {
   extern __shared__ float u_s[];  // rv floats
   const int hq = blockIdx.x, h = hq / qpk;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1435,16 +1478,16 @@ __global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ 
   (void)nslabs;
   (void)slab_stride;
   __syncthreads();
-  float rs = 0.f;
-#pragma unroll
-  for (int c = 0; c < SM_CHUNKS; ++c) rs += rowsum[hq * SM_CHUNKS + c];
+  // global maximum and denominator from the chunk-local ones; the tail chunk is the last one
+  __shared__ float w_s[SM_MAX_CHUNKS];
+  __shared__ float stats[2];
+  head_weights(chunk_max, rowsum, hq, nchunks, w_s, stats);
+  const float m = stats[0], rs = stats[1];
   const float inv = 1.f / rs;
+  const float w_tail = T > 0 ? w_s[nchunks - 1] : 0.f;
   if (lse_out != nullptr && blockIdx.y == 0 && threadIdx.x == 0) {
     // log-sum-exp of this head's scaled scores over the tokens of THIS call: what a flash-decoding style merge of
     // token shards needs besides the normalised output
-    float m = -INFINITY;
-#pragma unroll
-    for (int c = 0; c < SM_CHUNKS; ++c) m = fmaxf(m, chunk_max[hq * SM_CHUNKS + c]);
     lse_out[hq] = m + logf(rs);
   }
   for (int d = blockIdx.y * 8 + warp; d < min(D, blockIdx.y * 8 + 8); d += 8) {
@@ -1454,9 +1497,10 @@ __global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ 
       const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(row + j);
       acc = fmaf(u_s[j], __bfloat162float(b2.x), fmaf(u_s[j + 1], __bfloat162float(b2.y), acc));
     }
+    float acc_t = 0.f;
     for (int t = lane; t < T; t += 32)
-      acc = fmaf(__bfloat162float(prob[hq * ldp + S + t]), __bfloat162float(v_tail[h * sh + t * st + d]), acc);
-    acc = warp_sum(acc);
+      acc_t = fmaf(__bfloat162float(prob[hq * ldp + S + t]), __bfloat162float(v_tail[h * sh + t * st + d]), acc_t);
+    acc = warp_sum(fmaf(w_tail, acc_t, acc));
     if (lane == 0) out[hq * D + d] = __float2bfloat16_rn(acc * inv);
   }
 }
@@ -1518,7 +1562,7 @@ extern "C" size_t xkv_decode_workspace_bytes(int Hq, int S, int T, int rv) {
   size_t b = 0;
   b += al(Hq * ldl * 4);            // scores
   b += al(128 * ldl * 2);           // probabilities (bf16), padded to a full 128-row tile
-  b += al(2 * Hq * 16 * 4);         // per-chunk max / sum of the softmax
+  b += al(2 * Hq * SM_MAX_CHUNKS * 4);   // per-chunk max / sum of the softmax
   b += al(static_cast<size_t>(split + 1) * Hq * rv * 4);  // split-K slabs of U, then U itself
   return b + 1024;
 }
@@ -1556,8 +1600,8 @@ extern "C" int xkv_decode_attention_lse(const void* q, int Hq, int H, int D, con
   __nv_bfloat16* prob = reinterpret_cast<__nv_bfloat16*>(w);
   w += al(128 * ldl * 2);
   float* rowsum = reinterpret_cast<float*>(w);        // per-chunk sums of p
-  float* chunk_max = rowsum + Hq * SM_CHUNKS;
-  w += al(2 * Hq * SM_CHUNKS * 4);
+  float* chunk_max = rowsum + Hq * SM_MAX_CHUNKS;
+  w += al(2 * Hq * SM_MAX_CHUNKS * 4);
   float* u_slabs = reinterpret_cast<float*>(w);
   w += al(static_cast<size_t>(split + 1) * Hq * rv * 4);
 
@@ -1686,12 +1730,14 @@ extern "C" int xkv_decode_attention_lse(const void* q, int Hq, int H, int D, con
     decode_scores_kernel<64><<<grid, D_THREADS, D_SMEM_BYTES, st>>>(sp);
   }
   XKV_LAUNCHED();
-  // ---- softmax (also scores the dense tail) ----
-  softmax_max_kernel<<<dim3(Hq, SM_CHUNKS), 256, 0, st>>>(scores, ldl, S, T, static_cast<const __nv_bfloat16*>(q),
+  // ---- softmax with chunk-local maxima: chunk c = token range of split-K slab c, last chunk = the dense tail ----
+  const int nkb_p = (S + 63) / 64;
+  const int kps = (nkb_p + split - 1) / split;          // k-blocks per slab, as xkv_gemm_grouped cuts them
+  const int nchunks = split + 1;
+  XKV_REQUIRE(nchunks <= SM_MAX_CHUNKS, "decode: too many softmax chunks");
+  softmax_chunk_kernel<<<dim3(Hq, nchunks), 256, 0, st>>>(scores, ldl, S, T, kps, split, static_cast<const __nv_bfloat16*>(q),
                                                           static_cast<const __nv_bfloat16*>(k_tail), tail_stride_h,
-                                                          tail_stride_t, qpk, D, scale, chunk_max);
-  XKV_LAUNCHED();
-  softmax_exp_kernel<<<dim3(Hq, SM_CHUNKS), 256, 0, st>>>(scores, ldl, static_cast<int>(L), chunk_max, prob, ldl, rowsum);
+                                                          tail_stride_t, qpk, D, scale, prob, ldl, chunk_max, rowsum);
   XKV_LAUNCHED();
   // ---- U = P[:, :S] * A_v  (tokens are the contraction: P K-major, A_v MN-major) ----
   xkv_gemm_problem gp;
@@ -1714,12 +1760,13 @@ extern "C" int xkv_decode_attention_lse(const void* q, int Hq, int H, int D, con
   if (rc) return rc;
   // ---- o = (U Bv_l^T + P_tail V_tail) / rowsum, U reduced over the split-K slabs on the fly ----
   float* U = u_slabs + static_cast<size_t>(split) * Hq * rv;
-  reduce_u_kernel<<<(Hq * rv + 63) / 64, 256, 0, st>>>(u_slabs, split, static_cast<long long>(Hq) * rv, Hq * rv, U);
+  reduce_u_kernel<<<dim3((rv + 63) / 64, Hq), 256, 0, st>>>(u_slabs, split, static_cast<long long>(Hq) * rv, rv, chunk_max,
+                                                            rowsum, nchunks, U);
   XKV_LAUNCHED();
   combine_kernel<<<dim3(Hq, (D + 7) / 8), 256, rv * sizeof(float), st>>>(
       U, 1, 0, rv, static_cast<const __nv_bfloat16*>(Vv_layer), ldv_v, prob, ldl, S,
       T, static_cast<const __nv_bfloat16*>(v_tail), tail_stride_h, tail_stride_t, rowsum, qpk, D,
-      static_cast<__nv_bfloat16*>(out), chunk_max, lse_out);
+      static_cast<__nv_bfloat16*>(out), chunk_max, nchunks, lse_out);
   XKV_LAUNCHED();
   return 0;
 }
