@@ -50,6 +50,48 @@ def test_symmetrize_split_equals_reduce_then_split(n, slabs_n):
         assert torch.equal(hi[b], ref[b][0]) and torch.equal(mid[b], ref[b][1]) and torch.equal(lo[b], ref[b][2])
 
 
+def test_pass_flags_and_launch_predicate():
+    """Device-side conditional passes: flags from the Cholesky pivots; predicated launches leave the skipped matrices'
+    buffers untouched and process the others."""
+    from xkv_b200 import ops
+
+    l, dev = 128, "cuda"
+    torch.manual_seed(3)
+    good = torch.eye(l, device=dev) + 0.01 * torch.randn(l, l, device=dev)
+    good = (good + good.t()) / 2
+    v = torch.randn(l, 3, device=dev)
+    bad = (v @ v.t()) / 3 + 1e-4 * torch.eye(l, device=dev)      # numerically rank 3: tiny pivots after the third
+    bad = bad / bad.diagonal().max()
+    ss = [good.clone(), bad.clone(), good.clone()]
+    linvs = [torch.full((l, l), 7.0, device=dev) for _ in ss]
+    ops.cholesky_inverse(ss, linvs, shift=1e-6)
+    flags = torch.full((3,), -1, device=dev, dtype=torch.int32)
+    ops.pass_flags(linvs, 0.05, flags)
+    torch.cuda.synchronize()
+    assert flags.tolist() == [0, 1, 0]
+    # predicated Cholesky: only matrix 1 is redone (heavier shift); the others keep their inverse bit for bit
+    before = [t.clone() for t in linvs]
+    ss2 = [good.clone(), bad.clone(), good.clone()]
+    with ops.launch_predicate(flags):
+        ops.cholesky_inverse(ss2, linvs, shift=3e-4)
+    torch.cuda.synchronize()
+    assert torch.equal(linvs[0], before[0]) and torch.equal(linvs[2], before[2])
+    assert not torch.equal(linvs[1], before[1])
+    assert torch.equal(ss2[0], good) and torch.equal(ss2[2], good)          # S of a skipped matrix is not even touched
+    # predicated row normalisation
+    ys = [torch.randn(8, 64, device=dev) * 5 for _ in range(3)]
+    keep = [y.clone() for y in ys]
+    with ops.launch_predicate(flags):
+        ops.shift_normalize_rows(ys)
+    torch.cuda.synchronize()
+    assert torch.equal(ys[0], keep[0]) and torch.equal(ys[2], keep[2])
+    assert torch.allclose(ys[1].norm(dim=1), torch.ones(8, device=dev), atol=1e-5)
+    # outside the context everything runs again
+    ops.shift_normalize_rows(ys)
+    torch.cuda.synchronize()
+    assert torch.allclose(ys[0].norm(dim=1), torch.ones(8, device=dev), atol=1e-5)
+
+
 def test_split_bf16_limbs_reconstruct_fp32():
     from xkv_b200 import ops
 

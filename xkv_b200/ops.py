@@ -211,6 +211,34 @@ def rdiag_update(rdiag: Sequence[torch.Tensor], linvs: Sequence[torch.Tensor]) -
                                        linvs[0].stride(0), _stream()))
 
 
+def pass_flags(linvs: Sequence[torch.Tensor], min_pivot: float, flags: torch.Tensor) -> None:
+    """flags[b] = 1 when the Cholesky pass that produced linvs[b] met a pivot L_jj^2 < min_pivot (or a NaN), else 0.
+    `flags`: int32 CUDA tensor with one entry per matrix."""
+    _require_cuda(*linvs, flags)
+    l = linvs[0].shape[0]
+    check(_lib.load().xkv_pass_flags(_ptr_array(linvs), len(linvs), l, linvs[0].stride(0), C.c_float(min_pivot),
+                                     _ptr(flags), _stream()))
+
+
+class launch_predicate:
+    """Context manager: while active, this thread's batched launches of shift_normalize_rows, the batched slab reduction,
+    cholesky_inverse and rdiag_update skip matrix b when flags[b] == 0 ON THE DEVICE (no host synchronisation)."""
+
+    def __init__(self, flags: torch.Tensor):
+        _require_cuda(flags)
+        if flags.dtype != torch.int32:
+            raise _lib.XkvError("launch_predicate: int32 flags required")
+        self.flags = flags
+
+    def __enter__(self):
+        _lib.load().xkv_set_launch_predicate(_ptr(self.flags))
+        return self
+
+    def __exit__(self, *exc):
+        _lib.load().xkv_set_launch_predicate(None)
+        return False
+
+
 def cholesky_inverse(ss: Sequence[torch.Tensor], linvs: Sequence[torch.Tensor], shift: float = 0.0,
                      pivot_floor: float = 1e-12, limbs=None) -> None:
     """Batched (S + shift*I) = L L^T and Linv = L^{-1} in one cluster launch (S is destroyed); `limbs` =
