@@ -135,37 +135,69 @@ __global__ void __launch_bounds__(256) sym_split_kernel(const __grid_constant__ 
     --cnt;
   }
   const int bj = bi + t;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  // thread = (row ty / ty + 16, column pair 2 tx, 2 tx + 1): 8-byte loads per slab, 4-byte stores per limb
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const bool pair_ok = ((ld | ldo | slab_stride) & 1) == 0;   // even strides: the column pairs are 8 / 4-byte aligned
+  auto store2 = [&](long long o, float a, float b) {
+    __nv_bfloat16 h0, m0, l0, h1, m1, l1;
+    split3(a, h0, m0, l0);
+    split3(b, h1, m1, l1);
+    *reinterpret_cast<__nv_bfloat162*>(hi + o) = __halves2bfloat162(h0, h1);
+    *reinterpret_cast<__nv_bfloat162*>(mid + o) = __halves2bfloat162(m0, m1);
+    *reinterpret_cast<__nv_bfloat162*>(lo + o) = __halves2bfloat162(l0, l1);
+  };
+  auto store1 = [&](long long o, float a) {
+    __nv_bfloat16 h, m, l;
+    split3(a, h, m, l);
+    hi[o] = h;
+    mid[o] = m;
+    lo[o] = l;
+  };
 #pragma unroll
-  for (int r = ty; r < 32; r += 8) {
-    const int i = bi * 32 + r, j = bj * 32 + tx;
-    float acc = 0.f;
+  for (int rr = 0; rr < 2; ++rr) {
+    const int r = ty + 16 * rr;
+    const int i = bi * 32 + r, j = bj * 32 + 2 * tx;
+    float a0 = 0.f, a1 = 0.f;
     if (i < n && j < n) {
       const float* p = slabs + static_cast<long long>(i) * ld + j;
-      for (int s = 0; s < num_slabs; ++s) acc += p[static_cast<long long>(s) * slab_stride];
-      if (j >= i) {
-        __nv_bfloat16 h, m, l;
-        split3(acc, h, m, l);
-        const long long o = static_cast<long long>(i) * ldo + j;
-        hi[o] = h;
-        mid[o] = m;
-        lo[o] = l;
+      if (pair_ok && j + 1 < n) {
+        for (int s = 0; s < num_slabs; ++s) {
+          const float2 v = *reinterpret_cast<const float2*>(p + static_cast<long long>(s) * slab_stride);
+          a0 += v.x;
+          a1 += v.y;
+        }
+      } else {
+        for (int s = 0; s < num_slabs; ++s) {
+          a0 += p[static_cast<long long>(s) * slab_stride];
+          if (j + 1 < n) a1 += p[static_cast<long long>(s) * slab_stride + 1];
+        }
+      }
+      const long long o = static_cast<long long>(i) * ldo + j;
+      if (pair_ok && j + 1 < n && j >= i) {          // both columns on or above the diagonal
+        store2(o, a0, a1);
+      } else {
+        if (j >= i) store1(o, a0);
+        if (j + 1 < n && j + 1 >= i) store1(o + 1, a1);
       }
     }
-    tile[r][tx] = acc;
+    tile[r][2 * tx] = a0;
+    tile[r][2 * tx + 1] = a1;
   }
   __syncthreads();
 #pragma unroll
-  for (int r = ty; r < 32; r += 8) {
-    // mirrored element (i, j) = (bj*32 + r, bi*32 + tx) takes the value computed at (bi*32 + tx, bj*32 + r)
-    const int i = bj * 32 + r, j = bi * 32 + tx;
-    if (i < n && j < n && i > j) {
-      __nv_bfloat16 h, m, l;
-      split3(tile[tx][r], h, m, l);
+  for (int rr = 0; rr < 2; ++rr) {
+    // mirrored elements (i, j), (i, j + 1) = (bj*32 + r, bi*32 + 2 tx [+ 1]) take the values computed at the transposed places
+    const int r = ty + 16 * rr;
+    const int i = bj * 32 + r, j = bi * 32 + 2 * tx;
+    if (i < n && j < n) {
+      const float a0 = tile[2 * tx][r], a1 = tile[2 * tx + 1][r];
       const long long o = static_cast<long long>(i) * ldo + j;
-      hi[o] = h;
-      mid[o] = m;
-      lo[o] = l;
+      if (pair_ok && j + 1 < n && i > j + 1) {        // both strictly below the diagonal
+        store2(o, a0, a1);
+      } else {
+        if (i > j) store1(o, a0);
+        if (j + 1 < n && i > j + 1) store1(o + 1, a1);
+      }
     }
   }
 }
