@@ -281,7 +281,6 @@ def run_xkv_arm(args):
 
         cos, sin = synthetic.llama3_rope(S, HEAD_DIM, device=dev)
         cos, sin = cos[0].contiguous(), sin[0].contiguous()
-        rope_t = ops.rope_tables_dim_major(cos, sin)     # once per prefill: the tables depend on the positions only
         hq = 32
         gen = torch.Generator(device=dev).manual_seed(7)
         q = torch.randn(LAYERS, hq, HEAD_DIM, device=dev, generator=gen).bfloat16()
@@ -297,7 +296,7 @@ def run_xkv_arm(args):
                 i = l % GROUP
                 ops.decode_attention(q[l], gf.key.A, gf.key.V[i * hd:(i + 1) * hd], gf.value.A,
                                      gf.value.V[i * hd:(i + 1) * hd], HEADS, cos, sin, kt[l], vt[l],
-                                     1.0 / math.sqrt(HEAD_DIM), out=o, workspace=ws, rope_t=rope_t)
+                                     1.0 / math.sqrt(HEAD_DIM), out=o, workspace=ws)
 
         for _ in range(3):
             one_token()

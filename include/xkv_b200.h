@@ -220,7 +220,6 @@ XKV_API int xkv_factorize_batch(const void* const* X_host, int batch, int m, int
  *   Vv_layer   (H*D, rv) likewise for values
  *   cos, sin   (S, D) bf16 RoPE tables of the prefill positions (half-split convention), or NULL when the
  *              keys were compressed post-RoPE / need none (re_apply_rope=False, deepseek_v2.py:226)
- *   cos_t, sin_t  optional (D/2, ld_t) bf16 dim-major copies of cos / sin (xkv_rope_tables_dim_major), or NULL
  *   k_tail, v_tail  (H, T, D) bf16 dense decode tokens appended after prefill (keys post-RoPE), T may be 0
  *   out        (Hq, D) bf16 = softmax(scale * q [K^;K_tail]^T) [V^;V_tail] with GQA (Hq/H query heads per kv head)
  * Full-rank K^/V^ are never written to HBM. D in {64, 128}; Hq/H <= 8. */
@@ -230,8 +229,7 @@ XKV_API int xkv_decode_attention(const void* q, int Hq, int H, int D, const void
                                  const void* Vv_layer, int64_t ldv_v, int S, const void* cos, const void* sin,
                                  int64_t ld_cs, const void* k_tail, const void* v_tail, int T, int64_t tail_stride_h,
                                  int64_t tail_stride_t, float scale, void* out, void* workspace,
-                                 size_t workspace_bytes, const void* cos_t, const void* sin_t, int64_t ld_t,
-                                 void* stream);
+                                 size_t workspace_bytes, void* stream);
 /* Same, and lse_out[hq] (Hq floats, may be NULL) = log sum_t exp(scale * q_hq . k_t) over the S + T tokens of THIS call.
  * Token shards of a long context (each rank holds the rows of A_k / A_v of its tokens and the RoPE rows
  * of their positions) each call this on their rows and merge flash-decoding style:
@@ -241,22 +239,16 @@ XKV_API int xkv_decode_attention_lse(const void* q, int Hq, int H, int D, const 
                                      const void* Vv_layer, int64_t ldv_v, int S, const void* cos, const void* sin,
                                      int64_t ld_cs, const void* k_tail, const void* v_tail, int T, int64_t tail_stride_h,
                                      int64_t tail_stride_t, float scale, void* out, void* workspace,
-                                     size_t workspace_bytes, const void* cos_t, const void* sin_t, int64_t ld_t,
-                                     void* stream, float* lse_out);
-/* Dim-major copies of the RoPE tables for the decode kernel that keeps the right factor in tensor memory:
- * cos_t[i][t] = cos[t][i] for i < D/2 (the HF tables repeat the D/2 frequencies in both halves), t < S; columns
- * [S, ld_t) are zeroed.  ld_t must be a multiple of 128 and >= S.  Built once per prefill (the tables depend on the
- * positions only) and passed to xkv_decode_attention as cos_t / sin_t; with cos_t == NULL and cos != NULL the
- * decode falls back to the kernel that keeps the right factor in shared memory. */
-XKV_API int xkv_rope_tables_dim_major(const void* cos, const void* sin, int64_t ld_cs, int S, int D, void* cos_t,
-                                      void* sin_t, int64_t ld_t, void* stream);
+                                     size_t workspace_bytes, void* stream, float* lse_out);
 /* test hook: 1 forces the tile-per-CTA scores kernel (otherwise chosen only when one head's slice of the right
  * factor exceeds 128 KiB of shared memory), 0 restores the automatic choice */
 XKV_API void xkv_decode_force_tiled(int on);
-/* test hook: persistent scores kernel to use where several apply: 0 automatic (score MMA for head_dim 128),
- * 1 FFMA epilogue, 2 score MMA (tcgen05.mma with the rotated keys in TMEM), 3 CTA pair (cta_group::2),
- * 4 transposed (right factor in TMEM; the automatic choice when r_k <= 512 and the dim-major RoPE tables are given) */
+/* test hook: persistent scores kernel to use where several apply: 0 automatic (score MMA for head_dim 128, in clusters
+ * that share the A_k tiles by TMA multicast), 1 FFMA epilogue, 2 score MMA with one independent CTA per kv head */
 XKV_API void xkv_decode_set_variant(int variant);
+/* tuning hook: cluster size of the score-MMA kernel, i.e. how many adjacent kv heads share one multicast copy of each
+ * A_k tile: 0 automatic, else 1, 2, 4 or 8 (reduced to a divisor of the kv-head count the device can keep resident) */
+XKV_API void xkv_decode_set_cluster(int cluster);
 /* RoPE on materialised keys x (rows, H, D) bf16 in place, in the reference's bf16 arithmetic
  * (apply_rotary_pos_emb as called at cache:148,152): x*cos + rotate_half(x)*sin, cos/sin (rows, D). */
 XKV_API int xkv_rope_bf16(void* x, int64_t ld_row, int rows, int H, int D, const void* cos, const void* sin,

@@ -9,7 +9,36 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _case(S, H, D, qpk, rk, rv, T, layers_in_group, layer, rope, seed=0, dim_major_tables=True):
+VARIANTS = {          # name -> (force_tiled, variant, cluster)
+    "auto": (0, 0, 0),     # score MMA in clusters that share the A_k tiles by TMA multicast (head_dim 128)
+    "cl1": (0, 2, 1),      # score MMA, one independent CTA per kv head (round 1's default)
+    "cl2": (0, 0, 2),
+    "cl4": (0, 0, 4),
+    "cl8": (0, 0, 8),
+    "tiled": (1, 0, 0),    # tile-per-CTA kernel (right-factor slice does not fit in shared memory)
+    "ffma": (0, 1, 0),     # persistent kernel with the FFMA epilogue (the head_dim 64 path)
+}
+
+
+def _set_variant(name):
+    from xkv_b200 import _lib
+
+    lib = _lib.load()
+    tiled, variant, cluster = VARIANTS[name]
+    lib.xkv_decode_force_tiled(tiled)
+    lib.xkv_decode_set_variant(variant)
+    lib.xkv_decode_set_cluster(cluster)
+
+
+def _case(S, H, D, qpk, rk, rv, T, layers_in_group, layer, rope, seed=0, shape="flat", device_oracle=False):
+    """One fused decode call against the oracle's arithmetic.  `shape` picks the softmax the inputs produce:
+      flat      q ~ N(0,1), keys of norm ~0.2: an almost uniform average (round 1's only case)
+      sharp     q x 16: a handful of tokens carry the weight, chunk maxima differ by tens of units
+      spike     one prefix token's key x 60: a single dominant token for the heads it aligns with (+/- 30 in score)
+      tail      one DENSE tail token's key x 12: the dominant token lives in the tail chunk
+      equal     A_k = 0: every prefix score is exactly 0 (all-equal scores), only the tail differs
+    Checked: the output (2e-2 of its scale, bf16 tolerance) and the log-sum-exp of the scaled scores (absolute 2e-2:
+    one bf16 ulp of a score of magnitude ~4; relative 1e-2 beyond that)."""
     from oracle import xkv_oracle as O
     from xkv_b200 import ops, synthetic
 
@@ -23,32 +52,49 @@ def _case(S, H, D, qpk, rk, rv, T, layers_in_group, layer, rope, seed=0, dim_maj
     q = torch.randn(Hq, D, generator=g).bfloat16()
     k_tail = torch.randn(H, max(T, 1), D, generator=g).bfloat16()[:, :T]
     v_tail = torch.randn(H, max(T, 1), D, generator=g).bfloat16()[:, :T]
+    if shape == "sharp":
+        q = (q.float() * 16).bfloat16()
+    elif shape == "spike":
+        a_k[(7 * S) // 11] = (a_k[(7 * S) // 11].float() * 60).bfloat16()
+    elif shape == "tail":
+        assert T > 0
+        k_tail[:, T // 2] = (k_tail[:, T // 2].float() * 12).bfloat16()
+    elif shape == "equal":
+        a_k.zero_()
     cos, sin = synthetic.llama3_rope(S, D)
     cos, sin = cos[0], sin[0]
     rows = slice(layer * H * D, (layer + 1) * H * D)
-    # ---- oracle on the CPU ----
-    k_hat = (a_k.float() @ v_k[rows].float().t()).bfloat16().view(S, H, D).permute(1, 0, 2)[None]   # (1,H,S,D)
-    v_hat = (a_v.float() @ v_v[rows].float().t()).bfloat16().view(S, H, D).permute(1, 0, 2)[None]
-    if rope:
-        k_hat = O.apply_rope(k_hat, cos[None], sin[None])
-    kt = k_tail[None] if T else None
-    vt = v_tail[None] if T else None
-    ref = O.decode_attention(q[None, :, None, :].float(), k_hat.float(), v_hat.float(),
-                             kt.float() if T else None, vt.float() if T else None, scaling=1.0 / math.sqrt(D))[0, :, 0]
-    # ---- CUDA path ----
+    scaling = 1.0 / math.sqrt(D)
     dev = "cuda"
-    rope_t = ops.rope_tables_dim_major(cos.to(dev), sin.to(dev)) if (rope and dim_major_tables and D == 128) else None
+    od = dev if device_oracle else "cpu"      # the oracle's formulas, on the device for the 64K cases (CPU: minutes)
+    # ---- oracle arithmetic: dense K^ = bf16(A Vk_l^T), HF RoPE in bf16, cat-append of the tail, SDPA with repeat_kv ----
+    k_hat = (a_k.to(od).float() @ v_k[rows].to(od).float().t()).bfloat16().view(S, H, D).permute(1, 0, 2)[None]
+    v_hat = (a_v.to(od).float() @ v_v[rows].to(od).float().t()).bfloat16().view(S, H, D).permute(1, 0, 2)[None]
+    if rope:
+        k_hat = O.apply_rope(k_hat, cos[None].to(od), sin[None].to(od))
+    kt = k_tail[None].to(od).float() if T else None
+    vt = v_tail[None].to(od).float() if T else None
+    ref = O.decode_attention(q.to(od)[None, :, None, :].float(), k_hat.float(), v_hat.float(), kt, vt,
+                             scaling=scaling)[0, :, 0].cpu()
+    k_all = torch.cat([k_hat.float(), kt], dim=-2) if T else k_hat.float()
+    sc = torch.einsum("hd,hsd->hs", q.to(od).float(), k_all[0].repeat_interleave(qpk, dim=0)) * scaling
+    lse_ref = torch.logsumexp(sc, dim=-1).cpu()
+    # ---- CUDA path ----
+    lse = torch.empty(Hq, dtype=torch.float32, device=dev)
     out = ops.decode_attention(q.to(dev), a_k.to(dev), v_k.to(dev)[rows], a_v.to(dev), v_v.to(dev)[rows], H,
                                cos.to(dev) if rope else None, sin.to(dev) if rope else None,
-                               k_tail.to(dev) if T else None, v_tail.to(dev) if T else None, 1.0 / math.sqrt(D),
-                               rope_t=rope_t)
+                               k_tail.to(dev) if T else None, v_tail.to(dev) if T else None, scaling, lse_out=lse)
     torch.cuda.synchronize()
     got = out.float().cpu()
     scale = ref.abs().max().item()
     err = (got - ref).abs().max().item()
-    print(f"S={S} H={H} D={D} qpk={qpk} rk={rk} rv={rv} T={T} rope={rope}: max|diff|={err:.4f} (out scale {scale:.3f})")
-    assert torch.isfinite(got).all()
+    lse_err = ((lse.cpu() - lse_ref).abs() / lse_ref.abs().clamp(min=2.0)).max().item()
+    peak = torch.softmax(sc, dim=-1).max().item()
+    print(f"S={S} H={H} D={D} qpk={qpk} rk={rk} rv={rv} T={T} rope={rope} {shape}: max|diff|={err:.4f} "
+          f"(out scale {scale:.3f}), lse rel diff {lse_err:.2e}, largest softmax weight {peak:.3f}")
+    assert torch.isfinite(got).all() and torch.isfinite(lse).all()
     assert err <= 2e-2 * max(scale, 1e-3)
+    assert lse_err <= 1e-2
 
 
 @pytest.mark.parametrize(
@@ -62,23 +108,36 @@ def _case(S, H, D, qpk, rk, rv, T, layers_in_group, layer, rope, seed=0, dim_maj
         (300, 3, 128, 1, 96, 160, 1, 2, 0, True),      # MHA (qpk 1), 3 heads: second n-tile half empty, rank not /64
     ],
 )
-@pytest.mark.parametrize("variant", ["auto", "tr", "tiled", "ffma", "pair"])
+@pytest.mark.parametrize("variant", list(VARIANTS))
 def test_decode_attention_matches_oracle(S, H, D, qpk, rk, rv, T, G, layer, rope, variant):
-    """auto: persistent scores kernel with the right-factor slice resident in shared memory (for head_dim 128 the rotated
-    keys go back to TMEM and a second MMA contracts them with q); tr: the transposed persistent kernel (right-factor
-    slice resident in TENSOR memory, token stream as the shared-memory operand, RoPE partners meet by a warp shuffle,
-    dim-major RoPE tables; head_dim 128 and r_k <= 512); tiled: the tile-per-CTA kernel used when that slice
-    does not fit; ffma: persistent kernel with the FFMA epilogue (head_dim 64 path); pair: cta_group::2 CTA pairs."""
-    from xkv_b200 import _lib
-
-    lib = _lib.load()
-    lib.xkv_decode_force_tiled(int(variant == "tiled"))
-    lib.xkv_decode_set_variant({"auto": 0, "tr": 4, "tiled": 0, "ffma": 1, "pair": 3}[variant])
+    """Every scores kernel against the oracle (a requested cluster size is reduced to a divisor of the kv-head count)."""
+    _set_variant(variant)
     try:
-        _case(S, H, D, qpk, rk, rv, T, G, layer, rope, dim_major_tables=(variant in ("auto", "tr")))
+        _case(S, H, D, qpk, rk, rv, T, G, layer, rope)
     finally:
-        lib.xkv_decode_force_tiled(0)
-        lib.xkv_decode_set_variant(0)
+        _set_variant("auto")
+
+
+@pytest.mark.parametrize("shape", ["sharp", "spike", "tail", "equal"])
+@pytest.mark.parametrize("variant", ["auto", "cl1", "cl8", "tiled", "ffma"])
+@pytest.mark.parametrize("S,T", [(4096, 33), (4000, 100), (70, 5)])
+def test_peaked_softmax_matches_oracle(S, T, variant, shape):
+    """Softmax shapes a near-uniform case cannot catch: the chunk-local maxima (one chunk per split-K slab of P A_v plus
+    the dense tail) differ by tens of units, so the exp(m_c - m) rescale of the slab reduction and of the combine does
+    real work; S = 4000 is not a multiple of 64 and its 100-token tail spans several chunk-sized pieces; S = 70 is a
+    single ragged tile."""
+    _set_variant(variant)
+    try:
+        _case(S, 8, 128, 4, 128, 192, T, 4, 2, True, seed=3, shape=shape)
+    finally:
+        _set_variant("auto")
+
+
+@pytest.mark.parametrize("shape", ["flat", "sharp", "spike", "tail"])
+def test_peaked_softmax_at_64k_context(shape):
+    """Config 2's decode shape (65536 tokens + a ragged extra 37, rank 512 / 768, 32 / 8 heads x 128) with every softmax
+    shape; oracle formulas evaluated on the device."""
+    _case(65536 + 37, 8, 128, 4, 512, 768, 77, 4, 1, True, seed=5, shape=shape, device_oracle=True)
 
 
 @pytest.mark.parametrize("S,T", [(300, 700), (256, 90), (1024, 3000)])
@@ -93,25 +152,6 @@ def test_dense_tail_longer_than_a_softmax_chunk(S, T):
 def test_decode_large_rank_falls_back_to_tiled_kernel():
     # r_k = 1024: one head's slice is 256 KiB > 128 KiB of shared memory
     _case(1024, 2, 128, 4, 1024, 256, 2, 4, 1, True)
-
-
-def test_transposed_kernel_all_k_blocks_in_tensor_memory_and_the_eighth_in_shared_memory():
-    # r_k = 448: seven 64-wide K blocks, all in TMEM; r_k = 512: the eighth block goes through shared memory (SS form);
-    # r_k = 456: ragged last block; several token tiles per CTA at 148 CTAs needs S > 148 * 128 / H
-    from xkv_b200 import _lib
-
-    _lib.load().xkv_decode_set_variant(4)
-    try:
-        _tr_cases()
-    finally:
-        _lib.load().xkv_decode_set_variant(0)
-
-
-def _tr_cases():
-    _case(3000, 8, 128, 4, 448, 192, 2, 4, 1, True)
-    _case(3000, 8, 128, 4, 456, 192, 0, 4, 0, True)
-    _case(40000, 8, 128, 4, 512, 256, 3, 4, 2, True)
-    _case(5000, 2, 128, 8, 512, 128, 1, 2, 1, False)
 
 
 def test_token_shards_merge_to_the_unsharded_attention():
@@ -152,19 +192,6 @@ def test_token_shards_merge_to_the_unsharded_attention():
     print(f"token shards x{world}: max|diff| = {err:.5f} (output scale {scale_out:.3f}), lse diff {(lse - lse_full).abs().max().item():.2e}")
     assert err <= 2e-2 * scale_out
     assert (lse - lse_full).abs().max().item() < 1e-3
-
-
-def test_rope_tables_dim_major():
-    from xkv_b200 import ops, synthetic
-
-    S, D = 1000, 128
-    cos, sin = synthetic.llama3_rope(S, D)
-    cos, sin = cos[0].cuda(), sin[0].cuda()
-    ct, st = ops.rope_tables_dim_major(cos, sin, capacity=1100)
-    torch.cuda.synchronize()
-    assert ct.shape == (64, 1152) and st.shape == (64, 1152)
-    assert torch.equal(ct[:, :S], cos[:, :64].t()) and torch.equal(st[:, :S], sin[:, :64].t())
-    assert ct[:, S:].abs().max().item() == 0 and st[:, S:].abs().max().item() == 0
 
 
 def test_rope_bf16_matches_hf_formula():

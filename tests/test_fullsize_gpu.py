@@ -122,8 +122,7 @@ def test_full_size_decode_matches_oracle_arithmetic_on_device():
     k_hat = O.apply_rope(k_hat, cos[None], sin[None])
     ref = O.decode_attention(q[None, :, None, :].float(), k_hat.float(), v_hat.float(), k_tail[None].float(),
                              v_tail[None].float(), scaling=1.0 / math.sqrt(D))[0, :, 0]
-    out = ops.decode_attention(q, a_k, v_k[rows], a_v, v_v[rows], H, cos, sin, k_tail, v_tail, 1.0 / math.sqrt(D),
-                               rope_t=ops.rope_tables_dim_major(cos, sin))
+    out = ops.decode_attention(q, a_k, v_k[rows], a_v, v_v[rows], H, cos, sin, k_tail, v_tail, 1.0 / math.sqrt(D))
     torch.cuda.synchronize()
     scale = ref.abs().max().item()
     err = (out.float() - ref).abs().max().item()

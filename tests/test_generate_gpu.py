@@ -168,3 +168,66 @@ def test_patched_deepseek_v2_mla_matches_oracle_cache():
     bad = generate_consecutive_xKV_config(num_layers=3, end_layer=-1, group_size=3, rank_k=256, rank_v=64)
     with pytest.raises(ValueError, match="merge_v"):
         model(input_ids=ids[:, :300], past_key_values=FakeLayerMergingCache(bad), use_cache=True)
+
+
+def _windowed_model(family: str, window: int):
+    if family == "mistral":
+        from transformers import MistralConfig, MistralForCausalLM
+
+        cfg = MistralConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=4, num_attention_heads=8,
+                            num_key_value_heads=2, head_dim=64, vocab_size=512, max_position_embeddings=4096,
+                            sliding_window=window)
+        cls = MistralForCausalLM
+    else:
+        from transformers import Qwen2Config, Qwen2ForCausalLM
+
+        cfg = Qwen2Config(hidden_size=512, intermediate_size=512, num_hidden_layers=4, num_attention_heads=8,
+                          num_key_value_heads=2, vocab_size=512,   # head_dim = 512 / 8 = 64 max_position_embeddings=4096, sliding_window=window,
+                          use_sliding_window=True, max_window_layers=2)   # layers 2, 3 slide, layers 0, 1 attend fully
+        cls = Qwen2ForCausalLM
+    cfg._attn_implementation = "sdpa"
+    torch.manual_seed(0)
+    return cls(cfg).to(device="cuda", dtype=torch.bfloat16).eval()
+
+
+@pytest.mark.parametrize("family,window", [("mistral", 256), ("mistral", 4096), ("qwen", 256)])
+def test_sliding_window_checkpoints_match_oracle_cache(family, window):
+    """Reference mistral.py:69 forwards ``sliding_window`` to SDPA, whose mask hides tokens beyond the window.  The
+    fused decode kernel has no window, so a layer whose context outgrew its window must take the dense path (and the
+    fused path otherwise): decode logits against the oracle cache with a window SHORTER than the 700-token prompt,
+    with one that is longer (fused kernel runs), and on a Qwen2 model where only some layers slide."""
+    from tests.oracle_cache import OracleCache
+    from xkv_b200 import ops
+    from xkv_b200.configurations import generate_consecutive_xKV_config
+    from xkv_b200.customized_cache import FakeLayerMergingCache
+    from xkv_b200.patch import KVCompress
+
+    model = _windowed_model(family, window)
+    cfg = generate_consecutive_xKV_config(num_layers=4, end_layer=-1, group_size=2, rank_k=64, rank_v=128)
+    KVCompress(xKV_config=cfg)(model)
+    ids = torch.randint(0, 512, (1, 700), device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    lg_ours, _ = _decode_logits(model, FakeLayerMergingCache(cfg), ids, steps=4)
+    for layer in model.model.layers:
+        layer.self_attn.xkv_fused_decode = False
+    lg_ref, _ = _decode_logits(model, OracleCache(cfg), ids, steps=4)
+    # the same model with the window ignored (what the fused kernel would compute): must differ when the window bites
+    torch.cuda.synchronize()
+    assert torch.allclose(lg_ours[0], lg_ref[0], atol=1e-3)
+    dev = (lg_ours[1:] - lg_ref[1:]).abs().max().item()
+    scale = lg_ref[1:].abs().max().item()
+    print(f"{family} window {window}: decode logits max |ours - oracle| = {dev:.4f} (logit scale {scale:.3f})")
+    assert dev <= 5e-2 * scale
+    # which path ran: count fused-decode launches of one more step
+    for layer in model.model.layers:
+        layer.self_attn.xkv_fused_decode = True
+    cache = FakeLayerMergingCache(cfg)
+    out = model(input_ids=ids, past_key_values=cache, use_cache=True)
+    calls = []
+    orig = ops.decode_attention
+    ops.decode_attention = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    try:
+        model(input_ids=out.logits[:, -1].argmax(-1, keepdim=True), past_key_values=cache, use_cache=True)
+    finally:
+        ops.decode_attention = orig
+    expect = {("mistral", 256): 0, ("mistral", 4096): 4, ("qwen", 256): 2}[(family, window)]
+    assert len(calls) == expect, f"{len(calls)} layers used the fused kernel, expected {expect}"

@@ -1,4 +1,9 @@
-"""One decode token (32 layers) over random factors, bracketed by cudaProfilerStart/Stop (for ncu)."""
+"""Decode layers over random factors at config 2's shape, bracketed by cudaProfilerStart/Stop (for ncu).
+
+    python tools/run_decode_once.py [S] [layers] [--cluster 0|1|2|4|8] [--variant N] [--graph]
+
+Prints one JSON line: microseconds per layer enqueued from the host, and (with --graph) replayed as a CUDA graph."""
+import argparse
 import json
 import math
 import os
@@ -6,11 +11,19 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from xkv_b200 import ops, synthetic
+from xkv_b200 import _lib, ops, synthetic
 
-S = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
-layers = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-H, D, HQ, RK, RV, G = 8, 128, 32, 512, 768, 4
+ap = argparse.ArgumentParser()
+ap.add_argument("S", type=int, nargs="?", default=65536)
+ap.add_argument("layers", type=int, nargs="?", default=4)
+ap.add_argument("--cluster", type=int, default=0)
+ap.add_argument("--variant", type=int, default=0)
+ap.add_argument("--graph", action="store_true")
+ap.add_argument("--rk", type=int, default=512)
+ap.add_argument("--rv", type=int, default=768)
+args = ap.parse_args()
+S, layers = args.S, args.layers
+H, D, HQ, RK, RV, G = 8, 128, 32, args.rk, args.rv, 4
 n = G * H * D
 dev = "cuda"
 a_k = torch.randn(S, RK, device=dev).bfloat16()
@@ -19,21 +32,20 @@ v_k = torch.randn(n, RK, device=dev).bfloat16()
 v_v = torch.randn(n, RV, device=dev).bfloat16()
 cos, sin = synthetic.llama3_rope(S, D, device=dev)
 cos, sin = cos[0].contiguous(), sin[0].contiguous()
-rope_t = None if os.environ.get("XKV_NO_ROPE_T") else ops.rope_tables_dim_major(cos, sin)
 q = torch.randn(HQ, D, device=dev).bfloat16()
 kt = torch.randn(H, 1, D, device=dev).bfloat16()
 vt = torch.randn(H, 1, D, device=dev).bfloat16()
-if os.environ.get("XKV_VARIANT"):
-    from xkv_b200 import _lib
-    _lib.load().xkv_decode_set_variant(int(os.environ["XKV_VARIANT"]))
+_lib.load().xkv_decode_set_variant(args.variant)
+_lib.load().xkv_decode_set_cluster(args.cluster)
 ws = torch.empty(ops.decode_workspace_bytes(HQ, S, 1, RV) + 4096, dtype=torch.uint8, device=dev)
+o = torch.empty(HQ, D, dtype=torch.bfloat16, device=dev)
 
 
 def run():
     for l in range(layers):
         i = l % G
         ops.decode_attention(q, a_k, v_k[i * H * D:(i + 1) * H * D], a_v, v_v[i * H * D:(i + 1) * H * D], H, cos, sin,
-                             kt, vt, 1.0 / math.sqrt(D), workspace=ws, rope_t=rope_t)
+                             kt, vt, 1.0 / math.sqrt(D), out=o, workspace=ws)
 
 
 run()
@@ -45,4 +57,18 @@ run()
 e1.record()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
-print(json.dumps({"S": S, "layers": layers, "ms": e0.elapsed_time(e1), "us_per_layer": 1e3 * e0.elapsed_time(e1) / layers}))
+res = {"S": S, "layers": layers, "cluster": args.cluster, "variant": args.variant,
+       "us_per_layer_host_enqueue": 1e3 * e0.elapsed_time(e1) / layers}
+if args.graph:
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        run()
+    g.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(8):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    res["us_per_layer_graph"] = 1e3 * e0.elapsed_time(e1) / (8 * layers)
+print(json.dumps(res))

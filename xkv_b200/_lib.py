@@ -112,12 +112,12 @@ SIGNATURES = {
     "xkv_factorize_sigma_count": (_i, [_i, C.POINTER(FactorizeOptions)]),
     "xkv_decode_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "xkv_decode_attention": (_i, [_vp, _i, _i, _i, _vp, _i64, _i, _vp, _i64, _vp, _i64, _i, _vp, _i64, _i, _vp, _vp, _i64,
-                                  _vp, _vp, _i, _i64, _i64, _f, _vp, _vp, _sz, _vp, _vp, _i64, _vp]),
+                                  _vp, _vp, _i, _i64, _i64, _f, _vp, _vp, _sz, _vp]),
     "xkv_decode_attention_lse": (_i, [_vp, _i, _i, _i, _vp, _i64, _i, _vp, _i64, _vp, _i64, _i, _vp, _i64, _i, _vp, _vp,
-                                      _i64, _vp, _vp, _i, _i64, _i64, _f, _vp, _vp, _sz, _vp, _vp, _i64, _vp, _vp]),
-    "xkv_rope_tables_dim_major": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _i64, _vp]),
+                                      _i64, _vp, _vp, _i, _i64, _i64, _f, _vp, _vp, _sz, _vp, _vp]),
     "xkv_decode_force_tiled": (None, [_i]),
     "xkv_decode_set_variant": (None, [_i]),
+    "xkv_decode_set_cluster": (None, [_i]),
     "xkv_rope_bf16": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "xkv_append_workspace_bytes": (_sz, [_i, _i, _i]),
     "xkv_append_project": (_i, [_vp, _i64, _i, _vp, _i64, _i, _i, _vp, _i64, _vp, _sz, _vp]),

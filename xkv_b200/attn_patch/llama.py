@@ -5,7 +5,9 @@ Semantics kept from the reference:
 * prefill (q_len > 1) hands the PRE-RoPE keys plus cos/sin to ``cache.update(..., mode='prefill')`` and then
   attends on the ORIGINAL keys/values (llama.py:45-50) — compression only affects later decode steps;
 * decode appends the post-RoPE key (llama.py:51-53) and attends over the cache;
-* only the sdpa attention implementation is accepted (llama.py:55-56).
+* only the sdpa attention implementation is accepted (llama.py:55-56);
+* a sliding-window layer whose context exceeds the window attends through SDPA with transformers' mask
+  (mistral.py:69): the fused kernel has no window, so it is bypassed there.
 What differs: the decode step calls ``cache.attend`` — the fused reconstruct + RoPE + GQA-softmax kernel over
 the stored factors — instead of SDPA over dense reconstructed tensors.  Written against the installed
 transformers (``past_key_values`` kwarg; the reference's ``past_key_value`` spelling is accepted too).
@@ -63,8 +65,13 @@ def xKV_llama_forward(  # noqa: N802
         assert isinstance(cache, FakeLayerMergingCache)
         cache.update(k_pre, v, self.layer_idx, mode="prefill", cos=cos, sin=sin, return_dense=False)
     elif cache is not None:
-        # decode: fused attention over the factored cache when the layer's group is factored, else the dense path
-        if isinstance(cache, FakeLayerMergingCache) and getattr(self, "xkv_fused_decode", True):
+        # decode: fused attention over the factored cache when the layer's group is factored, else the dense path.
+        # The fused kernel attends over EVERY cached token; a sliding-window layer (Mistral / Qwen2 checkpoints with
+        # config.sliding_window, reference mistral.py:69) whose context has outgrown its window must honour the mask
+        # transformers built, so it takes the dense path (materialised K^ / V^ + SDPA with that mask).
+        window = kwargs.get("sliding_window")
+        windowed = window is not None and cache.get_seq_length(self.layer_idx) + hidden_states.shape[1] > window
+        if isinstance(cache, FakeLayerMergingCache) and getattr(self, "xkv_fused_decode", True) and not windowed:
             fused = cache.attend(q, k, v, self.layer_idx, self.scaling, key_pre_rope=k_pre, cos=cos, sin=sin)
             if fused is not None:
                 return self.o_proj(fused.transpose(1, 2).reshape(out_shape).contiguous()), None

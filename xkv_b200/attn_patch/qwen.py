@@ -11,5 +11,11 @@ from transformers.models.qwen2.modeling_qwen2 import Qwen2Attention
 from .llama import _bind, xKV_llama_forward
 
 
+def xKV_qwen2_forward(self, *args, **kwargs):  # noqa: N802
+    # Qwen2 layers of type "sliding_attention" carry their window on the module (None for full attention)
+    kwargs.setdefault("sliding_window", getattr(self, "sliding_window", None))
+    return xKV_llama_forward(self, *args, **kwargs)
+
+
 def enable_qwen_xKV_eval(model):  # noqa: N802
-    _bind(model, Qwen2Attention, xKV_llama_forward, "Qwen2Attention")
+    _bind(model, Qwen2Attention, xKV_qwen2_forward, "Qwen2Attention")

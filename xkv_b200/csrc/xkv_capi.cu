@@ -20,6 +20,18 @@ int set_error(const char* fmt, ...) {
   return 1;
 }
 
+int device_sm_count() {
+  static PerDevice<int> sms;
+  int& n = sms();
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
 // cuTensorMapEncodeTiled is a driver-API symbol. It is resolved at run time through the runtime's
 // driver entry-point query so the library has no link-time dependency on libcuda.so and still loads
 // (for symbol checks) on a machine without a GPU driver.
@@ -55,5 +67,5 @@ int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint
 }  // namespace xkv
 
 extern "C" const char* xkv_last_error(void) { return xkv::error_buffer(); }
-extern "C" int xkv_version(void) { return 100; }
+extern "C" int xkv_version(void) { return 200; }
 extern "C" int64_t xkv_launch_count(void) { return xkv::g_launch_count.load(); }

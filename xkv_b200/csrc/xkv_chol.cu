@@ -475,10 +475,10 @@ extern "C" int xkv_cholesky_inverse_limbs(float* const* S_host, float* const* Li
   p.shift = shift;
   p.run_if = launch_predicate();
   const int smem = CH_SMEM_FLOATS * static_cast<int>(sizeof(float));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDevice<bool> attr_set;
+  if (!attr_set()) {
     XKV_CHECK_CUDA(cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr_set() = true;
   }
   int CL = p.nblk >= 6 ? 8 : (p.nblk >= 3 ? 4 : (p.nblk == 2 ? 2 : 1));
   cudaLaunchConfig_t cfg;
@@ -494,20 +494,20 @@ extern "C" int xkv_cholesky_inverse_limbs(float* const* S_host, float* const* Li
   cfg.numAttrs = 1;
   // Wide factors (>= 20 blocks: sketch width 1280 and up, config 4 values) have enough tiles per step for 16 CTAs -- a non-portable cluster
   // size, used only when the device can keep one such cluster per matrix resident at once.
-  static int cl16_clusters = -1;   // resident 16-CTA clusters of this kernel on this device (0: unsupported)
-  if (cl16_clusters < 0) {
-    cl16_clusters = 0;
-    const char* e = getenv("XKV_CHOL_CL16");
-    if (!(e && e[0] == '0') &&
-        cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+  static PerDevice<int> cl16_state;   // 0: not probed; 1 + resident 16-CTA clusters of this kernel on this device
+  int& cl16_probe = cl16_state();
+  if (cl16_probe == 0) {
+    int cl16_clusters = 0;
+    if (cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
       cfg.gridDim = dim3(16, 1, 1);
       attr[0].val.clusterDim.x = 16;
       int n = 0;
       if (cudaOccupancyMaxActiveClusters(&n, chol_cluster_kernel, &cfg) == cudaSuccess) cl16_clusters = n;
     }
     (void)cudaGetLastError();
+    cl16_probe = 1 + cl16_clusters;
   }
-  if (p.nblk >= 20 && cl16_clusters >= batch) CL = 16;
+  if (p.nblk >= 20 && cl16_probe - 1 >= batch) CL = 16;
   cfg.gridDim = dim3(CL, batch, 1);
   attr[0].val.clusterDim.x = CL;
   XKV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, chol_cluster_kernel, p));

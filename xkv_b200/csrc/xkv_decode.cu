@@ -15,7 +15,6 @@
 //            merging, cache:131); their scores / values join the same softmax.
 #include "xkv_common.cuh"
 #include "xkv_host.h"
-#include <cstdlib>
 
 namespace xkv {
 
@@ -36,20 +35,27 @@ struct alignas(64) ScoreParams {
   CUtensorMap b_map;  // Bk_l (H*D x r_k), box {64, 256}
   CUtensorMap b_head_map;  // Bk_l, box {64, D}: one kv head (persistent kernel)
   CUtensorMap q_map;       // q (Hq x D), box {64, 16}: the q rows of one kv head (score MMA)
-  CUtensorMap q8_map;      // q, box {64, 8}: one CTA's half of the score MMA's N rows (pair kernel)
-  CUtensorMap b_half_map;  // Bk_l, box {64, 64}: one CTA's half of a head's rows (pair kernel)
+  CUtensorMap a_mc_map;    // A_k, box {64, 128 / cluster size}: one CTA's slice of a token tile (multicast kernel)
   const __nv_bfloat16* q;    // (Hq, D)
   const __nv_bfloat16* cos;  // (S, D) or null
   const __nv_bfloat16* sin;
-  const __nv_bfloat16* cos_t;  // (D/2, ld_t) dim-major copies of the first D/2 columns of cos / sin, zero padded to
-  const __nv_bfloat16* sin_t;  //   a multiple of 128 tokens (xkv_rope_tables_dim_major), or null
-  const __nv_bfloat16* bk;     // Bk_l (H*D x r_k), the layer's rows of the right factor (transposed kernel)
   float* scores;             // (Hq, ld_scores)
-  long long ld_cs, ld_scores, ld_t, ld_bk;
+  long long ld_cs, ld_scores;
   int S, rk, H, qpk, tiles_n, nkb;
-  int dbg;   // bisect switches of the transposed kernel (XKV_DECODE_DBG, profiling only; 0 in production)
+  int stages;   // ring slots of the score-MMA kernel
   float scale;
+#ifdef XKV_PROBE
+  int dbg;   // tools/probe_decode_scores.cu: bisect switches, compiled out of the library
+#endif
 };
+
+#ifdef XKV_PROBE
+static int g_probe_dbg = 0;
+static int g_probe_stages = 0;
+#define XKV_DBG(P, bit) (((P).dbg & (bit)) != 0)
+#else
+#define XKV_DBG(P, bit) false
+#endif
 
 __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
@@ -96,44 +102,48 @@ __global__ void __launch_bounds__(D_THREADS, 2) decode_scores_kernel(const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // warps 0 / 1: the whole warp runs the loop, one elected lane issues (see elect_one)
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int kb = 0; kb < P.nkb; ++kb) {
-        uint8_t* sA = smem + s * D_STAGE_BYTES;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = 0; kb < P.nkb; ++kb) {
+      uint8_t* sA = smem + s * D_STAGE_BYTES;
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      if (elect_one()) {
         mbar_expect_tx(&full_bar[s], D_STAGE_BYTES);
         tma_load_2d(sA, &P.a_map, &full_bar[s], kb * DBK, m0);
         tma_load_2d(sA + D_A_BYTES, &P.b_map, &full_bar[s], kb * DBK, n0);
-        if (++s == DSTAGES) {
-          s = 0;
-          ph ^= 1u;
-        }
+      }
+      __syncwarp();
+      if (++s == DSTAGES) {
+        s = 0;
+        ph ^= 1u;
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(DBM, DBN, 0, 0);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int kb = 0; kb < P.nkb; ++kb) {
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + s * D_STAGE_BYTES);
-        const uint32_t b_base = a_base + D_A_BYTES;
+    constexpr uint32_t idesc = umma_idesc_bf16(DBM, DBN, 0, 0);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int kb = 0; kb < P.nkb; ++kb) {
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(smem + s * D_STAGE_BYTES);
+      const uint32_t b_base = a_base + D_A_BYTES;
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < DBK / 16; ++k)
           umma_bf16_ss(tmem_base, umma_desc_sw128(a_base + k * 32, 16, 1024), umma_desc_sw128(b_base + k * 32, 16, 1024),
                        idesc, (kb > 0 || k > 0) ? 1u : 0u);
         umma_commit(&empty_bar[s]);
-        if (++s == DSTAGES) {
-          s = 0;
-          ph ^= 1u;
-        }
       }
-      umma_commit(tmem_full_bar);
+      __syncwarp();
+      if (++s == DSTAGES) {
+        s = 0;
+        ph ^= 1u;
+      }
     }
+    if (elect_one()) umma_commit(tmem_full_bar);
+    __syncwarp();
   } else {
     // ============ epilogue: K^ row (this thread's token) -> bf16 -> RoPE -> dot with the q heads ============
     const int qd = warp & 3;
@@ -278,52 +288,58 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(b_bar, static_cast<uint32_t>(P.nkb) * B_KB_BYTES);
       for (int kb = 0; kb < P.nkb; ++kb) tma_load_2d(sB + kb * B_KB_BYTES, &P.b_head_map, b_bar, kb * DBK, h * D);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = slot; tile < ntiles; tile += nslots) {
-        for (int kb = 0; kb < P.nkb; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1u);
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = slot; tile < ntiles; tile += nslots) {
+      for (int kb = 0; kb < P.nkb; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[s], D_A_BYTES);
           tma_load_2d(sA + s * D_A_BYTES, &P.a_map, &full_bar[s], kb * DBK, tile * DBM);
-          if (++s == PA_STAGES) {
-            s = 0;
-            ph ^= 1u;
-          }
+        }
+        __syncwarp();
+        if (++s == PA_STAGES) {
+          s = 0;
+          ph ^= 1u;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(DBM, D, 0, 0);
-      mbar_wait(b_bar, 0);
-      int s = 0, acc = 0;
-      uint32_t ph = 0, acc_ph = 0u;   // acc_ph: one phase bit per accumulator
-      const uint32_t b_base = smem_u32(sB);
-      for (int tile = slot; tile < ntiles; tile += nslots) {
-        mbar_wait(&tempty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);   // epilogue has drained this accumulator
+    constexpr uint32_t idesc = umma_idesc_bf16(DBM, D, 0, 0);
+    mbar_wait(b_bar, 0);
+    int s = 0, acc = 0;
+    uint32_t ph = 0, acc_ph = 0u;   // acc_ph: one phase bit per accumulator
+    const uint32_t b_base = smem_u32(sB);
+    for (int tile = slot; tile < ntiles; tile += nslots) {
+      mbar_wait(&tempty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);   // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * D);
+      for (int kb = 0; kb < P.nkb; ++kb) {
+        mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * D);
-        for (int kb = 0; kb < P.nkb; ++kb) {
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + s * D_A_BYTES);
+        const uint32_t a_base = smem_u32(sA + s * D_A_BYTES);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < DBK / 16; ++k)
             umma_bf16_ss(d_addr, umma_desc_sw128(a_base + k * 32, 16, 1024),
                          umma_desc_sw128(b_base + kb * B_KB_BYTES + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[s]);
-          if (++s == PA_STAGES) {
-            s = 0;
-            ph ^= 1u;
-          }
         }
-        umma_commit(&tfull_bar[acc]);
-        acc_ph ^= 1u << acc;
-        acc = (acc + 1) % P_NACC;
+        __syncwarp();
+        if (++s == PA_STAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
+      if (elect_one()) umma_commit(&tfull_bar[acc]);
+      __syncwarp();
+      acc_ph ^= 1u << acc;
+      acc = (acc + 1) % P_NACC;
     }
   } else {
     // ===== epilogue: 16 warps, four per TMEM lane quarter; each thread owns one token and PP rotation pairs
@@ -460,8 +476,16 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
 // exact bf16 x bf16 with fp32 accumulation, as before.  Warp roles: 0 TMA, 1 MMA (reconstruction), 2 MMA (scores),
 // 4..11 epilogue (two per TMEM lane quarter: dims [0,32)+[64,96) and [32,64)+[96,128)), 12..15 score read-out.
 //   TMEM: 2 x 128 columns reconstruction accumulators | 2 x 64 columns K^rot (bf16x2) | 2 x 32 columns scores.
+//
+// Cluster form (CL = 2, 4 or 8 CTAs = CL ADJACENT kv heads working on the SAME token tiles): every kv head needs
+// the whole A_k token tile, and with one independent CTA per head each tile travels L2 -> SM once per head
+// (8 x 67 MB per layer at config 2: the kernel ran at the chip's L2 -> SM limit, ~6300 B/clk, not at the tensor
+// pipe's).  In a cluster every CTA fetches 1/CL of each ring stage (128/CL token rows x 64 rank columns) and the
+// TMA unit MULTICASTS it into the same ring slot of all CL CTAs, so a tile leaves L2 once per cluster.  A stage is
+// refilled only when every CTA of the cluster has consumed it: the MMA warp's tcgen05.commit that releases a stage
+// is multicast to the empty barrier of all CL CTAs (count CL).
 // ---------------------------------------------------------------------------------------------
-constexpr int R_STAGES = 5;
+constexpr int R_MAX_STAGES = 12;   // ring slots of 16 KiB: as many as fit beside the head's right-factor slice (5 at r_k = 512, 9 at 256)
 constexpr int R_EPI_WARPS = 8;
 constexpr int R_OUT_WARPS = 4;
 constexpr int R_THREADS = 32 * (4 + R_EPI_WARPS + R_OUT_WARPS);
@@ -469,19 +493,30 @@ constexpr int R_QROWS = 16;                 // q rows of the score MMA (N = 16 >
 constexpr int R_Q_BYTES = 2 * R_QROWS * 128;  // two 64-dim chunks of 16 rows x 128 B
 constexpr int R_TMEM_COLS = 512;
 constexpr uint32_t R_COL_A2 = 256, R_COL_D2 = 384;
-constexpr size_t R_SMEM_BYTES = PB_MAX_BYTES + R_STAGES * D_A_BYTES + R_Q_BYTES + 1024 + 256;
+constexpr size_t R_SMEM_LIMIT = 227 * 1024;
+constexpr size_t R_FIXED_BYTES = R_Q_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+// shared memory of the score-MMA kernel for a right factor of nkb 64-wide rank blocks: (B slice, ring stages, total bytes)
+static inline int r_stages_for(int nkb) {
+  const size_t b = static_cast<size_t>(nkb) * 128 * DBK * 2;
+  int st = static_cast<int>((R_SMEM_LIMIT - R_FIXED_BYTES - b) / D_A_BYTES);
+  return st > R_MAX_STAGES ? R_MAX_STAGES : st;
+}
 
+template <int CL>
 __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const __grid_constant__ ScoreParams P) {
   constexpr int D = 128;
   constexpr int B_KB_BYTES = D * DBK * 2;
+  constexpr int SLICE_ROWS = DBM / CL;                 // token rows of a ring stage this CTA fetches
+  constexpr uint16_t CL_MASK = static_cast<uint16_t>((1u << CL) - 1u);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sB = smem;
-  uint8_t* sA = smem + PB_MAX_BYTES;
+  const int R_STAGES = P.stages;
+  uint8_t* sB = smem;                              // nkb x 16 KiB: this head's right-factor slice
+  uint8_t* sA = smem + P.nkb * B_KB_BYTES;
   uint8_t* sQ = sA + R_STAGES * D_A_BYTES;         // 1024-byte aligned (all sizes above are multiples of 1024)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sQ + R_Q_BYTES);
-  uint64_t* empty_bar = full_bar + R_STAGES;
-  uint64_t* tfull_bar = empty_bar + R_STAGES;      // [2] reconstruction accumulator ready
+  uint64_t* empty_bar = full_bar + R_MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + R_MAX_STAGES;  // [2] reconstruction accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;            // [2] ... drained by the epilogue warps
   uint64_t* a2full_bar = tempty_bar + 2;           // [2] rotated keys written to TMEM
   uint64_t* a2empty_bar = a2full_bar + 2;          // [2] ... consumed by the score MMAs
@@ -492,15 +527,22 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x % P.H;
-  const int slot = blockIdx.x / P.H;
-  const int nslots = (gridDim.x - h + P.H - 1) / P.H;
+  // cluster `cid` works on the head block hb (CL adjacent heads) and on the token tiles slot, slot + nslots, ...:
+  // the same tile sequence in every CTA of the cluster (the ring is filled jointly)
+  const int crank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cid = static_cast<int>(blockIdx.x) / CL;
+  const int ncl = static_cast<int>(gridDim.x) / CL;
+  const int nhb = P.H / CL;
+  const int hb = cid % nhb;
+  const int h = hb * CL + crank;
+  const int slot = cid / nhb;
+  const int nslots = (ncl - hb + nhb - 1) / nhb;
   const int ntiles = (P.S + DBM - 1) / DBM;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < R_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CL);      // one multicast commit per CTA of the cluster
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -513,69 +555,93 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
     mbar_init(b_bar, 1);
     mbar_init(q_bar, 1);
     mbar_fence_init();
-    tma_prefetch_desc(&P.a_map);
+    tma_prefetch_desc(CL > 1 ? &P.a_mc_map : &P.a_map);
     tma_prefetch_desc(&P.b_head_map);
     tma_prefetch_desc(&P.q_map);
   }
   if (warp == 1) tmem_alloc(tmem_slot, R_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // peers multicast into this CTA's ring and arrive on its barriers: all initialised first
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // warps 0..2: the whole warp runs the loop (waits included), one elected lane issues -- see elect_one()
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(q_bar, R_Q_BYTES);
       tma_load_2d(sQ, &P.q_map, q_bar, 0, h * P.qpk);            // dims 0..63 of q rows [h qpk, h qpk + 16)
       tma_load_2d(sQ + R_Q_BYTES / 2, &P.q_map, q_bar, 64, h * P.qpk);
       mbar_expect_tx(b_bar, static_cast<uint32_t>(P.nkb) * B_KB_BYTES);
       for (int kb = 0; kb < P.nkb; ++kb) tma_load_2d(sB + kb * B_KB_BYTES, &P.b_head_map, b_bar, kb * DBK, h * D);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = slot; tile < ntiles; tile += nslots) {
-        for (int kb = 0; kb < P.nkb; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1u);
-          mbar_expect_tx(&full_bar[s], D_A_BYTES);
-          tma_load_2d(sA + s * D_A_BYTES, &P.a_map, &full_bar[s], kb * DBK, tile * DBM);
-          if (++s == R_STAGES) {
-            s = 0;
-            ph ^= 1u;
-          }
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = slot; tile < ntiles && !XKV_DBG(P, 64); tile += nslots) {
+      for (int kb = 0; kb < P.nkb; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1u);       // CL > 1: every CTA of the cluster has consumed the slot
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[s], D_A_BYTES);   // the whole stage lands here: this CTA's slice + the peers'
+          if (CL > 1)
+            tma_load_2d_multicast(sA + s * D_A_BYTES + crank * (SLICE_ROWS * 128), &P.a_mc_map, &full_bar[s], kb * DBK,
+                                  tile * DBM + crank * SLICE_ROWS, CL_MASK);
+          else
+            tma_load_2d(sA + s * D_A_BYTES, &P.a_map, &full_bar[s], kb * DBK, tile * DBM);
+        }
+        __syncwarp();
+        if (++s == R_STAGES) {
+          s = 0;
+          ph ^= 1u;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(DBM, D, 0, 0);
-      mbar_wait(b_bar, 0);
-      int s = 0, acc = 0;
-      uint32_t ph = 0, acc_ph = 0u;
-      const uint32_t b_base = smem_u32(sB);
-      for (int tile = slot; tile < ntiles; tile += nslots) {
-        mbar_wait(&tempty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);
+    constexpr uint32_t idesc = umma_idesc_bf16(DBM, D, 0, 0);
+    mbar_wait(b_bar, 0);
+    int s = 0, acc = 0;
+    uint32_t ph = 0, acc_ph = 0u;
+    const uint32_t b_base = smem_u32(sB);
+    for (int tile = slot; tile < ntiles; tile += nslots) {
+      if (!XKV_DBG(P, 4)) mbar_wait(&tempty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * D);
+      for (int kb = 0; kb < P.nkb; ++kb) {
+        if (!XKV_DBG(P, 64)) mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * D);
-        for (int kb = 0; kb < P.nkb; ++kb) {
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + s * D_A_BYTES);
+        const uint32_t a_base = smem_u32(sA + s * D_A_BYTES);
+        if (elect_one()) {
+          if (XKV_DBG(P, 128)) {   // probe: A operand from tensor memory (TS form) instead of shared memory
 #pragma unroll
-          for (int k = 0; k < DBK / 16; ++k)
-            umma_bf16_ss(d_addr, umma_desc_sw128(a_base + k * 32, 16, 1024),
-                         umma_desc_sw128(b_base + kb * B_KB_BYTES + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
-          if (++s == R_STAGES) {
-            s = 0;
-            ph ^= 1u;
+            for (int k = 0; k < DBK / 16; ++k)
+              umma_bf16_ts(d_addr, tmem_base + R_COL_A2 + static_cast<uint32_t>(k * 8),
+                           umma_desc_sw128(b_base + kb * B_KB_BYTES + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          } else if (!XKV_DBG(P, 1)) {
+#pragma unroll
+            for (int k = 0; k < DBK / 16; ++k)
+              umma_bf16_ss(d_addr, umma_desc_sw128(a_base + k * 32, 16, 1024),
+                           umma_desc_sw128(b_base + kb * B_KB_BYTES + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
+          if (CL > 1)
+            umma_commit_multicast(&empty_bar[s], CL_MASK);
+          else
+            umma_commit(&empty_bar[s]);
         }
-        umma_commit(&tfull_bar[acc]);
-        acc_ph ^= 1u << acc;
-        acc ^= 1;
+        __syncwarp();
+        if (++s == R_STAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
+      if (elect_one()) umma_commit(&tfull_bar[acc]);
+      __syncwarp();
+      acc_ph ^= 1u << acc;
+      acc ^= 1;
     }
+  } else if (XKV_DBG(P, 4)) {
+    // probe: no epilogue pipeline at all
   } else if (warp == 2) {
-    if (lane == 0) {
+    if (!XKV_DBG(P, 16)) {
       // scores[128 x 16] = K^rot (TMEM, 64 packed columns) * Q^T (shared memory, K-major)
       constexpr uint32_t idesc2 = umma_idesc_bf16(DBM, R_QROWS, 0, 0);
       mbar_wait(q_bar, 0);
@@ -588,12 +654,15 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
         tc_fence_after();
         const uint32_t a2 = tmem_base + R_COL_A2 + static_cast<uint32_t>(b * 64);
         const uint32_t d2 = tmem_base + R_COL_D2 + static_cast<uint32_t>(b * 32);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k)
-          umma_bf16_ts(d2, a2 + static_cast<uint32_t>(k * 8),
-                       umma_desc_sw128(q_base + (k >> 2) * (R_Q_BYTES / 2) + (k & 3) * 32, 16, 1024), idesc2, k > 0 ? 1u : 0u);
-        umma_commit(&d2full_bar[b]);
-        umma_commit(&a2empty_bar[b]);
+          for (int k = 0; k < D / 16; ++k)
+            umma_bf16_ts(d2, a2 + static_cast<uint32_t>(k * 8),
+                         umma_desc_sw128(q_base + (k >> 2) * (R_Q_BYTES / 2) + (k & 3) * 32, 16, 1024), idesc2, k > 0 ? 1u : 0u);
+          umma_commit(&d2full_bar[b]);
+          umma_commit(&a2empty_bar[b]);
+        }
+        __syncwarp();
         bph ^= 1u << b;
         b ^= 1;
       }
@@ -604,7 +673,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
     const int half = (warp - 4) >> 2;
     const int row = qd * 32 + lane;
     const int d0 = half * 32;           // this thread rotates the pairs (d, d + 64), d in [d0, d0 + 32)
-    const bool rope = P.cos != nullptr;
+    const bool rope = P.cos != nullptr && !XKV_DBG(P, 8);
     int acc = 0;
     uint32_t acc_ph = 0u;
     for (int tile = slot; tile < ntiles; tile += nslots) {
@@ -655,6 +724,11 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (XKV_DBG(P, 16)) {
+        acc_ph ^= 1u << acc;
+        acc ^= 1;
+        continue;
+      }
       // K^rot -> TMEM (column c = dims 2c, 2c+1): wait until the score MMAs of two tiles ago released the buffer
       mbar_wait(&a2empty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);
       tc_fence_after();
@@ -669,7 +743,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
       acc_ph ^= 1u << acc;
       acc ^= 1;
     }
-  } else if (warp >= 4 + R_EPI_WARPS) {
+  } else if (warp >= 4 + R_EPI_WARPS && !XKV_DBG(P, 16)) {
     // ===== score read-out: one warp per TMEM lane quarter, thread = token =====
     const int qd = warp & 3;
     const int row = qd * 32 + lane;
@@ -697,617 +771,10 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer's commit may still arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, R_TMEM_COLS);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// CTA-pair variant of the kernel above (cta_group::2, head_dim 128): the two CTAs of a cluster work on the SAME kv
-// head with DIFFERENT 128-token tiles.  One tcgen05.mma of M = 256, N = 128 reconstructs both tiles; the head's
-// right-factor slice is split between the CTAs (64 of its 128 rows each, 64 KiB instead of 128 KiB), which
-//   * halves the shared-memory bytes an MMA reads per tensor cycle (the N = 128 single-CTA MMA sits exactly at the
-//     128 B/clk shared-memory limit, before counting the TMA writes), and
-//   * frees 64 KiB per SM for the A_k ring: 9 stages x 16 KiB in flight instead of 5 (the A_k stream is bound by
-//     latency x bytes in flight, profiles/r01_decode_scores_ncu_full.md).
-// The score MMA is the pair form too (M = 256, N = 16: 8 q rows per CTA; tcgen05 instructions of one kernel must
-// agree on the cta_group).  Barriers that gate the leader's MMA issue live in the leader CTA and are arrived on by
-// both CTAs (TMA bytes via the .cta_group::2 load form, epilogue warps via remote mbarrier.arrive); barriers that
-// gate a CTA's own warps are signalled by the leader's multicast commits.
-// Measured (config 2, one layer): 99 us against 92 us for the single-CTA kernel above - the cross-CTA barrier round
-// trips cost more than the deeper ring and the lighter MMAs gain, so this variant is opt-in (XKV_DECODE_PAIR=1);
-// it is parity-tested like the default.
-// ---------------------------------------------------------------------------------------------
-constexpr int Q_STAGES = 9;
-constexpr int Q_EPI_WARPS = 8;
-constexpr int Q_OUT_WARPS = 4;
-constexpr int Q_THREADS = 32 * (4 + Q_EPI_WARPS + Q_OUT_WARPS);
-constexpr int Q_BHALF_BYTES = 64 * 1024;           // 64 rows x r_k <= 512 bf16
-constexpr int Q_Q_BYTES = 2 * 8 * 128;             // two 64-dim chunks of 8 q rows x 128 B
-constexpr int Q_TMEM_COLS = 512;
-constexpr size_t Q_SMEM_BYTES = Q_BHALF_BYTES + Q_STAGES * D_A_BYTES + Q_Q_BYTES + 1024 + 512;
-
-__global__ void __launch_bounds__(Q_THREADS, 1) decode_scores_pair_kernel(const __grid_constant__ ScoreParams P) {
-  constexpr int D = 128;
-  constexpr int BH_KB_BYTES = (D / 2) * DBK * 2;   // one 64-wide K block of this CTA's 64 rows of the right factor
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sB = smem;
-  uint8_t* sA = smem + Q_BHALF_BYTES;
-  uint8_t* sQ = sA + Q_STAGES * D_A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sQ + Q_Q_BYTES);   // leader: bytes of both CTAs
-  uint64_t* empty_bar = full_bar + Q_STAGES;        // local, multicast commit
-  uint64_t* tfull_bar = empty_bar + Q_STAGES;       // [2] local, multicast commit
-  uint64_t* tempty_bar = tfull_bar + 2;             // [2] leader, 2 x epilogue warps
-  uint64_t* a2full_bar = tempty_bar + 2;            // [2] leader, 2 x epilogue warps
-  uint64_t* a2empty_bar = a2full_bar + 2;           // [2] local, multicast commit
-  uint64_t* d2full_bar = a2empty_bar + 2;           // [2] local, multicast commit
-  uint64_t* d2empty_bar = d2full_bar + 2;           // [2] leader, 2 x read-out warps
-  uint64_t* b_bar = d2empty_bar + 2;                // leader
-  uint64_t* q_bar = b_bar + 1;                      // leader
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_bar + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();          // 0 = leader
-  const int pair = blockIdx.x >> 1;
-  const int npairs = gridDim.x >> 1;
-  const int h = pair % P.H;
-  const int slot = pair / P.H;
-  const int nslots = (npairs - h + P.H - 1) / P.H;  // CTA pairs that share this head
-  const int ntp = (P.S + 2 * DBM - 1) / (2 * DBM);  // 256-token tile pairs
-
-  if (warp == 0 && lane == 0) {
-    for (int i = 0; i < Q_STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 2 * Q_EPI_WARPS);
-      mbar_init(&a2full_bar[i], 2 * Q_EPI_WARPS);
-      mbar_init(&a2empty_bar[i], 1);
-      mbar_init(&d2full_bar[i], 1);
-      mbar_init(&d2empty_bar[i], 2 * Q_OUT_WARPS);
-    }
-    mbar_init(b_bar, 1);
-    mbar_init(q_bar, 1);
-    mbar_fence_init();
-    tma_prefetch_desc(&P.a_map);
-    tma_prefetch_desc(&P.b_half_map);
-    tma_prefetch_desc(&P.q8_map);
-  }
-  __syncthreads();
-  cluster_sync_all();                               // barrier initialisation visible to the peer before any remote use
-  if (warp == 1) tmem_alloc_pair(tmem_slot, Q_TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // this CTA's q rows, this CTA's half of the head's right factor; bytes of both CTAs land on the leader's barriers
-      if (rank == 0) mbar_expect_tx(q_bar, 2u * Q_Q_BYTES);
-      tma_load_2d_pair(sQ, &P.q8_map, q_bar, 0, h * P.qpk + static_cast<int>(rank) * 8);
-      tma_load_2d_pair(sQ + Q_Q_BYTES / 2, &P.q8_map, q_bar, 64, h * P.qpk + static_cast<int>(rank) * 8);
-      if (rank == 0) mbar_expect_tx(b_bar, 2u * static_cast<uint32_t>(P.nkb) * BH_KB_BYTES);
-      for (int kb = 0; kb < P.nkb; ++kb)
-        tma_load_2d_pair(sB + kb * BH_KB_BYTES, &P.b_half_map, b_bar, kb * DBK, h * D + static_cast<int>(rank) * (D / 2));
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tp = slot; tp < ntp; tp += nslots) {
-        const int m0 = tp * 2 * DBM + static_cast<int>(rank) * DBM;
-        for (int kb = 0; kb < P.nkb; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1u);
-          if (rank == 0) mbar_expect_tx(&full_bar[s], 2u * D_A_BYTES);
-          tma_load_2d_pair(sA + s * D_A_BYTES, &P.a_map, &full_bar[s], kb * DBK, m0);
-          if (++s == Q_STAGES) {
-            s = 0;
-            ph ^= 1u;
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * DBM, D, 0, 0);
-      mbar_wait_cluster(b_bar, 0);
-      int s = 0, acc = 0;
-      uint32_t ph = 0, acc_ph = 0u;
-      const uint32_t b_base = smem_u32(sB);
-      for (int tp = slot; tp < ntp; tp += nslots) {
-        mbar_wait_cluster(&tempty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * D);
-        for (int kb = 0; kb < P.nkb; ++kb) {
-          mbar_wait_cluster(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + s * D_A_BYTES);
-#pragma unroll
-          for (int k = 0; k < DBK / 16; ++k)
-            umma_bf16_ss_pair(d_addr, umma_desc_sw128(a_base + k * 32, 16, 1024),
-                              umma_desc_sw128(b_base + kb * BH_KB_BYTES + k * 32, 16, 1024), idesc,
-                              (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit_pair(&empty_bar[s]);
-          if (++s == Q_STAGES) {
-            s = 0;
-            ph ^= 1u;
-          }
-        }
-        umma_commit_pair(&tfull_bar[acc]);
-        acc_ph ^= 1u << acc;
-        acc ^= 1;
-      }
-    }
-  } else if (warp == 2) {
-    if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc2 = umma_idesc_bf16(2 * DBM, 16, 0, 0);
-      mbar_wait_cluster(q_bar, 0);
-      const uint32_t q_base = smem_u32(sQ);
-      int b = 0;
-      uint32_t bph = 0u;
-      for (int tp = slot; tp < ntp; tp += nslots) {
-        mbar_wait_cluster(&a2full_bar[b], (bph >> b) & 1u);          // both CTAs' rotated keys are in TMEM
-        mbar_wait_cluster(&d2empty_bar[b], ((bph >> b) & 1u) ^ 1u);  // both CTAs' score buffers read out
-        tc_fence_after();
-        const uint32_t a2 = tmem_base + R_COL_A2 + static_cast<uint32_t>(b * 64);
-        const uint32_t d2 = tmem_base + R_COL_D2 + static_cast<uint32_t>(b * 32);
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k)
-          umma_bf16_ts_pair(d2, a2 + static_cast<uint32_t>(k * 8),
-                            umma_desc_sw128(q_base + (k >> 2) * (Q_Q_BYTES / 2) + (k & 3) * 32, 16, 1024), idesc2,
-                            k > 0 ? 1u : 0u);
-        umma_commit_pair(&d2full_bar[b]);
-        umma_commit_pair(&a2empty_bar[b]);
-        bph ^= 1u << b;
-        b ^= 1;
-      }
-    }
-  } else if (warp >= 4 && warp < 4 + Q_EPI_WARPS) {
-    // ===== epilogue (both CTAs, own tokens): K^ row -> bf16 -> RoPE -> TMEM =====
-    const int qd = warp & 3;
-    const int half = (warp - 4) >> 2;
-    const int row = qd * 32 + lane;
-    const int d0 = half * 32;
-    const bool rope = P.cos != nullptr;
-    int acc = 0;
-    uint32_t acc_ph = 0u;
-    for (int tp = slot; tp < ntp; tp += nslots) {
-      const int tok = tp * 2 * DBM + static_cast<int>(rank) * DBM + row;
-      uint32_t cs[16], sn[16];
-      if (rope && tok < P.S) {
-        const uint4* cp = reinterpret_cast<const uint4*>(P.cos + static_cast<long long>(tok) * P.ld_cs + d0);
-        const uint4* sp = reinterpret_cast<const uint4*>(P.sin + static_cast<long long>(tok) * P.ld_cs + d0);
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const uint4 cv = __ldg(cp + v), sv = __ldg(sp + v);
-          cs[4 * v] = cv.x, cs[4 * v + 1] = cv.y, cs[4 * v + 2] = cv.z, cs[4 * v + 3] = cv.w;
-          sn[4 * v] = sv.x, sn[4 * v + 1] = sv.y, sn[4 * v + 2] = sv.z, sn[4 * v + 3] = sv.w;
-        }
-      } else {
-#pragma unroll
-        for (int v = 0; v < 16; ++v) cs[v] = 0x3F803F80u, sn[v] = 0u;
-      }
-      mbar_wait(&tfull_bar[acc], (acc_ph >> acc) & 1u);
-      tc_fence_after();
-      const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
-      const uint32_t lane_addr = lane_base + static_cast<uint32_t>(acc * D);
-      uint32_t lo_w[16], hi_w[16];
-#pragma unroll
-      for (int sc = 0; sc < 2; ++sc) {
-        uint32_t x1[16], x2[16];
-        __syncwarp();
-        tmem_ld_32x16(lane_addr + static_cast<uint32_t>(d0 + sc * 16), x1);
-        tmem_ld_32x16(lane_addr + static_cast<uint32_t>(D / 2 + d0 + sc * 16), x2);
-        tmem_ld_wait();
-#pragma unroll
-        for (int jp = 0; jp < 8; ++jp) {
-          const __nv_bfloat162 k1 = __floats2bfloat162_rn(__uint_as_float(x1[2 * jp]), __uint_as_float(x1[2 * jp + 1]));
-          const __nv_bfloat162 k2 = __floats2bfloat162_rn(__uint_as_float(x2[2 * jp]), __uint_as_float(x2[2 * jp + 1]));
-          __nv_bfloat162 o1 = k1, o2 = k2;
-          if (rope) {
-            const __nv_bfloat162 cw = *reinterpret_cast<const __nv_bfloat162*>(&cs[sc * 8 + jp]);
-            const __nv_bfloat162 sw = *reinterpret_cast<const __nv_bfloat162*>(&sn[sc * 8 + jp]);
-            o1 = __hadd2(__hmul2(k1, cw), __hmul2(__hneg2(k2), sw));
-            o2 = __hadd2(__hmul2(k2, cw), __hmul2(k1, sw));
-          }
-          lo_w[sc * 8 + jp] = *reinterpret_cast<const uint32_t*>(&o1);
-          hi_w[sc * 8 + jp] = *reinterpret_cast<const uint32_t*>(&o2);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
-      mbar_wait(&a2empty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);
-      tc_fence_after();
-      const uint32_t a2 = lane_base + R_COL_A2 + static_cast<uint32_t>(acc * 64);
-      __syncwarp();
-      tmem_st_32x16(a2 + static_cast<uint32_t>(d0 / 2), lo_w);
-      tmem_st_32x16(a2 + static_cast<uint32_t>(32 + d0 / 2), hi_w);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&a2full_bar[acc]);
-      acc_ph ^= 1u << acc;
-      acc ^= 1;
-    }
-  } else if (warp >= 4 + Q_EPI_WARPS) {
-    // ===== score read-out (both CTAs, own tokens) =====
-    const int qd = warp & 3;
-    const int row = qd * 32 + lane;
-    int b = 0;
-    uint32_t bph = 0u;
-    for (int tp = slot; tp < ntp; tp += nslots) {
-      const int tok = tp * 2 * DBM + static_cast<int>(rank) * DBM + row;
-      mbar_wait(&d2full_bar[b], (bph >> b) & 1u);
-      tc_fence_after();
-      uint32_t v[8];
-      __syncwarp();
-      tmem_ld_32x8(tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + R_COL_D2 + static_cast<uint32_t>(b * 32), v);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&d2empty_bar[b]);
-      if (tok < P.S) {
-#pragma unroll
-        for (int g = 0; g < D_MAX_QPK; ++g)
-          if (g < P.qpk) P.scores[static_cast<long long>(h * P.qpk + g) * P.ld_scores + tok] = __uint_as_float(v[g]) * P.scale;
-      }
-      bph ^= 1u << b;
-      b ^= 1;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer may still signal its barriers
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc_pair(tmem_base, Q_TMEM_COLS);
-  }
-}
-
-
-// ---------------------------------------------------------------------------------------------
-// Transposed variant (head_dim 128, r_k <= 512: the default where it applies): the kernels above keep the head's
-// right-factor slice (128 KiB) in shared memory, which leaves room for only 5 stages of the A_k stream and makes
-// every reconstruction MMA read BOTH operands from shared memory (N = 128: 128 B/clk, the shared-memory limit).
-// Here the roles of the operands are swapped:
-//
-//     K^T tile [128 dims x 128 tokens] = Bk_head [128 dims x r_k] (TENSOR MEMORY, A operand, TS form)
-//                                        * A_k tile [128 tokens x r_k]^T (shared memory, B operand, TMA ring)
-//
-//   * the right-factor slice is written to TMEM once per CTA (tcgen05.st, 32 columns per 64-wide K block; the
-//     first 7 K blocks = 224 columns; an 8th block, if any, stays in shared memory and is applied in SS form),
-//     so shared memory holds only the token stream: 8 stages x 16 KiB in flight instead of 5, and an MMA reads
-//     half as many shared-memory bytes per tensor cycle;
-//   * the accumulator has lane = head dim, column = token.  The rows of the slice are PERMUTED over the TMEM lanes
-//     (lane 2i = dim i, lane 2i+1 = dim i + 64) so that the two RoPE partners of a pair sit in neighbouring lanes of
-//     one warp and meet by a shuffle; the rotation runs in packed bf16 over two TOKENS at a time with cos / sin read
-//     from dim-major tables (cos_t[i][token]); the rounding sequence is the reference's, as in the kernels above;
-//   * the rotated keys go to shared memory as an MN-major A operand (row = dim, 128 B = 64 tokens, SWIZZLE_128B) and
-//     a second tcgen05.mma (SS form, M = 128 tokens, N = 16 q rows, K = 128 dims) contracts them with q.
-//   TMEM: [0,224) right factor | [224,480) two K^T accumulators | [480,512) two score blocks.
-// Warp roles: 0 TMA, 1 reconstruction MMAs, 2 score MMAs, 4..11 epilogue (lane quarter x token half), 12..15 read-out.
-// ---------------------------------------------------------------------------------------------
-constexpr int T_STAGES = 8;
-constexpr int T_EPI_WARPS = 8;
-constexpr int T_OUT_WARPS = 4;
-constexpr int T_THREADS = 32 * (4 + T_EPI_WARPS + T_OUT_WARPS);
-constexpr int T_MAX_KB_TMEM = 7;                 // 64-wide K blocks of the right factor held in TMEM (32 columns each)
-constexpr int T_BS_BYTES = 128 * DBK * 2;        // the 8th K block (K-major, 128 permuted rows x 128 B)
-constexpr int T_KROT_BYTES = 128 * 128 * 2;      // rotated keys of one tile: two 64-token chunks of 128 rows x 128 B
-constexpr int T_TMEM_COLS = 512;
-constexpr uint32_t T_COL_ACC = 224, T_COL_D2 = 480;
-constexpr size_t T_SMEM_BYTES = T_BS_BYTES + T_STAGES * D_A_BYTES + 2 * T_KROT_BYTES + R_Q_BYTES + 1024 + 512;
-
-__global__ void __launch_bounds__(T_THREADS, 1) decode_scores_tr_kernel(const __grid_constant__ ScoreParams P) {
-  constexpr int D = 128;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sBs = smem;
-  uint8_t* sA = sBs + T_BS_BYTES;
-  uint8_t* sK = sA + T_STAGES * D_A_BYTES;
-  uint8_t* sQ = sK + 2 * T_KROT_BYTES;             // 1024-byte aligned (all sizes above are multiples of 1024)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sQ + R_Q_BYTES);
-  uint64_t* empty_bar = full_bar + T_STAGES;
-  uint64_t* tfull_bar = empty_bar + T_STAGES;      // [2] K^T accumulator ready
-  uint64_t* tempty_bar = tfull_bar + 2;            // [2] ... drained by the epilogue warps
-  uint64_t* kfull_bar = tempty_bar + 2;            // [2] rotated keys written to shared memory
-  uint64_t* kempty_bar = kfull_bar + 2;            // [2] ... consumed by the score MMAs
-  uint64_t* d2full_bar = kempty_bar + 2;           // [2] scores ready in TMEM
-  uint64_t* d2empty_bar = d2full_bar + 2;          // [2] ... read out
-  uint64_t* bready_bar = d2empty_bar + 2;          // right factor in TMEM / shared memory
-  uint64_t* q_bar = bready_bar + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_bar + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x % P.H;
-  const int slot = blockIdx.x / P.H;
-  const int nslots = (gridDim.x - h + P.H - 1) / P.H;
-  const int ntiles = (P.S + DBM - 1) / DBM;
-  const int nkb_t = P.nkb < T_MAX_KB_TMEM ? P.nkb : T_MAX_KB_TMEM;
-
-  if (warp == 0 && lane == 0) {
-    for (int i = 0; i < T_STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], T_EPI_WARPS);
-      mbar_init(&kfull_bar[i], T_EPI_WARPS);
-      mbar_init(&kempty_bar[i], 1);
-      mbar_init(&d2full_bar[i], 1);
-      mbar_init(&d2empty_bar[i], T_OUT_WARPS);
-    }
-    mbar_init(bready_bar, T_EPI_WARPS);
-    mbar_init(q_bar, 1);
-    mbar_fence_init();
-    tma_prefetch_desc(&P.a_map);
-    tma_prefetch_desc(&P.q_map);
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, T_TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(q_bar, R_Q_BYTES);
-      tma_load_2d(sQ, &P.q_map, q_bar, 0, h * P.qpk);            // dims 0..63 of q rows [h qpk, h qpk + 16)
-      tma_load_2d(sQ + R_Q_BYTES / 2, &P.q_map, q_bar, 64, h * P.qpk);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = slot; tile < ntiles; tile += nslots) {
-        for (int kb = 0; kb < P.nkb; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1u);
-          if (P.dbg & 32) {
-            mbar_arrive(&full_bar[s]);
-          } else {
-          mbar_expect_tx(&full_bar[s], D_A_BYTES);
-          tma_load_2d(sA + s * D_A_BYTES, &P.a_map, &full_bar[s], kb * DBK, tile * DBM);
-          }
-          if (++s == T_STAGES) {
-            s = 0;
-            ph ^= 1u;
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // K^T[128 dims x 128 tokens] += Bk_head (TMEM, or shared memory for the 8th K block) * A_k tile^T
-      constexpr uint32_t idesc = umma_idesc_bf16(D, DBM, 0, 0);
-      mbar_wait(bready_bar, 0);
-      tc_fence_after();
-      int s = 0, acc = 0;
-      uint32_t ph = 0, acc_ph = 0u;
-      const uint32_t bs_base = smem_u32(sBs);
-      for (int tile = slot; tile < ntiles; tile += nslots) {
-        if (!(P.dbg & 128)) mbar_wait(&tempty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t d_addr = tmem_base + T_COL_ACC + static_cast<uint32_t>(acc * DBM);
-        for (int kb = 0; kb < P.nkb; ++kb) {
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + s * D_A_BYTES);
-          if (P.dbg & 1) {
-          } else if (kb < nkb_t) {
-#pragma unroll
-            for (int k = 0; k < ((P.dbg & 64) ? 1 : DBK / 16); ++k)
-              umma_bf16_ts(d_addr, tmem_base + static_cast<uint32_t>(kb * 32 + k * 8),
-                           umma_desc_sw128(a_base + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          } else {
-#pragma unroll
-            for (int k = 0; k < DBK / 16; ++k)
-              umma_bf16_ss(d_addr, umma_desc_sw128(bs_base + k * 32, 16, 1024), umma_desc_sw128(a_base + k * 32, 16, 1024),
-                           idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[s]);
-          if (++s == T_STAGES) {
-            s = 0;
-            ph ^= 1u;
-          }
-        }
-        umma_commit(&tfull_bar[acc]);
-        acc_ph ^= 1u << acc;
-        acc ^= 1;
-      }
-    }
-  } else if (warp == 2) {
-    if (lane == 0) {
-      // scores[128 tokens x 16] = K^rot (shared memory, MN-major: row = dim, 64 tokens per 128 B) * Q^T (K-major)
-      constexpr uint32_t idesc2 = umma_idesc_bf16(DBM, R_QROWS, 1, 0);
-      mbar_wait(q_bar, 0);
-      const uint32_t q_base = smem_u32(sQ);
-      int b = 0;
-      uint32_t bph = 0u;
-      for (int tile = slot; tile < ntiles; tile += nslots) {
-        mbar_wait(&kfull_bar[b], (bph >> b) & 1u);                  // rotated keys of this tile are in shared memory
-        mbar_wait(&d2empty_bar[b], ((bph >> b) & 1u) ^ 1u);         // score buffer read out
-        tc_fence_after();
-        const uint32_t k_base = smem_u32(sK + b * T_KROT_BYTES);
-        const uint32_t d2 = tmem_base + T_COL_D2 + static_cast<uint32_t>(b * 16);
-        if (!(P.dbg & 4))
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k)
-          umma_bf16_ss(d2, umma_desc_sw128(k_base + k * 2048, T_KROT_BYTES / 2, 1024),
-                       umma_desc_sw128(q_base + (k >> 2) * (R_Q_BYTES / 2) + (k & 3) * 32, 16, 1024), idesc2, k > 0 ? 1u : 0u);
-        umma_commit(&d2full_bar[b]);
-        umma_commit(&kempty_bar[b]);
-        bph ^= 1u << b;
-        b ^= 1;
-      }
-    }
-  } else if (warp >= 4 && warp < 4 + T_EPI_WARPS) {
-    const int qd = warp & 3;
-    const int half = (warp - 4) >> 2;                 // token half of the tile (and K-block parity of the prologue)
-    const int L = qd * 32 + lane;                     // TMEM lane
-    const int fi = L >> 1;                            // RoPE frequency index
-    const int dim = fi + ((L & 1) << 6);              // head dim held by this lane
-    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
-    // ===== prologue: this lane's row of the head's right-factor slice -> TMEM (A operand: column c = k 2c, 2c+1) =====
-    {
-      const __nv_bfloat16* brow = P.bk + static_cast<long long>(h * D + dim) * P.ld_bk;
-      for (int kb = half; kb < P.nkb; kb += 2) {
-        uint4 v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int k0 = kb * DBK + j * 8;
-          v[j] = (k0 + 8 <= P.rk) ? __ldg(reinterpret_cast<const uint4*>(brow + k0)) : make_uint4(0u, 0u, 0u, 0u);
-        }
-        if (kb < nkb_t) {
-          uint32_t w0[16], w1[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            w0[4 * j] = v[j].x, w0[4 * j + 1] = v[j].y, w0[4 * j + 2] = v[j].z, w0[4 * j + 3] = v[j].w;
-            w1[4 * j] = v[4 + j].x, w1[4 * j + 1] = v[4 + j].y, w1[4 * j + 2] = v[4 + j].z, w1[4 * j + 3] = v[4 + j].w;
-          }
-          __syncwarp();
-          tmem_st_32x16(lane_base + static_cast<uint32_t>(kb * 32), w0);
-          tmem_st_32x16(lane_base + static_cast<uint32_t>(kb * 32 + 16), w1);
-        } else {
-          uint8_t* rowp = sBs + (L >> 3) * 1024 + (L & 7) * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(rowp + ((j ^ (L & 7)) << 4)) = v[j];
-        }
-      }
-      tmem_st_wait();
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bready_bar);
-    }
-    // ===== epilogue: K^T row -> bf16 -> RoPE with the partner lane -> shared memory (A operand of the score MMA) =====
-    const bool rope = P.cos_t != nullptr && !(P.dbg & 8);
-    const uint32_t sgn = (L & 1) ? 0u : 0x80008000u;  // dims < 64 take -partner * sin, dims >= 64 take +partner * sin
-    const __nv_bfloat16* crow = rope ? P.cos_t + static_cast<long long>(fi) * P.ld_t : nullptr;
-    const __nv_bfloat16* srow = rope ? P.sin_t + static_cast<long long>(fi) * P.ld_t : nullptr;
-    uint8_t* krow = sK + half * (T_KROT_BYTES / 2) + (dim >> 3) * 1024 + (dim & 7) * 128;
-    const int dsw = dim & 7;
-    int acc = 0;
-    uint32_t acc_ph = 0u;
-    for (int tile = slot; tile < ntiles; tile += nslots) {
-      const long long tok0 = static_cast<long long>(tile) * DBM + half * 64;
-      uint4 cq[2][2], sq[2][2];    // cos / sin words of 16 tokens, double buffered
-      if (rope) {
-        cq[0][0] = __ldg(reinterpret_cast<const uint4*>(crow + tok0));
-        cq[0][1] = __ldg(reinterpret_cast<const uint4*>(crow + tok0) + 1);
-        sq[0][0] = __ldg(reinterpret_cast<const uint4*>(srow + tok0));
-        sq[0][1] = __ldg(reinterpret_cast<const uint4*>(srow + tok0) + 1);
-      }
-      mbar_wait(&tfull_bar[acc], (acc_ph >> acc) & 1u);
-      if (!(P.dbg & 256)) mbar_wait(&kempty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);   // score MMAs of two tiles ago released the buffer
-      tc_fence_after();
-      const uint32_t col0 = lane_base + T_COL_ACC + static_cast<uint32_t>(acc * DBM + half * 64);
-      uint8_t* kdst = krow + acc * T_KROT_BYTES;
-#pragma unroll
-      for (int sc = 0; sc < 4; ++sc) {
-        uint32_t x[16];
-        __syncwarp();
-        if (P.dbg & 16) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) x[j] = 0u;
-        } else
-        tmem_ld_32x16(col0 + static_cast<uint32_t>(sc * 16), x);
-        if (rope && sc < 3) {
-          cq[(sc + 1) & 1][0] = __ldg(reinterpret_cast<const uint4*>(crow + tok0 + (sc + 1) * 16));
-          cq[(sc + 1) & 1][1] = __ldg(reinterpret_cast<const uint4*>(crow + tok0 + (sc + 1) * 16) + 1);
-          sq[(sc + 1) & 1][0] = __ldg(reinterpret_cast<const uint4*>(srow + tok0 + (sc + 1) * 16));
-          sq[(sc + 1) & 1][1] = __ldg(reinterpret_cast<const uint4*>(srow + tok0 + (sc + 1) * 16) + 1);
-        }
-        tmem_ld_wait();
-        uint32_t o[8];
-        const uint32_t* cw = reinterpret_cast<const uint32_t*>(&cq[sc & 1][0]);
-        const uint32_t* sw = reinterpret_cast<const uint32_t*>(&sq[sc & 1][0]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t own = pack_bf16x2(__uint_as_float(x[2 * j]), __uint_as_float(x[2 * j + 1]));
-          uint32_t res = own;
-          if (rope) {
-            const uint32_t par = __shfl_xor_sync(0xffffffffu, own, 1) ^ sgn;
-            const __nv_bfloat162 r = __hadd2(__hmul2(*reinterpret_cast<const __nv_bfloat162*>(&own),
-                                                     *reinterpret_cast<const __nv_bfloat162*>(&cw[j])),
-                                             __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&par),
-                                                     *reinterpret_cast<const __nv_bfloat162*>(&sw[j])));
-            res = *reinterpret_cast<const uint32_t*>(&r);
-          }
-          o[j] = res;
-        }
-        if (!(P.dbg & 2)) {
-        *reinterpret_cast<uint4*>(kdst + (((2 * sc) ^ dsw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<uint4*>(kdst + (((2 * sc + 1) ^ dsw) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
-        }
-      }
-      // the accumulator is drained: hand it back to the reconstruction MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      // rotated keys visible to the tensor core's (async proxy) reads
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&kfull_bar[acc]);
-      acc_ph ^= 1u << acc;
-      acc ^= 1;
-    }
-  } else if (warp >= 4 + T_EPI_WARPS) {
-    // ===== score read-out: one warp per TMEM lane quarter, thread = token =====
-    const int qd = warp & 3;
-    const int row = qd * 32 + lane;
-    int b = 0;
-    uint32_t bph = 0u;
-    for (int tile = slot; tile < ntiles; tile += nslots) {
-      const int tok = tile * DBM + row;
-      mbar_wait(&d2full_bar[b], (bph >> b) & 1u);
-      tc_fence_after();
-      uint32_t v[8];
-      __syncwarp();
-      tmem_ld_32x8(tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + T_COL_D2 + static_cast<uint32_t>(b * 16), v);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&d2empty_bar[b]);
-      if (tok < P.S) {
-#pragma unroll
-        for (int g = 0; g < D_MAX_QPK; ++g)
-          if (g < P.qpk) P.scores[static_cast<long long>(h * P.qpk + g) * P.ld_scores + tok] = __uint_as_float(v[g]) * P.scale;
-      }
-      bph ^= 1u << b;
-      b ^= 1;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, T_TMEM_COLS);
-  }
-}
-
-// cos_t[i][t] = cos[t][i], sin_t likewise, for i < D/2 (HF tables repeat the D/2 frequencies in both halves) and
-// t < S; columns [S, ld_t) are zeroed.  32 x 32 tiles through shared memory.
-__global__ void __launch_bounds__(256) rope_tables_dim_major_kernel(const __nv_bfloat16* __restrict__ cos,
-                                                                    const __nv_bfloat16* __restrict__ sin, long long ld_cs,
-                                                                    int S, int half_d, __nv_bfloat16* __restrict__ cos_t,
-                                                                    __nv_bfloat16* __restrict__ sin_t, long long ld_t) {
-  __shared__ __nv_bfloat16 tc[32][33], ts[32][33];
-  const int t0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int r = ty; r < 32; r += 8) {
-    const int t = t0 + r, i = i0 + tx;
-    const bool ok = t < S && i < half_d;
-    tc[r][tx] = ok ? cos[static_cast<long long>(t) * ld_cs + i] : __float2bfloat16(0.f);
-    ts[r][tx] = ok ? sin[static_cast<long long>(t) * ld_cs + i] : __float2bfloat16(0.f);
-  }
-  __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    const int i = i0 + r, t = t0 + tx;
-    if (i < half_d && t < ld_t) {
-      cos_t[static_cast<long long>(i) * ld_t + t] = tc[tx][r];
-      sin_t[static_cast<long long>(i) * ld_t + t] = ts[tx][r];
-    }
   }
 }
 
@@ -1532,12 +999,7 @@ static inline size_t al(size_t x) { return (x + 1023) / 1024 * 1024; }
 static inline int decode_split_k(int S, int rv) {
   const int nkb = (S + 63) / 64;
   const int tiles_n = (rv + 255) / 256;
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      sms = 148;
-  }
+  const int sms = device_sm_count();
   int split = sms / (tiles_n < 1 ? 1 : tiles_n);
   if (split > nkb) split = nkb;
   if (split > 64) split = 64;
@@ -1547,7 +1009,168 @@ static inline int decode_split_k(int S, int rv) {
 }
 
 static bool g_force_tiled_scores = false;  // test hook: exercise the tile-per-CTA scores kernel
-static int g_scores_variant = 0;           // test hook: 0 automatic, 1 FFMA epilogue, 2 score-MMA, 3 CTA pair
+static int g_scores_variant = 0;           // test hook: 0 automatic, 1 FFMA epilogue, 2 score MMA without cluster
+static int g_scores_cluster = 0;           // test / tuning hook: cluster size of the score-MMA kernel (0 automatic, 1, 2, 4, 8)
+
+// Launch the score-MMA kernel as clusters of CL CTAs (CL adjacent kv heads share every A_k tile by TMA multicast).
+// Returns 0 on success, -1 when this cluster size cannot be resident on the device (the caller tries a smaller one).
+template <int CL>
+static int launch_scores_mma2(const ScoreParams& sp, int S, int H, cudaStream_t st) {
+  auto kern = decode_scores_mma2_kernel<CL>;
+  static PerDevice<int> state;   // 0: not probed, -1: not launchable, > 0: resident clusters of this size
+  int& resident = state();
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(R_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = R_FIXED_BYTES + static_cast<size_t>(sp.nkb) * 128 * DBK * 2 + static_cast<size_t>(sp.stages) * D_A_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  if (resident == 0) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(R_SMEM_LIMIT)) != cudaSuccess) {
+      (void)cudaGetLastError();
+      resident = -1;
+    } else if (CL == 1) {
+      resident = device_sm_count();
+    } else {
+      int n = 0;
+      cfg.gridDim = dim3(CL, 1, 1);
+      const size_t launch_smem = cfg.dynamicSmemBytes;
+      cfg.dynamicSmemBytes = R_SMEM_LIMIT;   // one CTA per SM whatever the rank
+      const cudaError_t oe = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+      cfg.dynamicSmemBytes = launch_smem;
+      if (oe != cudaSuccess || n < 1) {
+        (void)cudaGetLastError();
+        resident = -1;
+      } else {
+        resident = n;
+      }
+    }
+  }
+  if (resident < 0) return -1;
+  // persistent: one resident CTA per SM slot; every head block needs at least one cluster
+  const int ntiles = (S + DBM - 1) / DBM;
+  const int nhb = H / CL;
+  int ncl = resident < ntiles * nhb ? resident : ntiles * nhb;
+  if (ncl < nhb) ncl = nhb;
+  cfg.gridDim = dim3(ncl * CL, 1, 1);
+  XKV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, sp));
+  return 0;
+}
+
+// scores[hq][t] = scale * q_hq . rope(bf16(A_k[t] Bk_l^T)) for the S tokens of the compressed prefix: fused reconstruct +
+// RoPE + q.K, one launch (kernel chosen by head_dim, rank and the test hooks)
+static int launch_scores(const void* q, int Hq, int H, int D, const void* A_k, int64_t lda_k, int rk, const void* Vk_layer,
+                         int64_t ldv_k, int S, const void* cos, const void* sin, int64_t ld_cs, float scale, float* scores,
+                         long long ldl, cudaStream_t st) {
+  const int qpk = Hq / H;
+  int rc;
+  static thread_local ScoreParams sp;
+  std::memset(&sp, 0, sizeof(sp));
+  rc = encode_tmap_2d_bf16(&sp.a_map, A_k, rk, S, lda_k, DBK, DBM);
+  if (rc) return rc;
+  rc = encode_tmap_2d_bf16(&sp.b_map, Vk_layer, rk, static_cast<uint64_t>(H) * D, ldv_k, DBK, DBN);
+  if (rc) return rc;
+  rc = encode_tmap_2d_bf16(&sp.b_head_map, Vk_layer, rk, static_cast<uint64_t>(H) * D, ldv_k, DBK, D);
+  if (rc) return rc;
+  const bool q_tma_ok = D == 128 && (reinterpret_cast<uintptr_t>(q) & 15) == 0;
+  if (q_tma_ok) {
+    rc = encode_tmap_2d_bf16(&sp.q_map, q, D, Hq, D, 64, R_QROWS);
+    if (rc) return rc;
+  }
+  // cluster size of the score-MMA kernel: the largest of 8, 4, 2 that divides the kv-head count (tuning hook: xkv_decode_set_cluster)
+  int want_cl = 1;
+  if (q_tma_ok && qpk <= 8) {
+    const int cap = g_scores_cluster > 0 ? g_scores_cluster : 1;   // measured: sharing the tiles by multicast is no faster
+    for (int c = 8; c >= 2; c >>= 1)
+      if (c <= cap && H % c == 0) {
+        want_cl = c;
+        break;
+      }
+    if (want_cl > 1) {
+      rc = encode_tmap_2d_bf16(&sp.a_mc_map, A_k, rk, S, lda_k, DBK, DBM / want_cl);
+      if (rc) return rc;
+    }
+  }
+  sp.q = static_cast<const __nv_bfloat16*>(q);
+  sp.cos = static_cast<const __nv_bfloat16*>(cos);
+  sp.sin = static_cast<const __nv_bfloat16*>(sin);
+  sp.scores = scores;
+  sp.ld_cs = ld_cs;
+  sp.ld_scores = ldl;
+  sp.S = S;
+  sp.rk = rk;
+  sp.H = H;
+  sp.qpk = qpk;
+  sp.tiles_n = (H * D + DBN - 1) / DBN;
+  sp.nkb = (rk + DBK - 1) / DBK;
+  sp.scale = scale;
+  sp.stages = r_stages_for(sp.nkb);
+#ifdef XKV_PROBE
+  sp.dbg = g_probe_dbg;
+  if (g_probe_stages > 0 && g_probe_stages < sp.stages) sp.stages = g_probe_stages;
+#endif
+  const int grid = ((S + DBM - 1) / DBM) * sp.tiles_n;
+  static PerDevice<bool> configured;
+  if (!configured()) {
+    XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(D_SMEM_BYTES)));
+    XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(D_SMEM_BYTES)));
+    XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_persistent_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(P_SMEM_BYTES)));
+    XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_persistent_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(P_SMEM_BYTES)));
+    configured() = true;
+  }
+  // persistent kernel when one head's slice of the right factor fits in shared memory
+  const bool persistent = static_cast<size_t>(sp.nkb) * D * DBK * 2 <= PB_MAX_BYTES && !g_force_tiled_scores;
+  if (persistent) {
+    const int sms = device_sm_count();
+    const int ntiles = (S + DBM - 1) / DBM;
+    int pgrid = sms < ntiles * H ? sms : ntiles * H;
+    if (pgrid < H) pgrid = H;   // every head needs at least one CTA
+    if (D == 128 && q_tma_ok && qpk <= 8 && g_scores_variant != 1) {
+      // score MMA; clusters of `want_cl` heads when the device can hold them, else smaller ones
+      int lrc = -1;
+      if (g_scores_variant == 2) want_cl = 1;
+      if (want_cl == 8) {
+        lrc = launch_scores_mma2<8>(sp, S, H, st);
+        if (lrc < 0) {
+          want_cl = 4;
+          rc = encode_tmap_2d_bf16(&sp.a_mc_map, A_k, rk, S, lda_k, DBK, DBM / 4);
+          if (rc) return rc;
+        }
+      }
+      if (lrc < 0 && want_cl == 4) {
+        lrc = launch_scores_mma2<4>(sp, S, H, st);
+        if (lrc < 0) {
+          want_cl = 2;
+          rc = encode_tmap_2d_bf16(&sp.a_mc_map, A_k, rk, S, lda_k, DBK, DBM / 2);
+          if (rc) return rc;
+        }
+      }
+      if (lrc < 0 && want_cl == 2) lrc = launch_scores_mma2<2>(sp, S, H, st);
+      if (lrc < 0) lrc = launch_scores_mma2<1>(sp, S, H, st);
+      if (lrc > 0) return lrc;
+      XKV_REQUIRE(lrc == 0, "decode: the score-MMA kernel cannot be launched on this device");
+    } else if (D == 128)
+      decode_scores_persistent_kernel<128><<<pgrid, P_THREADS, P_SMEM_BYTES, st>>>(sp);
+    else
+      decode_scores_persistent_kernel<64><<<pgrid, P_THREADS, P_SMEM_BYTES, st>>>(sp);
+  } else if (D == 128) {
+    decode_scores_kernel<128><<<grid, D_THREADS, D_SMEM_BYTES, st>>>(sp);
+  } else {
+    decode_scores_kernel<64><<<grid, D_THREADS, D_SMEM_BYTES, st>>>(sp);
+  }
+  XKV_LAUNCHED();
+  return 0;
+}
 
 }  // namespace xkv
 
@@ -1572,13 +1195,8 @@ extern "C" int xkv_decode_attention_lse(const void* q, int Hq, int H, int D, con
                                     const void* Vv_layer, int64_t ldv_v, int S, const void* cos, const void* sin,
                                     int64_t ld_cs, const void* k_tail, const void* v_tail, int T, int64_t tail_stride_h,
                                     int64_t tail_stride_t, float scale, void* out, void* workspace,
-                                    size_t workspace_bytes, const void* cos_t, const void* sin_t, int64_t ld_t,
-                                    void* stream, float* lse_out) {
+                                    size_t workspace_bytes, void* stream, float* lse_out) {
   XKV_REQUIRE(q && A_k && Vk_layer && A_v && Vv_layer && out && workspace, "decode: null argument");
-  XKV_REQUIRE((cos_t == nullptr) == (sin_t == nullptr), "decode: cos_t and sin_t must both be given or both be null");
-  XKV_REQUIRE(cos_t == nullptr || (cos != nullptr && ld_t % 128 == 0 && ld_t >= S &&
-                                   (reinterpret_cast<uintptr_t>(cos_t) & 15) == 0 && (reinterpret_cast<uintptr_t>(sin_t) & 15) == 0),
-              "decode: dim-major RoPE tables need cos/sin, 16-byte alignment and a row stride that is a multiple of 128 >= S");
   XKV_REQUIRE(D == 64 || D == 128, "decode: head_dim %d not supported (64 or 128)", D);
   XKV_REQUIRE(H >= 1 && Hq % H == 0 && Hq / H <= D_MAX_QPK && Hq <= 128, "decode: unsupported head counts Hq=%d H=%d", Hq, H);
   XKV_REQUIRE(S >= 1 && T >= 0 && rk >= 1 && rv >= 1 && rv % 2 == 0, "decode: bad sizes");
@@ -1606,130 +1224,8 @@ extern "C" int xkv_decode_attention_lse(const void* q, int Hq, int H, int D, con
   w += al(static_cast<size_t>(split + 1) * Hq * rv * 4);
 
   // ---- scores of the compressed prefix: fused reconstruct + RoPE + q.K ----
-  static thread_local ScoreParams sp;
-  std::memset(&sp, 0, sizeof(sp));
-  int rc = encode_tmap_2d_bf16(&sp.a_map, A_k, rk, S, lda_k, DBK, DBM);
+  int rc = launch_scores(q, Hq, H, D, A_k, lda_k, rk, Vk_layer, ldv_k, S, cos, sin, ld_cs, scale, scores, ldl, st);
   if (rc) return rc;
-  rc = encode_tmap_2d_bf16(&sp.b_map, Vk_layer, rk, static_cast<uint64_t>(H) * D, ldv_k, DBK, DBN);
-  if (rc) return rc;
-  rc = encode_tmap_2d_bf16(&sp.b_head_map, Vk_layer, rk, static_cast<uint64_t>(H) * D, ldv_k, DBK, D);
-  if (rc) return rc;
-  const bool q_tma_ok = D == 128 && (reinterpret_cast<uintptr_t>(q) & 15) == 0;
-  if (q_tma_ok) {
-    rc = encode_tmap_2d_bf16(&sp.q_map, q, D, Hq, D, 64, R_QROWS);
-    if (rc) return rc;
-    rc = encode_tmap_2d_bf16(&sp.q8_map, q, D, Hq, D, 64, 8);
-    if (rc) return rc;
-    rc = encode_tmap_2d_bf16(&sp.b_half_map, Vk_layer, rk, static_cast<uint64_t>(H) * D, ldv_k, DBK, 64);
-    if (rc) return rc;
-  }
-  sp.q = static_cast<const __nv_bfloat16*>(q);
-  sp.cos = static_cast<const __nv_bfloat16*>(cos);
-  sp.sin = static_cast<const __nv_bfloat16*>(sin);
-  sp.cos_t = static_cast<const __nv_bfloat16*>(cos_t);
-  sp.sin_t = static_cast<const __nv_bfloat16*>(sin_t);
-  sp.ld_t = ld_t;
-  sp.bk = static_cast<const __nv_bfloat16*>(Vk_layer);
-  sp.ld_bk = ldv_k;
-  sp.scores = scores;
-  sp.ld_cs = ld_cs;
-  sp.ld_scores = ldl;
-  sp.S = S;
-  sp.rk = rk;
-  sp.H = H;
-  sp.qpk = qpk;
-  sp.tiles_n = (H * D + DBN - 1) / DBN;
-  sp.nkb = (rk + DBK - 1) / DBK;
-  sp.scale = scale;
-  {
-    const char* e = getenv("XKV_DECODE_DBG");
-    sp.dbg = e ? atoi(e) : 0;
-  }
-  const int grid = ((S + DBM - 1) / DBM) * sp.tiles_n;
-  static bool configured = false;
-  if (!configured) {
-    XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(D_SMEM_BYTES)));
-    XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(D_SMEM_BYTES)));
-    configured = true;
-  }
-  // persistent kernel when one head's slice of the right factor fits in shared memory
-  const bool persistent = static_cast<size_t>(sp.nkb) * D * DBK * 2 <= PB_MAX_BYTES && !g_force_tiled_scores;
-  if (persistent) {
-    static bool pconf = false;
-    if (!pconf) {
-      XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_persistent_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(P_SMEM_BYTES)));
-      XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_persistent_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(P_SMEM_BYTES)));
-      pconf = true;
-    }
-    int dev = 0, sms = 148;
-    XKV_CHECK_CUDA(cudaGetDevice(&dev));
-    XKV_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int ntiles = (S + DBM - 1) / DBM;
-    int pgrid = sms < ntiles * H ? sms : ntiles * H;
-    if (pgrid < H) pgrid = H;   // every head needs at least one CTA
-    static const bool pair_env = getenv("XKV_DECODE_PAIR") != nullptr;   // opt-in: measured 99 us vs 92 us for the single-CTA kernel
-    const bool pair_off = !(pair_env || g_scores_variant == 3);
-    static const bool tr_default = getenv("XKV_DECODE_TR") != nullptr;   // transposed kernel: opt-in while it is slower
-    const int ntp = (S + 2 * DBM - 1) / (2 * DBM);
-    if (D == 128 && q_tma_ok && qpk <= 8 && !pair_off && sms >= 2 * H &&
-        static_cast<size_t>(sp.nkb) * 64 * DBK * 2 <= static_cast<size_t>(Q_BHALF_BYTES)) {
-      // CTA pairs: one cluster of 2 per (head, slot)
-      static bool qconf = false;
-      if (!qconf) {
-        XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(Q_SMEM_BYTES)));
-        qconf = true;
-      }
-      int npairs = sms / 2;
-      if (npairs > ntp * H) npairs = ntp * H;
-      if (npairs < H) npairs = H;
-      cudaLaunchConfig_t cfg;
-      std::memset(&cfg, 0, sizeof(cfg));
-      cfg.gridDim = dim3(2 * npairs, 1, 1);
-      cfg.blockDim = dim3(Q_THREADS, 1, 1);
-      cfg.dynamicSmemBytes = Q_SMEM_BYTES;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      XKV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_scores_pair_kernel, sp));
-    } else if (D == 128 && q_tma_ok && qpk <= 8 && (g_scores_variant == 4 || (g_scores_variant == 0 && tr_default)) &&
-               sp.nkb <= T_MAX_KB_TMEM + 1 && rk % 8 == 0 && ldv_k % 8 == 0 &&
-               (reinterpret_cast<uintptr_t>(Vk_layer) & 15) == 0 && (cos == nullptr || cos_t != nullptr)) {
-      // right factor resident in TMEM, token stream as the shared-memory operand
-      static bool tconf = false;
-      if (!tconf) {
-        XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_tr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(T_SMEM_BYTES)));
-        tconf = true;
-      }
-      decode_scores_tr_kernel<<<pgrid, T_THREADS, T_SMEM_BYTES, st>>>(sp);
-    } else if (D == 128 && q_tma_ok && qpk <= 8 && g_scores_variant != 1) {
-      static bool rconf = false;
-      if (!rconf) {
-        XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(R_SMEM_BYTES)));
-        rconf = true;
-      }
-      decode_scores_mma2_kernel<<<pgrid, R_THREADS, R_SMEM_BYTES, st>>>(sp);
-    } else if (D == 128)
-      decode_scores_persistent_kernel<128><<<pgrid, P_THREADS, P_SMEM_BYTES, st>>>(sp);
-    else
-      decode_scores_persistent_kernel<64><<<pgrid, P_THREADS, P_SMEM_BYTES, st>>>(sp);
-  } else if (D == 128) {
-    decode_scores_kernel<128><<<grid, D_THREADS, D_SMEM_BYTES, st>>>(sp);
-  } else {
-    decode_scores_kernel<64><<<grid, D_THREADS, D_SMEM_BYTES, st>>>(sp);
-  }
-  XKV_LAUNCHED();
   // ---- softmax with chunk-local maxima: chunk c = token range of split-K slab c, last chunk = the dense tail ----
   const int nkb_p = (S + 63) / 64;
   const int kps = (nkb_p + split - 1) / split;          // k-blocks per slab, as xkv_gemm_grouped cuts them
@@ -1784,30 +1280,19 @@ extern "C" int xkv_rope_bf16(void* x, int64_t ld_row, int rows, int H, int D, co
   return 0;
 }
 
-/* test hook: 1 forces the tile-per-CTA scores kernel, 0 restores the automatic choice */
-extern "C" int xkv_rope_tables_dim_major(const void* cos, const void* sin, int64_t ld_cs, int S, int D, void* cos_t,
-                                         void* sin_t, int64_t ld_t, void* stream) {
-  XKV_REQUIRE(cos && sin && cos_t && sin_t, "rope tables: null argument");
-  XKV_REQUIRE(S >= 1 && D >= 2 && D % 2 == 0 && ld_t >= S, "rope tables: bad sizes");
-  dim3 grid(static_cast<unsigned>((ld_t + 31) / 32), static_cast<unsigned>((D / 2 + 31) / 32));
-  rope_tables_dim_major_kernel<<<grid, 256, 0, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(cos), static_cast<const __nv_bfloat16*>(sin), ld_cs, S, D / 2,
-      static_cast<__nv_bfloat16*>(cos_t), static_cast<__nv_bfloat16*>(sin_t), ld_t);
-  XKV_LAUNCHED();
-  XKV_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
 extern "C" void xkv_decode_force_tiled(int on) { g_force_tiled_scores = on != 0; }
 /* test hook: which persistent scores kernel to use when several apply (0 automatic) */
 extern "C" void xkv_decode_set_variant(int variant) { g_scores_variant = variant; }
+/* tuning hook: cluster size of the score-MMA kernel (0 automatic) */
+extern "C" void xkv_decode_set_cluster(int cluster) { g_scores_cluster = cluster; }
 
 extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const void* A_k, int64_t lda_k, int rk,
                                     const void* Vk_layer, int64_t ldv_k, const void* A_v, int64_t lda_v, int rv,
                                     const void* Vv_layer, int64_t ldv_v, int S, const void* cos, const void* sin,
                                     int64_t ld_cs, const void* k_tail, const void* v_tail, int T, int64_t tail_stride_h,
                                     int64_t tail_stride_t, float scale, void* out, void* workspace,
-                                    size_t workspace_bytes, const void* cos_t, const void* sin_t, int64_t ld_t,
-                                    void* stream) {
-  return xkv_decode_attention_lse(q, Hq, H, D, A_k, lda_k, rk, Vk_layer, ldv_k, A_v, lda_v, rv, Vv_layer, ldv_v, S, cos, sin, ld_cs, k_tail, v_tail, T, tail_stride_h, tail_stride_t, scale, out, workspace, workspace_bytes, cos_t, sin_t, ld_t, stream, nullptr);
+                                    size_t workspace_bytes, void* stream) {
+  return xkv_decode_attention_lse(q, Hq, H, D, A_k, lda_k, rk, Vk_layer, ldv_k, A_v, lda_v, rv, Vv_layer, ldv_v, S, cos, sin,
+                                  ld_cs, k_tail, v_tail, T, tail_stride_h, tail_stride_t, scale, out, workspace,
+                                  workspace_bytes, stream, nullptr);
 }

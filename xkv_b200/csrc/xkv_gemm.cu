@@ -131,18 +131,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < niter; ++it) {
-        const int kb = kb0 + it / pr.nterms;
-        const int term = it - (it / pr.nterms) * pr.nterms;
-        const CUtensorMap* amap = &pr.a_map[pr.ta[term]];
-        const CUtensorMap* bmap = &pr.b_map[pr.tb[term]];
-        uint8_t* sA = smem + s * STAGE_BYTES;
-        uint8_t* sB = sA + A_TILE_BYTES;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
+    // ===================== TMA producer (whole warp in the loop, one elected lane issues) =====================
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < niter; ++it) {
+      const int kb = kb0 + it / pr.nterms;
+      const int term = it - (it / pr.nterms) * pr.nterms;
+      const CUtensorMap* amap = &pr.a_map[pr.ta[term]];
+      const CUtensorMap* bmap = &pr.b_map[pr.tb[term]];
+      uint8_t* sA = smem + s * STAGE_BYTES;
+      uint8_t* sB = sA + A_TILE_BYTES;
+      mbar_wait(&empty_bar[s], ph ^ 1u);
+      if (elect_one()) {
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
         if (A_MN == 0) {
           tma_load_2d(sA, amap, &full_bar[s], kb * BK, m0);
@@ -156,49 +156,51 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 #pragma unroll
           for (int c = 0; c < BN / 64; ++c) tma_load_2d(sB + c * CHUNK_BYTES, bmap, &full_bar[s], n0 + 64 * c, kb * BK);
         }
-        if (++s == STAGES) {
-          s = 0;
-          ph ^= 1u;
-        }
+      }
+      __syncwarp();
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1u;
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
-      int s = 0;
-      uint32_t ph = 0;
-      int it = 0;
-      for (int phs = 0; phs < nph; ++phs) {
-        const uint32_t acc = tmem_base + static_cast<uint32_t>(phs & 1) * TMEM_COLS;
-        if (phs >= 2) {   // the epilogue must have drained this accumulator (phase phs - 2)
-          mbar_wait(&tmem_empty_bar[phs & 1], static_cast<uint32_t>(((phs >> 1) - 1) & 1));
-          tc_fence_after();
-        }
-        const int it_end = (nph == 1) ? niter : static_cast<int>((static_cast<long long>(nk) * (phs + 1)) / nph) * pr.nterms;
-        bool fresh = true;
-        for (; it < it_end; ++it) {
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
-          const uint32_t b_base = a_base + A_TILE_BYTES;
+    // ===================== MMA issuer (whole warp in the loop, one elected lane issues) =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int phs = 0; phs < nph; ++phs) {
+      const uint32_t acc = tmem_base + static_cast<uint32_t>(phs & 1) * TMEM_COLS;
+      if (phs >= 2) {   // the epilogue must have drained this accumulator (phase phs - 2)
+        mbar_wait(&tmem_empty_bar[phs & 1], static_cast<uint32_t>(((phs >> 1) - 1) & 1));
+        tc_fence_after();
+      }
+      const int it_end = (nph == 1) ? niter : static_cast<int>((static_cast<long long>(nk) * (phs + 1)) / nph) * pr.nterms;
+      const int it_begin = it;
+      for (; it < it_end; ++it) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_base = a_base + A_TILE_BYTES;
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = A_MN ? umma_desc_sw128(a_base + k * 2048, CHUNK_BYTES, 1024)
                                      : umma_desc_sw128(a_base + k * 32, 16, 1024);
             const uint64_t db = B_MN ? umma_desc_sw128(b_base + k * 2048, CHUNK_BYTES, 1024)
                                      : umma_desc_sw128(b_base + k * 32, 16, 1024);
-            umma_bf16_ss(acc, da, db, idesc, (!fresh || k > 0) ? 1u : 0u);
+            umma_bf16_ss(acc, da, db, idesc, (it > it_begin || k > 0) ? 1u : 0u);
           }
-          fresh = false;
           umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
-          if (++s == STAGES) {
-            s = 0;
-            ph ^= 1u;
-          }
         }
-        umma_commit(&tmem_full_bar[phs & 1]);  // this phase's accumulator is complete
+        __syncwarp();
+        if (++s == STAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
+      if (elect_one()) umma_commit(&tmem_full_bar[phs & 1]);  // this phase's accumulator is complete
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -395,11 +397,11 @@ static int build_problem(const xkv_gemm_problem& in, GemmProb& out, int& cta_cur
 template <int A_MN, int B_MN>
 static int launch_variant(const GemmParams& params, int grid, cudaStream_t stream) {
   auto kern = gemm_kernel<A_MN, B_MN>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  static PerDevice<bool> configured;  // per instantiation and device
+  if (!configured()) {
     XKV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(GEMM_SMEM_BYTES)));
-    configured = true;
+    configured() = true;
   }
   kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(params);
   XKV_LAUNCHED();

@@ -24,6 +24,25 @@ const int*& launch_predicate();
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// One-time per-DEVICE set-up (cudaFuncSetAttribute and occupancy queries apply to the current device only; a
+// process that drives several GPUs must configure each).  Usage: static PerDevice<bool> done; if (!done()) {...}
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) d = 0;
+  return d < 0 ? 0 : (d >= kMaxDevices ? kMaxDevices - 1 : d);
+}
+template <class T>
+struct PerDevice {
+  T v[kMaxDevices];
+  PerDevice() {
+    for (int i = 0; i < kMaxDevices; ++i) v[i] = T();
+  }
+  T& operator()() { return v[current_device()]; }
+};
+// SM count of the current device (cached per device)
+int device_sm_count();
+
 #define XKV_CHECK_CUDA(expr)                                                                        \
   do {                                                                                              \
     cudaError_t _e = (expr);                                                                        \

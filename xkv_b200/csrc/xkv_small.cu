@@ -513,15 +513,7 @@ __global__ void sqrt_clamp_kernel(const float* __restrict__ in, float* __restric
   if (i < count) out[i] = sqrtf(fmaxf(in[i], 0.f));
 }
 
-static int sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      sms = 148;
-  }
-  return sms;
-}
+static int sm_count() { return device_sm_count(); }
 
 const int*& launch_predicate() {
   static thread_local const int* pred = nullptr;
@@ -752,12 +744,12 @@ extern "C" int xkv_jacobi_eigh(const float* const* T_host, float* const* evals_h
   p.ld = ld;
   p.ld_w = ld_w;
   const size_t smem = static_cast<size_t>(2 * W * (W + 1) + 2 * W) * sizeof(float) + 64;
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice<bool> configured;
+  if (!configured()) {
     XKV_CHECK_CUDA(cudaFuncSetAttribute(jacobi_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     XKV_CHECK_CUDA(cudaFuncSetAttribute(jacobi_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     XKV_CHECK_CUDA(cudaFuncSetAttribute(jacobi_kernel<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    configured = true;
+    configured() = true;
   }
   if (W == 128)
     jacobi_kernel<128><<<count, JAC_THREADS, smem, as_stream(stream)>>>(p);

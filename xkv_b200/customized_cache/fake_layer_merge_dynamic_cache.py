@@ -43,6 +43,7 @@ class _XkvLayer(DynamicLayer):
         self.tail_k: Optional[torch.Tensor] = None   # (1, H, T, D) post-RoPE keys appended during decode
         self.tail_v: Optional[torch.Tensor] = None
         self.tail_kpre: Optional[torch.Tensor] = None  # pre-RoPE copies, kept only when decode tokens get folded
+        self.kpre_from = 0                           # first tail row whose pre-RoPE copy is valid (0 = all of them)
         self.tail_len = 0
         self.dense_k: Optional[torch.Tensor] = None  # a slot of a compressed group that stayed dense (merge flag off)
         self.dense_v: Optional[torch.Tensor] = None
@@ -60,17 +61,24 @@ class _XkvLayer(DynamicLayer):
             cap = max(64, 2 * need)
             new_k = torch.empty(k.shape[0], k.shape[1], cap, k.shape[3], dtype=k.dtype, device=k.device)
             new_v = torch.empty(v.shape[0], v.shape[1], cap, v.shape[3], dtype=v.dtype, device=v.device)  # MLA: other width
-            new_p = torch.empty_like(new_k) if k_pre is not None else None
+            new_p = torch.empty_like(new_k) if (k_pre is not None or self.tail_kpre is not None) else None
+            if new_p is not None and self.tail_kpre is None:
+                self.kpre_from = self.tail_len       # rows appended before pre-RoPE copies were kept cannot be folded
             if self.tail_len:
                 new_k[:, :, : self.tail_len] = self.tail_k[:, :, : self.tail_len]
                 new_v[:, :, : self.tail_len] = self.tail_v[:, :, : self.tail_len]
                 if new_p is not None and self.tail_kpre is not None:
                     new_p[:, :, : self.tail_len] = self.tail_kpre[:, :, : self.tail_len]
             self.tail_k, self.tail_v, self.tail_kpre = new_k, new_v, new_p
+        if k_pre is not None and self.tail_kpre is None:   # the buffer predates the first pre-RoPE copy
+            self.tail_kpre = torch.empty_like(self.tail_k)
+            self.kpre_from = self.tail_len
         self.tail_k[:, :, self.tail_len:need] = k
         self.tail_v[:, :, self.tail_len:need] = v
         if k_pre is not None:
             self.tail_kpre[:, :, self.tail_len:need] = k_pre
+        elif self.tail_kpre is not None:
+            self.kpre_from = need                    # a token without a pre-RoPE copy: nothing up to here can be folded
         self.tail_len = need
 
 
@@ -78,7 +86,7 @@ class _GroupState:
     """Factors of one compressed group and the RoPE tables of its prefill positions."""
 
     def __init__(self, info: LayerGroup, factors: compress.GroupFactors, heads: int, head_dim: int,
-                 cos: Optional[torch.Tensor], sin: Optional[torch.Tensor], re_apply_rope: bool, prefill_len: int = 0):
+                 cos: Optional[torch.Tensor], sin: Optional[torch.Tensor], re_apply_rope: bool):
         self.info = info
         self.factors = factors
         self.heads = heads
@@ -86,10 +94,9 @@ class _GroupState:
         self.cos = cos      # (S, D) bf16 or None
         self.sin = sin
         self.re_apply_rope = re_apply_rope
-        # dim-major copies of the tables for the decode kernel that keeps the right factor in tensor memory
-        self.rope_t = None
-        if re_apply_rope and cos is not None and head_dim == 128:
-            self.rope_t = ops.rope_tables_dim_major(cos[:prefill_len], sin[:prefill_len], capacity=cos.shape[0])
+        # RoPE rows (cos, sin) of the decode tokens waiting in the dense tails, one per decode step (recorded when the
+        # group's first layer sees the token); consumed when the tokens are folded into the factors
+        self.tail_rope: List[Tuple[torch.Tensor, torch.Tensor]] = []
 
 
 class FakeLayerMergingCache(DynamicCache):
@@ -108,6 +115,7 @@ class FakeLayerMergingCache(DynamicCache):
         self.factorize_options = factorize_options
         self._groups: Dict[int, _GroupState] = {}
         self._workspace: Optional[torch.Tensor] = None
+        self._merge_cos_sin = (None, None, True)     # (cos, sin, re_apply_rope) of the prefill call being merged
         self.num_heads: Optional[int] = None
         self.head_dim: Optional[int] = None
 
@@ -143,6 +151,12 @@ class FakeLayerMergingCache(DynamicCache):
             return self.materialize(layer_idx) if return_dense else (None, None)
         if key.shape[0] != 1:
             raise XkvError("FakeLayerMergingCache: batch size 1 only on the B200 path")
+        if layer.group is not None:
+            # The reference would re-run its SVD on a cache whose keys already carry RoPE (a
+            # single prefill call is assumed); here the dense prefill tensors are gone, so say so instead of failing
+            # inside torch.cat.
+            raise XkvError(f"FakeLayerMergingCache: layer {layer_idx} is already compressed; a second prefill-mode update "
+                           "(chunked prefill, multi-turn reuse of one cache object) is not supported -- use a fresh cache")
         self.num_heads = key.shape[1]
         self.head_dim = key.shape[3]
         info = self.merge_setup.get_group_for_layer(layer_idx)
@@ -196,7 +210,7 @@ class FakeLayerMergingCache(DynamicCache):
             sn = torch.empty_like(cs)
             cs[:seq] = cos[0]
             sn[:seq] = sin[0]
-        state = _GroupState(info, gf, self.num_heads, self.head_dim, cs, sn, bool(re_rope), prefill_len=seq)
+        state = _GroupState(info, gf, self.num_heads, self.head_dim, cs, sn, bool(re_rope))
         state.length = seq
         state.layer_ids = ids
         self._groups[first] = state
@@ -297,6 +311,9 @@ class FakeLayerMergingCache(DynamicCache):
             return None
         fold = self.compress_decode_tokens and key_pre_rope is not None
         layer.append_tail(key, value, key_pre_rope if fold else None)
+        if fold and layer_idx == st.layer_ids[0] and st.re_apply_rope and cos is not None:
+            st.tail_rope.append((cos.reshape(-1, cos.shape[-1])[-1].to(torch.bfloat16),
+                                 sin.reshape(-1, sin.shape[-1])[-1].to(torch.bfloat16)))
         h, d = st.heads, st.head_dim
         rows = slice(layer.index_in_group * h * d, (layer.index_in_group + 1) * h * d)
         fk, fv = st.factors.key, st.factors.value
@@ -308,19 +325,23 @@ class FakeLayerMergingCache(DynamicCache):
             query[0, :, 0, :], fk.A_storage[:n_tok], fk.V[rows], fv.A_storage[:n_tok], fv.V[rows], h,
             st.cos[:n_tok] if st.re_apply_rope else None, st.sin[:n_tok] if st.re_apply_rope else None,
             layer.tail_k[0, :, : layer.tail_len], layer.tail_v[0, :, : layer.tail_len], scaling,
-            workspace=self._workspace, rope_t=st.rope_t if st.re_apply_rope else None)
+            workspace=self._workspace)
         if fold and layer_idx == st.layer_ids[-1]:
-            self._fold_tail(st, cos, sin)
+            self._fold_tail(st)
         return out[None, :, None, :]
 
     @torch.no_grad()
-    def _fold_tail(self, st: "_GroupState", cos: Optional[torch.Tensor], sin: Optional[torch.Tensor]) -> None:
+    def _fold_tail(self, st: "_GroupState") -> None:
         """North-star step 4: every layer of the group has now seen the same T tail tokens; gather their
         pre-RoPE keys / values into the group's token-major rows, project them onto the right factors and
-        append the result to A_k / A_v.  The tokens leave the dense tails."""
+        append the result to A_k / A_v.  The tokens leave the dense tails.  Each token's RoPE row was recorded when
+        it was appended (``st.tail_rope``); if the tails are not uniform (a layer took the dense path for a step, a
+        pre-RoPE copy is missing, a RoPE row is missing) nothing is folded and the tokens simply stay dense (exact)."""
         layers = [self._layer(i) for i in st.layer_ids]
         t = layers[0].tail_len
-        if t == 0 or any(l.tail_len != t or l.tail_kpre is None for l in layers):
+        if t == 0 or any(l.tail_len != t or l.tail_kpre is None or l.kpre_from > 0 for l in layers):
+            return
+        if st.re_apply_rope and st.cos is not None and len(st.tail_rope) != t:
             return
         fk, fv = st.factors.key, st.factors.value
         if st.length + t > fk.A_storage.shape[0]:
@@ -329,14 +350,34 @@ class FakeLayerMergingCache(DynamicCache):
         xv = ops.pack_group([l.tail_v[:, :, :t] for l in layers])[0]
         ops.append_project(xk, fk.V, out=fk.A_storage[st.length: st.length + t])
         ops.append_project(xv, fv.V, out=fv.A_storage[st.length: st.length + t])
-        if st.re_apply_rope and cos is not None:
-            st.cos[st.length: st.length + t] = cos.reshape(-1, cos.shape[-1])[-t:]
-            st.sin[st.length: st.length + t] = sin.reshape(-1, sin.shape[-1])[-t:]
-            if st.rope_t is not None:
-                half = st.head_dim // 2
-                st.rope_t[0][:, st.length: st.length + t] = st.cos[st.length: st.length + t, :half].t()
-                st.rope_t[1][:, st.length: st.length + t] = st.sin[st.length: st.length + t, :half].t()
+        if st.re_apply_rope and st.cos is not None:
+            st.cos[st.length: st.length + t] = torch.stack([c for c, _ in st.tail_rope])
+            st.sin[st.length: st.length + t] = torch.stack([x for _, x in st.tail_rope])
+        st.tail_rope.clear()
         st.length += t
         for l in layers:
             l.prefill_len = st.length
             l.tail_len = 0
+            l.kpre_from = 0
+
+    # ------------------------------------------------------------------ unsupported cache surgery
+    def _refuse_if_compressed(self, what: str) -> None:
+        if any(getattr(l, "group", None) is not None for l in self.layers):
+            raise XkvError(f"FakeLayerMergingCache.{what}: not supported once layer groups are factorised (the dense "
+                           "per-layer tensors no longer exist; beam search / cache cropping need the dense cache)")
+
+    def crop(self, max_length: int):
+        self._refuse_if_compressed("crop")
+        return super().crop(max_length)
+
+    def batch_repeat_interleave(self, repeats: int):
+        self._refuse_if_compressed("batch_repeat_interleave")
+        return super().batch_repeat_interleave(repeats)
+
+    def batch_select_indices(self, indices: torch.Tensor):
+        self._refuse_if_compressed("batch_select_indices")
+        return super().batch_select_indices(indices)
+
+    def reorder_cache(self, beam_idx: torch.LongTensor):
+        self._refuse_if_compressed("reorder_cache")
+        return super().reorder_cache(beam_idx)

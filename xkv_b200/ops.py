@@ -24,9 +24,20 @@ def _stream() -> C.c_void_p:
 
 
 def _require_cuda(*tensors: torch.Tensor) -> None:
+    """Every operand must live on the CURRENT CUDA device: the library launches on the current device's current
+    stream (kernels, tensor maps and per-device attributes all belong to it).  A process that shards a model over
+    several GPUs (device_map) wraps the call in ``torch.cuda.device(tensor.device)``."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise _lib.XkvError("xkv_b200 ops need CUDA tensors: there is no CPU path")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise _lib.XkvError(f"xkv_b200 op called with a tensor on cuda:{t.device.index} while cuda:{cur} is the current "
+                                "device: wrap the call in torch.cuda.device(tensor.device)")
 
 
 def launch_count() -> int:
@@ -290,16 +301,13 @@ def decode_attention(q: torch.Tensor, a_k: torch.Tensor, vk_layer: torch.Tensor,
                      sin: Optional[torch.Tensor], k_tail: Optional[torch.Tensor], v_tail: Optional[torch.Tensor],
                      scale: float, out: Optional[torch.Tensor] = None,
                      workspace: Optional[torch.Tensor] = None,
-                     rope_t: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
                      lse_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """softmax(scale * q [K^; K_tail]^T) [V^; V_tail] for one layer, batch 1, with K^ = rope(bf16(A_k Vk_l^T)) and
     V^ = A_v Vv_l^T never materialised.  q (Hq, D); a_k (S, rk); vk_layer (H*D, rk); a_v (S, rv);
     vv_layer (H*D, rv); cos/sin (S, D) or None; k_tail/v_tail (H, T, D) or None.  Returns (Hq, D) bf16.
-    rope_t: the dim-major copies of cos / sin from ``rope_tables_dim_major`` (built once per prefill); with them
-    the scores kernel that keeps the right factor in tensor memory is used (head_dim 128, r_k <= 512).
     lse_out: optional (Hq,) fp32 tensor that receives log sum exp of the scaled scores over THIS call's tokens
     (token-sharded contexts: see parallel.merge_token_shards)."""
-    _require_cuda(q, a_k, vk_layer, a_v, vv_layer)
+    _require_cuda(q, a_k, vk_layer, a_v, vv_layer, cos, sin, k_tail, v_tail, out, workspace)
     if lse_out is not None and (not lse_out.is_cuda or lse_out.dtype != torch.float32 or lse_out.numel() < q.shape[0]
                                 or not lse_out.is_contiguous()):
         raise _lib.XkvError("decode_attention: lse_out must be a contiguous CUDA fp32 tensor of Hq elements")
@@ -324,34 +332,12 @@ def decode_attention(q: torch.Tensor, a_k: torch.Tensor, vk_layer: torch.Tensor,
         if k_tail.stride() != v_tail.stride() or k_tail.stride(-1) != 1:
             raise _lib.XkvError("decode_attention: k_tail / v_tail must share strides, unit inner stride")
         sh, st = k_tail.stride(0), k_tail.stride(1)
-    cos_t = sin_t = None
-    if rope_t is not None and cos is not None:
-        cos_t, sin_t = rope_t
-        if (cos_t.dtype != torch.bfloat16 or cos_t.shape != sin_t.shape or cos_t.stride() != sin_t.stride()
-                or cos_t.stride(1) != 1 or cos_t.shape[0] != d // 2 or cos_t.shape[1] < s):
-            raise _lib.XkvError("decode_attention: rope_t must be the (D/2, >= S) bf16 tables of rope_tables_dim_major")
     check(_lib.load().xkv_decode_attention_lse(
         _ptr(q), hq, num_kv_heads, d, _ptr(a_k), a_k.stride(0), rk, _ptr(vk_layer), vk_layer.stride(0),
         _ptr(a_v), a_v.stride(0), rv, _ptr(vv_layer), vv_layer.stride(0), s, _ptr(cos), _ptr(sin),
         cos.stride(0) if cos is not None else 0, _ptr(k_tail if t else None), _ptr(v_tail if t else None), t, sh, st,
-        C.c_float(scale), _ptr(out), C.c_void_p(workspace.data_ptr()), workspace.numel(), _ptr(cos_t), _ptr(sin_t),
-        cos_t.stride(0) if cos_t is not None else 0, _stream(), _ptr(lse_out)))
+        C.c_float(scale), _ptr(out), C.c_void_p(workspace.data_ptr()), workspace.numel(), _stream(), _ptr(lse_out)))
     return out
-
-
-def rope_tables_dim_major(cos: torch.Tensor, sin: torch.Tensor, capacity: Optional[int] = None):
-    """(cos_t, sin_t): (D/2, ld) bf16 with cos_t[i, t] = cos[t, i] (the HF tables repeat the D/2 frequencies in both
-    halves), ld = max(S, capacity) rounded up to 128, columns >= S zeroed.  Built once per prefill."""
-    _require_cuda(cos, sin)
-    s, d = cos.shape
-    if cos.dtype != torch.bfloat16 or sin.dtype != torch.bfloat16 or cos.stride(1) != 1 or cos.stride() != sin.stride():
-        raise _lib.XkvError("rope_tables_dim_major: cos/sin must be bf16 (S, D) tables with equal strides")
-    ld = (max(s, capacity or 0) + 127) // 128 * 128
-    cos_t = torch.empty(d // 2, ld, dtype=torch.bfloat16, device=cos.device)
-    sin_t = torch.empty_like(cos_t)
-    check(_lib.load().xkv_rope_tables_dim_major(_ptr(cos), _ptr(sin), cos.stride(0), s, d, _ptr(cos_t), _ptr(sin_t), ld,
-                                                _stream()))
-    return cos_t, sin_t
 
 
 def rope_bf16_(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
