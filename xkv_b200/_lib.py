@@ -9,7 +9,8 @@ import ctypes as C
 import os
 from typing import Optional
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libxkv_b200.so")
+# XKV_B200_LIB: another build of the same library (same-box A/B measurements of a kernel change); default: the in-tree build
+_LIB_PATH = os.environ.get("XKV_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libxkv_b200.so")
 _lib: Optional[C.CDLL] = None
 
 MAX_GROUP_LAYERS = 16

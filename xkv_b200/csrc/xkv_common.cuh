@@ -225,6 +225,12 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+// shared memory -> tensor memory: 128 rows x 256 bits (one K = 16 slice of a bf16 operand tile described like an MMA
+// A operand) land in lanes 0..127, 8 consecutive 32-bit columns: the layout the TS-form MMA reads its A operand in.
+// Executes in issue order with the tcgen05.mma / tcgen05.commit of the same thread.
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t desc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(desc) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------

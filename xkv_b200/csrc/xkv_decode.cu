@@ -608,10 +608,19 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
       const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * D);
       for (int kb = 0; kb < P.nkb; ++kb) {
         if (!XKV_DBG(P, 64)) mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
+        if (!XKV_DBG(P, 2048)) tc_fence_after();
         const uint32_t a_base = smem_u32(sA + s * D_A_BYTES);
         if (elect_one()) {
-          if (XKV_DBG(P, 128)) {   // probe: A operand from tensor memory (TS form) instead of shared memory
+          if (XKV_DBG(P, 256)) {   // probe: stage the token tile in tensor memory (tcgen05.cp), then TS-form MMAs
+            const uint32_t a_tm = tmem_base + 448u + static_cast<uint32_t>((kb & 1) * 32);
+#pragma unroll
+            for (int k = 0; k < DBK / 16; ++k)
+              tmem_cp_128x256b(a_tm + static_cast<uint32_t>(k * 8), umma_desc_sw128(a_base + k * 32, 16, 1024));
+#pragma unroll
+            for (int k = 0; k < DBK / 16; ++k)
+              umma_bf16_ts(d_addr, a_tm + static_cast<uint32_t>(k * 8),
+                           umma_desc_sw128(b_base + kb * B_KB_BYTES + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          } else if (XKV_DBG(P, 128)) {   // probe: A operand from tensor memory (TS form) instead of shared memory
 #pragma unroll
             for (int k = 0; k < DBK / 16; ++k)
               umma_bf16_ts(d_addr, tmem_base + R_COL_A2 + static_cast<uint32_t>(k * 8),
@@ -622,12 +631,14 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
               umma_bf16_ss(d_addr, umma_desc_sw128(a_base + k * 32, 16, 1024),
                            umma_desc_sw128(b_base + kb * B_KB_BYTES + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          if (CL > 1)
+          if (XKV_DBG(P, 512)) {
+            // probe: no per-stage commit
+          } else if (CL > 1)
             umma_commit_multicast(&empty_bar[s], CL_MASK);
           else
             umma_commit(&empty_bar[s]);
         }
-        __syncwarp();
+        if (!XKV_DBG(P, 1024)) __syncwarp();
         if (++s == R_STAGES) {
           s = 0;
           ph ^= 1u;
