@@ -1,22 +1,29 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the xKV hot path on B200 (contract: see the task statement).
 
-Workload (BASELINE.json configs[1]): Llama-3.1-8B-shaped KV (32 layers, 8 KV heads x 128), 64K context,
-batch 1, xKV-4 (8 groups of 4 layers, rank_k 512 / rank_v 768).  One *step* = prefill compression of the
-whole cache: gather every group's K and V into token-major matrices and factorise them (16 matrices of
-65536 x 4096).  `value` is GB/s of bf16 KV consumed with inputs resident in HBM; `e2e` is the same through
-host buffers (pinned H2D of the KV and D2H of the factors inside the timed region).  The decode-side
-number (fused reconstruct + attention, tok/s) is reported beside it as `decode`.
+Workload (BASELINE.json configs[1], `--config 2`, the default): Llama-3.1-8B-shaped KV (32 layers, 8 KV heads x 128),
+64K context, batch 1, xKV-4 (8 groups of 4 layers, rank_k 512 / rank_v 768).  One *step* = prefill compression of the
+whole cache: every group's K and V gathered and factorised (16 matrices of 65536 x 4096).  `value` is GB/s of bf16 KV
+consumed with inputs resident in HBM; `e2e` is the same through host buffers (pinned H2D of the KV and D2H of the
+factors inside the timed region); `decode` is the fused reconstruct + attention over the factors (tok/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 2|3|4|5]
 
-N > 1 is launched with torchrun; each rank owns its own 8 groups (weak scaling over layer groups, no
-data-path collective); time is the max over ranks.
+N > 1 is launched with torchrun.  The headline `value` is the contract's weak-scaling number (every rank compresses a
+whole 8-group cache of its own: layer groups are independent, no data-path collective).  Two more multi-GPU records
+measure the partitions BASELINE.json names:
+  strong         ONE cache's 8 groups split over the ranks by parallel.assign_groups (1 group per GPU at N = 8);
+  token_sharded  configs[3] (Llama-3.1-70B shape, xKV-8, 128K): one K and one V matrix 131072 x 8192 (rank 1024 / 1536)
+                 with token rows split over the ranks; the only collective is the NCCL all-reduce of the packed upper
+                 triangle of each n x n fp32 Gram (factorize_batch(process_group=...)).
+The default run also reports `append` (north-star step 4), `other_configs` (configs[2] and [4] on this GPU) and, at
+N = 1, `gpu_reference` (the reference's own library path, torch.linalg.svd, on the same device) and `cpu_baseline`.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -27,9 +34,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "KV GB/s compressed (prefill, xKV-4, Llama-3.1-8B 64K)"
-LAYERS, GROUP, HEADS, HEAD_DIM = 32, 4, 8, 128
-RANK_K, RANK_V = 512, 768
+# BASELINE.json configs (index = position in `configs`, 1-based as SURVEY.md section 8 numbers them)
+CONFIGS = {
+    2: dict(title="xKV-4, Llama-3.1-8B 64K", model="Llama-3.1-8B-shaped KV", layers=32, group=4, heads=8, head_dim=128,
+            tokens=65536, rank_k=512, rank_v=768, merge_value=True, alpha_k=1.0, alpha_v=0.5),
+    3: dict(title="single SVD (layer_group_size 1), Llama-3.1-8B 64K", model="Llama-3.1-8B-shaped KV", layers=32, group=1,
+            heads=8, head_dim=128, tokens=65536, rank_k=128, rank_v=192, merge_value=True, alpha_k=1.0, alpha_v=0.5),
+    4: dict(title="xKV-8, Llama-3.1-70B 128K", model="Llama-3.1-70B-shaped KV", layers=80, group=8, heads=8, head_dim=128,
+            tokens=131072, rank_k=1024, rank_v=1536, merge_value=True, alpha_k=1.0, alpha_v=0.5),
+    5: dict(title="xKV-4 on MLA latents, DeepSeek-V2-Lite 32K", model="DeepSeek-V2-Lite MLA latents (kv_lora_rank 512)",
+            layers=27, group=4, heads=1, head_dim=512, tokens=32768, rank_k=512, rank_v=None, merge_value=False,
+            alpha_k=1.0, alpha_v=0.5),
+}
+METRIC = "KV GB/s compressed (prefill, {title})"
+SAMPLE_TOKENS = 4096   # tokens of the bounded CPU / library-SVD samples (BASELINE.json configs[0]'s shape)
 
 
 def parse_args():
@@ -38,34 +56,98 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="xkv_b200", choices=["xkv_b200", "reference"])
-    ap.add_argument("--tokens", type=int, default=65536)
-    ap.add_argument("--cpu-sample-tokens", type=int, default=4096)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--tokens", type=int, default=0, help="override the configuration's context length")
+    ap.add_argument("--cpu-sample-tokens", type=int, default=SAMPLE_TOKENS)
+    ap.add_argument("--cpu-full-tokens", type=int, default=65536,
+                    help="reference arm: ONE K matrix at this many tokens is timed once per run (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip strong / token_sharded / append / other_configs / gpu_reference")
     ap.add_argument("--streams", type=int, default=6, help="CUDA streams the K / V batches are spread over")
     ap.add_argument("--e2e-chunk", type=int, default=1, help="layer groups per pipelined chunk of the host-buffer path")
+    ap.add_argument("--packed", action="store_true", help="gather every group into a packed matrix first (round 1's path) "
+                    "instead of reading the layer tensors in place")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from the host instead of replaying a CUDA graph")
     return ap.parse_args()
+
+
+def config_of(args):
+    c = dict(CONFIGS[args.config])
+    if args.tokens:
+        c["tokens"] = args.tokens
+    return c
+
+
+def group_sizes(c):
+    """Layer groups of the configuration: consecutive chunks, the last one may be short (configurations.py:267-273)."""
+    full, rest = divmod(c["layers"], c["group"])
+    return [c["group"]] * full + ([rest] if rest else [])
+
+
+def kv_bytes_of(c):
+    sides = 2 if c["merge_value"] else 1
+    return sides * c["layers"] * c["tokens"] * c["heads"] * c["head_dim"] * 2
+
+
+def reference_sample_text(c, tokens):
+    return (f"ONE {min(c['group'], 4)}-layer group ({c['heads']} KV heads x {c['head_dim']}) at {tokens} tokens per step "
+            f"(BASELINE.json configs[0]'s shape; a bounded sample of the workload, GB/s of its own bytes): the reference's "
+            f"arithmetic, torch.linalg.svd fp32 -> truncate -> multiply back, K rank {c['rank_k']}"
+            + (f" + V rank {c['rank_v']}" if c["merge_value"] else ""))
+
+
+def workload_config(args, c):
+    ng = len(group_sizes(c))
+    return {
+        "workload": f"{c['model']}, {c['layers']} layers x {c['heads']} KV heads x {c['head_dim']}, {c['tokens']} tokens, "
+                    f"batch 1, xKV-{c['group']} ({ng} groups), rank_k {c['rank_k']} / rank_v {c['rank_v']}",
+        "baseline_config": args.config, "tokens": c["tokens"], "groups_per_gpu": ng,
+        "parallelism": f"layer-groups x{args.gpus}", "l2": f"inputs ({kv_bytes_of(c) / 1e9:.1f} GB per step) exceed L2",
+        "cuda_streams": args.streams,
+        # what `--impl reference` times per step (the CPU arm cannot run the 64K workload in minutes); both arms carry
+        # the same text so that the two `config` objects are equal by content
+        "reference_arm_sample": reference_sample_text(c, args.cpu_sample_tokens),
+    }
 
 
 # ----------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the reference's own arithmetic (oracle port of fake_svd etc.)
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_step(sample_tokens: int, seed: int = 0):
-    """One bounded sample of the workload on the host cores: one 4-layer group (K rank 512 + V rank 768)
-    at `sample_tokens` tokens through the oracle's grouped merge. Returns (seconds, bytes_of_kv)."""
+def cpu_reference_step(c, sample_tokens: int, seed: int = 0):
+    """One bounded sample of the workload on the host cores: one layer group at `sample_tokens` tokens through the
+    oracle's grouped merge. Returns (seconds, bytes_of_kv)."""
+    from oracle import xkv_oracle as O
+    from xkv_b200 import synthetic
+
+    g = min(c["group"], 4)
+    keys = synthetic.make_group_kv(g, c["heads"], sample_tokens, c["head_dim"], c["alpha_k"], seed)
+    vals = synthetic.make_group_kv(g, c["heads"], sample_tokens, c["head_dim"], c["alpha_v"], seed + 1)
+    t0 = time.perf_counter()
+    O.merge_group(keys, vals, c["rank_k"], c["rank_v"] if c["merge_value"] else None, True, c["merge_value"])
+    dt = time.perf_counter() - t0
+    nbytes = (2 if c["merge_value"] else 1) * g * c["heads"] * sample_tokens * c["head_dim"] * 2
+    return dt, nbytes
+
+
+def cpu_full_size_matrix(c, tokens: int):
+    """ONE K matrix of the configuration at `tokens` tokens (65536 x 4096 at config 2) through the reference's fake_svd
+    arithmetic, once: shows what the bounded sample's GB/s extrapolates to at the stated context length."""
     import torch
     from oracle import xkv_oracle as O
     from xkv_b200 import synthetic
 
-    keys = synthetic.make_group_kv(GROUP, HEADS, sample_tokens, HEAD_DIM, 1.0, seed)
-    vals = synthetic.make_group_kv(GROUP, HEADS, sample_tokens, HEAD_DIM, 0.5, seed + 1)
+    g = min(c["group"], 4)
+    keys = synthetic.make_group_kv(g, c["heads"], tokens, c["head_dim"], c["alpha_k"], 11)
+    x = torch.cat(keys, dim=1).float()
     t0 = time.perf_counter()
-    O.merge_group(keys, vals, RANK_K, RANK_V)
+    O.fake_svd(x, c["rank_k"])
     dt = time.perf_counter() - t0
-    nbytes = 2 * GROUP * HEADS * sample_tokens * HEAD_DIM * 2
-    return dt, nbytes
+    nbytes = g * c["heads"] * tokens * c["head_dim"] * 2
+    return {"tokens": tokens, "matrix": f"{tokens} x {g * c['heads'] * c['head_dim']} fp32, rank {c['rank_k']}", "seconds": dt,
+            "GBps_of_bf16_KV": nbytes / dt / 1e9,
+            "note": "one K matrix, timed once; the whole cache is 2 x groups such matrices (V at its own rank)"}
 
 
 def run_reference_arm(args):
@@ -74,37 +156,33 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    c = config_of(args)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     for _ in range(args.warmup):
-        cpu_reference_step(args.cpu_sample_tokens)
+        cpu_reference_step(c, args.cpu_sample_tokens)
     times = []
     nbytes = 0
     for i in range(args.steps):
-        dt, nbytes = cpu_reference_step(args.cpu_sample_tokens, seed=i)
+        dt, nbytes = cpu_reference_step(c, args.cpu_sample_tokens, seed=i)
         times.append(dt)
     total = sum(times)
     value = nbytes * len(times) / total / 1e9
-    sample = (f"one 4-layer group (8 KV heads x 128) at {args.cpu_sample_tokens} tokens per step: oracle port of "
-              f"grouped_layer_merging (torch.linalg.svd fp32, K rank {RANK_K} + V rank {RANK_V})")
+    sample = reference_sample_text(c, args.cpu_sample_tokens)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC.format(title=c["title"]), "value": value, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args),
+        "config": workload_config(args, c),
         "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if args.cpu_full_tokens and args.cpu_full_tokens > args.cpu_sample_tokens:
+        try:
+            line["cpu_baseline"]["full_size_check"] = cpu_full_size_matrix(c, args.cpu_full_tokens)
+        except Exception as ex:   # e.g. out of host memory: the bounded sample stands on its own
+            line["cpu_baseline"]["full_size_check"] = {"error": f"{type(ex).__name__}: {ex}"}
     print(json.dumps(line), flush=True)
-
-
-def workload_config(args):
-    return {
-        "workload": f"Llama-3.1-8B-shaped KV, {LAYERS} layers x {HEADS} KV heads x {HEAD_DIM}, {args.tokens} tokens, "
-                    f"batch 1, xKV-{GROUP} ({LAYERS // GROUP} groups), rank_k {RANK_K} / rank_v {RANK_V}",
-        "tokens": args.tokens, "groups_per_gpu": LAYERS // GROUP, "parallelism": f"layer-groups x{args.gpus}",
-        "l2": "inputs (8.6 GB per step) exceed L2", "cuda_streams": args.streams,
-    }
 
 
 # ----------------------------------------------------------------------------------------------
@@ -159,268 +237,556 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # the B200 arm
 # ----------------------------------------------------------------------------------------------
-def run_xkv_arm(args):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """Process-level state of one bench run (rank, device, collectives, timing helpers)."""
 
-    from xkv_b200 import compress, factorize, ops, synthetic
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    S = args.tokens
-    ng = LAYERS // GROUP
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        try:
+            self.peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            self.peaks = {}
+        self.peak_tf = float(self.peaks.get("bf16_tflops_sustained", 1400.0))
+        self.peak_hbm = float(self.peaks.get("hbm_gbs", 6550.0))
 
-    # ---- synthetic KV, resident in HBM (seeded per rank: every rank owns different groups) ----
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_ms(self, ms: float) -> float:
+        t = self.torch.tensor([ms], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.item()
+
+    def time_steps(self, fn, steps: int, warmup: int = 1) -> float:
+        """ms per call of fn(): barrier + synchronize on both sides, CUDA events, max over ranks."""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        return self.max_ms(e0.elapsed_time(e1)) / steps
+
+
+def make_cache(c, dev, seed_base=0):
+    """Synthetic KV of one model: keys[g][i] / vals[g][i] (1, H, S, D) bf16 views of token-major memory."""
+    from xkv_b200 import synthetic
+
     keys, vals = [], []
-    for g in range(ng):
-        keys.append(synthetic.make_group_kv(GROUP, HEADS, S, HEAD_DIM, 1.0, 1234 + 100 * rank + g, device=dev))
-        vals.append(synthetic.make_group_kv(GROUP, HEADS, S, HEAD_DIM, 0.5, 5678 + 100 * rank + g, device=dev))
-    kv_bytes = 2 * LAYERS * S * HEADS * HEAD_DIM * 2
+    for g, size in enumerate(group_sizes(c)):
+        keys.append(synthetic.make_group_kv(size, c["heads"], c["tokens"], c["head_dim"], c["alpha_k"],
+                                            1234 + seed_base + g, device=dev))
+        vals.append(synthetic.make_group_kv(size, c["heads"], c["tokens"], c["head_dim"], c["alpha_v"],
+                                            5678 + seed_base + g, device=dev) if c["merge_value"] else None)
+    return keys, vals
 
-    opts = factorize.FactorizeOptions()
 
-    graphed = None
-    if not args.no_graph:
-        graphed = compress.GraphedCompressor(keys, vals, RANK_K, RANK_V, opts=opts, num_streams=args.streams)
+def ctx_args_packed(step) -> bool:
+    return bool(getattr(step, "packed", False))
 
-    def step():
-        if graphed is not None:
-            return graphed.replay()
-        return compress.compress_groups(keys, vals, RANK_K, RANK_V, opts=opts, num_streams=args.streams)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+class CompressStep:
+    """The timed step: compress every layer group of a cache (equal-sized groups in one call, a short last group in
+    another), replayed as a CUDA graph unless --no-graph."""
+
+    def __init__(self, ctx, c, keys, vals, streams, graph=True):
+        from xkv_b200 import compress, factorize
+
+        self.torch = ctx.torch
+        self.opts = factorize.FactorizeOptions()
+        sizes = [len(k) for k in keys]
+        self.calls = []
+        for size in sorted(set(sizes), reverse=True):
+            idx = [i for i, s in enumerate(sizes) if s == size]
+            self.calls.append(([keys[i] for i in idx], [vals[i] if vals[i] is not None else keys[i] for i in idx], idx))
+        self.c, self.streams, self.compress = c, streams, compress
+        self.packed = bool(getattr(ctx.args, "packed", False))
+        self.graph = None
+        self.n_groups = len(keys)
+        self.out = None
+        if graph and self.n_groups:
+            self.enqueue()
+            ctx.torch.cuda.synchronize()
+            self.graph = ctx.torch.cuda.CUDAGraph()
+            with ctx.torch.cuda.graph(self.graph):
+                self.out = self.enqueue()
+
+    def enqueue(self):
+        out = [None] * self.n_groups
+        for ks, vs, idx in self.calls:
+            res = self.compress.compress_groups(ks, vs, self.c["rank_k"], self.c["rank_v"], merge_value=self.c["merge_value"],
+                                                opts=self.opts, num_streams=self.streams, in_place=not ctx_args_packed(self))
+            for i, r in zip(idx, res):
+                out[i] = r
+        return out
+
+    def __call__(self):
+        if self.graph is not None:
+            self.graph.replay()
+            return self.out
+        self.out = self.enqueue()
+        return self.out
+
+
+def gram_roofline(ctx, c, keys, ms_step):
+    """Roofline of the dominant kernel: the symmetric Gram GEMM (tcgen05), one launch over the K matrices of the
+    equal-sized groups, timed with the CUDA events the library records around that launch on its stream."""
+    from xkv_b200 import compress, factorize
+
+    size = c["group"]
+    groups = [k for k in keys if len(k) == size][:16]
+    nb = len(groups)
+    S, n = c["tokens"], size * c["heads"] * c["head_dim"]
+    xk = compress.pack_groups(groups)
+    fk = factorize.factorize_batch(xk, c["rank_k"], factorize.FactorizeOptions(profile=True))
+    stages = fk[0].timings
+    del fk, xk
+    gram_ms = stages["gram_gemm"]
+    alg_flops = nb * float(S) * n * n      # symmetric half of 2 m n^2 per matrix
+    achieved = alg_flops / (gram_ms * 1e-3) / 1e12
+    traffic = None
+    try:
+        per_matrix = json.load(open(os.path.join(ROOT, "profiles", "gram_traffic.json"))).get("dram_bytes_per_matrix")
+        if per_matrix is not None and S == 65536 and n == 4096:
+            traffic = per_matrix * nb
+    except Exception:
+        pass
+    ranks = c["rank_k"] + (c["rank_v"] or 0)
+    alg_pipeline = 4.0 * S * sum(g * c["heads"] * c["head_dim"] for g in group_sizes(c)) * ranks
+    return {
+        "kernel": "gemm_kernel<1,1> (Gram X^T X, symmetric tiles, tcgen05 M128 N256 K16)",
+        "bound": "tensor", "achieved": achieved, "peak": ctx.peak_tf, "unit": "TFLOP/s", "frac": achieved / ctx.peak_tf,
+        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if ctx.peaks else "fallback 1.4 PFLOP/s",
+        "traffic": traffic, "launch_ms": gram_ms, "matrices_per_launch": nb,
+        "algorithmic_flops_per_launch": alg_flops, "stages_ms_k_batch": stages,
+        "pipeline_algorithmic_frac": (alg_pipeline / (ms_step * 1e-3) / 1e12) / ctx.peak_tf,
+    }
+
+
+def hbm_roofline(ctx, c, ms_step):
+    """Whole-step roofline of a skinny-rank configuration (rank below the ridge => HBM-bound):
+    algorithmic bytes = two bf16 reads of every matrix + the factor writes."""
+    S = c["tokens"]
+    total = 0.0
+    for g in group_sizes(c):
+        n = g * c["heads"] * c["head_dim"]
+        for r in (c["rank_k"], c["rank_v"] if c["merge_value"] else None):
+            if r:
+                total += 2.0 * S * n * 2 + (S * r + r * n) * 2.0
+    achieved = total / (ms_step * 1e-3) / 1e9
+    return {"kernel": "whole compress step (Gram pass + projection pass over X)", "bound": "hbm", "achieved": achieved,
+            "peak": ctx.peak_hbm, "unit": "GB/s", "frac": achieved / ctx.peak_hbm, "traffic": None,
+            "algorithmic_bytes_per_step": total,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if ctx.peaks else "fallback 6550 GB/s"}
+
+
+def bench_decode(ctx, c, factors, no_graph):
+    """Fused reconstruct + RoPE + attention over the factors, all layers = one token (Llama-shaped configurations)."""
+    from xkv_b200 import ops, synthetic
+
+    torch = ctx.torch
+    dev = ctx.dev
+    S, H, D, L, G = c["tokens"], c["heads"], c["head_dim"], c["layers"], c["group"]
+    cos, sin = synthetic.llama3_rope(S, D, device=dev)
+    cos, sin = cos[0].contiguous(), sin[0].contiguous()
+    hq = 4 * H
+    gen = torch.Generator(device=dev).manual_seed(7)
+    q = torch.randn(L, hq, D, device=dev, generator=gen).bfloat16()
+    kt = torch.randn(L, H, 1, D, device=dev, generator=gen).bfloat16()
+    vt = torch.randn(L, H, 1, D, device=dev, generator=gen).bfloat16()
+    ws = torch.empty(ops.decode_workspace_bytes(hq, S, 1, c["rank_v"]) + 4096, dtype=torch.uint8, device=dev)
+    o = torch.empty(hq, D, dtype=torch.bfloat16, device=dev)
+    hd = H * D
+
+    def one_token():
+        for l in range(L):
+            gf = factors[l // G]
+            i = l % G
+            ops.decode_attention(q[l], gf.key.A, gf.key.V[i * hd:(i + 1) * hd], gf.value.A, gf.value.V[i * hd:(i + 1) * hd],
+                                 H, cos, sin, kt[l], vt[l], 1.0 / math.sqrt(D), out=o, workspace=ws)
+
+    for _ in range(3):
+        one_token()
+    ctx.barrier()
+    l0 = ops.launch_count()
+    one_token()
+    launches_per_token = ops.launch_count() - l0
+    token_graph = None
+    if not no_graph:
         torch.cuda.synchronize()
+        token_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(token_graph):
+            one_token()
+    ms_tok = ctx.time_steps(token_graph.replay if token_graph is not None else one_token, 8, warmup=1)
+    flops_k = 2.0 * S * c["rank_k"] * H * D * L
+    bytes_a = float(S) * (c["rank_k"] + c["rank_v"]) * 2 * L
+    rec = {
+        "metric": f"decode tok/s reconstructed (attention over the factored cache, {L} layers, batch 1, {S} context)",
+        "tok_s": ctx.world * 1e3 / ms_tok, "ms_per_token": ms_tok, "us_per_layer": 1e3 * ms_tok / L,
+        "equiv_dense_kv_GBps": ctx.world * L * 2.0 * S * H * D * 2 / (ms_tok * 1e-3) / 1e9,
+        "gpu_launches_per_token": launches_per_token,
+        "launch_mode": "cuda-graph replay" if token_graph is not None else "host enqueue",
+        "roofline": {"bound": "tensor", "achieved": flops_k / (ms_tok * 1e-3) / 1e12, "peak": ctx.peak_tf,
+                     "unit": "TFLOP/s", "frac": flops_k / (ms_tok * 1e-3) / 1e12 / ctx.peak_tf,
+                     "hbm_frac": bytes_a / (ms_tok * 1e-3) / 1e9 / ctx.peak_hbm,
+                     "note": "whole decode step (scores + softmax + P*A_v + combine) against the K^ reconstruction flops"},
+    }
+    del ws
+    if ctx.rank == 0:
+        # context, not a target: the library attention (torch SDPA, GQA) over an UNCOMPRESSED bf16 cache of one layer of the
+        # same shape -- what the reference's decode costs once its dense K^ / V^ exist (llama.py:58-69)
+        try:
+            import torch.nn.functional as F
 
-    for _ in range(max(args.warmup, 3)):
+            kd = torch.randn(1, H, S, D, device=dev, dtype=torch.bfloat16)
+            vd = torch.randn(1, H, S, D, device=dev, dtype=torch.bfloat16)
+            qd = torch.randn(1, hq, 1, D, device=dev, dtype=torch.bfloat16)
+            for _ in range(3):
+                F.scaled_dot_product_attention(qd, kd, vd, enable_gqa=True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(32):
+                F.scaled_dot_product_attention(qd, kd, vd, enable_gqa=True)
+            e1.record()
+            torch.cuda.synchronize()
+            rec["dense_sdpa_us_per_layer"] = 1e3 * e0.elapsed_time(e1) / 32
+            rec["dense_sdpa_note"] = ("torch SDPA over an uncompressed bf16 cache of the same shape (library kernel, "
+                                      "reported for context)")
+        except Exception as ex:
+            rec["dense_sdpa_note"] = f"not measured: {type(ex).__name__}"
+    return rec
+
+
+def bench_strong(ctx, c, streams, no_graph, ms_weak):
+    """ONE cache's layer groups split over the ranks (parallel.assign_groups: contiguous, balanced; 1 group per GPU at
+    N = 8 for config 2).  No data-path collective: a rank's groups are independent of everybody else's.  Every rank
+    regenerates only the groups it owns (seeded by GROUP, not by rank: the ranks hold disjoint parts of one cache)."""
+    from xkv_b200 import parallel, synthetic
+
+    sizes = group_sizes(c)
+    mine = parallel.assign_groups(len(sizes), ctx.world, ctx.rank)
+    per_rank = [len(parallel.assign_groups(len(sizes), ctx.world, r)) for r in range(ctx.world)]
+    if ctx.world == 1:
+        return {"scaling": "strong", "groups_per_rank": per_rank, "ms_per_step": ms_weak,
+                "value": kv_bytes_of(c) / (ms_weak * 1e-3) / 1e9, "unit": "GB/s", "note": "N = 1: the headline step itself"}
+    keys, vals = [], []
+    for g in mine:
+        keys.append(synthetic.make_group_kv(sizes[g], c["heads"], c["tokens"], c["head_dim"], c["alpha_k"], 1234 + g, device=ctx.dev))
+        vals.append(synthetic.make_group_kv(sizes[g], c["heads"], c["tokens"], c["head_dim"], c["alpha_v"], 5678 + g, device=ctx.dev)
+                    if c["merge_value"] else None)
+    step = CompressStep(ctx, c, keys, vals, streams, graph=not no_graph) if mine else (lambda: None)
+    ms = ctx.time_steps(step, max(3, min(ctx.args.steps, 10)), warmup=2)
+    return {"scaling": "strong", "groups_per_rank": per_rank, "ms_per_step": ms, "unit": "GB/s",
+            "value": kv_bytes_of(c) / (ms * 1e-3) / 1e9,
+            "ideal_ms": ms_weak / ctx.world, "efficiency_vs_one_gpu_step": (ms_weak / ctx.world) / ms,
+            "note": "one cache split by layer group, time = slowest rank, no data-path collective"}
+
+
+def bench_token_sharded(ctx):
+    """configs[3]: Llama-3.1-70B-shaped KV, xKV-8 at 128K.  One K and one V group matrix (131072 x 8192, rank 1024 /
+    1536; the cache has 10 such pairs) with the token rows split over the ranks (parallel.token_shard).  Every rank runs
+    the Gram of ITS rows, the packed upper triangles are summed with ONE NCCL all-reduce per matrix, every rank derives
+    the same right factor and projects its own rows."""
+    from xkv_b200 import factorize, parallel
+
+    torch, dist = ctx.torch, ctx.dist
+    c = CONFIGS[4]
+    S, n = c["tokens"], c["group"] * c["heads"] * c["head_dim"]
+    b, e = parallel.token_shard(S, ctx.world, ctx.rank)
+    rows = e - b
+
+    def shard(alpha, seed):
+        # X = T diag(s) W^T + noise with W shared by all ranks (same seed) and the rows of T i.i.d. (rank-local seed):
+        # the shards are rows of ONE matrix with a power-law spectrum
+        gw = torch.Generator(device=ctx.dev).manual_seed(seed)
+        w = torch.linalg.qr(torch.randn(n, 2048, generator=gw, device=ctx.dev))[0]
+        s = torch.arange(1, 2049, device=ctx.dev, dtype=torch.float32) ** (-alpha)
+        gt = torch.Generator(device=ctx.dev).manual_seed(seed * 1000 + ctx.rank)
+        out = torch.empty(rows, n, dtype=torch.bfloat16, device=ctx.dev)
+        for lo in range(0, rows, 16384):
+            hi = min(lo + 16384, rows)
+            t = torch.randn(hi - lo, 2048, generator=gt, device=ctx.dev) / S ** 0.5
+            x = (t * s) @ w.t()
+            x += 1e-3 * s[0] / S ** 0.5 * torch.randn(hi - lo, n, generator=gt, device=ctx.dev)
+            out[lo:hi] = x.to(torch.bfloat16)
+        return out
+
+    xk, xv = shard(c["alpha_k"], 41), shard(c["alpha_v"], 42)
+    group = dist.group.WORLD if ctx.world > 1 else None
+    opts = factorize.FactorizeOptions()
+    ws = torch.empty(max(factorize.workspace_bytes(1, rows, n, c["rank_k"], opts),
+                         factorize.workspace_bytes(1, rows, n, c["rank_v"], opts)), dtype=torch.uint8, device=ctx.dev)
+    comm = {"ms": 0.0, "bytes": 0}
+
+    def step(timed=False):
+        for x, r in ((xk, c["rank_k"]), (xv, c["rank_v"])):
+            ev = ([torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+                  if (timed and group is not None) else None)
+            factorize.factorize_batch([x], r, opts, workspace=ws, process_group=group, comm_events=ev)
+            if ev is not None:
+                torch.cuda.synchronize()
+                comm["ms"] += ev[0].elapsed_time(ev[1])
+                comm["bytes"] += ev[2]
+
+    ms = ctx.time_steps(step, 3, warmup=1)
+    step(timed=True)    # one more step with events around the collectives (synchronises, so outside the timed loop)
+    ar_ms = ctx.max_ms(comm["ms"])
+    kv = 2 * S * n * 2
+    rec = {
+        "workload": f"{c['model']}, ONE xKV-8 group (K and V matrices {S} x {n}, rank {c['rank_k']} / {c['rank_v']}) of the "
+                    f"10 the 80-layer cache has, token rows split over {ctx.world} rank(s)",
+        "scaling": "strong", "tokens_per_rank": rows, "ms_per_step": ms, "value": kv / (ms * 1e-3) / 1e9, "unit": "GB/s",
+        "collective": "NCCL all-reduce(sum, fp32) of the packed upper triangle of each n x n Gram" if group is not None else None,
+        "allreduce_bytes_per_step": comm["bytes"], "allreduce_full_gram_bytes": 2 * n * n * 4,
+        "allreduce_ms_per_step": ar_ms, "allreduce_share": (ar_ms / ms) if ms > 0 else None,
+        "allreduce_GBps": (comm["bytes"] / (ar_ms * 1e-3) / 1e9) if ar_ms > 0 else None,
+    }
+    del xk, xv, ws
+    torch.cuda.empty_cache()
+    return rec
+
+
+def bench_append(ctx, c, factors):
+    """North-star step 4: project T new token rows of a group onto its right factors (xkv_append_project), HBM-bound on
+    reading V (n x r bf16).  K and V factors of one group per call, as the cache does when it folds decode tokens."""
+    from xkv_b200 import ops
+
+    torch = ctx.torch
+    gf = factors[0]
+    n = gf.key.V.shape[0]
+    out = {}
+    lib_ws = torch.empty(1 << 24, dtype=torch.uint8, device=ctx.dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=ctx.dev)   # > L2: the factors are read from HBM
+    for T in (1, 8):
+        xk = torch.randn(T, n, device=ctx.dev).bfloat16()
+        xv = torch.randn(T, n, device=ctx.dev).bfloat16()
+        ok = torch.empty(T, gf.key.rank, dtype=torch.bfloat16, device=ctx.dev)
+        ov = torch.empty(T, gf.value.rank, dtype=torch.bfloat16, device=ctx.dev)
+
+        def run():
+            ops.append_project(xk, gf.key.V, out=ok, workspace=lib_ws)
+            ops.append_project(xv, gf.value.V, out=ov, workspace=lib_ws)
+
+        run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        total = 0.0
+        reps = 5
+        for _ in range(reps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            e0.record()
+            run()
+            e1.record()
+            torch.cuda.synchronize()
+            total += e0.elapsed_time(e1)
+        ms = total / reps
+        nbytes = n * (gf.key.rank + gf.value.rank) * 2
+        out[f"T{T}"] = {"us": 1e3 * ms, "V_bytes_read": nbytes, "GBps": nbytes / (ms * 1e-3) / 1e9,
+                        "hbm_frac": nbytes / (ms * 1e-3) / 1e9 / ctx.peak_hbm}
+    del flush, lib_ws
+    out["note"] = ("a_new (T x r) = x_new (T x n) V (n x r) for the K and the V factor of one group, L2 flushed between "
+                   "repetitions; bound: HBM read of V")
+    return out
+
+
+def bench_other_config(ctx, idx, streams):
+    """Compress step of another BASELINE.json configuration on this GPU (rank 0's device; N-independent)."""
+    c = CONFIGS[idx]
+    torch = ctx.torch
+    keys, vals = make_cache(c, ctx.dev, seed_base=1000 * idx)
+    step = CompressStep(ctx, c, keys, vals, streams, graph=True)
+    for _ in range(2):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    rec = {"workload": workload_config(ctx.args, c)["workload"], "ms_per_step": ms,
+           "value": kv_bytes_of(c) / (ms * 1e-3) / 1e9, "unit": "GB/s"}
+    ridge = ctx.peak_tf * 1e12 / (ctx.peak_hbm * 1e9)
+    if max(c["rank_k"], c["rank_v"] or 0) < ridge:      # two-pass flops per byte = rank: below the ridge the step is HBM-bound
+        rec["roofline"] = hbm_roofline(ctx, c, ms)
+    else:
+        ranks = c["rank_k"] + (c["rank_v"] or 0)
+        alg = 4.0 * c["tokens"] * sum(g * c["heads"] * c["head_dim"] for g in group_sizes(c)) * ranks
+        rec["roofline"] = {"bound": "tensor", "achieved": alg / (ms * 1e-3) / 1e12, "peak": ctx.peak_tf, "unit": "TFLOP/s",
+                           "frac": alg / (ms * 1e-3) / 1e12 / ctx.peak_tf,
+                           "note": "whole step against SURVEY 8d's two-pass algorithmic flops 4 m n r"}
+    del step, keys, vals
+    torch.cuda.empty_cache()
+    return rec
+
+
+def bench_gpu_reference(ctx, c):
+    """The reference's own library path ON THIS GPU (the bar is torch.linalg.svd / cuSOLVER + cuBLAS):
+    fake_svd's arithmetic (fp32 svd -> truncate -> multiply back) for one K and one V matrix of ONE group at the bounded
+    sample's context length, next to this library on the same matrices.  Context, not the contract's reference arm."""
+    from xkv_b200 import compress, synthetic
+
+    torch = ctx.torch
+    S = SAMPLE_TOKENS
+    g = min(c["group"], 4)
+    keys = synthetic.make_group_kv(g, c["heads"], S, c["head_dim"], c["alpha_k"], 77, device=ctx.dev)
+    vals = synthetic.make_group_kv(g, c["heads"], S, c["head_dim"], c["alpha_v"], 78, device=ctx.dev)
+    nbytes = 2 * g * c["heads"] * S * c["head_dim"] * 2
+
+    def ref():
+        for layers, r in ((keys, c["rank_k"]), (vals, c["rank_v"])):
+            x = torch.cat(layers, dim=1).transpose(1, 2).reshape(1, S, -1).float()
+            u, s, vh = torch.linalg.svd(x, full_matrices=False)
+            (u[:, :, :r] @ (torch.diag_embed(s[:, :r]) @ vh[:, :r, :])).to(torch.bfloat16)
+
+    def ours():
+        compress.compress_groups([keys], [vals], c["rank_k"], c["rank_v"])
+
+    out = {}
+    for name, fn, reps in (("torch_linalg_svd", ref, 2), ("xkv_b200", ours, 5)):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out[name] = {"ms": ms, "GBps": nbytes / (ms * 1e-3) / 1e9}
+    out["speedup"] = out["torch_linalg_svd"]["ms"] / out["xkv_b200"]["ms"]
+    out["sample"] = f"one {g}-layer group at {S} tokens (K rank {c['rank_k']} + V rank {c['rank_v']}), fp32 SVD on the same B200"
+    return out
+
+
+def run_xkv_arm(args):
+    ctx = Ctx(args)
+    torch = ctx.torch
+    from xkv_b200 import compress, ops
+
+    c = config_of(args)
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    warmup = max(args.warmup, 3)
+    kv_bytes = kv_bytes_of(c)
+
+    # ---- synthetic KV, resident in HBM (seeded per rank: the headline gives every rank a cache of its own) ----
+    keys, vals = make_cache(c, dev, seed_base=100 * rank)
+    step = CompressStep(ctx, c, keys, vals, args.streams, graph=not args.no_graph)
+    for _ in range(warmup):
         out = step()
-    barrier()
-    sampler = ClockSampler(local)
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local)
     if rank == 0:
         sampler.start()
-    launches0 = ops.launch_count()
-    launches_per_step = None
-    if graphed is not None:
-        # a replayed graph launches the captured kernels without passing through the library's counter
-        c0 = ops.launch_count()
-        compress.compress_groups(keys, vals, RANK_K, RANK_V, opts=opts)
-        launches_per_step = ops.launch_count() - c0
-        barrier()
-        launches0 = ops.launch_count()
+    # kernels per step: a replayed graph launches the captured kernels without passing through the library's counter
+    c0 = ops.launch_count()
+    step.enqueue()
+    launches_per_step = ops.launch_count() - c0
+    ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    ctx.barrier()
     torch.cuda.profiler.start()      # no-op unless run under `ncu --profile-from-start off` (launch list of the timed steps)
     e0.record()
     for _ in range(args.steps):
         out = step()
     e1.record()
-    barrier()
+    ctx.barrier()
     torch.cuda.profiler.stop()
-    ms_total = e0.elapsed_time(e1)
-    launches = ops.launch_count() - launches0
-    if launches_per_step is not None:
-        launches = launches_per_step * args.steps
+    ms_step = ctx.max_ms(e0.elapsed_time(e1)) / args.steps
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = t.item()
-    ms_step = ms_total / args.steps
     value = world * kv_bytes / (ms_step * 1e-3) / 1e9
 
-    # ---- roofline of the dominant kernel: the symmetric Gram GEMM (tcgen05), timed with CUDA events ----
-    popts = factorize.FactorizeOptions(profile=True)
-    xk = compress.pack_groups(keys)
-    fk = factorize.factorize_batch(xk, RANK_K, popts)
-    stages_k = fk[0].timings
-    del fk
-    n = GROUP * HEADS * HEAD_DIM
-    gram_ms = stages_k["gram_gemm"]                 # one launch, ng matrices
-    alg_flops = ng * float(S) * n * n               # symmetric half of 2*m*n^2 per matrix
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    achieved = alg_flops / (gram_ms * 1e-3) / 1e12
-    traffic = None
-    try:
-        per_matrix = json.load(open(os.path.join(ROOT, "profiles", "gram_traffic.json"))).get("dram_bytes_per_matrix")
-        if per_matrix is not None and S == 65536:
-            traffic = per_matrix * ng      # one launch covers the ng matrices of the batch
-    except Exception:
-        pass
-    roofline = {
-        "kernel": "gemm_kernel<1,1> (Gram X^T X, symmetric tiles, tcgen05 M128 N256 K16)",
-        "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-        "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s",
-        "traffic": traffic, "launch_ms": gram_ms, "algorithmic_flops_per_launch": alg_flops,
-        "stages_ms_k_batch": stages_k,
-        "pipeline_algorithmic_frac": (4.0 * S * n * (RANK_K + RANK_V) * ng / (ms_step * 1e-3) / 1e12) / peak_tf,
-    }
-    del xk
-
+    ridge = ctx.peak_tf * 1e12 / (ctx.peak_hbm * 1e9)
+    # SURVEY 8d: the two-pass minimum does 4 m n r flops over 4 m n bytes, i.e. r flop/B: HBM-bound below the ridge
+    skinny = max(c["rank_k"], c["rank_v"] or 0) < ridge
+    roofline = hbm_roofline(ctx, c, ms_step) if skinny else gram_roofline(ctx, c, keys, ms_step)
     line = {
-        "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
-        "gpu_launches": launches, "roofline": roofline,
-        "launch_mode": "cuda-graph replay" if graphed is not None else "host enqueue",
+        "metric": METRIC.format(title=c["title"]), "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, c),
+        "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
+        "launch_mode": "cuda-graph replay" if step.graph is not None else "host enqueue",
     }
 
-    # ---- decode: fused reconstruct + RoPE + attention over the factors, all 32 layers = one token ----
-    if not args.no_decode:
-        import math
-
-        cos, sin = synthetic.llama3_rope(S, HEAD_DIM, device=dev)
-        cos, sin = cos[0].contiguous(), sin[0].contiguous()
-        hq = 32
-        gen = torch.Generator(device=dev).manual_seed(7)
-        q = torch.randn(LAYERS, hq, HEAD_DIM, device=dev, generator=gen).bfloat16()
-        kt = torch.randn(LAYERS, HEADS, 1, HEAD_DIM, device=dev, generator=gen).bfloat16()
-        vt = torch.randn(LAYERS, HEADS, 1, HEAD_DIM, device=dev, generator=gen).bfloat16()
-        ws = torch.empty(ops.decode_workspace_bytes(hq, S, 1, RANK_V) + 4096, dtype=torch.uint8, device=dev)
-        o = torch.empty(hq, HEAD_DIM, dtype=torch.bfloat16, device=dev)
-        hd = HEADS * HEAD_DIM
-
-        def one_token():
-            for l in range(LAYERS):
-                gf = out[l // GROUP]
-                i = l % GROUP
-                ops.decode_attention(q[l], gf.key.A, gf.key.V[i * hd:(i + 1) * hd], gf.value.A,
-                                     gf.value.V[i * hd:(i + 1) * hd], HEADS, cos, sin, kt[l], vt[l],
-                                     1.0 / math.sqrt(HEAD_DIM), out=o, workspace=ws)
-
-        for _ in range(3):
-            one_token()
-        barrier()
-        l0 = ops.launch_count()
-        one_token()
-        launches_per_token = ops.launch_count() - l0
-        # one decode token = 32 layers x 5 kernels: replayed as a CUDA graph (static q / factors / workspace), like the
-        # compress step, unless --no-graph
-        token_graph = None
-        if not args.no_graph:
-            torch.cuda.synchronize()
-            token_graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(token_graph):
-                one_token()
-            token_graph.replay()
-        barrier()
-        ntok = 8
-        e0.record()
-        for _ in range(ntok):
-            if token_graph is not None:
-                token_graph.replay()
-            else:
-                one_token()
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_tok = t.item() / ntok
-        flops_k = 2.0 * S * RANK_K * HEADS * HEAD_DIM * LAYERS          # K^ reconstruction, the tensor-bound part
-        bytes_a = float(S) * (RANK_K + RANK_V) * 2 * LAYERS             # token factors streamed once per layer
-        peak_hbm = float(peaks.get("hbm_gbs", 6550.0))
-        line["decode"] = {
-            "metric": "decode tok/s reconstructed (attention over the factored cache, 32 layers, batch 1, 64K context)",
-            "tok_s": world * 1e3 / ms_tok, "ms_per_token": ms_tok, "us_per_layer": 1e3 * ms_tok / LAYERS,
-            "equiv_dense_kv_GBps": world * LAYERS * 2.0 * S * HEADS * HEAD_DIM * 2 / (ms_tok * 1e-3) / 1e9,
-            "gpu_launches_per_token": launches_per_token,
-            "launch_mode": "cuda-graph replay" if token_graph is not None else "host enqueue",
-            "roofline": {"bound": "tensor", "achieved": flops_k / (ms_tok * 1e-3) / 1e12, "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": flops_k / (ms_tok * 1e-3) / 1e12 / peak_tf,
-                         "hbm_frac": bytes_a / (ms_tok * 1e-3) / 1e9 / peak_hbm,
-                         "note": "whole decode step (scores + softmax + P*A_v + combine) against the K^ reconstruction flops"},
-        }
-        del ws
-        # context, not a target: the library attention (torch SDPA, GQA) over an UNCOMPRESSED bf16 cache of one layer of
-        # the same shape -- what the reference's decode costs once its dense K^ / V^ exist (llama.py:58-69).  It reads
-        # 268 MB per layer against the factored cache's 168 MB per layer (and 5.7x less resident memory).
-        if rank == 0:
-            try:
-                import torch.nn.functional as F
-
-                kd = torch.randn(1, HEADS, S, HEAD_DIM, device=dev, dtype=torch.bfloat16)
-                vd = torch.randn(1, HEADS, S, HEAD_DIM, device=dev, dtype=torch.bfloat16)
-                qd = torch.randn(1, hq, 1, HEAD_DIM, device=dev, dtype=torch.bfloat16)
-                for _ in range(3):
-                    F.scaled_dot_product_attention(qd, kd, vd, enable_gqa=True)
-                torch.cuda.synchronize()
-                e0.record()
-                for _ in range(32):
-                    F.scaled_dot_product_attention(qd, kd, vd, enable_gqa=True)
-                e1.record()
-                torch.cuda.synchronize()
-                line["decode"]["dense_sdpa_us_per_layer"] = 1e3 * e0.elapsed_time(e1) / 32
-                line["decode"]["dense_sdpa_note"] = ("torch SDPA over an uncompressed bf16 cache of the same shape "
-                                                     "(library kernel, reported for context)")
-                del kd, vd, qd
-            except Exception as ex:   # an older torch without enable_gqa: the context number is optional
-                line["decode"]["dense_sdpa_note"] = f"not measured: {type(ex).__name__}"
+    if not args.no_decode and c["merge_value"] and c["head_dim"] in (64, 128):
+        line["decode"] = bench_decode(ctx, c, out, args.no_graph)
+    if not args.no_extras and args.config == 2:
+        line["append"] = bench_append(ctx, c, out)
 
     # ---- end to end through the public API with HOST buffers ----
-    if not args.no_e2e:
-        # the synthetic cache is moved to pinned host memory and the device copies are dropped: every e2e step
-        # starts from HOST buffers and ends with the factors back in HOST buffers
+    uniform = len(set(group_sizes(c))) == 1 and c["merge_value"]
+    if not args.no_e2e and uniform:
+        # the synthetic cache is moved to pinned host memory and the device copies are dropped: every e2e step starts from
+        # HOST buffers and ends with the factors back in HOST buffers; device staging is allocated once, outside the loop
         h_keys = [[t.transpose(1, 2).contiguous().cpu().pin_memory() for t in grp] for grp in keys]
         h_vals = [[t.transpose(1, 2).contiguous().cpu().pin_memory() for t in grp] for grp in vals]
-        r_k, r_v, n_cols = RANK_K, RANK_V, GROUP * HEADS * HEAD_DIM
         h_out = []
-        for _ in range(ng):
-            for r in (r_k, r_v):
-                h_out.append(torch.empty(S, r, dtype=torch.bfloat16).pin_memory())
+        for g in group_sizes(c):
+            n_cols = g * c["heads"] * c["head_dim"]
+            for r in (c["rank_k"], c["rank_v"]):
+                h_out.append(torch.empty(c["tokens"], r, dtype=torch.bfloat16).pin_memory())
                 h_out.append(torch.empty(r, n_cols, dtype=torch.bfloat16).pin_memory())
         d2h_bytes = sum(t.numel() * t.element_size() for t in h_out)
-        if graphed is not None:
-            del graphed, out
-            graphed = None
-        del keys, vals
+        del step, out, keys, vals
         torch.cuda.empty_cache()
+        staging = compress.host_staging(h_keys, h_vals, dev)
 
         def e2e_step():
-            compress.compress_groups_from_host(h_keys, h_vals, RANK_K, RANK_V, dev, chunk_groups=args.e2e_chunk,
-                                               opts=opts, host_out=h_out)
-            return d2h_bytes
+            compress.compress_groups_from_host(h_keys, h_vals, c["rank_k"], c["rank_v"], dev, chunk_groups=args.e2e_chunk,
+                                               host_out=h_out, staging=staging)
 
-        d2h = e2e_step()
-        barrier()
         n_e2e = min(args.steps, 3)
-        e0.record()
-        for _ in range(n_e2e):
-            d2h = e2e_step()
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = t.item() / n_e2e
+        ms_e2e = ctx.time_steps(e2e_step, n_e2e, warmup=1)
         line["e2e"] = {"value": world * kv_bytes / (ms_e2e * 1e-3) / 1e9, "unit": "GB/s",
-                       "h2d_bytes_per_step": kv_bytes, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+                       "h2d_bytes_per_step": kv_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e,
                        "steps": n_e2e}
-        del h_keys, h_vals, h_out
+        del staging, h_keys, h_vals, h_out
+        torch.cuda.empty_cache()
+    else:
+        del step, out, keys, vals
+        torch.cuda.empty_cache()
+
+    if not args.no_extras and args.config == 2:
+        line["strong"] = bench_strong(ctx, c, args.streams, args.no_graph, ms_step)
+        torch.cuda.empty_cache()
+        line["token_sharded"] = bench_token_sharded(ctx)
+        if rank == 0:
+            line["other_configs"] = {"3": bench_other_config(ctx, 3, args.streams), "5": bench_other_config(ctx, 5, args.streams)}
+            if world == 1:
+                line["gpu_reference"] = bench_gpu_reference(ctx, c)
+        ctx.barrier()
 
     if rank == 0:
         line["clocks"] = clocks
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
-            dt, nbytes = cpu_reference_step(args.cpu_sample_tokens)
+            dt, nbytes = cpu_reference_step(c, args.cpu_sample_tokens)
             line["cpu_baseline"] = {
                 "value": nbytes / dt / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
-                "sample": f"one 4-layer group at {args.cpu_sample_tokens} tokens (K rank {RANK_K} + V rank {RANK_V}) "
-                          f"through the oracle port of grouped_layer_merging, {dt:.1f} s"}
+                "sample": reference_sample_text(c, args.cpu_sample_tokens) + f", {dt:.1f} s"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
 
 
 def main():

@@ -38,6 +38,7 @@ extern "C" {
 #define XKV_MAX_GROUP_LAYERS 16
 #define XKV_MAX_GEMM_PROBLEMS 16
 #define XKV_MAX_BATCH 16
+#define XKV_MAX_LAYER_MAPS 64
 
 /* ---- library ------------------------------------------------------------------------ */
 XKV_API const char* xkv_last_error(void);
@@ -80,8 +81,19 @@ typedef struct xkv_gemm_problem {
   int32_t accum_phases;    /* > 1: the k range of a CTA is accumulated in this many sequential pieces that are summed in
                             * fp32 outside the tensor core (long reductions: the Gram over 64K tokens); fp32 output only */
   const int32_t* run_if;   /* optional DEVICE flag (NULL = always): the problem is skipped when *run_if == 0 at run time */
+  /* Layered operands (the group's K / V read IN PLACE, no gather): with a_layers > 0 operand A is the column-wise
+   * concatenation [A_layer[0] | A_layer[1] | ...] of a_layers equally shaped row-major bf16 matrices, each
+   * layer_cols wide (a multiple of 64) with leading dimension lda -- exactly torch.cat(dim=1) + transpose(1,2).reshape of
+   * the reference (cache:170-171, :13-14) when every layer tensor is a (1, H, S, D) view of token-major memory.  A[] is
+   * ignored then and num_terms must be 1.  Likewise b_layers / B_layer.  One launch holds at most
+   * XKV_MAX_LAYER_MAPS layer matrices in total. */
+  int32_t a_layers, b_layers, layer_cols;
+  const void* A_layer[XKV_MAX_GROUP_LAYERS];
+  const void* B_layer[XKV_MAX_GROUP_LAYERS];
 } xkv_gemm_problem;
 XKV_API int xkv_gemm_grouped(const xkv_gemm_problem* problems_host, int num_problems, void* stream);
+/* sizeof(xkv_gemm_problem) of this build (bindings check their mirror of the struct against it) */
+XKV_API size_t xkv_gemm_problem_size(void);
 
 /* ---- small fp32 helpers of the factorisation ------------------------------------------ */
 /* out[i][j] = sum_s slabs[s][i][j]; with symmetrize=1 the strictly-lower triangle is mirrored
@@ -104,6 +116,13 @@ XKV_API int xkv_split_bf16_batched(const float* const* x_host, void* const* hi_h
 XKV_API int xkv_symmetrize_split_bf16(const float* const* slabs_host, int batch, int num_slabs, int64_t slab_stride,
                                       int n, int64_t ld, void* const* hi_host, void* const* mid_host,
                                       void* const* lo_host, int64_t ld_out, void* stream);
+/* Token-sharded factorisation: the only data-path collective is the all-reduce of each matrix's
+ * n x n fp32 Gram.  The Gram is symmetric, so only its upper triangle travels: row r contributes its columns
+ * [32 * (r / 32), n), packed back to back: xkv_gram_packed_elems(n) = n^2 / 2 + 16 n floats.  pack: full (n x n,
+ * symmetric or with a valid upper triangle) -> packed; unpack: packed -> full symmetric matrix (lower = mirrored upper). */
+XKV_API size_t xkv_gram_packed_elems(int n);
+XKV_API int xkv_gram_pack_upper(const float* full, int n, int64_t ld, float* packed, void* stream);
+XKV_API int xkv_gram_unpack_upper(const float* packed, int n, float* full, int64_t ld, void* stream);
 /* deterministic N(0,1) test matrix rounded to bf16 (counter-based generator) */
 XKV_API int xkv_fill_gaussian_bf16(void* out, int rows, int cols, int64_t ld, uint64_t seed, void* stream);
 /* Batched row normalisation: every row of Y[b] (rows x cols fp32, each row is a column of the sketch)
@@ -206,6 +225,15 @@ XKV_API void xkv_factorize_default_options(xkv_factorize_options* opts);
 XKV_API size_t xkv_factorize_options_size(void);
 XKV_API size_t xkv_factorize_workspace_bytes(int batch, int m, int n, int rank, const xkv_factorize_options* opts);
 XKV_API int xkv_factorize_sigma_count(int rank, const xkv_factorize_options* opts);
+/* Same on a layer group's K (or V) tensors IN PLACE: matrix b is the column-wise concatenation of `layers` row-major
+ * bf16 matrices layer_ptrs_host[b * layers + i] (m x layer_cols, row stride ld_layer) -- the reference's
+ * torch.cat(dim=1) + transpose(1,2).reshape (cache:170-171, :13-14) when every layer tensor is a (1, H, S, D) view of
+ * token-major memory (layer_cols = H * D).  The Gram pass and the projection pass read the layer tensors through
+ * per-layer tensor maps: no gather kernel, no packed copy (1 GiB per group at config 2).  n = layers * layer_cols. */
+XKV_API int xkv_factorize_groups(const void* const* layer_ptrs_host, int batch, int layers, int layer_cols, int m,
+                                 int64_t ld_layer, int rank, const xkv_factorize_options* opts, void* const* A_host,
+                                 void* const* Vt_host, void* const* V_host, float* const* sigma_host, void* workspace,
+                                 size_t workspace_bytes, void* const* stage_events_host, void* stream);
 XKV_API int xkv_factorize_batch(const void* const* X_host, int batch, int m, int n, int64_t ldx, int rank,
                                 const xkv_factorize_options* opts, void* const* A_host, void* const* Vt_host,
                                 void* const* V_host, float* const* sigma_host, float* const* gram_host,
@@ -249,6 +277,21 @@ XKV_API void xkv_decode_set_variant(int variant);
 /* tuning hook: cluster size of the score-MMA kernel, i.e. how many adjacent kv heads share one multicast copy of each
  * A_k tile: 0 automatic, else 1, 2, 4 or 8 (reduced to a divisor of the kv-head count the device can keep resident) */
 XKV_API void xkv_decode_set_cluster(int cluster);
+/* Absorbed attention over a token factor: replaces, for the MLA latent slot (deepseek_v2.py:217-235: reconstructed
+ * latents -> kv_a_layernorm -> kv_b_proj over the WHOLE cache -> attention, every decode step), the part that touches
+ * the cache.  The latent of token t is c_t = V_l a_t and both attention products are linear in it, so with the query
+ * folded into the rank space by the caller, q_hat[h] = V_l^T (gamma o W_UK[h]^T q_nope[h]) (Hq x r bf16):
+ *     s[h][t]  = scale * ( row_scale[t] * (q_hat[h] . A[t]) + bias_q[h] . bias_k[t] )
+ *     u_out[h] = sum_t softmax_t(s)[h][t] * row_scale[t] * A[t]         (Hq x r fp32, rank space)
+ *     lse_out[h] = log sum_t exp(s[h][t])                               (for merging with the dense decode tail)
+ * row_scale (S fp32, may be NULL = 1): 1 / rms of the reconstructed latent (kv_a_layernorm's per-token factor);
+ * bias_q (Hq x bias_dim) / bias_k (S x bias_dim, row stride ld_bias_k) bf16, may both be NULL: the RoPE part
+ * q_pe . k_pe.  A (S x r bf16, row stride lda) is read twice; the S x kv_lora_rank latents are never rebuilt. */
+XKV_API size_t xkv_decode_absorbed_workspace_bytes(int Hq, int S, int r);
+XKV_API int xkv_decode_absorbed(const void* q_hat, int Hq, const void* A, int64_t lda, int r, int S,
+                                const float* row_scale, const void* bias_q, const void* bias_k, int64_t ld_bias_k,
+                                int bias_dim, float scale, float* u_out, float* lse_out, void* workspace,
+                                size_t workspace_bytes, void* stream);
 /* RoPE on materialised keys x (rows, H, D) bf16 in place, in the reference's bf16 arithmetic
  * (apply_rotary_pos_emb as called at cache:148,152): x*cos + rotate_half(x)*sin, cos/sin (rows, D). */
 XKV_API int xkv_rope_bf16(void* x, int64_t ld_row, int rows, int H, int D, const void* cos, const void* sin,

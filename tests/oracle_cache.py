@@ -25,6 +25,9 @@ class OracleCache(FakeLayerMergingCache):
     def attend(self, *args, **kwargs):
         return None
 
+    def latent_slot(self, *args, **kwargs):
+        return None
+
     def update(self, key, value, layer_idx, mode="prefill", cos=None, sin=None, re_apply_rope=True,
                return_dense=True):
         layer = self._layer(layer_idx)

@@ -206,3 +206,37 @@ def test_rope_bf16_matches_hf_formula():
     got = ops.rope_bf16_(x.cuda().clone(), cos[0].cuda(), sin[0].cuda())
     torch.cuda.synchronize()
     assert torch.equal(got.cpu(), ref)
+
+
+@pytest.mark.parametrize("S,Hq,r,dr,sharp", [(600, 16, 256, 64, False), (5000, 16, 512, 64, True), (32768, 16, 512, 64, False),
+                                              (70, 4, 64, 0, False), (4097, 128, 128, 8, True)])
+def test_absorbed_attention_matches_dense_formula(S, Hq, r, dr, sharp):
+    """xkv_decode_absorbed (the MLA latent path): s = scale (row_scale (q_hat . a_t) + bias_q . bias_k[t]),
+    u = sum_t softmax(s) row_scale[t] a_t, lse — against the same formulas in fp64 on the device."""
+    from xkv_b200 import ops
+
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(S + r)
+    a = (torch.randn(S, r, generator=g, device=dev) * 0.5).bfloat16()
+    q_hat = (torch.randn(Hq, r, generator=g, device=dev) * (4.0 if sharp else 0.5)).bfloat16()
+    row_scale = (0.5 + torch.rand(S, generator=g, device=dev)).float()
+    bias_q = torch.randn(Hq, dr, generator=g, device=dev).bfloat16() if dr else None
+    bias_k = torch.randn(S, dr, generator=g, device=dev).bfloat16() if dr else None
+    scale = 0.07
+    u, lse = ops.decode_absorbed(q_hat, a, scale, row_scale=row_scale, bias_q=bias_q, bias_k=bias_k)
+    torch.cuda.synchronize()
+    s = (q_hat.double() @ a.double().t()) * row_scale.double()[None]
+    if dr:
+        s = s + bias_q.double() @ bias_k.double().t()
+    s = s * scale
+    p = torch.softmax(s, dim=-1)
+    u_ref = (p * row_scale.double()[None]) @ a.double()
+    lse_ref = torch.logsumexp(s, dim=-1)
+    err = (u.double() - u_ref).abs().max().item()
+    sc = u_ref.abs().max().item()
+    lse_err = (lse.double() - lse_ref).abs().max().item()
+    print(f"absorbed S={S} Hq={Hq} r={r}: max|du| = {err:.2e} (scale {sc:.3f}), max|dlse| = {lse_err:.2e}, "
+          f"largest weight {p.max().item():.3f}")
+    assert torch.isfinite(u).all() and torch.isfinite(lse).all()
+    assert err <= 1e-2 * max(sc, 1e-3)       # probabilities are rounded to bf16 for the tensor-core product
+    assert lse_err <= 2e-3

@@ -158,13 +158,28 @@ def test_patched_deepseek_v2_mla_matches_oracle_cache():
                                           merge_value=False)
     KVCompress(xKV_config=cfg)(model)
     ids = torch.randint(0, 512, (1, 600), device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
-    lg_ours, _ = _decode_logits(model, FakeLayerMergingCache(cfg), ids, steps=4)
-    lg_ref, _ = _decode_logits(model, OracleCache(cfg), ids, steps=4)
+    from xkv_b200 import ops
+
+    calls = []
+    orig = ops.decode_absorbed
+    ops.decode_absorbed = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    try:
+        lg_ours, _ = _decode_logits(model, FakeLayerMergingCache(cfg), ids, steps=6)
+    finally:
+        ops.decode_absorbed = orig
+    assert len(calls) == 3 * 6        # every layer of every decode step ran in the factors' rank space (no latent rebuild)
+    for layer in model.model.layers:
+        layer.self_attn.xkv_fused_decode = False
+    lg_dense, _ = _decode_logits(model, FakeLayerMergingCache(cfg), ids, steps=6)   # materialise + kv_b_proj over the cache
+    lg_ref, _ = _decode_logits(model, OracleCache(cfg), ids, steps=6)
+    for layer in model.model.layers:
+        layer.self_attn.xkv_fused_decode = True
     torch.cuda.synchronize()
     dev = (lg_ours - lg_ref).abs().max().item()
+    dev_dense = (lg_dense - lg_ref).abs().max().item()
     scale = lg_ref.abs().max().item()
-    print(f"MLA logits: max |ours - oracle| = {dev:.4f} (logit scale {scale:.3f})")
-    assert dev <= 5e-2 * scale
+    print(f"MLA logits: max |absorbed - oracle| = {dev:.4f}, max |materialised - oracle| = {dev_dense:.4f} (logit scale {scale:.3f})")
+    assert dev <= 5e-2 * scale and dev_dense <= 5e-2 * scale
     bad = generate_consecutive_xKV_config(num_layers=3, end_layer=-1, group_size=3, rank_k=256, rank_v=64)
     with pytest.raises(ValueError, match="merge_v"):
         model(input_ids=ids[:, :300], past_key_values=FakeLayerMergingCache(bad), use_cache=True)
@@ -181,8 +196,9 @@ def _windowed_model(family: str, window: int):
     else:
         from transformers import Qwen2Config, Qwen2ForCausalLM
 
+        # head_dim = 512 / 8 = 64 (the fused kernel handles 64 and 128)
         cfg = Qwen2Config(hidden_size=512, intermediate_size=512, num_hidden_layers=4, num_attention_heads=8,
-                          num_key_value_heads=2, vocab_size=512,   # head_dim = 512 / 8 = 64 max_position_embeddings=4096, sliding_window=window,
+                          num_key_value_heads=2, vocab_size=512, max_position_embeddings=4096, sliding_window=window,
                           use_sliding_window=True, max_window_layers=2)   # layers 2, 3 slide, layers 0, 1 attend fully
         cls = Qwen2ForCausalLM
     cfg._attn_implementation = "sdpa"

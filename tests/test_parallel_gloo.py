@@ -32,6 +32,41 @@ def test_token_shards_cover_the_sequence():
         assert all(b % 128 == 0 or b == tokens for b, _ in spans)
 
 
+def _packed_offsets(n):
+    """Row offsets of the packed upper triangle (row r keeps columns [32 * (r // 32), n)): the layout of
+    xkv_gram_pack_upper, restated in numpy-style Python."""
+    off, offs = 0, []
+    for r in range(n):
+        offs.append(off)
+        off += n - (r // 32) * 32
+    return offs, off
+
+
+def _pack_upper(g):
+    n = g.shape[0]
+    return torch.cat([g[r, (r // 32) * 32:] for r in range(n)])
+
+
+def _unpack_upper(packed, n):
+    offs, _ = _packed_offsets(n)
+    full = torch.zeros(n, n, dtype=packed.dtype)
+    for r in range(n):
+        c0 = (r // 32) * 32
+        full[r, c0:] = packed[offs[r]: offs[r] + n - c0]
+    upper = torch.triu(full)
+    return upper + torch.triu(full, 1).t()
+
+
+def test_packed_upper_triangle_size_matches_the_library():
+    """xkv_gram_packed_elems is host code: callable without a GPU."""
+    from xkv_b200 import _lib
+
+    lib = _lib.load()
+    for n in (32, 64, 100, 1024, 4096, 8192):
+        assert int(lib.xkv_gram_packed_elems(n)) == _packed_offsets(n)[1]
+    assert int(lib.xkv_gram_packed_elems(8192)) * 4 < 0.51 * 8192 * 8192 * 4      # half the all-reduce payload
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -47,8 +82,11 @@ def _worker(rank, world, port, ret):
         x = torch.randn(512, 64).bfloat16().float()        # the full matrix, identical on every rank
         b, e = parallel.token_shard(512, world, rank)
         g_local = x[b:e].t() @ x[b:e]                        # stand-in for the Gram kernel on the local rows
-        parallel.allreduce_gram([g_local])
-        ok_gram = torch.allclose(g_local, x.t() @ x, rtol=1e-5, atol=1e-4)
+        # as factorize_batch(process_group=...) does: only the packed upper triangle is reduced, then mirrored back
+        packed = _pack_upper(g_local)
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+        g_local = _unpack_upper(packed, 64)
+        ok_gram = torch.allclose(g_local, x.t() @ x, rtol=1e-5, atol=1e-4) and torch.equal(g_local, g_local.t())
         # every rank derives the same right factor from the reduced Gram and projects its own rows
         evals, evecs = torch.linalg.eigh(g_local.double())
         v = evecs[:, -16:].float()

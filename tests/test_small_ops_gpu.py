@@ -304,3 +304,26 @@ def test_slerp_merge_matches_reference_function():
     _, mask, _, _ = O.slerp_merge_rows_batch(x1.float(), x2.float(), t=0.6, gamma=0.05)
     keep = ~mask.squeeze(-1)
     assert keep.any() and torch.equal(e1[keep], x1[keep]) and torch.equal(e2[keep], x2[keep])
+
+
+@pytest.mark.parametrize("n", [64, 200, 1024, 4096])
+def test_gram_pack_unpack_upper(n):
+    """Payload of the token-sharded Gram all-reduce: pack keeps row r's columns from 32 * (r // 32); unpack mirrors the
+    upper triangle. Bit-exact against indexing."""
+    from xkv_b200 import ops
+
+    g = torch.randn(n, n, device="cuda")
+    g = g + g.t()
+    packed = ops.gram_pack_upper(g)
+    assert packed.numel() == ops.gram_packed_elems(n)
+    ref = torch.cat([g[r, (r // 32) * 32:] for r in range(0, n, max(1, n // 64))])   # spot rows
+    offs = [0]
+    for r in range(n):
+        offs.append(offs[-1] + n - (r // 32) * 32)
+    got = torch.cat([packed[offs[r]: offs[r + 1]] for r in range(0, n, max(1, n // 64))])
+    assert torch.equal(got, ref)
+    noisy = g + torch.tril(torch.randn(n, n, device="cuda"), -1)     # garbage below the diagonal must not survive
+    full = torch.empty(n, n, device="cuda")
+    ops.gram_unpack_upper(ops.gram_pack_upper(noisy), full)
+    torch.cuda.synchronize()
+    assert torch.equal(full, g)

@@ -47,6 +47,11 @@ class GemmProblem(C.Structure):
         ("split_stride", C.c_int64),
         ("accum_phases", C.c_int32),
         ("run_if", C.c_void_p),
+        ("a_layers", C.c_int32),
+        ("b_layers", C.c_int32),
+        ("layer_cols", C.c_int32),
+        ("A_layer", C.c_void_p * MAX_GROUP_LAYERS),
+        ("B_layer", C.c_void_p * MAX_GROUP_LAYERS),
     ]
 
 
@@ -95,6 +100,9 @@ SIGNATURES = {
     "xkv_symmetrize_split_bf16": (_i, [_pp, _i, _i, _i64, _i, _i64, _pp, _pp, _pp, _i64, _vp]),
     "xkv_split_bf16_batched": (_i, [_pp, _pp, _pp, _pp, _i, _i, _i, _i64, _i64, _vp]),
     "xkv_split_bf16": (_i, [_vp, _i, _i, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "xkv_gram_packed_elems": (_sz, [_i]),
+    "xkv_gram_pack_upper": (_i, [_vp, _i, _i64, _vp, _vp]),
+    "xkv_gram_unpack_upper": (_i, [_vp, _i, _vp, _i64, _vp]),
     "xkv_fill_gaussian_bf16": (_i, [_vp, _i, _i, _i64, C.c_uint64, _vp]),
     "xkv_normalize_rows": (_i, [_pp, _pp, _pp, _pp, _i, _i, _i, _i64, _i64, _vp]),
     "xkv_shift_normalize_rows": (_i, [_pp, _pp, _vp, _pp, _i, _pp, _pp, _pp, _i, _i, _i, _i64, _i64, _vp]),
@@ -116,6 +124,8 @@ SIGNATURES = {
                                   _vp, _vp, _i, _i64, _i64, _f, _vp, _vp, _sz, _vp]),
     "xkv_decode_attention_lse": (_i, [_vp, _i, _i, _i, _vp, _i64, _i, _vp, _i64, _vp, _i64, _i, _vp, _i64, _i, _vp, _vp,
                                       _i64, _vp, _vp, _i, _i64, _i64, _f, _vp, _vp, _sz, _vp, _vp]),
+    "xkv_decode_absorbed_workspace_bytes": (_sz, [_i, _i, _i]),
+    "xkv_decode_absorbed": (_i, [_vp, _i, _vp, _i64, _i, _i, _vp, _vp, _vp, _i64, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "xkv_decode_force_tiled": (None, [_i]),
     "xkv_decode_set_variant": (None, [_i]),
     "xkv_decode_set_cluster": (None, [_i]),
@@ -124,6 +134,9 @@ SIGNATURES = {
     "xkv_append_project": (_i, [_vp, _i64, _i, _vp, _i64, _i, _i, _vp, _i64, _vp, _sz, _vp]),
     "xkv_slerp_workspace_bytes": (_sz, [_i64]),
     "xkv_slerp_merge": (_i, [_vp, _vp, _i64, _i, _i64, _f, _f, _vp, _vp, _i64, _vp, _sz, _vp]),
+    "xkv_gemm_problem_size": (C.c_size_t, []),
+    "xkv_factorize_groups": (_i, [_pp, _i, _i, _i, _i, _i64, _i, C.POINTER(FactorizeOptions), _pp, _pp, _pp, _pp, _vp, _sz,
+                                  _pp, _vp]),
     "xkv_factorize_batch": (_i, [_pp, _i, _i, _i, _i64, _i, C.POINTER(FactorizeOptions), _pp, _pp, _pp, _pp, _pp, _i,
                                  _vp, _sz, _pp, _vp]),
 }

@@ -10,8 +10,20 @@ Semantics kept from the reference:
 * every step the (reconstructed) latents go through ``kv_a_layernorm`` + ``kv_b_proj`` (:235).
 What differs: written against transformers' native ``DeepseekV2Attention`` (the reference patches the Hub's
 remote-code ``DeepseekV2FlashAttention2``, which is not vendored), attention through the installed sdpa
-interface instead of flash-attn 2, and the latents come back from the factors through the tcgen05 GEMM
-(``FakeLayerMergingCache.materialize``) instead of being stored dense.
+interface instead of flash-attn 2.  Prefill gets the reconstructed latents from the factors through the tcgen05 GEMM
+(``FakeLayerMergingCache.materialize``), as the reference's cache return requires.
+
+Decode never rebuilds them.  The reference re-expands the WHOLE cache through ``kv_a_layernorm`` + ``kv_b_proj`` on
+every step (:235); here the step runs in the factors' rank space (``_absorbed_decode``).  With the stored latent
+``c_t = V_l a_t`` (``a_t``: row t of the group's token factor, ``V_l``: this layer's 512 rows of the right factor),
+``kv_a_layernorm(c_t) = gamma o c_t / rms_t`` and ``kv_b_proj = [W_UK; W_UV]`` per head:
+
+    q_nope[h] . k_nope[t,h] = (1 / rms_t) (V_l^T (gamma o W_UK[h]^T q_nope[h])) . a_t  =  (1 / rms_t) q_hat[h] . a_t
+    sum_t p[h,t] v[t,h]     = W_UV[h] (gamma o V_l sum_t (p[h,t] / rms_t) a_t)
+
+so one pass over ``A`` for the scores and one for the values replace the S x 512 reconstruction, the RMSNorm and the
+S x 512 x (heads x 256) projection; ``1 / rms_t`` is computed once per layer (first decode step) and kept.  Decode tokens
+stay dense and exact (cache:131) and join through a log-sum-exp merge.
 """
 from __future__ import annotations
 
@@ -52,6 +64,11 @@ def xKV_mla_forward(  # noqa: N802
     q_pe, k_pe = apply_rotary_emb(q_pe, k_pe, position_embeddings.to(q_pe.device))
 
     latent = compressed_kv.view(bsz, q_len, 1, self.kv_lora_rank).transpose(1, 2)   # (b, 1, l, kv_lora_rank)
+    if (cache is not None and not is_prefill and isinstance(cache, FakeLayerMergingCache)
+            and getattr(self, "xkv_fused_decode", True)):
+        fused = _absorbed_decode(self, cache, q_nope, q_pe, latent, k_pe.contiguous())
+        if fused is not None:
+            return self.o_proj(fused.reshape(bsz, q_len, -1).contiguous()), None
     if cache is not None:
         if is_prefill:
             assert isinstance(cache, FakeLayerMergingCache)
@@ -85,6 +102,42 @@ def xKV_mla_forward(  # noqa: N802
     )
     attn_output = attn_output.reshape(bsz, q_len, -1).contiguous()
     return self.o_proj(attn_output), attn_weights
+
+
+@torch.no_grad()
+def _absorbed_decode(self, cache: FakeLayerMergingCache, q_nope, q_pe, latent, k_pe) -> Optional[torch.Tensor]:
+    """One decode step of an MLA layer over the factored latent cache, in the rank space (see the module docstring).
+    q_nope (1, Hq, 1, dn), q_pe (1, Hq, 1, dr), latent (1, 1, 1, C), k_pe (1, 1, 1, dr) -> (1, 1, Hq, dv) or None."""
+    from .. import ops
+
+    slot = cache.latent_slot(latent, k_pe, self.layer_idx)
+    if slot is None:
+        return None
+    a, v_l, extras = slot["A"], slot["V"], slot["extras"]
+    hq, dn, dv, c = q_nope.shape[1], self.qk_nope_head_dim, self.v_head_dim, self.kv_lora_rank
+    gamma = self.kv_a_layernorm.weight.float()
+    w = self.kv_b_proj.weight.view(hq, dn + dv, c).float()
+    w_uk, w_uv = w[:, :dn], w[:, dn:]
+    if "inv_rms" not in extras:
+        # once per layer: 1 / rms of the reconstructed (bf16, as the reference stores them) latents
+        s_tok = a.shape[0]
+        lat = torch.empty(s_tok, c, dtype=torch.bfloat16, device=a.device)
+        ops.gemm_grouped([ops.make_problem([a], [v_l], lat, M=s_tok, N=c, K=a.shape[1])])
+        extras["inv_rms"] = torch.rsqrt(lat.float().pow(2).mean(-1) + self.kv_a_layernorm.variance_epsilon).contiguous()
+        del lat
+    qn, qp = q_nope[0, :, 0].float(), q_pe[0, :, 0]
+    q_hat = ((torch.einsum("hd,hdc->hc", qn, w_uk) * gamma) @ v_l.float()).to(torch.bfloat16).contiguous()
+    u, lse_p = ops.decode_absorbed(q_hat, a, self.scaling, row_scale=extras["inv_rms"], bias_q=qp.contiguous(),
+                                   bias_k=slot["v_prefix"])
+    out_p = torch.einsum("hc,hvc->hv", (u @ v_l.float().t()) * gamma, w_uv)
+    # decode tokens (the new one included): dense, exact latents through the module's own layernorm + projection
+    kv_t = self.kv_b_proj(self.kv_a_layernorm(slot["k_tail"])).view(-1, hq, dn + dv).float()
+    s_t = (torch.einsum("hd,thd->ht", qn, kv_t[:, :, :dn]) + qp.float() @ slot["v_tail"].float().t()) * self.scaling
+    lse_t = torch.logsumexp(s_t, dim=-1)
+    out_t = torch.einsum("ht,thv->hv", torch.softmax(s_t, dim=-1), kv_t[:, :, dn:])
+    lse = torch.logaddexp(lse_p, lse_t)
+    out = torch.exp(lse_p - lse)[:, None] * out_p + torch.exp(lse_t - lse)[:, None] * out_t
+    return out.to(q_nope.dtype)[None, None]
 
 
 def enable_deepseek_v2_xKV_eval(model):  # noqa: N802

@@ -58,13 +58,15 @@ def compress_groups(
     layer_ids: Optional[Sequence[Sequence[int]]] = None,
     num_streams: int = 4,
     extra_rows: int = 0,
+    in_place: bool = True,
 ) -> List[GroupFactors]:
     """Compress equally-shaped layer groups. keys[g][i] / values[g][i]: (1, H, S, D) bf16 of layer i of
     group g (keys PRE-RoPE, as the reference hands them over, llama.py:49).
 
     The K matrices and the V matrices are independent factorisations; they are cut into up to
     `num_streams` batches that run on separate CUDA streams, so that the latency-bound stages of one batch
-    (Cholesky panels, Jacobi) overlap the tensor-core GEMMs of another."""
+    (Cholesky panels, Jacobi) overlap the tensor-core GEMMs of another.  `in_place=False` forces the gather kernel +
+    packed-matrix path (the two give bit-identical factors; tests compare them)."""
     ng = len(keys)
     if ng == 0:
         return []
@@ -88,11 +90,19 @@ def compress_groups(
             stream.wait_stream(main)
             used.append(stream)
         with torch.cuda.stream(stream):
-            xs = pack_groups(groups)
-            fs = factorize.factorize_batch(xs, rank, opts, extra_rows=extra_rows)
-            if stream is not main:
-                for x in xs:
-                    x.record_stream(stream)
+            # token-major layer tensors (what HF hands over) are read in place through per-layer tensor maps; any other
+            # layout goes through the gather kernel first (reference cache:170-171 + :13-14)
+            rows = [[factorize.layer_rows(t) for t in grp] for grp in groups] if in_place else None
+            if rows is not None and all(r is not None for grp in rows for r in grp) and len(groups[0]) <= 16:
+                if groups[0][0].shape[0] != 1:
+                    raise XkvError("compress: batch size 1 per call (the reference's batched SVD is one SVD per sample)")
+                fs = factorize.factorize_groups(rows, rank, opts, extra_rows=extra_rows)
+            else:
+                xs = pack_groups(groups)
+                fs = factorize.factorize_batch(xs, rank, opts, extra_rows=extra_rows)
+                if stream is not main:
+                    for x in xs:
+                        x.record_stream(stream)
         for i, f in enumerate(fs):
             dst[lo + i] = f
             if stream is not main:
@@ -115,6 +125,7 @@ def compress_groups_from_host(
     opts: Optional[factorize.FactorizeOptions] = None,
     host_out: Optional[List[torch.Tensor]] = None,
     num_streams: int = 2,
+    staging=None,
 ):
     """Compress a KV cache that lives in (pinned) HOST memory, pipelined by chunks of `chunk_groups` layer groups:
     the host->device copy of chunk c+1 runs on a copy stream while chunk c is factorised, and the factors of chunk
@@ -122,14 +133,15 @@ def compress_groups_from_host(
     factorisation of the last chunk instead of copy + compute + copy in sequence.
 
     h_keys[g][i] / h_values[g][i]: pinned (1, S, H, D) bf16 tensors (token-major, as HF produces K/V before the
-    (bs, H, S, D) view).  Returns (factors per group, host tensors [A_k, Vt_k, A_v, Vt_v per group] or None)."""
+    (bs, H, S, D) view).  `staging`: device buffers from :func:`host_staging` (a serving loop allocates them once;
+    without them they are allocated here, on every call).  Returns (factors per group, host tensors [A_k, Vt_k,
+    A_v, Vt_v per group] or None)."""
     ng = len(h_keys)
     main = torch.cuda.current_stream(device)
     copy_s = _side_stream(device, 101)
     back_s = _side_stream(device, 102)
     # device staging for every group, allocated on the main stream (the copy stream only writes into it)
-    dk = [[torch.empty(h.shape, dtype=h.dtype, device=device) for h in grp] for grp in h_keys]
-    dv = [[torch.empty(h.shape, dtype=h.dtype, device=device) for h in grp] for grp in h_values]
+    dk, dv = staging if staging is not None else host_staging(h_keys, h_values, device)
     copy_s.wait_stream(main)
     ready = []
     with torch.cuda.stream(copy_s):
@@ -167,6 +179,13 @@ def compress_groups_from_host(
     main.wait_stream(back_s)
     main.wait_stream(copy_s)
     return out, host_tensors
+
+
+def host_staging(h_keys, h_values, device: torch.device):
+    """Device staging buffers for :func:`compress_groups_from_host` (same shapes as the host tensors)."""
+    dk = [[torch.empty(h.shape, dtype=h.dtype, device=device) for h in grp] for grp in h_keys]
+    dv = [[torch.empty(h.shape, dtype=h.dtype, device=device) for h in grp] for grp in h_values]
+    return dk, dv
 
 
 class GraphedCompressor:

@@ -983,6 +983,48 @@ __global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Absorbed attention over the token factor (MLA latents, deepseek_v2.py:217-235): the latent of token t is
+// c_t = V_l a_t and both products of the attention are LINEAR in it (kv_b_proj after a per-token RMS scale), so with
+// the query folded into the rank space, q^ = V_l^T (gamma o W_UK^T q_nope), the scores are
+//     s[h][t] = scale * ( row_scale[t] * (q^[h] . a_t) + bias_q[h] . bias_k[t] )
+// (row_scale = 1 / rms of the reconstructed latent, the bias term is the RoPE part q_pe . k_pe) and the values are
+//     u[h] = sum_t softmax(s)[h][t] * row_scale[t] * a_t          (rank space; the caller applies V_l, gamma, W_UV).
+// Two tensor-core GEMMs over A and three small kernels; the latents are never reconstructed.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) absorbed_scores_kernel(float* __restrict__ scores, const float* __restrict__ bias,
+                                                              long long ld, const float* __restrict__ row_scale, int S,
+                                                              float scale) {
+  const int hq = blockIdx.y;
+  float* s = scores + hq * ld;
+  const float* b = bias != nullptr ? bias + hq * ld : nullptr;
+  for (int t = blockIdx.x * 256 + threadIdx.x; t < S; t += gridDim.x * 256) {
+    float v = s[t];
+    if (row_scale != nullptr) v *= row_scale[t];
+    if (b != nullptr) v += b[t];
+    s[t] = v * scale;
+  }
+}
+__global__ void __launch_bounds__(256) scale_prob_kernel(__nv_bfloat16* __restrict__ prob, long long ldp,
+                                                         const float* __restrict__ row_scale, int S) {
+  __nv_bfloat16* p = prob + blockIdx.y * ldp;
+  for (int t = blockIdx.x * 256 + threadIdx.x; t < S; t += gridDim.x * 256)
+    p[t] = __float2bfloat16_rn(__bfloat162float(p[t]) * row_scale[t]);
+}
+// u_out[hq][j] = U[hq][j] / rowsum, lse[hq] = m + log(rowsum) from the chunk-local softmax statistics
+__global__ void __launch_bounds__(256) absorbed_finalize_kernel(const float* __restrict__ U, int r,
+                                                                const float* __restrict__ chunk_max,
+                                                                const float* __restrict__ chunk_sum, int nchunks,
+                                                                float* __restrict__ u_out, float* __restrict__ lse_out) {
+  __shared__ float w_s[SM_MAX_CHUNKS];
+  __shared__ float stats[2];
+  const int hq = blockIdx.x;
+  head_weights(chunk_max, chunk_sum, hq, nchunks, w_s, stats);
+  const float inv = 1.f / stats[1];
+  for (int j = threadIdx.x; j < r; j += 256) u_out[static_cast<long long>(hq) * r + j] = U[static_cast<long long>(hq) * r + j] * inv;
+  if (lse_out != nullptr && threadIdx.x == 0) lse_out[hq] = stats[0] + logf(stats[1]);
+}
+
 // RoPE on materialised keys, in the reference's bf16 arithmetic (cache:142-152): x (rows, H, D) in place
 __global__ void __launch_bounds__(256) rope_bf16_kernel(__nv_bfloat16* __restrict__ x, long long ld_row, int rows, int H,
                                                         int D, const __nv_bfloat16* __restrict__ cos,
@@ -1274,6 +1316,90 @@ extern "C" int xkv_decode_attention_lse(const void* q, int Hq, int H, int D, con
       U, 1, 0, rv, static_cast<const __nv_bfloat16*>(Vv_layer), ldv_v, prob, ldl, S,
       T, static_cast<const __nv_bfloat16*>(v_tail), tail_stride_h, tail_stride_t, rowsum, qpk, D,
       static_cast<__nv_bfloat16*>(out), chunk_max, nchunks, lse_out);
+  XKV_LAUNCHED();
+  return 0;
+}
+
+extern "C" size_t xkv_decode_absorbed_workspace_bytes(int Hq, int S, int r) {
+  const size_t ldl = (static_cast<size_t>(S) + 63) / 64 * 64;
+  size_t b = 0;
+  b += 2 * al(Hq * ldl * 4);                                // scores, bias scores
+  b += al(128 * ldl * 2);                                   // probabilities (bf16)
+  b += al(2 * Hq * SM_MAX_CHUNKS * 4);                      // per-chunk max / sum
+  b += al(static_cast<size_t>(64 + 1) * Hq * r * 4);        // split-K slabs of U, then U
+  return b + 1024;
+}
+
+extern "C" int xkv_decode_absorbed(const void* q_hat, int Hq, const void* A, int64_t lda, int r, int S,
+                                   const float* row_scale, const void* bias_q, const void* bias_k, int64_t ld_bias_k,
+                                   int bias_dim, float scale, float* u_out, float* lse_out, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  XKV_REQUIRE(q_hat && A && u_out && workspace, "absorbed decode: null argument");
+  XKV_REQUIRE(Hq >= 1 && Hq <= 128 && S >= 1 && r >= 8 && r % 8 == 0 && lda % 8 == 0, "absorbed decode: bad sizes");
+  XKV_REQUIRE((bias_q == nullptr) == (bias_k == nullptr), "absorbed decode: bias_q and bias_k go together");
+  XKV_REQUIRE(bias_q == nullptr || (bias_dim >= 8 && bias_dim % 8 == 0 && ld_bias_k % 8 == 0),
+              "absorbed decode: the bias width must be a multiple of 8");
+  XKV_REQUIRE(workspace_bytes >= xkv_decode_absorbed_workspace_bytes(Hq, S, r), "absorbed decode: workspace too small");
+  XKV_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "absorbed decode: workspace must be 256-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  const long long ldl = static_cast<long long>((static_cast<size_t>(S) + 63) / 64 * 64);
+  const int split = decode_split_k(S, r);
+  char* w = static_cast<char*>(workspace);
+  float* scores = reinterpret_cast<float*>(w);
+  w += al(Hq * ldl * 4);
+  float* bias = reinterpret_cast<float*>(w);
+  w += al(Hq * ldl * 4);
+  __nv_bfloat16* prob = reinterpret_cast<__nv_bfloat16*>(w);
+  w += al(128 * ldl * 2);
+  float* rowsum = reinterpret_cast<float*>(w);
+  float* chunk_max = rowsum + Hq * SM_MAX_CHUNKS;
+  w += al(2 * Hq * SM_MAX_CHUNKS * 4);
+  float* u_slabs = reinterpret_cast<float*>(w);
+  // ---- raw scores: q^ A^T (and the bias term q_pe k_pe^T), tokens along N ----
+  xkv_gemm_problem gp[2];
+  std::memset(gp, 0, sizeof(gp));
+  gp[0].M = Hq, gp[0].N = S, gp[0].K = r, gp[0].num_terms = 1;
+  gp[0].A[0] = q_hat, gp[0].B[0] = A, gp[0].lda = r, gp[0].ldb = lda;
+  gp[0].D = scores, gp[0].ldd = ldl, gp[0].split_k = 1;
+  int np = 1;
+  if (bias_q != nullptr) {
+    gp[1].M = Hq, gp[1].N = S, gp[1].K = bias_dim, gp[1].num_terms = 1;
+    gp[1].A[0] = bias_q, gp[1].B[0] = bias_k, gp[1].lda = bias_dim, gp[1].ldb = ld_bias_k;
+    gp[1].D = bias, gp[1].ldd = ldl, gp[1].split_k = 1;
+    np = 2;
+  }
+  int rc = xkv_gemm_grouped(gp, np, stream);
+  if (rc) return rc;
+  const int gx = (S + 1023) / 1024 < 1 ? 1 : (S + 1023) / 1024;
+  absorbed_scores_kernel<<<dim3(gx, Hq), 256, 0, st>>>(scores, bias_q != nullptr ? bias : nullptr, ldl, row_scale, S, scale);
+  XKV_LAUNCHED();
+  // ---- softmax with chunk-local maxima (chunk c = token range of split-K slab c; no dense tail here) ----
+  const int nkb_p = (S + 63) / 64;
+  const int kps = (nkb_p + split - 1) / split;
+  const int nchunks = split + 1;
+  XKV_REQUIRE(nchunks <= SM_MAX_CHUNKS, "absorbed decode: too many softmax chunks");
+  softmax_chunk_kernel<<<dim3(Hq, nchunks), 256, 0, st>>>(scores, ldl, S, 0, kps, split, nullptr, nullptr, 0, 0, 1, 0, scale,
+                                                          prob, ldl, chunk_max, rowsum);
+  XKV_LAUNCHED();
+  if (row_scale != nullptr) {
+    scale_prob_kernel<<<dim3(gx, Hq), 256, 0, st>>>(prob, ldl, row_scale, S);
+    XKV_LAUNCHED();
+  }
+  // ---- U = P' A (tokens are the contraction) ----
+  xkv_gemm_problem gu;
+  std::memset(&gu, 0, sizeof(gu));
+  gu.M = Hq, gu.N = r, gu.K = S, gu.num_terms = 1;
+  gu.a_mn_major = 0, gu.b_mn_major = 1;
+  gu.A[0] = prob, gu.B[0] = A, gu.lda = ldl, gu.ldb = lda;
+  gu.D = u_slabs, gu.ldd = r, gu.split_k = split;
+  gu.split_stride = static_cast<long long>(Hq) * r;
+  rc = xkv_gemm_grouped(&gu, 1, stream);
+  if (rc) return rc;
+  float* U = u_slabs + static_cast<size_t>(split) * Hq * r;
+  reduce_u_kernel<<<dim3((r + 63) / 64, Hq), 256, 0, st>>>(u_slabs, split, static_cast<long long>(Hq) * r, r, chunk_max, rowsum,
+                                                           nchunks, U);
+  XKV_LAUNCHED();
+  absorbed_finalize_kernel<<<Hq, 256, 0, st>>>(U, r, chunk_max, rowsum, nchunks, u_out, lse_out);
   XKV_LAUNCHED();
   return 0;
 }

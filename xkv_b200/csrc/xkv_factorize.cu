@@ -161,9 +161,11 @@ static xkv_gemm_problem problem(const void* a0, const void* a1, const void* a2, 
   return p;
 }
 
-static int run_gemms(std::vector<xkv_gemm_problem>& ps, void* stream) {
-  for (size_t i = 0; i < ps.size(); i += XKV_MAX_GEMM_PROBLEMS) {
-    const int cnt = static_cast<int>(ps.size() - i < XKV_MAX_GEMM_PROBLEMS ? ps.size() - i : XKV_MAX_GEMM_PROBLEMS);
+static int run_gemms(std::vector<xkv_gemm_problem>& ps, void* stream, int per_launch = XKV_MAX_GEMM_PROBLEMS) {
+  if (per_launch > XKV_MAX_GEMM_PROBLEMS) per_launch = XKV_MAX_GEMM_PROBLEMS;
+  if (per_launch < 1) per_launch = 1;
+  for (size_t i = 0; i < ps.size(); i += per_launch) {
+    const int cnt = static_cast<int>(ps.size() - i < static_cast<size_t>(per_launch) ? ps.size() - i : per_launch);
     int rc = xkv_gemm_grouped(ps.data() + i, cnt, stream);
     if (rc) return rc;
   }
@@ -243,11 +245,11 @@ extern "C" int xkv_factorize_sigma_count(int rank, const xkv_factorize_options* 
   return (P.rr && o.want_sigma) ? P.W : 0;
 }
 
-extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, int n, int64_t ldx, int rank,
-                                   const xkv_factorize_options* opts, void* const* A_host, void* const* Vt_host,
-                                   void* const* V_host, float* const* sigma_host, float* const* gram_host,
-                                   int phase, void* workspace, size_t workspace_bytes,
-                                   void* const* stage_events_host, void* stream) {
+// X_host: packed matrices (layers == 0) or per-layer pointers [batch][layers] read in place
+static int factorize_impl(const void* const* X_host, int layers, int layer_cols, int batch, int m, int n, int64_t ldx,
+                          int rank, const xkv_factorize_options* opts, void* const* A_host, void* const* Vt_host,
+                          void* const* V_host, float* const* sigma_host, float* const* gram_host, int phase,
+                          void* workspace, size_t workspace_bytes, void* const* stage_events_host, void* stream) {
   xkv_factorize_options o;
   if (opts)
     o = *opts;
@@ -281,8 +283,14 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
   // from the caller's reduced Gram.
   if (phase != 2) {
     for (int b = 0; b < B; ++b) {
-      xkv_gemm_problem p = problem(X_host[b], nullptr, nullptr, ldx, 1, X_host[b], nullptr, nullptr, ldx, 1,
+      const void* x0 = layers > 0 ? X_host[static_cast<size_t>(b) * layers] : X_host[b];
+      xkv_gemm_problem p = problem(x0, nullptr, nullptr, ldx, 1, x0, nullptr, nullptr, ldx, 1,
                                    P.gram_slabs + static_cast<size_t>(b) * P.gs * nn * nn, nn, n, n, m, 1);
+      if (layers > 0) {   // both operands are the group's layer tensors, read in place
+        p.a_layers = p.b_layers = layers;
+        p.layer_cols = layer_cols;
+        for (int i = 0; i < layers; ++i) p.A_layer[i] = p.B_layer[i] = X_host[static_cast<size_t>(b) * layers + i];
+      }
       p.sym_upper = 1;
       p.split_k = P.gs;
       p.split_stride = nn * nn;
@@ -293,7 +301,7 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
       }
       ps.push_back(p);
     }
-    XKV_TRY(run_gemms(ps, stream));
+    XKV_TRY(run_gemms(ps, stream, layers > 0 ? XKV_MAX_LAYER_MAPS / layers : XKV_MAX_GEMM_PROBLEMS));
   }
   XKV_TRY(mark());  // 1: Gram GEMM (the dominant kernel, timed on its own for the roofline)
   if (phase == 0) {
@@ -515,12 +523,37 @@ extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, 
   for (int b = 0; b < B; ++b) XKV_TRY(xkv_convert_bf16(cur[b], r, n, nn, Vt_host[b], nn, V_host[b], r, stream));
   // ---- 7. projection A = X V ----
   for (int b = 0; b < B; ++b) {
-    xkv_gemm_problem p =
-        problem(X_host[b], nullptr, nullptr, ldx, 0, Vt_host[b], nullptr, nullptr, nn, 0, A_host[b], r, m, r, n, 1);
+    const void* x0 = layers > 0 ? X_host[static_cast<size_t>(b) * layers] : X_host[b];
+    xkv_gemm_problem p = problem(x0, nullptr, nullptr, ldx, 0, Vt_host[b], nullptr, nullptr, nn, 0, A_host[b], r, m, r, n, 1);
+    if (layers > 0) {
+      p.a_layers = layers;
+      p.layer_cols = layer_cols;
+      for (int i = 0; i < layers; ++i) p.A_layer[i] = X_host[static_cast<size_t>(b) * layers + i];
+    }
     p.out_bf16 = 1;
     ps.push_back(p);
   }
-  XKV_TRY(run_gemms(ps, stream));
+  XKV_TRY(run_gemms(ps, stream, layers > 0 ? XKV_MAX_LAYER_MAPS / layers : XKV_MAX_GEMM_PROBLEMS));
   XKV_TRY(mark());  // 6: projection
   return 0;
+}
+
+extern "C" int xkv_factorize_batch(const void* const* X_host, int batch, int m, int n, int64_t ldx, int rank,
+                                   const xkv_factorize_options* opts, void* const* A_host, void* const* Vt_host,
+                                   void* const* V_host, float* const* sigma_host, float* const* gram_host,
+                                   int phase, void* workspace, size_t workspace_bytes,
+                                   void* const* stage_events_host, void* stream) {
+  return factorize_impl(X_host, 0, 0, batch, m, n, ldx, rank, opts, A_host, Vt_host, V_host, sigma_host, gram_host, phase,
+                        workspace, workspace_bytes, stage_events_host, stream);
+}
+
+extern "C" int xkv_factorize_groups(const void* const* layer_ptrs_host, int batch, int layers, int layer_cols, int m,
+                                    int64_t ld_layer, int rank, const xkv_factorize_options* opts, void* const* A_host,
+                                    void* const* Vt_host, void* const* V_host, float* const* sigma_host, void* workspace,
+                                    size_t workspace_bytes, void* const* stage_events_host, void* stream) {
+  XKV_REQUIRE(layers >= 1 && layers <= XKV_MAX_GROUP_LAYERS, "factorize: %d layers per group (1..%d)", layers, XKV_MAX_GROUP_LAYERS);
+  XKV_REQUIRE(layer_cols > 0 && layer_cols % 64 == 0, "factorize: layer_cols=%d must be a positive multiple of 64", layer_cols);
+  XKV_REQUIRE(ld_layer % 8 == 0 && ld_layer >= layer_cols, "factorize: bad layer row stride");
+  return factorize_impl(layer_ptrs_host, layers, layer_cols, batch, m, layers * layer_cols, ld_layer, rank, opts, A_host,
+                        Vt_host, V_host, sigma_host, nullptr, 0, workspace, workspace_bytes, stage_events_host, stream);
 }

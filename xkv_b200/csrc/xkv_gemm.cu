@@ -49,11 +49,24 @@ struct alignas(64) GemmProb {
   unsigned char ta[6], tb[6];
   const int* run_if;   // optional device predicate: the problem's CTAs exit at once when *run_if == 0
   int phases;          // sequential accumulation phases per CTA (two TMEM accumulators), see gemm_kernel
+  // layered operands: operand columns [i * layer_cols, (i + 1) * layer_cols) come from GemmParams::layer_maps[begin + i]
+  int a_layers, a_layer_begin, b_layers, b_layer_begin, layer_cols;
 };
 struct GemmParams {
   int nprob;
   GemmProb p[XKV_MAX_GEMM_PROBLEMS];
+  CUtensorMap layer_maps[XKV_MAX_LAYER_MAPS];
 };
+
+// Tensor map and in-layer column of column `col` of a layered operand.  Columns past the last layer map to the last
+// layer with an out-of-bounds coordinate (TMA zero-fills), like the tail of an ordinary operand.
+__device__ __forceinline__ const CUtensorMap* layer_map(const GemmParams& P, int begin, int layers, int layer_cols, int col,
+                                                        int& col_in_layer) {
+  int li = col / layer_cols;
+  li = li < layers ? li : layers - 1;
+  col_in_layer = col - li * layer_cols;
+  return &P.layer_maps[begin + li];
+}
 
 template <int A_MN, int B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmParams P) {
@@ -132,6 +145,33 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp in the loop, one elected lane issues) =====================
+    // Layered operands: which layer matrix a 64-column chunk of this CTA's tile comes from is fixed for the whole kernel
+    // (MN-major: the chunk's column is m0 / n0 + 64 c) or advances with the k block (K-major): resolved here, outside the
+    // loop, so that the issue path has no integer division.
+    const CUtensorMap* a_chunk_map[BM / 64];
+    int a_chunk_col[BM / 64];
+    const CUtensorMap* b_chunk_map[BN / 64];
+    int b_chunk_col[BN / 64];
+#pragma unroll
+    for (int c = 0; c < BM / 64; ++c) {
+      a_chunk_col[c] = m0 + 64 * c;
+      a_chunk_map[c] = (A_MN && pr.a_layers) ? layer_map(P, pr.a_layer_begin, pr.a_layers, pr.layer_cols, m0 + 64 * c, a_chunk_col[c]) : nullptr;
+    }
+#pragma unroll
+    for (int c = 0; c < BN / 64; ++c) {
+      b_chunk_col[c] = n0 + 64 * c;
+      b_chunk_map[c] = (B_MN && pr.b_layers) ? layer_map(P, pr.b_layer_begin, pr.b_layers, pr.layer_cols, n0 + 64 * c, b_chunk_col[c]) : nullptr;
+    }
+    // K-major layered operand: (layer, column inside the layer) of the current k block, advanced incrementally
+    int ka_layer = 0, ka_col = 0, kb_layer = 0, kb_col = 0;
+    if (!A_MN && pr.a_layers) {
+      ka_layer = (kb0 * BK) / pr.layer_cols;
+      ka_col = kb0 * BK - ka_layer * pr.layer_cols;
+    }
+    if (!B_MN && pr.b_layers) {
+      kb_layer = (kb0 * BK) / pr.layer_cols;
+      kb_col = kb0 * BK - kb_layer * pr.layer_cols;
+    }
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < niter; ++it) {
@@ -145,19 +185,38 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       if (elect_one()) {
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
         if (A_MN == 0) {
-          tma_load_2d(sA, amap, &full_bar[s], kb * BK, m0);
+          if (pr.a_layers)
+            tma_load_2d(sA, &P.layer_maps[pr.a_layer_begin + min(ka_layer, pr.a_layers - 1)], &full_bar[s],
+                        ka_layer < pr.a_layers ? ka_col : pr.layer_cols, m0);
+          else
+            tma_load_2d(sA, amap, &full_bar[s], kb * BK, m0);
         } else {
 #pragma unroll
-          for (int c = 0; c < BM / 64; ++c) tma_load_2d(sA + c * CHUNK_BYTES, amap, &full_bar[s], m0 + 64 * c, kb * BK);
+          for (int c = 0; c < BM / 64; ++c)
+            tma_load_2d(sA + c * CHUNK_BYTES, a_chunk_map[c] ? a_chunk_map[c] : amap, &full_bar[s], a_chunk_col[c], kb * BK);
         }
         if (B_MN == 0) {
-          tma_load_2d(sB, bmap, &full_bar[s], kb * BK, n0);
+          if (pr.b_layers)
+            tma_load_2d(sB, &P.layer_maps[pr.b_layer_begin + min(kb_layer, pr.b_layers - 1)], &full_bar[s],
+                        kb_layer < pr.b_layers ? kb_col : pr.layer_cols, n0);
+          else
+            tma_load_2d(sB, bmap, &full_bar[s], kb * BK, n0);
         } else {
 #pragma unroll
-          for (int c = 0; c < BN / 64; ++c) tma_load_2d(sB + c * CHUNK_BYTES, bmap, &full_bar[s], n0 + 64 * c, kb * BK);
+          for (int c = 0; c < BN / 64; ++c)
+            tma_load_2d(sB + c * CHUNK_BYTES, b_chunk_map[c] ? b_chunk_map[c] : bmap, &full_bar[s], b_chunk_col[c], kb * BK);
         }
       }
       __syncwarp();
+      // layered operands take one term: every iteration is a new k block
+      if (!A_MN && pr.a_layers && (ka_col += BK) >= pr.layer_cols) {
+        ka_col -= pr.layer_cols;
+        ++ka_layer;
+      }
+      if (!B_MN && pr.b_layers && (kb_col += BK) >= pr.layer_cols) {
+        kb_col -= pr.layer_cols;
+        ++kb_layer;
+      }
       if (++s == STAGES) {
         s = 0;
         ph ^= 1u;
@@ -329,7 +388,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int build_problem(const xkv_gemm_problem& in, GemmProb& out, int& cta_cursor) {
+static int build_problem(const xkv_gemm_problem& in, GemmProb& out, int& cta_cursor, GemmParams& params, int& map_cursor) {
   XKV_REQUIRE(in.M > 0 && in.N > 0 && in.K > 0, "gemm: empty problem M=%d N=%d K=%d", in.M, in.N, in.K);
   XKV_REQUIRE(in.num_terms >= 1 && in.num_terms <= 6, "gemm: num_terms=%d out of range", in.num_terms);
   XKV_REQUIRE(in.lda % 8 == 0 && in.ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements");
@@ -344,20 +403,60 @@ static int build_problem(const xkv_gemm_problem& in, GemmProb& out, int& cta_cur
     out.ta[t] = in.term_a[t];
     out.tb[t] = in.term_b[t];
   }
+  // layered operands: one tensor map per layer matrix in the launch's pool; the limb slots alias the first layer
+  XKV_REQUIRE(in.a_layers >= 0 && in.a_layers <= XKV_MAX_GROUP_LAYERS && in.b_layers >= 0 && in.b_layers <= XKV_MAX_GROUP_LAYERS,
+              "gemm: at most %d layers per operand", XKV_MAX_GROUP_LAYERS);
+  if (in.a_layers > 0 || in.b_layers > 0) {
+    XKV_REQUIRE(in.num_terms == 1, "gemm: layered operands take one term");
+    XKV_REQUIRE(in.layer_cols > 0 && in.layer_cols % 64 == 0, "gemm: layer_cols=%d must be a positive multiple of 64", in.layer_cols);
+  }
+  for (int side = 0; side < 2; ++side) {
+    const int layers = side == 0 ? in.a_layers : in.b_layers;
+    if (layers == 0) continue;
+    const void* const* ptrs = side == 0 ? in.A_layer : in.B_layer;
+    const bool mn = side == 0 ? in.a_mn_major != 0 : in.b_mn_major != 0;
+    const long long ld = side == 0 ? in.lda : in.ldb;
+    const int other = side == 0 ? in.M : in.N;   // extent of the operand's M / N dimension
+    if (side == 1 && in.a_layers == in.b_layers && in.a_mn_major && in.b_mn_major && in.lda == in.ldb &&
+        std::memcmp(in.A_layer, in.B_layer, sizeof(void*) * layers) == 0) {
+      out.b_layer_begin = out.a_layer_begin;   // X^T X: both operands are the same layer matrices, same boxes
+      continue;
+    }
+    (side == 0 ? out.a_layer_begin : out.b_layer_begin) = map_cursor;
+    for (int i = 0; i < layers; ++i) {
+      XKV_REQUIRE(ptrs[i] != nullptr && (reinterpret_cast<uintptr_t>(ptrs[i]) & 15) == 0, "gemm: layer %d null or unaligned", i);
+      XKV_REQUIRE(map_cursor < XKV_MAX_LAYER_MAPS, "gemm: more than %d layer matrices in one launch", XKV_MAX_LAYER_MAPS);
+      int rc;
+      if (!mn)   // K-major: rows = M (or N) index, the layer supplies layer_cols of the K columns
+        rc = encode_tmap_2d_bf16(&params.layer_maps[map_cursor++], ptrs[i], in.layer_cols, other, ld, BK, side == 0 ? BM : BN);
+      else       // MN-major: rows = K index, the layer supplies layer_cols of the M (or N) columns
+        rc = encode_tmap_2d_bf16(&params.layer_maps[map_cursor++], ptrs[i], in.layer_cols, in.K, ld, 64, BK);
+      if (rc) return rc;
+    }
+  }
+  out.a_layers = in.a_layers;
+  out.b_layers = in.b_layers;
+  out.layer_cols = in.layer_cols;
+  XKV_REQUIRE(in.a_layers == 0 || (in.a_mn_major ? in.M : in.K) <= in.a_layers * in.layer_cols, "gemm: layered A narrower than the problem");
+  XKV_REQUIRE(in.b_layers == 0 || (in.b_mn_major ? in.N : in.K) <= in.b_layers * in.layer_cols, "gemm: layered B narrower than the problem");
   for (int i = 0; i < 3; ++i) {
     // unused limbs alias limb 0 so every tensor map in parameter space is valid to prefetch
-    const void* a = used_a[i] ? in.A[i] : in.A[in.term_a[0]];
-    const void* b = used_b[i] ? in.B[i] : in.B[in.term_b[0]];
+    const void* a = in.a_layers > 0 ? in.A_layer[0] : (used_a[i] ? in.A[i] : in.A[in.term_a[0]]);
+    const void* b = in.b_layers > 0 ? in.B_layer[0] : (used_b[i] ? in.B[i] : in.B[in.term_b[0]]);
     XKV_REQUIRE(a != nullptr && b != nullptr, "gemm: null operand limb %d", i);
     XKV_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(b) & 15) == 0,
                 "gemm: operands must be 16-byte aligned");
-    int rc;
-    if (!in.a_mn_major)
+    int rc = 0;
+    if (in.a_layers > 0)
+      out.a_map[i] = params.layer_maps[out.a_layer_begin];   // valid to prefetch; the loads go through the layer maps
+    else if (!in.a_mn_major)
       rc = encode_tmap_2d_bf16(&out.a_map[i], a, in.K, in.M, in.lda, BK, BM);
     else
       rc = encode_tmap_2d_bf16(&out.a_map[i], a, in.M, in.K, in.lda, 64, BK);
     if (rc) return rc;
-    if (!in.b_mn_major)
+    if (in.b_layers > 0)
+      out.b_map[i] = params.layer_maps[out.b_layer_begin];
+    else if (!in.b_mn_major)
       rc = encode_tmap_2d_bf16(&out.b_map[i], b, in.K, in.N, in.ldb, BK, BN);
     else
       rc = encode_tmap_2d_bf16(&out.b_map[i], b, in.N, in.K, in.ldb, 64, BK);
@@ -410,19 +509,21 @@ static int launch_variant(const GemmParams& params, int grid, cudaStream_t strea
 
 }  // namespace xkv
 
+extern "C" size_t xkv_gemm_problem_size(void) { return sizeof(xkv_gemm_problem); }
+
 extern "C" int xkv_gemm_grouped(const xkv_gemm_problem* problems, int num_problems, void* stream) {
   using namespace xkv;
   XKV_REQUIRE(problems != nullptr && num_problems >= 1, "gemm: no problems");
   XKV_REQUIRE(num_problems <= XKV_MAX_GEMM_PROBLEMS, "gemm: at most %d problems per launch", XKV_MAX_GEMM_PROBLEMS);
   const int a_mn = problems[0].a_mn_major ? 1 : 0;
   const int b_mn = problems[0].b_mn_major ? 1 : 0;
-  static thread_local GemmParams params;  // ~14 KiB, keep it off the stack
+  static thread_local GemmParams params;  // ~22 KiB, keep it off the stack
   params.nprob = num_problems;
-  int cursor = 0;
+  int cursor = 0, map_cursor = 0;
   for (int i = 0; i < num_problems; ++i) {
     XKV_REQUIRE((problems[i].a_mn_major ? 1 : 0) == a_mn && (problems[i].b_mn_major ? 1 : 0) == b_mn,
                 "gemm: all problems of one launch must share operand majors");
-    int rc = build_problem(problems[i], params.p[i], cursor);
+    int rc = build_problem(problems[i], params.p[i], cursor, params, map_cursor);
     if (rc) return rc;
   }
   cudaStream_t st = as_stream(stream);

@@ -67,6 +67,58 @@ __global__ void __launch_bounds__(256) reduce_slabs_kernel(const __grid_constant
 }
 
 // =============================================================================================
+// upper-triangle packing of a symmetric fp32 matrix (the payload of the token-sharded Gram all-reduce)
+// =============================================================================================
+// Row r contributes its columns [r32, n), r32 = 32 * (r / 32): n^2 / 2 + 16 n floats instead of n^2.
+__host__ __device__ inline long long packed_row_offset(int r, int n) {
+  const long long g = r / 32;
+  return 32 * (g * n - 16 * g * (g - 1)) + (r - 32 * g) * (n - 32 * g);
+}
+__global__ void __launch_bounds__(256) pack_upper_kernel(const float* __restrict__ full, long long ld, int n,
+                                                         float* __restrict__ packed) {
+  const int r = blockIdx.x;
+  const int c0 = (r / 32) * 32;
+  const float* src = full + static_cast<long long>(r) * ld + c0;
+  float* dst = packed + packed_row_offset(r, n);
+  const int w = n - c0;            // multiple of 4 when n is (c0 is a multiple of 32); rows are 16-byte aligned then
+  if ((n & 3) == 0 && (ld & 3) == 0) {
+    for (int v = threadIdx.x; v < (w >> 2); v += 256)
+      reinterpret_cast<float4*>(dst)[v] = reinterpret_cast<const float4*>(src)[v];
+  } else {
+    for (int c = threadIdx.x; c < w; c += 256) dst[c] = src[c];
+  }
+}
+// full[i][j] = full[j][i] = packed(i, j) for j >= i: 32 x 32 tiles, mirrored through shared memory
+__global__ void __launch_bounds__(256) unpack_upper_kernel(const float* __restrict__ packed, int n, float* __restrict__ full,
+                                                           long long ld, int tiles_per_row) {
+  __shared__ float tile[32][33];
+  int t = blockIdx.x, bi = 0, cnt = tiles_per_row;
+  while (t >= cnt) {
+    t -= cnt;
+    ++bi;
+    --cnt;
+  }
+  const int bj = bi + t;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi * 32 + r, j = bj * 32 + tx;
+    float v = 0.f;
+    if (i < n && j < n) {
+      v = packed[packed_row_offset(i, n) + (j - bi * 32)];
+      if (j >= i) full[static_cast<long long>(i) * ld + j] = v;
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bj * 32 + r, j = bi * 32 + tx;
+    if (i < n && j < n && i > j) full[static_cast<long long>(i) * ld + j] = tile[tx][r];
+  }
+}
+
+// =============================================================================================
 // fp32 -> bf16 limbs
 // =============================================================================================
 __device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
@@ -573,6 +625,26 @@ extern "C" int xkv_reduce_slabs(const float* slabs, int num_slabs, int64_t slab_
                                 int symmetrize, float* out, int64_t ld_out, void* stream) {
   XKV_REQUIRE(slabs && out, "reduce_slabs: bad arguments");
   return xkv_reduce_slabs_batched(&slabs, &out, 1, num_slabs, slab_stride, rows, cols, ld, symmetrize, ld_out, stream);
+}
+
+extern "C" size_t xkv_gram_packed_elems(int n) {
+  if (n <= 0) return 0;
+  return static_cast<size_t>(packed_row_offset(n - 1, n) + (n - ((n - 1) / 32) * 32));
+}
+
+extern "C" int xkv_gram_pack_upper(const float* full, int n, int64_t ld, float* packed, void* stream) {
+  XKV_REQUIRE(full && packed && n > 0 && ld >= n, "gram pack: bad arguments");
+  pack_upper_kernel<<<n, 256, 0, as_stream(stream)>>>(full, ld, n, packed);
+  XKV_LAUNCHED();
+  return 0;
+}
+
+extern "C" int xkv_gram_unpack_upper(const float* packed, int n, float* full, int64_t ld, void* stream) {
+  XKV_REQUIRE(full && packed && n > 0 && ld >= n, "gram unpack: bad arguments");
+  const int tr = (n + 31) / 32;
+  unpack_upper_kernel<<<tr * (tr + 1) / 2, 256, 0, as_stream(stream)>>>(packed, n, full, ld, tr);
+  XKV_LAUNCHED();
+  return 0;
 }
 
 extern "C" int xkv_symmetrize_split_bf16(const float* const* slabs_host, int batch, int num_slabs, int64_t slab_stride,

@@ -47,6 +47,7 @@ class _XkvLayer(DynamicLayer):
         self.tail_len = 0
         self.dense_k: Optional[torch.Tensor] = None  # a slot of a compressed group that stayed dense (merge flag off)
         self.dense_v: Optional[torch.Tensor] = None
+        self.extras: Dict[str, torch.Tensor] = {}    # per-layer quantities callers derive once from the factors (MLA: 1 / rms)
 
     # --- sequence bookkeeping used by transformers' mask / position logic ---
     def get_seq_length(self) -> int:
@@ -165,7 +166,15 @@ class FakeLayerMergingCache(DynamicCache):
             if re_apply_rope:
                 key = self._rope_dense(key, cos, sin)
             return DynamicLayer.update(layer, key, value)
-        DynamicLayer.update(layer, key, value)
+        # Stash the layer's prefill tensors AS THEY ARE (views of the projections' token-major output): the reference's
+        # cat-append (cache:129) would copy them into head-major tensors, and the factorisation reads token-major layer
+        # tensors in place (no gather, no packed copy).  A grouped layer sees exactly one prefill call (checked above).
+        if not layer.is_initialized:
+            layer.lazy_initialization(key, value)
+        elif layer.keys is not None and layer.keys.numel() > 0:
+            raise XkvError(f"FakeLayerMergingCache: layer {layer_idx} already holds prefill tokens; chunked prefill of a "
+                           "grouped layer is not supported (the reference assumes a single prefill call, SURVEY.md 9.7)")
+        layer.keys, layer.values = key, value
         if self._should_merge(layer_idx):
             self._merge_cos_sin = (cos, sin, re_apply_rope)
             self.grouped_layer_merging(layer_idx)
@@ -329,6 +338,29 @@ class FakeLayerMergingCache(DynamicCache):
         if fold and layer_idx == st.layer_ids[-1]:
             self._fold_tail(st)
         return out[None, :, None, :]
+
+    @torch.no_grad()
+    def latent_slot(self, key: torch.Tensor, value: torch.Tensor, layer_idx: int) -> Optional[dict]:
+        """Decode step of a layer whose KEY slot is factored and whose VALUE slot stayed dense and needs no RoPE — the MLA
+        layout (reference deepseek_v2.py:217-232: latents in the key slot, rotated k_pe in the value slot,
+        re_apply_rope=False, merge_value off).  Appends the new token to the dense tails and hands the caller the pieces
+        of the layer's cache WITHOUT materialising the latents:
+          A (S, r) token factor of the group, V (D, r) this layer's rows of the right factor (latent_t = V a_t),
+          v_prefix (S, Dv) the dense value slot of the prefill tokens, k_tail (T, D) / v_tail (T, Dv) the decode tokens,
+          extras: a dict that lives as long as the layer's cache entry (callers memoise derived quantities in it).
+        Returns None when the layer is not in that state (the caller then uses update(mode='decode'))."""
+        layer = self._layer(layer_idx)
+        st = layer.group
+        if (st is None or st.factors.key is None or st.factors.value is not None or st.re_apply_rope or st.heads != 1
+                or layer.dense_v is None or key.shape[2] != 1):
+            return None
+        layer.append_tail(key, value)
+        d = st.head_dim
+        rows = slice(layer.index_in_group * d, (layer.index_in_group + 1) * d)
+        fk = st.factors.key
+        n_tok, t = layer.prefill_len, layer.tail_len
+        return {"A": fk.A_storage[:n_tok], "V": fk.V[rows], "v_prefix": layer.dense_v[0, 0, :n_tok],
+                "k_tail": layer.tail_k[0, 0, :t], "v_tail": layer.tail_v[0, 0, :t], "extras": layer.extras}
 
     @torch.no_grad()
     def _fold_tail(self, st: "_GroupState") -> None:

@@ -127,8 +127,89 @@ def workspace_bytes(batch: int, m: int, n: int, rank: int, opts: Optional[Factor
     return int(_lib.load().xkv_factorize_workspace_bytes(batch, m, n, rank, C.byref(o)))
 
 
+def layer_rows(t: torch.Tensor) -> Optional[torch.Tensor]:
+    """(S, H*D) row-major view of a (1, H, S, D) layer tensor whose memory is token-major (what HF produces:
+    ``proj(x).view(b, s, H, D).transpose(1, 2)``), or None when the layout is different (then the gather kernel runs)."""
+    if t.dim() != 4 or t.shape[0] != 1 or t.dtype != torch.bfloat16:
+        return None
+    _, h, s, d = t.shape
+    sb, sh, ss, sd = t.stride()
+    if sd != 1 or (h > 1 and sh != d) or ss < h * d or ss % 8 or (t.data_ptr() & 15) or (h * d) % 64:
+        return None
+    return t.as_strided((s, h * d), (ss, 1))
+
+
+def factorize_groups(groups: Sequence[Sequence[torch.Tensor]], rank: int, opts: Optional[FactorizeOptions] = None,
+                     workspace: Optional[torch.Tensor] = None, extra_rows: int = 0) -> List[Factors]:
+    """Factorise layer groups IN PLACE: groups[g][i] is the (S, H*D) row-major matrix of layer i of group g
+    (:func:`layer_rows`); the group matrix is their column-wise concatenation — the reference's ``torch.cat(dim=1)`` +
+    ``transpose(1, 2).reshape`` (cache:170-171, :13-14) — and is never materialised: the Gram pass and the projection pass
+    read the layer tensors through per-layer tensor maps (xkv_factorize_groups)."""
+    opts = opts or FactorizeOptions()
+    if len(groups) == 0:
+        return []
+    lib = _lib.load()
+    nl = len(groups[0])
+    m, lc = groups[0][0].shape
+    ld = groups[0][0].stride(0)
+    dev = groups[0][0].device
+    for grp in groups:
+        if len(grp) != nl:
+            raise XkvError("factorize_groups: equally sized groups required")
+        for t in grp:
+            if (not t.is_cuda or t.dtype != torch.bfloat16 or tuple(t.shape) != (m, lc) or t.stride() != (ld, 1)
+                    or t.data_ptr() & 15):
+                raise XkvError("factorize_groups: layers must be equally shaped row-major bf16 CUDA matrices, 16-byte aligned")
+    n = nl * lc
+    r = int(rank)
+    co = _c_options(opts)
+    per_call = max(1, min(_lib.MAX_BATCH, 64 // nl))     # XKV_MAX_LAYER_MAPS layer matrices per launch
+    chunk = min(len(groups), per_call)
+    need = int(lib.xkv_factorize_workspace_bytes(chunk, m, n, r, C.byref(co)))
+    if need == 0:
+        raise XkvError(lib.xkv_last_error().decode() or "factorize: invalid problem")
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    nsig = int(lib.xkv_factorize_sigma_count(r, C.byref(co)))
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    out: List[Factors] = []
+    all_events = []
+    for lo in range(0, len(groups), chunk):
+        part = groups[lo:lo + chunk]
+        nb = len(part)
+        a_store = [torch.empty(m + extra_rows, r, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
+        a = [t[:m] for t in a_store]
+        vt = [torch.empty(r, n, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
+        v = [torch.empty(n, r, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
+        sig = [torch.empty(nsig, dtype=torch.float32, device=dev) if nsig else None for _ in range(nb)]
+        ev_arr = None
+        if opts.profile:
+            events = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+            for e in events:
+                e.record()
+            ev_arr = (C.c_void_p * 7)(*[e.cuda_event for e in events])
+            all_events.append(events)
+        flat = [t for grp in part for t in grp]
+        _lib.check(lib.xkv_factorize_groups(
+            ops._ptr_array(flat), nb, nl, lc, m, ld, r, C.byref(co), ops._ptr_array(a), ops._ptr_array(vt),
+            ops._ptr_array(v), ops._ptr_array(sig) if nsig else None, C.c_void_p(workspace.data_ptr()),
+            workspace.numel() * workspace.element_size(), ev_arr, stream))
+        for b in range(nb):
+            out.append(Factors(A=a[b], Vt=vt[b], V=v[b], rank=r, sigma_lead=sig[b], A_storage=a_store[b]))
+    if opts.profile:
+        torch.cuda.synchronize()
+        timings: Dict[str, float] = {}
+        for events in all_events:
+            for i, name in enumerate(_STAGES):
+                timings[name] = timings.get(name, 0.0) + events[i].elapsed_time(events[i + 1])
+        for f in out:
+            f.timings = timings
+    return out
+
+
 def factorize_batch(xs: Sequence[torch.Tensor], rank: int, opts: Optional[FactorizeOptions] = None,
-                    workspace: Optional[torch.Tensor] = None, process_group=None, extra_rows: int = 0) -> List[Factors]:
+                    workspace: Optional[torch.Tensor] = None, process_group=None, extra_rows: int = 0,
+                    comm_events: Optional[list] = None) -> List[Factors]:
     """Factorise a batch of equally-shaped token-major matrices (m x n bf16) at rank `rank`.
 
     One call into the library's stream-ordered driver (xkv_factorize_batch); batches larger than the
@@ -136,7 +217,8 @@ def factorize_batch(xs: Sequence[torch.Tensor], rank: int, opts: Optional[Factor
 
     With `process_group` (torch.distributed, NCCL) the inputs are the LOCAL token shards of matrices whose
     rows are split over the group's ranks: the local Gram matrices are summed with one all-reduce, every
-    rank derives the same right factor, and `A` holds the local rows only."""
+    rank derives the same right factor, and `A` holds the local rows only.  `comm_events`: optional
+    [start, end] CUDA events (enable_timing) recorded around the all-reduce; the payload bytes are appended."""
     opts = opts or FactorizeOptions()
     if len(xs) == 0:
         return []
@@ -188,9 +270,22 @@ def factorize_batch(xs: Sequence[torch.Tensor], rank: int, opts: Optional[Factor
         else:
             import torch.distributed as dist
 
+            # the only data-path collective: all-reduce(sum) of the local Gram matrices, upper triangles only
+            # (n^2 / 2 + 16 n floats per matrix instead of n^2: the Gram is symmetric)
             grams = torch.empty(nb, n, n, dtype=torch.float32, device=dev)
             call(1, list(grams))
-            dist.all_reduce(grams, op=dist.ReduceOp.SUM, group=process_group)
+            per = ops.gram_packed_elems(n)
+            packed = torch.empty(nb, per, dtype=torch.float32, device=dev)
+            for b in range(nb):
+                ops.gram_pack_upper(grams[b], packed[b])
+            if comm_events is not None:
+                comm_events[0].record()
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=process_group)
+            if comm_events is not None:
+                comm_events[1].record()
+                comm_events.append(packed.numel() * packed.element_size())
+            for b in range(nb):
+                ops.gram_unpack_upper(packed[b], grams[b])
             call(2, list(grams))
         for b in range(nb):
             out.append(Factors(A=a[b], Vt=vt[b], V=v[b], rank=r, sigma_lead=sig[b], A_storage=a_store[b]))

@@ -101,11 +101,15 @@ def make_problem(
     split_k: int = 1,
     split_stride: int = 0,
     accum_phases: int = 1,
+    a_layers: Optional[Sequence[torch.Tensor]] = None,
+    b_layers: Optional[Sequence[torch.Tensor]] = None,
 ) -> GemmProblem:
     """Describe D = sum_t A[ta] @ B[tb]^T.  A limbs: (M, K) row-major, or (K, M) if a_mn_major;
     B limbs: (N, K) row-major, or (K, N) if b_mn_major. `out`: fp32/bf16, (M, N) or (N, M) if transposed;
     with split_k > 1 `out` is the first of split_k slabs `split_stride` elements apart.  accum_phases > 1: every
-    CTA accumulates its k range in that many pieces on the tensor core and sums the pieces in fp32 (fp32 output)."""
+    CTA accumulates its k range in that many pieces on the tensor core and sums the pieces in fp32 (fp32 output).
+    a_layers / b_layers: the operand is the column-wise concatenation of these equally shaped row-major matrices, read in
+    place (a layer group's K / V without the gather); `a_limbs` / `b_limbs` are then ignored (pass [])."""
     p = GemmProblem()
     p.M, p.N, p.K = M, N, K
     p.num_terms = len(terms)
@@ -115,11 +119,21 @@ def make_problem(
         b = b_limbs[i] if i < len(b_limbs) else None
         p.A[i] = a.data_ptr() if a is not None else None
         p.B[i] = b.data_ptr() if b is not None else None
-    for t in list(a_limbs) + list(b_limbs):
+    for t in list(a_limbs) + list(b_limbs) + list(a_layers or []) + list(b_layers or []):
         if t is not None and (t.dtype != torch.bfloat16 or t.stride(-1) != 1):
             raise _lib.XkvError("gemm operands must be bf16 with unit inner stride")
-    p.lda = a_limbs[0].stride(0)
-    p.ldb = b_limbs[0].stride(0)
+    for side, layers in (("a", a_layers), ("b", b_layers)):
+        if not layers:
+            continue
+        if len(layers) > _lib.MAX_GROUP_LAYERS or any(t.shape != layers[0].shape or t.stride() != layers[0].stride() for t in layers):
+            raise _lib.XkvError("gemm: layered operands must be equally shaped and strided (at most 16 layers)")
+        setattr(p, side + "_layers", len(layers))
+        p.layer_cols = layers[0].shape[1]
+        arr = p.A_layer if side == "a" else p.B_layer
+        for i, t in enumerate(layers):
+            arr[i] = t.data_ptr()
+    p.lda = (a_layers[0] if a_layers else a_limbs[0]).stride(0)
+    p.ldb = (b_layers[0] if b_layers else b_limbs[0]).stride(0)
     for t, (ta, tb) in enumerate(terms):
         p.term_a[t], p.term_b[t] = ta, tb
     if out.dtype not in (torch.float32, torch.bfloat16) or out.stride(-1) != 1:
@@ -180,6 +194,33 @@ def symmetrize_split_bf16(slabs: Sequence[torch.Tensor], hi: Sequence[torch.Tens
     check(_lib.load().xkv_symmetrize_split_bf16(_ptr_array(slabs), len(slabs), s, slabs[0].stride(0), n,
                                                 slabs[0].stride(1), _ptr_array(hi), _ptr_array(mid), _ptr_array(lo),
                                                 hi[0].stride(0), _stream()))
+
+
+def gram_packed_elems(n: int) -> int:
+    """Floats of the packed upper triangle of an n x n symmetric matrix (row r keeps its columns from 32 * (r // 32))."""
+    return int(_lib.load().xkv_gram_packed_elems(n))
+
+
+def gram_pack_upper(full: torch.Tensor, packed: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Upper triangle of a symmetric (n, n) fp32 matrix, packed: the payload of the token-sharded Gram all-reduce."""
+    _require_cuda(full, packed)
+    n = full.shape[0]
+    if full.dtype != torch.float32 or full.shape != (n, n) or full.stride(1) != 1:
+        raise _lib.XkvError("gram_pack_upper: square fp32 matrix with unit inner stride required")
+    if packed is None:
+        packed = torch.empty(gram_packed_elems(n), dtype=torch.float32, device=full.device)
+    check(_lib.load().xkv_gram_pack_upper(_ptr(full), n, full.stride(0), _ptr(packed), _stream()))
+    return packed
+
+
+def gram_unpack_upper(packed: torch.Tensor, full: torch.Tensor) -> torch.Tensor:
+    """Inverse of gram_pack_upper: fills `full` (n, n) symmetrically (lower triangle = mirrored upper)."""
+    _require_cuda(full, packed)
+    n = full.shape[0]
+    if packed.dtype != torch.float32 or packed.numel() < gram_packed_elems(n) or not packed.is_contiguous():
+        raise _lib.XkvError("gram_unpack_upper: contiguous fp32 buffer of gram_packed_elems(n) floats required")
+    check(_lib.load().xkv_gram_unpack_upper(_ptr(packed), n, _ptr(full), full.stride(0), _stream()))
+    return full
 
 
 def fill_gaussian_bf16(out: torch.Tensor, seed: int) -> None:
@@ -338,6 +379,36 @@ def decode_attention(q: torch.Tensor, a_k: torch.Tensor, vk_layer: torch.Tensor,
         cos.stride(0) if cos is not None else 0, _ptr(k_tail if t else None), _ptr(v_tail if t else None), t, sh, st,
         C.c_float(scale), _ptr(out), C.c_void_p(workspace.data_ptr()), workspace.numel(), _stream(), _ptr(lse_out)))
     return out
+
+
+def decode_absorbed(q_hat: torch.Tensor, a: torch.Tensor, scale: float, row_scale: Optional[torch.Tensor] = None,
+                    bias_q: Optional[torch.Tensor] = None, bias_k: Optional[torch.Tensor] = None,
+                    workspace: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Absorbed attention over a token factor (MLA latents).  q_hat (Hq, r) bf16: the query folded into the rank space;
+    a (S, r) bf16; row_scale (S,) fp32 or None; bias_q (Hq, d) / bias_k (S, d) bf16 or None (the RoPE part).
+    Returns (u (Hq, r) fp32 = sum_t softmax(s)[h, t] row_scale[t] a[t], lse (Hq,) fp32) with
+    s[h, t] = scale * (row_scale[t] * q_hat[h] . a[t] + bias_q[h] . bias_k[t])."""
+    _require_cuda(q_hat, a, row_scale, bias_q, bias_k, workspace)
+    hq, r = q_hat.shape
+    s = a.shape[0]
+    for name, x in (("q_hat", q_hat), ("a", a), ("bias_q", bias_q), ("bias_k", bias_k)):
+        if x is not None and (x.dtype != torch.bfloat16 or x.stride(-1) != 1):
+            raise _lib.XkvError(f"decode_absorbed: {name} must be bf16 with unit inner stride")
+    if a.shape[1] != r or not q_hat.is_contiguous() or (bias_q is not None and not bias_q.is_contiguous()):
+        raise _lib.XkvError("decode_absorbed: q_hat (Hq, r) / bias_q must be contiguous and match a (S, r)")
+    if row_scale is not None and (row_scale.dtype != torch.float32 or not row_scale.is_contiguous() or row_scale.numel() < s):
+        raise _lib.XkvError("decode_absorbed: row_scale must be a contiguous fp32 vector of S entries")
+    lib = _lib.load()
+    need = int(lib.xkv_decode_absorbed_workspace_bytes(hq, s, r))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=a.device)
+    u = torch.empty(hq, r, dtype=torch.float32, device=a.device)
+    lse = torch.empty(hq, dtype=torch.float32, device=a.device)
+    check(lib.xkv_decode_absorbed(_ptr(q_hat), hq, _ptr(a), a.stride(0), r, s, _ptr(row_scale), _ptr(bias_q), _ptr(bias_k),
+                                  bias_k.stride(0) if bias_k is not None else 0,
+                                  bias_q.shape[1] if bias_q is not None else 0, C.c_float(scale), _ptr(u), _ptr(lse),
+                                  C.c_void_p(workspace.data_ptr()), workspace.numel(), _stream()))
+    return u, lse
 
 
 def rope_bf16_(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
