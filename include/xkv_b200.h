@@ -303,6 +303,18 @@ XKV_API int xkv_rope_bf16(void* x, int64_t ld_row, int rows, int H, int D, const
 XKV_API size_t xkv_append_workspace_bytes(int T, int n, int r);
 XKV_API int xkv_append_project(const void* x_new, int64_t ldx, int T, const void* V, int64_t ldv, int n, int r,
                                void* a_out, int64_t lda, void* workspace, size_t workspace_bytes, void* stream);
+/* Several projections in ONE launch (a group's K and V factor: the step is a few microseconds of HBM time, so launches
+ * dominate otherwise).  workspace_bytes >= the sum of xkv_append_workspace_bytes(T, n, r) over the problems. */
+#define XKV_APPEND_MAX_PROBLEMS 4
+typedef struct xkv_append_problem {
+  const void* x_new;   /* T x n bf16, row stride ldx */
+  const void* V;       /* n x r bf16, row stride ldv */
+  void* a_out;         /* T x r bf16, row stride lda */
+  int64_t ldx, ldv, lda;
+  int32_t n, r;
+} xkv_append_problem;
+XKV_API int xkv_append_project_batch(const xkv_append_problem* problems_host, int count, int T, void* workspace,
+                                     size_t workspace_bytes, void* stream);
 
 /* ---- SLERP / MiniCache branch (layer_merge_impl == "slerp"): replaces fake_minicache_merge -----------
  * cache:32-100, called at cache:183-197 on two layers' rows (rows x d bf16, row stride ld). e1 / e2 receive the

@@ -20,6 +20,27 @@ def test_append_project_matches_torch(T, n, r):
     assert (got.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("T", [1, 8, 11])
+def test_append_project_many_is_one_launch_and_matches_the_single_calls(T):
+    """A group's K and V projection in one launch (config 2's shapes): bit-identical to two single calls."""
+    from xkv_b200 import ops
+
+    torch.manual_seed(T)
+    n = 4096
+    xs = [torch.randn(T, n, device="cuda").bfloat16() for _ in range(2)]
+    vs = [(torch.randn(n, r, device="cuda") / n ** 0.5).bfloat16() for r in (512, 768)]
+    outs = [torch.empty(T, r, dtype=torch.bfloat16, device="cuda") for r in (512, 768)]
+    before = ops.launch_count()
+    ops.append_project_many(xs, vs, outs)
+    assert ops.launch_count() - before == (T + 7) // 8
+    singles = [ops.append_project(x, v) for x, v in zip(xs, vs)]
+    torch.cuda.synchronize()
+    for o, s1, x, v in zip(outs, singles, xs, vs):
+        assert torch.equal(o, s1)
+        ref = x.float() @ v.float()
+        assert (o.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+
+
 def test_projected_token_reconstructs_like_prefill_tokens():
     from xkv_b200 import factorize, ops, synthetic
 

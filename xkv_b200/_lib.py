@@ -55,6 +55,13 @@ class GemmProblem(C.Structure):
     ]
 
 
+class AppendProblem(C.Structure):
+    """Mirror of ``xkv_append_problem`` (include/xkv_b200.h)."""
+
+    _fields_ = [("x_new", C.c_void_p), ("V", C.c_void_p), ("a_out", C.c_void_p), ("ldx", C.c_int64), ("ldv", C.c_int64),
+                ("lda", C.c_int64), ("n", C.c_int32), ("r", C.c_int32)]
+
+
 class FactorizeOptions(C.Structure):
     """Mirror of ``xkv_factorize_options`` (include/xkv_b200.h)."""
 
@@ -132,6 +139,7 @@ SIGNATURES = {
     "xkv_rope_bf16": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "xkv_append_workspace_bytes": (_sz, [_i, _i, _i]),
     "xkv_append_project": (_i, [_vp, _i64, _i, _vp, _i64, _i, _i, _vp, _i64, _vp, _sz, _vp]),
+    "xkv_append_project_batch": (_i, [C.POINTER(AppendProblem), _i, _i, _vp, _sz, _vp]),
     "xkv_slerp_workspace_bytes": (_sz, [_i64]),
     "xkv_slerp_merge": (_i, [_vp, _vp, _i64, _i, _i64, _f, _f, _vp, _vp, _i64, _vp, _sz, _vp]),
     "xkv_gemm_problem_size": (C.c_size_t, []),

@@ -380,8 +380,8 @@ class FakeLayerMergingCache(DynamicCache):
             return   # capacity exhausted: keep the tokens dense (still exact)
         xk = ops.pack_group([l.tail_kpre[:, :, :t] for l in layers])[0]
         xv = ops.pack_group([l.tail_v[:, :, :t] for l in layers])[0]
-        ops.append_project(xk, fk.V, out=fk.A_storage[st.length: st.length + t])
-        ops.append_project(xv, fv.V, out=fv.A_storage[st.length: st.length + t])
+        ops.append_project_many([xk, xv], [fk.V, fv.V], [fk.A_storage[st.length: st.length + t],
+                                                         fv.A_storage[st.length: st.length + t]])
         if st.re_apply_rope and st.cos is not None:
             st.cos[st.length: st.length + t] = torch.stack([c for c, _ in st.tail_rope])
             st.sin[st.length: st.length + t] = torch.stack([x for _, x in st.tail_rope])

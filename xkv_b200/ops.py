@@ -443,6 +443,29 @@ def append_project(x_new: torch.Tensor, v: torch.Tensor, out: Optional[torch.Ten
     return out
 
 
+def append_project_many(xs: Sequence[torch.Tensor], vs: Sequence[torch.Tensor], outs: Sequence[torch.Tensor],
+                        workspace: Optional[torch.Tensor] = None) -> None:
+    """outs[i] (T, r_i) = xs[i] (T, n_i) @ vs[i] (n_i, r_i) for up to 4 projections in ONE launch (a group's K and V
+    factor when decode tokens are folded)."""
+    _require_cuda(*xs, *vs, *outs, workspace)
+    lib = _lib.load()
+    t = xs[0].shape[0]
+    probs = (_lib.AppendProblem * len(xs))()
+    need = 0
+    for i, (x, v, o) in enumerate(zip(xs, vs, outs)):
+        if (x.dtype != torch.bfloat16 or v.dtype != torch.bfloat16 or o.dtype != torch.bfloat16 or x.stride(1) != 1
+                or v.stride(1) != 1 or o.stride(1) != 1 or x.shape[0] != t or x.shape[1] != v.shape[0]
+                or tuple(o.shape) != (t, v.shape[1])):
+            raise _lib.XkvError("append_project_many: bf16 (T, n) @ (n, r) -> (T, r) with unit inner strides required")
+        probs[i].x_new, probs[i].V, probs[i].a_out = x.data_ptr(), v.data_ptr(), o.data_ptr()
+        probs[i].ldx, probs[i].ldv, probs[i].lda = x.stride(0), v.stride(0), o.stride(0)
+        probs[i].n, probs[i].r = v.shape[0], v.shape[1]
+        need += int(lib.xkv_append_workspace_bytes(t, v.shape[0], v.shape[1]))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=vs[0].device)
+    check(lib.xkv_append_project_batch(probs, len(xs), t, C.c_void_p(workspace.data_ptr()), workspace.numel(), _stream()))
+
+
 # ---------------------------------------------------------------------------------------------
 # SLERP / MiniCache branch
 # ---------------------------------------------------------------------------------------------
