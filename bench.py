@@ -501,15 +501,17 @@ def bench_strong(ctx, c, streams, no_graph, ms_weak):
 
 
 def bench_token_sharded(ctx):
-    """configs[3]: Llama-3.1-70B-shaped KV, xKV-8 at 128K.  One K and one V group matrix (131072 x 8192, rank 1024 /
-    1536; the cache has 10 such pairs) with the token rows split over the ranks (parallel.token_shard).  Every rank runs
-    the Gram of ITS rows, the packed upper triangles are summed with ONE NCCL all-reduce per matrix, every rank derives
-    the same right factor and projects its own rows."""
+    """configs[3]: Llama-3.1-70B-shaped KV (80 layers, 8 KV heads x 128), xKV-8 at 128K: the WHOLE cache, 10 groups = 20
+    matrices 131072 x 8192 (K rank 1024, V rank 1536), with the token rows of every matrix split over the ranks
+    (parallel.token_shard).  factorize_token_sharded: every rank runs the Gram of ITS rows, the packed upper triangle of
+    matrix i is summed onto rank i mod N (NCCL reduce), that rank alone derives the right factor and broadcasts it, every
+    rank projects its own rows.  At N = 1 the same 20 matrices go through the single-GPU driver."""
     from xkv_b200 import factorize, parallel
 
     torch, dist = ctx.torch, ctx.dist
     c = CONFIGS[4]
     S, n = c["tokens"], c["group"] * c["heads"] * c["head_dim"]
+    ngroups = len(group_sizes(c))
     b, e = parallel.token_shard(S, ctx.world, ctx.rank)
     rows = e - b
 
@@ -529,37 +531,47 @@ def bench_token_sharded(ctx):
             out[lo:hi] = x.to(torch.bfloat16)
         return out
 
-    xk, xv = shard(c["alpha_k"], 41), shard(c["alpha_v"], 42)
+    jobs = []
+    for g in range(ngroups):
+        jobs.append((shard(c["alpha_k"], 41 + 2 * g), c["rank_k"]))
+        jobs.append((shard(c["alpha_v"], 42 + 2 * g), c["rank_v"]))
     group = dist.group.WORLD if ctx.world > 1 else None
     opts = factorize.FactorizeOptions()
-    ws = torch.empty(max(factorize.workspace_bytes(1, rows, n, c["rank_k"], opts),
-                         factorize.workspace_bytes(1, rows, n, c["rank_v"], opts)), dtype=torch.uint8, device=ctx.dev)
     comm = {"ms": 0.0, "bytes": 0}
+    ws = None
+    if group is None:
+        ws = torch.empty(max(factorize.workspace_bytes(ngroups, rows, n, r, opts) for _, r in jobs[:2]), dtype=torch.uint8,
+                         device=ctx.dev)
 
     def step(timed=False):
-        for x, r in ((xk, c["rank_k"]), (xv, c["rank_v"])):
-            ev = ([torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
-                  if (timed and group is not None) else None)
-            factorize.factorize_batch([x], r, opts, workspace=ws, process_group=group, comm_events=ev)
-            if ev is not None:
-                torch.cuda.synchronize()
-                comm["ms"] += ev[0].elapsed_time(ev[1])
-                comm["bytes"] += ev[2]
+        if group is None:     # one GPU: the K matrices in one batch, the V matrices in another
+            for r in (c["rank_k"], c["rank_v"]):
+                factorize.factorize_batch([x for x, rr in jobs if rr == r], r, opts, workspace=ws)
+            return
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if timed else None
+        factorize.factorize_token_sharded(jobs, group, opts, comm_events=ev)
+        if ev is not None:
+            torch.cuda.synchronize()
+            comm["ms"] += ev[0].elapsed_time(ev[1])
+            comm["bytes"] += ev[2]
 
-    ms = ctx.time_steps(step, 3, warmup=1)
+    ms = ctx.time_steps(step, 2, warmup=1)
     step(timed=True)    # one more step with events around the collectives (synchronises, so outside the timed loop)
     ar_ms = ctx.max_ms(comm["ms"])
-    kv = 2 * S * n * 2
+    kv = kv_bytes_of(c)
     rec = {
-        "workload": f"{c['model']}, ONE xKV-8 group (K and V matrices {S} x {n}, rank {c['rank_k']} / {c['rank_v']}) of the "
-                    f"10 the 80-layer cache has, token rows split over {ctx.world} rank(s)",
-        "scaling": "strong", "tokens_per_rank": rows, "ms_per_step": ms, "value": kv / (ms * 1e-3) / 1e9, "unit": "GB/s",
-        "collective": "NCCL all-reduce(sum, fp32) of the packed upper triangle of each n x n Gram" if group is not None else None,
-        "allreduce_bytes_per_step": comm["bytes"], "allreduce_full_gram_bytes": 2 * n * n * 4,
-        "allreduce_ms_per_step": ar_ms, "allreduce_share": (ar_ms / ms) if ms > 0 else None,
-        "allreduce_GBps": (comm["bytes"] / (ar_ms * 1e-3) / 1e9) if ar_ms > 0 else None,
+        "workload": f"{c['model']}, {c['layers']} layers, xKV-8 at {S} tokens: {len(jobs)} matrices {S} x {n} (rank {c['rank_k']} / "
+                    f"{c['rank_v']}), token rows split over {ctx.world} rank(s)",
+        "scaling": "strong", "tokens_per_rank": rows, "matrices": len(jobs), "ms_per_step": ms,
+        "value": kv / (ms * 1e-3) / 1e9, "unit": "GB/s",
+        "collective": ("NCCL all-reduce(sum, fp32) of the packed upper triangle of each n x n Gram (overlapping the next Gram) + "
+                       "broadcast of the right factor (bf16) from the rank that derived it") if group is not None else None,
+        "collective_bytes_per_step": comm["bytes"], "full_gram_allreduce_bytes": len(jobs) * n * n * 4,
+        "gram_to_factors_ms_per_step": ar_ms,
+        "note": "gram_to_factors_ms: from the first Gram to the last right factor received (Grams, collectives and the owners' "
+                "small-matrix stages overlap inside it); the projections follow",
     }
-    del xk, xv, ws
+    del jobs, ws
     torch.cuda.empty_cache()
     return rec
 

@@ -185,7 +185,9 @@ XKV_API int xkv_sqrt_clamp(const float* in, float* out, int count, void* stream)
  * Token-sharded use (rows of X split over GPUs): phase 1 writes each matrix's LOCAL Gram X_p^T X_p (n x n fp32,
  * symmetric) to gram_host[b] and returns; the caller all-reduces those buffers (NCCL) and calls again with
  * phase 2, which resumes from the reduced Gram and projects the local rows A_p = X_p V. phase 0 (gram_host may
- * be NULL) does everything on one device. */
+ * be NULL) does everything on one device.  Phases 3 and 4 split phase 2 so that the small-matrix stages of different
+ * matrices can run on different ranks: phase 3 derives Vt / V from gram_host[b] and stops (X_host / A_host may be NULL);
+ * phase 4 only projects, A = X V, with the Vt the caller supplies (e.g. received from the rank that ran phase 3). */
 typedef struct xkv_factorize_options {
   int32_t power_iters;    /* power steps on G after the range finder (default 4) */
   int32_t oversample;     /* extra sketch columns; sketch width l = round_up(rank + oversample, 64) */

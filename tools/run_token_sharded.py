@@ -31,6 +31,26 @@ ok = err_shard <= 1.002 * err_full
 if rank == 0:
     print(f"token-sharded x{world}: rel err {err_shard:.6f} vs single-GPU {err_full:.6f}; max|Vt diff| {same_v:.3e}; "
           f"{'OK' if ok else 'FAIL'}")
+# ---- the small-matrix stages distributed over the ranks (reduce onto the owner, broadcast of the right factor) ----
+x2 = synthetic.group_matrix(S, n, 0.5, seed=44, device=dev)
+jobs = [(x[b:e].contiguous(), r), (x2[b:e].contiguous(), 384), (x[b:e].contiguous(), 192)]
+fs = factorize.factorize_token_sharded(jobs, dist.group.WORLD)
+torch.cuda.synchronize()
+for (xl, rr), f, full_x in zip(jobs, fs, (x, x2, x)):
+    (f1,) = factorize.factorize_batch([full_x], rr)
+    e1 = (torch.linalg.norm(full_x.double() - f1.reconstruct().double()) / torch.linalg.norm(full_x.double())).item()
+    num = torch.linalg.norm(xl.double() - f.reconstruct().double()) ** 2
+    dist.all_reduce(num)
+    e2 = (num.sqrt() / torch.linalg.norm(full_x.double())).item()
+    vt_all = [torch.empty_like(f.Vt) for _ in range(world)]
+    dist.all_gather(vt_all, f.Vt)
+    same = all(torch.equal(vt_all[0], v) for v in vt_all)
+    okd = e2 <= 1.002 * e1 and same
+    ok = ok and okd
+    if rank == 0:
+        print(f"distributed small stages x{world}, rank {rr}: rel err {e2:.6f} vs single-GPU {e1:.6f}; same Vt on every rank: {same}; "
+              f"{'OK' if okd else 'FAIL'}")
+
 # ---- decode over the token shards: K and V factors of one 4-layer group (8 kv heads x 64), layer 1 of the group ----
 import math
 from xkv_b200 import ops

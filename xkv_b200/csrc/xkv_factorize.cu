@@ -255,9 +255,12 @@ static int factorize_impl(const void* const* X_host, int layers, int layer_cols,
     o = *opts;
   else
     xkv_factorize_default_options(&o);
-  XKV_REQUIRE(X_host && A_host && Vt_host && V_host && workspace, "factorize: null argument");
-  XKV_REQUIRE(phase >= 0 && phase <= 2, "factorize: phase must be 0 (all), 1 (Gram only) or 2 (resume from Gram)");
-  XKV_REQUIRE(phase == 0 || gram_host != nullptr, "factorize: phases 1/2 need the per-matrix Gram buffers");
+  XKV_REQUIRE(phase >= 0 && phase <= 4,
+              "factorize: phase must be 0 (all), 1 (Gram only), 2 (resume from Gram), 3 (right factor from Gram) or 4 (projection)");
+  XKV_REQUIRE(workspace && Vt_host && (phase == 1 || phase == 4 || V_host) && (phase == 3 || X_host) &&
+                  (phase == 1 || phase == 3 || A_host),
+              "factorize: null argument");
+  XKV_REQUIRE(phase == 0 || phase == 4 || gram_host != nullptr, "factorize: phases 1 / 2 / 3 need the per-matrix Gram buffers");
   static thread_local Plan P;
   Bump bump{static_cast<char*>(workspace), 0, workspace_bytes, false};
   XKV_TRY(make_plan(P, bump, batch, m, n, rank, o));
@@ -278,10 +281,27 @@ static int factorize_impl(const void* const* X_host, int layers, int layer_cols,
   xkv_set_launch_predicate(nullptr);   // a call that failed half-way must not leave this thread's launches predicated
   XKV_TRY(mark());  // 0: start
 
+  // ---- 7. projection A = X V (second and last pass over X); phase 4 runs only this, on a right factor the caller supplies ----
+  auto project = [&]() -> int {
+    for (int b = 0; b < B; ++b) {
+      const void* x0 = layers > 0 ? X_host[static_cast<size_t>(b) * layers] : X_host[b];
+      xkv_gemm_problem p = problem(x0, nullptr, nullptr, ldx, 0, Vt_host[b], nullptr, nullptr, nn, 0, A_host[b], r, m, r, n, 1);
+      if (layers > 0) {
+        p.a_layers = layers;
+        p.layer_cols = layer_cols;
+        for (int i = 0; i < layers; ++i) p.A_layer[i] = X_host[static_cast<size_t>(b) * layers + i];
+      }
+      p.out_bf16 = 1;
+      ps.push_back(p);
+    }
+    return run_gemms(ps, stream, layers > 0 ? XKV_MAX_LAYER_MAPS / layers : XKV_MAX_GEMM_PROBLEMS);
+  };
+  if (phase == 4) return project();
+
   // ---- 1. Gram matrices and their bf16 limbs ----
   // phase 1 stops after the (local) Gram so that token-sharded callers can all-reduce it; phase 2 resumes
   // from the caller's reduced Gram.
-  if (phase != 2) {
+  if (phase != 2 && phase != 3) {
     for (int b = 0; b < B; ++b) {
       const void* x0 = layers > 0 ? X_host[static_cast<size_t>(b) * layers] : X_host[b];
       xkv_gemm_problem p = problem(x0, nullptr, nullptr, ldx, 1, x0, nullptr, nullptr, ldx, 1,
@@ -317,7 +337,7 @@ static int factorize_impl(const void* const* X_host, int layers, int layer_cols,
     for (int b = 0; b < B; ++b) {
       float* g = gram_host[b];
       XKV_REQUIRE(g != nullptr, "factorize: null Gram buffer %d", b);
-      if (phase != 2)
+      if (phase != 2 && phase != 3)
         XKV_TRY(xkv_reduce_slabs(P.gram_slabs + static_cast<size_t>(b) * P.gs * nn * nn, P.gs, nn * nn, n, n, nn, 1, g, nn,
                                  stream));
       if (phase != 1) XKV_TRY(xkv_split_bf16(g, n, n, nn, P.g_limb[b][0], P.g_limb[b][1], P.g_limb[b][2], nn, stream));
@@ -521,19 +541,8 @@ static int factorize_impl(const void* const* X_host, int layers, int layer_cols,
 
   // ---- 6. right factor in bf16, both layouts ----
   for (int b = 0; b < B; ++b) XKV_TRY(xkv_convert_bf16(cur[b], r, n, nn, Vt_host[b], nn, V_host[b], r, stream));
-  // ---- 7. projection A = X V ----
-  for (int b = 0; b < B; ++b) {
-    const void* x0 = layers > 0 ? X_host[static_cast<size_t>(b) * layers] : X_host[b];
-    xkv_gemm_problem p = problem(x0, nullptr, nullptr, ldx, 0, Vt_host[b], nullptr, nullptr, nn, 0, A_host[b], r, m, r, n, 1);
-    if (layers > 0) {
-      p.a_layers = layers;
-      p.layer_cols = layer_cols;
-      for (int i = 0; i < layers; ++i) p.A_layer[i] = X_host[static_cast<size_t>(b) * layers + i];
-    }
-    p.out_bf16 = 1;
-    ps.push_back(p);
-  }
-  XKV_TRY(run_gemms(ps, stream, layers > 0 ? XKV_MAX_LAYER_MAPS / layers : XKV_MAX_GEMM_PROBLEMS));
+  if (phase == 3) return 0;   // the caller projects later (phase 4), possibly on another rank's rows
+  XKV_TRY(project());
   XKV_TRY(mark());  // 6: projection
   return 0;
 }
