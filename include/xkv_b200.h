@@ -236,6 +236,21 @@ XKV_API int xkv_factorize_groups(const void* const* layer_ptrs_host, int batch, 
                                  int64_t ld_layer, int rank, const xkv_factorize_options* opts, void* const* A_host,
                                  void* const* Vt_host, void* const* V_host, float* const* sigma_host, void* workspace,
                                  size_t workspace_bytes, void* const* stage_events_host, void* stream);
+/* Matrices of DIFFERENT rank in one batch (ranks_host[b]; same shape): a layer group's K and V matrices share every
+ * launch of the latency-bound stages (Cholesky clusters, Jacobi windows, the elementwise kernels), which otherwise run
+ * once per rank value with half the matrices each.  The ranks of a batch must give one Rayleigh-Ritz window width
+ * (always the case when every sketch is at least `window` wide).  sigma / workspace sizes: the _mixed size query. */
+XKV_API size_t xkv_factorize_workspace_bytes_mixed(int batch, int m, int n, const int32_t* ranks_host,
+                                                   const xkv_factorize_options* opts);
+XKV_API int xkv_factorize_groups_mixed(const void* const* layer_ptrs_host, int batch, int layers, int layer_cols, int m,
+                                       int64_t ld_layer, const int32_t* ranks_host, const xkv_factorize_options* opts,
+                                       void* const* A_host, void* const* Vt_host, void* const* V_host,
+                                       float* const* sigma_host, void* workspace, size_t workspace_bytes,
+                                       void* const* stage_events_host, void* stream);
+XKV_API int xkv_factorize_batch_mixed(const void* const* X_host, int batch, int m, int n, int64_t ldx,
+                                      const int32_t* ranks_host, const xkv_factorize_options* opts, void* const* A_host,
+                                      void* const* Vt_host, void* const* V_host, float* const* sigma_host, void* workspace,
+                                      size_t workspace_bytes, void* const* stage_events_host, void* stream);
 XKV_API int xkv_factorize_batch(const void* const* X_host, int batch, int m, int n, int64_t ldx, int rank,
                                 const xkv_factorize_options* opts, void* const* A_host, void* const* Vt_host,
                                 void* const* V_host, float* const* sigma_host, float* const* gram_host,

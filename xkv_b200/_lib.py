@@ -145,6 +145,11 @@ SIGNATURES = {
     "xkv_gemm_problem_size": (C.c_size_t, []),
     "xkv_factorize_groups": (_i, [_pp, _i, _i, _i, _i, _i64, _i, C.POINTER(FactorizeOptions), _pp, _pp, _pp, _pp, _vp, _sz,
                                   _pp, _vp]),
+    "xkv_factorize_workspace_bytes_mixed": (_sz, [_i, _i, _i, _vp, C.POINTER(FactorizeOptions)]),
+    "xkv_factorize_groups_mixed": (_i, [_pp, _i, _i, _i, _i, _i64, _vp, C.POINTER(FactorizeOptions), _pp, _pp, _pp, _pp, _vp,
+                                        _sz, _pp, _vp]),
+    "xkv_factorize_batch_mixed": (_i, [_pp, _i, _i, _i, _i64, _vp, C.POINTER(FactorizeOptions), _pp, _pp, _pp, _pp, _vp, _sz,
+                                       _pp, _vp]),
     "xkv_factorize_batch": (_i, [_pp, _i, _i, _i, _i64, _i, C.POINTER(FactorizeOptions), _pp, _pp, _pp, _pp, _pp, _i,
                                  _vp, _sz, _pp, _vp]),
 }

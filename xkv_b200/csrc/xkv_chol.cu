@@ -45,7 +45,8 @@ struct CholFusedParams {
   __nv_bfloat16* hi[XKV_MAX_BATCH];
   __nv_bfloat16* mid[XKV_MAX_BATCH];
   __nv_bfloat16* lo[XKV_MAX_BATCH];
-  int l, nblk;
+  int l, nblk;                 // uniform size (grid sizing, cluster size)
+  int l_b[XKV_MAX_BATCH];      // per-matrix size (0: the uniform l); see batch_rows_override
   long long ld, ld_limb;
   float pivot_floor, shift;
   const int* run_if;   // optional per-matrix device predicate (xkv_set_launch_predicate): the whole cluster exits
@@ -272,7 +273,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chol_cluster_kernel(const __gri
   float* S = p.S[blockIdx.y];
   float* Li = p.Linv[blockIdx.y];
   const long long ld = p.ld;
-  const int nblk = p.nblk;
+  const int lsize = p.l_b[blockIdx.y] > 0 ? p.l_b[blockIdx.y] : p.l;
+  const int nblk = lsize / CB;
   const int tid = threadIdx.x;
   auto blk = [&](float* base, int bi, int bj) -> float* {
     return base + static_cast<long long>(bi) * CB * ld + static_cast<long long>(bj) * CB;
@@ -418,8 +420,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chol_cluster_kernel(const __gri
   __nv_bfloat16* hi = p.hi[blockIdx.y];
   __nv_bfloat16* mid = p.mid[blockIdx.y];
   __nv_bfloat16* lo = p.lo[blockIdx.y];
-  const int l4 = p.l >> 2;
-  for (int r = c; r < p.l; r += CL) {
+  const int l4 = lsize >> 2;
+  for (int r = c; r < lsize; r += CL) {
     const int bi = r / CB;
     float* row = Li + static_cast<long long>(r) * ld;
     for (int q = tid; q < l4; q += CH_THREADS) {
@@ -466,6 +468,14 @@ extern "C" int xkv_cholesky_inverse_limbs(float* const* S_host, float* const* Li
     p.hi[b] = hi_host ? static_cast<__nv_bfloat16*>(hi_host[b]) : nullptr;
     p.mid[b] = mid_host ? static_cast<__nv_bfloat16*>(mid_host[b]) : nullptr;
     p.lo[b] = lo_host ? static_cast<__nv_bfloat16*>(lo_host[b]) : nullptr;
+  }
+  {
+    const int* ov = batch_rows_override();
+    for (int b = 0; b < XKV_MAX_BATCH; ++b) {
+      p.l_b[b] = (ov != nullptr && b < batch) ? ov[b] : 0;
+      XKV_REQUIRE(p.l_b[b] % CB == 0 && p.l_b[b] <= ld, "cholesky: per-matrix size %d must be a multiple of %d within ld", p.l_b[b], CB);
+      if (p.l_b[b] > l) l = p.l_b[b];
+    }
   }
   p.l = l;
   p.nblk = l / CB;

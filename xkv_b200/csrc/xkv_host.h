@@ -22,6 +22,17 @@ extern std::atomic<long long> g_launch_count;
 // rdiag update): matrix b is skipped when flags[b] == 0.  nullptr (the default) = unconditional.
 const int*& launch_predicate();
 
+// Per-matrix row counts of the calling thread's next batched launches (normalise, limb split, square slab reduction,
+// Cholesky, rdiag / pass-flag / Ritz-shift updates): with a non-null HOST array rows[b] matrix b has rows[b] rows (and
+// columns, where the matrix is square) instead of the call's uniform `rows`, which then only sizes the grid (pass the
+// maximum).  Lets one launch carry matrices of different sketch widths (a group's K and V factorisations).  nullptr
+// (the default) = uniform.  Internal to the library: the factorisation driver sets and clears it around each call.
+const int*& batch_rows_override();
+struct BatchRowsScope {
+  explicit BatchRowsScope(const int* rows) { batch_rows_override() = rows; }
+  ~BatchRowsScope() { batch_rows_override() = nullptr; }
+};
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // One-time per-DEVICE set-up (cudaFuncSetAttribute and occupancy queries apply to the current device only; a

@@ -139,15 +139,29 @@ def layer_rows(t: torch.Tensor) -> Optional[torch.Tensor]:
     return t.as_strided((s, h * d), (ss, 1))
 
 
-def factorize_groups(groups: Sequence[Sequence[torch.Tensor]], rank: int, opts: Optional[FactorizeOptions] = None,
+def mixed_ranks_ok(ranks: Sequence[int], opts: Optional[FactorizeOptions] = None) -> bool:
+    """Can matrices of these ranks share one driver call?  Their sketches must share a Rayleigh-Ritz window width: true when
+    every sketch is at least `window` wide and leaves room for at least one kept column in it."""
+    o = opts or FactorizeOptions()
+    ls = [sketch_width(int(r), o.oversample) for r in ranks]
+    w = min(o.window, 160) // 2 * 2
+    return all(l >= w and 0 < w - (l - int(r)) <= int(r) and (w - (l - int(r)) + (l - int(r))) % 2 == 0 for l, r in zip(ls, ranks))
+
+
+def factorize_groups(groups: Sequence[Sequence[torch.Tensor]], rank, opts: Optional[FactorizeOptions] = None,
                      workspace: Optional[torch.Tensor] = None, extra_rows: int = 0) -> List[Factors]:
     """Factorise layer groups IN PLACE: groups[g][i] is the (S, H*D) row-major matrix of layer i of group g
     (:func:`layer_rows`); the group matrix is their column-wise concatenation — the reference's ``torch.cat(dim=1)`` +
     ``transpose(1, 2).reshape`` (cache:170-171, :13-14) — and is never materialised: the Gram pass and the projection pass
-    read the layer tensors through per-layer tensor maps (xkv_factorize_groups)."""
+    read the layer tensors through per-layer tensor maps (xkv_factorize_groups).  `rank`: one rank for all, or one per group
+    matrix — a group's K and V matrices (different ranks, hence different sketch widths) then share every launch of the
+    latency-bound stages (xkv_factorize_groups_mixed)."""
     opts = opts or FactorizeOptions()
     if len(groups) == 0:
         return []
+    ranks = [int(rank)] * len(groups) if isinstance(rank, int) else [int(x) for x in rank]
+    if len(ranks) != len(groups):
+        raise XkvError("factorize_groups: one rank per group matrix required")
     lib = _lib.load()
     nl = len(groups[0])
     m, lc = groups[0][0].shape
@@ -161,26 +175,30 @@ def factorize_groups(groups: Sequence[Sequence[torch.Tensor]], rank: int, opts: 
                     or t.data_ptr() & 15):
                 raise XkvError("factorize_groups: layers must be equally shaped row-major bf16 CUDA matrices, 16-byte aligned")
     n = nl * lc
-    r = int(rank)
     co = _c_options(opts)
     per_call = max(1, min(_lib.MAX_BATCH, 64 // nl))     # XKV_MAX_LAYER_MAPS layer matrices per launch
     chunk = min(len(groups), per_call)
-    need = int(lib.xkv_factorize_workspace_bytes(chunk, m, n, r, C.byref(co)))
-    if need == 0:
-        raise XkvError(lib.xkv_last_error().decode() or "factorize: invalid problem")
+    need = 0
+    for lo in range(0, len(groups), chunk):
+        rk = (C.c_int32 * len(ranks[lo:lo + chunk]))(*ranks[lo:lo + chunk])
+        nb_ = int(lib.xkv_factorize_workspace_bytes_mixed(len(rk), m, n, rk, C.byref(co)))
+        if nb_ == 0:
+            raise XkvError(lib.xkv_last_error().decode() or "factorize: invalid problem")
+        need = max(need, nb_)
     if workspace is None or workspace.numel() * workspace.element_size() < need:
         workspace = torch.empty(need, dtype=torch.uint8, device=dev)
-    nsig = int(lib.xkv_factorize_sigma_count(r, C.byref(co)))
+    nsig = int(lib.xkv_factorize_sigma_count(ranks[0], C.byref(co)))
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     out: List[Factors] = []
     all_events = []
     for lo in range(0, len(groups), chunk):
         part = groups[lo:lo + chunk]
+        rs = ranks[lo:lo + chunk]
         nb = len(part)
-        a_store = [torch.empty(m + extra_rows, r, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
+        a_store = [torch.empty(m + extra_rows, r, dtype=torch.bfloat16, device=dev) for r in rs]
         a = [t[:m] for t in a_store]
-        vt = [torch.empty(r, n, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
-        v = [torch.empty(n, r, dtype=torch.bfloat16, device=dev) for _ in range(nb)]
+        vt = [torch.empty(r, n, dtype=torch.bfloat16, device=dev) for r in rs]
+        v = [torch.empty(n, r, dtype=torch.bfloat16, device=dev) for r in rs]
         sig = [torch.empty(nsig, dtype=torch.float32, device=dev) if nsig else None for _ in range(nb)]
         ev_arr = None
         if opts.profile:
@@ -190,12 +208,12 @@ def factorize_groups(groups: Sequence[Sequence[torch.Tensor]], rank: int, opts: 
             ev_arr = (C.c_void_p * 7)(*[e.cuda_event for e in events])
             all_events.append(events)
         flat = [t for grp in part for t in grp]
-        _lib.check(lib.xkv_factorize_groups(
-            ops._ptr_array(flat), nb, nl, lc, m, ld, r, C.byref(co), ops._ptr_array(a), ops._ptr_array(vt),
-            ops._ptr_array(v), ops._ptr_array(sig) if nsig else None, C.c_void_p(workspace.data_ptr()),
-            workspace.numel() * workspace.element_size(), ev_arr, stream))
+        _lib.check(lib.xkv_factorize_groups_mixed(
+            ops._ptr_array(flat), nb, nl, lc, m, ld, (C.c_int32 * nb)(*rs), C.byref(co), ops._ptr_array(a),
+            ops._ptr_array(vt), ops._ptr_array(v), ops._ptr_array(sig) if nsig else None,
+            C.c_void_p(workspace.data_ptr()), workspace.numel() * workspace.element_size(), ev_arr, stream))
         for b in range(nb):
-            out.append(Factors(A=a[b], Vt=vt[b], V=v[b], rank=r, sigma_lead=sig[b], A_storage=a_store[b]))
+            out.append(Factors(A=a[b], Vt=vt[b], V=v[b], rank=rs[b], sigma_lead=sig[b], A_storage=a_store[b]))
     if opts.profile:
         torch.cuda.synchronize()
         timings: Dict[str, float] = {}
