@@ -47,7 +47,7 @@ CONFIGS = {
             alpha_k=1.0, alpha_v=0.5),
 }
 METRIC = "KV GB/s compressed (prefill, {title})"
-SAMPLE_TOKENS = 4096   # tokens of the bounded CPU / library-SVD samples (BASELINE.json configs[0]'s shape)
+SAMPLE_TOKENS = 4096   # tokens of the library-SVD sample on the GPU and of the configs[0]-shaped CPU check
 
 
 def parse_args():
@@ -58,9 +58,11 @@ def parse_args():
     ap.add_argument("--impl", default="xkv_b200", choices=["xkv_b200", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--tokens", type=int, default=0, help="override the configuration's context length")
-    ap.add_argument("--cpu-sample-tokens", type=int, default=SAMPLE_TOKENS)
-    ap.add_argument("--cpu-full-tokens", type=int, default=65536,
-                    help="reference arm: ONE K matrix at this many tokens is timed once per run (0 = skip)")
+    ap.add_argument("--cpu-sample-tokens", type=int, default=0,
+                    help="context length of the CPU arm's per-step sample (ONE K matrix); 0 = the configuration's own")
+    ap.add_argument("--cpu-config1-tokens", type=int, default=SAMPLE_TOKENS,
+                    help="reference arm: one whole group (K + V) at this many tokens, BASELINE.json configs[0]'s shape, is "
+                         "timed once per run (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
@@ -77,6 +79,8 @@ def config_of(args):
     c = dict(CONFIGS[args.config])
     if args.tokens:
         c["tokens"] = args.tokens
+    if not getattr(args, "cpu_sample_tokens", 0):
+        args.cpu_sample_tokens = c["tokens"]
     return c
 
 
@@ -92,10 +96,12 @@ def kv_bytes_of(c):
 
 
 def reference_sample_text(c, tokens):
-    return (f"ONE {min(c['group'], 4)}-layer group ({c['heads']} KV heads x {c['head_dim']}) at {tokens} tokens per step "
-            f"(BASELINE.json configs[0]'s shape; a bounded sample of the workload, GB/s of its own bytes): the reference's "
-            f"arithmetic, torch.linalg.svd fp32 -> truncate -> multiply back, K rank {c['rank_k']}"
-            + (f" + V rank {c['rank_v']}" if c["merge_value"] else ""))
+    g = min(c["group"], 4)
+    return (f"ONE K matrix of a {g}-layer group per step, {tokens} x {g * c['heads'] * c['head_dim']} "
+            f"({tokens} tokens, {c['heads']} KV heads x {c['head_dim']}), through the reference's fake_svd arithmetic: "
+            f"torch.linalg.svd fp32 (full, whatever the rank) -> truncate to rank {c['rank_k']} -> multiply back; GB/s of the "
+            f"matrix's own bf16 bytes.  The cache is {2 * len(group_sizes(c)) if c['merge_value'] else len(group_sizes(c))} "
+            f"such matrices (a V matrix costs the same SVD)")
 
 
 def workload_config(args, c):
@@ -116,38 +122,39 @@ def workload_config(args, c):
 # CPU baseline / reference arm: the reference's own arithmetic (oracle port of fake_svd etc.)
 # ----------------------------------------------------------------------------------------------
 def cpu_reference_step(c, sample_tokens: int, seed: int = 0):
-    """One bounded sample of the workload on the host cores: one layer group at `sample_tokens` tokens through the
-    oracle's grouped merge. Returns (seconds, bytes_of_kv)."""
-    from oracle import xkv_oracle as O
-    from xkv_b200 import synthetic
-
-    g = min(c["group"], 4)
-    keys = synthetic.make_group_kv(g, c["heads"], sample_tokens, c["head_dim"], c["alpha_k"], seed)
-    vals = synthetic.make_group_kv(g, c["heads"], sample_tokens, c["head_dim"], c["alpha_v"], seed + 1)
-    t0 = time.perf_counter()
-    O.merge_group(keys, vals, c["rank_k"], c["rank_v"] if c["merge_value"] else None, True, c["merge_value"])
-    dt = time.perf_counter() - t0
-    nbytes = (2 if c["merge_value"] else 1) * g * c["heads"] * sample_tokens * c["head_dim"] * 2
-    return dt, nbytes
-
-
-def cpu_full_size_matrix(c, tokens: int):
-    """ONE K matrix of the configuration at `tokens` tokens (65536 x 4096 at config 2) through the reference's fake_svd
-    arithmetic, once: shows what the bounded sample's GB/s extrapolates to at the stated context length."""
+    """One bounded sample of the workload on the host cores: ONE K matrix of a layer group at `sample_tokens` tokens (the
+    configuration's own context length by default: the cost of the reference's full SVD is far from linear in the token
+    count, a short sample would misstate its throughput) through the oracle's fake_svd. Returns (seconds, bytes_of_kv)."""
     import torch
     from oracle import xkv_oracle as O
     from xkv_b200 import synthetic
 
     g = min(c["group"], 4)
-    keys = synthetic.make_group_kv(g, c["heads"], tokens, c["head_dim"], c["alpha_k"], 11)
+    keys = synthetic.make_group_kv(g, c["heads"], sample_tokens, c["head_dim"], c["alpha_k"], seed)
     x = torch.cat(keys, dim=1).float()
     t0 = time.perf_counter()
     O.fake_svd(x, c["rank_k"])
     dt = time.perf_counter() - t0
-    nbytes = g * c["heads"] * tokens * c["head_dim"] * 2
-    return {"tokens": tokens, "matrix": f"{tokens} x {g * c['heads'] * c['head_dim']} fp32, rank {c['rank_k']}", "seconds": dt,
-            "GBps_of_bf16_KV": nbytes / dt / 1e9,
-            "note": "one K matrix, timed once; the whole cache is 2 x groups such matrices (V at its own rank)"}
+    nbytes = g * c["heads"] * sample_tokens * c["head_dim"] * 2
+    return dt, nbytes
+
+
+def cpu_config1_group(c, tokens: int):
+    """BASELINE.json configs[0]: one whole layer group (K and V) at 4K tokens through the oracle's grouped merge, once."""
+    from oracle import xkv_oracle as O
+    from xkv_b200 import synthetic
+
+    g = min(c["group"], 4)
+    keys = synthetic.make_group_kv(g, c["heads"], tokens, c["head_dim"], c["alpha_k"], 11)
+    vals = synthetic.make_group_kv(g, c["heads"], tokens, c["head_dim"], c["alpha_v"], 12)
+    t0 = time.perf_counter()
+    O.merge_group(keys, vals, c["rank_k"], c["rank_v"] if c["merge_value"] else None, True, c["merge_value"])
+    dt = time.perf_counter() - t0
+    nbytes = (2 if c["merge_value"] else 1) * g * c["heads"] * tokens * c["head_dim"] * 2
+    return {"tokens": tokens, "what": f"one {g}-layer group, K rank {c['rank_k']}" + (f" + V rank {c['rank_v']}" if c["merge_value"] else ""),
+            "seconds": dt, "GBps_of_bf16_KV": nbytes / dt / 1e9,
+            "note": "BASELINE.json configs[0]'s shape; square-ish matrices: the SVD's n^3 terms dominate, GB/s is ~5x lower "
+                    "than at the 64K context of the headline"}
 
 
 def run_reference_arm(args):
@@ -177,11 +184,11 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    if args.cpu_full_tokens and args.cpu_full_tokens > args.cpu_sample_tokens:
+    if args.cpu_config1_tokens:
         try:
-            line["cpu_baseline"]["full_size_check"] = cpu_full_size_matrix(c, args.cpu_full_tokens)
-        except Exception as ex:   # e.g. out of host memory: the bounded sample stands on its own
-            line["cpu_baseline"]["full_size_check"] = {"error": f"{type(ex).__name__}: {ex}"}
+            line["cpu_baseline"]["config1_check"] = cpu_config1_group(c, args.cpu_config1_tokens)
+        except Exception as ex:   # the per-step sample stands on its own
+            line["cpu_baseline"]["config1_check"] = {"error": f"{type(ex).__name__}: {ex}"}
     print(json.dumps(line), flush=True)
 
 
@@ -657,6 +664,58 @@ def bench_other_config(ctx, idx, streams):
     return rec
 
 
+def bench_mla_decode(ctx):
+    """configs[4] decode: one token over the factored latent cache of a DeepSeek-V2-Lite-shaped model (27 layers, 16 heads,
+    kv_lora_rank 512, rope dim 64, 32K context, xKV-4 rank 512) in the factors' rank space (xkv_decode_absorbed: scores and
+    values are two streaming passes over the group's token factor A; the latents are never rebuilt, kv_b_proj never runs
+    over the cache).  The per-head folding of the query / unfolding of the result (a few 16 x 512 x 512 products) belongs
+    to the attention module and is not part of the cache kernel timed here."""
+    from xkv_b200 import ops
+
+    torch = ctx.torch
+    c = CONFIGS[5]
+    S, r, L, hq, dr = c["tokens"], c["rank_k"], c["layers"], 16, 64
+    gen = torch.Generator(device=ctx.dev).manual_seed(3)
+    ngroups = len(group_sizes(c))
+    a = [(torch.randn(S, r, device=ctx.dev, generator=gen) * 0.3).bfloat16() for _ in range(ngroups)]
+    kpe = [torch.randn(S, dr, device=ctx.dev, generator=gen).bfloat16() for _ in range(L)]
+    inv_rms = [(0.5 + torch.rand(S, device=ctx.dev, generator=gen)).float() for _ in range(L)]
+    q_hat = torch.randn(L, hq, r, device=ctx.dev, generator=gen).bfloat16()
+    q_pe = torch.randn(L, hq, dr, device=ctx.dev, generator=gen).bfloat16()
+    ws = torch.empty(int(ops._lib.load().xkv_decode_absorbed_workspace_bytes(hq, S, r)) + 4096, dtype=torch.uint8, device=ctx.dev)
+
+    def one_token():
+        for l in range(L):
+            ops.decode_absorbed(q_hat[l], a[l // c["group"]], 0.07, row_scale=inv_rms[l], bias_q=q_pe[l], bias_k=kpe[l], workspace=ws)
+
+    for _ in range(2):
+        one_token()
+    torch.cuda.synchronize()
+    l0 = ops.launch_count()
+    one_token()
+    launches = ops.launch_count() - l0
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        one_token()
+    graph.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(8):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 8
+    nbytes = L * (2.0 * S * r * 2 + S * dr * 2)        # A is read for the scores and again for the values
+    return {"metric": f"decode tok/s over the factored MLA latent cache ({L} layers, {hq} heads, rank {r}, {S} context)",
+            "tok_s": 1e3 / ms, "us_per_layer": 1e3 * ms / L, "gpu_launches_per_token": launches,
+            "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": ctx.peak_hbm, "unit": "GB/s",
+                         "frac": nbytes / (ms * 1e-3) / 1e9 / ctx.peak_hbm,
+                         "note": "token factor read twice (scores, values) + k_pe once, per layer"},
+            "reference_path_note": "the reference re-expands the whole cache every step: S x 512 reconstruction + RMSNorm + "
+                                   "kv_b_proj (S x 512 x 4096) per layer, 1.4e11 flop per layer at 32K"}
+
+
 def bench_gpu_reference(ctx, c):
     """The reference's own library path ON THIS GPU (the bar is torch.linalg.svd / cuSOLVER + cuBLAS):
     fake_svd's arithmetic (fp32 svd -> truncate -> multiply back) for one K and one V matrix of ONE group at the bounded
@@ -789,6 +848,7 @@ def run_xkv_arm(args):
         line["token_sharded"] = bench_token_sharded(ctx)
         if rank == 0:
             line["other_configs"] = {"3": bench_other_config(ctx, 3, args.streams), "5": bench_other_config(ctx, 5, args.streams)}
+            line["other_configs"]["5"]["decode"] = bench_mla_decode(ctx)
             if world == 1:
                 line["gpu_reference"] = bench_gpu_reference(ctx, c)
         ctx.barrier()
