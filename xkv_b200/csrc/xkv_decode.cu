@@ -576,60 +576,56 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
       for (int kb = 0; kb < P.nkb; ++kb) tma_load_2d(sB + kb * B_KB_BYTES, &P.b_head_map, b_bar, kb * DBK, h * D);
     }
     __syncwarp();
-    int s = 0;
-    uint32_t ph = 0;
-    for (int tile = slot; tile < ntiles && !XKV_DBG(P, 64); tile += nslots) {
-      for (int kb = 0; kb < P.nkb; ++kb) {
-        mbar_wait(&empty_bar[s], ph ^ 1u);       // CL > 1: every CTA of the cluster has consumed the slot
-        if (elect_one()) {
+    if (elect_one()) {   // the whole producer loop in one lane (see the MMA warp)
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = slot; tile < ntiles && !XKV_DBG(P, 64); tile += nslots) {
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);       // CL > 1: every CTA of the cluster has consumed the slot
           mbar_expect_tx(&full_bar[s], D_A_BYTES);   // the whole stage lands here: this CTA's slice + the peers'
           if (CL > 1)
             tma_load_2d_multicast(sA + s * D_A_BYTES + crank * (SLICE_ROWS * 128), &P.a_mc_map, &full_bar[s], kb * DBK,
                                   tile * DBM + crank * SLICE_ROWS, CL_MASK);
           else
             tma_load_2d(sA + s * D_A_BYTES, &P.a_map, &full_bar[s], kb * DBK, tile * DBM);
-        }
-        __syncwarp();
-        if (++s == R_STAGES) {
-          s = 0;
-          ph ^= 1u;
+          if (++s == R_STAGES) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
+    // Reconstruction MMAs.  At N = 128 an M128 K16 instruction occupies the tensor pipe for 64 clk, so the issuing
+    // thread has 256 clk per rank block for the barrier wait, four MMAs and the commit -- and a warp-converged loop
+    // that re-elects a lane, rebuilds eight descriptors (~45 uniform-datapath instructions) and reconverges every rank
+    // block does not fit in them: the kernel ran at ~100 clk per MMA, issue-bound (tools/probe_mma_rate.cu: 64.2 clk
+    // with a bare loop, 82 with two integer modulos in it, 100 with a commit per block on top).  So ONE elected lane
+    // runs the whole loop, and the descriptors advance by 64-bit adds (start address field in 16-byte units: +2 per
+    // K = 16 step, + stage / block size per rank block; no carry out of the 14-bit field below 256 KiB).
     constexpr uint32_t idesc = umma_idesc_bf16(DBM, D, 0, 0);
+    constexpr uint64_t kKStep = 32 >> 4, kStageStep = D_A_BYTES >> 4, kBlockStep = B_KB_BYTES >> 4;
     mbar_wait(b_bar, 0);
-    int s = 0, acc = 0;
-    uint32_t ph = 0, acc_ph = 0u;
-    const uint32_t b_base = smem_u32(sB);
-    for (int tile = slot; tile < ntiles; tile += nslots) {
-      if (!XKV_DBG(P, 4)) mbar_wait(&tempty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);
-      tc_fence_after();
-      const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * D);
-      for (int kb = 0; kb < P.nkb; ++kb) {
-        if (!XKV_DBG(P, 64)) mbar_wait(&full_bar[s], ph);
-        if (!XKV_DBG(P, 2048)) tc_fence_after();
-        const uint32_t a_base = smem_u32(sA + s * D_A_BYTES);
-        if (elect_one()) {
-          if (XKV_DBG(P, 256)) {   // probe: stage the token tile in tensor memory (tcgen05.cp), then TS-form MMAs
-            const uint32_t a_tm = tmem_base + 448u + static_cast<uint32_t>((kb & 1) * 32);
-#pragma unroll
-            for (int k = 0; k < DBK / 16; ++k)
-              tmem_cp_128x256b(a_tm + static_cast<uint32_t>(k * 8), umma_desc_sw128(a_base + k * 32, 16, 1024));
-#pragma unroll
-            for (int k = 0; k < DBK / 16; ++k)
-              umma_bf16_ts(d_addr, a_tm + static_cast<uint32_t>(k * 8),
-                           umma_desc_sw128(b_base + kb * B_KB_BYTES + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          } else if (XKV_DBG(P, 128)) {   // probe: A operand from tensor memory (TS form) instead of shared memory
-#pragma unroll
-            for (int k = 0; k < DBK / 16; ++k)
-              umma_bf16_ts(d_addr, tmem_base + R_COL_A2 + static_cast<uint32_t>(k * 8),
-                           umma_desc_sw128(b_base + kb * B_KB_BYTES + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          } else if (!XKV_DBG(P, 1)) {
-#pragma unroll
-            for (int k = 0; k < DBK / 16; ++k)
-              umma_bf16_ss(d_addr, umma_desc_sw128(a_base + k * 32, 16, 1024),
-                           umma_desc_sw128(b_base + kb * B_KB_BYTES + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+    if (elect_one()) {
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA), 16, 1024);
+      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB), 16, 1024);
+      uint64_t a_desc = a_desc0;
+      int s = 0, acc = 0;
+      uint32_t ph = 0, acc_ph = 0u;
+      for (int tile = slot; tile < ntiles; tile += nslots) {
+        if (!XKV_DBG(P, 4)) mbar_wait(&tempty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * D);
+        uint64_t b_desc = b_desc0;
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          if (!XKV_DBG(P, 64)) mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          if (!XKV_DBG(P, 1)) {
+            umma_bf16_ss(d_addr, a_desc, b_desc, idesc, kb > 0 ? 1u : 0u);
+            umma_bf16_ss(d_addr, a_desc + kKStep, b_desc + kKStep, idesc, 1u);
+            umma_bf16_ss(d_addr, a_desc + 2 * kKStep, b_desc + 2 * kKStep, idesc, 1u);
+            umma_bf16_ss(d_addr, a_desc + 3 * kKStep, b_desc + 3 * kKStep, idesc, 1u);
           }
           if (XKV_DBG(P, 512)) {
             // probe: no per-stage commit
@@ -637,18 +633,20 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
             umma_commit_multicast(&empty_bar[s], CL_MASK);
           else
             umma_commit(&empty_bar[s]);
+          b_desc += kBlockStep;
+          a_desc += kStageStep;
+          if (++s == R_STAGES) {
+            s = 0;
+            ph ^= 1u;
+            a_desc = a_desc0;
+          }
         }
-        if (!XKV_DBG(P, 1024)) __syncwarp();
-        if (++s == R_STAGES) {
-          s = 0;
-          ph ^= 1u;
-        }
+        umma_commit(&tfull_bar[acc]);
+        acc_ph ^= 1u << acc;
+        acc ^= 1;
       }
-      if (elect_one()) umma_commit(&tfull_bar[acc]);
-      __syncwarp();
-      acc_ph ^= 1u << acc;
-      acc ^= 1;
     }
+    __syncwarp();
   } else if (XKV_DBG(P, 4)) {
     // probe: no epilogue pipeline at all
   } else if (warp == 2) {
@@ -657,26 +655,27 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
       constexpr uint32_t idesc2 = umma_idesc_bf16(DBM, R_QROWS, 0, 0);
       mbar_wait(q_bar, 0);
       const uint32_t q_base = smem_u32(sQ);
-      int b = 0;
-      uint32_t bph = 0u;
-      for (int tile = slot; tile < ntiles; tile += nslots) {
-        mbar_wait(&a2full_bar[b], (bph >> b) & 1u);                 // rotated keys of this tile are in TMEM
-        mbar_wait(&d2empty_bar[b], ((bph >> b) & 1u) ^ 1u);         // score buffer read out
-        tc_fence_after();
-        const uint32_t a2 = tmem_base + R_COL_A2 + static_cast<uint32_t>(b * 64);
-        const uint32_t d2 = tmem_base + R_COL_D2 + static_cast<uint32_t>(b * 32);
-        if (elect_one()) {
+      if (elect_one()) {
+        const uint64_t q_desc0 = umma_desc_sw128(q_base, 16, 1024);
+        int b = 0;
+        uint32_t bph = 0u;
+        for (int tile = slot; tile < ntiles; tile += nslots) {
+          mbar_wait(&a2full_bar[b], (bph >> b) & 1u);                 // rotated keys of this tile are in TMEM
+          mbar_wait(&d2empty_bar[b], ((bph >> b) & 1u) ^ 1u);         // score buffer read out
+          tc_fence_after();
+          const uint32_t a2 = tmem_base + R_COL_A2 + static_cast<uint32_t>(b * 64);
+          const uint32_t d2 = tmem_base + R_COL_D2 + static_cast<uint32_t>(b * 32);
 #pragma unroll
           for (int k = 0; k < D / 16; ++k)
             umma_bf16_ts(d2, a2 + static_cast<uint32_t>(k * 8),
-                         umma_desc_sw128(q_base + (k >> 2) * (R_Q_BYTES / 2) + (k & 3) * 32, 16, 1024), idesc2, k > 0 ? 1u : 0u);
+                         q_desc0 + static_cast<uint64_t>(((k >> 2) * (R_Q_BYTES / 2) + (k & 3) * 32) >> 4), idesc2, k > 0 ? 1u : 0u);
           umma_commit(&d2full_bar[b]);
           umma_commit(&a2empty_bar[b]);
+          bph ^= 1u << b;
+          b ^= 1;
         }
-        __syncwarp();
-        bph ^= 1u << b;
-        b ^= 1;
       }
+      __syncwarp();
     }
   } else if (warp >= 4 && warp < 4 + R_EPI_WARPS) {
     // ===== epilogue: K^ row -> bf16 -> RoPE (packed bf16) -> back to TMEM as the A operand of the score MMA =====
@@ -709,32 +708,36 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
       const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
       const uint32_t lane_addr = lane_base + static_cast<uint32_t>(acc * D);
       uint32_t lo_w[16], hi_w[16];      // packed bf16x2: dims d0 + 2j, d0 + 2j + 1 and their partners + 64
-#pragma unroll
-      for (int sc = 0; sc < 2; ++sc) {
-        uint32_t x1[16], x2[16];
+      {
+        // read the accumulator, round to bf16 (the reference's cast of the reconstructed keys) and hand the buffer back
+        // to the reconstruction MMAs BEFORE the rotation: the issue loop of the tile after next waits for this arrive
+        uint32_t x1[32], x2[32];
         __syncwarp();
-        tmem_ld_32x16(lane_addr + static_cast<uint32_t>(d0 + sc * 16), x1);
-        tmem_ld_32x16(lane_addr + static_cast<uint32_t>(D / 2 + d0 + sc * 16), x2);
+        tmem_ld_32x32(lane_addr + static_cast<uint32_t>(d0), x1);
+        tmem_ld_32x32(lane_addr + static_cast<uint32_t>(D / 2 + d0), x2);
         tmem_ld_wait();
 #pragma unroll
-        for (int jp = 0; jp < 8; ++jp) {
-          const __nv_bfloat162 k1 = __floats2bfloat162_rn(__uint_as_float(x1[2 * jp]), __uint_as_float(x1[2 * jp + 1]));
-          const __nv_bfloat162 k2 = __floats2bfloat162_rn(__uint_as_float(x2[2 * jp]), __uint_as_float(x2[2 * jp + 1]));
-          __nv_bfloat162 o1 = k1, o2 = k2;
-          if (rope) {
-            const __nv_bfloat162 cw = *reinterpret_cast<const __nv_bfloat162*>(&cs[sc * 8 + jp]);
-            const __nv_bfloat162 sw = *reinterpret_cast<const __nv_bfloat162*>(&sn[sc * 8 + jp]);
-            o1 = __hadd2(__hmul2(k1, cw), __hmul2(__hneg2(k2), sw));
-            o2 = __hadd2(__hmul2(k2, cw), __hmul2(k1, sw));
-          }
-          lo_w[sc * 8 + jp] = *reinterpret_cast<const uint32_t*>(&o1);
-          hi_w[sc * 8 + jp] = *reinterpret_cast<const uint32_t*>(&o2);
+        for (int j = 0; j < 16; ++j) {
+          lo_w[j] = pack_bf16x2(__uint_as_float(x1[2 * j]), __uint_as_float(x1[2 * j + 1]));
+          hi_w[j] = pack_bf16x2(__uint_as_float(x2[2 * j]), __uint_as_float(x2[2 * j + 1]));
         }
       }
-      // the accumulator is in registers: hand it back to the reconstruction MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (rope) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const __nv_bfloat162 k1 = *reinterpret_cast<const __nv_bfloat162*>(&lo_w[j]);
+          const __nv_bfloat162 k2 = *reinterpret_cast<const __nv_bfloat162*>(&hi_w[j]);
+          const __nv_bfloat162 cw = *reinterpret_cast<const __nv_bfloat162*>(&cs[j]);
+          const __nv_bfloat162 sw = *reinterpret_cast<const __nv_bfloat162*>(&sn[j]);
+          const __nv_bfloat162 o1 = __hadd2(__hmul2(k1, cw), __hmul2(__hneg2(k2), sw));
+          const __nv_bfloat162 o2 = __hadd2(__hmul2(k2, cw), __hmul2(k1, sw));
+          lo_w[j] = *reinterpret_cast<const uint32_t*>(&o1);
+          hi_w[j] = *reinterpret_cast<const uint32_t*>(&o2);
+        }
+      }
       if (XKV_DBG(P, 16)) {
         acc_ph ^= 1u << acc;
         acc ^= 1;
