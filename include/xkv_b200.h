@@ -288,12 +288,15 @@ XKV_API int xkv_decode_attention_lse(const void* q, int Hq, int H, int D, const 
 /* test hook: 1 forces the tile-per-CTA scores kernel (otherwise chosen only when one head's slice of the right
  * factor exceeds 128 KiB of shared memory), 0 restores the automatic choice */
 XKV_API void xkv_decode_force_tiled(int on);
-/* test hook: persistent scores kernel to use where several apply: 0 automatic (score MMA for head_dim 128, in clusters
- * that share the A_k tiles by TMA multicast), 1 FFMA epilogue, 2 score MMA with one independent CTA per kv head */
+/* test hook: persistent scores kernel to use where several apply: 0 automatic (head_dim 128: score MMA in CTA pairs,
+ * cta_group::2, half a right-factor slice per CTA), 1 FFMA epilogue, 2 score MMA with one independent CTA per kv head,
+ * 3 CTA pairs */
 XKV_API void xkv_decode_set_variant(int variant);
 /* tuning hook: cluster size of the score-MMA kernel, i.e. how many adjacent kv heads share one multicast copy of each
  * A_k tile: 0 automatic, else 1, 2, 4 or 8 (reduced to a divisor of the kv-head count the device can keep resident) */
 XKV_API void xkv_decode_set_cluster(int cluster);
+/* tuning hook: cap on the TMA ring depth (16 KiB slots of A_k in flight per CTA) of the pair kernel: 0 automatic, else >= 3 */
+XKV_API void xkv_decode_set_stages(int stages);
 /* Absorbed attention over a token factor: replaces, for the MLA latent slot (deepseek_v2.py:217-235: reconstructed
  * latents -> kv_a_layernorm -> kv_b_proj over the WHOLE cache -> attention, every decode step), the part that touches
  * the cache.  The latent of token t is c_t = V_l a_t and both attention products are linear in it, so with the query

@@ -10,8 +10,9 @@ pytestmark = pytest.mark.gpu
 
 
 VARIANTS = {          # name -> (force_tiled, variant, cluster)
-    "auto": (0, 0, 0),     # score MMA in clusters that share the A_k tiles by TMA multicast (head_dim 128)
-    "cl1": (0, 2, 1),      # score MMA, one independent CTA per kv head (round 1's default)
+    "auto": (0, 0, 0),     # head_dim 128: CTA pairs (cta_group::2), half a right-factor slice per CTA
+    "pair": (0, 3, 0),     # the same, requested explicitly
+    "cl1": (0, 2, 1),      # score MMA, one independent CTA per kv head
     "cl2": (0, 0, 2),
     "cl4": (0, 0, 4),
     "cl8": (0, 0, 8),

@@ -18,6 +18,7 @@ ap.add_argument("S", type=int, nargs="?", default=65536)
 ap.add_argument("layers", type=int, nargs="?", default=4)
 ap.add_argument("--cluster", type=int, default=0)
 ap.add_argument("--variant", type=int, default=0)
+ap.add_argument("--stages", type=int, default=0)
 ap.add_argument("--graph", action="store_true")
 ap.add_argument("--rk", type=int, default=512)
 ap.add_argument("--rv", type=int, default=768)
@@ -37,6 +38,7 @@ kt = torch.randn(H, 1, D, device=dev).bfloat16()
 vt = torch.randn(H, 1, D, device=dev).bfloat16()
 _lib.load().xkv_decode_set_variant(args.variant)
 _lib.load().xkv_decode_set_cluster(args.cluster)
+_lib.load().xkv_decode_set_stages(args.stages)
 ws = torch.empty(ops.decode_workspace_bytes(HQ, S, 1, RV) + 4096, dtype=torch.uint8, device=dev)
 o = torch.empty(HQ, D, dtype=torch.bfloat16, device=dev)
 
@@ -57,7 +59,7 @@ run()
 e1.record()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
-res = {"S": S, "layers": layers, "cluster": args.cluster, "variant": args.variant,
+res = {"S": S, "layers": layers, "cluster": args.cluster, "variant": args.variant, "stages": args.stages,
        "us_per_layer_host_enqueue": 1e3 * e0.elapsed_time(e1) / layers}
 if args.graph:
     g = torch.cuda.CUDAGraph()

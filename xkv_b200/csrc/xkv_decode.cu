@@ -36,6 +36,8 @@ struct alignas(64) ScoreParams {
   CUtensorMap b_head_map;  // Bk_l, box {64, D}: one kv head (persistent kernel)
   CUtensorMap q_map;       // q (Hq x D), box {64, 16}: the q rows of one kv head (score MMA)
   CUtensorMap a_mc_map;    // A_k, box {64, 128 / cluster size}: one CTA's slice of a token tile (multicast kernel)
+  CUtensorMap b_half_map;  // Bk_l, box {64, 64}: half a kv head's dims (pair kernel)
+  CUtensorMap q_half_map;  // q, box {64, 8}: the q rows one CTA of a pair supplies to the score MMA
   const __nv_bfloat16* q;    // (Hq, D)
   const __nv_bfloat16* cos;  // (S, D) or null
   const __nv_bfloat16* sin;
@@ -792,6 +794,291 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pair form of the score-MMA kernel: a CTA PAIR (cta_group::2, the two SMs of a TPC) owns one kv head and works on 256
+// tokens per step.  Each CTA streams ITS 128 tokens of A_k, keeps HALF of the head's right-factor slice (64 dims x
+// r_k: 64 KiB at r_k = 512 instead of 128) and receives the K^ tile of its tokens (128 x 128, all dims of the head) in
+// its own tensor memory: M = 256, N = 128 tcgen05.mma issued by the even CTA.  Why: with the whole slice resident only
+// 5 ring slots of 16 KiB fit beside it, and the kernel's time followed the ring depth (2 / 3 / 4 / 5 slots: 114 / 77 /
+// 66 / 61 us per layer): a slot is held from the TMA issue until the MMAs that read it RETIRE, so at most ~2-3 loads
+// were in flight against an L2 round trip of ~0.6 us.  Half a slice leaves room for 9 slots (7 are used; 7 at r_k 768,
+// 5 at 1024 -- ranks whose whole slice does not fit at all).  The epilogue is the single-CTA kernel's, run by both
+// CTAs on their own tokens; the score MMA (M = 256, N = 16: 8 q rows from each CTA) is issued by the even CTA once
+// BOTH epilogues have written their rotated keys (remote mbarrier arrivals), commits are multicast to both CTAs.
+// ---------------------------------------------------------------------------------------------
+constexpr int PR_B_KB_BYTES = 64 * DBK * 2;        // one rank block of a half slice: 64 dims x 128 B
+constexpr int PR_Q_BYTES = 2 * 8 * 128;            // 8 q rows per CTA, two 64-dim chunks
+constexpr size_t PR_FIXED_BYTES = PR_Q_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+static inline int pair_stages_for(int nkb) {
+  const size_t b = static_cast<size_t>(nkb) * PR_B_KB_BYTES;
+  if (b + PR_FIXED_BYTES + 3 * D_A_BYTES > R_SMEM_LIMIT) return 0;
+  int st = static_cast<int>((R_SMEM_LIMIT - PR_FIXED_BYTES - b) / D_A_BYTES);
+  // measured (config 2, one layer): 3 / 5 / 6 / 7 / 8 / 9 slots -> 75.6 / 53.8 / 49.9 / 49.5 / 51.4 / 53.0 us: past 7 the extra
+  // loads in flight only add L2 contention
+  return st > 7 ? 7 : st;
+}
+
+__global__ void __launch_bounds__(R_THREADS, 1) decode_scores_pair_kernel(const __grid_constant__ ScoreParams P) {
+  constexpr int D = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int R_STAGES = P.stages;
+  uint8_t* sB = smem;                              // nkb x 8 KiB: this CTA's half of the head's right-factor slice
+  uint8_t* sA = smem + P.nkb * PR_B_KB_BYTES;
+  uint8_t* sQ = sA + R_STAGES * D_A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sQ + PR_Q_BYTES);   // used in the even CTA: both CTAs' loads land
+  uint64_t* empty_bar = full_bar + R_MAX_STAGES;   // in each CTA: multicast commit
+  uint64_t* tfull_bar = empty_bar + R_MAX_STAGES;  // [2] in each CTA: multicast commit
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2] even CTA: the epilogue warps of BOTH CTAs
+  uint64_t* a2full_bar = tempty_bar + 2;           // [2] even CTA: both epilogues
+  uint64_t* a2empty_bar = a2full_bar + 2;          // [2] in each CTA: multicast commit
+  uint64_t* d2full_bar = a2empty_bar + 2;          // [2] in each CTA: multicast commit
+  uint64_t* d2empty_bar = d2full_bar + 2;          // [2] even CTA: both read-outs
+  uint64_t* b_bar = d2empty_bar + 2;               // even CTA: both half slices
+  uint64_t* q_bar = b_bar + 1;                     // even CTA: both q halves
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = static_cast<int>(cluster_ctarank());
+  const bool leader = crank == 0;
+  const int pid = static_cast<int>(blockIdx.x) >> 1;
+  const int npairs = static_cast<int>(gridDim.x) >> 1;
+  const int h = pid % P.H;
+  const int slot = pid / P.H;
+  const int nslots = (npairs - h + P.H - 1) / P.H;
+  const int ntiles = (P.S + 2 * DBM - 1) / (2 * DBM);   // pair tiles of 256 tokens
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < R_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 2 * R_EPI_WARPS);
+      mbar_init(&a2full_bar[i], 2 * R_EPI_WARPS);
+      mbar_init(&a2empty_bar[i], 1);
+      mbar_init(&d2full_bar[i], 1);
+      mbar_init(&d2empty_bar[i], 2 * R_OUT_WARPS);
+    }
+    mbar_init(b_bar, 1);
+    mbar_init(q_bar, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&P.a_map);
+    tma_prefetch_desc(&P.b_half_map);
+    tma_prefetch_desc(&P.q_half_map);
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, R_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's loads, commits and arrivals target this CTA's barriers: all initialised first
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // both CTAs load their halves; every completion is counted on the even CTA's barriers
+      const uint32_t qb = cluster_map_shared(smem_u32(q_bar), 0), bb = cluster_map_shared(smem_u32(b_bar), 0);
+      if (leader) {
+        mbar_expect_tx(q_bar, 2 * PR_Q_BYTES);
+        mbar_expect_tx(b_bar, 2u * static_cast<uint32_t>(P.nkb) * PR_B_KB_BYTES);
+      }
+      tma_load_2d_pair(sQ, &P.q_half_map, qb, 0, h * P.qpk + crank * 8);
+      tma_load_2d_pair(sQ + PR_Q_BYTES / 2, &P.q_half_map, qb, 64, h * P.qpk + crank * 8);
+      for (int kb = 0; kb < P.nkb; ++kb)
+        tma_load_2d_pair(sB + kb * PR_B_KB_BYTES, &P.b_half_map, bb, kb * DBK, h * D + crank * 64);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = slot; tile < ntiles; tile += nslots) {
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * D_A_BYTES);
+          tma_load_2d_pair(sA + s * D_A_BYTES, &P.a_map, cluster_map_shared(smem_u32(&full_bar[s]), 0), kb * DBK,
+                           (2 * tile + crank) * DBM);
+          if (++s == R_STAGES) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * DBM, D, 0, 0);
+      constexpr uint64_t kKStep = 32 >> 4, kStageStep = D_A_BYTES >> 4, kBlockStep = PR_B_KB_BYTES >> 4;
+      if (elect_one()) {
+        mbar_wait_cluster(b_bar, 0);
+        const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA), 16, 1024);
+        const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB), 16, 1024);
+        uint64_t a_desc = a_desc0;
+        int s = 0, acc = 0;
+        uint32_t ph = 0, acc_ph = 0u;
+        for (int tile = slot; tile < ntiles; tile += nslots) {
+          mbar_wait_cluster(&tempty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * D);
+          uint64_t b_desc = b_desc0;
+          for (int kb = 0; kb < P.nkb; ++kb) {
+            mbar_wait_cluster(&full_bar[s], ph);
+            tc_fence_after();
+            umma_bf16_ss_pair(d_addr, a_desc, b_desc, idesc, kb > 0 ? 1u : 0u);
+            umma_bf16_ss_pair(d_addr, a_desc + kKStep, b_desc + kKStep, idesc, 1u);
+            umma_bf16_ss_pair(d_addr, a_desc + 2 * kKStep, b_desc + 2 * kKStep, idesc, 1u);
+            umma_bf16_ss_pair(d_addr, a_desc + 3 * kKStep, b_desc + 3 * kKStep, idesc, 1u);
+            umma_commit_pair(&empty_bar[s]);
+            b_desc += kBlockStep;
+            a_desc += kStageStep;
+            if (++s == R_STAGES) {
+              s = 0;
+              ph ^= 1u;
+              a_desc = a_desc0;
+            }
+          }
+          umma_commit_pair(&tfull_bar[acc]);
+          acc_ph ^= 1u << acc;
+          acc ^= 1;
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 2) {
+    if (leader) {
+      // scores[256 x 16] = K^rot (each CTA's tensor memory) * Q^T (8 q rows from each CTA's shared memory)
+      constexpr uint32_t idesc2 = umma_idesc_bf16(2 * DBM, R_QROWS, 0, 0);
+      if (elect_one()) {
+        mbar_wait_cluster(q_bar, 0);
+        const uint64_t q_desc0 = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+        int b = 0;
+        uint32_t bph = 0u;
+        for (int tile = slot; tile < ntiles; tile += nslots) {
+          mbar_wait_cluster(&a2full_bar[b], (bph >> b) & 1u);
+          mbar_wait_cluster(&d2empty_bar[b], ((bph >> b) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t a2 = tmem_base + R_COL_A2 + static_cast<uint32_t>(b * 64);
+          const uint32_t d2 = tmem_base + R_COL_D2 + static_cast<uint32_t>(b * 32);
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k)
+            umma_bf16_ts_pair(d2, a2 + static_cast<uint32_t>(k * 8),
+                              q_desc0 + static_cast<uint64_t>(((k >> 2) * (PR_Q_BYTES / 2) + (k & 3) * 32) >> 4), idesc2,
+                              k > 0 ? 1u : 0u);
+          umma_commit_pair(&d2full_bar[b]);
+          umma_commit_pair(&a2empty_bar[b]);
+          bph ^= 1u << b;
+          b ^= 1;
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4 && warp < 4 + R_EPI_WARPS) {
+    // ===== epilogue (as in decode_scores_mma2_kernel): K^ row -> bf16 -> RoPE -> tensor memory, on this CTA's tokens =====
+    const int qd = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int row = qd * 32 + lane;
+    const int d0 = half * 32;
+    const bool rope = P.cos != nullptr;
+    const uint32_t tempty0 = cluster_map_shared(smem_u32(&tempty_bar[0]), 0);
+    const uint32_t a2full0 = cluster_map_shared(smem_u32(&a2full_bar[0]), 0);
+    int acc = 0;
+    uint32_t acc_ph = 0u;
+    for (int tile = slot; tile < ntiles; tile += nslots) {
+      const int tok = (2 * tile + crank) * DBM + row;
+      uint32_t cs[16], sn[16];
+      if (rope && tok < P.S) {
+        const uint4* cp = reinterpret_cast<const uint4*>(P.cos + static_cast<long long>(tok) * P.ld_cs + d0);
+        const uint4* sp = reinterpret_cast<const uint4*>(P.sin + static_cast<long long>(tok) * P.ld_cs + d0);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const uint4 cv = __ldg(cp + v), sv = __ldg(sp + v);
+          cs[4 * v] = cv.x, cs[4 * v + 1] = cv.y, cs[4 * v + 2] = cv.z, cs[4 * v + 3] = cv.w;
+          sn[4 * v] = sv.x, sn[4 * v + 1] = sv.y, sn[4 * v + 2] = sv.z, sn[4 * v + 3] = sv.w;
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < 16; ++v) cs[v] = 0x3F803F80u, sn[v] = 0u;   // cos = 1, sin = 0
+      }
+      mbar_wait(&tfull_bar[acc], (acc_ph >> acc) & 1u);
+      tc_fence_after();
+      const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
+      const uint32_t lane_addr = lane_base + static_cast<uint32_t>(acc * D);
+      uint32_t lo_w[16], hi_w[16];
+      {
+        uint32_t x1[32], x2[32];
+        __syncwarp();
+        tmem_ld_32x32(lane_addr + static_cast<uint32_t>(d0), x1);
+        tmem_ld_32x32(lane_addr + static_cast<uint32_t>(D / 2 + d0), x2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          lo_w[j] = pack_bf16x2(__uint_as_float(x1[2 * j]), __uint_as_float(x1[2 * j + 1]));
+          hi_w[j] = pack_bf16x2(__uint_as_float(x2[2 * j]), __uint_as_float(x2[2 * j + 1]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty0 + static_cast<uint32_t>(acc * 8));
+      if (rope) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const __nv_bfloat162 k1 = *reinterpret_cast<const __nv_bfloat162*>(&lo_w[j]);
+          const __nv_bfloat162 k2 = *reinterpret_cast<const __nv_bfloat162*>(&hi_w[j]);
+          const __nv_bfloat162 cw = *reinterpret_cast<const __nv_bfloat162*>(&cs[j]);
+          const __nv_bfloat162 sw = *reinterpret_cast<const __nv_bfloat162*>(&sn[j]);
+          const __nv_bfloat162 o1 = __hadd2(__hmul2(k1, cw), __hmul2(__hneg2(k2), sw));
+          const __nv_bfloat162 o2 = __hadd2(__hmul2(k2, cw), __hmul2(k1, sw));
+          lo_w[j] = *reinterpret_cast<const uint32_t*>(&o1);
+          hi_w[j] = *reinterpret_cast<const uint32_t*>(&o2);
+        }
+      }
+      mbar_wait(&a2empty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t a2 = lane_base + R_COL_A2 + static_cast<uint32_t>(acc * 64);
+      __syncwarp();
+      tmem_st_32x16(a2 + static_cast<uint32_t>(d0 / 2), lo_w);
+      tmem_st_32x16(a2 + static_cast<uint32_t>(32 + d0 / 2), hi_w);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(a2full0 + static_cast<uint32_t>(acc * 8));
+      acc_ph ^= 1u << acc;
+      acc ^= 1;
+    }
+  } else if (warp >= 4 + R_EPI_WARPS) {
+    // ===== score read-out: one warp per TMEM lane quarter, thread = token =====
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t d2empty0 = cluster_map_shared(smem_u32(&d2empty_bar[0]), 0);
+    int b = 0;
+    uint32_t bph = 0u;
+    for (int tile = slot; tile < ntiles; tile += nslots) {
+      const int tok = (2 * tile + crank) * DBM + row;
+      mbar_wait(&d2full_bar[b], (bph >> b) & 1u);
+      tc_fence_after();
+      uint32_t v[8];
+      __syncwarp();
+      tmem_ld_32x8(tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + R_COL_D2 + static_cast<uint32_t>(b * 32), v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(d2empty0 + static_cast<uint32_t>(b * 8));
+      if (tok < P.S) {
+#pragma unroll
+        for (int g = 0; g < D_MAX_QPK; ++g)
+          if (g < P.qpk) P.scores[static_cast<long long>(h * P.qpk + g) * P.ld_scores + tok] = __uint_as_float(v[g]) * P.scale;
+      }
+      bph ^= 1u << b;
+      b ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // nobody leaves (or frees tensor memory) while the pair's MMAs, commits or arrivals are pending
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, R_TMEM_COLS);
+  }
+}
+
 // Softmax over L = S + T scores of one q-head in ONE launch, with chunk-local maxima (flash-decoding style): chunk c of
 // the compressed prefix is exactly the token range of split-K slab c of U = P A_v (kps k-blocks of 64 tokens), chunk
 // `nchunk_s` is the dense tail.  A CTA takes the maximum m_c of its chunk, writes p = exp(s - m_c) as bf16 (the GEMM
@@ -1065,7 +1352,8 @@ static inline int decode_split_k(int S, int rv) {
 }
 
 static bool g_force_tiled_scores = false;  // test hook: exercise the tile-per-CTA scores kernel
-static int g_scores_variant = 0;           // test hook: 0 automatic, 1 FFMA epilogue, 2 score MMA without cluster
+static int g_scores_variant = 0;           // test hook: 0 automatic, 1 FFMA epilogue, 2 score MMA in single CTAs, 3 CTA pairs
+static int g_scores_stages = 0;            // tuning hook: cap on the TMA ring depth of the score-MMA kernels (0: as many slots as fit)
 static int g_scores_cluster = 0;           // test / tuning hook: cluster size of the score-MMA kernel (0 automatic, 1, 2, 4, 8)
 
 // Launch the score-MMA kernel as clusters of CL CTAs (CL adjacent kv heads share every A_k tile by TMA multicast).
@@ -1119,6 +1407,51 @@ static int launch_scores_mma2(const ScoreParams& sp, int S, int H, cudaStream_t 
   return 0;
 }
 
+// Launch the pair kernel: one cluster of two CTAs per (kv head, slot).  Returns 0 on success, -1 when the device cannot
+// hold such a cluster (the caller falls back to the single-CTA kernels).
+static int launch_scores_pair(ScoreParams& sp, int S, int H, cudaStream_t st) {
+  static PerDevice<int> state;   // 0: not probed, -1: not launchable, > 0: resident pairs
+  int& resident = state();
+  sp.stages = pair_stages_for(sp.nkb);
+  if (sp.stages < 3) return -1;
+  if (g_scores_stages >= 3 && g_scores_stages < sp.stages) sp.stages = g_scores_stages;
+#ifdef XKV_PROBE
+  if (g_probe_stages > 0 && g_probe_stages < sp.stages) sp.stages = g_probe_stages;
+#endif
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.blockDim = dim3(R_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = PR_FIXED_BYTES + static_cast<size_t>(sp.nkb) * PR_B_KB_BYTES + static_cast<size_t>(sp.stages) * D_A_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (resident == 0) {
+    resident = -1;
+    if (cudaFuncSetAttribute(decode_scores_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(R_SMEM_LIMIT)) == cudaSuccess) {
+      int n = 0;
+      cfg.gridDim = dim3(2, 1, 1);
+      const size_t launch_smem = cfg.dynamicSmemBytes;
+      cfg.dynamicSmemBytes = R_SMEM_LIMIT;   // one CTA per SM whatever the rank
+      if (cudaOccupancyMaxActiveClusters(&n, decode_scores_pair_kernel, &cfg) == cudaSuccess && n >= 1) resident = n;
+      cfg.dynamicSmemBytes = launch_smem;
+    }
+    (void)cudaGetLastError();
+  }
+  if (resident < 0) return -1;
+  const int ptiles = (S + 2 * DBM - 1) / (2 * DBM);
+  int npairs = resident < ptiles * H ? resident : ptiles * H;
+  if (npairs < H) npairs = H;   // every head needs at least one pair
+  cfg.gridDim = dim3(2 * npairs, 1, 1);
+  XKV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_scores_pair_kernel, sp));
+  return 0;
+}
+
 // scores[hq][t] = scale * q_hq . rope(bf16(A_k[t] Bk_l^T)) for the S tokens of the compressed prefix: fused reconstruct +
 // RoPE + q.K, one launch (kernel chosen by head_dim, rank and the test hooks)
 static int launch_scores(const void* q, int Hq, int H, int D, const void* A_k, int64_t lda_k, int rk, const void* Vk_layer,
@@ -1137,6 +1470,10 @@ static int launch_scores(const void* q, int Hq, int H, int D, const void* A_k, i
   const bool q_tma_ok = D == 128 && (reinterpret_cast<uintptr_t>(q) & 15) == 0;
   if (q_tma_ok) {
     rc = encode_tmap_2d_bf16(&sp.q_map, q, D, Hq, D, 64, R_QROWS);
+    if (rc) return rc;
+    rc = encode_tmap_2d_bf16(&sp.q_half_map, q, D, Hq, D, 64, 8);
+    if (rc) return rc;
+    rc = encode_tmap_2d_bf16(&sp.b_half_map, Vk_layer, rk, static_cast<uint64_t>(H) * D, ldv_k, DBK, 64);
     if (rc) return rc;
   }
   // cluster size of the score-MMA kernel: the largest of 8, 4, 2 that divides the kv-head count (tuning hook: xkv_decode_set_cluster)
@@ -1183,6 +1520,17 @@ static int launch_scores(const void* q, int Hq, int H, int D, const void* A_k, i
     XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_persistent_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(P_SMEM_BYTES)));
     configured() = true;
+  }
+  // CTA pairs (half a slice per CTA, deep ring) when the head layout allows the score MMA: the default for head_dim 128
+  if (D == 128 && q_tma_ok && qpk <= 8 && !g_force_tiled_scores && g_scores_cluster <= 1 &&
+      (g_scores_variant == 0 || g_scores_variant == 3)) {
+    const int prc = launch_scores_pair(sp, S, H, st);
+    if (prc > 0) return prc;
+    if (prc == 0) {
+      XKV_LAUNCHED();
+      return 0;
+    }
+    sp.stages = r_stages_for(sp.nkb);
   }
   // persistent kernel when one head's slice of the right factor fits in shared memory
   const bool persistent = static_cast<size_t>(sp.nkb) * D * DBK * 2 <= PB_MAX_BYTES && !g_force_tiled_scores;
@@ -1425,6 +1773,8 @@ extern "C" void xkv_decode_force_tiled(int on) { g_force_tiled_scores = on != 0;
 extern "C" void xkv_decode_set_variant(int variant) { g_scores_variant = variant; }
 /* tuning hook: cluster size of the score-MMA kernel (0 automatic) */
 extern "C" void xkv_decode_set_cluster(int cluster) { g_scores_cluster = cluster; }
+
+extern "C" void xkv_decode_set_stages(int stages) { g_scores_stages = stages; }
 
 extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const void* A_k, int64_t lda_k, int rk,
                                     const void* Vk_layer, int64_t ldv_k, const void* A_v, int64_t lda_v, int rv,
