@@ -172,17 +172,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       kb_layer = (kb0 * BK) / pr.layer_cols;
       kb_col = kb0 * BK - kb_layer * pr.layer_cols;
     }
-    int s = 0;
-    uint32_t ph = 0;
-    for (int it = 0; it < niter; ++it) {
-      const int kb = kb0 + it / pr.nterms;
-      const int term = it - (it / pr.nterms) * pr.nterms;
-      const CUtensorMap* amap = &pr.a_map[pr.ta[term]];
-      const CUtensorMap* bmap = &pr.b_map[pr.tb[term]];
-      uint8_t* sA = smem + s * STAGE_BYTES;
-      uint8_t* sB = sA + A_TILE_BYTES;
-      mbar_wait(&empty_bar[s], ph ^ 1u);
-      if (elect_one()) {
+    // One elected lane runs the whole loop (waits included): no re-election / reconvergence per k block, the loop state
+    // stays in uniform registers, and (term, k block) advance without a division.
+    if (elect_one()) {
+      int s = 0, term = 0, kb = kb0;
+      uint32_t ph = 0;
+      for (int it = 0; it < niter; ++it) {
+        const CUtensorMap* amap = &pr.a_map[pr.ta[term]];
+        const CUtensorMap* bmap = &pr.b_map[pr.tb[term]];
+        uint8_t* sA = smem + s * STAGE_BYTES;
+        uint8_t* sB = sA + A_TILE_BYTES;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
         if (A_MN == 0) {
           if (pr.a_layers)
@@ -206,61 +206,72 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
           for (int c = 0; c < BN / 64; ++c)
             tma_load_2d(sB + c * CHUNK_BYTES, b_chunk_map[c] ? b_chunk_map[c] : bmap, &full_bar[s], b_chunk_col[c], kb * BK);
         }
-      }
-      __syncwarp();
-      // layered operands take one term: every iteration is a new k block
-      if (!A_MN && pr.a_layers && (ka_col += BK) >= pr.layer_cols) {
-        ka_col -= pr.layer_cols;
-        ++ka_layer;
-      }
-      if (!B_MN && pr.b_layers && (kb_col += BK) >= pr.layer_cols) {
-        kb_col -= pr.layer_cols;
-        ++kb_layer;
-      }
-      if (++s == STAGES) {
-        s = 0;
-        ph ^= 1u;
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp in the loop, one elected lane issues) =====================
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
-    int s = 0;
-    uint32_t ph = 0;
-    int it = 0;
-    for (int phs = 0; phs < nph; ++phs) {
-      const uint32_t acc = tmem_base + static_cast<uint32_t>(phs & 1) * TMEM_COLS;
-      if (phs >= 2) {   // the epilogue must have drained this accumulator (phase phs - 2)
-        mbar_wait(&tmem_empty_bar[phs & 1], static_cast<uint32_t>(((phs >> 1) - 1) & 1));
-        tc_fence_after();
-      }
-      const int it_end = (nph == 1) ? niter : static_cast<int>((static_cast<long long>(nk) * (phs + 1)) / nph) * pr.nterms;
-      const int it_begin = it;
-      for (; it < it_end; ++it) {
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t b_base = a_base + A_TILE_BYTES;
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = A_MN ? umma_desc_sw128(a_base + k * 2048, CHUNK_BYTES, 1024)
-                                     : umma_desc_sw128(a_base + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? umma_desc_sw128(b_base + k * 2048, CHUNK_BYTES, 1024)
-                                     : umma_desc_sw128(b_base + k * 32, 16, 1024);
-            umma_bf16_ss(acc, da, db, idesc, (it > it_begin || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+        // layered operands take one term: every iteration is a new k block
+        if (!A_MN && pr.a_layers && (ka_col += BK) >= pr.layer_cols) {
+          ka_col -= pr.layer_cols;
+          ++ka_layer;
         }
-        __syncwarp();
+        if (!B_MN && pr.b_layers && (kb_col += BK) >= pr.layer_cols) {
+          kb_col -= pr.layer_cols;
+          ++kb_layer;
+        }
+        if (++term == pr.nterms) {
+          term = 0;
+          ++kb;
+        }
         if (++s == STAGES) {
           s = 0;
           ph ^= 1u;
         }
       }
-      if (elect_one()) umma_commit(&tmem_full_bar[phs & 1]);  // this phase's accumulator is complete
-      __syncwarp();
     }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer: one elected lane runs the whole loop =====================
+    // (see decode_scores_mma2_kernel: a warp-converged loop that re-elects a lane and rebuilds the descriptors every k
+    // block costs ~300 clk of issue per block; the descriptors advance by 64-bit adds on the start-address field,
+    // 16-byte units, no carry below 256 KiB)
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    constexpr uint64_t kStageStep = STAGE_BYTES >> 4;
+    constexpr uint64_t kAStep = (A_MN ? 2048 : 32) >> 4, kBStep = (B_MN ? 2048 : 32) >> 4;
+    if (elect_one()) {
+      const uint32_t a_base0 = smem_u32(smem);
+      const uint64_t a_desc0 = A_MN ? umma_desc_sw128(a_base0, CHUNK_BYTES, 1024) : umma_desc_sw128(a_base0, 16, 1024);
+      const uint64_t b_desc0 = B_MN ? umma_desc_sw128(a_base0 + A_TILE_BYTES, CHUNK_BYTES, 1024)
+                                    : umma_desc_sw128(a_base0 + A_TILE_BYTES, 16, 1024);
+      uint64_t a_desc = a_desc0, b_desc = b_desc0;
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int phs = 0; phs < nph; ++phs) {
+        const uint32_t acc = tmem_base + static_cast<uint32_t>(phs & 1) * TMEM_COLS;
+        if (phs >= 2) {   // the epilogue must have drained this accumulator (phase phs - 2)
+          mbar_wait(&tmem_empty_bar[phs & 1], static_cast<uint32_t>(((phs >> 1) - 1) & 1));
+          tc_fence_after();
+        }
+        const int it_end = (nph == 1) ? niter : static_cast<int>((static_cast<long long>(nk) * (phs + 1)) / nph) * pr.nterms;
+        const int it_begin = it;
+        for (; it < it_end; ++it) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          umma_bf16_ss(acc, a_desc, b_desc, idesc, it > it_begin ? 1u : 0u);
+          umma_bf16_ss(acc, a_desc + kAStep, b_desc + kBStep, idesc, 1u);
+          umma_bf16_ss(acc, a_desc + 2 * kAStep, b_desc + 2 * kBStep, idesc, 1u);
+          umma_bf16_ss(acc, a_desc + 3 * kAStep, b_desc + 3 * kBStep, idesc, 1u);
+          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+          a_desc += kStageStep;
+          b_desc += kStageStep;
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1u;
+            a_desc = a_desc0;
+            b_desc = b_desc0;
+          }
+        }
+        umma_commit(&tmem_full_bar[phs & 1]);  // this phase's accumulator is complete
+      }
+    }
+    __syncwarp();
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may access
