@@ -192,44 +192,64 @@ def compress_groups_from_host(
     main = torch.cuda.current_stream(device)
     copy_s = _side_stream(device, 101)
     back_s = _side_stream(device, 102)
+    # The K side and the V side of a chunk are independent factorisations: each starts as soon as ITS tensors have landed
+    # (V is sent first: its chain is the longer one and runs under the K copy; what remains after the last byte arrives
+    # is one K chain + the copy-back of its factors), on its own stream.
+    side_s = {"v": _side_stream(device, 103), "k": _side_stream(device, 104)}
     # device staging for every group, allocated on the main stream (the copy stream only writes into it)
     dk, dv = staging if staging is not None else host_staging(h_keys, h_values, device)
     copy_s.wait_stream(main)
-    ready = []
+    for st in side_s.values():
+        st.wait_stream(main)
+    sides = (["v"] if rank_v is not None else []) + (["k"] if rank_k is not None else [])
+    ready = {"k": [], "v": []}
     with torch.cuda.stream(copy_s):
         for lo in range(0, ng, chunk_groups):
-            for g in range(lo, min(lo + chunk_groups, ng)):
-                for d, h in zip(dk[g], h_keys[g]):
-                    d.copy_(h, non_blocking=True)
-                for d, h in zip(dv[g], h_values[g]):
-                    d.copy_(h, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_s)
-            ready.append(ev)
-    out: List[GroupFactors] = []
-    host_tensors: Optional[List[torch.Tensor]] = [] if host_out is not None else None
-    k = 0
+            for side in ("v", "k"):
+                dst, src = (dv, h_values) if side == "v" else (dk, h_keys)
+                for g in range(lo, min(lo + chunk_groups, ng)):
+                    for d, h in zip(dst[g], src[g]):
+                        d.copy_(h, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_s)
+                ready[side].append(ev)
+    kf: List[Optional[factorize.Factors]] = [None] * ng
+    vf: List[Optional[factorize.Factors]] = [None] * ng
+    slot = {side: i for i, side in enumerate(x for x in ("k", "v") if x in sides)}   # host_out: [A, Vt] per compressed side, K first
+    host_tensors: Optional[List[Optional[torch.Tensor]]] = [None] * (2 * len(sides) * ng) if host_out is not None else None
     for c, lo in enumerate(range(0, ng, chunk_groups)):
         hi = min(lo + chunk_groups, ng)
-        main.wait_event(ready[c])
         keys = [[t.transpose(1, 2) for t in dk[g]] for g in range(lo, hi)]
         vals = [[t.transpose(1, 2) for t in dv[g]] for g in range(lo, hi)]
-        res = compress_groups(keys, vals, rank_k, rank_v, opts=opts, num_streams=num_streams)
-        out.extend(res)
-        if host_out is not None:
-            done = torch.cuda.Event()
-            done.record(main)
-            back_s.wait_event(done)
-            with torch.cuda.stream(back_s):
-                for gf in res:
-                    for f in (gf.key, gf.value):
-                        for t in (f.A, f.Vt):
+        for side in sides:
+            st = side_s[side]
+            st.wait_event(ready[side][c])
+            with torch.cuda.stream(st):
+                res = compress_groups(keys, vals, rank_k, rank_v, merge_key=side == "k", merge_value=side == "v", opts=opts,
+                                      num_streams=max(1, num_streams // 2))
+                done = torch.cuda.Event()
+                done.record(st)
+            for g, gf in zip(range(lo, hi), res):
+                f = gf.key if side == "k" else gf.value
+                (kf if side == "k" else vf)[g] = f
+                for t in (f.A_storage, f.Vt, f.V, f.sigma_lead):
+                    if t is not None:
+                        t.record_stream(main)
+            if host_out is not None:
+                back_s.wait_event(done)
+                with torch.cuda.stream(back_s):
+                    for g in range(lo, hi):
+                        f = kf[g] if side == "k" else vf[g]
+                        for j, t in enumerate((f.A, f.Vt)):
+                            k = 2 * len(sides) * g + 2 * slot[side] + j
                             host_out[k].copy_(t, non_blocking=True)
                             t.record_stream(back_s)
-                            host_tensors.append(host_out[k])
-                            k += 1
+                            host_tensors[k] = host_out[k]
+    for st in side_s.values():
+        main.wait_stream(st)
     main.wait_stream(back_s)
     main.wait_stream(copy_s)
+    out = [GroupFactors(layers=list(range(len(h_keys[g]))), key=kf[g], value=vf[g]) for g in range(ng)]
     return out, host_tensors
 
 
