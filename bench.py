@@ -67,7 +67,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip strong / token_sharded / append / other_configs / gpu_reference")
-    ap.add_argument("--streams", type=int, default=6, help="CUDA streams the K / V batches are spread over")
+    ap.add_argument("--streams", type=int, default=8, help="CUDA streams the K / V batches are spread over")
     ap.add_argument("--e2e-chunk", type=int, default=1, help="layer groups per pipelined chunk of the host-buffer path")
     ap.add_argument("--packed", action="store_true", help="gather every group into a packed matrix first (round 1's path) "
                     "instead of reading the layer tensors in place")
