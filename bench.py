@@ -71,6 +71,7 @@ def parse_args():
     ap.add_argument("--e2e-chunk", type=int, default=1, help="layer groups per pipelined chunk of the host-buffer path")
     ap.add_argument("--packed", action="store_true", help="gather every group into a packed matrix first (round 1's path) "
                     "instead of reading the layer tensors in place")
+    ap.add_argument("--factorize-opts", default="", help="JSON of FactorizeOptions overrides for the timed step (tuning experiments)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from the host instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -317,7 +318,7 @@ class CompressStep:
         from xkv_b200 import compress, factorize
 
         self.torch = ctx.torch
-        self.opts = factorize.FactorizeOptions()
+        self.opts = factorize.FactorizeOptions(**json.loads(getattr(ctx.args, "factorize_opts", "") or "{}"))
         sizes = [len(k) for k in keys]
         self.calls = []
         for size in sorted(set(sizes), reverse=True):

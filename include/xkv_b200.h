@@ -290,7 +290,7 @@ XKV_API int xkv_decode_attention_lse(const void* q, int Hq, int H, int D, const 
 XKV_API void xkv_decode_force_tiled(int on);
 /* test hook: persistent scores kernel to use where several apply: 0 automatic (head_dim 128: score MMA in CTA pairs,
  * cta_group::2, half a right-factor slice per CTA), 1 FFMA epilogue, 2 score MMA with one independent CTA per kv head,
- * 3 CTA pairs */
+ * 3 CTA pairs; 4 = automatic scores kernel, but slab reduction and combine as two launches (default: one cluster launch) */
 XKV_API void xkv_decode_set_variant(int variant);
 /* tuning hook: cluster size of the score-MMA kernel, i.e. how many adjacent kv heads share one multicast copy of each
  * A_k tile: 0 automatic, else 1, 2, 4 or 8 (reduced to a divisor of the kv-head count the device can keep resident) */

@@ -18,6 +18,7 @@ VARIANTS = {          # name -> (force_tiled, variant, cluster)
     "cl8": (0, 0, 8),
     "tiled": (1, 0, 0),    # tile-per-CTA kernel (right-factor slice does not fit in shared memory)
     "ffma": (0, 1, 0),     # persistent kernel with the FFMA epilogue (the head_dim 64 path)
+    "split_rc": (0, 4, 0), # slab reduction and combine as two launches (default: one cluster launch)
 }
 
 

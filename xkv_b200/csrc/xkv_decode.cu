@@ -13,8 +13,12 @@
 //            ever formed.
 //   tail     decode tokens appended after prefill stay dense and exact (reference: mode='decode' skips
 //            merging, cache:131); their scores / values join the same softmax.
+#include <cooperative_groups.h>
+
 #include "xkv_common.cuh"
 #include "xkv_host.h"
+
+namespace cg = cooperative_groups;
 
 namespace xkv {
 
@@ -1273,6 +1277,75 @@ __global__ void __launch_bounds__(256) combine_kernel(const float* __restrict__ 
   }
 }
 
+// Slab reduction and combine in ONE launch: the RC_CL CTAs of a thread-block cluster share a q head.  CTA c sums its
+// rv / RC_CL columns of U over the split-K slabs (weighted by exp(m_s - m), fixed order: deterministic), writes them into
+// the shared memory of every CTA of the cluster (distributed shared memory), and after one cluster barrier each CTA
+// contracts the whole U row with ITS D / RC_CL rows of the layer's value factor.  Replaces reduce_u_kernel +
+// combine_kernel (two launches and a round trip of U through L2) on the Llama path.
+constexpr int RC_CL = 8;
+__global__ void __launch_bounds__(256) reduce_combine_kernel(const float* __restrict__ slabs, int nslabs, long long slab_stride,
+                                                             int rv, const __nv_bfloat16* __restrict__ Bv, long long ldb,
+                                                             const __nv_bfloat16* __restrict__ prob, long long ldp, int S, int T,
+                                                             const __nv_bfloat16* __restrict__ v_tail, long long sh, long long st,
+                                                             const float* __restrict__ rowsum, int qpk, int D,
+                                                             __nv_bfloat16* __restrict__ out,
+                                                             const float* __restrict__ chunk_max, int nchunks,
+                                                             float* __restrict__ lse_out) {
+  extern __shared__ float u_s[];  // rv floats: the whole U row of this head, filled by the cluster
+  __shared__ float part[128];
+  __shared__ float w_s[SM_MAX_CHUNKS];
+  __shared__ float stats[2];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cr = static_cast<int>(cluster.block_rank());   // == blockIdx.y
+  const int hq = blockIdx.x, h = hq / qpk;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cpc = (rv + RC_CL - 1) / RC_CL;                // columns of U this CTA reduces (<= 128)
+  const int el = threadIdx.x & 127, g = threadIdx.x >> 7;
+  const int j = cr * cpc + el;
+  const bool active = el < cpc && j < rv;
+  const long long e = static_cast<long long>(hq) * rv + j;
+  float v[32];   // slabs g, g + 2, ...: all loads in flight while warp 0 works the weights out
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int sl = g + 2 * k;
+    v[k] = (active && sl < nslabs) ? slabs[sl * slab_stride + e] : 0.f;
+  }
+  head_weights(chunk_max, rowsum, hq, nchunks, w_s, stats);
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const int sl = g + 2 * k;
+    if (sl < nslabs) a[k & 3] = fmaf(w_s[sl], v[k], a[k & 3]);
+  }
+  const float mine = (a[0] + a[1]) + (a[2] + a[3]);
+  if (g == 1) part[el] = mine;
+  __syncthreads();
+  if (g == 0 && active) {
+    const float u = mine + part[el];
+#pragma unroll
+    for (int r = 0; r < RC_CL; ++r) cluster.map_shared_rank(u_s, r)[j] = u;
+  }
+  cluster.sync();
+  const float m = stats[0], rs = stats[1];
+  const float inv = 1.f / rs;
+  const float w_tail = T > 0 ? w_s[nchunks - 1] : 0.f;
+  if (lse_out != nullptr && cr == 0 && threadIdx.x == 0) lse_out[hq] = m + logf(rs);
+  const int dpc = (D + RC_CL - 1) / RC_CL;                 // output dims of this CTA
+  for (int d = cr * dpc + warp; d < min(D, (cr + 1) * dpc); d += 8) {
+    const __nv_bfloat16* row = Bv + static_cast<long long>(h * D + d) * ldb;
+    float acc = 0.f;
+    for (int jj = lane * 2; jj < rv; jj += 64) {
+      const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(row + jj);
+      acc = fmaf(u_s[jj], __bfloat162float(b2.x), fmaf(u_s[jj + 1], __bfloat162float(b2.y), acc));
+    }
+    float acc_t = 0.f;
+    for (int t = lane; t < T; t += 32)
+      acc_t = fmaf(__bfloat162float(prob[hq * ldp + S + t]), __bfloat162float(v_tail[h * sh + t * st + d]), acc_t);
+    acc = warp_sum(fmaf(w_tail, acc_t, acc));
+    if (lane == 0) out[hq * D + d] = __float2bfloat16_rn(acc * inv);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Absorbed attention over the token factor (MLA latents, deepseek_v2.py:217-235): the latent of token t is
 // c_t = V_l a_t and both products of the attention are LINEAR in it (kv_b_proj after a per-token RMS scale), so with
@@ -1353,6 +1426,7 @@ static inline int decode_split_k(int S, int rv) {
 
 static bool g_force_tiled_scores = false;  // test hook: exercise the tile-per-CTA scores kernel
 static int g_scores_variant = 0;           // test hook: 0 automatic, 1 FFMA epilogue, 2 score MMA in single CTAs, 3 CTA pairs
+static bool g_split_reduce_combine = false;   // test hook (variant 4): slab reduction and combine as two launches
 static int g_scores_stages = 0;            // tuning hook: cap on the TMA ring depth of the score-MMA kernels (0: as many slots as fit)
 static int g_scores_cluster = 0;           // test / tuning hook: cluster size of the score-MMA kernel (0 automatic, 1, 2, 4, 8)
 
@@ -1658,7 +1732,30 @@ extern "C" int xkv_decode_attention_lse(const void* q, int Hq, int H, int D, con
   gp.split_stride = static_cast<long long>(Hq) * rv;
   rc = xkv_gemm_grouped(&gp, 1, stream);
   if (rc) return rc;
-  // ---- o = (U Bv_l^T + P_tail V_tail) / rowsum, U reduced over the split-K slabs on the fly ----
+  // ---- o = (U Bv_l^T + P_tail V_tail) / rowsum, U reduced over the split-K slabs by the same launch ----
+  if (rv <= 128 * RC_CL && split <= 64 && !g_split_reduce_combine) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(Hq, RC_CL, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.dynamicSmemBytes = rv * sizeof(float);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = RC_CL;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    XKV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, reduce_combine_kernel, static_cast<const float*>(u_slabs), split,
+                                      static_cast<long long>(Hq) * rv, rv, static_cast<const __nv_bfloat16*>(Vv_layer),
+                                      static_cast<long long>(ldv_v), static_cast<const __nv_bfloat16*>(prob), ldl, S, T,
+                                      static_cast<const __nv_bfloat16*>(v_tail), static_cast<long long>(tail_stride_h),
+                                      static_cast<long long>(tail_stride_t), static_cast<const float*>(rowsum), qpk, D,
+                                      static_cast<__nv_bfloat16*>(out), static_cast<const float*>(chunk_max), nchunks, lse_out));
+    XKV_LAUNCHED();
+    return 0;
+  }
   float* U = u_slabs + static_cast<size_t>(split) * Hq * rv;
   reduce_u_kernel<<<dim3((rv + 63) / 64, Hq), 256, 0, st>>>(u_slabs, split, static_cast<long long>(Hq) * rv, rv, chunk_max,
                                                             rowsum, nchunks, U);
@@ -1770,7 +1867,10 @@ extern "C" int xkv_rope_bf16(void* x, int64_t ld_row, int rows, int H, int D, co
 
 extern "C" void xkv_decode_force_tiled(int on) { g_force_tiled_scores = on != 0; }
 /* test hook: which persistent scores kernel to use when several apply (0 automatic) */
-extern "C" void xkv_decode_set_variant(int variant) { g_scores_variant = variant; }
+extern "C" void xkv_decode_set_variant(int variant) {
+  g_split_reduce_combine = variant == 4;
+  g_scores_variant = variant == 4 ? 0 : variant;
+}
 /* tuning hook: cluster size of the score-MMA kernel (0 automatic) */
 extern "C" void xkv_decode_set_cluster(int cluster) { g_scores_cluster = cluster; }
 
