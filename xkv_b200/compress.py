@@ -131,12 +131,13 @@ def compress_groups(
         for lo in range(0, ng, size):
             jobs.append((dst, lo, src[lo:lo + size], rank))
     used = []
-    # Every chain on its own side stream, with CTA-level priorities 0 / -1 / -2 dealt round-robin: when SMs free up, the
+    # Every chain on its own side stream, with CTA-level priorities -1 / -2 / -3 dealt round-robin (0, the lowest, is what the
+    # projection GEMMs are launched with: xkv_host.h gemm_low_priority): when SMs free up, the
     # pending CTAs of a higher-priority chain go first, so one chain's latency-bound kernels (Cholesky clusters, Jacobi
     # windows) are not queued behind the hundreds of GEMM CTAs of another.  Measured (bench step, 10 steps, two runs):
     # no priorities, last job on the caller's stream 44.3 / 43.1 ms; all side streams 41.9; priorities 39.2 - 39.8 (8 jobs).
     for j, (dst, lo, groups, rank) in enumerate(jobs):
-        stream = main if num_streams <= 1 else _side_stream(dev, 200 + j, priority=-(j % 3))
+        stream = main if num_streams <= 1 else _side_stream(dev, 200 + j, priority=-1 - (j % 3))
         if stream is not main:
             stream.wait_stream(main)
             used.append(stream)

@@ -335,6 +335,7 @@ static int factorize_impl(const void* const* X_host, int layers, int layer_cols,
       p.out_bf16 = 1;
       ps.push_back(p);
     }
+    GemmLowPriorityScope low;
     return run_gemms(ps, stream, layers > 0 ? XKV_MAX_LAYER_MAPS / layers : XKV_MAX_GEMM_PROBLEMS);
   };
   if (phase == 4) return project();

@@ -17,6 +17,8 @@
 //               optionally transposed)
 // Problems are passed by value in __grid_constant__ parameter space (tensor maps included), so a
 // launch needs no device-side descriptor memory.
+#include <cstdlib>
+
 #include "xkv_common.cuh"
 #include "xkv_host.h"
 
@@ -504,6 +506,11 @@ static int build_problem(const xkv_gemm_problem& in, GemmProb& out, int& cta_cur
   return 0;
 }
 
+bool& gemm_low_priority() {
+  static thread_local bool low = false;
+  return low;
+}
+
 template <int A_MN, int B_MN>
 static int launch_variant(const GemmParams& params, int grid, cudaStream_t stream) {
   auto kern = gemm_kernel<A_MN, B_MN>;
@@ -513,7 +520,22 @@ static int launch_variant(const GemmParams& params, int grid, cudaStream_t strea
                                         static_cast<int>(GEMM_SMEM_BYTES)));
     configured() = true;
   }
-  kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(params);
+  if (gemm_low_priority()) {   // see xkv_host.h: the projection yields freed SMs to the other chains' small kernels
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributePriority;
+    attr[0].val.priority = 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    XKV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, params));
+  } else {
+    kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(params);
+  }
   XKV_LAUNCHED();
   return 0;
 }

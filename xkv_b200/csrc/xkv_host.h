@@ -33,6 +33,16 @@ struct BatchRowsScope {
   ~BatchRowsScope() { batch_rows_override() = nullptr; }
 };
 
+// Launch priority of the calling thread's next GEMM launches: true = the lowest CTA-level priority whatever the stream's.
+// The factorisation driver sets it around the projection A = X V, the last kernel of a chain (thousands of CTAs, nothing
+// waits for its first results): the SMs that free up go to the latency-bound kernels of the other chains first
+// (measured on the bench step: 39.4 -> 38.3 ms; the same hint on the Gram, the FIRST kernel of a chain, costs 0.7 ms).
+bool& gemm_low_priority();
+struct GemmLowPriorityScope {
+  GemmLowPriorityScope() { gemm_low_priority() = true; }
+  ~GemmLowPriorityScope() { gemm_low_priority() = false; }
+};
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // One-time per-DEVICE set-up (cudaFuncSetAttribute and occupancy queries apply to the current device only; a
