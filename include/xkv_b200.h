@@ -292,9 +292,6 @@ XKV_API void xkv_decode_force_tiled(int on);
  * cta_group::2, half a right-factor slice per CTA), 1 FFMA epilogue, 2 score MMA with one independent CTA per kv head,
  * 3 CTA pairs; 4 = automatic scores kernel, but slab reduction and combine as two launches (default: one cluster launch) */
 XKV_API void xkv_decode_set_variant(int variant);
-/* tuning hook: cluster size of the score-MMA kernel, i.e. how many adjacent kv heads share one multicast copy of each
- * A_k tile: 0 automatic, else 1, 2, 4 or 8 (reduced to a divisor of the kv-head count the device can keep resident) */
-XKV_API void xkv_decode_set_cluster(int cluster);
 /* tuning hook: cap on the TMA ring depth (16 KiB slots of A_k in flight per CTA) of the pair kernel: 0 automatic, else >= 3 */
 XKV_API void xkv_decode_set_stages(int stages);
 /* Absorbed attention over a token factor: replaces, for the MLA latent slot (deepseek_v2.py:217-235: reconstructed

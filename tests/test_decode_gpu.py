@@ -9,16 +9,13 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-VARIANTS = {          # name -> (force_tiled, variant, cluster)
-    "auto": (0, 0, 0),     # head_dim 128: CTA pairs (cta_group::2), half a right-factor slice per CTA
-    "pair": (0, 3, 0),     # the same, requested explicitly
-    "cl1": (0, 2, 1),      # score MMA, one independent CTA per kv head
-    "cl2": (0, 0, 2),
-    "cl4": (0, 0, 4),
-    "cl8": (0, 0, 8),
-    "tiled": (1, 0, 0),    # tile-per-CTA kernel (right-factor slice does not fit in shared memory)
-    "ffma": (0, 1, 0),     # persistent kernel with the FFMA epilogue (the head_dim 64 path)
-    "split_rc": (0, 4, 0), # slab reduction and combine as two launches (default: one cluster launch)
+VARIANTS = {          # name -> (force_tiled, variant)
+    "auto": (0, 0),     # head_dim 128: CTA pairs (cta_group::2), half a right-factor slice per CTA
+    "pair": (0, 3),     # the same, requested explicitly
+    "cl1": (0, 2),         # score MMA, one independent CTA per kv head
+    "tiled": (1, 0),    # tile-per-CTA kernel (right-factor slice does not fit in shared memory)
+    "ffma": (0, 1),     # persistent kernel with the FFMA epilogue (the head_dim 64 path)
+    "split_rc": (0, 4), # slab reduction and combine as two launches (default: one cluster launch)
 }
 
 
@@ -26,10 +23,9 @@ def _set_variant(name):
     from xkv_b200 import _lib
 
     lib = _lib.load()
-    tiled, variant, cluster = VARIANTS[name]
+    tiled, variant = VARIANTS[name]
     lib.xkv_decode_force_tiled(tiled)
     lib.xkv_decode_set_variant(variant)
-    lib.xkv_decode_set_cluster(cluster)
 
 
 def _case(S, H, D, qpk, rk, rv, T, layers_in_group, layer, rope, seed=0, shape="flat", device_oracle=False):
@@ -112,7 +108,7 @@ def _case(S, H, D, qpk, rk, rv, T, layers_in_group, layer, rope, seed=0, shape="
 )
 @pytest.mark.parametrize("variant", list(VARIANTS))
 def test_decode_attention_matches_oracle(S, H, D, qpk, rk, rv, T, G, layer, rope, variant):
-    """Every scores kernel against the oracle (a requested cluster size is reduced to a divisor of the kv-head count)."""
+    """Every scores kernel (and the two-launch slab reduction) against the oracle."""
     _set_variant(variant)
     try:
         _case(S, H, D, qpk, rk, rv, T, G, layer, rope)
@@ -121,7 +117,7 @@ def test_decode_attention_matches_oracle(S, H, D, qpk, rk, rv, T, G, layer, rope
 
 
 @pytest.mark.parametrize("shape", ["sharp", "spike", "tail", "equal"])
-@pytest.mark.parametrize("variant", ["auto", "cl1", "cl8", "tiled", "ffma"])
+@pytest.mark.parametrize("variant", ["auto", "cl1", "tiled", "ffma", "split_rc"])
 @pytest.mark.parametrize("S,T", [(4096, 33), (4000, 100), (70, 5)])
 def test_peaked_softmax_matches_oracle(S, T, variant, shape):
     """Softmax shapes a near-uniform case cannot catch: the chunk-local maxima (one chunk per split-K slab of P A_v plus

@@ -3,7 +3,7 @@
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -o tools/probe_decode_scores \
 //        tools/probe_decode_scores.cu -lcuda
-//   tools/probe_decode_scores <dbg bits> [cluster: 0 = CTA pairs, 1 = single CTAs, 2/4/8 = multicast clusters] [rk] [S] [stages]
+//   tools/probe_decode_scores <dbg bits> [kernel: 0 = CTA pairs, 1 = single CTAs] [rk] [S] [stages]
 // bits: 1 no reconstruction MMAs, 2 ring stages released by a plain mbarrier arrive instead of tcgen05.commit,
 //       4 no epilogue pipeline at all, 8 no RoPE (no cos / sin loads), 16 epilogue stops after reading the accumulator
 #define XKV_PROBE 1
@@ -43,7 +43,6 @@ int main(int argc, char** argv) {
   cudaMemset(sn, 0x3c, static_cast<size_t>(S) * D * 2);
   xkv::g_probe_dbg = dbg;
   xkv::g_probe_stages = argc > 5 ? atoi(argv[5]) : 0;
-  xkv::g_scores_cluster = cluster;
   if (cluster == 1) xkv::g_scores_variant = 2;
   if (cluster == 0) xkv::g_scores_variant = 3;   // CTA pairs
   cudaEvent_t e0, e1;

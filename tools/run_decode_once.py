@@ -1,6 +1,6 @@
 """Decode layers over random factors at config 2's shape, bracketed by cudaProfilerStart/Stop (for ncu).
 
-    python tools/run_decode_once.py [S] [layers] [--cluster 0|1|2|4|8] [--variant N] [--graph]
+    python tools/run_decode_once.py [S] [layers] [--variant N] [--graph]
 
 Prints one JSON line: microseconds per layer enqueued from the host, and (with --graph) replayed as a CUDA graph."""
 import argparse
@@ -16,7 +16,6 @@ from xkv_b200 import _lib, ops, synthetic
 ap = argparse.ArgumentParser()
 ap.add_argument("S", type=int, nargs="?", default=65536)
 ap.add_argument("layers", type=int, nargs="?", default=4)
-ap.add_argument("--cluster", type=int, default=0)
 ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--stages", type=int, default=0)
 ap.add_argument("--graph", action="store_true")
@@ -37,7 +36,6 @@ q = torch.randn(HQ, D, device=dev).bfloat16()
 kt = torch.randn(H, 1, D, device=dev).bfloat16()
 vt = torch.randn(H, 1, D, device=dev).bfloat16()
 _lib.load().xkv_decode_set_variant(args.variant)
-_lib.load().xkv_decode_set_cluster(args.cluster)
 _lib.load().xkv_decode_set_stages(args.stages)
 ws = torch.empty(ops.decode_workspace_bytes(HQ, S, 1, RV) + 4096, dtype=torch.uint8, device=dev)
 o = torch.empty(HQ, D, dtype=torch.bfloat16, device=dev)
@@ -59,7 +57,7 @@ run()
 e1.record()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
-res = {"S": S, "layers": layers, "cluster": args.cluster, "variant": args.variant, "stages": args.stages,
+res = {"S": S, "layers": layers, "variant": args.variant, "stages": args.stages,
        "us_per_layer_host_enqueue": 1e3 * e0.elapsed_time(e1) / layers}
 if args.graph:
     g = torch.cuda.CUDAGraph()

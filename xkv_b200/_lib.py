@@ -135,7 +135,6 @@ SIGNATURES = {
     "xkv_decode_absorbed": (_i, [_vp, _i, _vp, _i64, _i, _i, _vp, _vp, _vp, _i64, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "xkv_decode_force_tiled": (None, [_i]),
     "xkv_decode_set_variant": (None, [_i]),
-    "xkv_decode_set_cluster": (None, [_i]),
     "xkv_decode_set_stages": (None, [_i]),
     "xkv_rope_bf16": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "xkv_append_workspace_bytes": (_sz, [_i, _i, _i]),

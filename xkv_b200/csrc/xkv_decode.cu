@@ -39,7 +39,6 @@ struct alignas(64) ScoreParams {
   CUtensorMap b_map;  // Bk_l (H*D x r_k), box {64, 256}
   CUtensorMap b_head_map;  // Bk_l, box {64, D}: one kv head (persistent kernel)
   CUtensorMap q_map;       // q (Hq x D), box {64, 16}: the q rows of one kv head (score MMA)
-  CUtensorMap a_mc_map;    // A_k, box {64, 128 / cluster size}: one CTA's slice of a token tile (multicast kernel)
   CUtensorMap b_half_map;  // Bk_l, box {64, 64}: half a kv head's dims (pair kernel)
   CUtensorMap q_half_map;  // q, box {64, 8}: the q rows one CTA of a pair supplies to the score MMA
   const __nv_bfloat16* q;    // (Hq, D)
@@ -483,13 +482,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
 // 4..11 epilogue (two per TMEM lane quarter: dims [0,32)+[64,96) and [32,64)+[96,128)), 12..15 score read-out.
 //   TMEM: 2 x 128 columns reconstruction accumulators | 2 x 64 columns K^rot (bf16x2) | 2 x 32 columns scores.
 //
-// Cluster form (CL = 2, 4 or 8 CTAs = CL ADJACENT kv heads working on the SAME token tiles): every kv head needs
-// the whole A_k token tile, and with one independent CTA per head each tile travels L2 -> SM once per head
-// (8 x 67 MB per layer at config 2: the kernel ran at the chip's L2 -> SM limit, ~6300 B/clk, not at the tensor
-// pipe's).  In a cluster every CTA fetches 1/CL of each ring stage (128/CL token rows x 64 rank columns) and the
-// TMA unit MULTICASTS it into the same ring slot of all CL CTAs, so a tile leaves L2 once per cluster.  A stage is
-// refilled only when every CTA of the cluster has consumed it: the MMA warp's tcgen05.commit that releases a stage
-// is multicast to the empty barrier of all CL CTAs (count CL).
+// (A cluster form that shared every A_k tile between the kv heads' CTAs by TMA multicast was built in round 2, measured
+// no faster -- 119 -> 120 / 129 / 140 us per layer at cluster size 2 / 4 / 8 -- and removed: profiles/r02_decode_scores_bisect.md.
+// The default for head_dim 128 is the CTA-pair kernel below; this one remains for devices that cannot hold a pair.)
 // ---------------------------------------------------------------------------------------------
 constexpr int R_MAX_STAGES = 12;   // ring slots of 16 KiB: as many as fit beside the head's right-factor slice (5 at r_k = 512, 9 at 256)
 constexpr int R_EPI_WARPS = 8;
@@ -508,12 +503,9 @@ static inline int r_stages_for(int nkb) {
   return st > R_MAX_STAGES ? R_MAX_STAGES : st;
 }
 
-template <int CL>
 __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const __grid_constant__ ScoreParams P) {
   constexpr int D = 128;
   constexpr int B_KB_BYTES = D * DBK * 2;
-  constexpr int SLICE_ROWS = DBM / CL;                 // token rows of a ring stage this CTA fetches
-  constexpr uint16_t CL_MASK = static_cast<uint16_t>((1u << CL) - 1u);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int R_STAGES = P.stages;
@@ -533,22 +525,18 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // cluster `cid` works on the head block hb (CL adjacent heads) and on the token tiles slot, slot + nslots, ...:
-  // the same tile sequence in every CTA of the cluster (the ring is filled jointly)
-  const int crank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
-  const int cid = static_cast<int>(blockIdx.x) / CL;
-  const int ncl = static_cast<int>(gridDim.x) / CL;
-  const int nhb = P.H / CL;
-  const int hb = cid % nhb;
-  const int h = hb * CL + crank;
-  const int slot = cid / nhb;
-  const int nslots = (ncl - hb + nhb - 1) / nhb;
+  // CTA `cid` works on kv head h and on the token tiles slot, slot + nslots, ...
+  const int cid = static_cast<int>(blockIdx.x);
+  const int ncta = static_cast<int>(gridDim.x);
+  const int h = cid % P.H;
+  const int slot = cid / P.H;
+  const int nslots = (ncta - h + P.H - 1) / P.H;
   const int ntiles = (P.S + DBM - 1) / DBM;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < R_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CL);      // one multicast commit per CTA of the cluster
+      mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -561,14 +549,13 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
     mbar_init(b_bar, 1);
     mbar_init(q_bar, 1);
     mbar_fence_init();
-    tma_prefetch_desc(CL > 1 ? &P.a_mc_map : &P.a_map);
+    tma_prefetch_desc(&P.a_map);
     tma_prefetch_desc(&P.b_head_map);
     tma_prefetch_desc(&P.q_map);
   }
   if (warp == 1) tmem_alloc(tmem_slot, R_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();   // peers multicast into this CTA's ring and arrive on its barriers: all initialised first
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -587,13 +574,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
       uint32_t ph = 0;
       for (int tile = slot; tile < ntiles && !XKV_DBG(P, 64); tile += nslots) {
         for (int kb = 0; kb < P.nkb; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1u);       // CL > 1: every CTA of the cluster has consumed the slot
-          mbar_expect_tx(&full_bar[s], D_A_BYTES);   // the whole stage lands here: this CTA's slice + the peers'
-          if (CL > 1)
-            tma_load_2d_multicast(sA + s * D_A_BYTES + crank * (SLICE_ROWS * 128), &P.a_mc_map, &full_bar[s], kb * DBK,
-                                  tile * DBM + crank * SLICE_ROWS, CL_MASK);
-          else
-            tma_load_2d(sA + s * D_A_BYTES, &P.a_map, &full_bar[s], kb * DBK, tile * DBM);
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], D_A_BYTES);
+          tma_load_2d(sA + s * D_A_BYTES, &P.a_map, &full_bar[s], kb * DBK, tile * DBM);
           if (++s == R_STAGES) {
             s = 0;
             ph ^= 1u;
@@ -635,9 +618,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
           }
           if (XKV_DBG(P, 512)) {
             // probe: no per-stage commit
-          } else if (CL > 1)
-            umma_commit_multicast(&empty_bar[s], CL_MASK);
-          else
+          } else
             umma_commit(&empty_bar[s]);
           b_desc += kBlockStep;
           a_desc += kStageStep;
@@ -791,7 +772,6 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer's commit may still arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, R_TMEM_COLS);
@@ -1428,56 +1408,21 @@ static bool g_force_tiled_scores = false;  // test hook: exercise the tile-per-C
 static int g_scores_variant = 0;           // test hook: 0 automatic, 1 FFMA epilogue, 2 score MMA in single CTAs, 3 CTA pairs
 static bool g_split_reduce_combine = false;   // test hook (variant 4): slab reduction and combine as two launches
 static int g_scores_stages = 0;            // tuning hook: cap on the TMA ring depth of the score-MMA kernels (0: as many slots as fit)
-static int g_scores_cluster = 0;           // test / tuning hook: cluster size of the score-MMA kernel (0 automatic, 1, 2, 4, 8)
 
-// Launch the score-MMA kernel as clusters of CL CTAs (CL adjacent kv heads share every A_k tile by TMA multicast).
-// Returns 0 on success, -1 when this cluster size cannot be resident on the device (the caller tries a smaller one).
-template <int CL>
+// Launch the single-CTA score-MMA kernel (persistent: one CTA per SM, every head at least one).
 static int launch_scores_mma2(const ScoreParams& sp, int S, int H, cudaStream_t st) {
-  auto kern = decode_scores_mma2_kernel<CL>;
-  static PerDevice<int> state;   // 0: not probed, -1: not launchable, > 0: resident clusters of this size
-  int& resident = state();
-  cudaLaunchConfig_t cfg;
-  std::memset(&cfg, 0, sizeof(cfg));
-  cfg.blockDim = dim3(R_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = R_FIXED_BYTES + static_cast<size_t>(sp.nkb) * 128 * DBK * 2 + static_cast<size_t>(sp.stages) * D_A_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = CL > 1 ? 1 : 0;
-  if (resident == 0) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(R_SMEM_LIMIT)) != cudaSuccess) {
-      (void)cudaGetLastError();
-      resident = -1;
-    } else if (CL == 1) {
-      resident = device_sm_count();
-    } else {
-      int n = 0;
-      cfg.gridDim = dim3(CL, 1, 1);
-      const size_t launch_smem = cfg.dynamicSmemBytes;
-      cfg.dynamicSmemBytes = R_SMEM_LIMIT;   // one CTA per SM whatever the rank
-      const cudaError_t oe = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
-      cfg.dynamicSmemBytes = launch_smem;
-      if (oe != cudaSuccess || n < 1) {
-        (void)cudaGetLastError();
-        resident = -1;
-      } else {
-        resident = n;
-      }
-    }
+  static PerDevice<bool> configured;
+  if (!configured()) {
+    XKV_CHECK_CUDA(cudaFuncSetAttribute(decode_scores_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(R_SMEM_LIMIT)));
+    configured() = true;
   }
-  if (resident < 0) return -1;
-  // persistent: one resident CTA per SM slot; every head block needs at least one cluster
+  const size_t smem = R_FIXED_BYTES + static_cast<size_t>(sp.nkb) * 128 * DBK * 2 + static_cast<size_t>(sp.stages) * D_A_BYTES;
   const int ntiles = (S + DBM - 1) / DBM;
-  const int nhb = H / CL;
-  int ncl = resident < ntiles * nhb ? resident : ntiles * nhb;
-  if (ncl < nhb) ncl = nhb;
-  cfg.gridDim = dim3(ncl * CL, 1, 1);
-  XKV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, sp));
+  const int sms = device_sm_count();
+  int ncta = sms < ntiles * H ? sms : ntiles * H;
+  if (ncta < H) ncta = H;
+  decode_scores_mma2_kernel<<<ncta, R_THREADS, smem, st>>>(sp);
   return 0;
 }
 
@@ -1550,20 +1495,6 @@ static int launch_scores(const void* q, int Hq, int H, int D, const void* A_k, i
     rc = encode_tmap_2d_bf16(&sp.b_half_map, Vk_layer, rk, static_cast<uint64_t>(H) * D, ldv_k, DBK, 64);
     if (rc) return rc;
   }
-  // cluster size of the score-MMA kernel: the largest of 8, 4, 2 that divides the kv-head count (tuning hook: xkv_decode_set_cluster)
-  int want_cl = 1;
-  if (q_tma_ok && qpk <= 8) {
-    const int cap = g_scores_cluster > 0 ? g_scores_cluster : 1;   // measured: sharing the tiles by multicast is no faster
-    for (int c = 8; c >= 2; c >>= 1)
-      if (c <= cap && H % c == 0) {
-        want_cl = c;
-        break;
-      }
-    if (want_cl > 1) {
-      rc = encode_tmap_2d_bf16(&sp.a_mc_map, A_k, rk, S, lda_k, DBK, DBM / want_cl);
-      if (rc) return rc;
-    }
-  }
   sp.q = static_cast<const __nv_bfloat16*>(q);
   sp.cos = static_cast<const __nv_bfloat16*>(cos);
   sp.sin = static_cast<const __nv_bfloat16*>(sin);
@@ -1596,8 +1527,7 @@ static int launch_scores(const void* q, int Hq, int H, int D, const void* A_k, i
     configured() = true;
   }
   // CTA pairs (half a slice per CTA, deep ring) when the head layout allows the score MMA: the default for head_dim 128
-  if (D == 128 && q_tma_ok && qpk <= 8 && !g_force_tiled_scores && g_scores_cluster <= 1 &&
-      (g_scores_variant == 0 || g_scores_variant == 3)) {
+  if (D == 128 && q_tma_ok && qpk <= 8 && !g_force_tiled_scores && (g_scores_variant == 0 || g_scores_variant == 3)) {
     const int prc = launch_scores_pair(sp, S, H, st);
     if (prc > 0) return prc;
     if (prc == 0) {
@@ -1614,29 +1544,8 @@ static int launch_scores(const void* q, int Hq, int H, int D, const void* A_k, i
     int pgrid = sms < ntiles * H ? sms : ntiles * H;
     if (pgrid < H) pgrid = H;   // every head needs at least one CTA
     if (D == 128 && q_tma_ok && qpk <= 8 && g_scores_variant != 1) {
-      // score MMA; clusters of `want_cl` heads when the device can hold them, else smaller ones
-      int lrc = -1;
-      if (g_scores_variant == 2) want_cl = 1;
-      if (want_cl == 8) {
-        lrc = launch_scores_mma2<8>(sp, S, H, st);
-        if (lrc < 0) {
-          want_cl = 4;
-          rc = encode_tmap_2d_bf16(&sp.a_mc_map, A_k, rk, S, lda_k, DBK, DBM / 4);
-          if (rc) return rc;
-        }
-      }
-      if (lrc < 0 && want_cl == 4) {
-        lrc = launch_scores_mma2<4>(sp, S, H, st);
-        if (lrc < 0) {
-          want_cl = 2;
-          rc = encode_tmap_2d_bf16(&sp.a_mc_map, A_k, rk, S, lda_k, DBK, DBM / 2);
-          if (rc) return rc;
-        }
-      }
-      if (lrc < 0 && want_cl == 2) lrc = launch_scores_mma2<2>(sp, S, H, st);
-      if (lrc < 0) lrc = launch_scores_mma2<1>(sp, S, H, st);
-      if (lrc > 0) return lrc;
-      XKV_REQUIRE(lrc == 0, "decode: the score-MMA kernel cannot be launched on this device");
+      rc = launch_scores_mma2(sp, S, H, st);
+      if (rc) return rc;
     } else if (D == 128)
       decode_scores_persistent_kernel<128><<<pgrid, P_THREADS, P_SMEM_BYTES, st>>>(sp);
     else
@@ -1872,8 +1781,6 @@ extern "C" void xkv_decode_set_variant(int variant) {
   g_scores_variant = variant == 4 ? 0 : variant;
 }
 /* tuning hook: cluster size of the score-MMA kernel (0 automatic) */
-extern "C" void xkv_decode_set_cluster(int cluster) { g_scores_cluster = cluster; }
-
 extern "C" void xkv_decode_set_stages(int stages) { g_scores_stages = stages; }
 
 extern "C" int xkv_decode_attention(const void* q, int Hq, int H, int D, const void* A_k, int64_t lda_k, int rk,
