@@ -1076,13 +1076,40 @@ __global__ void __launch_bounds__(256) softmax_chunk_kernel(float* __restrict__ 
                                                             const __nv_bfloat16* __restrict__ k_tail, long long sh,
                                                             long long st, int qpk, int D, float scale,
                                                             __nv_bfloat16* __restrict__ prob, long long ldp,
-                                                            float* __restrict__ chunk_max, float* __restrict__ chunk_sum) {
+                                                            float* __restrict__ chunk_max, float* __restrict__ chunk_sum,
+                                                            const float* __restrict__ raw_bias, const float* __restrict__ row_scale,
+                                                            float raw_scale) {
+  // MLA path (raw_scale != 0): the scores buffer holds the RAW products q^ . a_t; the score of token t is
+  // (raw * row_scale[t] + raw_bias[t]) * raw_scale, applied on the fly in both passes, and the probability that goes to
+  // the GEMM is p * row_scale[t] (the value side of the absorbed form) while the chunk sum stays that of p.
+  const bool xf = raw_scale != 0.f;
   __shared__ float red[8];
   __shared__ float bcast;
   const int hq = blockIdx.x, ch = blockIdx.y;
   float* s = scores + hq * ld;
+  const float* rb = raw_bias != nullptr ? raw_bias + hq * ld : nullptr;
   __nv_bfloat16* p = prob + hq * ldp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto load4 = [&](int i) -> float4 {   // four transformed scores from token i (16-byte aligned)
+    float4 x = *reinterpret_cast<const float4*>(s + i);
+    if (xf) {
+      if (row_scale != nullptr) {
+        const float4 r4 = *reinterpret_cast<const float4*>(row_scale + i);
+        x.x *= r4.x, x.y *= r4.y, x.z *= r4.z, x.w *= r4.w;
+      }
+      if (rb != nullptr) {
+        const float4 b4 = *reinterpret_cast<const float4*>(rb + i);
+        x.x += b4.x, x.y += b4.y, x.z += b4.z, x.w += b4.w;
+      }
+      x.x *= raw_scale, x.y *= raw_scale, x.z *= raw_scale, x.w *= raw_scale;
+    }
+    return x;
+  };
+  auto load1 = [&](int i) -> float {
+    float x = s[i];
+    if (xf) x = (x * (row_scale != nullptr ? row_scale[i] : 1.f) + (rb != nullptr ? rb[i] : 0.f)) * raw_scale;
+    return x;
+  };
   int i0, i1;
   if (ch < nchunk_s) {
     i0 = min(S, ch * kps * 64);
@@ -1105,10 +1132,10 @@ __global__ void __launch_bounds__(256) softmax_chunk_kernel(float* __restrict__ 
   const int nvec = vec ? max(i1 - i0, 0) >> 2 : 0;
   float m = -INFINITY;
   for (int v = tid; v < nvec; v += 256) {
-    const float4 x = *reinterpret_cast<const float4*>(s + i0 + 4 * v);
+    const float4 x = load4(i0 + 4 * v);
     m = fmaxf(fmaxf(m, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
   }
-  for (int i = i0 + 4 * nvec + tid; i < i1; i += 256) m = fmaxf(m, s[i]);
+  for (int i = i0 + 4 * nvec + tid; i < i1; i += 256) m = fmaxf(m, load1(i));
   m = warp_max(m);
   if (lane == 0) red[warp] = m;
   __syncthreads();
@@ -1121,18 +1148,25 @@ __global__ void __launch_bounds__(256) softmax_chunk_kernel(float* __restrict__ 
   m = bcast;
   // ---- p = exp(s - m_c), l_c = sum p (second pass over a few KB that are in L1 / L2) ----
   float sum = 0.f;
+  const bool vs = xf && row_scale != nullptr;   // value-side scale of the absorbed form
   for (int v = tid; v < nvec; v += 256) {
-    const float4 x = *reinterpret_cast<const float4*>(s + i0 + 4 * v);
-    const float e0 = __expf(x.x - m), e1 = __expf(x.y - m), e2 = __expf(x.z - m), e3 = __expf(x.w - m);
+    const float4 x = load4(i0 + 4 * v);
+    float e0 = __expf(x.x - m), e1 = __expf(x.y - m), e2 = __expf(x.z - m), e3 = __expf(x.w - m);
     sum += (e0 + e1) + (e2 + e3);
+    if (vs) {
+      // the probability is rounded to bf16 BEFORE the value-side scale, as the separate scale pass did
+      const float4 r4 = *reinterpret_cast<const float4*>(row_scale + i0 + 4 * v);
+      e0 = bf16r(e0) * r4.x, e1 = bf16r(e1) * r4.y, e2 = bf16r(e2) * r4.z, e3 = bf16r(e3) * r4.w;
+    }
     uint2 w;
     w.x = pack_bf16x2(e0, e1);
     w.y = pack_bf16x2(e2, e3);
     *reinterpret_cast<uint2*>(p + i0 + 4 * v) = w;
   }
   for (int i = i0 + 4 * nvec + tid; i < i1; i += 256) {
-    const float e = __expf(s[i] - m);
+    float e = __expf(load1(i) - m);
     sum += e;
+    if (vs) e = bf16r(e) * row_scale[i];
     p[i] = __float2bfloat16_rn(e);
   }
   sum = warp_sum(sum);
@@ -1186,7 +1220,7 @@ __device__ __forceinline__ void head_weights(const float* __restrict__ chunk_max
 __global__ void __launch_bounds__(256) reduce_u_kernel(const float* __restrict__ slabs, int nslabs, long long slab_stride,
                                                        int rv, const float* __restrict__ chunk_max,
                                                        const float* __restrict__ chunk_sum, int nchunks,
-                                                       float* __restrict__ U) {
+                                                       float* __restrict__ U, int normalise, float* __restrict__ lse_out) {
   __shared__ float part[4][64];
   __shared__ float w_s[SM_MAX_CHUNKS];
   __shared__ float stats[2];
@@ -1210,7 +1244,9 @@ __global__ void __launch_bounds__(256) reduce_u_kernel(const float* __restrict__
   }
   part[g][el] = (a[0] + a[1]) + (a[2] + a[3]);
   __syncthreads();
-  if (g == 0 && j < rv) U[e] = (part[0][el] + part[1][el]) + (part[2][el] + part[3][el]);
+  // normalise: U / (sum of the softmax) and the log-sum-exp, what absorbed_finalize_kernel did in a launch of its own
+  if (g == 0 && j < rv) U[e] = ((part[0][el] + part[1][el]) + (part[2][el] + part[3][el])) * (normalise ? 1.f / stats[1] : 1.f);
+  if (lse_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) lse_out[hq] = stats[0] + logf(stats[1]);
 }
 
 // o[hq][d] = ( sum_j U[hq][j] * Bv[(h*D + d)][j]  +  sum_t p_tail[hq][t] * v_tail[h][t][d] ) / rowsum[hq]
@@ -1333,40 +1369,10 @@ __global__ void __launch_bounds__(256) reduce_combine_kernel(const float* __rest
 //     s[h][t] = scale * ( row_scale[t] * (q^[h] . a_t) + bias_q[h] . bias_k[t] )
 // (row_scale = 1 / rms of the reconstructed latent, the bias term is the RoPE part q_pe . k_pe) and the values are
 //     u[h] = sum_t softmax(s)[h][t] * row_scale[t] * a_t          (rank space; the caller applies V_l, gamma, W_UV).
-// Two tensor-core GEMMs over A and three small kernels; the latents are never reconstructed.
+// Four launches: the raw products q^ A^T (+ the bias GEMM), the chunk-local softmax (which applies row_scale, bias and
+// scale to the raw products on the fly and emits p * row_scale), U = P' A, and the slab reduction that also normalises and
+// writes the log-sum-exp (round 2, first half: seven launches).  The latents are never reconstructed.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) absorbed_scores_kernel(float* __restrict__ scores, const float* __restrict__ bias,
-                                                              long long ld, const float* __restrict__ row_scale, int S,
-                                                              float scale) {
-  const int hq = blockIdx.y;
-  float* s = scores + hq * ld;
-  const float* b = bias != nullptr ? bias + hq * ld : nullptr;
-  for (int t = blockIdx.x * 256 + threadIdx.x; t < S; t += gridDim.x * 256) {
-    float v = s[t];
-    if (row_scale != nullptr) v *= row_scale[t];
-    if (b != nullptr) v += b[t];
-    s[t] = v * scale;
-  }
-}
-__global__ void __launch_bounds__(256) scale_prob_kernel(__nv_bfloat16* __restrict__ prob, long long ldp,
-                                                         const float* __restrict__ row_scale, int S) {
-  __nv_bfloat16* p = prob + blockIdx.y * ldp;
-  for (int t = blockIdx.x * 256 + threadIdx.x; t < S; t += gridDim.x * 256)
-    p[t] = __float2bfloat16_rn(__bfloat162float(p[t]) * row_scale[t]);
-}
-// u_out[hq][j] = U[hq][j] / rowsum, lse[hq] = m + log(rowsum) from the chunk-local softmax statistics
-__global__ void __launch_bounds__(256) absorbed_finalize_kernel(const float* __restrict__ U, int r,
-                                                                const float* __restrict__ chunk_max,
-                                                                const float* __restrict__ chunk_sum, int nchunks,
-                                                                float* __restrict__ u_out, float* __restrict__ lse_out) {
-  __shared__ float w_s[SM_MAX_CHUNKS];
-  __shared__ float stats[2];
-  const int hq = blockIdx.x;
-  head_weights(chunk_max, chunk_sum, hq, nchunks, w_s, stats);
-  const float inv = 1.f / stats[1];
-  for (int j = threadIdx.x; j < r; j += 256) u_out[static_cast<long long>(hq) * r + j] = U[static_cast<long long>(hq) * r + j] * inv;
-  if (lse_out != nullptr && threadIdx.x == 0) lse_out[hq] = stats[0] + logf(stats[1]);
-}
 
 // RoPE on materialised keys, in the reference's bf16 arithmetic (cache:142-152): x (rows, H, D) in place
 __global__ void __launch_bounds__(256) rope_bf16_kernel(__nv_bfloat16* __restrict__ x, long long ld_row, int rows, int H,
@@ -1620,7 +1626,8 @@ extern "C" int xkv_decode_attention_lse(const void* q, int Hq, int H, int D, con
   XKV_REQUIRE(nchunks <= SM_MAX_CHUNKS, "decode: too many softmax chunks");
   softmax_chunk_kernel<<<dim3(Hq, nchunks), 256, 0, st>>>(scores, ldl, S, T, kps, split, static_cast<const __nv_bfloat16*>(q),
                                                           static_cast<const __nv_bfloat16*>(k_tail), tail_stride_h,
-                                                          tail_stride_t, qpk, D, scale, prob, ldl, chunk_max, rowsum);
+                                                          tail_stride_t, qpk, D, scale, prob, ldl, chunk_max, rowsum, nullptr, nullptr,
+                                                          0.f);
   XKV_LAUNCHED();
   // ---- U = P[:, :S] * A_v  (tokens are the contraction: P K-major, A_v MN-major) ----
   xkv_gemm_problem gp;
@@ -1667,7 +1674,7 @@ extern "C" int xkv_decode_attention_lse(const void* q, int Hq, int H, int D, con
   }
   float* U = u_slabs + static_cast<size_t>(split) * Hq * rv;
   reduce_u_kernel<<<dim3((rv + 63) / 64, Hq), 256, 0, st>>>(u_slabs, split, static_cast<long long>(Hq) * rv, rv, chunk_max,
-                                                            rowsum, nchunks, U);
+                                                            rowsum, nchunks, U, 0, nullptr);
   XKV_LAUNCHED();
   combine_kernel<<<dim3(Hq, (D + 7) / 8), 256, rv * sizeof(float), st>>>(
       U, 1, 0, rv, static_cast<const __nv_bfloat16*>(Vv_layer), ldv_v, prob, ldl, S,
@@ -1727,21 +1734,19 @@ extern "C" int xkv_decode_absorbed(const void* q_hat, int Hq, const void* A, int
   }
   int rc = xkv_gemm_grouped(gp, np, stream);
   if (rc) return rc;
-  const int gx = (S + 1023) / 1024 < 1 ? 1 : (S + 1023) / 1024;
-  absorbed_scores_kernel<<<dim3(gx, Hq), 256, 0, st>>>(scores, bias_q != nullptr ? bias : nullptr, ldl, row_scale, S, scale);
-  XKV_LAUNCHED();
-  // ---- softmax with chunk-local maxima (chunk c = token range of split-K slab c; no dense tail here) ----
+  // ---- softmax with chunk-local maxima (chunk c = token range of split-K slab c; no dense tail here); the per-token
+  // scale, the bias term and the softmax scale are applied to the raw products on the fly, and the probabilities leave
+  // already multiplied by the value-side per-token scale (three elementwise launches folded into this one) ----
   const int nkb_p = (S + 63) / 64;
   const int kps = (nkb_p + split - 1) / split;
   const int nchunks = split + 1;
   XKV_REQUIRE(nchunks <= SM_MAX_CHUNKS, "absorbed decode: too many softmax chunks");
+  XKV_REQUIRE(scale != 0.f, "absorbed decode: the softmax scale must not be zero");
+  XKV_REQUIRE(row_scale == nullptr || (reinterpret_cast<uintptr_t>(row_scale) & 15) == 0, "absorbed decode: row_scale must be 16-byte aligned");
   softmax_chunk_kernel<<<dim3(Hq, nchunks), 256, 0, st>>>(scores, ldl, S, 0, kps, split, nullptr, nullptr, 0, 0, 1, 0, scale,
-                                                          prob, ldl, chunk_max, rowsum);
+                                                          prob, ldl, chunk_max, rowsum, bias_q != nullptr ? bias : nullptr,
+                                                          row_scale, scale);
   XKV_LAUNCHED();
-  if (row_scale != nullptr) {
-    scale_prob_kernel<<<dim3(gx, Hq), 256, 0, st>>>(prob, ldl, row_scale, S);
-    XKV_LAUNCHED();
-  }
   // ---- U = P' A (tokens are the contraction) ----
   xkv_gemm_problem gu;
   std::memset(&gu, 0, sizeof(gu));
@@ -1752,11 +1757,9 @@ extern "C" int xkv_decode_absorbed(const void* q_hat, int Hq, const void* A, int
   gu.split_stride = static_cast<long long>(Hq) * r;
   rc = xkv_gemm_grouped(&gu, 1, stream);
   if (rc) return rc;
-  float* U = u_slabs + static_cast<size_t>(split) * Hq * r;
+  // slab reduction, normalisation and log-sum-exp in one launch
   reduce_u_kernel<<<dim3((r + 63) / 64, Hq), 256, 0, st>>>(u_slabs, split, static_cast<long long>(Hq) * r, r, chunk_max, rowsum,
-                                                           nchunks, U);
-  XKV_LAUNCHED();
-  absorbed_finalize_kernel<<<Hq, 256, 0, st>>>(U, r, chunk_max, rowsum, nchunks, u_out, lse_out);
+                                                           nchunks, u_out, 1, lse_out);
   XKV_LAUNCHED();
   return 0;
 }
