@@ -318,6 +318,17 @@ def factorize_batch(xs: Sequence[torch.Tensor], rank: int, opts: Optional[Factor
     return out
 
 
+_chain_streams = {}
+
+
+def _chain_stream(device, index: int):
+    """Prioritised side stream for one of several concurrent factorisation chains (see compress.compress_groups)."""
+    key = (device.index, index)
+    if key not in _chain_streams:
+        _chain_streams[key] = torch.cuda.Stream(device=device, priority=-1 - (index % 3))
+    return _chain_streams[key]
+
+
 def factorize_token_sharded(jobs: Sequence, process_group, opts: Optional[FactorizeOptions] = None,
                             comm_events: Optional[list] = None) -> List[Factors]:
     """Token-sharded factorisation of several matrices with the small-matrix stages DISTRIBUTED over the ranks.
@@ -344,7 +355,7 @@ def factorize_token_sharded(jobs: Sequence, process_group, opts: Optional[Factor
     per = ops.gram_packed_elems(n)
     nj = len(jobs)
 
-    def call(phase, xs, r, a_s, vts_, vs, grams, ws):
+    def call(phase, xs, r, a_s, vts_, vs, grams, ws, on=None):
         """One driver call for a batch of matrices of equal shape and rank (xs / a_s / vs / grams may be None per phase)."""
         nb = len(vts_)
         m = xs[0].shape[0] if xs is not None else n
@@ -352,7 +363,7 @@ def factorize_token_sharded(jobs: Sequence, process_group, opts: Optional[Factor
             ops._ptr_array(xs) if xs is not None else None, nb, m, n, xs[0].stride(0) if xs is not None else n, r, C.byref(co),
             ops._ptr_array(a_s) if a_s is not None else None, ops._ptr_array(vts_), ops._ptr_array(vs) if vs is not None else None,
             None, ops._ptr_array(grams) if grams is not None else None, phase, C.c_void_p(ws.data_ptr()),
-            ws.numel(), None, stream))
+            ws.numel(), None, stream if on is None else C.c_void_p(on.cuda_stream)))
 
     m_loc = jobs[0][0].shape[0]
     for x, r in jobs:
@@ -386,16 +397,32 @@ def factorize_token_sharded(jobs: Sequence, process_group, opts: Optional[Factor
         sums.append(dist.all_reduce(packed[i], op=dist.ReduceOp.SUM, group=process_group, async_op=True))
     # 3. the owner of matrix i (rank i mod P) derives its right factor: all the matrices a rank owns at one rank value in
     # ONE batched call (the latency-bound stages carry several matrices per launch); the owners work side by side
-    for r, idx in owned.items():
-        for lo in range(0, len(idx), _lib.MAX_BATCH):
-            part = idx[lo:lo + _lib.MAX_BATCH]
-            grams = torch.empty(len(part), n, n, dtype=torch.float32, device=dev)
-            for k, i in enumerate(part):
-                sums[i].wait()
-                ops.gram_unpack_upper(packed[i], grams[k])
-            v_tmp = [torch.empty(n, r, dtype=torch.bfloat16, device=dev) for _ in part]
-            call(3, None, r, None, [vts[i] for i in part], v_tmp, list(grams), ws)
-            del v_tmp, grams
+    # Each rank value's batch is a latency-bound chain of ~160 launches (Cholesky clusters at l = 1088 / 1600 are most of it):
+    # the chains of different rank values run on their own prioritised side streams, each with its own workspace, so that
+    # the K chain fills the SMs the V chain leaves idle (one stream: the chains ran back to back).
+    main_stream = torch.cuda.current_stream(dev)
+    chain_streams = []
+    for gi, (r, idx) in enumerate(owned.items()):
+        st = _chain_stream(dev, gi) if len(owned) > 1 else main_stream
+        if st is not main_stream:
+            st.wait_stream(main_stream)
+            chain_streams.append(st)
+        with torch.cuda.stream(st):
+            ws_r = ws if st is main_stream else torch.empty(
+                max(int(lib.xkv_factorize_workspace_bytes(len(idx[lo:lo + _lib.MAX_BATCH]), n, n, r, C.byref(co)))
+                    for lo in range(0, len(idx), _lib.MAX_BATCH)), dtype=torch.uint8, device=dev)
+            for lo in range(0, len(idx), _lib.MAX_BATCH):
+                part = idx[lo:lo + _lib.MAX_BATCH]
+                grams = torch.empty(len(part), n, n, dtype=torch.float32, device=dev)
+                for k, i in enumerate(part):
+                    sums[i].wait()
+                    ops.gram_unpack_upper(packed[i], grams[k])
+                v_tmp = [torch.empty(n, r, dtype=torch.bfloat16, device=dev) for _ in part]
+                call(3, None, r, None, [vts[i] for i in part], v_tmp, list(grams), ws_r, on=st)
+                del v_tmp, grams
+            del ws_r
+    for st in chain_streams:
+        main_stream.wait_stream(st)
     # ... and broadcasts it; everybody issues the broadcasts in the same order
     casts = []
     for i in range(nj):
