@@ -793,6 +793,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_mma2_kernel(const 
 constexpr int PR_B_KB_BYTES = 64 * DBK * 2;        // one rank block of a half slice: 64 dims x 128 B
 constexpr int PR_Q_BYTES = 2 * 8 * 128;            // 8 q rows per CTA, two 64-dim chunks
 constexpr size_t PR_FIXED_BYTES = PR_Q_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+constexpr int PR_A2 = 3, PR_D2 = 4;         // rotated-key / score buffers in tensor memory
+constexpr uint32_t PR_COL_A2 = 256, PR_COL_D2 = 256 + PR_A2 * 64;   // 256 accumulator columns, then 3 x 64, then 4 x 16 = 512
 static inline int pair_stages_for(int nkb) {
   const size_t b = static_cast<size_t>(nkb) * PR_B_KB_BYTES;
   if (b + PR_FIXED_BYTES + 3 * D_A_BYTES > R_SMEM_LIMIT) return 0;
@@ -814,11 +816,14 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_pair_kernel(const 
   uint64_t* empty_bar = full_bar + R_MAX_STAGES;   // in each CTA: multicast commit
   uint64_t* tfull_bar = empty_bar + R_MAX_STAGES;  // [2] in each CTA: multicast commit
   uint64_t* tempty_bar = tfull_bar + 2;            // [2] even CTA: the epilogue warps of BOTH CTAs
-  uint64_t* a2full_bar = tempty_bar + 2;           // [2] even CTA: both epilogues
-  uint64_t* a2empty_bar = a2full_bar + 2;          // [2] in each CTA: multicast commit
-  uint64_t* d2full_bar = a2empty_bar + 2;          // [2] in each CTA: multicast commit
-  uint64_t* d2empty_bar = d2full_bar + 2;          // [2] even CTA: both read-outs
-  uint64_t* b_bar = d2empty_bar + 2;               // even CTA: both half slices
+  // Rotated-key and score buffers: 3 and 4 deep (tensor memory: 256 accumulator columns + 3 x 64 + 4 x 16 = 512).  The score
+  // MMA of a tile queues BEHIND the reconstruction MMAs already issued (the pipe is in order), so with two buffers each the
+  // recurrences  score MMA(t) -> read-out -> score MMA(t + 2)  and  score MMA(t) -> epilogue store(t + 2)  sat at the tile period.
+  uint64_t* a2full_bar = tempty_bar + 2;           // [PR_A2] even CTA: both epilogues
+  uint64_t* a2empty_bar = a2full_bar + PR_A2;      // [PR_A2] in each CTA: multicast commit
+  uint64_t* d2full_bar = a2empty_bar + PR_A2;      // [PR_D2] in each CTA: multicast commit
+  uint64_t* d2empty_bar = d2full_bar + PR_D2;      // [PR_D2] even CTA: both read-outs
+  uint64_t* b_bar = d2empty_bar + PR_D2;           // even CTA: both half slices
   uint64_t* q_bar = b_bar + 1;                     // even CTA: both q halves
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_bar + 1);
 
@@ -840,8 +845,12 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_pair_kernel(const 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 2 * R_EPI_WARPS);
+    }
+    for (int i = 0; i < PR_A2; ++i) {
       mbar_init(&a2full_bar[i], 2 * R_EPI_WARPS);
       mbar_init(&a2empty_bar[i], 1);
+    }
+    for (int i = 0; i < PR_D2; ++i) {
       mbar_init(&d2full_bar[i], 1);
       mbar_init(&d2empty_bar[i], 2 * R_OUT_WARPS);
     }
@@ -933,23 +942,25 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_pair_kernel(const 
       if (elect_one()) {
         mbar_wait_cluster(q_bar, 0);
         const uint64_t q_desc0 = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-        int b = 0;
-        uint32_t bph = 0u;
+        int ba = 0, bd = 0;
+        uint32_t pa = 0u, pd = 0u;   // phase bit per buffer
         for (int tile = slot; tile < ntiles; tile += nslots) {
-          mbar_wait_cluster(&a2full_bar[b], (bph >> b) & 1u);
-          mbar_wait_cluster(&d2empty_bar[b], ((bph >> b) & 1u) ^ 1u);
+          mbar_wait_cluster(&a2full_bar[ba], (pa >> ba) & 1u);
+          mbar_wait_cluster(&d2empty_bar[bd], ((pd >> bd) & 1u) ^ 1u);
           tc_fence_after();
-          const uint32_t a2 = tmem_base + R_COL_A2 + static_cast<uint32_t>(b * 64);
-          const uint32_t d2 = tmem_base + R_COL_D2 + static_cast<uint32_t>(b * 32);
+          const uint32_t a2 = tmem_base + PR_COL_A2 + static_cast<uint32_t>(ba * 64);
+          const uint32_t d2 = tmem_base + PR_COL_D2 + static_cast<uint32_t>(bd * 16);
 #pragma unroll
           for (int k = 0; k < D / 16; ++k)
             umma_bf16_ts_pair(d2, a2 + static_cast<uint32_t>(k * 8),
                               q_desc0 + static_cast<uint64_t>(((k >> 2) * (PR_Q_BYTES / 2) + (k & 3) * 32) >> 4), idesc2,
                               k > 0 ? 1u : 0u);
-          umma_commit_pair(&d2full_bar[b]);
-          umma_commit_pair(&a2empty_bar[b]);
-          bph ^= 1u << b;
-          b ^= 1;
+          umma_commit_pair(&d2full_bar[bd]);
+          umma_commit_pair(&a2empty_bar[ba]);
+          pa ^= 1u << ba;
+          pd ^= 1u << bd;
+          ba = ba + 1 == PR_A2 ? 0 : ba + 1;
+          bd = bd + 1 == PR_D2 ? 0 : bd + 1;
         }
       }
       __syncwarp();
@@ -963,8 +974,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_pair_kernel(const 
     const bool rope = P.cos != nullptr;
     const uint32_t tempty0 = cluster_map_shared(smem_u32(&tempty_bar[0]), 0);
     const uint32_t a2full0 = cluster_map_shared(smem_u32(&a2full_bar[0]), 0);
-    int acc = 0;
-    uint32_t acc_ph = 0u;
+    int acc = 0, ba = 0;
+    uint32_t acc_ph = 0u, pa = 0u;
     for (int tile = slot; tile < ntiles; tile += nslots) {
       const int tok = (2 * tile + crank) * DBM + row;
       uint32_t cs[16], sn[16];
@@ -1014,18 +1025,20 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_pair_kernel(const 
           hi_w[j] = *reinterpret_cast<const uint32_t*>(&o2);
         }
       }
-      mbar_wait(&a2empty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);
+      mbar_wait(&a2empty_bar[ba], ((pa >> ba) & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t a2 = lane_base + R_COL_A2 + static_cast<uint32_t>(acc * 64);
+      const uint32_t a2 = lane_base + PR_COL_A2 + static_cast<uint32_t>(ba * 64);
       __syncwarp();
       tmem_st_32x16(a2 + static_cast<uint32_t>(d0 / 2), lo_w);
       tmem_st_32x16(a2 + static_cast<uint32_t>(32 + d0 / 2), hi_w);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(a2full0 + static_cast<uint32_t>(acc * 8));
+      if (lane == 0) mbar_arrive_cluster(a2full0 + static_cast<uint32_t>(ba * 8));
       acc_ph ^= 1u << acc;
       acc ^= 1;
+      pa ^= 1u << ba;
+      ba = ba + 1 == PR_A2 ? 0 : ba + 1;
     }
   } else if (warp >= 4 + R_EPI_WARPS) {
     // ===== score read-out: one warp per TMEM lane quarter, thread = token =====
@@ -1040,7 +1053,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_pair_kernel(const 
       tc_fence_after();
       uint32_t v[8];
       __syncwarp();
-      tmem_ld_32x8(tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + R_COL_D2 + static_cast<uint32_t>(b * 32), v);
+      tmem_ld_32x8(tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + PR_COL_D2 + static_cast<uint32_t>(b * 16), v);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -1051,7 +1064,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_pair_kernel(const 
           if (g < P.qpk) P.scores[static_cast<long long>(h * P.qpk + g) * P.ld_scores + tok] = __uint_as_float(v[g]) * P.scale;
       }
       bph ^= 1u << b;
-      b ^= 1;
+      b = b + 1 == PR_D2 ? 0 : b + 1;
     }
   }
   tc_fence_before();
