@@ -1084,25 +1084,25 @@ __global__ void __launch_bounds__(R_THREADS, 1) decode_scores_pair_kernel(const 
 // The tail chunk's CTA first scores its tokens (scale * q . k_tail): nobody else reads those scores.
 constexpr int SM_MAX_CHUNKS = 72;   // >= 64 split-K slabs + the tail chunk
 
-__global__ void __launch_bounds__(256) softmax_chunk_kernel(float* __restrict__ scores, long long ld, int S, int T,
-                                                            int kps, int nchunk_s, const __nv_bfloat16* __restrict__ q,
-                                                            const __nv_bfloat16* __restrict__ k_tail, long long sh,
-                                                            long long st, int qpk, int D, float scale,
-                                                            __nv_bfloat16* __restrict__ prob, long long ldp,
-                                                            float* __restrict__ chunk_max, float* __restrict__ chunk_sum,
-                                                            const float* __restrict__ raw_bias, const float* __restrict__ row_scale,
-                                                            float raw_scale) {
+// One (q head, chunk) unit, worked by NT threads (NT = 32: one warp, shuffles only -- the prefix chunks, a few KB each;
+// NT = 256: the whole block -- the dense tail chunk, which first has to score its tokens).
+template <int NT>
+__device__ __forceinline__ void softmax_unit(float* __restrict__ scores, long long ld, int S, int T, int kps, int nchunk_s,
+                                             const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k_tail,
+                                             long long sh, long long st, int qpk, int D, float scale,
+                                             __nv_bfloat16* __restrict__ prob, long long ldp, float* __restrict__ chunk_max,
+                                             float* __restrict__ chunk_sum, const float* __restrict__ raw_bias,
+                                             const float* __restrict__ row_scale, float raw_scale, int hq, int ch, float* red,
+                                             float* bcast) {
   // MLA path (raw_scale != 0): the scores buffer holds the RAW products q^ . a_t; the score of token t is
   // (raw * row_scale[t] + raw_bias[t]) * raw_scale, applied on the fly in both passes, and the probability that goes to
   // the GEMM is p * row_scale[t] (the value side of the absorbed form) while the chunk sum stays that of p.
   const bool xf = raw_scale != 0.f;
-  __shared__ float red[8];
-  __shared__ float bcast;
-  const int hq = blockIdx.x, ch = blockIdx.y;
   float* s = scores + hq * ld;
   const float* rb = raw_bias != nullptr ? raw_bias + hq * ld : nullptr;
   __nv_bfloat16* p = prob + hq * ldp;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tid = NT == 32 ? lane : static_cast<int>(threadIdx.x);
   auto load4 = [&](int i) -> float4 {   // four transformed scores from token i (16-byte aligned)
     float4 x = *reinterpret_cast<const float4*>(s + i);
     if (xf) {
@@ -1131,38 +1131,40 @@ __global__ void __launch_bounds__(256) softmax_chunk_kernel(float* __restrict__ 
     i0 = S;
     i1 = S + T;
     const int h = hq / qpk;
-    for (int t = warp; t < T; t += 8) {
+    for (int t = warp; t < T; t += NT / 32) {
       const __nv_bfloat16* kr = k_tail + h * sh + t * st;
       float acc = 0.f;
       for (int d = lane; d < D; d += 32) acc += __bfloat162float(q[hq * D + d]) * __bfloat162float(kr[d]);
       acc = warp_sum(acc);
       if (lane == 0) s[S + t] = acc * scale;
     }
-    __syncthreads();
+    if (NT > 32) __syncthreads();
   }
   // ---- chunk maximum (prefix chunks start at multiples of 64 tokens: 16-byte aligned rows) ----
   const bool vec = ch < nchunk_s;
   const int nvec = vec ? max(i1 - i0, 0) >> 2 : 0;
   float m = -INFINITY;
-  for (int v = tid; v < nvec; v += 256) {
+  for (int v = tid; v < nvec; v += NT) {
     const float4 x = load4(i0 + 4 * v);
     m = fmaxf(fmaxf(m, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
   }
-  for (int i = i0 + 4 * nvec + tid; i < i1; i += 256) m = fmaxf(m, load1(i));
+  for (int i = i0 + 4 * nvec + tid; i < i1; i += NT) m = fmaxf(m, load1(i));
   m = warp_max(m);
-  if (lane == 0) red[warp] = m;
-  __syncthreads();
-  if (tid == 0) {
-    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
-    bcast = m;
-    chunk_max[hq * SM_MAX_CHUNKS + ch] = m;
+  if (NT > 32) {
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < NT / 32; ++w) m = fmaxf(m, red[w]);
+      *bcast = m;
+    }
+    __syncthreads();
+    m = *bcast;
   }
-  __syncthreads();
-  m = bcast;
+  if (tid == 0) chunk_max[hq * SM_MAX_CHUNKS + ch] = m;
   // ---- p = exp(s - m_c), l_c = sum p (second pass over a few KB that are in L1 / L2) ----
   float sum = 0.f;
   const bool vs = xf && row_scale != nullptr;   // value-side scale of the absorbed form
-  for (int v = tid; v < nvec; v += 256) {
+  for (int v = tid; v < nvec; v += NT) {
     const float4 x = load4(i0 + 4 * v);
     float e0 = __expf(x.x - m), e1 = __expf(x.y - m), e2 = __expf(x.z - m), e3 = __expf(x.w - m);
     sum += (e0 + e1) + (e2 + e3);
@@ -1176,19 +1178,45 @@ __global__ void __launch_bounds__(256) softmax_chunk_kernel(float* __restrict__ 
     w.y = pack_bf16x2(e2, e3);
     *reinterpret_cast<uint2*>(p + i0 + 4 * v) = w;
   }
-  for (int i = i0 + 4 * nvec + tid; i < i1; i += 256) {
+  for (int i = i0 + 4 * nvec + tid; i < i1; i += NT) {
     float e = __expf(load1(i) - m);
     sum += e;
     if (vs) e = bf16r(e) * row_scale[i];
     p[i] = __float2bfloat16_rn(e);
   }
   sum = warp_sum(sum);
-  __syncthreads();
-  if (lane == 0) red[warp] = sum;
-  __syncthreads();
-  if (tid == 0) {
-    for (int w = 1; w < 8; ++w) sum += red[w];
-    chunk_sum[hq * SM_MAX_CHUNKS + ch] = sum;
+  if (NT > 32) {
+    __syncthreads();
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    if (tid == 0)
+      for (int w = 1; w < NT / 32; ++w) sum += red[w];
+  }
+  if (tid == 0) chunk_sum[hq * SM_MAX_CHUNKS + ch] = sum;
+}
+
+// grid: ceil(Hq * nchunk_s / 8) blocks whose eight warps take one prefix (q head, chunk) unit each -- no block barrier, the
+// whole unit is one L2 round trip, a shuffle reduction, the exps and another shuffle reduction (the one-block-per-unit form
+// with its six block barriers took 7-8 us per layer) -- followed by Hq blocks for the tail chunks.
+__global__ void __launch_bounds__(256) softmax_chunk_kernel(float* __restrict__ scores, long long ld, int S, int T,
+                                                            int kps, int nchunk_s, int Hq, const __nv_bfloat16* __restrict__ q,
+                                                            const __nv_bfloat16* __restrict__ k_tail, long long sh,
+                                                            long long st, int qpk, int D, float scale,
+                                                            __nv_bfloat16* __restrict__ prob, long long ldp,
+                                                            float* __restrict__ chunk_max, float* __restrict__ chunk_sum,
+                                                            const float* __restrict__ raw_bias, const float* __restrict__ row_scale,
+                                                            float raw_scale) {
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const int nprefix_blocks = (Hq * nchunk_s + 7) / 8;
+  if (static_cast<int>(blockIdx.x) < nprefix_blocks) {
+    const int unit = static_cast<int>(blockIdx.x) * 8 + static_cast<int>(threadIdx.x >> 5);
+    if (unit >= Hq * nchunk_s) return;
+    softmax_unit<32>(scores, ld, S, T, kps, nchunk_s, q, k_tail, sh, st, qpk, D, scale, prob, ldp, chunk_max, chunk_sum, raw_bias,
+                     row_scale, raw_scale, unit / nchunk_s, unit % nchunk_s, red, &bcast);
+  } else {
+    softmax_unit<256>(scores, ld, S, T, kps, nchunk_s, q, k_tail, sh, st, qpk, D, scale, prob, ldp, chunk_max, chunk_sum, raw_bias,
+                      row_scale, raw_scale, static_cast<int>(blockIdx.x) - nprefix_blocks, nchunk_s, red, &bcast);
   }
 }
 
@@ -1637,7 +1665,7 @@ extern "C" int xkv_decode_attention_lse(const void* q, int Hq, int H, int D, con
   const int kps = (nkb_p + split - 1) / split;          // k-blocks per slab, as xkv_gemm_grouped cuts them
   const int nchunks = split + 1;
   XKV_REQUIRE(nchunks <= SM_MAX_CHUNKS, "decode: too many softmax chunks");
-  softmax_chunk_kernel<<<dim3(Hq, nchunks), 256, 0, st>>>(scores, ldl, S, T, kps, split, static_cast<const __nv_bfloat16*>(q),
+  softmax_chunk_kernel<<<(Hq * split + 7) / 8 + Hq, 256, 0, st>>>(scores, ldl, S, T, kps, split, Hq, static_cast<const __nv_bfloat16*>(q),
                                                           static_cast<const __nv_bfloat16*>(k_tail), tail_stride_h,
                                                           tail_stride_t, qpk, D, scale, prob, ldl, chunk_max, rowsum, nullptr, nullptr,
                                                           0.f);
@@ -1756,7 +1784,7 @@ extern "C" int xkv_decode_absorbed(const void* q_hat, int Hq, const void* A, int
   XKV_REQUIRE(nchunks <= SM_MAX_CHUNKS, "absorbed decode: too many softmax chunks");
   XKV_REQUIRE(scale != 0.f, "absorbed decode: the softmax scale must not be zero");
   XKV_REQUIRE(row_scale == nullptr || (reinterpret_cast<uintptr_t>(row_scale) & 15) == 0, "absorbed decode: row_scale must be 16-byte aligned");
-  softmax_chunk_kernel<<<dim3(Hq, nchunks), 256, 0, st>>>(scores, ldl, S, 0, kps, split, nullptr, nullptr, 0, 0, 1, 0, scale,
+  softmax_chunk_kernel<<<(Hq * split + 7) / 8 + Hq, 256, 0, st>>>(scores, ldl, S, 0, kps, split, Hq, nullptr, nullptr, 0, 0, 1, 0, scale,
                                                           prob, ldl, chunk_max, rowsum, bias_q != nullptr ? bias : nullptr,
                                                           row_scale, scale);
   XKV_LAUNCHED();
