@@ -147,9 +147,16 @@ def test_dense_tail_longer_than_a_softmax_chunk(S, T):
     _case(S, 4, 64, 2, 32, 64, T, 1, 0, False)
 
 
-def test_decode_large_rank_falls_back_to_tiled_kernel():
-    # r_k = 1024: one head's slice is 256 KiB > 128 KiB of shared memory
-    _case(1024, 2, 128, 4, 1024, 256, 2, 4, 1, True)
+@pytest.mark.parametrize("rk,H,variant", [(768, 2, "auto"), (1024, 2, "auto"), (1024, 2, "cl1"), (1536, 4, "auto")])
+def test_decode_large_ranks(rk, H, variant):
+    """r_k = 768 / 1024: half a head's slice (96 / 128 KiB) still fits beside a 7- / 5-slot ring in the CTA-pair kernel;
+    the single-CTA kernels cannot hold the whole slice (192 / 256 KiB > 128 KiB) and take the tile-per-CTA kernel, as every
+    kernel does from r_k = 1408 up."""
+    _set_variant(variant)
+    try:
+        _case(1024, H, 128, 4, rk, 256, 2, 4, 1, True)
+    finally:
+        _set_variant("auto")
 
 
 def test_token_shards_merge_to_the_unsharded_attention():
