@@ -298,54 +298,59 @@ __global__ void __launch_bounds__(P_THREADS, 1) decode_scores_persistent_kernel(
       for (int kb = 0; kb < P.nkb; ++kb) tma_load_2d(sB + kb * B_KB_BYTES, &P.b_head_map, b_bar, kb * DBK, h * D);
     }
     __syncwarp();
-    int s = 0;
-    uint32_t ph = 0;
-    for (int tile = slot; tile < ntiles; tile += nslots) {
-      for (int kb = 0; kb < P.nkb; ++kb) {
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        if (elect_one()) {
+    if (elect_one()) {   // one lane runs the whole loop (see decode_scores_mma2_kernel)
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = slot; tile < ntiles; tile += nslots) {
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
           mbar_expect_tx(&full_bar[s], D_A_BYTES);
           tma_load_2d(sA + s * D_A_BYTES, &P.a_map, &full_bar[s], kb * DBK, tile * DBM);
-        }
-        __syncwarp();
-        if (++s == PA_STAGES) {
-          s = 0;
-          ph ^= 1u;
+          if (++s == PA_STAGES) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     constexpr uint32_t idesc = umma_idesc_bf16(DBM, D, 0, 0);
+    constexpr uint64_t kKStep = 32 >> 4, kStageStep = D_A_BYTES >> 4, kBlockStep = B_KB_BYTES >> 4;
     mbar_wait(b_bar, 0);
-    int s = 0, acc = 0;
-    uint32_t ph = 0, acc_ph = 0u;   // acc_ph: one phase bit per accumulator
-    const uint32_t b_base = smem_u32(sB);
-    for (int tile = slot; tile < ntiles; tile += nslots) {
-      mbar_wait(&tempty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);   // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * D);
-      for (int kb = 0; kb < P.nkb; ++kb) {
-        mbar_wait(&full_bar[s], ph);
+    if (elect_one()) {   // one lane issues everything, descriptors advance by 64-bit adds (see decode_scores_mma2_kernel)
+      const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA), 16, 1024);
+      const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB), 16, 1024);
+      uint64_t a_desc = a_desc0;
+      int s = 0, acc = 0;
+      uint32_t ph = 0, acc_ph = 0u;   // acc_ph: one phase bit per accumulator
+      for (int tile = slot; tile < ntiles; tile += nslots) {
+        mbar_wait(&tempty_bar[acc], ((acc_ph >> acc) & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_base = smem_u32(sA + s * D_A_BYTES);
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < DBK / 16; ++k)
-            umma_bf16_ss(d_addr, umma_desc_sw128(a_base + k * 32, 16, 1024),
-                         umma_desc_sw128(b_base + kb * B_KB_BYTES + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        const uint32_t d_addr = tmem_base + static_cast<uint32_t>(acc * D);
+        uint64_t b_desc = b_desc0;
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          umma_bf16_ss(d_addr, a_desc, b_desc, idesc, kb > 0 ? 1u : 0u);
+          umma_bf16_ss(d_addr, a_desc + kKStep, b_desc + kKStep, idesc, 1u);
+          umma_bf16_ss(d_addr, a_desc + 2 * kKStep, b_desc + 2 * kKStep, idesc, 1u);
+          umma_bf16_ss(d_addr, a_desc + 3 * kKStep, b_desc + 3 * kKStep, idesc, 1u);
           umma_commit(&empty_bar[s]);
+          b_desc += kBlockStep;
+          a_desc += kStageStep;
+          if (++s == PA_STAGES) {
+            s = 0;
+            ph ^= 1u;
+            a_desc = a_desc0;
+          }
         }
-        __syncwarp();
-        if (++s == PA_STAGES) {
-          s = 0;
-          ph ^= 1u;
-        }
+        umma_commit(&tfull_bar[acc]);
+        acc_ph ^= 1u << acc;
+        acc = (acc + 1) % P_NACC;
       }
-      if (elect_one()) umma_commit(&tfull_bar[acc]);
-      __syncwarp();
-      acc_ph ^= 1u << acc;
-      acc = (acc + 1) % P_NACC;
     }
+    __syncwarp();
   } else {
     // ===== epilogue: 16 warps, four per TMEM lane quarter; each thread owns one token and PP rotation pairs
     // (d, d + D/2) of it.  ncu on the 8-warp version: the epilogue, not the MMA or the TMA ring, set the pace
