@@ -169,3 +169,54 @@ def test_grouped_launch():
     torch.cuda.synchronize()
     for o, r in zip(outs, refs):
         assert torch.equal(o, r)
+
+
+def _gram(n, K, *, layers=0, split_k=1, phases=1, ints=True, seed=5):
+    """Upper-triangle tiles of G = X^T X through xkv_gemm_grouped; X (K x n) packed or as `layers` column blocks."""
+    from xkv_b200 import ops
+
+    X = _mk(K, n, ints, seed)
+    out = torch.full((split_k, n, n), float("nan"), device="cuda")
+    kw = dict(M=n, N=n, K=K, a_mn_major=True, b_mn_major=True, sym_upper=True, split_k=split_k,
+              split_stride=out.stride(0), accum_phases=phases)
+    if layers:
+        cols = n // layers
+        # per-layer tensors as the cache holds them: separate allocations with their own leading dimension
+        parts = [X[:, i * cols:(i + 1) * cols].contiguous() for i in range(layers)]
+        p = ops.make_problem([], [], out[0], a_layers=parts, b_layers=parts, **kw)
+    else:
+        parts = [X]
+        p = ops.make_problem([X], [X], out[0], **kw)
+    ops.gemm_grouped([p])
+    torch.cuda.synchronize()
+    return out.sum(0), X.float().t() @ X.float()
+
+
+@pytest.mark.parametrize("n,K,layers,split_k,phases", [
+    (256, 64, 0, 1, 1),        # one pair tile, one k block
+    (768, 1024, 0, 2, 1),      # 3 x 3 pair tiles (6 in the upper set), split-K
+    (1024, 4096, 4, 1, 4),     # layered operands read in place, accumulation phases
+    (200, 1100, 0, 1, 3),      # ragged: the odd CTA's rows and columns are partly out of range
+    (328, 168, 0, 1, 1),       # n not a multiple of 64, K not a multiple of 64; the odd CTA of tile row 1 is all padding
+    (1536, 2048, 3, 3, 5),     # 3 layers of 512 columns: pair tiles straddle layer boundaries
+])
+def test_gram_pair_kernel_matches_single_cta_tiles_bit_for_bit(n, K, layers, split_k, phases):
+    """The CTA-pair Gram (cta_group::2, 256 x 256 tiles) against torch (exact on integer data) and against the single-CTA
+    tiles of the same engine on Gaussian data: the K reduction of an output element runs in the same order in both, so the
+    upper-triangle tiles agree bit for bit."""
+    from xkv_b200 import _lib
+
+    lib = _lib.load()
+    try:
+        lib.xkv_gemm_set_gram_pair(1)
+        got, ref = _gram(n, K, layers=layers, split_k=split_k, phases=phases)
+        _check(got, ref, exact=True, sym=True)
+        pair, _ = _gram(n, K, layers=layers, split_k=split_k, phases=phases, ints=False)
+        lib.xkv_gemm_set_gram_pair(0)
+        single, ref = _gram(n, K, layers=layers, split_k=split_k, phases=phases, ints=False)
+    finally:
+        lib.xkv_gemm_set_gram_pair(1)
+    mask = torch.triu(torch.ones_like(ref, dtype=torch.bool))
+    assert not torch.isnan(pair[mask]).any()
+    assert torch.equal(pair[mask], single[mask])
+    _check(pair, ref, exact=False, sym=True)

@@ -143,6 +143,7 @@ SIGNATURES = {
     "xkv_slerp_workspace_bytes": (_sz, [_i64]),
     "xkv_slerp_merge": (_i, [_vp, _vp, _i64, _i, _i64, _f, _f, _vp, _vp, _i64, _vp, _sz, _vp]),
     "xkv_gemm_problem_size": (C.c_size_t, []),
+    "xkv_gemm_set_gram_pair": (None, [_i]),
     "xkv_factorize_groups": (_i, [_pp, _i, _i, _i, _i, _i64, _i, C.POINTER(FactorizeOptions), _pp, _pp, _pp, _pp, _vp, _sz,
                                   _pp, _vp]),
     "xkv_factorize_workspace_bytes_mixed": (_sz, [_i, _i, _i, _vp, C.POINTER(FactorizeOptions)]),

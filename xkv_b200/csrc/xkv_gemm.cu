@@ -399,9 +399,271 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// Gram in CTA pairs: G = X^T X (both operands MN-major tiles of X, fp32 output, symmetric tile set) with a 256 x 256
+// output tile per CTA PAIR (cta_group::2, the two SMs of a TPC).  CTA r of the pair streams the 128 columns
+// [m0 + 128 r, +128) of X as its rows of A and the 128 columns [n0 + 128 r, +128) as its HALF of B, the even CTA issues
+// one M = 256, N = 256 tcgen05.mma per K = 16 slice and each CTA receives its 128 rows x 256 columns of the tile in its
+// own tensor memory.  Why: the single-CTA 128 x 256 tile pulls 48 KiB from L2 per k block (96 B/clk per SM at the
+// MMA rate, and 12 KiB of shared-memory operand reads per MMA); the pair pulls 32 KiB per CTA (64 B/clk, 8 KiB per MMA)
+// for the same flops, which leaves room for 6 ring stages instead of 4.  Everything else is gemm_kernel<1, 1>: layered
+// operands read in place, split-K slabs, accumulation phases that alternate between two accumulators and are summed in
+// fp32 by the epilogue warps (of both CTAs, each on its own rows).
+// Barriers: full[s] lives in the even CTA (both CTAs' loads complete on it); empty[s] and tmem_full[2] exist in each
+// CTA and are signalled by multicast commits; tmem_empty[2] lives in the even CTA and counts the epilogue warps of both.
+// ---------------------------------------------------------------------------------------------
+constexpr int PG_BM = 256;                              // pair tile rows (128 per CTA)
+constexpr int PG_STAGES = 6;
+constexpr int PG_A_BYTES = 2 * CHUNK_BYTES;             // 128 A columns of this CTA
+constexpr int PG_B_BYTES = 2 * CHUNK_BYTES;             // this CTA's 128 of the tile's 256 B columns
+constexpr int PG_STAGE_BYTES = PG_A_BYTES + PG_B_BYTES; // 32 KiB
+constexpr size_t PG_SMEM_BYTES = PG_STAGES * PG_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gram_pair_kernel(const __grid_constant__ GemmParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + PG_STAGES * PG_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + PG_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + PG_STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int crank = static_cast<int>(cluster_ctarank());
+  const bool leader = crank == 0;
+
+  // ---- locate this pair's problem / split / tile (cta_begin counts CTAs: two per pair tile) ----
+  int pi = 0;
+  while (pi + 1 < P.nprob && static_cast<int>(blockIdx.x) >= P.p[pi + 1].cta_begin) ++pi;
+  const GemmProb& pr = P.p[pi];
+  if (pr.run_if != nullptr && *pr.run_if == 0) return;   // uniform over the pair, before any barrier / TMEM allocation
+  const int local = (static_cast<int>(blockIdx.x) - pr.cta_begin) >> 1;
+  const int split = local / pr.ntiles;
+  int t = local - split * pr.ntiles;
+  int tm = 0, tn = 0;
+  if (pr.sym_upper) {
+    for (int i = 0; i < pr.tiles_m; ++i) {
+      const int cnt = pr.tiles_n - i;
+      if (t < cnt) {
+        tm = i;
+        tn = i + t;
+        break;
+      }
+      t -= cnt;
+    }
+  } else {
+    tm = t / pr.tiles_n;
+    tn = t - tm * pr.tiles_n;
+  }
+  const int m0 = tm * PG_BM + crank * BM;   // this CTA's rows of the tile
+  const int n0 = tn * BN;                   // the tile's columns (all 256 land in this CTA's tensor memory)
+  const int nb0 = n0 + crank * (BN / 2);    // the B columns this CTA loads
+  const int kb0 = split * pr.kblocks_per_split;
+  const int kb1 = min(kb0 + pr.kblocks_per_split, pr.nkb);
+  const int nk = max(kb1 - kb0, 0);
+  const int nph = max(1, min(pr.phases, nk));
+  const uint32_t tmem_cols = nph > 1 ? 2 * TMEM_COLS : TMEM_COLS;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < PG_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&tmem_full_bar[0], 1);
+    mbar_init(&tmem_full_bar[1], 1);
+    mbar_init(&tmem_empty_bar[0], 8);   // one arrival per epilogue warp of BOTH CTAs
+    mbar_init(&tmem_empty_bar[1], 8);
+    mbar_fence_init();
+    tma_prefetch_desc(&pr.a_map[0]);
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's loads, commits and arrivals target this CTA's barriers: all initialised first
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (in each CTA; completions are counted on the even CTA's barrier) =====================
+    const CUtensorMap* chunk_map[4];   // A chunk 0, 1, B chunk 0, 1
+    int chunk_col[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int col = (c < 2 ? m0 : nb0) + 64 * (c & 1);
+      chunk_col[c] = col;
+      const int layers = c < 2 ? pr.a_layers : pr.b_layers;
+      chunk_map[c] = layers ? layer_map(P, c < 2 ? pr.a_layer_begin : pr.b_layer_begin, layers, pr.layer_cols, col, chunk_col[c])
+                            : (c < 2 ? &pr.a_map[0] : &pr.b_map[0]);
+    }
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t full0 = cluster_map_shared(smem_u32(&full_bar[0]), 0);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        uint8_t* st = smem + s * PG_STAGE_BYTES;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        if (leader) mbar_expect_tx(&full_bar[s], 2 * PG_STAGE_BYTES);
+        const uint32_t fb = full0 + static_cast<uint32_t>(s * 8);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tma_load_2d_pair(st + c * CHUNK_BYTES, chunk_map[c], fb, chunk_col[c], kb * BK);
+        if (++s == PG_STAGES) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer: one elected lane of the even CTA =====================
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(PG_BM, BN, 1, 1);
+      constexpr uint64_t kStageStep = PG_STAGE_BYTES >> 4;
+      constexpr uint64_t kKStep = 2048 >> 4;   // MN-major: 16 K rows of 128 B
+      if (elect_one()) {
+        const uint32_t base = smem_u32(smem);
+        const uint64_t a_desc0 = umma_desc_sw128(base, CHUNK_BYTES, 1024);
+        const uint64_t b_desc0 = umma_desc_sw128(base + PG_A_BYTES, CHUNK_BYTES, 1024);
+        uint64_t a_desc = a_desc0, b_desc = b_desc0;
+        int s = 0;
+        uint32_t ph = 0;
+        int it = 0;
+        for (int phs = 0; phs < nph; ++phs) {
+          const uint32_t acc = tmem_base + static_cast<uint32_t>(phs & 1) * TMEM_COLS;
+          if (phs >= 2) {   // the epilogues of both CTAs must have drained this accumulator (phase phs - 2)
+            mbar_wait_cluster(&tmem_empty_bar[phs & 1], static_cast<uint32_t>(((phs >> 1) - 1) & 1));
+            tc_fence_after();
+          }
+          const int it_end = (nph == 1) ? nk : static_cast<int>((static_cast<long long>(nk) * (phs + 1)) / nph);
+          const int it_begin = it;
+          for (; it < it_end; ++it) {
+            mbar_wait_cluster(&full_bar[s], ph);
+            tc_fence_after();
+            umma_bf16_ss_pair(acc, a_desc, b_desc, idesc, it > it_begin ? 1u : 0u);
+            umma_bf16_ss_pair(acc, a_desc + kKStep, b_desc + kKStep, idesc, 1u);
+            umma_bf16_ss_pair(acc, a_desc + 2 * kKStep, b_desc + 2 * kKStep, idesc, 1u);
+            umma_bf16_ss_pair(acc, a_desc + 3 * kKStep, b_desc + 3 * kKStep, idesc, 1u);
+            umma_commit_pair(&empty_bar[s]);   // frees the stage in BOTH CTAs once these MMAs have read it
+            a_desc += kStageStep;
+            b_desc += kStageStep;
+            if (++s == PG_STAGES) {
+              s = 0;
+              ph ^= 1u;
+              a_desc = a_desc0;
+              b_desc = b_desc0;
+            }
+          }
+          umma_commit_pair(&tmem_full_bar[phs & 1]);   // this phase's accumulator is complete (both CTAs' halves)
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 of each CTA, on its own 128 rows) =====================
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < pr.M;
+    float* outf = reinterpret_cast<float*>(pr.D) + static_cast<long long>(split) * pr.split_stride;
+    const bool vec_ok = (pr.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(pr.D) & 15) == 0) && ((pr.split_stride % 4) == 0);
+    const uint32_t tempty0 = cluster_map_shared(smem_u32(&tmem_empty_bar[0]), 0);
+#pragma unroll 1
+    for (int phs = 0; phs < nph; ++phs) {
+      // later phases add into what this same thread stored one phase ago; the partial sums are fetched one column block
+      // ahead (the first one before the accumulator is complete)
+      float4 pre[8];
+      auto prefetch = [&](int c) -> bool {
+        const int col0 = n0 + c * 32;
+        if (!(phs > 0 && row_ok && vec_ok && c < BN / 32 && col0 + 32 <= pr.N)) return false;
+        const float4* src = reinterpret_cast<const float4*>(outf + static_cast<long long>(row) * pr.ldd + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pre[j] = src[j];
+        return true;
+      };
+      bool have_pre = prefetch(0);
+      mbar_wait(&tmem_full_bar[phs & 1], static_cast<uint32_t>((phs >> 1) & 1));
+      tc_fence_after();
+      const uint32_t acc = tmem_base + static_cast<uint32_t>(phs & 1) * TMEM_COLS;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= pr.N) break;  // warp-uniform
+        uint32_t v[32];
+        __syncwarp();
+        if (nk > 0) {
+          tmem_ld_32x32(acc + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), v);
+          float4 cur[8];
+          const bool have_cur = have_pre;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cur[j] = pre[j];
+          have_pre = prefetch(c + 1);
+          tmem_ld_wait();
+          if (have_cur) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + cur[j].x);
+              v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + cur[j].y);
+              v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + cur[j].z);
+              v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + cur[j].w);
+            }
+          } else if (phs > 0 && row_ok) {
+            const float* src = outf + static_cast<long long>(row) * pr.ldd + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < pr.N) v[j] = __float_as_uint(__uint_as_float(v[j]) + src[j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        if (row_ok) {
+          float* dst = outf + static_cast<long long>(row) * pr.ldd + col0;
+          if (col0 + 32 <= pr.N && vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<uint4*>(dst)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < pr.N) dst[j] = __uint_as_float(v[j]);
+          }
+        }
+      }
+      if (phs + 2 < nph) {   // hand the accumulator back to the issuer (in the even CTA)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty0 + static_cast<uint32_t>((phs & 1) * 8));
+      }
+    }
+  }
+
+  // ---- teardown: nobody leaves (or frees tensor memory) while the pair's MMAs, commits or arrivals are pending ----
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int build_problem(const xkv_gemm_problem& in, GemmProb& out, int& cta_cursor, GemmParams& params, int& map_cursor) {
+static int g_gram_pair = 1;   // xkv_gemm_set_gram_pair
+
+// the launch is a Gram in the pair kernel's form: every problem G = X^T X on MN-major operands, symmetric tile set,
+// one term, plain fp32 output
+static bool pair_form(const xkv_gemm_problem* ps, int n) {
+  if (!g_gram_pair) return false;
+  for (int i = 0; i < n; ++i) {
+    const xkv_gemm_problem& p = ps[i];
+    if (!(p.a_mn_major && p.b_mn_major && p.sym_upper && p.num_terms == 1 && !p.out_bf16 && !p.out_transposed && p.M == p.N))
+      return false;
+  }
+  return true;
+}
+
+static int build_problem(const xkv_gemm_problem& in, GemmProb& out, int& cta_cursor, GemmParams& params, int& map_cursor,
+                         bool pair = false) {
   XKV_REQUIRE(in.M > 0 && in.N > 0 && in.K > 0, "gemm: empty problem M=%d N=%d K=%d", in.M, in.N, in.K);
   XKV_REQUIRE(in.num_terms >= 1 && in.num_terms <= 6, "gemm: num_terms=%d out of range", in.num_terms);
   XKV_REQUIRE(in.lda % 8 == 0 && in.ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements");
@@ -482,12 +744,13 @@ static int build_problem(const xkv_gemm_problem& in, GemmProb& out, int& cta_cur
   out.N = in.N;
   out.K = in.K;
   out.nterms = in.num_terms;
-  out.tiles_m = (in.M + BM - 1) / BM;
+  const int bm = pair ? PG_BM : BM;   // the pair kernel's tile is 256 x 256, two CTAs
+  out.tiles_m = (in.M + bm - 1) / bm;
   out.tiles_n = (in.N + BN - 1) / BN;
   out.sym_upper = in.sym_upper ? 1 : 0;
   if (out.sym_upper) {
     int cnt = 0;
-    for (int i = 0; i < out.tiles_m; ++i) cnt += out.tiles_n - (i * BM) / BN;
+    for (int i = 0; i < out.tiles_m; ++i) cnt += out.tiles_n - (i * bm) / BN;
     out.ntiles = cnt;
   } else {
     out.ntiles = out.tiles_m * out.tiles_n;
@@ -502,13 +765,43 @@ static int build_problem(const xkv_gemm_problem& in, GemmProb& out, int& cta_cur
   XKV_REQUIRE(out.phases == 1 || (!in.out_bf16 && !in.out_transposed),
               "gemm: accum_phases > 1 needs a plain fp32 output");
   out.cta_begin = cta_cursor;
-  cta_cursor += out.ntiles * out.split_k;
+  cta_cursor += out.ntiles * out.split_k * (pair ? 2 : 1);
   return 0;
 }
 
 bool& gemm_low_priority() {
   static thread_local bool low = false;
   return low;
+}
+
+static int launch_gram_pair(const GemmParams& params, int grid, cudaStream_t stream) {
+  static PerDevice<bool> configured;
+  if (!configured()) {
+    XKV_CHECK_CUDA(cudaFuncSetAttribute(gram_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(PG_SMEM_BYTES)));
+    configured() = true;
+  }
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = PG_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.numAttrs = 1;
+  if (gemm_low_priority()) {
+    attr[1].id = cudaLaunchAttributePriority;
+    attr[1].val.priority = 0;
+    cfg.numAttrs = 2;
+  }
+  cfg.attrs = attr;
+  XKV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gram_pair_kernel, params));
+  XKV_LAUNCHED();
+  return 0;
 }
 
 template <int A_MN, int B_MN>
@@ -543,6 +836,7 @@ static int launch_variant(const GemmParams& params, int grid, cudaStream_t strea
 }  // namespace xkv
 
 extern "C" size_t xkv_gemm_problem_size(void) { return sizeof(xkv_gemm_problem); }
+extern "C" void xkv_gemm_set_gram_pair(int on) { xkv::g_gram_pair = on ? 1 : 0; }
 
 extern "C" int xkv_gemm_grouped(const xkv_gemm_problem* problems, int num_problems, void* stream) {
   using namespace xkv;
@@ -553,13 +847,15 @@ extern "C" int xkv_gemm_grouped(const xkv_gemm_problem* problems, int num_proble
   static thread_local GemmParams params;  // ~22 KiB, keep it off the stack
   params.nprob = num_problems;
   int cursor = 0, map_cursor = 0;
+  const bool pair = pair_form(problems, num_problems);
   for (int i = 0; i < num_problems; ++i) {
     XKV_REQUIRE((problems[i].a_mn_major ? 1 : 0) == a_mn && (problems[i].b_mn_major ? 1 : 0) == b_mn,
                 "gemm: all problems of one launch must share operand majors");
-    int rc = build_problem(problems[i], params.p[i], cursor, params, map_cursor);
+    int rc = build_problem(problems[i], params.p[i], cursor, params, map_cursor, pair);
     if (rc) return rc;
   }
   cudaStream_t st = as_stream(stream);
+  if (pair) return launch_gram_pair(params, cursor, st);
   if (!a_mn && !b_mn) return launch_variant<0, 0>(params, cursor, st);
   if (!a_mn && b_mn) return launch_variant<0, 1>(params, cursor, st);
   if (a_mn && !b_mn) return launch_variant<1, 0>(params, cursor, st);
