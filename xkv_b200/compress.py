@@ -62,6 +62,7 @@ def compress_groups(
     in_place: bool = True,
     job_events: Optional[list] = None,
     mixed: bool = False,
+    priorities: Optional[Sequence[int]] = None,
 ) -> List[GroupFactors]:
     """Compress equally-shaped layer groups. keys[g][i] / values[g][i]: (1, H, S, D) bf16 of layer i of
     group g (keys PRE-RoPE, as the reference hands them over, llama.py:49).
@@ -74,7 +75,8 @@ def compress_groups(
     launch (Cholesky clusters, Jacobi windows, elementwise kernels) carries both.  Built, parity-tested and measured
     SLOWER at config 2 (48.4 ms against 18.3 + 24.4 ms for the two batches: the 16-matrix Gram launch alone takes 17.7 ms
     against 6.9 + 6.6 ms — a power-capped part sustains a 7 ms tensor burst at a higher clock than a 17 ms one — and the
-    latency-bound stages did not shrink), so it is off by default; see DESIGN.md."""
+    latency-bound stages did not shrink), so it is off by default; see DESIGN.md.  `priorities`: stream priority of job j
+    (jobs: the K chains in group order, then the V chains; cycled when shorter), default -1 / -2 / -3 round-robin."""
     ng = len(keys)
     if ng == 0:
         return []
@@ -137,7 +139,8 @@ def compress_groups(
     # windows) are not queued behind the hundreds of GEMM CTAs of another.  Measured (bench step, 10 steps, two runs):
     # no priorities, last job on the caller's stream 44.3 / 43.1 ms; all side streams 41.9; priorities 39.2 - 39.8 (8 jobs).
     for j, (dst, lo, groups, rank) in enumerate(jobs):
-        stream = main if num_streams <= 1 else _side_stream(dev, 200 + j, priority=-1 - (j % 3))
+        prio = priorities[j % len(priorities)] if priorities else -1 - (j % 3)
+        stream = main if num_streams <= 1 else _side_stream(dev, 200 + j, priority=prio)
         if stream is not main:
             stream.wait_stream(main)
             used.append(stream)
