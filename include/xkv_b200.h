@@ -96,7 +96,8 @@ XKV_API int xkv_gemm_grouped(const xkv_gemm_problem* problems_host, int num_prob
 XKV_API size_t xkv_gemm_problem_size(void);
 /* test / tuning hook: a launch whose problems are all Grams (G = X^T X: both operands MN-major, sym_upper, one term,
  * fp32 output) runs in CTA pairs (cta_group::2, one 256 x 256 tile per pair: gram_pair_kernel); 0 sends it through the
- * single-CTA 128 x 256 tiles of every other product, 1 (default) restores the pairs.  Same results bit for bit. */
+ * single-CTA 128 x 256 tiles of every other product, 1 (default) restores the pairs, 3 .. 7 = pairs with that many
+ * 32 KiB ring stages per CTA instead of the default 6.  Same results bit for bit. */
 XKV_API void xkv_gemm_set_gram_pair(int on);
 
 /* ---- small fp32 helpers of the factorisation ------------------------------------------ */

@@ -7,27 +7,29 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
-from xkv_b200 import compress
+from xkv_b200 import compress, factorize
 
 c = bench.CONFIGS[2]
 dev = torch.device("cuda")
 keys, vals = bench.make_cache(c, dev)
 lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -5)
 print(json.dumps({"priority_range": [lo, hi]}), flush=True)
+VH = [-1, -1, -1, -1, -3, -3, -3, -3]
+RR = [-1, -2, -3]
 schemes = {
-    "default -1-j%3": None,
-    "V high K low": [-1, -1, -1, -1, -3, -3, -3, -3],
-    "V high staggered": [-1, -1, -2, -2, -3, -3, -4, -4],
-    "K high V low": [-3, -3, -3, -3, -1, -1, -1, -1],
-    "distinct V first": [-1, -1, -2, -2, -5, -4, -4, -3],
-    "interleaved pairs": [-1, -2, -3, -4, -2, -3, -4, -5],
-    "all equal": [-1],
-    "two levels alternate": [-1, -2],
+    "no stagger": dict(stagger=False),
+    "stagger at Gram": dict(stagger=True),
+    "stagger at reduce+split": dict(stagger=True, mark=2),
+    "stagger at range finder": dict(stagger=True, mark=3),
 }
 graphs = {}
+runs = {}
 for name, pr in schemes.items():
     def run(pr=pr):
-        return compress.compress_groups(keys, vals, c["rank_k"], c["rank_v"], num_streams=8, priorities=pr)
+        pr = dict(pr)
+        factorize._STAGGER_MARK = pr.pop("mark", 1)
+        return compress.compress_groups(keys, vals, c["rank_k"], c["rank_v"], num_streams=8, **pr)
+    runs[name] = run
     run()
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
@@ -45,5 +47,18 @@ for rnd in range(2):
             g.replay()
         e1.record()
         torch.cuda.synchronize()
-        print(json.dumps({"round": rnd, "scheme": name, "priorities": schemes[name], "ms_per_step": round(e0.elapsed_time(e1) / 10, 3)}),
+        print(json.dumps({"round": rnd, "scheme": name, "ms_per_step": round(e0.elapsed_time(e1) / 10, 3)}),
+              flush=True)
+
+    for name, run in runs.items():
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        print(json.dumps({"round": rnd, "scheme": name, "mode": "host-enqueued", "ms_per_step": round(e0.elapsed_time(e1) / 10, 3)}),
               flush=True)

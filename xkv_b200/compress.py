@@ -63,6 +63,8 @@ def compress_groups(
     job_events: Optional[list] = None,
     mixed: bool = False,
     priorities: Optional[Sequence[int]] = None,
+    stagger: bool = False,
+    v_first: bool = False,
 ) -> List[GroupFactors]:
     """Compress equally-shaped layer groups. keys[g][i] / values[g][i]: (1, H, S, D) bf16 of layer i of
     group g (keys PRE-RoPE, as the reference hands them over, llama.py:49).
@@ -76,7 +78,9 @@ def compress_groups(
     SLOWER at config 2 (48.4 ms against 18.3 + 24.4 ms for the two batches: the 16-matrix Gram launch alone takes 17.7 ms
     against 6.9 + 6.6 ms — a power-capped part sustains a 7 ms tensor burst at a higher clock than a 17 ms one — and the
     latency-bound stages did not shrink), so it is off by default; see DESIGN.md.  `priorities`: stream priority of job j
-    (jobs: the K chains in group order, then the V chains; cycled when shorter), default -1 / -2 / -3 round-robin."""
+    (jobs: the K chains in group order, then the V chains; cycled when shorter).  `stagger`: every chain's Gram launch waits
+    for the Gram of the chain enqueued before it (measured: within the noise of the simultaneous start, off by default);
+    `v_first`: enqueue the V chains before the K chains."""
     ng = len(keys)
     if ng == 0:
         return []
@@ -87,6 +91,8 @@ def compress_groups(
     if keys[0][0].shape[0] != 1:
         raise XkvError("compress: batch size 1 per call (the reference's batched SVD is one SVD per sample)")
     sides = (["k"] if merge_key else []) + (["v"] if merge_value else [])
+    if v_first:
+        sides.reverse()
     # ---- K and V matrices of a chunk of groups in ONE driver call (different ranks, one set of launches) ----
     # Needs token-major layer tensors (read in place) and sketch widths that share a Rayleigh-Ritz window.
     if (mixed and in_place and len(sides) == 2 and rank_k != rank_v and len(keys[0]) <= 16
@@ -133,17 +139,29 @@ def compress_groups(
         for lo in range(0, ng, size):
             jobs.append((dst, lo, src[lo:lo + size], rank))
     used = []
-    # Every chain on its own side stream, with CTA-level priorities -1 / -2 / -3 dealt round-robin (0, the lowest, is what the
-    # projection GEMMs are launched with: xkv_host.h gemm_low_priority): when SMs free up, the
-    # pending CTAs of a higher-priority chain go first, so one chain's latency-bound kernels (Cholesky clusters, Jacobi
-    # windows) are not queued behind the hundreds of GEMM CTAs of another.  Measured (bench step, 10 steps, two runs):
-    # no priorities, last job on the caller's stream 44.3 / 43.1 ms; all side streams 41.9; priorities 39.2 - 39.8 (8 jobs).
+    # Every chain on its own side stream with a CTA-level priority (0, the lowest, is what the projection GEMMs are
+    # launched with: xkv_host.h gemm_low_priority): when SMs free up, the pending CTAs of a higher-priority chain go first, so
+    # one chain's latency-bound kernels (Cholesky clusters, Jacobi windows) are not queued behind the hundreds of GEMM CTAs
+    # of another.  Measured (bench step, 10 steps, two runs): no priorities, last job on the caller's stream 44.3 / 43.1 ms;
+    # all side streams 41.9; priorities -1 / -2 / -3 dealt round-robin 39.2 - 39.8 (8 jobs).  With both sides compressed the
+    # chains of the larger rank (the longer ones: wider sketch, more Cholesky block steps) get the top priority -3 and the
+    # others -1, so that all chains end together: 37.9 / 38.1 -> 37.1 / 37.2 ms same box (tools/ab_priorities.py; the
+    # device has four levels, 0 .. -3; the reverse order costs 0.6 ms, distinct levels per chain gain nothing).
+    prev_gram = None   # staggered start: a chain's Gram launch waits for the Gram of the chain enqueued before it
     for j, (dst, lo, groups, rank) in enumerate(jobs):
-        prio = priorities[j % len(priorities)] if priorities else -1 - (j % 3)
+        if priorities:
+            prio = priorities[j % len(priorities)]
+        elif len(sides) == 2 and rank_k != rank_v:
+            prio = -3 if rank == max(rank_k, rank_v) else -1   # the longer chains (wider sketch) first
+        else:
+            prio = -1 - (j % 3)
         stream = main if num_streams <= 1 else _side_stream(dev, 200 + j, priority=prio)
         if stream is not main:
             stream.wait_stream(main)
             used.append(stream)
+            if prev_gram is not None:
+                stream.wait_event(prev_gram)
+        gram_done = torch.cuda.Event() if (stagger and stream is not main) else None
         with torch.cuda.stream(stream):
             if job_events is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -153,8 +171,10 @@ def compress_groups(
             # layout goes through the gather kernel first (reference cache:170-171 + :13-14)
             rows = [[factorize.layer_rows(t) for t in grp] for grp in groups] if in_place else None
             if rows is not None and all(r is not None for grp in rows for r in grp) and len(groups[0]) <= 16:
-                fs = factorize.factorize_groups(rows, rank, opts, extra_rows=extra_rows)
+                fs = factorize.factorize_groups(rows, rank, opts, extra_rows=extra_rows, gram_done=gram_done)
+                prev_gram = gram_done
             else:
+                prev_gram = None
                 xs = pack_groups(groups)
                 fs = factorize.factorize_batch(xs, rank, opts, extra_rows=extra_rows)
                 if stream is not main:

@@ -56,6 +56,7 @@ struct alignas(64) GemmProb {
 };
 struct GemmParams {
   int nprob;
+  int pair_stages;   // gram_pair_kernel: ring depth
   GemmProb p[XKV_MAX_GEMM_PROBLEMS];
   CUtensorMap layer_maps[XKV_MAX_LAYER_MAPS];
 };
@@ -412,18 +413,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 // CTA and are signalled by multicast commits; tmem_empty[2] lives in the even CTA and counts the epilogue warps of both.
 // ---------------------------------------------------------------------------------------------
 constexpr int PG_BM = 256;                              // pair tile rows (128 per CTA)
-constexpr int PG_STAGES = 6;
+constexpr int PG_STAGES = 6;                            // default ring depth (measured 5 / 6 / 7: see xkv_gemm_set_gram_pair)
+constexpr int PG_MAX_STAGES = 7;
 constexpr int PG_A_BYTES = 2 * CHUNK_BYTES;             // 128 A columns of this CTA
 constexpr int PG_B_BYTES = 2 * CHUNK_BYTES;             // this CTA's 128 of the tile's 256 B columns
 constexpr int PG_STAGE_BYTES = PG_A_BYTES + PG_B_BYTES; // 32 KiB
-constexpr size_t PG_SMEM_BYTES = PG_STAGES * PG_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr size_t pg_smem_bytes(int stages) { return static_cast<size_t>(stages) * PG_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gram_pair_kernel(const __grid_constant__ GemmParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + PG_STAGES * PG_STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + PG_STAGES;
-  uint64_t* tmem_full_bar = empty_bar + PG_STAGES;   // [2]
+  const int nstages = P.pair_stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + nstages * PG_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + PG_MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + PG_MAX_STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
@@ -465,7 +468,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gram_pair_kernel(const __grid
   const uint32_t tmem_cols = nph > 1 ? 2 * TMEM_COLS : TMEM_COLS;
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < PG_STAGES; ++i) {
+    for (int i = 0; i < nstages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -506,7 +509,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gram_pair_kernel(const __grid
         const uint32_t fb = full0 + static_cast<uint32_t>(s * 8);
 #pragma unroll
         for (int c = 0; c < 4; ++c) tma_load_2d_pair(st + c * CHUNK_BYTES, chunk_map[c], fb, chunk_col[c], kb * BK);
-        if (++s == PG_STAGES) {
+        if (++s == nstages) {
           s = 0;
           ph ^= 1u;
         }
@@ -545,7 +548,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gram_pair_kernel(const __grid
             umma_commit_pair(&empty_bar[s]);   // frees the stage in BOTH CTAs once these MMAs have read it
             a_desc += kStageStep;
             b_desc += kStageStep;
-            if (++s == PG_STAGES) {
+            if (++s == nstages) {
               s = 0;
               ph ^= 1u;
               a_desc = a_desc0;
@@ -648,7 +651,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gram_pair_kernel(const __grid
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int g_gram_pair = 1;   // xkv_gemm_set_gram_pair
+static int g_gram_pair = 1;   // xkv_gemm_set_gram_pair: 0 off, 1 default ring depth, 3 .. 7 that many stages
 
 // the launch is a Gram in the pair kernel's form: every problem G = X^T X on MN-major operands, symmetric tile set,
 // one term, plain fp32 output
@@ -774,18 +777,19 @@ bool& gemm_low_priority() {
   return low;
 }
 
-static int launch_gram_pair(const GemmParams& params, int grid, cudaStream_t stream) {
+static int launch_gram_pair(GemmParams& params, int grid, cudaStream_t stream) {
   static PerDevice<bool> configured;
   if (!configured()) {
     XKV_CHECK_CUDA(cudaFuncSetAttribute(gram_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(PG_SMEM_BYTES)));
+                                        static_cast<int>(pg_smem_bytes(PG_MAX_STAGES))));
     configured() = true;
   }
+  params.pair_stages = (g_gram_pair >= 3 && g_gram_pair <= PG_MAX_STAGES) ? g_gram_pair : PG_STAGES;
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid, 1, 1);
   cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = PG_SMEM_BYTES;
+  cfg.dynamicSmemBytes = pg_smem_bytes(params.pair_stages);
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -836,7 +840,7 @@ static int launch_variant(const GemmParams& params, int grid, cudaStream_t strea
 }  // namespace xkv
 
 extern "C" size_t xkv_gemm_problem_size(void) { return sizeof(xkv_gemm_problem); }
-extern "C" void xkv_gemm_set_gram_pair(int on) { xkv::g_gram_pair = on ? 1 : 0; }
+extern "C" void xkv_gemm_set_gram_pair(int on) { xkv::g_gram_pair = on < 0 ? 0 : on; }
 
 extern "C" int xkv_gemm_grouped(const xkv_gemm_problem* problems, int num_problems, void* stream) {
   using namespace xkv;

@@ -148,14 +148,20 @@ def mixed_ranks_ok(ranks: Sequence[int], opts: Optional[FactorizeOptions] = None
     return all(l >= w and 0 < w - (l - int(r)) <= int(r) and (w - (l - int(r)) + (l - int(r))) % 2 == 0 for l, r in zip(ls, ranks))
 
 
+_STAGGER_MARK = 1   # stage mark of the driver the `gram_done` event is recorded at (1: behind the Gram launch)
+
+
 def factorize_groups(groups: Sequence[Sequence[torch.Tensor]], rank, opts: Optional[FactorizeOptions] = None,
-                     workspace: Optional[torch.Tensor] = None, extra_rows: int = 0) -> List[Factors]:
+                     workspace: Optional[torch.Tensor] = None, extra_rows: int = 0,
+                     gram_done: Optional[torch.cuda.Event] = None) -> List[Factors]:
     """Factorise layer groups IN PLACE: groups[g][i] is the (S, H*D) row-major matrix of layer i of group g
     (:func:`layer_rows`); the group matrix is their column-wise concatenation — the reference's ``torch.cat(dim=1)`` +
     ``transpose(1, 2).reshape`` (cache:170-171, :13-14) — and is never materialised: the Gram pass and the projection pass
     read the layer tensors through per-layer tensor maps (xkv_factorize_groups).  `rank`: one rank for all, or one per group
     matrix — a group's K and V matrices (different ranks, hence different sketch widths) then share every launch of the
-    latency-bound stages (xkv_factorize_groups_mixed)."""
+    latency-bound stages (xkv_factorize_groups_mixed).  `gram_done`: an event the driver records on the current stream
+    right behind the (last) Gram launch — what a concurrent chain on another stream waits for when the chains' Gram launches
+    are staggered (compress.compress_groups)."""
     opts = opts or FactorizeOptions()
     if len(groups) == 0:
         return []
@@ -207,6 +213,9 @@ def factorize_groups(groups: Sequence[Sequence[torch.Tensor]], rank, opts: Optio
                 e.record()
             ev_arr = (C.c_void_p * 7)(*[e.cuda_event for e in events])
             all_events.append(events)
+        elif gram_done is not None and lo + chunk >= len(groups):
+            gram_done.record()   # materialises the handle; the driver records it again behind the Gram launch (stage mark 1)
+            ev_arr = (C.c_void_p * 7)(*[gram_done.cuda_event if i == _STAGGER_MARK else None for i in range(7)])
         flat = [t for grp in part for t in grp]
         _lib.check(lib.xkv_factorize_groups_mixed(
             ops._ptr_array(flat), nb, nl, lc, m, ld, (C.c_int32 * nb)(*rs), C.byref(co), ops._ptr_array(a),
