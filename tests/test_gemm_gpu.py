@@ -220,3 +220,62 @@ def test_gram_pair_kernel_matches_single_cta_tiles_bit_for_bit(n, K, layers, spl
     assert not torch.isnan(pair[mask]).any()
     assert torch.equal(pair[mask], single[mask])
     _check(pair, ref, exact=False, sym=True)
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,kw", [
+    (4096, 576, 1024, False, False, dict(terms="T3", transposed=True)),     # power step, roles swapped: N = 3 x 192
+    (2048, 832, 512, False, False, dict(terms="T6", transposed=True)),      # N = 4 x 208
+    (1024, 576, 576, True, False, dict(terms="T6", transposed=True)),       # triangular solve, roles swapped
+    (2304, 512, 1024, False, False, dict(out_bf16=True)),                   # projection form
+    (2100, 768, 640, False, False, dict(out_bf16=True, split_k=1)),         # ragged M, 3 N tiles
+    (512, 100, 256, False, False, dict()),                                  # N tile 112, mostly padding in the last 16
+    (768, 40, 192, True, False, dict(transposed=True, split_k=2)),          # N tile 48
+    (456, 256, 320, False, True, dict(terms="T3")),                         # MN-major B: 64-column chunks
+])
+def test_pair_kernels_match_single_cta_tiles(M, N, K, a_mn, b_mn, kw):
+    """Every product form the CTA-pair kernel takes over (cta_group::2, 256 x bn tiles, bn a multiple of 16) against torch
+    (exact on integer data) and bit for bit against the single-CTA tiles on Gaussian data."""
+    from xkv_b200 import _lib, ops
+
+    kw = dict(kw)
+    terms = {"T3": ops.TERMS_3, "T6": ops.TERMS_6, None: None}[kw.pop("terms", None)]
+    lib = _lib.load()
+    try:
+        lib.xkv_gemm_set_gram_pair(1)
+        got, ref = _run(M, N, K, a_mn, b_mn, ints=True, terms=terms, **kw)
+        _check(got, ref, exact=True, out_bf16=kw.get("out_bf16", False))
+        pair, _ = _run(M, N, K, a_mn, b_mn, terms=terms, **kw)
+        lib.xkv_gemm_set_gram_pair(0)
+        single, _ = _run(M, N, K, a_mn, b_mn, terms=terms, **kw)
+    finally:
+        lib.xkv_gemm_set_gram_pair(1)
+    assert torch.equal(pair, single)
+
+
+def test_pair_kernel_layered_projection_form():
+    """A = X V with X the column-wise concatenation of layer matrices read in place (K-major layered A, the k range
+    crosses layer boundaries), bf16 output: the pair kernel against the packed operand on single-CTA tiles."""
+    from xkv_b200 import _lib, ops
+
+    lib = _lib.load()
+    S, lc, nl, r = 1280, 256, 3, 192
+    layers = [_mk(S, lc, False, 40 + i) for i in range(nl)]
+    X = torch.cat(layers, dim=1).contiguous()
+    V = _mk(r, nl * lc, False, 50)
+    outs = []
+    try:
+        for pair, layered in ((1, True), (0, True), (0, False)):
+            lib.xkv_gemm_set_gram_pair(pair)
+            out = torch.full((S, r), float("nan"), device="cuda", dtype=torch.bfloat16)
+            if layered:
+                p = ops.make_problem([], [V], out, M=S, N=r, K=nl * lc, a_layers=layers)
+            else:
+                p = ops.make_problem([X], [V], out, M=S, N=r, K=nl * lc)
+            ops.gemm_grouped([p])
+            torch.cuda.synchronize()
+            outs.append(out)
+    finally:
+        lib.xkv_gemm_set_gram_pair(1)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    ref = (X.float() @ V.float().t())
+    assert (outs[0].float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()

@@ -181,6 +181,30 @@ static xkv_gemm_problem problem(const void* a0, const void* a1, const void* a2, 
   return p;
 }
 
+// D = A B^T (plain output) restated as D^T = B A^T stored transposed: the same memory, the same sequence of limb products
+// per k block, hence the same bits -- but the operand with the long dimension supplies M.  The products with M = sketch
+// width (576 / 832: 11 % / 8 % of padding in 128-row tiles, 33 % / 23 % in 256-row ones) and N = n = 4096 become
+// M = 4096, N = l, which the CTA-pair kernel tiles exactly (xkv_gemm.cu pair_bn).
+static xkv_gemm_problem swap_roles(const xkv_gemm_problem& p) {
+  xkv_gemm_problem q = p;
+  q.M = p.N;
+  q.N = p.M;
+  q.a_mn_major = p.b_mn_major;
+  q.b_mn_major = p.a_mn_major;
+  for (int i = 0; i < 3; ++i) {
+    q.A[i] = p.B[i];
+    q.B[i] = p.A[i];
+  }
+  q.lda = p.ldb;
+  q.ldb = p.lda;
+  for (int t = 0; t < 6; ++t) {
+    q.term_a[t] = p.term_b[t];
+    q.term_b[t] = p.term_a[t];
+  }
+  q.out_transposed = p.out_transposed ? 0 : 1;
+  return q;
+}
+
 static int run_gemms(std::vector<xkv_gemm_problem>& ps, void* stream, int per_launch = XKV_MAX_GEMM_PROBLEMS) {
   if (per_launch > XKV_MAX_GEMM_PROBLEMS) per_launch = XKV_MAX_GEMM_PROBLEMS;
   if (per_launch < 1) per_launch = 1;
@@ -468,9 +492,12 @@ static int factorize_impl(const void* const* X_host, int layers, int layer_cols,
           BatchRowsScope rows(l_rows);
           XKV_TRY(xkv_rdiag_update(P.rdiag, P.linv, B, lmax, lmax, stream));
         }
+        // Q = Linv Y, computed as Q^T = Y^T Linv^T with the result stored transposed (same memory, same order of products):
+        // the long dimension n becomes M, the sketch width l becomes N, which the CTA-pair GEMM tiles without padding
+        // (l = 576 as 3 x 192 columns, 832 as 4 x 208)
         for (int b = 0; b < B; ++b) {
-          xkv_gemm_problem p = problem(P.linv_l[b][0], P.linv_l[b][1], P.linv_l[b][2], lmax, 0, P.lh[b], P.lm[b], P.ll[b], nn,
-                                       1, cond ? cur[b] : nxt[b], nn, l[b], n, l[b], nt);
+          xkv_gemm_problem p = swap_roles(problem(P.linv_l[b][0], P.linv_l[b][1], P.linv_l[b][2], lmax, 0, P.lh[b], P.lm[b],
+                                                  P.ll[b], nn, 1, cond ? cur[b] : nxt[b], nn, l[b], n, l[b], nt));
           p.run_if = cond ? P.pass_flags + b : nullptr;
           ps.push_back(p);
         }
@@ -485,9 +512,9 @@ static int factorize_impl(const void* const* X_host, int layers, int layer_cols,
   };
   // cur <- (limbs lh/lm of the current basis) * G
   auto apply_gram = [&](int nterms) -> int {
-    for (int b = 0; b < B; ++b)
-      ps.push_back(problem(P.lh[b], P.lm[b], P.ll[b], nn, 0, P.g_limb[b][0], P.g_limb[b][1], P.g_limb[b][2], nn, 0,
-                           nxt[b], nn, l[b], n, n, nterms));
+    for (int b = 0; b < B; ++b)   // as (G Q^T)^T: see swap_roles
+      ps.push_back(swap_roles(problem(P.lh[b], P.lm[b], P.ll[b], nn, 0, P.g_limb[b][0], P.g_limb[b][1], P.g_limb[b][2], nn, 0,
+                                      nxt[b], nn, l[b], n, n, nterms)));
     XKV_TRY(run_gemms(ps, stream));
     swap_bufs();
     return 0;

@@ -47,6 +47,7 @@ struct alignas(64) GemmProb {
   int tiles_m, tiles_n, ntiles;
   int split_k, kblocks_per_split, nkb;
   int cta_begin;
+  int bn;              // N tile (256; the pair kernel: any multiple of 16 up to 256)
   int out_bf16, out_transposed, sym_upper;
   unsigned char ta[6], tb[6];
   const int* run_if;   // optional device predicate: the problem's CTAs exit at once when *run_if == 0
@@ -56,7 +57,7 @@ struct alignas(64) GemmProb {
 };
 struct GemmParams {
   int nprob;
-  int pair_stages;   // gram_pair_kernel: ring depth
+  int pair_stages;   // gemm_pair_kernel: ring depth
   GemmProb p[XKV_MAX_GEMM_PROBLEMS];
   CUtensorMap layer_maps[XKV_MAX_LAYER_MAPS];
 };
@@ -400,34 +401,38 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------
-// Gram in CTA pairs: G = X^T X (both operands MN-major tiles of X, fp32 output, symmetric tile set) with a 256 x 256
-// output tile per CTA PAIR (cta_group::2, the two SMs of a TPC).  CTA r of the pair streams the 128 columns
-// [m0 + 128 r, +128) of X as its rows of A and the 128 columns [n0 + 128 r, +128) as its HALF of B, the even CTA issues
-// one M = 256, N = 256 tcgen05.mma per K = 16 slice and each CTA receives its 128 rows x 256 columns of the tile in its
-// own tensor memory.  Why: the single-CTA 128 x 256 tile pulls 48 KiB from L2 per k block (96 B/clk per SM at the
-// MMA rate, and 12 KiB of shared-memory operand reads per MMA); the pair pulls 32 KiB per CTA (64 B/clk, 8 KiB per MMA)
-// for the same flops, which leaves room for 6 ring stages instead of 4.  Everything else is gemm_kernel<1, 1>: layered
-// operands read in place, split-K slabs, accumulation phases that alternate between two accumulators and are summed in
-// fp32 by the epilogue warps (of both CTAs, each on its own rows).
+// The same products in CTA PAIRS (cta_group::2, the two SMs of a TPC): a 256 x bn output tile per pair, bn <= 256.
+// CTA r of the pair streams ITS 128 rows of A and HALF of the tile's B rows (bn / 2), the even CTA issues one M = 256,
+// N = bn tcgen05.mma per K = 16 slice and each CTA receives its 128 rows x bn columns of the tile in its own tensor
+// memory.  Why: the single-CTA 128 x 256 tile pulls 48 KiB from L2 per k block (96 B/clk per SM at the MMA rate, and
+// 12 KiB of shared-memory operand reads per MMA); the pair pulls <= 32 KiB per CTA (64 B/clk, 8 KiB per MMA) for the same
+// flops -- on a power-capped part less operand traffic is a higher tensor clock -- and has room for 6 ring stages
+// instead of 4.  Measured on the Gram of the bench step (8 matrices 65536 x 4096, same box): 7.7 -> 6.25 ms.
+// A runtime tile width lets the products with a narrow N (the sketch width l = 576 / 832 as N = 3 x 192 / 4 x 208)
+// run without padding.  Used for launches whose M is large enough not to pay for the 256-row granularity (pair_bn):
+// the Gram, the projection A = X V, and -- with the operand roles swapped by the factorisation driver, output stored
+// transposed -- the power step G Q^T and the triangular solve.  MN-major B operands need bn = 256 (64-column chunks).
+// Everything else is gemm_kernel: limb terms, layered operands read in place, split-K slabs, accumulation phases.
 // Barriers: full[s] lives in the even CTA (both CTAs' loads complete on it); empty[s] and tmem_full[2] exist in each
 // CTA and are signalled by multicast commits; tmem_empty[2] lives in the even CTA and counts the epilogue warps of both.
 // ---------------------------------------------------------------------------------------------
 constexpr int PG_BM = 256;                              // pair tile rows (128 per CTA)
 constexpr int PG_STAGES = 6;                            // default ring depth (measured 5 / 6 / 7: see xkv_gemm_set_gram_pair)
 constexpr int PG_MAX_STAGES = 7;
-constexpr int PG_A_BYTES = 2 * CHUNK_BYTES;             // 128 A columns of this CTA
-constexpr int PG_B_BYTES = 2 * CHUNK_BYTES;             // this CTA's 128 of the tile's 256 B columns
+constexpr int PG_A_BYTES = BM * BK * 2;                 // this CTA's 128 rows of A
+constexpr int PG_B_BYTES = (BN / 2) * BK * 2;           // this CTA's half of the tile's B rows (bn / 2 <= 128)
 constexpr int PG_STAGE_BYTES = PG_A_BYTES + PG_B_BYTES; // 32 KiB
 constexpr size_t pg_smem_bytes(int stages) { return static_cast<size_t>(stages) * PG_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gram_pair_kernel(const __grid_constant__ GemmParams P) {
+template <int A_MN, int B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_pair_kernel(const __grid_constant__ GemmParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nstages = P.pair_stages;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + nstages * PG_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + PG_MAX_STAGES;
   uint64_t* tmem_full_bar = empty_bar + PG_MAX_STAGES;   // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -440,11 +445,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gram_pair_kernel(const __grid
   while (pi + 1 < P.nprob && static_cast<int>(blockIdx.x) >= P.p[pi + 1].cta_begin) ++pi;
   const GemmProb& pr = P.p[pi];
   if (pr.run_if != nullptr && *pr.run_if == 0) return;   // uniform over the pair, before any barrier / TMEM allocation
+  const int bn = pr.bn;
   const int local = (static_cast<int>(blockIdx.x) - pr.cta_begin) >> 1;
   const int split = local / pr.ntiles;
   int t = local - split * pr.ntiles;
   int tm = 0, tn = 0;
-  if (pr.sym_upper) {
+  if (pr.sym_upper) {   // bn = 256: square pair tiles
     for (int i = 0; i < pr.tiles_m; ++i) {
       const int cnt = pr.tiles_n - i;
       if (t < cnt) {
@@ -459,13 +465,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gram_pair_kernel(const __grid
     tn = t - tm * pr.tiles_n;
   }
   const int m0 = tm * PG_BM + crank * BM;   // this CTA's rows of the tile
-  const int n0 = tn * BN;                   // the tile's columns (all 256 land in this CTA's tensor memory)
-  const int nb0 = n0 + crank * (BN / 2);    // the B columns this CTA loads
+  const int n0 = tn * bn;                   // the tile's columns (all bn land in this CTA's tensor memory)
+  const int nb0 = n0 + crank * (bn >> 1);   // the B rows this CTA loads
+  const int n_end = min(pr.N, n0 + bn);
   const int kb0 = split * pr.kblocks_per_split;
   const int kb1 = min(kb0 + pr.kblocks_per_split, pr.nkb);
   const int nk = max(kb1 - kb0, 0);
+  const int niter = nk * pr.nterms;
   const int nph = max(1, min(pr.phases, nk));
   const uint32_t tmem_cols = nph > 1 ? 2 * TMEM_COLS : TMEM_COLS;
+  const uint32_t b_bytes = B_MN ? static_cast<uint32_t>(PG_B_BYTES) : static_cast<uint32_t>(bn >> 1) * (BK * 2);
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < nstages; ++i) {
@@ -477,7 +486,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gram_pair_kernel(const __grid
     mbar_init(&tmem_empty_bar[0], 8);   // one arrival per epilogue warp of BOTH CTAs
     mbar_init(&tmem_empty_bar[1], 8);
     mbar_fence_init();
-    tma_prefetch_desc(&pr.a_map[0]);
+    tma_prefetch_desc(&pr.a_map[pr.ta[0]]);
+    tma_prefetch_desc(&pr.b_map[pr.tb[0]]);
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, tmem_cols);
   tc_fence_before();
@@ -488,27 +498,74 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gram_pair_kernel(const __grid
 
   if (warp == 0) {
     // ===================== TMA producer (in each CTA; completions are counted on the even CTA's barrier) =====================
-    const CUtensorMap* chunk_map[4];   // A chunk 0, 1, B chunk 0, 1
-    int chunk_col[4];
+    // MN-major operands: two 64-column chunks per CTA, the layer matrix of a chunk is fixed for the whole kernel
+    const CUtensorMap* a_chunk_map[2];
+    const CUtensorMap* b_chunk_map[2];
+    int a_chunk_col[2], b_chunk_col[2];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int col = (c < 2 ? m0 : nb0) + 64 * (c & 1);
-      chunk_col[c] = col;
-      const int layers = c < 2 ? pr.a_layers : pr.b_layers;
-      chunk_map[c] = layers ? layer_map(P, c < 2 ? pr.a_layer_begin : pr.b_layer_begin, layers, pr.layer_cols, col, chunk_col[c])
-                            : (c < 2 ? &pr.a_map[0] : &pr.b_map[0]);
+    for (int c = 0; c < 2; ++c) {
+      a_chunk_col[c] = m0 + 64 * c;
+      a_chunk_map[c] = (A_MN && pr.a_layers) ? layer_map(P, pr.a_layer_begin, pr.a_layers, pr.layer_cols, m0 + 64 * c, a_chunk_col[c]) : nullptr;
+      b_chunk_col[c] = nb0 + 64 * c;
+      b_chunk_map[c] = (B_MN && pr.b_layers) ? layer_map(P, pr.b_layer_begin, pr.b_layers, pr.layer_cols, nb0 + 64 * c, b_chunk_col[c]) : nullptr;
+    }
+    // K-major layered operand: (layer, column inside the layer) of the current k block, advanced incrementally
+    int ka_layer = 0, ka_col = 0, kb_layer = 0, kb_col = 0;
+    if (!A_MN && pr.a_layers) {
+      ka_layer = (kb0 * BK) / pr.layer_cols;
+      ka_col = kb0 * BK - ka_layer * pr.layer_cols;
+    }
+    if (!B_MN && pr.b_layers) {
+      kb_layer = (kb0 * BK) / pr.layer_cols;
+      kb_col = kb0 * BK - kb_layer * pr.layer_cols;
     }
     if (elect_one()) {
-      int s = 0;
+      int s = 0, term = 0, kb = kb0;
       uint32_t ph = 0;
-      uint32_t full0 = cluster_map_shared(smem_u32(&full_bar[0]), 0);
-      for (int kb = kb0; kb < kb1; ++kb) {
-        uint8_t* st = smem + s * PG_STAGE_BYTES;
+      const uint32_t full0 = cluster_map_shared(smem_u32(&full_bar[0]), 0);
+      const uint32_t tx = 2u * (static_cast<uint32_t>(PG_A_BYTES) + b_bytes);
+      for (int it = 0; it < niter; ++it) {
+        const CUtensorMap* amap = &pr.a_map[pr.ta[term]];
+        const CUtensorMap* bmap = &pr.b_map[pr.tb[term]];
+        uint8_t* sA = smem + s * PG_STAGE_BYTES;
+        uint8_t* sB = sA + PG_A_BYTES;
         mbar_wait(&empty_bar[s], ph ^ 1u);
-        if (leader) mbar_expect_tx(&full_bar[s], 2 * PG_STAGE_BYTES);
+        if (leader) mbar_expect_tx(&full_bar[s], tx);
         const uint32_t fb = full0 + static_cast<uint32_t>(s * 8);
+        if (A_MN == 0) {
+          if (pr.a_layers)
+            tma_load_2d_pair(sA, &P.layer_maps[pr.a_layer_begin + min(ka_layer, pr.a_layers - 1)], fb,
+                             ka_layer < pr.a_layers ? ka_col : pr.layer_cols, m0);
+          else
+            tma_load_2d_pair(sA, amap, fb, kb * BK, m0);
+        } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tma_load_2d_pair(st + c * CHUNK_BYTES, chunk_map[c], fb, chunk_col[c], kb * BK);
+          for (int c = 0; c < 2; ++c)
+            tma_load_2d_pair(sA + c * CHUNK_BYTES, a_chunk_map[c] ? a_chunk_map[c] : amap, fb, a_chunk_col[c], kb * BK);
+        }
+        if (B_MN == 0) {
+          if (pr.b_layers)
+            tma_load_2d_pair(sB, &P.layer_maps[pr.b_layer_begin + min(kb_layer, pr.b_layers - 1)], fb,
+                             kb_layer < pr.b_layers ? kb_col : pr.layer_cols, nb0);
+          else
+            tma_load_2d_pair(sB, bmap, fb, kb * BK, nb0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            tma_load_2d_pair(sB + c * CHUNK_BYTES, b_chunk_map[c] ? b_chunk_map[c] : bmap, fb, b_chunk_col[c], kb * BK);
+        }
+        if (!A_MN && pr.a_layers && (ka_col += BK) >= pr.layer_cols) {
+          ka_col -= pr.layer_cols;
+          ++ka_layer;
+        }
+        if (!B_MN && pr.b_layers && (kb_col += BK) >= pr.layer_cols) {
+          kb_col -= pr.layer_cols;
+          ++kb_layer;
+        }
+        if (++term == pr.nterms) {
+          term = 0;
+          ++kb;
+        }
         if (++s == nstages) {
           s = 0;
           ph ^= 1u;
@@ -519,13 +576,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gram_pair_kernel(const __grid
   } else if (warp == 1) {
     // ===================== MMA issuer: one elected lane of the even CTA =====================
     if (leader) {
-      constexpr uint32_t idesc = umma_idesc_bf16(PG_BM, BN, 1, 1);
+      const uint32_t idesc = umma_idesc_bf16(PG_BM, 0, A_MN, B_MN) | (static_cast<uint32_t>(bn >> 3) << 17);
       constexpr uint64_t kStageStep = PG_STAGE_BYTES >> 4;
-      constexpr uint64_t kKStep = 2048 >> 4;   // MN-major: 16 K rows of 128 B
+      constexpr uint64_t kAStep = (A_MN ? 2048 : 32) >> 4, kBStep = (B_MN ? 2048 : 32) >> 4;
       if (elect_one()) {
         const uint32_t base = smem_u32(smem);
-        const uint64_t a_desc0 = umma_desc_sw128(base, CHUNK_BYTES, 1024);
-        const uint64_t b_desc0 = umma_desc_sw128(base + PG_A_BYTES, CHUNK_BYTES, 1024);
+        const uint64_t a_desc0 = A_MN ? umma_desc_sw128(base, CHUNK_BYTES, 1024) : umma_desc_sw128(base, 16, 1024);
+        const uint64_t b_desc0 = B_MN ? umma_desc_sw128(base + PG_A_BYTES, CHUNK_BYTES, 1024)
+                                      : umma_desc_sw128(base + PG_A_BYTES, 16, 1024);
         uint64_t a_desc = a_desc0, b_desc = b_desc0;
         int s = 0;
         uint32_t ph = 0;
@@ -536,15 +594,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gram_pair_kernel(const __grid
             mbar_wait_cluster(&tmem_empty_bar[phs & 1], static_cast<uint32_t>(((phs >> 1) - 1) & 1));
             tc_fence_after();
           }
-          const int it_end = (nph == 1) ? nk : static_cast<int>((static_cast<long long>(nk) * (phs + 1)) / nph);
+          const int it_end = (nph == 1) ? niter : static_cast<int>((static_cast<long long>(nk) * (phs + 1)) / nph) * pr.nterms;
           const int it_begin = it;
           for (; it < it_end; ++it) {
             mbar_wait_cluster(&full_bar[s], ph);
             tc_fence_after();
             umma_bf16_ss_pair(acc, a_desc, b_desc, idesc, it > it_begin ? 1u : 0u);
-            umma_bf16_ss_pair(acc, a_desc + kKStep, b_desc + kKStep, idesc, 1u);
-            umma_bf16_ss_pair(acc, a_desc + 2 * kKStep, b_desc + 2 * kKStep, idesc, 1u);
-            umma_bf16_ss_pair(acc, a_desc + 3 * kKStep, b_desc + 3 * kKStep, idesc, 1u);
+            umma_bf16_ss_pair(acc, a_desc + kAStep, b_desc + kBStep, idesc, 1u);
+            umma_bf16_ss_pair(acc, a_desc + 2 * kAStep, b_desc + 2 * kBStep, idesc, 1u);
+            umma_bf16_ss_pair(acc, a_desc + 3 * kAStep, b_desc + 3 * kBStep, idesc, 1u);
             umma_commit_pair(&empty_bar[s]);   // frees the stage in BOTH CTAs once these MMAs have read it
             a_desc += kStageStep;
             b_desc += kStageStep;
@@ -566,16 +624,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gram_pair_kernel(const __grid
     const int row = m0 + q * 32 + lane;
     const bool row_ok = row < pr.M;
     float* outf = reinterpret_cast<float*>(pr.D) + static_cast<long long>(split) * pr.split_stride;
-    const bool vec_ok = (pr.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(pr.D) & 15) == 0) && ((pr.split_stride % 4) == 0);
+    __nv_bfloat16* outh = reinterpret_cast<__nv_bfloat16*>(pr.D) + static_cast<long long>(split) * pr.split_stride;
+    const bool vec_ok = (pr.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(pr.D) & 15) == 0) && ((pr.split_stride % 8) == 0);
     const uint32_t tempty0 = cluster_map_shared(smem_u32(&tmem_empty_bar[0]), 0);
+    const int ncb = (bn + 31) >> 5;   // 32-column blocks of the tile (the last one may be half used: bn % 16 == 0)
 #pragma unroll 1
     for (int phs = 0; phs < nph; ++phs) {
-      // later phases add into what this same thread stored one phase ago; the partial sums are fetched one column block
-      // ahead (the first one before the accumulator is complete)
+      // later phases add into what this same thread stored one phase ago (phases > 1 implies plain fp32 output); the
+      // partial sums are fetched one column block ahead, the first one before the accumulator is complete
       float4 pre[8];
       auto prefetch = [&](int c) -> bool {
         const int col0 = n0 + c * 32;
-        if (!(phs > 0 && row_ok && vec_ok && c < BN / 32 && col0 + 32 <= pr.N)) return false;
+        if (!(phs > 0 && row_ok && vec_ok && c < ncb && col0 + 32 <= n_end)) return false;
         const float4* src = reinterpret_cast<const float4*>(outf + static_cast<long long>(row) * pr.ldd + col0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) pre[j] = src[j];
@@ -586,12 +646,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gram_pair_kernel(const __grid
       tc_fence_after();
       const uint32_t acc = tmem_base + static_cast<uint32_t>(phs & 1) * TMEM_COLS;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < ncb; ++c) {
         const int col0 = n0 + c * 32;
-        if (col0 >= pr.N) break;  // warp-uniform
+        if (col0 >= n_end) break;  // warp-uniform
         uint32_t v[32];
         __syncwarp();
-        if (nk > 0) {
+        if (niter > 0) {
           tmem_ld_32x32(acc + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c * 32), v);
           float4 cur[8];
           const bool have_cur = have_pre;
@@ -611,22 +671,57 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gram_pair_kernel(const __grid
             const float* src = outf + static_cast<long long>(row) * pr.ldd + col0;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (col0 + j < pr.N) v[j] = __float_as_uint(__uint_as_float(v[j]) + src[j]);
+              if (col0 + j < n_end) v[j] = __float_as_uint(__uint_as_float(v[j]) + src[j]);
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0u;
         }
-        if (row_ok) {
-          float* dst = outf + static_cast<long long>(row) * pr.ldd + col0;
-          if (col0 + 32 <= pr.N && vec_ok) {
+        const bool full = (col0 + 32 <= n_end);
+        if (!pr.out_transposed) {
+          if (!row_ok) {
+            // rows past M (zero-filled by TMA): nothing to store
+          } else if (!pr.out_bf16) {
+            float* dst = outf + static_cast<long long>(row) * pr.ldd + col0;
+            if (full && vec_ok) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              reinterpret_cast<uint4*>(dst)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              for (int j = 0; j < 8; ++j)
+                reinterpret_cast<uint4*>(dst)[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < n_end) dst[j] = __uint_as_float(v[j]);
+            }
+          } else {
+            __nv_bfloat16* dst = outh + static_cast<long long>(row) * pr.ldd + col0;
+            if (full && vec_ok) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 w;
+                w.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                w.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                w.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                w.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+                reinterpret_cast<uint4*>(dst)[j] = w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < n_end) dst[j] = __float2bfloat16_rn(__uint_as_float(v[j]));
+            }
+          }
+        } else {
+          // transposed store: for a fixed column the warp's 32 rows are contiguous in memory
+          if (!pr.out_bf16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (row_ok && col0 + j < n_end)
+                outf[static_cast<long long>(col0 + j) * pr.ldd + row] = __uint_as_float(v[j]);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (col0 + j < pr.N) dst[j] = __uint_as_float(v[j]);
+              if (row_ok && col0 + j < n_end)
+                outh[static_cast<long long>(col0 + j) * pr.ldd + row] = __float2bfloat16_rn(__uint_as_float(v[j]));
           }
         }
       }
@@ -653,20 +748,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gram_pair_kernel(const __grid
 // ---------------------------------------------------------------------------------------------
 static int g_gram_pair = 1;   // xkv_gemm_set_gram_pair: 0 off, 1 default ring depth, 3 .. 7 that many stages
 
-// the launch is a Gram in the pair kernel's form: every problem G = X^T X on MN-major operands, symmetric tile set,
-// one term, plain fp32 output
-static bool pair_form(const xkv_gemm_problem* ps, int n) {
-  if (!g_gram_pair) return false;
-  for (int i = 0; i < n; ++i) {
-    const xkv_gemm_problem& p = ps[i];
-    if (!(p.a_mn_major && p.b_mn_major && p.sym_upper && p.num_terms == 1 && !p.out_bf16 && !p.out_transposed && p.M == p.N))
-      return false;
-  }
-  return true;
+// N tile of the problem in the pair kernel, 0 = the problem stays on single-CTA tiles.  Pairs are used where the 256-row
+// tile granularity costs nothing (M large, a multiple of 256, or its last 256 rows more than half used) and the operand
+// layouts allow it: the symmetric tile set only in the Gram form (square 256 x 256 tiles), an MN-major B in 64-column
+// chunks (bn = 256), a K-major B at any multiple of 16: N is cut into the fewest tiles of at most 256 columns, equally wide.
+static int pair_bn(const xkv_gemm_problem& p) {
+  if (!g_gram_pair) return 0;
+  const int rem = p.M % PG_BM;
+  if (!(p.M >= 2048 || rem == 0 || rem > BM)) return 0;
+  if (p.sym_upper) return (p.a_mn_major && p.b_mn_major && p.M == p.N) ? BN : 0;
+  if (p.b_mn_major) return BN;
+  const int ntn = (p.N + BN - 1) / BN;
+  const int w = (p.N + ntn - 1) / ntn;
+  return (w + 15) & ~15;
 }
 
 static int build_problem(const xkv_gemm_problem& in, GemmProb& out, int& cta_cursor, GemmParams& params, int& map_cursor,
-                         bool pair = false) {
+                         int pair_n = 0) {
+  const bool pair = pair_n > 0;
+  const int bn = pair ? pair_n : BN;   // N tile; the pair kernel loads bn / 2 B rows per CTA
   XKV_REQUIRE(in.M > 0 && in.N > 0 && in.K > 0, "gemm: empty problem M=%d N=%d K=%d", in.M, in.N, in.K);
   XKV_REQUIRE(in.num_terms >= 1 && in.num_terms <= 6, "gemm: num_terms=%d out of range", in.num_terms);
   XKV_REQUIRE(in.lda % 8 == 0 && in.ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements");
@@ -706,7 +806,8 @@ static int build_problem(const xkv_gemm_problem& in, GemmProb& out, int& cta_cur
       XKV_REQUIRE(map_cursor < XKV_MAX_LAYER_MAPS, "gemm: more than %d layer matrices in one launch", XKV_MAX_LAYER_MAPS);
       int rc;
       if (!mn)   // K-major: rows = M (or N) index, the layer supplies layer_cols of the K columns
-        rc = encode_tmap_2d_bf16(&params.layer_maps[map_cursor++], ptrs[i], in.layer_cols, other, ld, BK, side == 0 ? BM : BN);
+        rc = encode_tmap_2d_bf16(&params.layer_maps[map_cursor++], ptrs[i], in.layer_cols, other, ld, BK,
+                                 side == 0 ? BM : (pair ? bn / 2 : BN));
       else       // MN-major: rows = K index, the layer supplies layer_cols of the M (or N) columns
         rc = encode_tmap_2d_bf16(&params.layer_maps[map_cursor++], ptrs[i], in.layer_cols, in.K, ld, 64, BK);
       if (rc) return rc;
@@ -735,7 +836,7 @@ static int build_problem(const xkv_gemm_problem& in, GemmProb& out, int& cta_cur
     if (in.b_layers > 0)
       out.b_map[i] = params.layer_maps[out.b_layer_begin];
     else if (!in.b_mn_major)
-      rc = encode_tmap_2d_bf16(&out.b_map[i], b, in.K, in.N, in.ldb, BK, BN);
+      rc = encode_tmap_2d_bf16(&out.b_map[i], b, in.K, in.N, in.ldb, BK, pair ? bn / 2 : BN);
     else
       rc = encode_tmap_2d_bf16(&out.b_map[i], b, in.N, in.K, in.ldb, 64, BK);
     if (rc) return rc;
@@ -747,13 +848,14 @@ static int build_problem(const xkv_gemm_problem& in, GemmProb& out, int& cta_cur
   out.N = in.N;
   out.K = in.K;
   out.nterms = in.num_terms;
-  const int bm = pair ? PG_BM : BM;   // the pair kernel's tile is 256 x 256, two CTAs
+  const int bm = pair ? PG_BM : BM;   // the pair kernel's tile is 256 x bn, two CTAs
+  out.bn = bn;
   out.tiles_m = (in.M + bm - 1) / bm;
-  out.tiles_n = (in.N + BN - 1) / BN;
+  out.tiles_n = (in.N + bn - 1) / bn;
   out.sym_upper = in.sym_upper ? 1 : 0;
   if (out.sym_upper) {
     int cnt = 0;
-    for (int i = 0; i < out.tiles_m; ++i) cnt += out.tiles_n - (i * bm) / BN;
+    for (int i = 0; i < out.tiles_m; ++i) cnt += out.tiles_n - (i * bm) / bn;
     out.ntiles = cnt;
   } else {
     out.ntiles = out.tiles_m * out.tiles_n;
@@ -777,10 +879,12 @@ bool& gemm_low_priority() {
   return low;
 }
 
-static int launch_gram_pair(GemmParams& params, int grid, cudaStream_t stream) {
-  static PerDevice<bool> configured;
+template <int A_MN, int B_MN>
+static int launch_pair_variant(GemmParams& params, int grid, cudaStream_t stream) {
+  auto kern = gemm_pair_kernel<A_MN, B_MN>;
+  static PerDevice<bool> configured;  // per instantiation and device
   if (!configured()) {
-    XKV_CHECK_CUDA(cudaFuncSetAttribute(gram_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    XKV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(pg_smem_bytes(PG_MAX_STAGES))));
     configured() = true;
   }
@@ -803,7 +907,7 @@ static int launch_gram_pair(GemmParams& params, int grid, cudaStream_t stream) {
     cfg.numAttrs = 2;
   }
   cfg.attrs = attr;
-  XKV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gram_pair_kernel, params));
+  XKV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, params));
   XKV_LAUNCHED();
   return 0;
 }
@@ -851,15 +955,21 @@ extern "C" int xkv_gemm_grouped(const xkv_gemm_problem* problems, int num_proble
   static thread_local GemmParams params;  // ~22 KiB, keep it off the stack
   params.nprob = num_problems;
   int cursor = 0, map_cursor = 0;
-  const bool pair = pair_form(problems, num_problems);
+  bool pair = true;   // one kernel per launch: pairs only when every problem qualifies
+  for (int i = 0; i < num_problems; ++i) pair = pair && pair_bn(problems[i]) > 0;
   for (int i = 0; i < num_problems; ++i) {
     XKV_REQUIRE((problems[i].a_mn_major ? 1 : 0) == a_mn && (problems[i].b_mn_major ? 1 : 0) == b_mn,
                 "gemm: all problems of one launch must share operand majors");
-    int rc = build_problem(problems[i], params.p[i], cursor, params, map_cursor, pair);
+    int rc = build_problem(problems[i], params.p[i], cursor, params, map_cursor, pair ? pair_bn(problems[i]) : 0);
     if (rc) return rc;
   }
   cudaStream_t st = as_stream(stream);
-  if (pair) return launch_gram_pair(params, cursor, st);
+  if (pair) {
+    if (!a_mn && !b_mn) return launch_pair_variant<0, 0>(params, cursor, st);
+    if (!a_mn && b_mn) return launch_pair_variant<0, 1>(params, cursor, st);
+    if (a_mn && !b_mn) return launch_pair_variant<1, 0>(params, cursor, st);
+    return launch_pair_variant<1, 1>(params, cursor, st);
+  }
   if (!a_mn && !b_mn) return launch_variant<0, 0>(params, cursor, st);
   if (!a_mn && b_mn) return launch_variant<0, 1>(params, cursor, st);
   if (a_mn && !b_mn) return launch_variant<1, 0>(params, cursor, st);
