@@ -17,10 +17,13 @@ print(json.dumps({"priority_range": [lo, hi]}), flush=True)
 VH = [-1, -1, -1, -1, -3, -3, -3, -3]
 RR = [-1, -2, -3]
 schemes = {
-    "no stagger": dict(stagger=False),
-    "stagger at Gram": dict(stagger=True),
-    "stagger at reduce+split": dict(stagger=True, mark=2),
-    "stagger at range finder": dict(stagger=True, mark=3),
+    "8 streams (default)": dict(num_streams=8),
+    "6 streams": dict(num_streams=6),
+    "12 streams": dict(num_streams=12),
+    "16 streams": dict(num_streams=16),
+    "8 streams, V -3 K -2": dict(num_streams=8, priorities=[-2, -2, -2, -2, -3, -3, -3, -3]),
+    "8 streams, V -2 K -1": dict(num_streams=8, priorities=[-1, -1, -1, -1, -2, -2, -2, -2]),
+    "16 streams, V -3 K -2": dict(num_streams=16, priorities=[-2] * 8 + [-3] * 8),
 }
 graphs = {}
 runs = {}
@@ -28,7 +31,7 @@ for name, pr in schemes.items():
     def run(pr=pr):
         pr = dict(pr)
         factorize._STAGGER_MARK = pr.pop("mark", 1)
-        return compress.compress_groups(keys, vals, c["rank_k"], c["rank_v"], num_streams=8, **pr)
+        return compress.compress_groups(keys, vals, c["rank_k"], c["rank_v"], **pr)
     runs[name] = run
     run()
     torch.cuda.synchronize()
@@ -50,15 +53,3 @@ for rnd in range(2):
         print(json.dumps({"round": rnd, "scheme": name, "ms_per_step": round(e0.elapsed_time(e1) / 10, 3)}),
               flush=True)
 
-    for name, run in runs.items():
-        for _ in range(2):
-            run()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10):
-            run()
-        e1.record()
-        torch.cuda.synchronize()
-        print(json.dumps({"round": rnd, "scheme": name, "mode": "host-enqueued", "ms_per_step": round(e0.elapsed_time(e1) / 10, 3)}),
-              flush=True)
