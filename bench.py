@@ -379,7 +379,7 @@ def gram_roofline(ctx, c, keys, ms_step):
     ranks = c["rank_k"] + (c["rank_v"] or 0)
     alg_pipeline = 4.0 * S * sum(g * c["heads"] * c["head_dim"] for g in group_sizes(c)) * ranks
     return {
-        "kernel": "gemm_kernel<1,1> (Gram X^T X, symmetric tiles, tcgen05 M128 N256 K16)",
+        "kernel": "gemm_pair_kernel<1,1> (Gram X^T X, symmetric 256 x 256 tiles per CTA pair, tcgen05 cta_group::2 M256 N256 K16)",
         "bound": "tensor", "achieved": achieved, "peak": ctx.peak_tf, "unit": "TFLOP/s", "frac": achieved / ctx.peak_tf,
         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if ctx.peaks else "fallback 1.4 PFLOP/s",
         "traffic": traffic, "launch_ms": gram_ms, "matrices_per_launch": nb,
