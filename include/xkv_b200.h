@@ -169,6 +169,9 @@ XKV_API int xkv_cholesky_inverse(float* const* S_host, float* const* Linv_host, 
 XKV_API int xkv_cholesky_inverse_limbs(float* const* S_host, float* const* Linv_host, void* const* hi_host,
                                        void* const* mid_host, void* const* lo_host, int batch, int l, int64_t ld,
                                        int64_t ld_limb, float shift, float pivot_floor, void* stream);
+/* tuning hook: cap on the thread-block cluster size per matrix of the Cholesky launch (0 = automatic: 8 CTAs from 6 block
+ * columns up, 16 from 20 up where the device can keep them resident).  Fewer CTAs per matrix hold fewer SMs for longer. */
+XKV_API void xkv_cholesky_set_cluster_cap(int cap);
 /* Shared-memory two-sided Jacobi eigen-solver for the Rayleigh-Ritz windows: `count` symmetric W x W
  * fp32 matrices (W even, <= 160), one CTA each. evals: eigenvalues sorted descending; Wt (optional):
  * eigenvectors as rows, same order. */
@@ -224,6 +227,10 @@ typedef struct xkv_factorize_options {
   float second_pass_min_pivot; /* a single-pass step runs a second pass ON DEVICE DECISION for every matrix whose first
                                 * pass met a Cholesky pivot below this (ill-conditioned: steep spectrum at high rank);
                                 * 0 = never (default 0.05) */
+  int32_t solve_terms;      /* bf16-limb terms (3 or 6) of the triangular solve Q = L^-1 Y in every CholeskyQR pass whose result a
+                             * later pass or power step orthonormalises again (range finder, all power steps but the last); the
+                             * last power step always uses 6.  Unlike the Gram of the basis (pass0_terms) the solve cannot break
+                             * down: 3 terms (default) leave the intermediate bases orthonormal to ~1e-5 instead of ~1e-7 */
   uint64_t seed;
 } xkv_factorize_options;
 XKV_API void xkv_factorize_default_options(xkv_factorize_options* opts);

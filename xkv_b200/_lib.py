@@ -88,6 +88,7 @@ class FactorizeOptions(C.Structure):
         ("heavy_redo", C.c_int32),
         ("power_terms", C.c_int32),
         ("second_pass_min_pivot", C.c_float),
+        ("solve_terms", C.c_int32),
         ("seed", C.c_uint64),
     ]
 
@@ -120,6 +121,7 @@ SIGNATURES = {
     "xkv_set_launch_predicate": (None, [_vp]),
     "xkv_cholesky_inverse": (_i, [_pp, _pp, _i, _i, _i64, _f, _f, _vp]),
     "xkv_cholesky_inverse_limbs": (_i, [_pp, _pp, _pp, _pp, _pp, _i, _i, _i64, _i64, _f, _f, _vp]),
+    "xkv_cholesky_set_cluster_cap": (None, [_i]),
     "xkv_jacobi_eigh": (_i, [_pp, _pp, _pp, _i, _i, _i64, _i64, _i, _vp]),
     "xkv_convert_bf16": (_i, [_vp, _i, _i, _i64, _vp, _i64, _vp, _i64, _vp]),
     "xkv_sqrt_clamp": (_i, [_vp, _vp, _i, _vp]),

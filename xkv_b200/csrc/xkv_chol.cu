@@ -450,6 +450,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chol_cluster_kernel(const __gri
 
 using namespace xkv;
 
+static int g_chol_cluster_cap = 0;   // xkv_cholesky_set_cluster_cap
+extern "C" void xkv_cholesky_set_cluster_cap(int cap) { g_chol_cluster_cap = cap; }
+
 extern "C" int xkv_cholesky_inverse_limbs(float* const* S_host, float* const* Linv_host, void* const* hi_host,
                                           void* const* mid_host, void* const* lo_host, int batch, int l, int64_t ld,
                                           int64_t ld_limb, float shift, float pivot_floor, void* stream) {
@@ -491,6 +494,7 @@ extern "C" int xkv_cholesky_inverse_limbs(float* const* S_host, float* const* Li
     attr_set() = true;
   }
   int CL = p.nblk >= 6 ? 8 : (p.nblk >= 3 ? 4 : (p.nblk == 2 ? 2 : 1));
+  if (g_chol_cluster_cap > 0 && CL > g_chol_cluster_cap) CL = g_chol_cluster_cap;
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.blockDim = dim3(CH_THREADS, 1, 1);
@@ -517,7 +521,7 @@ extern "C" int xkv_cholesky_inverse_limbs(float* const* S_host, float* const* Li
     (void)cudaGetLastError();
     cl16_probe = 1 + cl16_clusters;
   }
-  if (p.nblk >= 20 && cl16_probe - 1 >= batch) CL = 16;
+  if (p.nblk >= 20 && cl16_probe - 1 >= batch && g_chol_cluster_cap == 0) CL = 16;
   cfg.gridDim = dim3(CL, batch, 1);
   attr[0].val.clusterDim.x = CL;
   XKV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, chol_cluster_kernel, p));

@@ -243,6 +243,7 @@ extern "C" void xkv_factorize_default_options(xkv_factorize_options* o) {
   o->pass0_terms = 6;
   o->power_terms = 3;
   o->heavy_redo = 1;
+  o->solve_terms = 3;
   o->oversample = 64;
   o->first_passes = 2;
   o->passes = 2;
@@ -426,7 +427,8 @@ static int factorize_impl(const void* const* X_host, int layers, int layer_cols,
   // Cholesky pivots) whether one more pass runs; its kernels are always enqueued and exit at once for the matrices
   // that do not need it.  That pass writes its result over `cur` (its operands are the limb copies), so the
   // buffers are where the following stages expect them either way.
-  auto cholqr = [&](int npass, bool shifted, bool track, int p0, bool conditional_extra) -> int {
+  // `final_call`: nothing orthonormalises the result again (the last power step): the solve keeps all 6 limb terms
+  auto cholqr = [&](int npass, bool shifted, bool track, int p0, bool conditional_extra, bool final_call) -> int {
     const int total = npass + (conditional_extra ? 1 : 0);
     for (int ip = 0; ip < total; ++ip) {
       const int pp = ip + p0;  // index into the per-pass parameters (shift, limb terms)
@@ -497,7 +499,8 @@ static int factorize_impl(const void* const* X_host, int layers, int layer_cols,
         // (l = 576 as 3 x 192 columns, 832 as 4 x 208)
         for (int b = 0; b < B; ++b) {
           xkv_gemm_problem p = swap_roles(problem(P.linv_l[b][0], P.linv_l[b][1], P.linv_l[b][2], lmax, 0, P.lh[b], P.lm[b],
-                                                  P.ll[b], nn, 1, cond ? cur[b] : nxt[b], nn, l[b], n, l[b], nt));
+                                                  P.ll[b], nn, 1, cond ? cur[b] : nxt[b], nn, l[b], n, l[b],
+                                                  (o.solve_terms == 3 && !final_call) ? 3 : nt));
           p.run_if = cond ? P.pass_flags + b : nullptr;
           ps.push_back(p);
         }
@@ -523,7 +526,7 @@ static int factorize_impl(const void* const* X_host, int layers, int layer_cols,
   // ---- 2-3. Gaussian range finder ----
   for (int b = 0; b < B; ++b) XKV_TRY(xkv_fill_gaussian_bf16(P.lh[b], l[b], n, nn, o.seed + 7919ull * b, stream));
   XKV_TRY(apply_gram(1));
-  XKV_TRY(cholqr(o.first_passes, false, false, 0, false));
+  XKV_TRY(cholqr(o.first_passes, false, false, 0, false, o.power_iters == 0));
   XKV_TRY(mark());  // 3: range finder
 
   // ---- 4. power steps ----
@@ -553,7 +556,7 @@ static int factorize_impl(const void* const* X_host, int layers, int layer_cols,
     const bool last = it == o.power_iters - 1;
     const bool single = o.single_pass_from > 0 && it >= o.single_pass_from && !(last && o.final_passes > 1 && o.single_pass_last == 0);
     XKV_TRY(cholqr(single ? 1 : (last ? o.final_passes : o.passes), shifted, use_shift && it + 1 < o.power_iters,
-                   single ? 1 : 0, single && o.second_pass_min_pivot > 0.f));
+                   single ? 1 : 0, single && o.second_pass_min_pivot > 0.f, last));
   }
   XKV_TRY(mark());  // 4: power iterations
 

@@ -68,6 +68,8 @@ class FactorizeOptions:
     power_terms: int = 3            # limb terms of the power-step product Y = Q G
     second_pass_min_pivot: float = 0.05   # single-pass steps: the DEVICE adds a second pass for every matrix whose first
                                           # pass met a Cholesky pivot below this (steep spectrum at high rank); 0 = never
+    solve_terms: int = 3            # limb terms of Q = L^-1 Y in the passes a later pass / step re-orthonormalises (the last power
+                                    # step always uses 6); 3 vs 6: same full-size error to 4e-5, step -0.1 .. -0.8 ms
     seed: int = 1234
     profile: bool = False
 
@@ -118,6 +120,7 @@ def _c_options(opts: FactorizeOptions) -> "_lib.FactorizeOptions":
     o.pass0_terms = int(opts.pass0_terms)
     o.power_terms = int(opts.power_terms)
     o.heavy_redo = int(opts.heavy_redo)
+    o.solve_terms = int(opts.solve_terms)
     o.seed = opts.seed
     return o
 
