@@ -572,8 +572,9 @@ static int factorize_impl(const void* const* X_host, int layers, int layer_cols,
     }
     for (int b = 0; b < B; ++b)
       for (int w = 0; w < nw; ++w)
-        ps.push_back(problem(row_bf16(P.lh[b], w0(b, w), nn), row_bf16(P.lm[b], w0(b, w), nn), row_bf16(P.ll[b], w0(b, w), nn),
-                             nn, 0, P.g_limb[b][0], P.g_limb[b][1], P.g_limb[b][2], nn, 0, P.yw[b][w], nn, W, n, n, 6));
+        ps.push_back(swap_roles(problem(row_bf16(P.lh[b], w0(b, w), nn), row_bf16(P.lm[b], w0(b, w), nn),
+                                        row_bf16(P.ll[b], w0(b, w), nn), nn, 0, P.g_limb[b][0], P.g_limb[b][1], P.g_limb[b][2],
+                                        nn, 0, P.yw[b][w], nn, W, n, n, 6)));   // as (G Qw^T)^T: M = n in CTA pairs, N = W
     XKV_TRY(run_gemms(ps, stream));
     {
       // all windows' limbs in launches of up to XKV_MAX_BATCH matrices

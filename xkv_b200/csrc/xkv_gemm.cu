@@ -48,6 +48,12 @@ struct alignas(64) GemmProb {
   int split_k, kblocks_per_split, nkb;
   int cta_begin;
   int bn;              // N tile (256; the pair kernel: any multiple of 16 up to 256)
+  // pair kernel, limb terms: a ring stage holds every DISTINCT limb tile of a k block once (A slots, then B slots, 16 KiB
+  // each) and all the terms' MMAs read from it -- 3 terms load 2 + 2 tiles instead of 3 + 3, 6 terms 3 + 3 instead of 6 + 6
+  int na, nb;                        // distinct A / B limbs
+  unsigned char la[3], lb[3];        // slot -> limb
+  unsigned char sa[3], sb[3];        // limb -> slot
+  int pstages;                       // ring depth of this problem: ring bytes / ((na + nb) * 16 KiB)
   int out_bf16, out_transposed, sym_upper;
   unsigned char ta[6], tb[6];
   const int* run_if;   // optional device predicate: the problem's CTAs exit at once when *run_if == 0
@@ -428,8 +434,7 @@ template <int A_MN, int B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_pair_kernel(const __grid_constant__ GemmParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int nstages = P.pair_stages;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + nstages * PG_STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P.pair_stages * PG_STAGE_BYTES);   // behind the launch's ring
   uint64_t* empty_bar = full_bar + PG_MAX_STAGES;
   uint64_t* tmem_full_bar = empty_bar + PG_MAX_STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2]
@@ -446,6 +451,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_pair_kernel(const __grid
   const GemmProb& pr = P.p[pi];
   if (pr.run_if != nullptr && *pr.run_if == 0) return;   // uniform over the pair, before any barrier / TMEM allocation
   const int bn = pr.bn;
+  const int nstages = pr.pstages;
+  const int na = pr.na;
+  const uint32_t stage_bytes = static_cast<uint32_t>(pr.na + pr.nb) * PG_A_BYTES;
   const int local = (static_cast<int>(blockIdx.x) - pr.cta_begin) >> 1;
   const int split = local / pr.ntiles;
   int t = local - split * pr.ntiles;
@@ -520,40 +528,47 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_pair_kernel(const __grid
       kb_col = kb0 * BK - kb_layer * pr.layer_cols;
     }
     if (elect_one()) {
-      int s = 0, term = 0, kb = kb0;
+      int s = 0;
       uint32_t ph = 0;
       const uint32_t full0 = cluster_map_shared(smem_u32(&full_bar[0]), 0);
-      const uint32_t tx = 2u * (static_cast<uint32_t>(PG_A_BYTES) + b_bytes);
-      for (int it = 0; it < niter; ++it) {
-        const CUtensorMap* amap = &pr.a_map[pr.ta[term]];
-        const CUtensorMap* bmap = &pr.b_map[pr.tb[term]];
-        uint8_t* sA = smem + s * PG_STAGE_BYTES;
-        uint8_t* sB = sA + PG_A_BYTES;
+      const uint32_t tx = 2u * (static_cast<uint32_t>(pr.na) * PG_A_BYTES + static_cast<uint32_t>(pr.nb) * b_bytes);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        uint8_t* sA = smem + s * stage_bytes;
+        uint8_t* sB = sA + na * PG_A_BYTES;
         mbar_wait(&empty_bar[s], ph ^ 1u);
         if (leader) mbar_expect_tx(&full_bar[s], tx);
         const uint32_t fb = full0 + static_cast<uint32_t>(s * 8);
-        if (A_MN == 0) {
-          if (pr.a_layers)
-            tma_load_2d_pair(sA, &P.layer_maps[pr.a_layer_begin + min(ka_layer, pr.a_layers - 1)], fb,
-                             ka_layer < pr.a_layers ? ka_col : pr.layer_cols, m0);
-          else
-            tma_load_2d_pair(sA, amap, fb, kb * BK, m0);
-        } else {
+        for (int i = 0; i < pr.na; ++i) {   // every distinct A limb of this k block, once
+          const CUtensorMap* amap = &pr.a_map[pr.la[i]];
+          uint8_t* dst = sA + i * PG_A_BYTES;
+          if (A_MN == 0) {
+            if (pr.a_layers)
+              tma_load_2d_pair(dst, &P.layer_maps[pr.a_layer_begin + min(ka_layer, pr.a_layers - 1)], fb,
+                               ka_layer < pr.a_layers ? ka_col : pr.layer_cols, m0);
+            else
+              tma_load_2d_pair(dst, amap, fb, kb * BK, m0);
+          } else {
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
-            tma_load_2d_pair(sA + c * CHUNK_BYTES, a_chunk_map[c] ? a_chunk_map[c] : amap, fb, a_chunk_col[c], kb * BK);
+            for (int c = 0; c < 2; ++c)
+              tma_load_2d_pair(dst + c * CHUNK_BYTES, a_chunk_map[c] ? a_chunk_map[c] : amap, fb, a_chunk_col[c], kb * BK);
+          }
         }
-        if (B_MN == 0) {
-          if (pr.b_layers)
-            tma_load_2d_pair(sB, &P.layer_maps[pr.b_layer_begin + min(kb_layer, pr.b_layers - 1)], fb,
-                             kb_layer < pr.b_layers ? kb_col : pr.layer_cols, nb0);
-          else
-            tma_load_2d_pair(sB, bmap, fb, kb * BK, nb0);
-        } else {
+        for (int i = 0; i < pr.nb; ++i) {
+          const CUtensorMap* bmap = &pr.b_map[pr.lb[i]];
+          uint8_t* dst = sB + i * PG_B_BYTES;
+          if (B_MN == 0) {
+            if (pr.b_layers)
+              tma_load_2d_pair(dst, &P.layer_maps[pr.b_layer_begin + min(kb_layer, pr.b_layers - 1)], fb,
+                               kb_layer < pr.b_layers ? kb_col : pr.layer_cols, nb0);
+            else
+              tma_load_2d_pair(dst, bmap, fb, kb * BK, nb0);
+          } else {
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
-            tma_load_2d_pair(sB + c * CHUNK_BYTES, b_chunk_map[c] ? b_chunk_map[c] : bmap, fb, b_chunk_col[c], kb * BK);
+            for (int c = 0; c < 2; ++c)
+              tma_load_2d_pair(dst + c * CHUNK_BYTES, b_chunk_map[c] ? b_chunk_map[c] : bmap, fb, b_chunk_col[c], kb * BK);
+          }
         }
+        // layered operands take one term: one tile per k block
         if (!A_MN && pr.a_layers && (ka_col += BK) >= pr.layer_cols) {
           ka_col -= pr.layer_cols;
           ++ka_layer;
@@ -561,10 +576,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_pair_kernel(const __grid
         if (!B_MN && pr.b_layers && (kb_col += BK) >= pr.layer_cols) {
           kb_col -= pr.layer_cols;
           ++kb_layer;
-        }
-        if (++term == pr.nterms) {
-          term = 0;
-          ++kb;
         }
         if (++s == nstages) {
           s = 0;
@@ -577,32 +588,37 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_pair_kernel(const __grid
     // ===================== MMA issuer: one elected lane of the even CTA =====================
     if (leader) {
       const uint32_t idesc = umma_idesc_bf16(PG_BM, 0, A_MN, B_MN) | (static_cast<uint32_t>(bn >> 3) << 17);
-      constexpr uint64_t kStageStep = PG_STAGE_BYTES >> 4;
       constexpr uint64_t kAStep = (A_MN ? 2048 : 32) >> 4, kBStep = (B_MN ? 2048 : 32) >> 4;
+      constexpr uint64_t kSlot = PG_A_BYTES >> 4;   // one limb slot (A and B slots are the same size)
       if (elect_one()) {
+        const uint64_t kStageStep = stage_bytes >> 4;
         const uint32_t base = smem_u32(smem);
         const uint64_t a_desc0 = A_MN ? umma_desc_sw128(base, CHUNK_BYTES, 1024) : umma_desc_sw128(base, 16, 1024);
-        const uint64_t b_desc0 = B_MN ? umma_desc_sw128(base + PG_A_BYTES, CHUNK_BYTES, 1024)
-                                      : umma_desc_sw128(base + PG_A_BYTES, 16, 1024);
+        const uint64_t b_desc0 = B_MN ? umma_desc_sw128(base + na * PG_A_BYTES, CHUNK_BYTES, 1024)
+                                      : umma_desc_sw128(base + na * PG_A_BYTES, 16, 1024);
         uint64_t a_desc = a_desc0, b_desc = b_desc0;
         int s = 0;
         uint32_t ph = 0;
-        int it = 0;
+        int kb = 0;   // k blocks done
         for (int phs = 0; phs < nph; ++phs) {
           const uint32_t acc = tmem_base + static_cast<uint32_t>(phs & 1) * TMEM_COLS;
           if (phs >= 2) {   // the epilogues of both CTAs must have drained this accumulator (phase phs - 2)
             mbar_wait_cluster(&tmem_empty_bar[phs & 1], static_cast<uint32_t>(((phs >> 1) - 1) & 1));
             tc_fence_after();
           }
-          const int it_end = (nph == 1) ? niter : static_cast<int>((static_cast<long long>(nk) * (phs + 1)) / nph) * pr.nterms;
-          const int it_begin = it;
-          for (; it < it_end; ++it) {
+          const int kb_end = (nph == 1) ? nk : static_cast<int>((static_cast<long long>(nk) * (phs + 1)) / nph);
+          const int kb_begin = kb;
+          for (; kb < kb_end; ++kb) {
             mbar_wait_cluster(&full_bar[s], ph);
             tc_fence_after();
-            umma_bf16_ss_pair(acc, a_desc, b_desc, idesc, it > it_begin ? 1u : 0u);
-            umma_bf16_ss_pair(acc, a_desc + kAStep, b_desc + kBStep, idesc, 1u);
-            umma_bf16_ss_pair(acc, a_desc + 2 * kAStep, b_desc + 2 * kBStep, idesc, 1u);
-            umma_bf16_ss_pair(acc, a_desc + 3 * kAStep, b_desc + 3 * kBStep, idesc, 1u);
+            for (int t = 0; t < pr.nterms; ++t) {   // the terms of this k block in order, each from its limbs' slots
+              const uint64_t ad = a_desc + kSlot * pr.sa[pr.ta[t]];
+              const uint64_t bd = b_desc + kSlot * pr.sb[pr.tb[t]];
+              umma_bf16_ss_pair(acc, ad, bd, idesc, (kb > kb_begin || t > 0) ? 1u : 0u);
+              umma_bf16_ss_pair(acc, ad + kAStep, bd + kBStep, idesc, 1u);
+              umma_bf16_ss_pair(acc, ad + 2 * kAStep, bd + 2 * kBStep, idesc, 1u);
+              umma_bf16_ss_pair(acc, ad + 3 * kAStep, bd + 3 * kBStep, idesc, 1u);
+            }
             umma_commit_pair(&empty_bar[s]);   // frees the stage in BOTH CTAs once these MMAs have read it
             a_desc += kStageStep;
             b_desc += kStageStep;
@@ -860,6 +876,16 @@ static int build_problem(const xkv_gemm_problem& in, GemmProb& out, int& cta_cur
   } else {
     out.ntiles = out.tiles_m * out.tiles_n;
   }
+  for (int i = 0; i < 3; ++i) {   // distinct limbs in slot order (pair kernel)
+    if (used_a[i]) {
+      out.sa[i] = static_cast<unsigned char>(out.na);
+      out.la[out.na++] = static_cast<unsigned char>(i);
+    }
+    if (used_b[i]) {
+      out.sb[i] = static_cast<unsigned char>(out.nb);
+      out.lb[out.nb++] = static_cast<unsigned char>(i);
+    }
+  }
   out.nkb = (in.K + BK - 1) / BK;
   out.split_k = in.split_k;
   out.kblocks_per_split = (out.nkb + in.split_k - 1) / in.split_k;
@@ -889,6 +915,11 @@ static int launch_pair_variant(GemmParams& params, int grid, cudaStream_t stream
     configured() = true;
   }
   params.pair_stages = (g_gram_pair >= 3 && g_gram_pair <= PG_MAX_STAGES) ? g_gram_pair : PG_STAGES;
+  for (int i = 0; i < params.nprob; ++i) {   // each problem cuts the launch's ring into stages of its own size
+    const int stage = (params.p[i].na + params.p[i].nb) * PG_A_BYTES;
+    const int st = params.pair_stages * PG_STAGE_BYTES / stage;
+    params.p[i].pstages = st > PG_MAX_STAGES ? PG_MAX_STAGES : st;
+  }
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid, 1, 1);
