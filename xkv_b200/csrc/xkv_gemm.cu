@@ -17,6 +17,12 @@
 //               optionally transposed)
 // Problems are passed by value in __grid_constant__ parameter space (tensor maps included), so a
 // launch needs no device-side descriptor memory.
+//
+// Two kernels share this structure: gemm_kernel (one CTA per 128 x 256 tile: the small-M products -- Gram of the basis,
+// Rayleigh-Ritz window, the decode's P A_v) and gemm_pair_kernel (a CTA PAIR per 256 x bn tile, cta_group::2: the Gram,
+// the projection, and the power step / triangular solve / window product with their operand roles swapped by the
+// factorisation driver so that the long dimension is M).  xkv_gemm_grouped picks per launch (pair_bn); both give the
+// same bits.
 #include <cstdlib>
 
 #include "xkv_common.cuh"
