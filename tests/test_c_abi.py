@@ -38,3 +38,27 @@ def test_version_and_error_channel():
     import ctypes as C
 
     assert lib.xkv_factorize_options_size() == C.sizeof(_lib.FactorizeOptions)
+
+
+def test_python_option_defaults_are_the_library_defaults():
+    """FactorizeOptions() on the Python side and xkv_factorize_default_options() must describe the same factorisation: a
+    default changed on one side only (solve_terms, power_terms, shifts ...) would make bench.py and the C-ABI callers of
+    INTEGRATION.md run different algorithms."""
+    import ctypes as C
+
+    import pytest
+
+    from xkv_b200 import factorize
+
+    lib = _lib.load()
+    c_def = _lib.FactorizeOptions()
+    lib.xkv_factorize_default_options(C.byref(c_def))
+    py_def = factorize._c_options(factorize.FactorizeOptions())
+    for name, ctype in _lib.FactorizeOptions._fields_:
+        a, b = getattr(c_def, name), getattr(py_def, name)
+        if hasattr(a, "__len__"):
+            assert list(a) == pytest.approx(list(b)), name
+        elif isinstance(a, float):
+            assert a == pytest.approx(b), name
+        else:
+            assert a == b, name
